@@ -1,0 +1,228 @@
+// Shared device helpers for the sonar_b200 kernels (sm_100a).
+//
+// Everything here is bandwidth-oriented plumbing: vector loads/stores, warp/block reductions,
+// the torch-compatible two-branch lerp, and a random-access Philox4x32-10 front end that reproduces
+// the element -> (thread, call, lane) mapping of ATen's CUDA distribution kernels so that a fused
+// kernel can regenerate "torch.randn(device='cuda')" values in registers instead of reading them
+// from HBM.
+//
+// NOTE: this translation unit family must NOT be compiled with --use_fast_math: curand's Box-Muller
+// uses logf/sqrtf (accurate) and __sincosf (fast) explicitly and the bit pattern depends on it.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <stdint.h>
+
+#define SONAR_LAUNCH_CHECK()                         \
+  do {                                               \
+    cudaError_t err__ = cudaGetLastError();          \
+    if (err__ != cudaSuccess) return (int)err__;     \
+  } while (0)
+
+#define SONAR_CUDA_TRY(expr)                         \
+  do {                                               \
+    cudaError_t err__ = (expr);                      \
+    if (err__ != cudaSuccess) return (int)err__;     \
+  } while (0)
+
+namespace sonar {
+
+constexpr int kBlock = 256;          // ATen's distribution block size; also our default
+constexpr int kSmCountB200 = 148;
+
+// ---------------------------------------------------------------------------------------------
+// device properties (cached per device)
+// ---------------------------------------------------------------------------------------------
+struct DeviceInfo {
+  int sm_count;
+  int max_threads_per_sm;
+  int max_smem_optin;
+};
+
+inline const DeviceInfo& device_info() {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo info{kSmCountB200, 2048, 227 * 1024};
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev) {
+    cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&info.max_threads_per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    cudaDeviceGetAttribute(&info.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cached_dev = dev;
+  }
+  return info;
+}
+
+// Grid for a streaming element-wise kernel: enough CTAs to cover the work, capped at a whole number
+// of waves (SMs x resident CTAs of 256 threads) so the tail wave is never ragged.
+inline int streaming_grid(int64_t work_items, int items_per_block, int waves = 4) {
+  const DeviceInfo& di = device_info();
+  int64_t need = (work_items + items_per_block - 1) / items_per_block;
+  int64_t cap = (int64_t)di.sm_count * (di.max_threads_per_sm / kBlock) * waves;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// blend functions (reference: py/utils.py:17-21 BLENDING_MODES; ATen/native/Lerp.h:21-35)
+// ---------------------------------------------------------------------------------------------
+enum BlendMode : int { BLEND_LERP = 0, BLEND_INJECT = 1, BLEND_SUBTRACT_B = 2 };
+
+__device__ __forceinline__ float torch_lerp(float a, float b, float w) {
+  return fabsf(w) < 0.5f ? a + w * (b - a) : b - (b - a) * (1.0f - w);
+}
+
+__device__ __forceinline__ double torch_lerp(double a, double b, double w) {
+  return fabs(w) < 0.5 ? a + w * (b - a) : b - (b - a) * (1.0 - w);
+}
+
+template <typename T>
+__device__ __forceinline__ T blend(int mode, T a, T b, T t) {
+  switch (mode) {
+    case BLEND_INJECT: return b * t + a;      // (b * t).add_(a)
+    case BLEND_SUBTRACT_B: return a - b * t;  // a - b * t
+    default: return torch_lerp(a, b, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of two doubles; result valid in thread 0. `scratch` needs 2*32 doubles.
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    scratch[warp] = a;
+    scratch[32 + warp] = b;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    a = lane < nw ? scratch[lane] : 0.0;
+    b = lane < nw ? scratch[32 + lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox, ATen-compatible random access
+//
+// ATen (ATen/native/cuda/DistributionTemplates.h:50-82): thread `t` of a grid of T = grid*256
+// threads runs curand_init(seed, /*subsequence=*/t, /*offset=*/off) and its k-th curand_*4 call
+// yields the values of elements  li = t + T*(4k + lane), lane = 0..3.
+// curand_init + k calls  ==  Philox4x32-10(counter = {off/4 + k (64 bit), t (64 bit)}, key = seed).
+// ---------------------------------------------------------------------------------------------
+struct PhiloxStream {
+  uint64_t seed;
+  uint64_t offset;     // torch generator offset at the draw (multiple of 4)
+  uint32_t threads;    // T = grid_blocks * 256 of the emulated ATen launch
+};
+
+__device__ __forceinline__ uint4 philox_raw(const PhiloxStream& s, uint32_t thread, uint64_t call) {
+  const uint64_t c = (s.offset >> 2) + call;
+  uint4 ctr = make_uint4((uint32_t)c, (uint32_t)(c >> 32), thread, 0u);
+  uint2 key = make_uint2((uint32_t)s.seed, (uint32_t)(s.seed >> 32));
+  return curand_Philox4x32_10(ctr, key);
+}
+
+// curand_normal4 on the k-th block of thread `thread` (curand_normal.h: curand_box_muller4)
+__device__ __forceinline__ float4 philox_normal4(const PhiloxStream& s, uint32_t thread, uint64_t call) {
+  const uint4 r = philox_raw(s, thread, call);
+  const float2 a = _curand_box_muller(r.x, r.y);
+  const float2 b = _curand_box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// curand_uniform4 (values in (0, 1])
+__device__ __forceinline__ float4 philox_uniform4(const PhiloxStream& s, uint32_t thread, uint64_t call) {
+  return _curand_uniform4(philox_raw(s, thread, call));
+}
+
+// at::uniform_kernel's transform: rand * range + from, with the (0,1] -> [0,1) bound reversal
+// (ATen/native/cuda/DistributionTemplates.h:487-501)
+__device__ __forceinline__ float uniform_transform(float r, float from, float to) {
+  const float range = to - from;
+  const float v = r * range + from;
+  return v == to ? from : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale_noise decision (reference py/utils.py:100-106), evaluated on the device from the two
+// global sums so that no .item() host sync is needed. mean/std are rounded to float first because
+// the reference compares the float32 results of noise.mean()/noise.std() in Python doubles.
+// ---------------------------------------------------------------------------------------------
+struct NormDecision {
+  float mean;
+  float std;
+  int sub_mean;
+  int div_std;
+};
+
+__device__ __forceinline__ NormDecision decide_normalisation(const double* __restrict__ sums, int64_t count,
+                                                             float threshold_std_devs) {
+  NormDecision d{0.0f, 1.0f, 0, 0};
+  if (sums == nullptr || count <= 0) return d;
+  const double n = (double)count;
+  const double s = sums[0], ss = sums[1];
+  const double mean = s / n;
+  double var = (ss - s * s / n) / (n - 1.0);  // unbiased; n == 1 -> NaN like torch.std
+  if (var < 0.0) var = 0.0;
+  d.mean = (float)mean;
+  d.std = (float)sqrt(var);
+  const double thr = (double)threshold_std_devs / sqrt(n);
+  d.sub_mean = fabs((double)d.mean) > thr ? 1 : 0;
+  d.div_std = fabs(1.0 - (double)d.std) > thr ? 1 : 0;
+  return d;
+}
+
+__device__ __forceinline__ float apply_norm(float v, const NormDecision& d) {
+  if (d.sub_mean) v -= d.mean;
+  if (d.div_std) v /= d.std;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector access helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void st4_stream(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace sonar

@@ -1,0 +1,409 @@
+// Streaming noise-synthesis kernels: fused multi-level resample-and-accumulate (pyramid family),
+// Perlin 2x2 gradient stencil, blends / composites, power-law shaping and per-item range reductions.
+//
+// Reference (py/noise_generation.py): PyramidNoiseGenerator.generate :621-649,
+// HighresPyramidNoiseGenerator.generate :539-564, PyramidOldNoiseGenerator.generate :579-606,
+// PerlinOldNoiseGenerator :289-493, PowerLawNoiseGenerator.generate :775-786;
+// (py/noise.py) CompositeNoise :524-531, BlendedNoise :1391-1405; (py/utils.py) normalize_to_scale
+// :452-470. Resampling follows ATen's area_pixel_compute_source_index (ATen/native/UpSample.h:289-312).
+#include "common.cuh"
+#include "../../include/sonar_b200.h"
+
+namespace sonar {
+
+// ---------------------------------------------------------------------------------------------
+// resampling taps (align_corners = False), identical index math to ATen
+// ---------------------------------------------------------------------------------------------
+struct LinTap {
+  int i0, i1;
+  float w0, w1;
+};
+
+__device__ __forceinline__ LinTap linear_tap(int dst, int in_size, float scale) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.0f) src = 0.0f;
+  int i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  float l1 = src - (float)i0;
+  l1 = fminf(fmaxf(l1, 0.0f), 1.0f);
+  LinTap t;
+  t.i0 = i0;
+  t.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  t.w1 = l1;
+  t.w0 = 1.0f - l1;
+  return t;
+}
+
+__device__ __forceinline__ int nearest_exact_idx(int dst, int in_size, float scale) {
+  const int i = (int)floorf(((float)dst + 0.5f) * scale);
+  return i < in_size - 1 ? i : in_size - 1;
+}
+
+__device__ __forceinline__ int pool_start(int dst, int out_size, int in_size) {
+  return (dst / out_size) * in_size + ((dst % out_size) * in_size) / out_size;
+}
+__device__ __forceinline__ int pool_end(int dst, int out_size, int in_size) {
+  return 1 + ((dst + 1) * in_size - 1) / out_size;
+}
+
+__device__ __forceinline__ float sample_level(const float* __restrict__ src, int lh, int lw, int H, int W, int y, int x,
+                                              int mode) {
+  if (lh == H && lw == W) return src[(int64_t)y * lw + x];  // identity for every mode
+  if (mode == SONAR_RESAMPLE_BILINEAR) {
+    const LinTap ty = linear_tap(y, lh, (float)lh / (float)H);
+    const LinTap tx = linear_tap(x, lw, (float)lw / (float)W);
+    const float* r0 = src + (int64_t)ty.i0 * lw;
+    const float* r1 = src + (int64_t)ty.i1 * lw;
+    return ty.w0 * (tx.w0 * r0[tx.i0] + tx.w1 * r0[tx.i1]) + ty.w1 * (tx.w0 * r1[tx.i0] + tx.w1 * r1[tx.i1]);
+  }
+  if (mode == SONAR_RESAMPLE_NEAREST_EXACT) {
+    const int sy = nearest_exact_idx(y, lh, (float)lh / (float)H);
+    const int sx = nearest_exact_idx(x, lw, (float)lw / (float)W);
+    return src[(int64_t)sy * lw + sx];
+  }
+  // area == adaptive average pooling
+  const int y0 = pool_start(y, H, lh), y1 = pool_end(y, H, lh);
+  const int x0 = pool_start(x, W, lw), x1 = pool_end(x, W, lw);
+  float acc = 0.0f;
+  for (int yy = y0; yy < y1; ++yy)
+    for (int xx = x0; xx < x1; ++xx) acc += src[(int64_t)yy * lw + xx];
+  return acc / (float)(y1 - y0) / (float)(x1 - x0);
+}
+
+// out[p, y, x] = base_scale * base[p, y, x] + sum_i weight_i * resample(level_i[p])[y, x]
+// One thread produces 4 consecutive x (float4 store) when W % 4 == 0, else one pixel.
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+pyramid_accum_kernel(SonarPyramidParams p) {
+  const int Wv = p.W / VEC;
+  const int64_t total = p.planes * (int64_t)p.H * Wv;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int xv = (int)(idx % Wv);
+    const int y = (int)((idx / Wv) % p.H);
+    const int64_t plane = idx / ((int64_t)Wv * p.H);
+    const int64_t o = (plane * p.H + y) * (int64_t)p.W + (int64_t)xv * VEC;
+    float acc[VEC];
+    if (p.base != nullptr) {
+      if (VEC == 4) {
+        const float4 b = ld4_stream(p.base + o);
+        acc[0] = b.x;
+        acc[1 % VEC] = b.y;
+        acc[2 % VEC] = b.z;
+        acc[3 % VEC] = b.w;
+      } else {
+        acc[0] = p.base[o];
+      }
+      if (p.base_scale != 1.0f) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] *= p.base_scale;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.0f;
+    }
+    for (int l = 0; l < p.n_levels; ++l) {
+      const int lh = p.level_h[l], lw = p.level_w[l];
+      const float* src = p.levels[l] + plane * (int64_t)lh * lw;
+      const float wgt = p.weights[l];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float s = sample_level(src, lh, lw, p.H, p.W, y, xv * VEC + v, p.mode);
+        // reference: noise += upsampled.mul_(discount ** i)  -> separate mul then add
+        acc[v] = acc[v] + __fmul_rn(s, wgt);
+      }
+    }
+    if (VEC == 4) {
+      st4_stream(p.out + o, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
+    } else {
+      p.out[o] = acc[0];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Perlin: grid cell == 1 pixel, so every output is the blend of four corner gradients dotted with
+// (+-0.5, +-0.5) (closed form verified against perlin_noise).
+// The (C,H,W) stencil result is shared by the whole batch: compute once, add to every item.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float perlin_value(const float* __restrict__ ang, int H, int W, int y, int x, int mode) {
+  const int64_t gw = W + 1;
+  const float* a0 = ang + (int64_t)y * gw + x;
+  const float* a1 = a0 + gw;
+  float s00, c00, s01, c01, s10, c10, s11, c11;
+  sincosf(a0[0], &s00, &c00);
+  sincosf(a0[1], &s01, &c01);
+  sincosf(a1[0], &s10, &c10);
+  sincosf(a1[1], &s11, &c11);
+  // positions = (0.5, 0.5); offsets (1,0), (0,1), (1,1) subtracted for the other corners
+  const float d00 = __fadd_rn(__fmul_rn(c00, 0.5f), __fmul_rn(s00, 0.5f));
+  const float d01 = __fadd_rn(__fmul_rn(c01, -0.5f), __fmul_rn(s01, 0.5f));
+  const float d10 = __fadd_rn(__fmul_rn(c10, 0.5f), __fmul_rn(s10, -0.5f));
+  const float d11 = __fadd_rn(__fmul_rn(c11, -0.5f), __fmul_rn(s11, -0.5f));
+  const float row0 = blend<float>(mode, d00, d01, 0.5f);
+  const float row1 = blend<float>(mode, d10, d11, 0.5f);
+  return blend<float>(mode, row0, row1, 0.5f);
+}
+
+__global__ void __launch_bounds__(kBlock)
+perlin_accum_kernel(SonarPerlinParams p) {
+  const int64_t chw = (int64_t)p.C * p.H * p.W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chw;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    const int c = (int)(idx / ((int64_t)p.W * p.H));
+    float pv[SONAR_PERLIN_MAX_ITERS];
+    for (int it = 0; it < p.iterations; ++it)
+      pv[it] = perlin_value(p.angles[it] + (int64_t)c * (p.H + 1) * (p.W + 1), p.H, p.W, y, x, p.blend_mode);
+    for (int b = 0; b < p.B; ++b) {
+      const int64_t o = (int64_t)b * chw + idx;
+      float v = p.base != nullptr ? p.base[o] / p.div_fac : 0.0f;
+      for (int it = 0; it < p.iterations; ++it) v += pv[it];
+      p.out[o] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise: blend, axpby, composite, power law
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ t_tensor, float t_scalar,
+             float* __restrict__ out, int64_t n, int mode) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float t = t_tensor != nullptr ? t_tensor[i] : t_scalar;
+    out[i] = blend<float>(mode, a[i], b[i], t);
+  }
+}
+
+// out = a * alpha + b * beta (b may be NULL)
+__global__ void __launch_bounds__(kBlock)
+axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta, float* __restrict__ out,
+             int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = alpha == 1.0f ? a[i] : a[i] * alpha;
+    if (b != nullptr) v = v + __fmul_rn(b[i], beta);
+    out[i] = v;
+  }
+}
+
+// out = ((x + pre) * mul) + post with three separately rounded steps (sub_/mul_/add_ chains such as
+// UniformNoiseGenerator.generate, py/noise_generation.py:508-514, stay bit-exact)
+__global__ void __launch_bounds__(kBlock)
+affine_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, float pre, float mul, float post) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(__fadd_rn(x[i], pre), mul), post);
+}
+
+// out = dst * (1 - mask) + src * mask, mask is (B, 1, H, W) broadcast over channels
+__global__ void __launch_bounds__(kBlock)
+composite_kernel(const float* __restrict__ dst, const float* __restrict__ src, const float* __restrict__ mask,
+                 float* __restrict__ out, int64_t n, int64_t chw, int64_t hw) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / chw;
+    const float m = mask[b * hw + (i % hw)];
+    const float im = 1.0f - m;
+    out[i] = __fadd_rn(__fmul_rn(dst[i], im), __fmul_rn(src[i], m));
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+powerlaw_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, float alpha, int use_sign) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float mod = powf(fabsf(v), alpha);
+    const float lead = use_sign ? (float)((v > 0.0f) - (v < 0.0f)) : v;
+    out[i] = lead * mod;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-item (leading dim) range reductions, two stage, no atomics
+// ---------------------------------------------------------------------------------------------
+constexpr int kRangeChunks = 64;
+
+// partial[item][chunk] = {min, max} over that chunk (optionally of |x|)
+__global__ void __launch_bounds__(kBlock)
+item_range_kernel(const float* __restrict__ x, int64_t per_item, int use_abs, float2* __restrict__ partial) {
+  __shared__ float smin[32], smax[32];
+  const int item = blockIdx.y, chunk = blockIdx.x;
+  const int64_t chunk_len = (per_item + kRangeChunks - 1) / kRangeChunks;
+  const int64_t lo = (int64_t)chunk * chunk_len;
+  const int64_t hi = lo + chunk_len < per_item ? lo + chunk_len : per_item;
+  const float* base = x + (int64_t)item * per_item;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float v = base[i];
+    if (use_abs) v = fabsf(v);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    smin[warp] = mn;
+    smax[warp] = mx;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    mn = lane < nw ? smin[lane] : INFINITY;
+    mx = lane < nw ? smax[lane] : -INFINITY;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) partial[item * kRangeChunks + chunk] = make_float2(mn, mx);
+  }
+}
+
+__device__ __forceinline__ float2 item_range(const float2* __restrict__ partial, int item) {
+  float mn = INFINITY, mx = -INFINITY;
+  for (int c = 0; c < kRangeChunks; ++c) {
+    const float2 v = partial[item * kRangeChunks + c];
+    mn = fminf(mn, v.x);
+    mx = fmaxf(mx, v.y);
+  }
+  return make_float2(mn, mx);
+}
+
+// op 0: out = x / max ; op 1: normalize_to_scale
+__global__ void __launch_bounds__(kBlock)
+item_range_apply_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t per_item,
+                        const float2* __restrict__ partial, int op, float tmin, float tmax, float eps) {
+  __shared__ float2 rng;
+  const int item = blockIdx.y;
+  if (threadIdx.x == 0) rng = item_range(partial, item);
+  __syncthreads();
+  const float mn = rng.x, mx = rng.y;
+  const float* src = x + (int64_t)item * per_item;
+  float* dst = out + (int64_t)item * per_item;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_item; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    if (op == 0) {
+      dst[i] = v / mx;
+    } else {
+      float r = (v - mn) / ((mx - mn) + eps);
+      r = __fadd_rn(__fmul_rn(r, tmax - tmin), tmin);
+      dst[i] = fminf(fmaxf(r, tmin), tmax);
+    }
+  }
+}
+
+}  // namespace sonar
+
+extern "C" {
+
+int sonar_pyramid_accum_f32(const SonarPyramidParams* params, void* stream) {
+  using namespace sonar;
+  if (params == nullptr) return (int)cudaErrorInvalidValue;
+  SonarPyramidParams p = *params;
+  if (p.planes <= 0 || p.H <= 0 || p.W <= 0) return 0;
+  if (p.n_levels < 0 || p.n_levels > SONAR_PYRAMID_MAX_LEVELS || p.out == nullptr) return (int)cudaErrorInvalidValue;
+  for (int l = 0; l < p.n_levels; ++l)
+    if (p.levels[l] == nullptr || p.level_h[l] <= 0 || p.level_w[l] <= 0) return (int)cudaErrorInvalidValue;
+  const bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
+  const int64_t total = p.planes * (int64_t)p.H * (vec ? p.W / 4 : p.W);
+  const int grid = streaming_grid(total, kBlock, 4);
+  if (vec)
+    pyramid_accum_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(p);
+  else
+    pyramid_accum_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(p);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
+  using namespace sonar;
+  if (params == nullptr) return (int)cudaErrorInvalidValue;
+  SonarPerlinParams p = *params;
+  if (p.B <= 0 || p.C <= 0 || p.H <= 0 || p.W <= 0) return 0;
+  if (p.iterations < 0 || p.iterations > SONAR_PERLIN_MAX_ITERS || p.out == nullptr) return (int)cudaErrorInvalidValue;
+  for (int i = 0; i < p.iterations; ++i)
+    if (p.angles[i] == nullptr) return (int)cudaErrorInvalidValue;
+  const int grid = streaming_grid((int64_t)p.C * p.H * p.W, kBlock, 4);
+  perlin_accum_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(p);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_blend_f32(const float* a, const float* b, const float* t_tensor, float t_scalar, float* out, int64_t n,
+                    int mode, void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::blend_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::axpby_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_affine_f32(const float* x, float* out, int64_t n, float pre_add, float mul, float post_add, void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::affine_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, pre_add, mul, post_add);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_composite_f32(const float* dst, const float* src, const float* mask, float* out, int64_t batch,
+                        int64_t channels, int64_t hw, void* stream) {
+  const int64_t n = batch * channels * hw;
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::composite_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(dst, src, mask, out, n, channels * hw, hw);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_powerlaw_f32(const float* x, float* out, int64_t n, float alpha, int use_sign, void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::powerlaw_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, alpha, use_sign);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_item_range_scratch_bytes(int64_t items) { return (int)(items * sonar::kRangeChunks * sizeof(float2)); }
+
+int sonar_item_div_max_f32(const float* x, float* out, int64_t items, int64_t per_item, int use_abs, void* scratch,
+                           void* stream) {
+  using namespace sonar;
+  if (items <= 0 || per_item <= 0) return 0;
+  if (items > 65535) return (int)cudaErrorInvalidValue;
+  float2* partial = (float2*)scratch;
+  item_range_kernel<<<dim3(kRangeChunks, (unsigned)items), kBlock, 0, (cudaStream_t)stream>>>(x, per_item, use_abs, partial);
+  SONAR_LAUNCH_CHECK();
+  int gx = (int)((per_item + kBlock * 4 - 1) / (kBlock * 4));
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  item_range_apply_kernel<<<dim3(gx, (unsigned)items), kBlock, 0, (cudaStream_t)stream>>>(x, out, per_item, partial, 0,
+                                                                                          0.f, 0.f, 0.f);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_item_minmax_rescale_f32(const float* x, float* out, int64_t items, int64_t per_item, float target_min,
+                                  float target_max, float eps, void* scratch, void* stream) {
+  using namespace sonar;
+  if (items <= 0 || per_item <= 0) return 0;
+  if (items > 65535) return (int)cudaErrorInvalidValue;
+  float2* partial = (float2*)scratch;
+  item_range_kernel<<<dim3(kRangeChunks, (unsigned)items), kBlock, 0, (cudaStream_t)stream>>>(x, per_item, 0, partial);
+  SONAR_LAUNCH_CHECK();
+  int gx = (int)((per_item + kBlock * 4 - 1) / (kBlock * 4));
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  item_range_apply_kernel<<<dim3(gx, (unsigned)items), kBlock, 0, (cudaStream_t)stream>>>(
+      x, out, per_item, partial, 1, target_min, target_max, eps);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

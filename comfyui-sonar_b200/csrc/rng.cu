@@ -1,0 +1,103 @@
+// Device Philox generators that reproduce torch.randn / torch.rand / Tensor.uniform_ on CUDA
+// bit-for-bit (same seed, same generator offset), plus slice generation for batch sharding.
+//
+// Replaces, on the hot path: NoiseGenerator.rand_like (reference py/noise_generation.py:133-155)
+// and the direct torch.randn calls in PyramidNoiseGenerator.generate (:632-640),
+// PerlinOldNoiseGenerator.perlin_noise (:465-469) and PowerNoiseItem (py/nodes/powernoise.py:396-401).
+#include "common.cuh"
+#include "../../include/sonar_b200.h"
+
+namespace sonar {
+
+enum DistKind : int { DIST_NORMAL = 0, DIST_UNIFORM = 1 };
+
+// One "pair" = one Philox block of one emulated ATen thread = 4 output elements
+//   li = t + T*(4k + lane).
+// The launch covers pairs p in [0, T*k_count): t = p % T, k = k_lo + p / T. With k_lo = 0 and
+// k_count = ceil(numel / 4T) this is exactly ATen's grid-stride loop. A slice [begin, end) of
+// the virtual tensor only keeps the lanes that fall inside it and writes them at (li - begin).
+template <int KIND>
+__global__ void __launch_bounds__(kBlock)
+philox_fill_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream s, uint32_t k_lo,
+                   int64_t n_pairs, float p0, float p1) {
+  const int64_t T = s.threads;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = (uint32_t)(p % T);
+    const uint64_t k = k_lo + (uint64_t)(p / T);
+    float4 v;
+    if (KIND == DIST_NORMAL) {
+      v = philox_normal4(s, t, k);
+      v.x = v.x * p1 + p0;  // at::transformation::normal: val * std + mean
+      v.y = v.y * p1 + p0;
+      v.z = v.z * p1 + p0;
+      v.w = v.w * p1 + p0;
+    } else {
+      v = philox_uniform4(s, t, k);
+      v.x = uniform_transform(v.x, p0, p1);
+      v.y = uniform_transform(v.y, p0, p1);
+      v.z = uniform_transform(v.z, p0, p1);
+      v.w = uniform_transform(v.w, p0, p1);
+    }
+    const int64_t li0 = (int64_t)t + T * (int64_t)(4 * k);
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int lane = 0; lane < 4; ++lane) {
+      const int64_t li = li0 + T * lane;
+      if (li >= begin && li < end) out[li - begin] = vals[lane];
+    }
+  }
+}
+
+template <int KIND>
+int launch_fill(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                uint64_t offset, uint32_t grid_blocks, float p0, float p1, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  if (grid_blocks == 0 || begin < 0 || begin + count > numel_total) return (int)cudaErrorInvalidValue;
+  PhiloxStream s{seed, offset, grid_blocks * (uint32_t)kBlock};
+  const int64_t T = s.threads;
+  const int64_t end = begin + count;
+  // rows r = li / T touched by the slice -> Philox calls k = r / 4
+  const int64_t k_lo = (begin / T) / 4;
+  const int64_t k_hi = ((end - 1) / T) / 4;
+  const int64_t n_pairs = T * (k_hi - k_lo + 1);
+  const int grid = streaming_grid(n_pairs, kBlock, 1);
+  philox_fill_kernel<KIND><<<grid, kBlock, 0, stream>>>(out, begin, end, s, (uint32_t)k_lo, n_pairs, p0, p1);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sonar
+
+extern "C" {
+
+int sonar_philox_policy(int64_t numel, uint32_t* grid_blocks, uint64_t* counter_offset) {
+  // ATen/native/cuda/DistributionTemplates.h:50-62 (calc_execution_policy), unroll = 4
+  if (numel <= 0) {
+    if (grid_blocks) *grid_blocks = 0;
+    if (counter_offset) *counter_offset = 0;
+    return 0;
+  }
+  const sonar::DeviceInfo& di = sonar::device_info();
+  uint64_t n = (uint64_t)numel;
+  uint64_t grid = (n + sonar::kBlock - 1) / sonar::kBlock;
+  uint64_t cap = (uint64_t)di.sm_count * (uint64_t)(di.max_threads_per_sm / sonar::kBlock);
+  if (grid > cap) grid = cap;
+  if (grid_blocks) *grid_blocks = (uint32_t)grid;
+  if (counter_offset) *counter_offset = ((n - 1) / ((uint64_t)sonar::kBlock * grid * 4) + 1) * 4;
+  return 0;
+}
+
+int sonar_philox_normal_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                            uint64_t offset, uint32_t grid_blocks, float mean, float std, void* stream) {
+  return sonar::launch_fill<sonar::DIST_NORMAL>(out, begin, count, numel_total, seed, offset, grid_blocks, mean,
+                                                std, (cudaStream_t)stream);
+}
+
+int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                             uint64_t offset, uint32_t grid_blocks, float from, float to, void* stream) {
+  return sonar::launch_fill<sonar::DIST_UNIFORM>(out, begin, count, numel_total, seed, offset, grid_blocks, from,
+                                                 to, (cudaStream_t)stream);
+}
+
+}  // extern "C"

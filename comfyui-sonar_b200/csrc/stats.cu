@@ -1,0 +1,195 @@
+// Global moments + the conditional normalisation of `scale_noise`.
+//
+// Reference: py/utils.py:85-106. The reference reduces mean/std over the WHOLE tensor (batch
+// included), syncs them to the host with .item(), then conditionally centres / rescales:
+//     if |mean| > thr: noise -= mean;  if |1 - std| > thr: noise /= std;  noise *= factor
+// with thr = 2.5 / sqrt(numel) and the unbiased std. Here the two sums live in a device buffer
+// (so a batch-sharded run can all-reduce them) and the conditional is evaluated on the device by
+// the apply kernel itself: no host round trip.
+#include "common.cuh"
+#include "../../include/sonar_b200.h"
+
+namespace sonar {
+
+// ---------------------------------------------------------------------------------------------
+// moments: sums[0] += sum(x), sums[1] += sum(x^2), double accumulation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+moments_kernel(const float* __restrict__ x, int64_t n, int vec_ok, double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  double s = 0.0, ss = 0.0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 v = ld4_stream(x + 4 * i);
+      // pairwise in float for the 4-vector keeps the fp64 pipe at 1/4 rate of the loads
+      const double a = (double)v.x + (double)v.y, b = (double)v.z + (double)v.w;
+      s += a + b;
+      ss += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
+      const double v = x[i];
+      s += v;
+      ss += v * v;
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += stride) {
+      const double v = x[i];
+      s += v;
+      ss += v * v;
+    }
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s);
+    atomicAdd(&sums[1], ss);
+  }
+}
+
+// Moments of a Philox normal draw restricted to the slice [begin, end) without materialising it.
+__global__ void __launch_bounds__(kBlock)
+philox_normal_moments_kernel(int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo, int64_t n_pairs,
+                             double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  double s = 0.0, ss = 0.0;
+  const int64_t T = st.threads;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = (uint32_t)(p % T);
+    const uint64_t k = k_lo + (uint64_t)(p / T);
+    const float4 v = philox_normal4(st, t, k);
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+    const int64_t li0 = (int64_t)t + T * (int64_t)(4 * k);
+#pragma unroll
+    for (int lane = 0; lane < 4; ++lane) {
+      const int64_t li = li0 + T * lane;
+      if (li >= begin && li < end) {
+        const double d = vals[lane];
+        s += d;
+        ss += d * d;
+      }
+    }
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s);
+    atomicAdd(&sums[1], ss);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale_noise apply
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+scale_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, int vec_ok,
+                   const double* __restrict__ sums, int64_t count, float factor, float threshold_std_devs) {
+  const NormDecision nd = decide_normalisation(sums, count, threshold_std_devs);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 v = ld4(x + 4 * i);  // plain load: `out` may alias `x`
+      v.x = apply_norm(v.x, nd) * factor;
+      v.y = apply_norm(v.y, nd) * factor;
+      v.z = apply_norm(v.z, nd) * factor;
+      v.w = apply_norm(v.w, nd) * factor;
+      st4(out + 4 * i, v);
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) out[i] = apply_norm(x[i], nd) * factor;
+  } else {
+    for (int64_t i = tid; i < n; i += stride) out[i] = apply_norm(x[i], nd) * factor;
+  }
+}
+
+// out = x * (scale / std(x)) with the unbiased std taken from device sums
+// (GreenTestNoiseGenerator: noise *= scale / noise.std(), py/noise_generation.py:703)
+__global__ void __launch_bounds__(kBlock)
+scale_by_std_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, const double* __restrict__ sums,
+                    int64_t count, float scale) {
+  const double cnt = (double)count;
+  double var = (sums[1] - sums[0] * sums[0] / cnt) / (cnt - 1.0);
+  if (var < 0.0) var = 0.0;
+  const float mult = scale / (float)sqrt(var);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] * mult;
+}
+
+// out = (a [+ b]) and moments of the result in the same pass (chain accumulation, noise.py:189-194)
+__global__ void __launch_bounds__(kBlock)
+add_moments_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n,
+                   double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  double s = 0.0, ss = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = a[i] + b[i];
+    out[i] = v;
+    s += (double)v;
+    ss += (double)v * (double)v;
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s);
+    atomicAdd(&sums[1], ss);
+  }
+}
+
+}  // namespace sonar
+
+extern "C" {
+
+int sonar_moments_f32(const float* x, int64_t n, double* sums, void* stream) {
+  if (n <= 0) return 0;
+  const int vec_ok = sonar::aligned16(x) ? 1 : 0;
+  const int grid = sonar::streaming_grid((n + 3) / 4, sonar::kBlock, 2);
+  sonar::moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, n, vec_ok, sums);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_total, uint64_t seed, uint64_t offset,
+                                uint32_t grid_blocks, double* sums, void* stream) {
+  if (count <= 0) return 0;
+  if (grid_blocks == 0 || begin < 0 || begin + count > numel_total) return (int)cudaErrorInvalidValue;
+  sonar::PhiloxStream s{seed, offset, grid_blocks * (uint32_t)sonar::kBlock};
+  const int64_t T = s.threads, end = begin + count;
+  const int64_t k_lo = (begin / T) / 4, k_hi = ((end - 1) / T) / 4;
+  const int64_t n_pairs = T * (k_hi - k_lo + 1);
+  const int grid = sonar::streaming_grid(n_pairs, sonar::kBlock, 1);
+  sonar::philox_normal_moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(begin, end, s, (uint32_t)k_lo,
+                                                                                       n_pairs, sums);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_scale_noise_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float factor,
+                          float threshold_std_devs, void* stream) {
+  if (n <= 0) return 0;
+  const int vec_ok = (sonar::aligned16(x) && sonar::aligned16(out)) ? 1 : 0;
+  const int grid = sonar::streaming_grid((n + 3) / 4, sonar::kBlock, 2);
+  sonar::scale_noise_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, vec_ok, sums, count, factor,
+                                                                             threshold_std_devs);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_scale_by_std_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float scale,
+                           void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::scale_by_std_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, sums, count, scale);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_add_moments_f32(const float* a, const float* b, float* out, int64_t n, double* sums, void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 2);
+  sonar::add_moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(a, b, out, n, sums);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,571 @@
+"""Noise generators: the host-side mirror of the reference's in-scope generator classes
+(py/noise_generation.py), with every tensor pass replaced by a CUDA kernel launch (`ops`).
+
+Same class names, `ng_params`, call protocol (`gen(sigma, sigma_next) -> Tensor`) and error behaviour
+as the reference so the noise graph above it is unchanged. Differences that are inherent to a
+device-only path:
+
+* every base draw comes from the torch CUDA Philox stream on `x.device` (`rng.normal/uniform`); the
+  `cpu` parameter is accepted for signature compatibility and ignored (there is no CPU path), and a
+  CPU `generator` only feeds the *host* draws the reference also makes on the CPU (pyramid level
+  sizes, py/noise_generation.py:627-630);
+* out-of-scope generator types raise NotImplementedError naming the type.
+"""
+
+from __future__ import annotations
+
+import math
+from enum import Enum, auto
+from typing import Callable
+
+import torch
+
+from . import hostutil, ops, parallel, rng
+from .hostutil import fallback, scale_noise
+
+
+class NoiseType(Enum):
+    # Same members and order as the reference enum (py/noise_generation.py:31-69): the names are
+    # the node dropdown values.
+    BROWNIAN = auto()
+    COLLATZ = auto()
+    DISTRO = auto()
+    GAUSSIAN = auto()
+    GREEN_TEST = auto()
+    GREY = auto()
+    HIGHRES_PYRAMID = auto()
+    HIGHRES_PYRAMID_AREA = auto()
+    HIGHRES_PYRAMID_BISLERP = auto()
+    LAPLACIAN = auto()
+    ONEF_GREENISH = auto()
+    ONEF_GREENISH_MIX = auto()
+    ONEF_PINKISH = auto()
+    ONEF_PINKISH_MIX = auto()
+    ONEF_PINKISHGREENISH = auto()
+    PERLIN = auto()
+    PINK_OLD = auto()
+    POWER_OLD = auto()
+    PYRAMID = auto()
+    PYRAMID_AREA = auto()
+    PYRAMID_BISLERP = auto()
+    PYRAMID_DISCOUNT5 = auto()
+    PYRAMID_MIX = auto()
+    PYRAMID_MIX_AREA = auto()
+    PYRAMID_MIX_BISLERP = auto()
+    PYRAMID_OLD = auto()
+    PYRAMID_OLD_AREA = auto()
+    PYRAMID_OLD_BISLERP = auto()
+    RAINBOW_INTENSE = auto()
+    RAINBOW_MILD = auto()
+    STUDENTT = auto()
+    UNIFORM = auto()
+    VELVET = auto()
+    VIOLET = auto()
+    VORONOI_FUZZ = auto()
+    VORONOI_MIX = auto()
+    WAVELET = auto()
+    WHITE = auto()
+
+    @classmethod
+    def get_names(cls, default=GAUSSIAN, skip=None):
+        if default is not None:
+            if isinstance(default, int):
+                default = cls(default)
+            yield default.name.lower()
+        for nt in cls:
+            if nt == default or (skip and nt in skip):
+                continue
+            yield nt.name.lower()
+
+
+class NoiseError(Exception):
+    pass
+
+
+class NoiseGenerator:
+    """Base class (reference py/noise_generation.py:87-179)."""
+
+    name = "unknown"
+    MIN_DIMS = 1
+    MAX_DIMS = 0
+
+    def __init__(self, x: torch.Tensor, **kwargs):
+        if x.ndim < self.MIN_DIMS:
+            raise ValueError(
+                f"Noise generator {self.name} requires at least {self.MIN_DIMS} dimension(s) but got input with shape {x.shape}",
+            )
+        if self.MAX_DIMS > 0 and x.ndim > self.MAX_DIMS:
+            raise ValueError(
+                f"Noise generator {self.name} requires at most {self.MAX_DIMS} dimension(s) but got input with shape {x.shape}",
+            )
+        defaults = self.ng_params()
+        merged = defaults | kwargs
+        for key in defaults:
+            setattr(self, key, merged.pop(key))
+        self.options = merged
+        self.update_x(x)
+
+    @classmethod
+    def ng_params(cls) -> dict:
+        return {
+            "normalized": True,
+            "force_normalize": None,
+            "normalize_dims": None,
+            "cpu": True,
+            "generator": None,
+        }
+
+    def update_x(self, x: torch.Tensor) -> None:
+        if not x.is_cuda:
+            raise RuntimeError(
+                f"sonar_b200 noise generator {self.name}: latent must live on a CUDA device (got {x.device}); "
+                "there is no CPU generation path",
+            )
+        self.shape = x.shape
+        if x.ndim in {4, 5}:
+            self.batch, self.channels = x.shape[:2]
+            self.height, self.width = x.shape[-2:]
+            self.frames = x.shape[-3] if x.ndim == 5 else None
+        else:
+            self.batch = self.channels = self.frames = self.height = self.width = None
+        self.device = x.device
+        self.gen_device = x.device
+        self.layout = x.layout
+        self.dtype = x.dtype
+
+    def device_generator(self):
+        """A torch.Generator is only usable for device draws if it is a CUDA generator."""
+        gen = self.generator
+        return gen if gen is not None and gen.device.type == "cuda" else None
+
+    def rand_like(self, *, fun="normal", shape=None, dtype=None, **_ignored) -> torch.Tensor:
+        """Base draw of `shape` (default: the latent shape) on the latent's device.
+
+        `fun` is "normal" / "uniform"; torch.randn / torch.rand are accepted for source
+        compatibility with callers written against the reference signature (:133-155)."""
+        if fun is torch.randn:
+            fun = "normal"
+        elif fun is torch.rand:
+            fun = "uniform"
+        draw = rng.normal if fun == "normal" else rng.uniform
+        return draw(
+            tuple(fallback(shape, self.shape)),
+            device=self.device,
+            dtype=fallback(dtype, self.dtype),
+            generator=self.device_generator(),
+        )
+
+    def output_hook(self, noise: torch.Tensor) -> torch.Tensor:
+        return scale_noise(
+            noise,
+            normalized=self.normalized and (self.force_normalize is None or self.force_normalize is True),
+            normalize_dims=self.normalize_dims,
+        )
+
+    def pre_hook(self) -> None:
+        pass
+
+    def generate(self, *args):
+        raise NotImplementedError
+
+    def __call__(self, *args, **kwargs) -> torch.Tensor:
+        self.pre_hook()
+        return self.output_hook(self.generate(*args, **kwargs))
+
+    def __str__(self) -> str:
+        pretty = ", ".join(f"{k}={getattr(self, k)!s}" for k in self.ng_params())
+        return f"<NoiseGenerator({self.name}): device={self.device}, shape={self.shape}, dtype={self.dtype}, {pretty}>"
+
+
+class FramesToChannelsNoiseGenerator(NoiseGenerator):
+    """5-D (B,C,F,H,W) latents are generated as (B, C*F, H, W) planes (:182-209). Index-only."""
+
+    MIN_DIMS = 4
+    MAX_DIMS = 5
+
+    def get_adjusted_shape(self):
+        if self.frames:
+            return (self.batch, self.channels * self.frames, self.height, self.width)
+        return (self.batch, self.channels, self.height, self.width)
+
+    def fix_output_frames(self, noise: torch.Tensor) -> torch.Tensor:
+        if not self.frames:
+            return noise
+        return noise.reshape(self.batch, self.channels, self.frames, self.height, self.width)
+
+    def rand_like(self, *args, shape=None, **kwargs) -> torch.Tensor:
+        noise = super().rand_like(*args, shape=shape, **kwargs)
+        if shape is not None:
+            return noise
+        adjusted = self.get_adjusted_shape()
+        return noise.reshape(*adjusted) if noise.shape != adjusted else noise
+
+
+class GaussianNoiseGenerator(NoiseGenerator):
+    name = "gaussian"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {"normalized": False}
+
+    def generate(self, *_args):
+        return self.rand_like()
+
+
+class UniformNoiseGenerator(NoiseGenerator):
+    name = "uniform"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {"normalized": False, "sub_fac": 0.5, "mul_fac": 3.46, "mean_fac": 0.0}
+
+    def generate(self, *_args):
+        # rand.sub_(sub).mul_(mul).add_(mean): one kernel, each step rounded like the op chain
+        return ops.affine(self.rand_like(fun="uniform"), -self.sub_fac, self.mul_fac, self.mean_fac)
+
+
+class PerlinOldNoiseGenerator(FramesToChannelsNoiseGenerator):
+    """Perlin with one grid cell per pixel (:289-493): the whole block-position machinery of the
+    reference collapses to a 2x2 gradient stencil, shared by every batch item."""
+
+    name = "perlin_old"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {"div_fac": 2.0, "iterations": 2, "blend_mode": "lerp"}
+
+    def generate(self, *_args):
+        hostutil.blend_mode_id(self.blend_mode)  # validates like BLENDING_MODES[...] would
+        base = self.rand_like(fun="uniform")
+        b, c, h, w = base.shape
+        angles = [
+            rng.uniform(
+                (c, h + 1, w + 1),
+                device=self.device,
+                generator=self.device_generator(),
+                low=0.0,
+                high=2.0 * math.pi,
+                batch_sharded=False,
+            )
+            for _ in range(self.iterations)
+        ]
+        if base.dtype != torch.float32:
+            base = base.float()
+        noise = ops.perlin_accumulate(base, angles, shape=(b, c, h, w), div_fac=self.div_fac, blend_mode=self.blend_mode)
+        return self.fix_output_frames(noise.to(self.dtype))
+
+
+class _PyramidBase(FramesToChannelsNoiseGenerator):
+    def _accumulate(self, base, levels, weights, orig_h, orig_w):
+        mode = self.upscale_mode
+        if mode in ops.RESAMPLE_IDS and (base is None or base.dtype == torch.float32):
+            return ops.pyramid_accumulate(base, levels, weights, out_hw=(orig_h, orig_w), mode=mode)
+        # modes without a fused kernel (bicubic, nearest): resize each level, accumulate with axpby
+        noise = base
+        for lv, wgt in zip(levels, weights):
+            up = hostutil.scale_samples(lv, orig_w, orig_h, mode=mode).contiguous()
+            noise = ops.axpby(up, wgt, None) if noise is None else ops.axpby(noise, 1.0, up, wgt, out=noise)
+        return noise
+
+
+class PyramidNoiseGenerator(_PyramidBase):
+    name = "pyramid"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {"discount": 0.7, "upscale_mode": "bilinear", "iterations": 10}
+
+    def level_sizes(self, h: int, w: int) -> list[tuple[int, int]]:
+        """Level sizes from the CPU generator, one host draw per level exactly like the reference
+        (:626-648): r = U(0,1)*2+2, cumulative int division, stop at a 1-pixel side."""
+        sizes = []
+        host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
+        for i in range(self.iterations):
+            r = torch.rand(1, generator=host_gen).cpu().item() * 2 + 2
+            w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
+            sizes.append((h, w))
+            if w == 1 or h == 1:
+                break
+        return sizes
+
+    def generate(self, *_args):
+        base = self.rand_like()
+        b, c, h, w = base.shape
+        sizes = self.level_sizes(h, w)
+        levels = [
+            rng.normal((b, c, lh, lw), device=self.device, dtype=base.dtype, generator=self.device_generator())
+            for lh, lw in sizes
+        ]
+        weights = [self.discount**i for i in range(len(levels))]
+        return self.fix_output_frames(self._accumulate(base, levels, weights, h, w))
+
+
+class HighresPyramidNoiseGenerator(_PyramidBase):
+    name = "highres_pyramid"
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.noise_generator is None:
+            self.noise_generator = UniformNoiseGenerator(*args, **(kwargs | {"normalized": self.normalize_noise}))
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {
+            "normalized": True,
+            "discount": 0.7,
+            "upscale_mode": "bilinear",
+            "iterations": 4,
+            "noise_generator": None,
+            "normalize_noise": False,
+        }
+
+    def generate(self, s, sn):
+        b, c, h, w = adjusted = self.get_adjusted_shape()
+        orig_h, orig_w = h, w
+        base = self.noise_generator(s, sn).reshape(*adjusted)
+        host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
+        rs = torch.rand(self.iterations, dtype=torch.float32, generator=host_gen).cpu() * 2 + 2
+        levels, weights = [], []
+        for i in range(self.iterations):
+            r = rs[i].item()
+            h, w = min(orig_h * 15, int(h * (r**i))), min(orig_w * 15, int(w * (r**i)))
+            levels.append(rng.normal((b, c, h, w), device=self.device, generator=self.device_generator()))
+            weights.append(self.discount**i)
+            if h >= orig_h * 15 or w >= orig_w * 15:
+                break
+        return self.fix_output_frames(self._accumulate(base.contiguous(), levels, weights, orig_h, orig_w))
+
+
+class PyramidOldNoiseGenerator(_PyramidBase):
+    name = "pyramid_old"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {
+            "discount": 0.8,
+            "iterations": 5,
+            "upscale_mode": "nearest-exact",
+            "normalized": False,
+        }
+
+    def generate(self, *_args):
+        b, c, h, w = self.get_adjusted_shape()
+        levels, weights = [], []
+        r = 1
+        for i in range(self.iterations):
+            r *= 2
+            levels.append(
+                rng.normal((b, c, h * r, w * r), device=self.device, generator=self.device_generator(), std=0.5**i),
+            )
+            weights.append(self.discount**i)
+        # the reference accumulates into zeros: 0 + level*w is exact, so no base tensor is needed
+        return self.fix_output_frames(self._accumulate(None, levels, weights, h, w).to(self.dtype))
+
+
+class _SpectralGainGenerator(FramesToChannelsNoiseGenerator):
+    """Shared tail of the fft -> real gain -> ifft(.real) generators (OneF, GreenTest)."""
+
+    MIN_DIMS = 4
+    MAX_DIMS = 5
+
+    def full_gain(self) -> torch.Tensor:
+        """(H, W) real gain on the host (float32), same op sequence as the reference."""
+        raise NotImplementedError
+
+    def half_gain(self) -> torch.Tensor:
+        cache = getattr(self, "_gain_cache", None)
+        if cache is not None:
+            return cache
+        g = self.full_gain()
+        # real(ifft2(fft2(x) * G)) for real x equals filtering with the Hermitian-symmetrised gain
+        g_neg = torch.roll(torch.flip(g, dims=(0, 1)), shifts=(1, 1), dims=(0, 1))
+        g_sym = (g + g_neg) * 0.5
+        half = g_sym[:, : self.width // 2 + 1].contiguous().to(self.device)
+        self._gain_cache = half
+        return half
+
+    def filtered(self) -> torch.Tensor:
+        noise = self.rand_like()
+        if noise.dtype != torch.float32:
+            noise = noise.float()
+        return ops.spectral_filter(
+            real=noise,
+            mask=self.half_gain(),
+            hw=(self.height, self.width),
+            out_scale=1.0 / (self.height * self.width),
+        )
+
+
+class GreenTestNoiseGenerator(_SpectralGainGenerator):
+    name = "green_test"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {"scale_fac": 1.0, "x_pow": 2, "y_pow": 2, "power_base": 1}
+
+    def full_gain(self):
+        fy = torch.fft.fftfreq(self.height)[:, None] ** self.y_pow
+        fx = torch.fft.fftfreq(self.width) ** self.x_pow
+        power = torch.sqrt(fy + fx)
+        power[0, 0] = self.power_base
+        return 1.0 / torch.sqrt(power)
+
+    def generate(self, *_args):
+        noise = self.filtered()
+        # noise *= scale / noise.std()  (:703; the complex std equals the std of the real part up to
+        # the ~1e-8 imaginary residue of a Hermitian-symmetric filter)
+        sums = ops.moments(noise)
+        count = parallel.global_count(noise.numel(), sums)
+        ops.scale_by_std(noise, sums, count, self.scale_fac / (self.width * self.height))
+        return self.fix_output_frames(noise.to(self.dtype))
+
+
+class OneFNoiseGenerator(_SpectralGainGenerator):
+    name = "onef"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {
+            "alpha": 2.0,
+            "k": 1.0,
+            "hfac": 1.0,
+            "wfac": 1.0,
+            "base_power": 1.0,
+            "use_sqrt": True,
+        }
+
+    def full_gain(self):
+        freq_x = torch.fft.fftfreq(self.height, self.hfac)
+        freq_y = torch.fft.fftfreq(self.width, self.wfac)
+        fx, fy = torch.meshgrid(freq_x, freq_y, indexing="ij")
+        power = (fx**2 + fy**2) ** (-self.alpha / 2.0)
+        if self.k != 0:
+            power = self.k / power
+        power[0, 0] = self.base_power
+        if self.use_sqrt and bool((power < 0).any()):
+            raise NotImplementedError("onef noise with a negative power spectrum (complex gain) has no kernel")
+        return 1.0 / (torch.sqrt(power) if self.use_sqrt else power)
+
+    def generate(self, *_args):
+        # fftn over (B,C,H,W) with a gain constant over B,C == per-plane 2-D transform (:750-759)
+        return self.fix_output_frames(self.filtered().to(self.dtype))
+
+
+class PowerLawNoiseGenerator(NoiseGenerator):
+    name = "powerlaw"
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {"alpha": 2.0, "div_max_dims": None, "use_sign": False, "use_div_max_abs": True}
+
+    def generate(self, *_args):
+        noise = self.rand_like()
+        if noise.dtype != torch.float32:
+            noise = noise.float()
+        ops.powerlaw(noise, self.alpha, use_sign=self.use_sign, out=noise)
+        if self.div_max_dims is not None:
+            dims = tuple(sorted(d % noise.ndim for d in self.div_max_dims))
+            if dims == tuple(range(1, noise.ndim)):
+                ops.div_item_max(noise, use_abs=self.use_div_max_abs)
+            else:
+                noise /= torch.amax(
+                    torch.abs(noise) if self.use_div_max_abs else noise,
+                    keepdim=True,
+                    dim=self.div_max_dims,
+                )
+        return noise.to(self.dtype)
+
+
+class MixedNoiseGenerator(NoiseGenerator):
+    """Weighted sum of child generators (:212-249). `noise_mix` entries are
+    (generator class, kwargs, scale or None); `output_scale` multiplies the sum."""
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {
+            "name": "mixed_noise",
+            "normalized": True,
+            "pass_args": frozenset(("cpu",)),
+            "noise_mix": (),
+            "output_scale": None,
+        }
+
+    def __init__(self, x, *args, **kwargs):
+        lo = hi = None
+        self.name = kwargs["name"]
+        for item in kwargs["noise_mix"]:
+            ng_class = item[0] if isinstance(item, (tuple, list)) else item
+            cmin, cmax = ng_class.MIN_DIMS, ng_class.MAX_DIMS
+            lo = max(lo if lo is not None else cmin, cmin)
+            hi = min(hi if hi is not None else cmax, cmax)
+        self.MIN_DIMS, self.MAX_DIMS = lo, hi
+        super().__init__(x, *args, **kwargs)
+        # children keep their own class-default `normalized`; only pass_args are forwarded (:236-237)
+        forwarded = {k: v for k, v in kwargs.items() if k in self.pass_args}
+        self.ng_list = [(ng_class(x, **ng_kwargs, **forwarded), mult) for ng_class, ng_kwargs, mult in self.noise_mix]
+
+    def generate(self, *args):
+        total = None
+        for ng, mult in self.ng_list:
+            part = ng(*args)
+            if part.dtype != torch.float32:
+                part = part.float()
+            if total is None:
+                total = part if mult is None else ops.scale(part, mult)
+            else:
+                ops.axpby(total, 1.0, part, 1.0 if mult is None else mult, out=total)
+        if self.output_scale is not None:
+            ops.scale(total, self.output_scale)
+        return total.to(self.dtype)
+
+
+def _unsupported(name: str, why: str) -> Callable:
+    class _Unsupported(NoiseGenerator):
+        def __init__(self, *_a, **_k):
+            raise NotImplementedError(f"sonar_b200: noise type {name!r} is out of scope for the B200 hot path ({why})")
+
+    _Unsupported.name = name
+    _Unsupported.__name__ = f"Unsupported_{name}"
+    return _Unsupported
+
+
+BrownianNoiseGenerator = _unsupported("brownian", "needs torchsde's BrownianTree")
+StudentTNoiseGenerator = _unsupported("studentt", "torch.distributions sampler")
+LaplacianNoiseGenerator = _unsupported("laplacian", "torch.distributions sampler")
+DistroNoiseGenerator = _unsupported("distro", "torch.distributions zoo")
+PowerOldNoiseGenerator = _unsupported("power_old", "documented as wrong upstream")
+PinkOldNoiseGenerator = _unsupported("pink_old", "documented as wrong upstream")
+VoronoiNoiseGenerator = _unsupported("voronoi", "not on the configured hot path")
+CollatzNoiseGenerator = _unsupported("collatz", "not on the configured hot path")
+WaveletNoiseGenerator = _unsupported("wavelet", "ranked 'next' in SURVEY.md section 8f")
+WaveletFilteredNoiseGenerator = _unsupported("wavelet_filtered", "ranked 'next' in SURVEY.md section 8f")
+ScatternetFilteredNoiseGenerator = _unsupported("scatternet_filtered", "needs pytorch_wavelets ScatLayer")
+
+
+__all__ = [
+    "BrownianNoiseGenerator",
+    "CollatzNoiseGenerator",
+    "DistroNoiseGenerator",
+    "FramesToChannelsNoiseGenerator",
+    "GaussianNoiseGenerator",
+    "GreenTestNoiseGenerator",
+    "HighresPyramidNoiseGenerator",
+    "LaplacianNoiseGenerator",
+    "MixedNoiseGenerator",
+    "NoiseError",
+    "NoiseGenerator",
+    "NoiseType",
+    "OneFNoiseGenerator",
+    "PerlinOldNoiseGenerator",
+    "PinkOldNoiseGenerator",
+    "PowerLawNoiseGenerator",
+    "PowerOldNoiseGenerator",
+    "PyramidNoiseGenerator",
+    "PyramidOldNoiseGenerator",
+    "ScatternetFilteredNoiseGenerator",
+    "StudentTNoiseGenerator",
+    "UniformNoiseGenerator",
+    "VoronoiNoiseGenerator",
+    "WaveletFilteredNoiseGenerator",
+    "WaveletNoiseGenerator",
+]

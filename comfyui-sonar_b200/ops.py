@@ -1,0 +1,620 @@
+"""Tensor-level wrappers over the C ABI (include/sonar_b200.h).
+
+Every function here takes CUDA tensors, enqueues hand-written kernels on torch's current stream and
+returns CUDA tensors. Nothing in this module computes with torch ops on the hot path and nothing
+falls back to the CPU: a non-CUDA tensor is an error.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Sequence
+
+import torch
+
+from . import _native
+from ._native import SonarStepParams
+
+# enums of include/sonar_b200.h
+STEP_EULER, STEP_DPMPP = 0, 1
+MODE_CLASSIC, MODE_NEW, MODE_DENOISED = 0, 1, 2
+BLEND_IDS = {"lerp": 0, "inject": 1, "subtract_b": 2}
+HIST_NONE, HIST_PRESENT, HIST_INIT = 0, 1, 2
+NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX, NOISE_PHILOX_NORMALIZED = 0, 1, 2, 3
+
+LAUNCH_COUNT = 0  # number of kernels launched through this module (bench.py's gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCH_COUNT  # noqa: PLW0603
+    LAUNCH_COUNT += n
+
+
+_LAST_DEVICE: int | None = None
+
+
+def _prepare(*tensors: torch.Tensor | None) -> tuple[ctypes.CDLL, ctypes.c_void_p]:
+    """Validates devices, binds the library's runtime to the tensors' device, returns (lib, stream)."""
+    global _LAST_DEVICE  # noqa: PLW0603
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("sonar_b200 kernels take CUDA tensors only (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("sonar_b200 kernels take contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    if dev is None:
+        raise RuntimeError("no tensor given")
+    lib = _native.load()
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx != _LAST_DEVICE:
+        _native.check(lib.sonar_set_device(idx), "sonar_set_device")
+        _LAST_DEVICE = idx
+    return lib, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+
+
+# --------------------------------------------------------------------------------------------
+# Philox draws
+# --------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class PhiloxDraw:
+    """Identity of one torch-compatible CUDA draw: what torch.randn(numel) would have produced."""
+
+    seed: int
+    offset: int
+    grid_blocks: int
+    numel: int  # float elements of the draw (2x for complex64)
+    counter_offset: int  # how far the draw advances the generator
+
+
+def philox_policy(numel: int) -> tuple[int, int]:
+    """(grid_blocks, counter_offset) of ATen's calc_execution_policy for the current device."""
+    lib = _native.load()
+    grid = ctypes.c_uint32(0)
+    inc = ctypes.c_uint64(0)
+    _native.check(lib.sonar_philox_policy(int(numel), ctypes.byref(grid), ctypes.byref(inc)), "sonar_philox_policy")
+    return grid.value, inc.value
+
+
+def reserve_draw(numel: int, device: torch.device, generator: torch.Generator | None = None) -> PhiloxDraw:
+    """Consumes `numel` values from torch's CUDA generator exactly like an ATen distribution kernel
+    would (same offset arithmetic), without launching anything."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("reserve_draw needs a CUDA device")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = generator if generator is not None else torch.cuda.default_generators[idx]
+    with torch.cuda.device(idx):
+        grid, inc = philox_policy(numel)
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    if numel > 0:
+        gen.set_offset(offset + inc)
+    return PhiloxDraw(seed=seed, offset=offset, grid_blocks=grid, numel=int(numel), counter_offset=inc)
+
+
+def philox_fill(
+    draw: PhiloxDraw,
+    out: torch.Tensor,
+    *,
+    kind: str = "normal",
+    p0: float = 0.0,
+    p1: float = 1.0,
+    begin: int = 0,
+) -> torch.Tensor:
+    """Materialises elements [begin, begin + out.numel()) of `draw` into `out` (float32 storage)."""
+    lib, stream = _prepare(out)
+    count = out.numel() * (2 if out.is_complex() else 1)
+    fn = lib.sonar_philox_normal_f32 if kind == "normal" else lib.sonar_philox_uniform_f32
+    _native.check(
+        fn(_ptr(out), begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, p0, p1, stream),
+        f"sonar_philox_{kind}_f32",
+    )
+    _count()
+    return out
+
+
+def randn(
+    shape: Sequence[int],
+    *,
+    device: torch.device,
+    dtype: torch.dtype = torch.float32,
+    generator: torch.Generator | None = None,
+) -> torch.Tensor:
+    """torch.randn(shape, device='cuda', dtype=float32|complex64), bit-exact, from our kernel."""
+    if dtype not in {torch.float32, torch.complex64}:
+        raise TypeError(f"sonar_b200.randn supports float32 and complex64, got {dtype}")
+    out = torch.empty(tuple(shape), device=device, dtype=dtype)
+    if out.numel() == 0:
+        return out
+    is_c = dtype == torch.complex64
+    draw = reserve_draw(out.numel() * (2 if is_c else 1), out.device, generator)
+    # complex normal: real/imag each N(0, 1/2) (ATen normal_ on view_as_real with std/sqrt(2))
+    std = float(1.0 / math.sqrt(2.0)) if is_c else 1.0
+    return philox_fill(draw, out, kind="normal", p0=0.0, p1=std)
+
+
+def rand(
+    shape: Sequence[int],
+    *,
+    device: torch.device,
+    generator: torch.Generator | None = None,
+    low: float = 0.0,
+    high: float = 1.0,
+) -> torch.Tensor:
+    """torch.rand / torch.empty(shape).uniform_(low, high) on CUDA, bit-exact."""
+    out = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
+    draw = reserve_draw(out.numel(), out.device, generator)
+    return philox_fill(draw, out, kind="uniform", p0=float(low), p1=float(high))
+
+
+# --------------------------------------------------------------------------------------------
+# moments / scale_noise
+# --------------------------------------------------------------------------------------------
+def new_sums(device: torch.device) -> torch.Tensor:
+    return torch.zeros(2, device=device, dtype=torch.float64)
+
+
+def moments(x: torch.Tensor, sums: torch.Tensor | None = None) -> torch.Tensor:
+    """Accumulates (sum, sum of squares) of x into the device double[2] `sums`."""
+    _f32(x, "x")
+    if sums is None:
+        sums = new_sums(x.device)
+    lib, stream = _prepare(x, sums)
+    _native.check(lib.sonar_moments_f32(_ptr(x), x.numel(), _ptr(sums), stream), "sonar_moments_f32")
+    _count()
+    return sums
+
+
+def philox_normal_moments(draw: PhiloxDraw, *, begin: int, count: int, sums: torch.Tensor) -> torch.Tensor:
+    lib, stream = _prepare(sums)
+    _native.check(
+        lib.sonar_philox_normal_moments(
+            begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, _ptr(sums), stream,
+        ),
+        "sonar_philox_normal_moments",
+    )
+    _count()
+    return sums
+
+
+def scale_noise_apply(
+    x: torch.Tensor,
+    sums: torch.Tensor,
+    count: int,
+    factor: float = 1.0,
+    *,
+    threshold_std_devs: float = 2.5,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """The conditional centre / rescale / multiply of scale_noise, decided on the device."""
+    _f32(x, "x")
+    out = x if out is None else out
+    lib, stream = _prepare(x, out, sums)
+    _native.check(
+        lib.sonar_scale_noise_f32(
+            _ptr(x), _ptr(out), x.numel(), _ptr(sums), int(count), float(factor), float(threshold_std_devs), stream,
+        ),
+        "sonar_scale_noise_f32",
+    )
+    _count()
+    return out
+
+
+def add_moments(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _f32(a, "a")
+    _f32(b, "b")
+    out = a if out is None else out
+    lib, stream = _prepare(a, b, out, sums)
+    _native.check(
+        lib.sonar_add_moments_f32(_ptr(a), _ptr(b), _ptr(out), a.numel(), _ptr(sums), stream),
+        "sonar_add_moments_f32",
+    )
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# fused sonar step
+# --------------------------------------------------------------------------------------------
+def sonar_step(params: SonarStepParams, *tensors: torch.Tensor | None) -> None:
+    """Launches the fused step; `tensors` are the live tensors behind the pointers (validation)."""
+    lib, stream = _prepare(*tensors)
+    _native.check(lib.sonar_step_f32(ctypes.byref(params), stream), "sonar_step_f32")
+    _count()
+
+
+# --------------------------------------------------------------------------------------------
+# element-wise combinators
+# --------------------------------------------------------------------------------------------
+def scale(x: torch.Tensor, factor: float) -> torch.Tensor:
+    """x *= factor (in place) through the axpby kernel."""
+    _f32(x, "x")
+    lib, stream = _prepare(x)
+    _native.check(lib.sonar_axpby_f32(_ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), stream), "sonar_axpby_f32")
+    _count()
+    return x
+
+
+def axpby(a: torch.Tensor, alpha: float, b: torch.Tensor | None, beta: float = 1.0, out: torch.Tensor | None = None):
+    """out = a * alpha + b * beta."""
+    _f32(a, "a")
+    out = torch.empty_like(a) if out is None else out
+    lib, stream = _prepare(a, b, out)
+    _native.check(
+        lib.sonar_axpby_f32(_ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), stream),
+        "sonar_axpby_f32",
+    )
+    _count()
+    return out
+
+
+def affine(x: torch.Tensor, pre_add: float, mul: float, post_add: float, out: torch.Tensor | None = None):
+    """out = ((x + pre_add) * mul) + post_add, rounding after each step like the eager op chain."""
+    _f32(x, "x")
+    out = x if out is None else out
+    lib, stream = _prepare(x, out)
+    _native.check(
+        lib.sonar_affine_f32(_ptr(x), _ptr(out), x.numel(), float(pre_add), float(mul), float(post_add), stream),
+        "sonar_affine_f32",
+    )
+    _count()
+    return out
+
+
+def scale_by_std(x: torch.Tensor, sums: torch.Tensor, count: int, scale: float) -> torch.Tensor:
+    """x *= scale / std(x) (in place), std from device sums."""
+    _f32(x, "x")
+    lib, stream = _prepare(x, sums)
+    _native.check(
+        lib.sonar_scale_by_std_f32(_ptr(x), _ptr(x), x.numel(), _ptr(sums), int(count), float(scale), stream),
+        "sonar_scale_by_std_f32",
+    )
+    _count()
+    return x
+
+
+def blend(a: torch.Tensor, b: torch.Tensor, t, *, mode: str = "lerp", out: torch.Tensor | None = None) -> torch.Tensor:
+    """BLENDING_MODES[mode](a, b, t); t is a python scalar, a one-element tensor or a full tensor."""
+    _f32(a, "a")
+    _f32(b, "b")
+    if a.shape != b.shape:
+        raise ValueError(f"blend: shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    t_tensor = None
+    t_scalar = 0.0
+    if isinstance(t, torch.Tensor):
+        if t.numel() == 1:
+            t_scalar = float(t.item())
+        else:
+            t_tensor = t.expand_as(a).contiguous() if t.shape != a.shape else t
+            _f32(t_tensor, "t")
+    else:
+        t_scalar = float(t)
+    out = torch.empty_like(a) if out is None else out
+    lib, stream = _prepare(a, b, t_tensor, out)
+    _native.check(
+        lib.sonar_blend_f32(_ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], stream),
+        "sonar_blend_f32",
+    )
+    _count()
+    return out
+
+
+def composite(dst: torch.Tensor, src: torch.Tensor, mask: torch.Tensor, out: torch.Tensor | None = None):
+    """dst * (1 - mask) + src * mask, mask (B, 1, H, W) broadcast over channels."""
+    _f32(dst, "dst")
+    b = dst.shape[0]
+    hw = dst.shape[-2] * dst.shape[-1]
+    channels = dst.numel() // (b * hw)
+    if mask.numel() != b * hw:
+        raise ValueError("composite: mask must have shape (batch, 1, H, W)")
+    out = torch.empty_like(dst) if out is None else out
+    lib, stream = _prepare(dst, src, mask, out)
+    _native.check(
+        lib.sonar_composite_f32(_ptr(dst), _ptr(src), _ptr(mask), _ptr(out), b, channels, hw, stream),
+        "sonar_composite_f32",
+    )
+    _count()
+    return out
+
+
+def powerlaw(x: torch.Tensor, alpha: float, *, use_sign: bool, out: torch.Tensor | None = None) -> torch.Tensor:
+    _f32(x, "x")
+    out = torch.empty_like(x) if out is None else out
+    lib, stream = _prepare(x, out)
+    _native.check(lib.sonar_powerlaw_f32(_ptr(x), _ptr(out), x.numel(), float(alpha), int(use_sign), stream), "sonar_powerlaw_f32")
+    _count()
+    return out
+
+
+def _range_scratch(items: int, device: torch.device) -> torch.Tensor:
+    lib = _native.load()
+    return torch.empty(max(1, lib.sonar_item_range_scratch_bytes(items)), device=device, dtype=torch.uint8)
+
+
+def div_item_max(x: torch.Tensor, *, use_abs: bool = True) -> torch.Tensor:
+    """x / amax(|x|) over everything but the leading dim, in place."""
+    _f32(x, "x")
+    items = x.shape[0]
+    scratch = _range_scratch(items, x.device)
+    lib, stream = _prepare(x, scratch)
+    _native.check(
+        lib.sonar_item_div_max_f32(_ptr(x), _ptr(x), items, x.numel() // items, int(use_abs), _ptr(scratch), stream),
+        "sonar_item_div_max_f32",
+    )
+    _count(2)
+    return x
+
+
+def minmax_rescale(x: torch.Tensor, target_min: float, target_max: float, *, eps: float = 1e-7) -> torch.Tensor:
+    _f32(x, "x")
+    items = x.shape[0]
+    out = torch.empty_like(x)
+    scratch = _range_scratch(items, x.device)
+    lib, stream = _prepare(x, out, scratch)
+    _native.check(
+        lib.sonar_item_minmax_rescale_f32(
+            _ptr(x), _ptr(out), items, x.numel() // items, float(target_min), float(target_max), float(eps),
+            _ptr(scratch), stream,
+        ),
+        "sonar_item_minmax_rescale_f32",
+    )
+    _count(2)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# pyramid / resample / perlin
+# --------------------------------------------------------------------------------------------
+RESAMPLE_IDS = {"bilinear": 0, "nearest-exact": 1, "area": 2}
+
+
+def pyramid_accumulate(
+    base: torch.Tensor | None,
+    levels: Sequence[torch.Tensor],
+    weights: Sequence[float],
+    *,
+    out_hw: tuple[int, int],
+    mode: str = "bilinear",
+    base_scale: float = 1.0,
+    out: torch.Tensor | None = None,
+) -> torch.Tensor:
+    """out = base_scale*base + sum_i weights[i] * resample(levels[i] -> out_hw), one pass."""
+    if mode not in RESAMPLE_IDS:
+        raise NotImplementedError(f"resample mode {mode!r} has no kernel (supported: {', '.join(RESAMPLE_IDS)})")
+    if len(levels) > _native.PYRAMID_MAX_LEVELS:
+        raise ValueError("too many pyramid levels")
+    H, W = out_hw
+    ref = base if base is not None else levels[0]
+    planes = ref.numel() // (ref.shape[-2] * ref.shape[-1])
+    if out is None:
+        out = torch.empty((*ref.shape[:-2], H, W), device=ref.device, dtype=torch.float32)
+    p = _native.SonarPyramidParams()
+    p.out, p.base = out.data_ptr(), (0 if base is None else base.data_ptr())
+    for i, (lv, wgt) in enumerate(zip(levels, weights)):
+        _f32(lv, "level")
+        if lv.numel() // (lv.shape[-2] * lv.shape[-1]) != planes:
+            raise ValueError("pyramid level plane count mismatch")
+        p.levels[i] = lv.data_ptr()
+        p.level_h[i], p.level_w[i] = lv.shape[-2], lv.shape[-1]
+        p.weights[i] = float(wgt)
+    p.planes, p.H, p.W = planes, H, W
+    p.n_levels, p.mode, p.base_scale = len(levels), RESAMPLE_IDS[mode], float(base_scale)
+    lib, stream = _prepare(out, base, *levels)
+    _native.check(lib.sonar_pyramid_accum_f32(ctypes.byref(p), stream), "sonar_pyramid_accum_f32")
+    _count()
+    return out
+
+
+def resample(x: torch.Tensor, height: int, width: int, *, mode: str = "bilinear") -> torch.Tensor:
+    """F.interpolate(x, size=(height, width), mode=mode) for bilinear / nearest-exact / area."""
+    _f32(x, "x")
+    return pyramid_accumulate(None, [x.contiguous()], [1.0], out_hw=(height, width), mode=mode)
+
+
+def perlin_accumulate(
+    base: torch.Tensor | None,
+    angles: Sequence[torch.Tensor],
+    *,
+    shape: tuple[int, int, int, int],
+    div_fac: float = 2.0,
+    blend_mode: str = "lerp",
+) -> torch.Tensor:
+    B, C, H, W = shape
+    if len(angles) > _native.PERLIN_MAX_ITERS:
+        raise ValueError("too many perlin iterations")
+    out = torch.empty(shape, device=angles[0].device if angles else base.device, dtype=torch.float32)
+    p = _native.SonarPerlinParams()
+    p.out, p.base = out.data_ptr(), (0 if base is None else base.data_ptr())
+    for i, a in enumerate(angles):
+        _f32(a, "angles")
+        if tuple(a.shape) != (C, H + 1, W + 1):
+            raise ValueError(f"perlin angle grid must be {(C, H + 1, W + 1)}, got {tuple(a.shape)}")
+        p.angles[i] = a.data_ptr()
+    p.B, p.C, p.H, p.W = B, C, H, W
+    p.iterations, p.blend_mode, p.div_fac = len(angles), BLEND_IDS[blend_mode], float(div_fac)
+    lib, stream = _prepare(out, base, *angles)
+    _native.check(lib.sonar_perlin_accum_f32(ctypes.byref(p), stream), "sonar_perlin_accum_f32")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# spectral shaping
+# --------------------------------------------------------------------------------------------
+_SPECTRAL_SCRATCH: dict[tuple, torch.Tensor] = {}
+
+
+def spectral_filter(
+    *,
+    real: torch.Tensor | None = None,
+    spectrum: torch.Tensor | None = None,
+    mask: torch.Tensor | None,
+    hw: tuple[int, int],
+    out_scale: float,
+) -> torch.Tensor:
+    """[rfft2 ->] mask -> irfft2 per (H, W) plane. Exactly one of real / spectrum is given.
+
+    real: (..., H, W) float32; spectrum: (..., H, W//2+1) complex64; mask: (H, W//2+1) float32.
+    """
+    H, W = hw
+    wh = W // 2 + 1
+    src = real if real is not None else spectrum
+    if (real is None) == (spectrum is None):
+        raise ValueError("give exactly one of real / spectrum")
+    if real is not None:
+        _f32(real, "real")
+        if tuple(real.shape[-2:]) != (H, W):
+            raise ValueError("real input plane size mismatch")
+        lead = real.shape[:-2]
+    else:
+        if spectrum.dtype != torch.complex64 or tuple(spectrum.shape[-2:]) != (H, wh):
+            raise ValueError(f"spectrum must be complex64 (..., {H}, {wh})")
+        lead = spectrum.shape[:-2]
+    if mask is not None:
+        _f32(mask, "mask")
+        if mask.numel() != H * wh:
+            raise ValueError(f"mask must have {H}x{wh} elements")
+    out = torch.empty((*lead, H, W), device=src.device, dtype=torch.float32)
+    planes = out.numel() // (H * W)
+    lib, stream = _prepare(src, mask, out)
+    scratch = None
+    need = lib.sonar_spectral_scratch_bytes(H, W)
+    if need > 0:
+        key = (src.device, H, W)
+        scratch = _SPECTRAL_SCRATCH.get(key)
+        if scratch is None:
+            scratch = torch.empty(need, device=src.device, dtype=torch.uint8)
+            _SPECTRAL_SCRATCH[key] = scratch
+    p = _native.SonarSpectralParams()
+    p.out = out.data_ptr()
+    p.in_real = 0 if real is None else real.data_ptr()
+    p.in_spec = 0 if spectrum is None else spectrum.data_ptr()
+    p.mask = 0 if mask is None else mask.data_ptr()
+    p.scratch = 0 if scratch is None else scratch.data_ptr()
+    p.planes, p.H, p.W, p.out_scale = planes, H, W, float(out_scale)
+    _native.check(lib.sonar_spectral_filter_f32(ctypes.byref(p), stream), "sonar_spectral_filter_f32")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# DWT levels
+# --------------------------------------------------------------------------------------------
+DWT_MODE_IDS = {"symmetric": 0, "zero": 1, "reflect": 2, "periodic": 3}
+
+
+def make_filters(dec_lo, dec_hi, rec_lo, rec_hi) -> _native.SonarWaveletFilters:
+    f = _native.SonarWaveletFilters()
+    n = len(dec_lo)
+    if n > _native.DWT_MAX_TAPS or n % 2 or n < 2:
+        raise ValueError(f"unsupported wavelet filter length {n}")
+    f.length = n
+    for i in range(n):
+        f.dec_lo[i], f.dec_hi[i], f.rec_lo[i], f.rec_hi[i] = dec_lo[i], dec_hi[i], rec_lo[i], rec_hi[i]
+    return f
+
+
+def dwt_coeff_len(n: int, filter_len: int) -> int:
+    return (n + filter_len - 1) // 2
+
+
+def dwt2_analysis(
+    a: torch.Tensor,
+    b: torch.Tensor | None,
+    filters: _native.SonarWaveletFilters,
+    *,
+    mode: str,
+    coeff_dtype: torch.dtype,
+    valid_hw: tuple[int, int] | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """One analysis level of (a - b). a: (planes, rows, W); valid_hw selects the top-left (H, W)
+    region of a buffer whose rows exceed H. Returns ll (planes, h, w), hi (planes, 3, h, w)."""
+    planes, rows, cols = a.shape
+    H, W = valid_hw if valid_hw is not None else (rows, cols)
+    if W != cols:
+        raise ValueError("dwt2_analysis needs the row length of the buffer to equal W")
+    L = filters.length
+    h, w = dwt_coeff_len(H, L), dwt_coeff_len(W, L)
+    ll = torch.empty((planes, h, w), device=a.device, dtype=coeff_dtype)
+    hi = torch.empty((planes, 3, h, w), device=a.device, dtype=coeff_dtype)
+    p = _native.SonarDwtAnalysisParams()
+    p.in_a, p.in_b = a.data_ptr(), (0 if b is None else b.data_ptr())
+    p.ll, p.hi = ll.data_ptr(), hi.data_ptr()
+    p.planes, p.H, p.W, p.in_stride_h, p.h, p.w = planes, H, W, rows, h, w
+    p.mode = DWT_MODE_IDS[mode]
+    p.in_is_f32 = 0
+    if a.dtype == torch.float32 and coeff_dtype == torch.float64:
+        p.in_is_f32 = 1
+        if rows != H:
+            raise ValueError("fp32 level-1 input must be dense")
+    elif a.dtype != coeff_dtype:
+        raise TypeError(f"dwt2_analysis: input {a.dtype} vs coefficient {coeff_dtype}")
+    p.use_f64 = int(coeff_dtype == torch.float64)
+    p.filters = filters
+    lib, stream = _prepare(a, b, ll, hi)
+    _native.check(lib.sonar_dwt2_analysis(ctypes.byref(p), stream), "sonar_dwt2_analysis")
+    _count()
+    return ll, hi
+
+
+def dwt2_synthesis(
+    sets: Sequence[tuple[torch.Tensor, torch.Tensor, Sequence[float]]],
+    filters: _native.SonarWaveletFilters,
+    *,
+    final: dict | None = None,
+) -> torch.Tensor:
+    """One synthesis level. sets: [(ll, hi, (s_ll, s_h0, s_h1, s_h2)), ...] (1 or 2 entries);
+    ll may be one row/col larger than hi ("unpad"). final = dict(crop=(h, w), addend=, addend_scale=,
+    x=, x_scale=, recon_sign=) turns it into the fp32 epilogue level."""
+    ll0, hi0, _ = sets[0]
+    planes, _, h, w = hi0.shape
+    L = filters.length
+    out_h, out_w = 2 * h - L + 2, 2 * w - L + 2
+    p = _native.SonarDwtSynthesisParams()
+    live = []
+    for i, (ll, hi, sc) in enumerate(sets):
+        p.ll[i], p.hi[i] = ll.data_ptr(), hi.data_ptr()
+        p.ll_rows[i], p.ll_cols[i] = ll.shape[-2], ll.shape[-1]
+        for j in range(4):
+            p.scales[i][j] = float(sc[j])
+        live += [ll, hi]
+    p.n_sets, p.planes, p.h, p.w = len(sets), planes, h, w
+    p.use_f64 = int(hi0.dtype == torch.float64)
+    p.filters = filters
+    if final is None:
+        out = torch.empty((planes, out_h, out_w), device=hi0.device, dtype=hi0.dtype)
+        p.out, p.out_f32 = out.data_ptr(), 0
+    else:
+        ch, cw = final["crop"]
+        out = torch.empty((planes, ch, cw), device=hi0.device, dtype=torch.float32)
+        p.out, p.out_f32 = 0, out.data_ptr()
+        p.crop_h, p.crop_w = ch, cw
+        addend, x = final.get("addend"), final.get("x")
+        p.addend = 0 if addend is None else addend.data_ptr()
+        p.addend_scale = float(final.get("addend_scale", 1.0))
+        p.x = 0 if x is None else x.data_ptr()
+        p.x_scale = float(final.get("x_scale", 1.0))
+        p.recon_sign = float(final.get("recon_sign", 1.0))
+        live += [addend, x]
+    lib, stream = _prepare(out, *live)
+    _native.check(lib.sonar_dwt2_synthesis(ctypes.byref(p), stream), "sonar_dwt2_synthesis")
+    _count()
+    return out

@@ -1,0 +1,577 @@
+"""Sonar momentum samplers on the fused CUDA step.
+
+Host-side mirror of the reference's py/sonar.py: same config objects (`SonarConfig`,
+`GuidanceConfig`, enums), same `sonar_params` merging and error messages (:98-131), same sampler
+function signatures and callback payloads (:483-526, :576-623, :773-820), same registration
+(`add_samplers`, :823-847). The per-step tensor arithmetic -- ~15 full-tensor ATen passes and 4 host
+syncs per Euler-ancestral step upstream -- is ONE launch of `sonar_step_f32` per model evaluation.
+
+Scalar schedule math (ancestral split, DPM-Solver++ log-sigma arithmetic) is evaluated once per step
+on a CPU float32 mirror of `sigmas` with the reference's own op sequence, so the coefficients handed
+to the kernel are the float32 values the reference computes and no step waits on the device.
+"""
+
+from __future__ import annotations
+
+import importlib
+from enum import Enum, auto
+from sys import stderr
+from typing import Any, Callable, NamedTuple
+
+import torch
+from torch import Tensor
+from tqdm.auto import trange
+
+from . import hostutil, noise_graph as noise, ops, parallel
+from ._native import SonarStepParams
+from .kdiff import get_ancestral_step
+
+
+class HistoryType(Enum):
+    ZERO = auto()
+    RAND = auto()
+    SAMPLE = auto()
+    SAMPLE_NORM = auto()
+
+
+class GuidanceType(Enum):
+    LINEAR = auto()
+    EULER = auto()
+
+
+class GuidanceConfig(NamedTuple):
+    guidance_type: GuidanceType = GuidanceType.LINEAR
+    factor: float = 0.01
+    start_step: int = 1
+    end_step: int = 9999
+    latent: Tensor | None = None
+
+
+class MomentumMode(Enum):
+    CLASSIC = auto()
+    NEW = auto()
+    DENOISED = auto()
+
+
+_MODE_IDS = {MomentumMode.CLASSIC: ops.MODE_CLASSIC, MomentumMode.NEW: ops.MODE_NEW, MomentumMode.DENOISED: ops.MODE_DENOISED}
+
+
+class SonarConfig(NamedTuple):
+    momentum: float = 0.95
+    momentum_hist: float = 0.75
+    direction: float = 1.0
+    momentum_start_step: int = 0
+    momentum_end_step: int = 9999
+    always_update_history: bool = True
+    momentum_mode: MomentumMode = MomentumMode.NEW
+    init: HistoryType = HistoryType.ZERO
+    noise_type: noise.NoiseType | None = None
+    custom_noise: noise.CustomNoise | None = None
+    rand_init_noise_type: noise.NoiseType | None = None
+    rand_init_noise_multiplier: float | int = 1.0
+    guidance: GuidanceConfig | None = None
+    blend_mode: str = "lerp"
+    momentum_blend_mode: str | None = None
+    history_blend_mode: str | None = None
+    guidance_blend_mode: str | None = None
+
+    def get_with_default(self, k: str, default: Any) -> Any:  # noqa: ANN401
+        val = getattr(self, k)
+        return val if val is not None else default
+
+
+class SonarBase:
+    """Momentum state + the fused step launcher (reference SonarBase, py/sonar.py:70-320)."""
+
+    DEFAULT_NOISE_TYPE = noise.NoiseType.GAUSSIAN
+
+    def __init__(self, cfg: SonarConfig) -> None:
+        self.history_d: Tensor | None = None
+        self.cfg = cfg
+        self.noise_sampler = None
+        base = cfg.blend_mode
+        # BLENDING_MODES[...] raises KeyError for unknown names, like the reference
+        self.blend = hostutil.BLENDING_MODES[base]
+        self.momentum_blend = hostutil.BLENDING_MODES[cfg.get_with_default("momentum_blend_mode", base)]
+        self.history_blend = hostutil.BLENDING_MODES[cfg.get_with_default("history_blend_mode", base)]
+        self.guidance_blend = hostutil.BLENDING_MODES[cfg.get_with_default("guidance_blend_mode", base)]
+        self._hist_pending_init: tuple[Tensor, float] | None = None
+
+    _cfg_fixups = (
+        ("momentum_mode", MomentumMode),
+        ("init", HistoryType),
+        ("noise_type", noise.NoiseType),
+    )
+
+    @classmethod
+    def get_config(cls, cfg: SonarConfig | None = None, ext: dict | None = None) -> SonarConfig:
+        merged = dict(ext) if ext is not None else {}
+        missing = object()
+        for key, enum_class in cls._cfg_fixups:
+            val = merged.get(key, missing)
+            if val is missing:
+                continue
+            if isinstance(val, str):
+                member = getattr(enum_class, val.strip().upper(), missing)
+                if member is missing:
+                    valid = ", ".join(enum_class.__members__.keys())
+                    raise ValueError(
+                        f"Bad value for {key} of type enum {enum_class.__name__}, must be one of the following: {valid}",
+                    )
+                merged[key] = member
+            elif not isinstance(val, enum_class):
+                raise TypeError(
+                    f"Bad parameter type for {key}: Must be valid string or instance of {enum_class.__name__}",
+                )
+        if cfg is None:
+            return SonarConfig(**merged)
+        return SonarConfig(**(cfg._asdict() | merged))
+
+    def set_noise_sampler(self, x: Tensor, sigmas: Tensor, noise_sampler: Callable | None, seed: int | None = None):
+        sigmas_host = sigmas.detach().float().cpu()
+        sigma_min, sigma_max = sigmas_host[sigmas_host > 0].min(), sigmas_host.max()
+        if noise_sampler is not None and self.cfg.noise_type not in {None, self.DEFAULT_NOISE_TYPE}:
+            print("Sonar: Warning: Noise sampler supplied, overriding noise type from settings", file=stderr)
+        if self.cfg.custom_noise:
+            noise_sampler = self.cfg.custom_noise.make_noise_sampler(x, sigma_min, sigma_max, seed=seed)
+        elif noise_sampler is None:
+            noise_sampler = noise.get_noise_sampler(
+                self.cfg.noise_type or self.DEFAULT_NOISE_TYPE,
+                x,
+                sigma_min,
+                sigma_max,
+                seed=seed,
+                cpu=True,
+                normalized=True,
+            )
+        self.noise_sampler = noise_sampler
+        return noise_sampler
+
+    @property
+    def history_ratios(self) -> tuple[float, float, float]:
+        direction, momentum_hist = self.cfg.direction, self.cfg.momentum_hist
+        hd_scale = 1.0 + abs(direction) * (1 - momentum_hist) if direction < 0 else 2.0 - direction
+        return (momentum_hist, hd_scale, direction)
+
+    def check_step(self, step: int, *, is_history: bool = False) -> bool:
+        cfg = self.cfg
+        if is_history and cfg.always_update_history:
+            return True
+        return cfg.momentum_start_step <= step <= cfg.momentum_end_step
+
+    # ------------------------------------------------------------------------------------
+    # history initialisation (reference init_hist_d, :169-206). It runs once, after the first
+    # momentum mix of the call, so the kernel gets HIST_INIT: used by updates, not by the first mix.
+    # ------------------------------------------------------------------------------------
+    def _initial_history(self, x: Tensor, denoised: Tensor, sigma: float, *, step: int):
+        """Returns (tensor, divisor) for a history born in this call, or None."""
+        if self.history_d is not None or not self.check_step(step, is_history=True):
+            return None
+        cfg, init = self.cfg, self.cfg.init
+        source = denoised if cfg.momentum_mode == MomentumMode.DENOISED else x
+        if init == HistoryType.ZERO:
+            return None
+        if init == HistoryType.SAMPLE:
+            return (source, 1.0)
+        if init == HistoryType.SAMPLE_NORM:
+            return (source, sigma)
+        if init == HistoryType.RAND:
+            ns = noise.get_noise_sampler(
+                cfg.rand_init_noise_type,
+                x,
+                None,
+                None,
+                seed=self.extra_args.get("seed"),
+                cpu=True,
+                normalized=True,
+            )
+            hist = ns(None, None)
+            if cfg.rand_init_noise_multiplier != 1:
+                ops.scale(hist, cfg.rand_init_noise_multiplier)
+            return (hist, 1.0)
+        raise ValueError("Sonar sampler: bad history type")
+
+    # ------------------------------------------------------------------------------------
+    # the fused launch
+    # ------------------------------------------------------------------------------------
+    def fused_step(
+        self,
+        step: int,
+        x: Tensor,
+        denoised: Tensor,
+        sigma: float,
+        *,
+        kind: int,
+        c0: float,
+        c1: float = 0.0,
+        noise_tensor: Tensor | None = None,
+        noise_scale: float = 0.0,
+        noise_philox: dict | None = None,
+    ) -> Tensor:
+        """One kernel: momentum mix, both history updates, Euler / DPM++ update, noise injection."""
+        cfg = self.cfg
+        if x.dtype != torch.float32:
+            raise TypeError(f"sonar_b200 samplers run on float32 latents (got {x.dtype})")
+        x = x.contiguous()
+        denoised = denoised.to(torch.float32).contiguous()
+        hr, hs, ms = self.history_ratios
+        history_active = self.check_step(step, is_history=True) and cfg.momentum_hist != 1
+
+        p = SonarStepParams()
+        hist_in, hist_state, hist_div = self.history_d, ops.HIST_PRESENT, 1.0
+        if hist_in is None:
+            born = self._initial_history(x, denoised, sigma, step=step)
+            if born is None:
+                hist_state = ops.HIST_NONE
+            else:
+                hist_in, hist_div = born
+                hist_in = hist_in.contiguous()
+                hist_state = ops.HIST_INIT
+        # Does this call leave a history behind? (update_hist assigns when it runs, or init did)
+        runs_second_update = cfg.momentum != 1 and cfg.momentum_mode != MomentumMode.DENOISED
+        keeps_history = hist_state != ops.HIST_NONE or history_active
+        x_out = torch.empty_like(x)
+        hist_out = None
+        if keeps_history:
+            # in place unless the incoming history aliases x / denoised (SAMPLE init)
+            hist_out = hist_in if hist_state == ops.HIST_PRESENT else torch.empty_like(x)
+        _ = runs_second_update
+
+        p.x, p.denoised, p.x_out = x.data_ptr(), denoised.data_ptr(), x_out.data_ptr()
+        p.hist_in = 0 if hist_in is None else hist_in.data_ptr()
+        p.hist_out = 0 if hist_out is None else hist_out.data_ptr()
+        p.n = x.numel()
+        p.kind, p.mode = kind, _MODE_IDS[cfg.momentum_mode]
+        p.momentum_blend = hostutil.blend_mode_id(self.momentum_blend)
+        p.history_blend = hostutil.blend_mode_id(self.history_blend)
+        p.hist_state = hist_state
+        p.momentum_active = int(self.check_step(step))
+        p.history_active = int(history_active)
+        p.momentum, p.sigma, p.c0, p.c1 = cfg.momentum, sigma, c0, c1
+        p.hd_ratio, p.hd_scale, p.md_scale = hr, hs, ms
+        p.hist_in_div = hist_div
+        p.noise_scale = noise_scale
+        p.noise_kind = ops.NOISE_NONE
+        live = [x, denoised, x_out, hist_in, hist_out]
+        if noise_philox is not None:
+            draw = noise_philox["draw"]
+            p.noise_kind = ops.NOISE_PHILOX_NORMALIZED if noise_philox["normalized"] else ops.NOISE_PHILOX
+            p.noise_factor = noise_philox["factor"]
+            p.noise_threshold_std_devs = 2.5
+            p.philox_seed, p.philox_offset, p.philox_grid_blocks = draw.seed, draw.offset, draw.grid_blocks
+            p.noise_begin, p.noise_numel_total = noise_philox["begin"], draw.numel
+            sums = noise_philox.get("sums")
+            p.noise_sums = 0 if sums is None else sums.data_ptr()
+            p.noise_count = noise_philox.get("count", 0)
+            live.append(sums)
+        elif noise_tensor is not None:
+            noise_tensor = noise_tensor.to(torch.float32).contiguous()
+            p.noise_kind = ops.NOISE_TENSOR
+            p.noise = noise_tensor.data_ptr()
+            live.append(noise_tensor)
+        ops.sonar_step(p, *live)
+        if keeps_history:
+            self.history_d = hist_out
+        return x_out
+
+    def momentum_step(self, step: int, x: Tensor, denoised: Tensor, sigma: float, sigma_down: float, **noise_kw) -> Tensor:
+        """x + momentum_d * (sigma_down - sigma) (:309-320), optionally with the ancestral noise fused in."""
+        dt = float(torch.tensor(sigma_down, dtype=torch.float32) - torch.tensor(sigma, dtype=torch.float32))
+        return self.fused_step(step, x, denoised, sigma, kind=ops.STEP_EULER, c0=dt, **noise_kw)
+
+    # ------------------------------------------------------------------------------------
+    # ancestral noise: fuse the default Gaussian, otherwise sample a tensor
+    # ------------------------------------------------------------------------------------
+    def ancestral_noise(self, x: Tensor, sigma: Tensor, sigma_next: Tensor, scale: float) -> dict:
+        """kwargs for fused_step that add noise_sampler(sigma, sigma_next) * scale."""
+        ns = self.noise_sampler
+        spec = ns.fused_gaussian() if hasattr(ns, "fused_gaussian") and not _rng_is_injected() else None
+        if spec is not None and tuple(spec[2]) == tuple(x.shape):
+            factor, normalized, _shape = spec
+            total, begin = parallel.global_draw_geometry(x.shape)
+            draw = ops.reserve_draw(total, x.device)
+            kw = {"draw": draw, "factor": factor, "normalized": normalized, "begin": begin}
+            if normalized:
+                sums = ops.new_sums(x.device)
+                ops.philox_normal_moments(draw, begin=begin, count=x.numel(), sums=sums)
+                kw["sums"] = sums
+                kw["count"] = parallel.global_count(x.numel(), sums)
+            return {"noise_philox": kw, "noise_scale": scale}
+        return {"noise_tensor": ns(sigma, sigma_next), "noise_scale": scale}
+
+
+def _rng_is_injected() -> bool:
+    from . import rng
+
+    return rng._INJECT is not None  # noqa: SLF001
+
+
+class SonarGuidanceMixin:
+    """Reference-latent guidance (:323-411). Ranked "next" in SURVEY.md section 8f: it runs as
+    device-side torch ops after the fused step, not yet fused into it."""
+
+    def __init__(self, cfg: GuidanceConfig | None = None) -> None:
+        self.guidance = cfg
+        self.ref_latent = self.prepare_ref_latent(cfg.latent) if cfg and cfg.latent is not None else None
+
+    @staticmethod
+    def prepare_ref_latent(latent: Tensor | None) -> Tensor | None:
+        if latent is None:
+            return None
+        avg = latent.mean(dim=(-2, -1), keepdim=True)
+        std = latent.std(dim=(-2, -1), keepdim=True)
+        return (latent - avg).div_(std).to(latent.dtype)
+
+    def guidance_step(self, step_index: int, x: Tensor, denoised: Tensor) -> Tensor:
+        g = self.guidance
+        if g is None or g.factor == 0.0 or not g.start_step <= step_index <= g.end_step:
+            return x
+        if self.ref_latent.device != x.device:
+            self.ref_latent = self.ref_latent.to(device=x.device)
+        if g.guidance_type == GuidanceType.LINEAR:
+            return self.guidance_linear(x, self.ref_latent, g.factor, blend=self.guidance_blend)
+        if g.guidance_type == GuidanceType.EULER:
+            return self.guidance_euler(
+                self.sigmas[step_index], self.sigmas[step_index + 1], x, denoised, self.ref_latent, g.factor,
+            )
+        raise ValueError("Sonar: Guidance: Unknown guidance type")
+
+    @classmethod
+    def guidance_shift(cls, t: Tensor, ref_latent: Tensor, *, dim=None) -> Tensor:
+        if dim is None:
+            dim = tuple(range(-(t.ndim - 1), 0))
+        return (ref_latent * t.std(dim=dim, keepdim=True)).add_(t.mean(dim=dim, keepdim=True))
+
+    @classmethod
+    def guidance_euler(cls, sigma, sigma_next, x, denoised, ref_latent, factor: float = 0.2, *, do_shift: bool = True):
+        if torch.equal(torch.as_tensor(sigma), torch.as_tensor(sigma_next)):
+            return cls.guidance_linear(x, ref_latent, factor=factor, do_shift=do_shift)
+        target = cls.guidance_shift(denoised, ref_latent) if do_shift else ref_latent
+        d = (x - target) / sigma
+        return (d * ((sigma_next - sigma) * factor)).add_(x)
+
+    @classmethod
+    def guidance_linear(cls, x, ref_latent, factor: float = 0.2, *, blend=None, do_shift: bool = True):
+        target = cls.guidance_shift(x, ref_latent) if do_shift else ref_latent
+        blend = hostutil.BLENDING_MODES["lerp"] if blend is None else blend
+        return blend(x.contiguous(), target.contiguous(), factor)
+
+
+class SonarWithGuidance(SonarBase, SonarGuidanceMixin):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        SonarGuidanceMixin.__init__(self, self.cfg.guidance)
+
+
+class SonarSampler(SonarWithGuidance):
+    def __init__(self, model, sigmas: Tensor, s_in: Tensor, extra_args: dict[str, Any], *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.model = model
+        self.sigmas = sigmas
+        self.s_in = s_in
+        self.extra_args = extra_args
+        # one device->host copy of the schedule for the whole run; per-step scalars come from here
+        self.sigmas_host = sigmas.detach().to(dtype=torch.float32, device="cpu")
+
+    def call_model(self, x: Tensor, sigma: Tensor, *args, s_in=None, extra_args=None) -> Tensor:
+        s_in = self.s_in if s_in is None else s_in
+        extra_args = self.extra_args if extra_args is None else self.extra_args | extra_args
+        return self.model(x, sigma * s_in, *args, **extra_args)
+
+    def run(self, x: Tensor, callback, disable) -> Tensor:
+        sigmas = self.sigmas
+        for i in trange(len(sigmas) - 1, disable=disable):
+            x, sigma, sigma_hat, denoised = self.step(i, x)
+            if callback is not None:
+                callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+        return x
+
+    @classmethod
+    def _build(cls, ctor_args: tuple, model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params):
+        sonar_config = cls.get_config(sonar_config, sonar_params)
+        s_in = x.new_ones((x.shape[0],))
+        sonar = cls(*ctor_args, model, sigmas, s_in, {} if extra_args is None else extra_args, sonar_config)
+        sonar.set_noise_sampler(x, sigmas, noise_sampler, seed=extra_args.get("seed"))
+        return sonar
+
+
+class SonarEuler(SonarSampler):
+    def step(self, step_index: int, sample: Tensor):
+        sigma = self.sigmas[step_index]
+        sigma_h, sigma_next_h = self.sigmas_host[step_index], self.sigmas_host[step_index + 1]
+        denoised = self.call_model(sample, sigma)
+        result = self.momentum_step(step_index, sample, denoised, sigma_h.item(), sigma_next_h.item())
+        if sigma_next_h > 0:
+            result = self.guidance_step(step_index, result, denoised)
+        return (result, sigma, sigma, denoised)
+
+    @classmethod
+    def sampler(
+        cls,
+        model,
+        x: Tensor,
+        sigmas: Tensor,
+        extra_args: dict | None = None,
+        callback=None,
+        disable: bool | None = None,  # noqa: FBT001
+        noise_sampler: Callable | None = None,
+        sonar_config: SonarConfig | None = None,
+        sonar_params: dict | None = None,
+    ) -> Tensor:
+        sonar = cls._build((), model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
+        return sonar.run(x, callback, disable)
+
+
+class SonarEulerAncestral(SonarSampler):
+    def __init__(self, eta: float = 1.0, s_noise: float = 1.0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.eta = eta
+        self.s_noise = s_noise
+
+    def step(self, step_index: int, sample: Tensor):
+        sigma = self.sigmas[step_index]
+        sigma_h, sigma_next_h = self.sigmas_host[step_index], self.sigmas_host[step_index + 1]
+        sigma_down, sigma_up = get_ancestral_step(sigma_h, sigma_next_h, eta=self.eta)
+        denoised = self.call_model(sample, sigma)
+        noise_kw = {}
+        add_noise = bool(sigma_next_h > 0)
+        guided = self.guidance is not None and self.guidance.factor != 0.0
+        if add_noise and not guided:
+            # x' = momentum_step(...) + noise * (s_noise * sigma_up): one launch
+            noise_kw = self.ancestral_noise(sample, sigma_h, sigma_next_h, float(self.s_noise * sigma_up))
+        result = self.momentum_step(step_index, sample, denoised, float(sigma_h), float(sigma_down), **noise_kw)
+        if add_noise and guided:
+            result = self.guidance_step(step_index, result, denoised)
+            drawn = self.noise_sampler(sigma_h, sigma_next_h)
+            result = ops.axpby(result.contiguous(), 1.0, drawn.contiguous(), float(self.s_noise * sigma_up))
+        return (result, sigma, sigma, denoised)
+
+    @classmethod
+    def sampler(
+        cls,
+        model,
+        x,
+        sigmas,
+        extra_args=None,
+        callback=None,
+        disable=None,
+        sonar_config: SonarConfig | None = None,
+        sonar_params: dict | None = None,
+        eta=1.0,
+        s_noise=1.0,
+        noise_sampler: Callable | None = None,
+    ):
+        sonar = cls._build((eta, s_noise), model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
+        return sonar.run(x, callback, disable)
+
+
+class SonarDPMPPSDE(SonarSampler):
+    """DPM-Solver++(SDE), r = 1/2, with momentum on both half steps (:626-770): two model
+    evaluations and two fused launches per step, four history updates."""
+
+    DEFAULT_NOISE_TYPE = noise.NoiseType.BROWNIAN
+
+    def __init__(self, eta: float = 1.0, s_noise: float = 1.0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.eta = eta
+        self.s_noise = s_noise
+
+    @staticmethod
+    def sigma_fn(t: Tensor) -> Tensor:
+        return t.neg().exp()
+
+    @staticmethod
+    def t_fn(sigma: Tensor) -> Tensor:
+        return sigma.log().neg()
+
+    def dpm_step(self, step_index: int, x: Tensor, denoised: Tensor, sigma_h: Tensor, sigma_next_h: Tensor) -> Tensor:
+        # host float32 scalars, same op sequence as the reference (:669-719)
+        r = 1 / 2
+        t, t_next = self.t_fn(sigma_h), self.t_fn(sigma_next_h)
+        h = t_next - t
+        s = t + h * r
+        s_t, s_s = self.sigma_fn(t), self.sigma_fn(s)
+        sd, su = get_ancestral_step(s_t, s_s, self.eta)
+        s_ = self.t_fn(sd)
+        guided = self.guidance is not None and self.guidance.factor != 0.0
+
+        # ---- stage 1: x_2 = (sigma_fn(s_)/s_t) * x - momentum(expm1(t - s_) * denoised) + noise ----
+        noise_kw = self.ancestral_noise(x, s_t, s_s, float(self.s_noise * su))
+        x_2 = self.fused_step(
+            step_index, x, denoised, float(sigma_h),
+            kind=ops.STEP_DPMPP, c0=float((t - s_).expm1()), c1=float(self.sigma_fn(s_) / s_t), **noise_kw,
+        )  # fmt: skip
+        sigma_2 = s_s
+        denoised_2 = self.call_model(x_2, sigma_2.to(self.sigmas.device))
+
+        # ---- stage 2 (fac = 1/(2r) = 1: denoised_d = 0*md1 + 1*md2) ----
+        s_t_next = self.sigma_fn(t_next)
+        sd, su = get_ancestral_step(s_t, s_t_next, self.eta)
+        t_down = self.t_fn(sd)
+        if guided:
+            out = self.fused_step(
+                step_index, x, denoised_2, float(sigma_2),
+                kind=ops.STEP_DPMPP, c0=float((t - t_down).expm1()), c1=float(self.sigma_fn(t_down) / s_t),
+            )  # fmt: skip
+            out = self.guidance_step(step_index, out, denoised_2)
+            drawn = self.noise_sampler(s_t, s_t_next)
+            return ops.axpby(out.contiguous(), 1.0, drawn.contiguous(), float(self.s_noise * su))
+        noise_kw = self.ancestral_noise(x, s_t, s_t_next, float(self.s_noise * su))
+        return self.fused_step(
+            step_index, x, denoised_2, float(sigma_2),
+            kind=ops.STEP_DPMPP, c0=float((t - t_down).expm1()), c1=float(self.sigma_fn(t_down) / s_t), **noise_kw,
+        )  # fmt: skip
+
+    def step(self, step_index: int, sample: Tensor):
+        sigma = self.sigmas[step_index]
+        sigma_h, sigma_next_h = self.sigmas_host[step_index], self.sigmas_host[step_index + 1]
+        denoised = self.call_model(sample, sigma)
+        if sigma_next_h == 0:
+            sigma_down, _ = get_ancestral_step(sigma_h, sigma_next_h, eta=self.eta)
+            result = self.momentum_step(step_index, sample, denoised, float(sigma_h), float(sigma_down))
+        else:
+            result = self.dpm_step(step_index, sample, denoised, sigma_h, sigma_next_h)
+        return (result, sigma, sigma, denoised)
+
+    @classmethod
+    def sampler(
+        cls,
+        model,
+        x: Tensor,
+        sigmas: Tensor,
+        extra_args: dict | None = None,
+        callback=None,
+        disable: bool | None = None,  # noqa: FBT001
+        sonar_config: SonarConfig | None = None,
+        sonar_params: dict | None = None,
+        eta=1.0,
+        s_noise=1.0,
+        noise_sampler=None,
+    ) -> Tensor:
+        sonar = cls._build((eta, s_noise), model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
+        return sonar.run(x, callback, disable)
+
+
+EXTRA_SAMPLERS = {
+    "sonar_euler": SonarEuler.sampler,
+    "sonar_euler_ancestral": SonarEulerAncestral.sampler,
+    "sonar_dpmpp_sde": SonarDPMPPSDE.sampler,
+}
+
+
+def add_samplers() -> None:
+    """Registers the three samplers with ComfyUI (reference :823-847). Needs `comfy` importable."""
+    from comfy.samplers import KSampler, k_diffusion_sampling
+
+    added = 0
+    for name, fn in EXTRA_SAMPLERS.items():
+        if name in KSampler.SAMPLERS:
+            continue
+        try:
+            KSampler.SAMPLERS.append(name)
+            setattr(k_diffusion_sampling, f"sample_{name}", fn)
+            added += 1
+        except ValueError as exc:
+            print(f"Sonar: Failed to add {name} to built in samplers list: {exc}")
+    if added > 0:
+        importlib.reload(k_diffusion_sampling)

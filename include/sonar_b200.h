@@ -1,0 +1,316 @@
+/*
+ * sonar_b200 -- C ABI of libsonar_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (blepping/ComfyUI-sonar) is pure Python on eager PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b): the drop-in boundary is the ComfyUI node surface, kept in Python by the
+ * package `comfyui-sonar_b200/`. This header is the NEW seam underneath that surface: each entry
+ * point replaces a group of eager ATen passes in the reference, cited as file:line below.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - tensors are dense, row-major (NCHW / planes x H x W), fp32 unless the name says f64;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, otherwise the cudaError_t of the failed call / launch
+ *     (cudaErrorInvalidValue == 1 for argument errors). No exceptions, no global state.
+ *   - there is NO CPU fallback behind any of these symbols.
+ */
+#ifndef SONAR_B200_H_
+#define SONAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONAR_B200_ABI_VERSION 1
+int sonar_abi_version(void);
+/* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
+ * statically; one process per GPU normally makes this a no-op). */
+int sonar_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Philox generators, bit-exact with torch.randn / torch.rand / Tensor.uniform_ on CUDA.
+ * replaces: NoiseGenerator.rand_like                       py/noise_generation.py:133-155
+ *           torch.randn in PyramidNoiseGenerator.generate  py/noise_generation.py:632-640
+ *           Tensor.uniform_ in perlin_noise                py/noise_generation.py:465-469
+ *           complex64 torch.randn in PowerNoiseItem        py/nodes/powernoise.py:396-401
+ * mirrors : ATen/native/cuda/DistributionTemplates.h:50-82 (launch policy and element mapping)
+ *
+ * A draw of `numel_total` elements is identified by (seed, offset, grid_blocks) where offset is the
+ * torch CUDA generator's philox offset BEFORE the draw and grid_blocks comes from
+ * sonar_philox_policy(). [begin, begin+count) selects a slice of the flattened draw (batch
+ * sharding); out[0] receives element `begin`. A complex64 randn is a float normal draw over
+ * 2*numel floats with std = 1/sqrt(2) (interleaved re, im).
+ * ---------------------------------------------------------------------------------------------- */
+int sonar_philox_policy(int64_t numel, uint32_t* grid_blocks_host, uint64_t* counter_offset_host);
+int sonar_philox_normal_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                            uint64_t offset, uint32_t grid_blocks, float mean, float std, void* stream);
+int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                             uint64_t offset, uint32_t grid_blocks, float from, float to, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Global moments and scale_noise.
+ * replaces: scale_noise                                    py/utils.py:85-106
+ *           chain accumulation + normalisation             py/noise.py:189-194
+ * `sums` is double[2] = {sum, sum of squares}; the kernels ACCUMULATE into it (zero it first),
+ * so a batch-sharded run can all-reduce the two doubles between the moments pass and the apply
+ * pass. `count` is the GLOBAL element count the sums cover. `out` may alias `x`.
+ * ---------------------------------------------------------------------------------------------- */
+int sonar_moments_f32(const float* x, int64_t n, double* sums, void* stream);
+int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_total, uint64_t seed, uint64_t offset,
+                                uint32_t grid_blocks, double* sums, void* stream);
+int sonar_scale_noise_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float factor,
+                          float threshold_std_devs, void* stream);
+int sonar_add_moments_f32(const float* a, const float* b, float* out, int64_t n, double* sums, void* stream);
+/* out = x * (scale / unbiased_std) -- GreenTestNoiseGenerator.generate, py/noise_generation.py:703 */
+int sonar_scale_by_std_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float scale,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused Sonar momentum step.
+ * replaces: SonarBase.update_hist/momentum_mix/get_momentum_denoised/get_momentum_d/momentum_step
+ *                                                          py/sonar.py:227-320
+ *           SonarEuler.step / SonarEulerAncestral.step     py/sonar.py:460-480, :541-573
+ *           SonarDPMPPSDE.momentum_step (each half step)   py/sonar.py:649-735
+ * ---------------------------------------------------------------------------------------------- */
+enum { SONAR_STEP_EULER = 0, SONAR_STEP_DPMPP = 1 };
+enum { SONAR_MODE_CLASSIC = 0, SONAR_MODE_NEW = 1, SONAR_MODE_DENOISED = 2 };
+enum { SONAR_BLEND_LERP = 0, SONAR_BLEND_INJECT = 1, SONAR_BLEND_SUBTRACT_B = 2 };
+/* history at entry: none (first step, ZERO init) / present / initialised by this very call
+ * (SAMPLE, SAMPLE_NORM, RAND init: used by the updates but not by the first momentum mix,
+ * py/sonar.py:272-282) */
+enum { SONAR_HIST_NONE = 0, SONAR_HIST_PRESENT = 1, SONAR_HIST_INIT = 2 };
+enum {
+  SONAR_NOISE_NONE = 0,
+  SONAR_NOISE_TENSOR = 1,            /* noise read from `noise` */
+  SONAR_NOISE_PHILOX = 2,            /* torch.randn(device='cuda') regenerated in registers */
+  SONAR_NOISE_PHILOX_NORMALIZED = 3  /* ... followed by scale_noise from `noise_sums` */
+};
+
+typedef struct SonarStepParams {
+  const float* x;        /* sample at sigma                                   */
+  const float* denoised; /* model output                                      */
+  const float* hist_in;  /* history_d, may alias hist_out; NULL if HIST_NONE  */
+  const float* noise;    /* SONAR_NOISE_TENSOR only                           */
+  float* x_out;          /* must not alias x                                  */
+  float* hist_out;       /* NULL: do not store the history                    */
+  int64_t n;             /* elements in this (local) tensor                   */
+
+  int32_t kind;            /* SONAR_STEP_*                                     */
+  int32_t mode;            /* SONAR_MODE_*                                     */
+  int32_t momentum_blend;  /* SONAR_BLEND_*                                    */
+  int32_t history_blend;   /* SONAR_BLEND_*                                    */
+  int32_t hist_state;      /* SONAR_HIST_*                                     */
+  int32_t momentum_active; /* check_step(step)                                 */
+  int32_t history_active;  /* check_step(step, is_history) && momentum_hist!=1 */
+  int32_t noise_kind;      /* SONAR_NOISE_*                                    */
+
+  float momentum;
+  float sigma;       /* sigma the denoised was evaluated at                   */
+  float c0;          /* EULER: dt = sigma_down - sigma; DPMPP: expm1(t - s)   */
+  float c1;          /* DPMPP: sigma_fn(s) / sigma_fn(t); unused for EULER    */
+  float hd_ratio;    /* history_ratios, py/sonar.py:208-219                   */
+  float hd_scale;
+  float md_scale;
+  float hist_in_div; /* history = hist_in / hist_in_div (SAMPLE_NORM init)    */
+  float noise_scale; /* s_noise * sigma_up                                    */
+  float noise_factor;            /* factor applied by scale_noise (philox kinds) */
+  float noise_threshold_std_devs;
+
+  /* Philox noise: the draw torch.randn(x.shape) would make, this tensor = slice at noise_begin */
+  uint64_t philox_seed;
+  uint64_t philox_offset;
+  uint32_t philox_grid_blocks;
+  int64_t noise_begin;
+  int64_t noise_numel_total;
+  const double* noise_sums; /* double[2], PHILOX_NORMALIZED */
+  int64_t noise_count;      /* global count behind noise_sums */
+} SonarStepParams;
+
+int sonar_step_f32(const SonarStepParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pyramid family: fused multi-level resample-and-accumulate.
+ *   out[p,y,x] = base_scale*base[p,y,x] + sum_i weights[i] * resample(levels[i][p] -> HxW)[y,x]
+ * replaces: PyramidNoiseGenerator.generate                 py/noise_generation.py:621-649
+ *           HighresPyramidNoiseGenerator.generate          py/noise_generation.py:539-564
+ *           PyramidOldNoiseGenerator.generate              py/noise_generation.py:579-606
+ *           utils.scale_samples -> common_upscale          py/utils.py:58-67
+ * Level tensors are (planes, level_h, level_w); level sizes are decided on the host from the CPU
+ * generator draws exactly as the reference does (:627-630). `base` may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+#define SONAR_PYRAMID_MAX_LEVELS 16
+enum { SONAR_RESAMPLE_BILINEAR = 0, SONAR_RESAMPLE_NEAREST_EXACT = 1, SONAR_RESAMPLE_AREA = 2 };
+
+typedef struct SonarPyramidParams {
+  float* out;
+  const float* base;
+  const float* levels[SONAR_PYRAMID_MAX_LEVELS];
+  int32_t level_h[SONAR_PYRAMID_MAX_LEVELS];
+  int32_t level_w[SONAR_PYRAMID_MAX_LEVELS];
+  float weights[SONAR_PYRAMID_MAX_LEVELS];
+  int64_t planes;
+  int32_t H;
+  int32_t W;
+  int32_t n_levels;
+  int32_t mode; /* SONAR_RESAMPLE_* */
+  float base_scale;
+} SonarPyramidParams;
+
+int sonar_pyramid_accum_f32(const SonarPyramidParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Perlin (grid cell == one pixel): out[b,c,y,x] = base[b,c,y,x]/div_fac + sum_it stencil(angles[it][c])[y,x]
+ * replaces: PerlinOldNoiseGenerator.generate/perlin_noise/perlin_noise_tensor
+ *                                                          py/noise_generation.py:353-493
+ * angles[it] is (C, H+1, W+1) uniform in [0, 2pi); the stencil is shared by all B batch items.
+ * ---------------------------------------------------------------------------------------------- */
+#define SONAR_PERLIN_MAX_ITERS 8
+typedef struct SonarPerlinParams {
+  float* out;
+  const float* base; /* (B,C,H,W) uniform [0,1); NULL = zeros */
+  const float* angles[SONAR_PERLIN_MAX_ITERS];
+  int32_t B;
+  int32_t C;
+  int32_t H;
+  int32_t W;
+  int32_t iterations;
+  int32_t blend_mode; /* SONAR_BLEND_* */
+  float div_fac;
+} SonarPerlinParams;
+
+int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise combinators.
+ * replaces: BLENDING_MODES                                 py/utils.py:17-21
+ *           BlendedNoise noise_sampler                     py/noise.py:1391-1405
+ *           CompositeNoise noise_sampler                   py/noise.py:524-531
+ *           MixedNoiseGenerator.generate accumulate        py/noise_generation.py:240-249
+ *           PowerLawNoiseGenerator.generate                py/noise_generation.py:775-786
+ *           normalize_to_scale                             py/utils.py:452-470
+ * blend: out = mode(a, b, t) with t = t_tensor[i] if t_tensor else t_scalar. `out` may alias a or b.
+ * axpby: out = a*alpha + b*beta (b may be NULL).
+ * composite: out = dst*(1-mask) + src*mask, mask (batch,1,H,W) broadcast over channels.
+ * item_*: reductions over everything but the leading dim; scratch from sonar_item_range_scratch_bytes.
+ * ---------------------------------------------------------------------------------------------- */
+int sonar_blend_f32(const float* a, const float* b, const float* t_tensor, float t_scalar, float* out, int64_t n,
+                    int mode, void* stream);
+int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, void* stream);
+/* out = ((x + pre_add) * mul) + post_add, each step rounded (UniformNoiseGenerator.generate,
+ * py/noise_generation.py:508-514) */
+int sonar_affine_f32(const float* x, float* out, int64_t n, float pre_add, float mul, float post_add, void* stream);
+int sonar_composite_f32(const float* dst, const float* src, const float* mask, float* out, int64_t batch,
+                        int64_t channels, int64_t hw, void* stream);
+int sonar_powerlaw_f32(const float* x, float* out, int64_t n, float alpha, int use_sign, void* stream);
+int sonar_item_range_scratch_bytes(int64_t items);
+int sonar_item_div_max_f32(const float* x, float* out, int64_t items, int64_t per_item, int use_abs, void* scratch,
+                           void* stream);
+int sonar_item_minmax_rescale_f32(const float* x, float* out, int64_t items, int64_t per_item, float target_min,
+                                  float target_max, float eps, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral shaping: [rfft2 ->] gain mask -> irfft2, one CTA per (H, W) plane, spectrum resident in
+ * shared memory (or in `scratch` when H*(W/2+1) complex64 exceeds it).
+ * replaces: PowerNoiseItem sampler (irfft2 of a shaped half spectrum, optional rfft2 front end)
+ *                                                          py/nodes/powernoise.py:355-366
+ *           OneFNoiseGenerator.generate (fftn -> gain -> ifftn.real)
+ *                                                          py/noise_generation.py:737-759
+ *           GreenTestNoiseGenerator.generate               py/noise_generation.py:694-704
+ *           FreeU-Extreme ffilter (same op, "next" caller) py/nodes/freeu_extreme.py:10-29
+ * Exactly one of in_real (planes,H,W) / in_spec (planes,H,W/2+1 complex64, interleaved) is set.
+ * mask is a real (H, W/2+1) gain shared by all planes (NULL = 1). out = out_scale * result:
+ * 1/sqrt(H*W) for an "ortho" irfft2 alone, 1/(H*W) for a forward+inverse round trip.
+ * H and W may be any positive sizes (mixed radix 4/2 + direct prime radices).
+ * ---------------------------------------------------------------------------------------------- */
+#define SONAR_FFT_MAX_FACTORS 24
+typedef struct SonarSpectralParams {
+  float* out;
+  const float* in_real;
+  const float* in_spec; /* complex64 as interleaved (re, im) */
+  const float* mask;
+  float* scratch;       /* sonar_spectral_scratch_bytes(H, W) bytes, may be NULL when that is 0 */
+  int64_t planes;
+  int32_t H;
+  int32_t W;
+  float out_scale;
+} SonarSpectralParams;
+
+int64_t sonar_spectral_scratch_bytes(int H, int W);
+int sonar_spectral_filter_f32(const SonarSpectralParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2-D DWT levels + wavelet-CFG combine.
+ * replaces: Wavelet.forward / Wavelet.inverse               py/wavelet_functions.py:81-105
+ *             (-> pytorch_wavelets.DWTForward / DWTInverse, [upstream], restated)
+ *           wavelet_scaling / wavelet_blend                 py/wavelet_functions.py:193-238
+ *           WaveletCFG.wavelet_cfg / process_output         py/wavelet_cfg.py:729-791
+ * One analysis call = one decomposition level: in (planes,H,W) -> ll (planes,h,w) and
+ * hi (planes,3,h,w) with h = (H+L-1)/2. in_b (optional) is subtracted on load, so level 1 can
+ * transform (cond - uncond) straight from the fp32 inputs (in_is_f32). Coefficients are fp64
+ * (use_f64, the reference's high_precision_mode default) or fp32.
+ * One synthesis call = one reconstruction level over 1 or 2 coefficient sets, each band multiplied
+ * by scales[set][ll, hi0, hi1, hi2] on load. Intermediate levels write `out` (planes, 2h-L+2,
+ * 2w-L+2) in the coefficient type; the final level writes fp32 `out_f32` cropped to
+ * (crop_h, crop_w):  out_f32 = x_scale*x + (float)(recon_sign*(recon + addend_scale*addend)).
+ * ---------------------------------------------------------------------------------------------- */
+#define SONAR_DWT_MAX_TAPS 40
+enum { SONAR_DWT_MODE_SYMMETRIC = 0, SONAR_DWT_MODE_ZERO = 1, SONAR_DWT_MODE_REFLECT = 2, SONAR_DWT_MODE_PERIODIC = 3 };
+
+typedef struct SonarWaveletFilters {
+  int32_t length;
+  double dec_lo[SONAR_DWT_MAX_TAPS];
+  double dec_hi[SONAR_DWT_MAX_TAPS];
+  double rec_lo[SONAR_DWT_MAX_TAPS];
+  double rec_hi[SONAR_DWT_MAX_TAPS];
+} SonarWaveletFilters;
+
+typedef struct SonarDwtAnalysisParams {
+  const void* in_a;
+  const void* in_b; /* optional, subtracted */
+  void* ll;
+  void* hi;
+  int64_t planes;
+  int32_t H;
+  int32_t W;
+  int32_t in_stride_h; /* rows per plane of the input buffer (>= H; 0 = H); row length is W */
+  int32_t h;
+  int32_t w;
+  int32_t mode;      /* SONAR_DWT_MODE_* */
+  int32_t in_is_f32; /* inputs are fp32 tensors (level 1) */
+  int32_t use_f64;
+  SonarWaveletFilters filters;
+} SonarDwtAnalysisParams;
+
+typedef struct SonarDwtSynthesisParams {
+  const void* ll[2];
+  const void* hi[2];
+  int32_t ll_rows[2]; /* actual rows / cols of the ll buffers (>= h, w) */
+  int32_t ll_cols[2];
+  double scales[2][4];
+  int32_t n_sets;
+  int64_t planes;
+  int32_t h;
+  int32_t w;
+  void* out;      /* intermediate level output, coefficient type */
+  float* out_f32; /* final level output */
+  int32_t crop_h;
+  int32_t crop_w;
+  const float* addend;
+  float addend_scale;
+  const float* x;
+  float x_scale;
+  float recon_sign;
+  int32_t use_f64;
+  SonarWaveletFilters filters;
+} SonarDwtSynthesisParams;
+
+int sonar_dwt_coeff_len(int n, int filter_len);
+int sonar_dwt2_analysis(const SonarDwtAnalysisParams* params_host, void* stream);
+int sonar_dwt2_synthesis(const SonarDwtSynthesisParams* params_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONAR_B200_H_ */
