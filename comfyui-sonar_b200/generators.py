@@ -281,7 +281,7 @@ class PyramidNoiseGenerator(_PyramidBase):
         sizes = []
         host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
         for i in range(self.iterations):
-            r = torch.rand(1, generator=host_gen).cpu().item() * 2 + 2
+            r = rng.host_rand(1, host_gen).item() * 2 + 2
             w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
             sizes.append((h, w))
             if w == 1 or h == 1:
@@ -324,7 +324,7 @@ class HighresPyramidNoiseGenerator(_PyramidBase):
         orig_h, orig_w = h, w
         base = self.noise_generator(s, sn).reshape(*adjusted)
         host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
-        rs = torch.rand(self.iterations, dtype=torch.float32, generator=host_gen).cpu() * 2 + 2
+        rs = rng.host_rand(self.iterations, host_gen) * 2 + 2
         levels, weights = [], []
         for i in range(self.iterations):
             r = rs[i].item()

@@ -97,3 +97,12 @@ def uniform(
             shape, device=device, generator=generator, low=low, high=high, batch_sharded=batch_sharded,
         ).to(dtype)
     return _fill(shape, device, dtype, generator, "uniform", float(low), float(high), batch_sharded)
+
+
+def host_rand(n: int, generator: torch.Generator | None = None) -> torch.Tensor:
+    """torch.rand(n) on the CPU generator -- the host draws that size pyramid levels
+    (reference py/noise_generation.py:544-552, :627-629). Injectable like the device draws."""
+    inj = _take_injected((n,), torch.device("cpu"), torch.float32)
+    if inj is not None:
+        return inj
+    return torch.rand(n, dtype=torch.float32, generator=generator)
