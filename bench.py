@@ -1,0 +1,550 @@
+"""Benchmark of the sonar_b200 hot path (driver contract: ONE JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): sonar_euler_ancestral -- Sonar momentum step fused with
+Gaussian ancestral noise -- on SDXL latents 8x4x128x128, 30 sampler steps, defaults (momentum 0.95,
+history 0.75, NEW mode, eta 1, s_noise 1); denoiser stub x*0.9 outside the timed regions.
+One bench "step" = one 30-step sampling run over one batch. Metric: latent noise elements / second
+(elements = 30 x 524,288 per batch).
+
+* value     : device-resident throughput. Every sampler step's kernels (Philox moments pre-pass + fused
+              step) are bracketed by CUDA events on the launching stream; between sampler steps the
+              stub denoiser runs and L2 is flushed (256 MiB write), as a real UNet call would do.
+              ms_per_step = sum of those 30 event intervals, max over ranks.
+* e2e       : the same run through the public sampler function with HOST buffers: pinned x0 -> H2D,
+              30 steps, result D2H, wall clock between device synchronisations.
+* roofline  : dominant kernel (sonar_step_philox_kernel): algorithmic bytes per launch
+              (20 B/element: read x, denoised, history; write x', history'; noise regenerated in
+              registers) / CUDA-event duration of that launch, against MEASURED_PEAKS.json hbm_gbs.
+* cpu_baseline : the CPU oracle port of the reference algorithm (oracle/sonar_oracle.py) on the host
+              cores, same workload, bounded sample.
+* N > 1     : weak scaling by batch: every rank holds 8 latents of a global batch of 8N; the global
+              scale_noise statistics are all-reduced (2 doubles, NCCL) per sampler step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+SHAPE = (8, 4, 128, 128)
+N_SAMPLER_STEPS = 30
+ELEMS_PER_RUN = N_SAMPLER_STEPS * SHAPE[0] * SHAPE[1] * SHAPE[2] * SHAPE[3]
+STEP_BYTES_PER_ELEM = 20  # x, denoised, hist in; x', hist' out (fp32); Philox noise costs no HBM bytes
+WORKLOAD = "C2 sonar_euler_ancestral, SDXL latents 8x4x128x128, 30 steps, fused Gaussian noise"
+
+
+def make_sigmas() -> torch.Tensor:
+    return torch.cat((torch.linspace(14.6, 0.03, N_SAMPLER_STEPS), torch.zeros(1)))
+
+
+def measured_peak() -> tuple[float, str]:
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, sm_max, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(sm_max) if sm_max else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(n_runs: int, sampler_steps: int = N_SAMPLER_STEPS) -> dict:
+    """Times oracle.SonarOracle.euler_ancestral + CPU Gaussian noise + scale_noise (what the
+    reference's SonarEulerAncestral.step does on CPU, py/sonar.py:541-573), all host threads."""
+    from oracle import sonar_oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sigmas = make_sigmas()
+    torch.manual_seed(0)
+    x0 = torch.randn(SHAPE) * sigmas[0]
+    times = []
+    for _ in range(n_runs):
+        o = orc.SonarOracle()
+        x = x0.clone()
+        den = x * 0.9
+        t_run = 0.0
+        for i in range(sampler_steps):
+            t0 = time.perf_counter()
+            noise = orc.scale_noise(torch.randn(SHAPE), 1.0, normalized=True) if sigmas[i + 1] > 0 else None
+            x = o.euler_ancestral(i, x, den, sigmas[i], sigmas[i + 1], noise)
+            t_run += time.perf_counter() - t0
+            den = x * 0.9  # denoiser stub, untimed
+        times.append(t_run)
+    best = min(times)
+    elems = sampler_steps * x0.numel()
+    return {
+        "value": elems / best,
+        "unit": "elements/s",
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{n_runs} x {sampler_steps} sampler steps of C2 on CPU (oracle port, best run, stub denoiser untimed)",
+        "ms_per_step": best * 1e3 * (N_SAMPLER_STEPS / sampler_steps),
+    }
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    for _ in range(args.warmup):
+        cpu_reference_run(1, sampler_steps=10)
+    res = cpu_reference_run(max(1, args.steps))
+    line = {
+        "impl": "reference",
+        "metric": "latent noise elements/sec",
+        "value": res["value"],
+        "unit": "elements/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "where": "host CPU", "threads": res["cores"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+class StepTimer:
+    """Denoiser stub that doubles as the boundary of the timed regions: everything the sampler
+    enqueues between two model calls is the hot path of one sampler step."""
+
+    def __init__(self, device, flush_bytes: int = 256 << 20, timed: bool = True):
+        self.flush = torch.empty(flush_bytes, dtype=torch.uint8, device=device) if flush_bytes else None
+        self.timed = timed
+        self.pairs: list[tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        self._open: torch.cuda.Event | None = None
+
+    def close(self):
+        if self._open is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            self.pairs.append((self._open, end))
+            self._open = None
+
+    def __call__(self, x, sigma, **_kw):
+        if self.timed:
+            self.close()
+        if self.flush is not None:
+            self.flush.zero_()  # evicts L2, like the UNet forward that sits here in real use
+        den = x * 0.9
+        if self.timed:
+            self._open = torch.cuda.Event(enable_timing=True)
+            self._open.record()
+        return den
+
+    def total_ms(self) -> float:
+        return sum(a.elapsed_time(b) for a, b in self.pairs)
+
+
+def sampler_run(sb, model, x0, sigmas):
+    return sb.samplers.SonarEulerAncestral.sampler(model, x0, sigmas, extra_args={"seed": 0}, disable=True)
+
+
+def run_b200_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; sonar_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import sonar_b200 as sb
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sigmas_host = make_sigmas()
+    sigmas = sigmas_host.to(dev)
+    torch.manual_seed(1234 + rank)
+    x0 = torch.randn(SHAPE, device=dev) * sigmas_host[0]
+    x0_host = x0.cpu().pin_memory()
+    global_batch = SHAPE[0] * world
+
+    def one_run(model, src):
+        torch.manual_seed(99)  # replicated generator: every rank reserves the same global draws
+        if world > 1:
+            with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
+                return sampler_run(sb, model, src, sigmas)
+        return sampler_run(sb, model, src, sigmas)
+
+    # ---------------- device-resident throughput ----------------
+    warm_model = StepTimer(dev, timed=False)
+    for _ in range(max(3, args.warmup)):
+        one_run(warm_model, x0)
+    barrier()
+    launches0 = sb.ops.LAUNCH_COUNT
+    timers = []
+    with ClockSampler(local_rank) as clocks:
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            timer = StepTimer(dev)
+            one_run(timer, x0)
+            timer.close()
+            timers.append(timer)
+        barrier()
+        wall = time.perf_counter() - t_wall
+        # keep the sampler busy long enough for a few clock samples
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            one_run(warm_model, x0)
+        torch.cuda.synchronize()
+    launches = sb.ops.LAUNCH_COUNT - launches0
+    run_ms = [t.total_ms() for t in timers]
+    ms_per_step = statistics.mean(run_ms)
+    t_dev = torch.tensor([ms_per_step], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_dev.item())
+    value = ELEMS_PER_RUN * world / (ms_per_step * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (per-launch CUDA events) ----------------
+    sb.ops.TRACE = []
+    timer = StepTimer(dev, timed=False)
+    for _ in range(3):
+        one_run(timer, x0)
+    torch.cuda.synchronize()
+    per_kernel: dict[str, list[float]] = {}
+    for name, a, b in sb.ops.TRACE:
+        per_kernel.setdefault(name, []).append(a.elapsed_time(b) * 1e3)  # us
+    sb.ops.TRACE = None
+    step_us = statistics.mean(per_kernel["sonar_step_f32"])
+    peak, peak_src = measured_peak()
+    algo_bytes = STEP_BYTES_PER_ELEM * x0.numel()
+    achieved = algo_bytes / (step_us * 1e-6) / 1e9
+    traffic_path = REPO / "profiles" / "traffic.json"
+    traffic = None
+    if traffic_path.exists():
+        traffic = json.loads(traffic_path.read_text()).get("sonar_step_philox_kernel")
+    roofline = {
+        "bound": "hbm",
+        "kernel": "sonar_step_philox_kernel",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": traffic,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": algo_bytes,
+        "launch_us": step_us,
+        "kernel_us": {k: statistics.mean(v) for k, v in per_kernel.items()},
+    }
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    e2e_times = []
+    e2e_model = StepTimer(dev, flush_bytes=0, timed=False)
+    for i in range(3 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        x_dev = x0_host.to(dev, non_blocking=True)
+        out = one_run(e2e_model, x_dev)
+        if world > 1:
+            with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
+                out = sb.parallel.gather(out, dst=0)
+        out_host = out.to("cpu") if out is not None else None
+        torch.cuda.synchronize()
+        if i >= 3:
+            e2e_times.append(time.perf_counter() - t0)
+        del out_host
+    e2e_s = statistics.mean(e2e_times)
+    t_dev = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_dev.item())
+    bytes_x = x0.numel() * 4
+    e2e = {
+        "value": ELEMS_PER_RUN * world / e2e_s,
+        "unit": "elements/s",
+        "h2d_bytes_per_step": bytes_x + sigmas.numel() * 0,
+        "d2h_bytes_per_step": bytes_x * (world if rank == 0 else 1),
+        "ms_per_step": e2e_s * 1e3,
+        "note": "public sampler function, pinned host x0 -> H2D, 30 steps (stub denoiser inside), result D2H"
+        + (" after NCCL gather to rank 0" if world > 1 else ""),
+    }
+
+    extras = None
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            extras = run_extras(sb, dev, peak)
+        cpu = cpu_reference_run(3)
+        cpu_baseline = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "latent noise elements/sec",
+            "value": value,
+            "unit": "elements/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD,
+                "global_batch": global_batch,
+                "per_gpu_shape": list(SHAPE),
+                "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
+                "l2": "256 MiB flush between sampler steps (where the UNet runs); stub denoiser untimed",
+                "timing": "sum of 30 CUDA-event intervals per run (Philox moments pre-pass + fused step), max over ranks",
+            },
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "wall_s_timed_region": wall,
+            "runs_ms": run_ms,
+        }
+        if extras is not None:
+            line["other_configs"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (single GPU): elements/s and roofline fraction of the top kernel
+# ---------------------------------------------------------------------------------------------
+def _time_traced(sb, fn, reps: int, flush: torch.Tensor) -> tuple[float, dict]:
+    """Mean total kernel time (us) and per-kernel means over `reps` traced invocations."""
+    for _ in range(3):
+        fn()
+    totals, per = [], {}
+    for _ in range(reps):
+        flush.zero_()
+        sb.ops.TRACE = []
+        fn()
+        torch.cuda.synchronize()
+        trace, sb.ops.TRACE = sb.ops.TRACE, None
+        tot = 0.0
+        for name, a, b in trace:
+            us = a.elapsed_time(b) * 1e3
+            per.setdefault(name, []).append(us)
+            tot += us
+        totals.append(tot)
+    return statistics.mean(totals), {k: statistics.mean(v) * (len(v) / reps) for k, v in per.items()}
+
+
+def run_extras(sb, dev, peak: float) -> list[dict]:
+    import math
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+
+    def record(name, elems, algo_bytes_per_elem, total_us, per, note):
+        top = max(per, key=per.get)
+        out.append(
+            {
+                "config": name,
+                "elements": elems,
+                "kernel_us": total_us,
+                "elements_per_s": elems / (total_us * 1e-6),
+                "algorithmic_bytes_per_element": algo_bytes_per_elem,
+                "hbm_gbs": elems * algo_bytes_per_elem / (total_us * 1e-6) / 1e9,
+                "frac_of_measured_peak": elems * algo_bytes_per_elem / (total_us * 1e-6) / 1e9 / peak,
+                "top_kernel": top,
+                "per_kernel_us": per,
+                "note": note,
+            },
+        )
+
+    # C1: SonarPowerNoise pink on 1x4x64x64 (RNG draw of the half spectrum + irfft2 + normalisation)
+    ng, sn = sb.noise_graph, sb.spectral_noise
+    power_kw = dict(time_brownian=False, alpha=1.0, max_freq=0.7071, min_freq=0.0, stretch=1.0, rotate=0.0, pnorm=2.0,
+                    mix=1.0, common_mode=0.0, channel_correlation="1, 1, 1, 1, 1, 1")  # fmt: skip
+
+    def power_chain():
+        c = ng.CustomNoiseChain()
+        c.add(sn.PowerNoiseItem(1.0, **power_kw))
+        return c
+
+    x = torch.zeros(1, 4, 64, 64, device=dev)
+    ns = power_chain().make_noise_sampler(x, None, None, seed=0)
+    us, per = _time_traced(sb, lambda: ns(None, None), 10, flush)
+    record("C1 SonarPowerNoise pink 1x4x64x64", x.numel(), 8.125 + 8.125 + 12, us, per,
+           "bytes: spectrum write+read 2x8.125, irfft2 write 4, moments read 4, scale r/w... (see DESIGN.md)")
+
+    # C3: Scheduled(Blended(lerp .5, pyramid, perlin), fallback gaussian) on 16x16x128x128
+    def chain_of(t):
+        c = ng.CustomNoiseChain()
+        c.add(ng.CustomNoiseItem(1.0, noise_type=t))
+        return c
+
+    blended = ng.CustomNoiseChain()
+    blended.add(ng.BlendedNoise(1.0, normalize=None, blend_function=sb.hostutil.BLENDING_MODES["lerp"],
+                                custom_noise_1=chain_of("pyramid"), custom_noise_2=chain_of("perlin"), noise_2_percent=0.5))
+    sched = ng.CustomNoiseChain()
+    sched.add(ng.ScheduledNoise(1.0, noise=blended, start_sigma=10.0, end_sigma=1.0, normalize=None, fallback_noise=chain_of("gaussian")))
+    x = torch.zeros(16, 16, 128, 128, device=dev)
+    ns = sched.make_noise_sampler(x, torch.tensor(0.03), torch.tensor(14.6), seed=0)
+    s, sn_ = torch.tensor(5.0), torch.tensor(4.5)
+
+    def c3():
+        torch.manual_seed(0)
+        return ns(s, sn_)
+
+    us, per = _time_traced(sb, c3, 5, flush)
+    record("C3 Scheduled(Blended(pyramid, perlin)) 16x16x128x128", x.numel(), 16.8, us, per,
+           "16.8 B/el = injected-draw accounting of SURVEY 8d; the run also writes its own Philox draws")
+
+    # C4: wavelet CFG db2 / 3 levels / separate H,V,D scales on 16x4x128x128
+    class _MS:
+        sigma_min, sigma_max = torch.tensor(0.03), torch.tensor(14.6)
+
+        @staticmethod
+        def timestep(sg):
+            return (sg.log() - math.log(0.03)) / (math.log(14.6) - math.log(0.03)) * 999
+
+    class _Model:
+        model_sampling = _MS()
+
+    cond, uncond, xin = (torch.randn(16, 4, 128, 128, device=dev) for _ in range(3))
+    fn = sb.wcfg.WaveletCFG(existing_cfg=None, rules=sb.wcfg.WCFGRules.build(
+        wave="db2", level=3, diff={"yl_scale": 5, "yh_scales": [[3, 4, 5]] * 3}))
+    wargs = {"sigma": torch.full((16,), 5.0, device=dev), "input": xin, "cond_denoised": cond, "uncond_denoised": uncond,
+             "cond_scale": 7.0, "model": _Model(), "model_options": {}}  # fmt: skip
+    us, per = _time_traced(sb, lambda: fn(wargs), 10, flush)
+    record("C4 wavelet CFG db2 L3 16x4x128x128 (fp64 coefficients)", xin.numel(), 16.0, us, per,
+           "16 B/el: read cond, uncond, x; write result (fp64 is internal)")
+
+    # C5 per-GPU shard: video latent 1x16x33x90x160, power noise via frames_to_channels + DPM++ SDE half steps
+    x5 = torch.zeros(1, 16, 33, 90, 160, device=dev)
+    params = ng.CustomNoiseParametersNoise(
+        1.0, noise=power_chain(), normalize=None, override_device=None, override_dtype=None, frames_to_channels=True,
+        ensure_square_aspect_ratio=False, fix_invalid=False, rng_mode="default", rng_offset_mode="disabled", rng_state_offset=0)
+    c5 = ng.CustomNoiseChain()
+    c5.add(params)
+    ns5 = c5.make_noise_sampler(x5, None, None, seed=0)
+    us, per = _time_traced(sb, lambda: ns5(None, None), 5, flush)
+    record("C5 shard power noise 1x16x33x90x160", x5.numel(), 8.125 + 8.125 + 12, us, per, "as C1")
+
+    sig5 = torch.tensor([14.6, 7.0, 2.0, 0.7], device=dev)
+    xv = torch.randn(1, 16, 33, 90, 160, device=dev) * 14.6
+    cfg = {"noise_type": "gaussian"}
+
+    def c5_dpm():
+        torch.manual_seed(0)
+        return sb.samplers.SonarDPMPPSDE.sampler(lambda x, s, **k: x * 0.9, xv, sig5, extra_args={"seed": 0}, disable=True, sonar_params=cfg)
+
+    us, per = _time_traced(sb, c5_dpm, 3, flush)
+    record("C5 shard sonar_dpmpp_sde 3 steps 1x16x33x90x160 (fused Gaussian noise)", 3 * xv.numel(), 40.0, us, per,
+           "40 B/el/step: two fused half steps x 20 B/el; Philox moments pre-passes cost no HBM bytes")
+    return out
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE.json configs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

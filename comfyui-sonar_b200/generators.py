@@ -275,29 +275,22 @@ class PyramidNoiseGenerator(_PyramidBase):
     def ng_params(cls):
         return super().ng_params() | {"discount": 0.7, "upscale_mode": "bilinear", "iterations": 10}
 
-    def level_sizes(self, h: int, w: int) -> list[tuple[int, int]]:
-        """Level sizes from the CPU generator, one host draw per level exactly like the reference
-        (:626-648): r = U(0,1)*2+2, cumulative int division, stop at a 1-pixel side."""
-        sizes = []
-        host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
-        for i in range(self.iterations):
-            r = rng.host_rand(1, host_gen).item() * 2 + 2
-            w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
-            sizes.append((h, w))
-            if w == 1 or h == 1:
-                break
-        return sizes
-
     def generate(self, *_args):
         base = self.rand_like()
         b, c, h, w = base.shape
-        sizes = self.level_sizes(h, w)
-        levels = [
-            rng.normal((b, c, lh, lw), device=self.device, dtype=base.dtype, generator=self.device_generator())
-            for lh, lw in sizes
-        ]
-        weights = [self.discount**i for i in range(len(levels))]
-        return self.fix_output_frames(self._accumulate(base, levels, weights, h, w))
+        orig_h, orig_w = h, w
+        host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
+        levels, weights = [], []
+        for i in range(self.iterations):
+            # level size from one CPU-generator draw per level, exactly like the reference (:626-648):
+            # r = U(0,1)*2+2, cumulative int division, stop at a 1-pixel side (level 0 is full size)
+            r = rng.host_rand(1, host_gen).item() * 2 + 2
+            w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
+            levels.append(rng.normal((b, c, h, w), device=self.device, dtype=base.dtype, generator=self.device_generator()))
+            weights.append(self.discount**i)
+            if w == 1 or h == 1:
+                break
+        return self.fix_output_frames(self._accumulate(base, levels, weights, orig_h, orig_w))
 
 
 class HighresPyramidNoiseGenerator(_PyramidBase):

@@ -27,9 +27,22 @@ NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX, NOISE_PHILOX_NORMALIZED = 0, 1, 2, 3
 LAUNCH_COUNT = 0  # number of kernels launched through this module (bench.py's gpu_launches)
 
 
-def _count(n: int = 1) -> None:
+TRACE: list | None = None  # when a list: (name, start_event, end_event) per launch (bench.py roofline)
+
+
+def _launch(name: str, fn, *args, launches: int = 1) -> None:
+    """Calls one C-ABI entry point (which enqueues `launches` kernels on torch's current stream)."""
     global LAUNCH_COUNT  # noqa: PLW0603
-    LAUNCH_COUNT += n
+    if TRACE is None:
+        code = fn(*args)
+    else:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        code = fn(*args)
+        end.record()
+        TRACE.append((name, start, end))
+    _native.check(code, name)
+    LAUNCH_COUNT += launches
 
 
 _LAST_DEVICE: int | None = None
@@ -121,11 +134,10 @@ def philox_fill(
     lib, stream = _prepare(out)
     count = out.numel() * (2 if out.is_complex() else 1)
     fn = lib.sonar_philox_normal_f32 if kind == "normal" else lib.sonar_philox_uniform_f32
-    _native.check(
-        fn(_ptr(out), begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, p0, p1, stream),
-        f"sonar_philox_{kind}_f32",
-    )
-    _count()
+    _launch(
+        f"sonar_philox_{kind}_f32", fn,
+        _ptr(out), begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, p0, p1, stream,
+    )  # fmt: skip
     return out
 
 
@@ -178,20 +190,13 @@ def moments(x: torch.Tensor, sums: torch.Tensor | None = None) -> torch.Tensor:
     if sums is None:
         sums = new_sums(x.device)
     lib, stream = _prepare(x, sums)
-    _native.check(lib.sonar_moments_f32(_ptr(x), x.numel(), _ptr(sums), stream), "sonar_moments_f32")
-    _count()
+    _launch("sonar_moments_f32", lib.sonar_moments_f32, _ptr(x), x.numel(), _ptr(sums), stream)
     return sums
 
 
 def philox_normal_moments(draw: PhiloxDraw, *, begin: int, count: int, sums: torch.Tensor) -> torch.Tensor:
     lib, stream = _prepare(sums)
-    _native.check(
-        lib.sonar_philox_normal_moments(
-            begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, _ptr(sums), stream,
-        ),
-        "sonar_philox_normal_moments",
-    )
-    _count()
+    _launch("sonar_philox_normal_moments", lib.sonar_philox_normal_moments, begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, _ptr(sums), stream)
     return sums
 
 
@@ -208,13 +213,7 @@ def scale_noise_apply(
     _f32(x, "x")
     out = x if out is None else out
     lib, stream = _prepare(x, out, sums)
-    _native.check(
-        lib.sonar_scale_noise_f32(
-            _ptr(x), _ptr(out), x.numel(), _ptr(sums), int(count), float(factor), float(threshold_std_devs), stream,
-        ),
-        "sonar_scale_noise_f32",
-    )
-    _count()
+    _launch("sonar_scale_noise_f32", lib.sonar_scale_noise_f32, _ptr(x), _ptr(out), x.numel(), _ptr(sums), int(count), float(factor), float(threshold_std_devs), stream)
     return out
 
 
@@ -223,11 +222,7 @@ def add_moments(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, out: torch
     _f32(b, "b")
     out = a if out is None else out
     lib, stream = _prepare(a, b, out, sums)
-    _native.check(
-        lib.sonar_add_moments_f32(_ptr(a), _ptr(b), _ptr(out), a.numel(), _ptr(sums), stream),
-        "sonar_add_moments_f32",
-    )
-    _count()
+    _launch("sonar_add_moments_f32", lib.sonar_add_moments_f32, _ptr(a), _ptr(b), _ptr(out), a.numel(), _ptr(sums), stream)
     return out
 
 
@@ -237,8 +232,7 @@ def add_moments(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, out: torch
 def sonar_step(params: SonarStepParams, *tensors: torch.Tensor | None) -> None:
     """Launches the fused step; `tensors` are the live tensors behind the pointers (validation)."""
     lib, stream = _prepare(*tensors)
-    _native.check(lib.sonar_step_f32(ctypes.byref(params), stream), "sonar_step_f32")
-    _count()
+    _launch("sonar_step_f32", lib.sonar_step_f32, ctypes.byref(params), stream)
 
 
 # --------------------------------------------------------------------------------------------
@@ -248,8 +242,7 @@ def scale(x: torch.Tensor, factor: float) -> torch.Tensor:
     """x *= factor (in place) through the axpby kernel."""
     _f32(x, "x")
     lib, stream = _prepare(x)
-    _native.check(lib.sonar_axpby_f32(_ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), stream), "sonar_axpby_f32")
-    _count()
+    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), stream)
     return x
 
 
@@ -258,11 +251,7 @@ def axpby(a: torch.Tensor, alpha: float, b: torch.Tensor | None, beta: float = 1
     _f32(a, "a")
     out = torch.empty_like(a) if out is None else out
     lib, stream = _prepare(a, b, out)
-    _native.check(
-        lib.sonar_axpby_f32(_ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), stream),
-        "sonar_axpby_f32",
-    )
-    _count()
+    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), stream)
     return out
 
 
@@ -271,11 +260,7 @@ def affine(x: torch.Tensor, pre_add: float, mul: float, post_add: float, out: to
     _f32(x, "x")
     out = x if out is None else out
     lib, stream = _prepare(x, out)
-    _native.check(
-        lib.sonar_affine_f32(_ptr(x), _ptr(out), x.numel(), float(pre_add), float(mul), float(post_add), stream),
-        "sonar_affine_f32",
-    )
-    _count()
+    _launch("sonar_affine_f32", lib.sonar_affine_f32, _ptr(x), _ptr(out), x.numel(), float(pre_add), float(mul), float(post_add), stream)
     return out
 
 
@@ -283,11 +268,7 @@ def scale_by_std(x: torch.Tensor, sums: torch.Tensor, count: int, scale: float) 
     """x *= scale / std(x) (in place), std from device sums."""
     _f32(x, "x")
     lib, stream = _prepare(x, sums)
-    _native.check(
-        lib.sonar_scale_by_std_f32(_ptr(x), _ptr(x), x.numel(), _ptr(sums), int(count), float(scale), stream),
-        "sonar_scale_by_std_f32",
-    )
-    _count()
+    _launch("sonar_scale_by_std_f32", lib.sonar_scale_by_std_f32, _ptr(x), _ptr(x), x.numel(), _ptr(sums), int(count), float(scale), stream)
     return x
 
 
@@ -309,11 +290,7 @@ def blend(a: torch.Tensor, b: torch.Tensor, t, *, mode: str = "lerp", out: torch
         t_scalar = float(t)
     out = torch.empty_like(a) if out is None else out
     lib, stream = _prepare(a, b, t_tensor, out)
-    _native.check(
-        lib.sonar_blend_f32(_ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], stream),
-        "sonar_blend_f32",
-    )
-    _count()
+    _launch("sonar_blend_f32", lib.sonar_blend_f32, _ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], stream)
     return out
 
 
@@ -327,11 +304,7 @@ def composite(dst: torch.Tensor, src: torch.Tensor, mask: torch.Tensor, out: tor
         raise ValueError("composite: mask must have shape (batch, 1, H, W)")
     out = torch.empty_like(dst) if out is None else out
     lib, stream = _prepare(dst, src, mask, out)
-    _native.check(
-        lib.sonar_composite_f32(_ptr(dst), _ptr(src), _ptr(mask), _ptr(out), b, channels, hw, stream),
-        "sonar_composite_f32",
-    )
-    _count()
+    _launch("sonar_composite_f32", lib.sonar_composite_f32, _ptr(dst), _ptr(src), _ptr(mask), _ptr(out), b, channels, hw, stream)
     return out
 
 
@@ -339,8 +312,7 @@ def powerlaw(x: torch.Tensor, alpha: float, *, use_sign: bool, out: torch.Tensor
     _f32(x, "x")
     out = torch.empty_like(x) if out is None else out
     lib, stream = _prepare(x, out)
-    _native.check(lib.sonar_powerlaw_f32(_ptr(x), _ptr(out), x.numel(), float(alpha), int(use_sign), stream), "sonar_powerlaw_f32")
-    _count()
+    _launch("sonar_powerlaw_f32", lib.sonar_powerlaw_f32, _ptr(x), _ptr(out), x.numel(), float(alpha), int(use_sign), stream)
     return out
 
 
@@ -355,11 +327,7 @@ def div_item_max(x: torch.Tensor, *, use_abs: bool = True) -> torch.Tensor:
     items = x.shape[0]
     scratch = _range_scratch(items, x.device)
     lib, stream = _prepare(x, scratch)
-    _native.check(
-        lib.sonar_item_div_max_f32(_ptr(x), _ptr(x), items, x.numel() // items, int(use_abs), _ptr(scratch), stream),
-        "sonar_item_div_max_f32",
-    )
-    _count(2)
+    _launch("sonar_item_div_max_f32", lib.sonar_item_div_max_f32, _ptr(x), _ptr(x), items, x.numel() // items, int(use_abs), _ptr(scratch), stream, launches=2)
     return x
 
 
@@ -369,14 +337,8 @@ def minmax_rescale(x: torch.Tensor, target_min: float, target_max: float, *, eps
     out = torch.empty_like(x)
     scratch = _range_scratch(items, x.device)
     lib, stream = _prepare(x, out, scratch)
-    _native.check(
-        lib.sonar_item_minmax_rescale_f32(
-            _ptr(x), _ptr(out), items, x.numel() // items, float(target_min), float(target_max), float(eps),
-            _ptr(scratch), stream,
-        ),
-        "sonar_item_minmax_rescale_f32",
-    )
-    _count(2)
+    _launch("sonar_item_minmax_rescale_f32", lib.sonar_item_minmax_rescale_f32, _ptr(x), _ptr(out), items, x.numel() // items, float(target_min), float(target_max), float(eps),
+            _ptr(scratch), stream, launches=2)
     return out
 
 
@@ -418,8 +380,7 @@ def pyramid_accumulate(
     p.planes, p.H, p.W = planes, H, W
     p.n_levels, p.mode, p.base_scale = len(levels), RESAMPLE_IDS[mode], float(base_scale)
     lib, stream = _prepare(out, base, *levels)
-    _native.check(lib.sonar_pyramid_accum_f32(ctypes.byref(p), stream), "sonar_pyramid_accum_f32")
-    _count()
+    _launch("sonar_pyramid_accum_f32", lib.sonar_pyramid_accum_f32, ctypes.byref(p), stream)
     return out
 
 
@@ -451,8 +412,7 @@ def perlin_accumulate(
     p.B, p.C, p.H, p.W = B, C, H, W
     p.iterations, p.blend_mode, p.div_fac = len(angles), BLEND_IDS[blend_mode], float(div_fac)
     lib, stream = _prepare(out, base, *angles)
-    _native.check(lib.sonar_perlin_accum_f32(ctypes.byref(p), stream), "sonar_perlin_accum_f32")
-    _count()
+    _launch("sonar_perlin_accum_f32", lib.sonar_perlin_accum_f32, ctypes.byref(p), stream)
     return out
 
 
@@ -510,8 +470,7 @@ def spectral_filter(
     p.mask = 0 if mask is None else mask.data_ptr()
     p.scratch = 0 if scratch is None else scratch.data_ptr()
     p.planes, p.H, p.W, p.out_scale = planes, H, W, float(out_scale)
-    _native.check(lib.sonar_spectral_filter_f32(ctypes.byref(p), stream), "sonar_spectral_filter_f32")
-    _count()
+    _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
     return out
 
 
@@ -570,8 +529,7 @@ def dwt2_analysis(
     p.use_f64 = int(coeff_dtype == torch.float64)
     p.filters = filters
     lib, stream = _prepare(a, b, ll, hi)
-    _native.check(lib.sonar_dwt2_analysis(ctypes.byref(p), stream), "sonar_dwt2_analysis")
-    _count()
+    _launch("sonar_dwt2_analysis", lib.sonar_dwt2_analysis, ctypes.byref(p), stream)
     return ll, hi
 
 
@@ -615,6 +573,5 @@ def dwt2_synthesis(
         p.recon_sign = float(final.get("recon_sign", 1.0))
         live += [addend, x]
     lib, stream = _prepare(out, *live)
-    _native.check(lib.sonar_dwt2_synthesis(ctypes.byref(p), stream), "sonar_dwt2_synthesis")
-    _count()
+    _launch("sonar_dwt2_synthesis", lib.sonar_dwt2_synthesis, ctypes.byref(p), stream)
     return out

@@ -220,7 +220,9 @@ class SonarBase:
         p = SonarStepParams()
         hist_in, hist_state, hist_div = self.history_d, ops.HIST_PRESENT, 1.0
         if hist_in is None:
-            born = self._initial_history(x, denoised, sigma, step=step)
+            born, self._hist_pending_init = self._hist_pending_init, None
+            if born is None:
+                born = self._initial_history(x, denoised, sigma, step=step)
             if born is None:
                 hist_state = ops.HIST_NONE
             else:
@@ -273,6 +275,13 @@ class SonarBase:
         if keeps_history:
             self.history_d = hist_out
         return x_out
+
+    def prime_history(self, step: int, x: Tensor, denoised: Tensor, sigma: float) -> None:
+        """Performs the (possibly random) history initialisation of this step NOW. The reference draws
+        the RAND history inside momentum_step, i.e. before the step's ancestral noise; callers that
+        sample noise ahead of the fused launch call this first so the draw order is preserved."""
+        if self.history_d is None and self._hist_pending_init is None:
+            self._hist_pending_init = self._initial_history(x, denoised, sigma, step=step)
 
     def momentum_step(self, step: int, x: Tensor, denoised: Tensor, sigma: float, sigma_down: float, **noise_kw) -> Tensor:
         """x + momentum_d * (sigma_down - sigma) (:309-320), optionally with the ancestral noise fused in."""
@@ -438,6 +447,7 @@ class SonarEulerAncestral(SonarSampler):
         guided = self.guidance is not None and self.guidance.factor != 0.0
         if add_noise and not guided:
             # x' = momentum_step(...) + noise * (s_noise * sigma_up): one launch
+            self.prime_history(step_index, sample, denoised, float(sigma_h))
             noise_kw = self.ancestral_noise(sample, sigma_h, sigma_next_h, float(self.s_noise * sigma_up))
         result = self.momentum_step(step_index, sample, denoised, float(sigma_h), float(sigma_down), **noise_kw)
         if add_noise and guided:
@@ -496,6 +506,7 @@ class SonarDPMPPSDE(SonarSampler):
         guided = self.guidance is not None and self.guidance.factor != 0.0
 
         # ---- stage 1: x_2 = (sigma_fn(s_)/s_t) * x - momentum(expm1(t - s_) * denoised) + noise ----
+        self.prime_history(step_index, x, denoised, float(sigma_h))
         noise_kw = self.ancestral_noise(x, s_t, s_s, float(self.s_noise * su))
         x_2 = self.fused_step(
             step_index, x, denoised, float(sigma_h),

@@ -91,7 +91,9 @@ def aten_uniform(numel: int, seed: int, offset: int, grid_blocks: int, low: floa
     rounding) then rand * (to - from) + from with the `== to -> from` reversal (:487-501)."""
     raw = aten_raw_u32(numel, seed, offset, grid_blocks)
     inv = np.longdouble(np.float32(2.3283064e-10))
-    u = (raw.astype(np.longdouble) * inv + inv / 2).astype(np.float32)  # exact in 64-bit mantissa -> 1 rounding
+    # `x * CURAND_2POW32_INV + CURAND_2POW32_INV/2`: the uint32 is first converted to float (rounded to
+    # 24 bits), then one fused multiply-add; the long-double product/sum below is exact -> 1 rounding
+    u = (raw.astype(np.float32).astype(np.longdouble) * inv + inv / 2).astype(np.float32)
     lo, hi = np.float32(low), np.float32(high)
     rng = np.float32(hi - lo)
     val = (u.astype(np.longdouble) * np.longdouble(rng) + np.longdouble(lo)).astype(np.float32)

@@ -65,7 +65,7 @@ def test_uniform_matches_cpu_oracle(sb, cuda):
     assert np.array_equal(got, want)
     torch.manual_seed(99)
     normal = sb.ops.randn((n,), device=cuda).cpu().numpy()
-    np.testing.assert_allclose(normal, orc.aten_normal(n, seed, offset, grid), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(normal, orc.aten_normal(n, seed, offset, grid), rtol=0, atol=1e-5)  # __sincosf is the fast intrinsic
 
 
 def test_generator_argument(sb, cuda):
