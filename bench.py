@@ -310,10 +310,10 @@ def run_b200_arm(args) -> None:
     traffic_path = REPO / "profiles" / "traffic.json"
     traffic = None
     if traffic_path.exists():
-        traffic = json.loads(traffic_path.read_text()).get("sonar_step_philox_kernel")
+        traffic = json.loads(traffic_path.read_text()).get("sonar_step_coop_kernel" if world == 1 else "sonar_step_philox_kernel")
     roofline = {
         "bound": "hbm",
-        "kernel": "sonar_step_philox_kernel",
+        "kernel": "sonar_step_coop_kernel" if world == 1 else "sonar_step_philox_kernel",
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",

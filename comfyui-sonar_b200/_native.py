@@ -57,6 +57,8 @@ class SonarStepParams(ctypes.Structure):
         ("noise_numel_total", c_int64),
         ("noise_sums", c_void_p),
         ("noise_count", c_int64),
+        ("sums_scratch", c_void_p),
+        ("sums_parity", c_int32),
     ]
 
 
@@ -185,6 +187,10 @@ SIGNATURES: dict[str, list] = {
     "sonar_scale_by_std_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p],
     "sonar_affine_f32": [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p],
     "sonar_step_f32": [POINTER(SonarStepParams), c_void_p],
+    "sonar_step_single_launch_ok": [c_int64, c_uint32],
+    "sonar_philox_normal_fill_moments_f32": [
+        c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p,
+    ],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
     "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],

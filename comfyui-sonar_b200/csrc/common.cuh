@@ -155,6 +155,12 @@ __device__ __forceinline__ float4 philox_normal4(const PhiloxStream& s, uint32_t
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// Only the first Box-Muller pair (lanes 0, 1) -- for draws where lanes 2, 3 fall outside the tensor
+__device__ __forceinline__ float2 philox_normal2_lo(const PhiloxStream& s, uint32_t thread, uint64_t call) {
+  const uint4 r = philox_raw(s, thread, call);
+  return _curand_box_muller(r.x, r.y);
+}
+
 // curand_uniform4 (values in (0, 1])
 __device__ __forceinline__ float4 philox_uniform4(const PhiloxStream& s, uint32_t thread, uint64_t call) {
   return _curand_uniform4(philox_raw(s, thread, call));

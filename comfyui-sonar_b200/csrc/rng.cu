@@ -18,33 +18,36 @@ enum DistKind : int { DIST_NORMAL = 0, DIST_UNIFORM = 1 };
 // the virtual tensor only keeps the lanes that fall inside it and writes them at (li - begin).
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
-philox_fill_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream s, uint32_t k_lo,
-                   int64_t n_pairs, float p0, float p1) {
+philox_fill_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream s, uint32_t k_lo, uint32_t k_hi,
+                   float p0, float p1) {
   const int64_t T = s.threads;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
-       p += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t t = (uint32_t)(p % T);
-    const uint64_t k = k_lo + (uint64_t)(p / T);
-    float4 v;
-    if (KIND == DIST_NORMAL) {
-      v = philox_normal4(s, t, k);
-      v.x = v.x * p1 + p0;  // at::transformation::normal: val * std + mean
-      v.y = v.y * p1 + p0;
-      v.z = v.z * p1 + p0;
-      v.w = v.w * p1 + p0;
-    } else {
-      v = philox_uniform4(s, t, k);
-      v.x = uniform_transform(v.x, p0, p1);
-      v.y = uniform_transform(v.y, p0, p1);
-      v.z = uniform_transform(v.z, p0, p1);
-      v.w = uniform_transform(v.w, p0, p1);
-    }
-    const int64_t li0 = (int64_t)t + T * (int64_t)(4 * k);
-    const float vals[4] = {v.x, v.y, v.z, v.w};
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  // virtual ATen thread vt (Philox subsequence) x call k; no 64-bit div/mod in the loop
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      float4 v;
+      if (KIND == DIST_NORMAL) {
+        v = philox_normal4(s, (uint32_t)vt, k);
+        v.x = v.x * p1 + p0;  // at::transformation::normal: val * std + mean
+        v.y = v.y * p1 + p0;
+        v.z = v.z * p1 + p0;
+        v.w = v.w * p1 + p0;
+      } else {
+        v = philox_uniform4(s, (uint32_t)vt, k);
+        v.x = uniform_transform(v.x, p0, p1);
+        v.y = uniform_transform(v.y, p0, p1);
+        v.z = uniform_transform(v.z, p0, p1);
+        v.w = uniform_transform(v.w, p0, p1);
+      }
+      const float vals[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int lane = 0; lane < 4; ++lane) {
-      const int64_t li = li0 + T * lane;
-      if (li >= begin && li < end) out[li - begin] = vals[lane];
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) out[li - begin] = vals[lane];
+      }
     }
   }
 }
@@ -60,9 +63,8 @@ int launch_fill(float* out, int64_t begin, int64_t count, int64_t numel_total, u
   // rows r = li / T touched by the slice -> Philox calls k = r / 4
   const int64_t k_lo = (begin / T) / 4;
   const int64_t k_hi = ((end - 1) / T) / 4;
-  const int64_t n_pairs = T * (k_hi - k_lo + 1);
-  const int grid = streaming_grid(n_pairs, kBlock, 1);
-  philox_fill_kernel<KIND><<<grid, kBlock, 0, stream>>>(out, begin, end, s, (uint32_t)k_lo, n_pairs, p0, p1);
+  const int grid = streaming_grid(T, kBlock, 1);
+  philox_fill_kernel<KIND><<<grid, kBlock, 0, stream>>>(out, begin, end, s, (uint32_t)k_lo, (uint32_t)k_hi, p0, p1);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

@@ -11,6 +11,9 @@
 // Philox stream torch.randn(device='cuda') would have produced, optionally with the conditional
 // global normalisation of scale_noise applied from device-resident sums (stats pre-pass in
 // stats.cu: zero HBM bytes for the noise).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/sonar_b200.h"
 
@@ -68,8 +71,13 @@ __device__ __forceinline__ StepElem step_element(const SonarStepParams& p, float
 __global__ void __launch_bounds__(kBlock)
 sonar_step_vec_kernel(SonarStepParams p) {
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
-  const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR;
+  const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
   const bool write_h = p.hist_out != nullptr;
+  // raw Gaussian tensor + device-resident sums: apply scale_noise on load
+  const bool norm_noise = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
+  const NormDecision nd = norm_noise ? decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs)
+                                     : NormDecision{0.f, 1.f, 0, 0};
+  const float nfac = norm_noise ? p.noise_factor : 1.0f;
   const int64_t n4 = p.n >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -77,7 +85,13 @@ sonar_step_vec_kernel(SonarStepParams p) {
     const float4 x = ld4_stream(p.x + 4 * i);
     const float4 dn = ld4_stream(p.denoised + 4 * i);
     const float4 h = has_h_in ? ld4(p.hist_in + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 nz = has_noise ? ld4_stream(p.noise + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nz = has_noise ? ld4_stream(p.noise + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (norm_noise) {
+      nz.x = apply_norm(nz.x, nd) * nfac;
+      nz.y = apply_norm(nz.y, nd) * nfac;
+      nz.z = apply_norm(nz.z, nd) * nfac;
+      nz.w = apply_norm(nz.w, nd) * nfac;
+    }
     const StepElem a = step_element(p, x.x, dn.x, h.x, nz.x);
     const StepElem b = step_element(p, x.y, dn.y, h.y, nz.y);
     const StepElem c = step_element(p, x.z, dn.z, h.z, nz.z);
@@ -86,7 +100,8 @@ sonar_step_vec_kernel(SonarStepParams p) {
     if (write_h) st4(p.hist_out + 4 * i, make_float4(a.h_out, b.h_out, c.h_out, d.h_out));
   }
   for (int64_t i = (n4 << 2) + tid; i < p.n; i += stride) {
-    const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, has_noise ? p.noise[i] : 0.f);
+    const float nzs = has_noise ? apply_norm(p.noise[i], nd) * nfac : 0.f;
+    const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, nzs);
     p.x_out[i] = a.x_out;
     if (write_h) p.hist_out[i] = a.h_out;
   }
@@ -95,50 +110,205 @@ sonar_step_vec_kernel(SonarStepParams p) {
 __global__ void __launch_bounds__(kBlock)
 sonar_step_scalar_kernel(SonarStepParams p) {
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
-  const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR;
+  const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
   const bool write_h = p.hist_out != nullptr;
+  const bool norm_noise = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
+  const NormDecision nd = norm_noise ? decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs)
+                                     : NormDecision{0.f, 1.f, 0, 0};
+  const float nfac = norm_noise ? p.noise_factor : 1.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
-    const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, has_noise ? p.noise[i] : 0.f);
+    const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f,
+                                    has_noise ? apply_norm(p.noise[i], nd) * nfac : 0.f);
     p.x_out[i] = a.x_out;
     if (write_h) p.hist_out[i] = a.h_out;
   }
 }
 
-// ---- Philox variant: thread <-> (emulated ATen thread t, call k); 4 elements T apart ----
-// Element index li below is GLOBAL (position in the un-sharded noise tensor); the local tensors
-// hold the slice [noise_begin, noise_begin + n).
+// ---- Philox variants: CUDA thread <-> virtual ATen thread vt (Philox subsequence), call k ----
+// A (vt, k) pair owns the 4 elements li = vt + T*(4k + lane): T apart, so consecutive threads touch
+// consecutive addresses (coalesced scalar accesses). Element index li is GLOBAL (position in the
+// un-sharded noise tensor); the local tensors hold the slice [noise_begin, noise_begin + n).
+__device__ __forceinline__ void step_pair(const SonarStepParams& p, const NormDecision& nd, const float z[4],
+                                          int64_t li0, int64_t T, int64_t begin, int64_t end, bool has_h_in,
+                                          bool write_h) {
+  float xs[4], ds[4], hs[4];
+  bool ok[4];
+#pragma unroll
+  for (int lane = 0; lane < 4; ++lane) {  // issue every load of the pair before any arithmetic
+    const int64_t li = li0 + T * lane;
+    ok[lane] = li >= begin && li < end;
+    const int64_t i = ok[lane] ? li - begin : 0;
+    xs[lane] = ok[lane] ? __ldg(p.x + i) : 0.0f;
+    ds[lane] = ok[lane] ? __ldg(p.denoised + i) : 0.0f;
+    hs[lane] = (ok[lane] && has_h_in) ? p.hist_in[i] : 0.0f;
+  }
+#pragma unroll
+  for (int lane = 0; lane < 4; ++lane) {
+    if (!ok[lane]) continue;
+    const int64_t i = li0 + T * lane - begin;
+    const float nz = apply_norm(z[lane], nd) * p.noise_factor;
+    const StepElem a = step_element(p, xs[lane], ds[lane], hs[lane], nz);
+    p.x_out[i] = a.x_out;
+    if (write_h) p.hist_out[i] = a.h_out;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
-sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, int64_t n_pairs) {
+sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint32_t k_hi) {
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
   const bool write_h = p.hist_out != nullptr;
   const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
                               ? decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs)
                               : NormDecision{0.f, 1.f, 0, 0};
   const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t begin = p.noise_begin, end = p.noise_begin + p.n;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_pairs;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t t = (uint32_t)(q % T);
-    const uint64_t k = k_lo + (uint64_t)(q / T);
-    const int64_t li0 = (int64_t)t + T * (int64_t)(4 * k);
-    if (li0 >= end) continue;  // whole pair beyond the slice (li grows with lane)
-    const float4 z = philox_normal4(st, t, k);
-    const float zs[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-    for (int lane = 0; lane < 4; ++lane) {
-      const int64_t li = li0 + T * lane;
-      if (li >= begin && li < end) {
-        const int64_t i = li - begin;
-        const float nz = apply_norm(zs[lane], nd) * p.noise_factor;
-        const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, nz);
-        p.x_out[i] = a.x_out;
-        if (write_h) p.hist_out[i] = a.h_out;
-      }
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      const float4 z4 = philox_normal4(st, (uint32_t)vt, k);
+      const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+      step_pair(p, nd, z, li0, T, begin, end, has_h_in, write_h);
     }
   }
 }
 
+// Single-launch variant for small tensors (launch-bound regime): phase 1 draws the Philox normals
+// into registers and reduces their moments, a grid-wide barrier publishes the global sums, phase 2
+// applies the conditional normalisation to the SAME registers and performs the step. The whole
+// grid must be co-resident (cooperative launch); each thread owns at most kCoopPairs (vt, k) pairs.
+// The double[2] sums slot is zeroed for the next launch by the kernel itself (ping-pong slots).
+constexpr int kCoopPairs = 4;
+
+// moments of the un-materialised Philox normal draw (same kernel as stats.cu's, local to this TU)
+__global__ void __launch_bounds__(kBlock)
+philox_normal_moments_device(int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo, uint32_t k_hi,
+                             double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  double s = 0.0, ss = 0.0;
+  const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    float fs = 0.0f, fss = 0.0f;
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      const float4 v = philox_normal4(st, (uint32_t)vt, k);
+      const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) {
+          fs += vals[lane];
+          fss += vals[lane] * vals[lane];
+        }
+      }
+    }
+    s += (double)fs;
+    ss += (double)fss;
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s);
+    atomicAdd(&sums[1], ss);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock, 4)
+sonar_step_coop_kernel(SonarStepParams p, PhiloxStream st, uint32_t calls, double* __restrict__ slot,
+                       double* __restrict__ next_slot) {
+  __shared__ double scratch[64];
+  const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
+  const bool write_h = p.hist_out != nullptr;
+  const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t end = p.n;  // cooperative path: un-sharded draw, begin == 0
+  float z[kCoopPairs][4];
+  float fs = 0.0f, fss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < kCoopPairs; ++j) {
+    const int64_t vt = tid + (int64_t)(j / calls) * nthreads;
+    const uint32_t k = (uint32_t)j % calls;
+    const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+    const bool live = vt < T && (uint32_t)j < calls * (uint32_t)((T + nthreads - 1) / nthreads) && li0 < end;
+    if (live) {
+      if (li0 + 2 * T < end) {
+        const float4 z4 = philox_normal4(st, (uint32_t)vt, k);
+        z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
+      } else {  // lanes 2, 3 lie beyond the tensor: one Box-Muller is enough
+        const float2 z2 = philox_normal2_lo(st, (uint32_t)vt, k);
+        z[j][0] = z2.x; z[j][1] = z2.y; z[j][2] = 0.0f; z[j][3] = 0.0f;
+      }
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li < end) {
+          fs += z[j][lane];
+          fss += z[j][lane] * z[j][lane];
+        }
+      }
+    } else {
+      z[j][0] = z[j][1] = z[j][2] = z[j][3] = 0.0f;
+    }
+  }
+  double s = (double)fs, ss = (double)fss;
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&slot[0], s);
+    atomicAdd(&slot[1], ss);
+  }
+  cooperative_groups::this_grid().sync();
+  const NormDecision nd = decide_normalisation(slot, p.noise_count, p.noise_threshold_std_devs);
+  if (tid == 0) {
+    next_slot[0] = 0.0;
+    next_slot[1] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < kCoopPairs; ++j) {
+    const int64_t vt = tid + (int64_t)(j / calls) * nthreads;
+    const uint32_t k = (uint32_t)j % calls;
+    const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+    const bool live = vt < T && (uint32_t)j < calls * (uint32_t)((T + nthreads - 1) / nthreads) && li0 < end;
+    if (live) step_pair(p, nd, z[j], li0, T, 0, end, has_h_in, write_h);
+  }
+}
+
 }  // namespace sonar
+
+namespace sonar {
+static int coop_blocks_per_sm() {
+  static thread_local int cached = -1;
+  if (cached < 0) {
+    int dev = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cached = 0;
+    if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached, sonar_step_coop_kernel, kBlock, 0);
+    if (getenv("SONAR_B200_NO_COOP") != nullptr) cached = 0;
+  }
+  return cached;
+}
+
+// cooperative grid for a draw of `grid_blocks` emulated ATen blocks covering n elements, or 0
+static int64_t coop_grid_for(int64_t n, uint32_t grid_blocks) {
+  const int64_t T = (int64_t)grid_blocks * kBlock;
+  if (T <= 0 || n <= 0) return 0;
+  int64_t g = (int64_t)coop_blocks_per_sm() * device_info().sm_count;
+  if (g > (int64_t)grid_blocks) g = grid_blocks;
+  if (g <= 0) return 0;
+  const int64_t calls = ((n - 1) / T) / 4 + 1;
+  const int64_t pairs = ((T + g * kBlock - 1) / (g * kBlock)) * calls;
+  return pairs <= kCoopPairs ? g : 0;
+}
+}  // namespace sonar
+
+extern "C" int sonar_step_single_launch_ok(int64_t n, uint32_t philox_grid_blocks) {
+  return sonar::coop_grid_for(n, philox_grid_blocks) > 0 ? 1 : 0;
+}
 
 extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
   using namespace sonar;
@@ -147,8 +317,11 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
   if (p.n <= 0) return 0;
   if (p.x == nullptr || p.denoised == nullptr || p.x_out == nullptr) return (int)cudaErrorInvalidValue;
   if (p.hist_state != SONAR_HIST_NONE && p.hist_in == nullptr) return (int)cudaErrorInvalidValue;
-  if (p.noise_kind == SONAR_NOISE_TENSOR && p.noise == nullptr) return (int)cudaErrorInvalidValue;
-  if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr) return (int)cudaErrorInvalidValue;
+  if ((p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED) && p.noise == nullptr)
+    return (int)cudaErrorInvalidValue;
+  if (p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED && p.noise_sums == nullptr) return (int)cudaErrorInvalidValue;
+  if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr && p.sums_scratch == nullptr)
+    return (int)cudaErrorInvalidValue;
   cudaStream_t stream = (cudaStream_t)stream_;
 
   if (p.noise_kind == SONAR_NOISE_PHILOX || p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED) {
@@ -157,9 +330,33 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     PhiloxStream st{p.philox_seed, p.philox_offset, p.philox_grid_blocks * (uint32_t)kBlock};
     const int64_t T = st.threads, end = p.noise_begin + p.n;
     const int64_t k_lo = (p.noise_begin / T) / 4, k_hi = ((end - 1) / T) / 4;
-    const int64_t n_pairs = T * (k_hi - k_lo + 1);
-    const int grid = streaming_grid(n_pairs, kBlock, 1);
-    sonar_step_philox_kernel<<<grid, kBlock, 0, stream>>>(p, st, (uint32_t)k_lo, n_pairs);
+    const bool self_stats = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr;
+    if (self_stats) {
+      // the caller left the moments pre-pass to us (un-sharded draw): sums_scratch is double[4],
+      // two ping-pong slots, zero-initialised once by the caller
+      if (p.sums_scratch == nullptr || p.noise_begin != 0 || p.n != p.noise_numel_total) return (int)cudaErrorInvalidValue;
+      double* slot = p.sums_scratch + 2 * (p.sums_parity & 1);
+      double* next_slot = p.sums_scratch + 2 * ((p.sums_parity & 1) ^ 1);
+      p.noise_count = p.n;
+      const int64_t calls = k_hi + 1;
+      const int64_t coop_grid = coop_grid_for(p.n, p.philox_grid_blocks);
+      if (coop_grid > 0) {
+        uint32_t calls32 = (uint32_t)calls;
+        void* args[] = {&p, &st, &calls32, &slot, &next_slot};
+        SONAR_CUDA_TRY(cudaLaunchCooperativeKernel((void*)sonar_step_coop_kernel, dim3((unsigned)coop_grid), dim3(kBlock),
+                                                   args, 0, stream));
+        return 0;
+      }
+      // large tensors: moments pre-pass + step as two launches (launch cost is negligible there)
+      SONAR_CUDA_TRY(cudaMemsetAsync(slot, 0, 2 * sizeof(double), stream));
+      const int grid_m = streaming_grid(T, kBlock, 1);
+      philox_normal_moments_device<<<grid_m, kBlock, 0, stream>>>(0, end, st, (uint32_t)k_lo, (uint32_t)k_hi, slot);
+      SONAR_LAUNCH_CHECK();
+      p.noise_sums = slot;
+      p.sums_parity = 0;
+    }
+    const int grid = streaming_grid(T, kBlock, 1);
+    sonar_step_philox_kernel<<<grid, kBlock, 0, stream>>>(p, st, (uint32_t)k_lo, (uint32_t)k_hi);
     SONAR_LAUNCH_CHECK();
     return 0;
   }

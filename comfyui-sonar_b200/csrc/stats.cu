@@ -50,27 +50,68 @@ moments_kernel(const float* __restrict__ x, int64_t n, int vec_ok, double* __res
 
 // Moments of a Philox normal draw restricted to the slice [begin, end) without materialising it.
 __global__ void __launch_bounds__(kBlock)
-philox_normal_moments_kernel(int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo, int64_t n_pairs,
+philox_normal_moments_kernel(int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo, uint32_t k_hi,
                              double* __restrict__ sums) {
   __shared__ double scratch[64];
   double s = 0.0, ss = 0.0;
   const int64_t T = st.threads;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
-       p += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t t = (uint32_t)(p % T);
-    const uint64_t k = k_lo + (uint64_t)(p / T);
-    const float4 v = philox_normal4(st, t, k);
-    const float vals[4] = {v.x, v.y, v.z, v.w};
-    const int64_t li0 = (int64_t)t + T * (int64_t)(4 * k);
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    float fs = 0.0f, fss = 0.0f;  // per-thread partials stay fp32 (<= 4*calls terms), block/global sums fp64
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      const float4 v = philox_normal4(st, (uint32_t)vt, k);
+      const float vals[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int lane = 0; lane < 4; ++lane) {
-      const int64_t li = li0 + T * lane;
-      if (li >= begin && li < end) {
-        const double d = vals[lane];
-        s += d;
-        ss += d * d;
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) {
+          fs += vals[lane];
+          fss += vals[lane] * vals[lane];
+        }
       }
     }
+    s += (double)fs;
+    ss += (double)fss;
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s);
+    atomicAdd(&sums[1], ss);
+  }
+}
+
+// One pass: materialise the slice of a Philox normal draw AND reduce its moments (for tensors too
+// large to keep the normals in registers across a grid barrier: write once, read once).
+__global__ void __launch_bounds__(kBlock)
+philox_normal_fill_moments_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo,
+                                  uint32_t k_hi, double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  double s = 0.0, ss = 0.0;
+  const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    float fs = 0.0f, fss = 0.0f;
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      const float4 v = philox_normal4(st, (uint32_t)vt, k);
+      const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) {
+          out[li - begin] = vals[lane];
+          fs += vals[lane];
+          fss += vals[lane] * vals[lane];
+        }
+      }
+    }
+    s += (double)fs;
+    ss += (double)fss;
   }
   block_sum2(s, ss, scratch);
   if (threadIdx.x == 0) {
@@ -156,10 +197,24 @@ int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_tota
   sonar::PhiloxStream s{seed, offset, grid_blocks * (uint32_t)sonar::kBlock};
   const int64_t T = s.threads, end = begin + count;
   const int64_t k_lo = (begin / T) / 4, k_hi = ((end - 1) / T) / 4;
-  const int64_t n_pairs = T * (k_hi - k_lo + 1);
-  const int grid = sonar::streaming_grid(n_pairs, sonar::kBlock, 1);
+  const int grid = sonar::streaming_grid(T, sonar::kBlock, 1);
   sonar::philox_normal_moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(begin, end, s, (uint32_t)k_lo,
-                                                                                       n_pairs, sums);
+                                                                                       (uint32_t)k_hi, sums);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_philox_normal_fill_moments_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                                         uint64_t offset, uint32_t grid_blocks, double* sums, void* stream) {
+  if (count <= 0) return 0;
+  if (grid_blocks == 0 || begin < 0 || begin + count > numel_total) return (int)cudaErrorInvalidValue;
+  sonar::PhiloxStream s{seed, offset, grid_blocks * (uint32_t)sonar::kBlock};
+  const int64_t T = s.threads, end = begin + count;
+  const int64_t k_lo = (begin / T) / 4, k_hi = ((end - 1) / T) / 4;
+  SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
+  const int grid = sonar::streaming_grid(T, sonar::kBlock, 1);
+  sonar::philox_normal_fill_moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(
+      out, begin, end, s, (uint32_t)k_lo, (uint32_t)k_hi, sums);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

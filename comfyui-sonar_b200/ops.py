@@ -22,7 +22,7 @@ STEP_EULER, STEP_DPMPP = 0, 1
 MODE_CLASSIC, MODE_NEW, MODE_DENOISED = 0, 1, 2
 BLEND_IDS = {"lerp": 0, "inject": 1, "subtract_b": 2}
 HIST_NONE, HIST_PRESENT, HIST_INIT = 0, 1, 2
-NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX, NOISE_PHILOX_NORMALIZED = 0, 1, 2, 3
+NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX, NOISE_PHILOX_NORMALIZED, NOISE_TENSOR_NORMALIZED = 0, 1, 2, 3, 4
 
 LAUNCH_COUNT = 0  # number of kernels launched through this module (bench.py's gpu_launches)
 
@@ -70,7 +70,14 @@ def _prepare(*tensors: torch.Tensor | None) -> tuple[ctypes.CDLL, ctypes.c_void_
     if idx != _LAST_DEVICE:
         _native.check(lib.sonar_set_device(idx), "sonar_set_device")
         _LAST_DEVICE = idx
-    return lib, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    return lib, ctypes.c_void_p(_raw_stream(idx))
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # noqa: SLF001  (fast path, ~0.3 us)
+if _raw_stream is None:  # pragma: no cover - older torch
+
+    def _raw_stream(idx: int) -> int:
+        return torch.cuda.current_stream(idx).cuda_stream
 
 
 def _ptr(t: torch.Tensor | None) -> ctypes.c_void_p:
@@ -96,6 +103,9 @@ class PhiloxDraw:
     counter_offset: int  # how far the draw advances the generator
 
 
+_POLICY_CACHE: dict[tuple[int, int], tuple[int, int]] = {}
+
+
 def philox_policy(numel: int) -> tuple[int, int]:
     """(grid_blocks, counter_offset) of ATen's calc_execution_policy for the current device."""
     lib = _native.load()
@@ -113,8 +123,15 @@ def reserve_draw(numel: int, device: torch.device, generator: torch.Generator | 
         raise RuntimeError("reserve_draw needs a CUDA device")
     idx = device.index if device.index is not None else torch.cuda.current_device()
     gen = generator if generator is not None else torch.cuda.default_generators[idx]
-    with torch.cuda.device(idx):
-        grid, inc = philox_policy(numel)
+    key = (idx, int(numel))
+    policy = _POLICY_CACHE.get(key)
+    if policy is None:
+        with torch.cuda.device(idx):
+            policy = philox_policy(numel)
+        if len(_POLICY_CACHE) > 4096:
+            _POLICY_CACHE.clear()
+        _POLICY_CACHE[key] = policy
+    grid, inc = policy
     seed, offset = gen.initial_seed(), gen.get_offset()
     if numel > 0:
         gen.set_offset(offset + inc)
@@ -198,6 +215,27 @@ def philox_normal_moments(draw: PhiloxDraw, *, begin: int, count: int, sums: tor
     lib, stream = _prepare(sums)
     _launch("sonar_philox_normal_moments", lib.sonar_philox_normal_moments, begin, count, draw.numel, draw.seed, draw.offset, draw.grid_blocks, _ptr(sums), stream)
     return sums
+
+
+def philox_normal_fill_moments(draw: PhiloxDraw, out: torch.Tensor, sums: torch.Tensor, *, begin: int = 0) -> torch.Tensor:
+    """Materialises the slice of `draw` into `out` and writes its (sum, sum^2) into `sums`: one pass."""
+    lib, stream = _prepare(out, sums)
+    _launch(
+        "sonar_philox_normal_fill_moments_f32", lib.sonar_philox_normal_fill_moments_f32,
+        _ptr(out), begin, out.numel(), draw.numel, draw.seed, draw.offset, draw.grid_blocks, _ptr(sums), stream,
+    )  # fmt: skip
+    return out
+
+
+_SINGLE_LAUNCH_CACHE: dict[tuple[int, int], bool] = {}
+
+
+def step_single_launch_ok(numel: int, grid_blocks: int) -> bool:
+    key = (int(numel), int(grid_blocks))
+    hit = _SINGLE_LAUNCH_CACHE.get(key)
+    if hit is None:
+        hit = _SINGLE_LAUNCH_CACHE[key] = bool(_native.load().sonar_step_single_launch_ok(*key))
+    return hit
 
 
 def scale_noise_apply(

@@ -96,6 +96,7 @@ class SonarBase:
         self.history_blend = hostutil.BLENDING_MODES[cfg.get_with_default("history_blend_mode", base)]
         self.guidance_blend = hostutil.BLENDING_MODES[cfg.get_with_default("guidance_blend_mode", base)]
         self._hist_pending_init: tuple[Tensor, float] | None = None
+        self._sums_parity = 0
 
     _cfg_fixups = (
         ("momentum_mode", MomentumMode),
@@ -194,6 +195,20 @@ class SonarBase:
     # ------------------------------------------------------------------------------------
     # the fused launch
     # ------------------------------------------------------------------------------------
+    def _step_params(self) -> SonarStepParams:
+        """Per-sampler parameter block; the fields that never change are filled once."""
+        p = getattr(self, "_params", None)
+        if p is None:
+            cfg = self.cfg
+            p = self._params = SonarStepParams()
+            p.mode = _MODE_IDS[cfg.momentum_mode]
+            p.momentum_blend = hostutil.blend_mode_id(self.momentum_blend)
+            p.history_blend = hostutil.blend_mode_id(self.history_blend)
+            p.momentum = cfg.momentum
+            p.hd_ratio, p.hd_scale, p.md_scale = self.history_ratios
+            p.noise_threshold_std_devs = 2.5
+        return p
+
     def fused_step(
         self,
         step: int,
@@ -208,16 +223,16 @@ class SonarBase:
         noise_scale: float = 0.0,
         noise_philox: dict | None = None,
     ) -> Tensor:
-        """One kernel: momentum mix, both history updates, Euler / DPM++ update, noise injection."""
+        """One C-ABI call: momentum mix, both history updates, Euler / DPM++ update, noise injection."""
         cfg = self.cfg
         if x.dtype != torch.float32:
             raise TypeError(f"sonar_b200 samplers run on float32 latents (got {x.dtype})")
-        x = x.contiguous()
-        denoised = denoised.to(torch.float32).contiguous()
-        hr, hs, ms = self.history_ratios
-        history_active = self.check_step(step, is_history=True) and cfg.momentum_hist != 1
+        if not x.is_contiguous():
+            x = x.contiguous()
+        if denoised.dtype != torch.float32 or not denoised.is_contiguous():
+            denoised = denoised.to(torch.float32).contiguous()
+        history_active = cfg.momentum_hist != 1 and self.check_step(step, is_history=True)
 
-        p = SonarStepParams()
         hist_in, hist_state, hist_div = self.history_d, ops.HIST_PRESENT, 1.0
         if hist_in is None:
             born, self._hist_pending_init = self._hist_pending_init, None
@@ -229,63 +244,73 @@ class SonarBase:
                 hist_in, hist_div = born
                 hist_in = hist_in.contiguous()
                 hist_state = ops.HIST_INIT
-        # Does this call leave a history behind? (update_hist assigns when it runs, or init did)
-        runs_second_update = cfg.momentum != 1 and cfg.momentum_mode != MomentumMode.DENOISED
+        # a history survives this call if one came in (or was born) or an update creates it
         keeps_history = hist_state != ops.HIST_NONE or history_active
         x_out = torch.empty_like(x)
         hist_out = None
         if keeps_history:
-            # in place unless the incoming history aliases x / denoised (SAMPLE init)
+            # in place, unless the incoming history aliases x / denoised (SAMPLE init) or was just born
             hist_out = hist_in if hist_state == ops.HIST_PRESENT else torch.empty_like(x)
-        _ = runs_second_update
 
+        p = self._step_params()
         p.x, p.denoised, p.x_out = x.data_ptr(), denoised.data_ptr(), x_out.data_ptr()
         p.hist_in = 0 if hist_in is None else hist_in.data_ptr()
         p.hist_out = 0 if hist_out is None else hist_out.data_ptr()
         p.n = x.numel()
-        p.kind, p.mode = kind, _MODE_IDS[cfg.momentum_mode]
-        p.momentum_blend = hostutil.blend_mode_id(self.momentum_blend)
-        p.history_blend = hostutil.blend_mode_id(self.history_blend)
+        p.kind = kind
         p.hist_state = hist_state
         p.momentum_active = int(self.check_step(step))
         p.history_active = int(history_active)
-        p.momentum, p.sigma, p.c0, p.c1 = cfg.momentum, sigma, c0, c1
-        p.hd_ratio, p.hd_scale, p.md_scale = hr, hs, ms
+        p.sigma, p.c0, p.c1 = sigma, c0, c1
         p.hist_in_div = hist_div
         p.noise_scale = noise_scale
-        p.noise_kind = ops.NOISE_NONE
-        live = [x, denoised, x_out, hist_in, hist_out]
+        p.noise_kind, p.noise, p.noise_sums, p.sums_scratch = ops.NOISE_NONE, 0, 0, 0
+        keep = None
         if noise_philox is not None:
             draw = noise_philox["draw"]
             p.noise_kind = ops.NOISE_PHILOX_NORMALIZED if noise_philox["normalized"] else ops.NOISE_PHILOX
             p.noise_factor = noise_philox["factor"]
-            p.noise_threshold_std_devs = 2.5
             p.philox_seed, p.philox_offset, p.philox_grid_blocks = draw.seed, draw.offset, draw.grid_blocks
             p.noise_begin, p.noise_numel_total = noise_philox["begin"], draw.numel
-            sums = noise_philox.get("sums")
-            p.noise_sums = 0 if sums is None else sums.data_ptr()
-            p.noise_count = noise_philox.get("count", 0)
-            live.append(sums)
+            keep = noise_philox.get("sums")
+            if keep is not None:  # materialised raw normals + device-resident (possibly all-reduced) sums
+                raw = noise_philox["tensor"]
+                p.noise_kind, p.noise = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr()
+                p.noise_sums, p.noise_count = keep.data_ptr(), noise_philox["count"]
+                keep = (keep, raw)
+            elif noise_philox["normalized"]:  # the call does its own moments pre-pass (one launch when small)
+                keep = self._sums_scratch(x.device)
+                p.sums_scratch, p.sums_parity = keep.data_ptr(), self._sums_parity
+                self._sums_parity ^= 1
+                p.noise_count = x.numel()
         elif noise_tensor is not None:
-            noise_tensor = noise_tensor.to(torch.float32).contiguous()
-            p.noise_kind = ops.NOISE_TENSOR
-            p.noise = noise_tensor.data_ptr()
-            live.append(noise_tensor)
-        ops.sonar_step(p, *live)
+            if noise_tensor.dtype != torch.float32 or not noise_tensor.is_contiguous():
+                noise_tensor = noise_tensor.to(torch.float32).contiguous()
+            p.noise_kind, p.noise, keep = ops.NOISE_TENSOR, noise_tensor.data_ptr(), noise_tensor
+        ops.sonar_step(p, x, denoised)
+        del keep
         if keeps_history:
             self.history_d = hist_out
         return x_out
+
+    def _sums_scratch(self, device) -> Tensor:
+        buf = getattr(self, "_sums_buf", None)
+        if buf is None or buf.device != device:
+            buf = self._sums_buf = torch.zeros(4, device=device, dtype=torch.float64)
+            self._sums_parity = 0
+        return buf
 
     def prime_history(self, step: int, x: Tensor, denoised: Tensor, sigma: float) -> None:
         """Performs the (possibly random) history initialisation of this step NOW. The reference draws
         the RAND history inside momentum_step, i.e. before the step's ancestral noise; callers that
         sample noise ahead of the fused launch call this first so the draw order is preserved."""
-        if self.history_d is None and self._hist_pending_init is None:
+        if self.history_d is None and self._hist_pending_init is None and self.cfg.init != HistoryType.ZERO:
             self._hist_pending_init = self._initial_history(x, denoised, sigma, step=step)
 
-    def momentum_step(self, step: int, x: Tensor, denoised: Tensor, sigma: float, sigma_down: float, **noise_kw) -> Tensor:
+    def momentum_step(self, step: int, x: Tensor, denoised: Tensor, sigma: float, sigma_down: float, *, dt=None, **noise_kw):
         """x + momentum_d * (sigma_down - sigma) (:309-320), optionally with the ancestral noise fused in."""
-        dt = float(torch.tensor(sigma_down, dtype=torch.float32) - torch.tensor(sigma, dtype=torch.float32))
+        if dt is None:  # float32 subtraction, like the reference's 0-d tensors
+            dt = float(torch.tensor(sigma_down, dtype=torch.float32) - torch.tensor(sigma, dtype=torch.float32))
         return self.fused_step(step, x, denoised, sigma, kind=ops.STEP_EULER, c0=dt, **noise_kw)
 
     # ------------------------------------------------------------------------------------
@@ -293,20 +318,37 @@ class SonarBase:
     # ------------------------------------------------------------------------------------
     def ancestral_noise(self, x: Tensor, sigma: Tensor, sigma_next: Tensor, scale: float) -> dict:
         """kwargs for fused_step that add noise_sampler(sigma, sigma_next) * scale."""
-        ns = self.noise_sampler
-        spec = ns.fused_gaussian() if hasattr(ns, "fused_gaussian") and not _rng_is_injected() else None
-        if spec is not None and tuple(spec[2]) == tuple(x.shape):
-            factor, normalized, _shape = spec
-            total, begin = parallel.global_draw_geometry(x.shape)
+        spec = self._fused_noise_spec(x)
+        if spec is not None:
+            factor, normalized = spec
+            sharded = parallel.active() is not None and parallel.active().world_size > 1
+            total, begin = parallel.global_draw_geometry(x.shape) if sharded else (x.numel(), 0)
             draw = ops.reserve_draw(total, x.device)
             kw = {"draw": draw, "factor": factor, "normalized": normalized, "begin": begin}
-            if normalized:
-                sums = ops.new_sums(x.device)
-                ops.philox_normal_moments(draw, begin=begin, count=x.numel(), sums=sums)
-                kw["sums"] = sums
-                kw["count"] = parallel.global_count(x.numel(), sums)
+            if normalized and (sharded or not ops.step_single_launch_ok(x.numel(), draw.grid_blocks)):
+                # Too large to keep the normals in registers across a grid barrier, or the statistics
+                # span several ranks: materialise this rank's slice once while reducing its moments
+                # (2 doubles all-reduced when sharded); the step kernel normalises on load.
+                raw = torch.empty_like(x)
+                sums = torch.empty(2, device=x.device, dtype=torch.float64)
+                ops.philox_normal_fill_moments(draw, raw, sums, begin=begin)
+                kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums) if sharded else x.numel()}
             return {"noise_philox": kw, "noise_scale": scale}
-        return {"noise_tensor": ns(sigma, sigma_next), "noise_scale": scale}
+        return {"noise_tensor": self.noise_sampler(sigma, sigma_next), "noise_scale": scale}
+
+    def _fused_noise_spec(self, x: Tensor):
+        """(factor, normalized) when the noise sampler is plain Gaussian noise of x's shape that the
+        step kernel can regenerate from the Philox stream; None otherwise. Cached per sampler."""
+        if _rng_is_injected():
+            return None
+        cached = getattr(self, "_fused_spec", False)
+        if cached is False:
+            ns = self.noise_sampler
+            spec = ns.fused_gaussian() if hasattr(ns, "fused_gaussian") else None
+            cached = self._fused_spec = None if spec is None else (spec[0], spec[1], tuple(spec[2]))
+        if cached is None or cached[2] != tuple(x.shape):
+            return None
+        return cached[0], cached[1]
 
 
 def _rng_is_injected() -> bool:
@@ -400,17 +442,36 @@ class SonarSampler(SonarWithGuidance):
         sonar_config = cls.get_config(sonar_config, sonar_params)
         s_in = x.new_ones((x.shape[0],))
         sonar = cls(*ctor_args, model, sigmas, s_in, {} if extra_args is None else extra_args, sonar_config)
-        sonar.set_noise_sampler(x, sigmas, noise_sampler, seed=extra_args.get("seed"))
+        sonar.set_noise_sampler(x, sigmas, noise_sampler, seed=(extra_args or {}).get("seed"))
         return sonar
 
 
+def ancestral_steps(sigma_from: Tensor, sigma_to: Tensor, eta: float) -> tuple[Tensor, Tensor]:
+    """get_ancestral_step for a whole schedule at once: the same float32 element-wise operations
+    (mul, sub, div, sqrt, min) the reference applies to 0-d tensors, so identical values."""
+    if not eta:
+        return sigma_to.clone(), torch.zeros_like(sigma_to)
+    sigma_up = torch.minimum(sigma_to, eta * (sigma_to**2 * (sigma_from**2 - sigma_to**2) / sigma_from**2) ** 0.5)
+    sigma_down = (sigma_to**2 - sigma_up**2) ** 0.5
+    return sigma_down, sigma_up
+
+
 class SonarEuler(SonarSampler):
+    def schedule(self) -> list:
+        """Per-step host scalars, computed once with float32 tensor arithmetic like the reference."""
+        sched = getattr(self, "_schedule", None)
+        if sched is None:
+            sh = self.sigmas_host
+            dt = (sh[1:] - sh[:-1]).tolist()
+            sched = self._schedule = list(zip(sh[:-1].tolist(), sh[1:].tolist(), dt))
+        return sched
+
     def step(self, step_index: int, sample: Tensor):
         sigma = self.sigmas[step_index]
-        sigma_h, sigma_next_h = self.sigmas_host[step_index], self.sigmas_host[step_index + 1]
+        sigma_f, sigma_next_f, dt = self.schedule()[step_index]
         denoised = self.call_model(sample, sigma)
-        result = self.momentum_step(step_index, sample, denoised, sigma_h.item(), sigma_next_h.item())
-        if sigma_next_h > 0:
+        result = self.momentum_step(step_index, sample, denoised, sigma_f, sigma_next_f, dt=dt)
+        if sigma_next_f > 0:
             result = self.guidance_step(step_index, result, denoised)
         return (result, sigma, sigma, denoised)
 
@@ -437,23 +498,37 @@ class SonarEulerAncestral(SonarSampler):
         self.eta = eta
         self.s_noise = s_noise
 
+    def schedule(self) -> list:
+        """(sigma, sigma_next, sigma_down, dt, s_noise*sigma_up) per step; get_ancestral_step and the
+        subtraction run on float32 0-d host tensors exactly as upstream (:546-551, :317)."""
+        sched = getattr(self, "_schedule", None)
+        if sched is None:
+            sh = self.sigmas_host
+            sigma_down, sigma_up = ancestral_steps(sh[:-1], sh[1:], self.eta)
+            dt = sigma_down - sh[:-1]
+            noise_scale = self.s_noise * sigma_up
+            sched = self._schedule = list(
+                zip(sh[:-1].tolist(), sh[1:].tolist(), sigma_down.tolist(), dt.tolist(), noise_scale.tolist()),
+            )
+        return sched
+
     def step(self, step_index: int, sample: Tensor):
         sigma = self.sigmas[step_index]
-        sigma_h, sigma_next_h = self.sigmas_host[step_index], self.sigmas_host[step_index + 1]
-        sigma_down, sigma_up = get_ancestral_step(sigma_h, sigma_next_h, eta=self.eta)
+        sigma_f, sigma_next_f, sigma_down_f, dt, noise_scale = self.schedule()[step_index]
         denoised = self.call_model(sample, sigma)
         noise_kw = {}
-        add_noise = bool(sigma_next_h > 0)
+        add_noise = sigma_next_f > 0
         guided = self.guidance is not None and self.guidance.factor != 0.0
         if add_noise and not guided:
             # x' = momentum_step(...) + noise * (s_noise * sigma_up): one launch
-            self.prime_history(step_index, sample, denoised, float(sigma_h))
-            noise_kw = self.ancestral_noise(sample, sigma_h, sigma_next_h, float(self.s_noise * sigma_up))
-        result = self.momentum_step(step_index, sample, denoised, float(sigma_h), float(sigma_down), **noise_kw)
+            self.prime_history(step_index, sample, denoised, sigma_f)
+            sh = self.sigmas_host
+            noise_kw = self.ancestral_noise(sample, sh[step_index], sh[step_index + 1], noise_scale)
+        result = self.momentum_step(step_index, sample, denoised, sigma_f, sigma_down_f, dt=dt, **noise_kw)
         if add_noise and guided:
             result = self.guidance_step(step_index, result, denoised)
-            drawn = self.noise_sampler(sigma_h, sigma_next_h)
-            result = ops.axpby(result.contiguous(), 1.0, drawn.contiguous(), float(self.s_noise * sigma_up))
+            drawn = self.noise_sampler(self.sigmas_host[step_index], self.sigmas_host[step_index + 1])
+            result = ops.axpby(result.contiguous(), 1.0, drawn.contiguous(), noise_scale)
         return (result, sigma, sigma, denoised)
 
     @classmethod
@@ -494,54 +569,104 @@ class SonarDPMPPSDE(SonarSampler):
     def t_fn(sigma: Tensor) -> Tensor:
         return sigma.log().neg()
 
-    def dpm_step(self, step_index: int, x: Tensor, denoised: Tensor, sigma_h: Tensor, sigma_next_h: Tensor) -> Tensor:
-        # host float32 scalars, same op sequence as the reference (:669-719)
+    def schedule(self) -> list:
+        """Per-step coefficients of both half steps, host float32 tensor math in the reference's op
+        order (:669-719), plus the mid-point sigmas on the device for the second model call."""
+        sched = getattr(self, "_schedule", None)
+        if sched is not None:
+            return sched
+        sh = self.sigmas_host
+        sigma, sigma_next = sh[:-1], sh[1:]
+        last = sigma_next == 0
+        safe_next = torch.where(last, sigma, sigma_next)  # keep log() finite on the final step
         r = 1 / 2
-        t, t_next = self.t_fn(sigma_h), self.t_fn(sigma_next_h)
+        t, t_next = self.t_fn(sigma), self.t_fn(safe_next)
         h = t_next - t
         s = t + h * r
         s_t, s_s = self.sigma_fn(t), self.sigma_fn(s)
-        sd, su = get_ancestral_step(s_t, s_s, self.eta)
+        sd, su = ancestral_steps(s_t, s_s, self.eta)
         s_ = self.t_fn(sd)
-        guided = self.guidance is not None and self.guidance.factor != 0.0
-
-        # ---- stage 1: x_2 = (sigma_fn(s_)/s_t) * x - momentum(expm1(t - s_) * denoised) + noise ----
-        self.prime_history(step_index, x, denoised, float(sigma_h))
-        noise_kw = self.ancestral_noise(x, s_t, s_s, float(self.s_noise * su))
-        x_2 = self.fused_step(
-            step_index, x, denoised, float(sigma_h),
-            kind=ops.STEP_DPMPP, c0=float((t - s_).expm1()), c1=float(self.sigma_fn(s_) / s_t), **noise_kw,
-        )  # fmt: skip
-        sigma_2 = s_s
-        denoised_2 = self.call_model(x_2, sigma_2.to(self.sigmas.device))
-
-        # ---- stage 2 (fac = 1/(2r) = 1: denoised_d = 0*md1 + 1*md2) ----
         s_t_next = self.sigma_fn(t_next)
-        sd, su = get_ancestral_step(s_t, s_t_next, self.eta)
-        t_down = self.t_fn(sd)
+        sd2, su2 = ancestral_steps(s_t, s_t_next, self.eta)
+        t_down = self.t_fn(sd2)
+        cols = {
+            "sigma": sigma, "sigma_2": s_s,
+            "c0_1": (t - s_).expm1(), "c1_1": self.sigma_fn(s_) / s_t, "ns_1": self.s_noise * su,
+            "c0_2": (t - t_down).expm1(), "c1_2": self.sigma_fn(t_down) / s_t, "ns_2": self.s_noise * su2,
+        }  # fmt: skip
+        cols = {k: v.tolist() for k, v in cols.items()}
+        down_last, _ = ancestral_steps(sigma, sigma_next, self.eta)
+        dt_last = (down_last - sigma).tolist()
+        down_last = down_last.tolist()
+        sched = self._schedule = []
+        for i in range(len(sigma)):
+            if bool(last[i]):
+                sched.append({"last": True, "sigma": cols["sigma"][i], "sigma_down": down_last[i], "dt": dt_last[i]})
+            else:
+                row = {k: v[i] for k, v in cols.items()}
+                row |= {"last": False, "s_t": s_t[i], "s_s": s_s[i], "s_t_next": s_t_next[i]}
+                sched.append(row)
+        self._sigma_mid_dev = s_s.to(self.sigmas.device, non_blocking=True)
+        return sched
+        sched = self._schedule = []
+        sh = self.sigmas_host
+        mids = []
+        for i in range(len(sh) - 1):
+            sigma, sigma_next = sh[i], sh[i + 1]
+            if sigma_next == 0:
+                sigma_down, _ = get_ancestral_step(sigma, sigma_next, eta=self.eta)
+                sigma_down = torch.as_tensor(sigma_down, dtype=torch.float32)
+                sched.append({"last": True, "sigma": float(sigma), "sigma_down": float(sigma_down), "dt": float(sigma_down - sigma)})
+                mids.append(torch.zeros(()))
+                continue
+            r = 1 / 2
+            t, t_next = self.t_fn(sigma), self.t_fn(sigma_next)
+            h = t_next - t
+            s = t + h * r
+            s_t, s_s = self.sigma_fn(t), self.sigma_fn(s)
+            sd, su = get_ancestral_step(s_t, s_s, self.eta)
+            s_ = self.t_fn(torch.as_tensor(sd))
+            s_t_next = self.sigma_fn(t_next)
+            sd2, su2 = get_ancestral_step(s_t, s_t_next, self.eta)
+            t_down = self.t_fn(torch.as_tensor(sd2))
+            sched.append(
+                {
+                    "last": False,
+                    "sigma": float(sigma),
+                    "s_t": s_t, "s_s": s_s, "s_t_next": s_t_next,
+                    "sigma_2": float(s_s),
+                    "c0_1": float((t - s_).expm1()), "c1_1": float(self.sigma_fn(s_) / s_t), "ns_1": float(self.s_noise * su),
+                    "c0_2": float((t - t_down).expm1()), "c1_2": float(self.sigma_fn(t_down) / s_t), "ns_2": float(self.s_noise * su2),
+                },  # fmt: skip
+            )
+            mids.append(s_s)
+        self._sigma_mid_dev = torch.stack(mids).to(self.sigmas.device, non_blocking=True)
+        return sched
+
+    def dpm_step(self, step_index: int, x: Tensor, denoised: Tensor, sc: dict) -> Tensor:
+        guided = self.guidance is not None and self.guidance.factor != 0.0
+        # ---- stage 1: x_2 = (sigma_fn(s_)/s_t) * x - momentum(expm1(t - s_) * denoised) + noise ----
+        self.prime_history(step_index, x, denoised, sc["sigma"])
+        noise_kw = self.ancestral_noise(x, sc["s_t"], sc["s_s"], sc["ns_1"])
+        x_2 = self.fused_step(step_index, x, denoised, sc["sigma"], kind=ops.STEP_DPMPP, c0=sc["c0_1"], c1=sc["c1_1"], **noise_kw)
+        denoised_2 = self.call_model(x_2, self._sigma_mid_dev[step_index])
+        # ---- stage 2 (fac = 1/(2r) = 1: denoised_d = 0*md1 + 1*md2) ----
         if guided:
-            out = self.fused_step(
-                step_index, x, denoised_2, float(sigma_2),
-                kind=ops.STEP_DPMPP, c0=float((t - t_down).expm1()), c1=float(self.sigma_fn(t_down) / s_t),
-            )  # fmt: skip
+            out = self.fused_step(step_index, x, denoised_2, sc["sigma_2"], kind=ops.STEP_DPMPP, c0=sc["c0_2"], c1=sc["c1_2"])
             out = self.guidance_step(step_index, out, denoised_2)
-            drawn = self.noise_sampler(s_t, s_t_next)
-            return ops.axpby(out.contiguous(), 1.0, drawn.contiguous(), float(self.s_noise * su))
-        noise_kw = self.ancestral_noise(x, s_t, s_t_next, float(self.s_noise * su))
-        return self.fused_step(
-            step_index, x, denoised_2, float(sigma_2),
-            kind=ops.STEP_DPMPP, c0=float((t - t_down).expm1()), c1=float(self.sigma_fn(t_down) / s_t), **noise_kw,
-        )  # fmt: skip
+            drawn = self.noise_sampler(sc["s_t"], sc["s_t_next"])
+            return ops.axpby(out.contiguous(), 1.0, drawn.contiguous(), sc["ns_2"])
+        noise_kw = self.ancestral_noise(x, sc["s_t"], sc["s_t_next"], sc["ns_2"])
+        return self.fused_step(step_index, x, denoised_2, sc["sigma_2"], kind=ops.STEP_DPMPP, c0=sc["c0_2"], c1=sc["c1_2"], **noise_kw)
 
     def step(self, step_index: int, sample: Tensor):
         sigma = self.sigmas[step_index]
-        sigma_h, sigma_next_h = self.sigmas_host[step_index], self.sigmas_host[step_index + 1]
+        sc = self.schedule()[step_index]
         denoised = self.call_model(sample, sigma)
-        if sigma_next_h == 0:
-            sigma_down, _ = get_ancestral_step(sigma_h, sigma_next_h, eta=self.eta)
-            result = self.momentum_step(step_index, sample, denoised, float(sigma_h), float(sigma_down))
+        if sc["last"]:
+            result = self.momentum_step(step_index, sample, denoised, sc["sigma"], sc["sigma_down"], dt=sc["dt"])
         else:
-            result = self.dpm_step(step_index, sample, denoised, sigma_h, sigma_next_h)
+            result = self.dpm_step(step_index, sample, denoised, sc)
         return (result, sigma, sigma, denoised)
 
     @classmethod

@@ -60,6 +60,9 @@ int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t n
 int sonar_moments_f32(const float* x, int64_t n, double* sums, void* stream);
 int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_total, uint64_t seed, uint64_t offset,
                                 uint32_t grid_blocks, double* sums, void* stream);
+/* materialise the slice AND write (not accumulate) its moments into sums, one pass */
+int sonar_philox_normal_fill_moments_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
+                                         uint64_t offset, uint32_t grid_blocks, double* sums, void* stream);
 int sonar_scale_noise_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float factor,
                           float threshold_std_devs, void* stream);
 int sonar_add_moments_f32(const float* a, const float* b, float* out, int64_t n, double* sums, void* stream);
@@ -85,7 +88,8 @@ enum {
   SONAR_NOISE_NONE = 0,
   SONAR_NOISE_TENSOR = 1,            /* noise read from `noise` */
   SONAR_NOISE_PHILOX = 2,            /* torch.randn(device='cuda') regenerated in registers */
-  SONAR_NOISE_PHILOX_NORMALIZED = 3  /* ... followed by scale_noise from `noise_sums` */
+  SONAR_NOISE_PHILOX_NORMALIZED = 3, /* ... followed by scale_noise from `noise_sums` */
+  SONAR_NOISE_TENSOR_NORMALIZED = 4  /* raw Gaussian in `noise`, scale_noise applied on load from `noise_sums` */
 };
 
 typedef struct SonarStepParams {
@@ -124,11 +128,21 @@ typedef struct SonarStepParams {
   uint32_t philox_grid_blocks;
   int64_t noise_begin;
   int64_t noise_numel_total;
-  const double* noise_sums; /* double[2], PHILOX_NORMALIZED */
+  const double* noise_sums; /* double[2], PHILOX_NORMALIZED: externally reduced sums (batch-sharded
+                               runs all-reduce them); NULL = let this call do the moments pre-pass */
   int64_t noise_count;      /* global count behind noise_sums */
+  /* noise_sums == NULL: double[4] scratch (two ping-pong slots, zeroed ONCE by the caller) + which
+   * slot this launch uses. Small tensors then take a single cooperative launch (moments -> grid
+   * barrier -> step, normals kept in registers); large ones a moments launch + a step launch. */
+  double* sums_scratch;
+  int32_t sums_parity;
 } SonarStepParams;
 
 int sonar_step_f32(const SonarStepParams* params_host, void* stream);
+/* 1 if a PHILOX_NORMALIZED step over n elements with noise_sums == NULL takes the single cooperative
+ * launch (moments -> grid barrier -> step); callers with larger tensors materialise the noise with
+ * sonar_philox_normal_fill_moments_f32 and use SONAR_NOISE_TENSOR_NORMALIZED instead. */
+int sonar_step_single_launch_ok(int64_t n, uint32_t philox_grid_blocks);
 
 /* ------------------------------------------------------------------------------------------------
  * Pyramid family: fused multi-level resample-and-accumulate.

@@ -98,7 +98,7 @@ def test_philox_moments_match_materialised(sb, cuda):
     torch.manual_seed(8)
     x = torch.randn(n, device=cuda).double()
     want = torch.stack((x.sum(), (x * x).sum()))
-    torch.testing.assert_close(sums, want, rtol=1e-12, atol=1e-9)
+    torch.testing.assert_close(sums, want, rtol=1e-6, atol=1e-3)  # per-thread partials are fp32
 
 
 def test_empty_and_errors(sb, cuda):

@@ -96,6 +96,33 @@ def test_fused_philox_noise_equals_tensor_noise(sb, cuda):
     assert_close(fused, plain, what="fused vs tensor noise", rtol=1e-6, atol=1e-5)
 
 
+def test_fused_noise_large_tensor_path(sb, cuda):
+    """Tensors too large for the single cooperative launch: noise materialised once with its
+    moments, normalised on load by the step kernel -- same values and generator advance as
+    torch.randn + scale_noise (config C5 per-GPU shard shape, DPM++ SDE)."""
+    sigmas = torch.tensor([14.6, 6.0, 1.5, 0.0])
+    torch.manual_seed(0)
+    x0 = (torch.randn(1, 16, 33, 90, 160) * sigmas[0]).to(cuda)
+    assert not sb.ops.step_single_launch_ok(x0.numel(), sb.ops.philox_policy(x0.numel())[0])
+
+    def run(explicit):
+        torch.manual_seed(5)
+        ns = None
+        if explicit:
+            def ns(_s, _sn):
+                return sb.hostutil.scale_noise(torch.randn(x0.shape, device=cuda), 1.0, normalized=True)
+        out = sb.samplers.SonarDPMPPSDE.sampler(
+            lambda x, s, **k: x * 0.9, x0.clone(), sigmas.to(cuda), extra_args={"seed": 0}, disable=True,
+            sonar_params={"noise_type": "gaussian"}, noise_sampler=ns,
+        )
+        return out, torch.cuda.default_generators[0].get_offset()
+
+    fused, off_a = run(False)
+    plain, off_b = run(True)
+    assert off_a == off_b
+    assert_close(fused, plain, what="large fused vs tensor noise", rtol=1e-6, atol=1e-5)
+
+
 def test_c2_full_size_vs_oracle(sb, cuda):
     """BASELINE.json config C2: sonar_euler_ancestral, SDXL latents 8x4x128x128, 30 steps."""
     torch.manual_seed(1)
