@@ -409,6 +409,11 @@ def _time_traced(sb, fn, reps: int, flush: torch.Tensor) -> tuple[float, dict]:
     """Mean total kernel time (us) and per-kernel means over `reps` traced invocations."""
     for _ in range(3):
         fn()
+    t_end = time.perf_counter() + 0.3  # the GPU drops to idle clocks while Python sets a config up
+    while time.perf_counter() < t_end:
+        flush.zero_()
+        fn()
+    torch.cuda.synchronize()
     totals, per = [], {}
     for _ in range(reps):
         flush.zero_()

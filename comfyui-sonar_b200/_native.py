@@ -188,6 +188,7 @@ SIGNATURES: dict[str, list] = {
     "sonar_affine_f32": [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p],
     "sonar_step_f32": [POINTER(SonarStepParams), c_void_p],
     "sonar_step_single_launch_ok": [c_int64, c_uint32],
+    "sonar_step_enable_cooperative": [c_int],
     "sonar_philox_normal_fill_moments_f32": [
         c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p,
     ],

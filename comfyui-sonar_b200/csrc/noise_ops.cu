@@ -121,6 +121,101 @@ pyramid_accum_kernel(SonarPyramidParams p) {
   }
 }
 
+// Table-driven variant (bilinear / nearest-exact): the x taps of every level depend only on x, so
+// each CTA computes them once into shared memory; a warp then walks whole rows, computing the y taps
+// once per row. Per pixel and level that leaves 3 table reads, 4 cached loads and 6 FMAs instead of
+// the float divisions and tap arithmetic of the generic path.
+constexpr int kRowUnroll = 4;  // pixels per lane per pass, 32 apart: conflict-free tables, coalesced rows
+
+__global__ void __launch_bounds__(kBlock)
+pyramid_rows_kernel(SonarPyramidParams p) {
+  extern __shared__ __align__(16) unsigned char pyr_smem[];
+  const int W = p.W, H = p.H;
+  // structure-of-arrays tables [n_levels][W]
+  int* tab_i0 = reinterpret_cast<int*>(pyr_smem);
+  int* tab_i1 = tab_i0 + p.n_levels * W;
+  float* tab_w1 = reinterpret_cast<float*>(tab_i1 + p.n_levels * W);
+  for (int i = threadIdx.x; i < p.n_levels * W; i += blockDim.x) {
+    const int l = i / W, x = i - l * W;
+    const int lw = p.level_w[l];
+    if (p.mode == SONAR_RESAMPLE_BILINEAR) {
+      const LinTap lt = linear_tap(x, lw, (float)lw / (float)W);
+      tab_i0[i] = lt.i0;
+      tab_i1[i] = lt.i1;
+      tab_w1[i] = lt.w1;
+    } else {
+      tab_i0[i] = tab_i1[i] = nearest_exact_idx(x, lw, (float)lw / (float)W);
+      tab_w1[i] = 0.0f;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t n_rows = p.planes * (int64_t)H;
+  for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
+       row += (int64_t)gridDim.x * warps_per_block) {
+    const int y = (int)(row % H);
+    const int64_t plane = row / H;
+    const int64_t obase = row * W;
+    for (int x0 = lane; x0 < W; x0 += 32 * kRowUnroll) {
+      float acc[kRowUnroll];
+      bool ok[kRowUnroll];
+#pragma unroll
+      for (int v = 0; v < kRowUnroll; ++v) {
+        const int x = x0 + 32 * v;
+        ok[v] = x < W;
+        acc[v] = (ok[v] && p.base != nullptr) ? __ldg(p.base + obase + x) : 0.0f;
+        if (p.base_scale != 1.0f) acc[v] *= p.base_scale;
+      }
+      for (int l = 0; l < p.n_levels; ++l) {
+        const int lh = p.level_h[l], lw = p.level_w[l];
+        const float* src = p.levels[l] + plane * (int64_t)lh * lw;
+        const float wgt = p.weights[l];
+        if (lh == H && lw == W) {  // identity level: straight copy-accumulate
+          const float* r = src + (int64_t)y * W;
+#pragma unroll
+          for (int v = 0; v < kRowUnroll; ++v)
+            if (ok[v]) acc[v] = acc[v] + __fmul_rn(__ldg(r + x0 + 32 * v), wgt);
+          continue;
+        }
+        const float* r0;
+        const float* r1;
+        float wy0, wy1;
+        if (p.mode == SONAR_RESAMPLE_BILINEAR) {
+          const LinTap ty = linear_tap(y, lh, (float)lh / (float)H);
+          r0 = src + (int64_t)ty.i0 * lw;
+          r1 = src + (int64_t)ty.i1 * lw;
+          wy0 = ty.w0;
+          wy1 = ty.w1;
+        } else {
+          r0 = r1 = src + (int64_t)nearest_exact_idx(y, lh, (float)lh / (float)H) * lw;
+          wy0 = 1.0f;
+          wy1 = 0.0f;
+        }
+        const int tb = l * W;
+#pragma unroll
+        for (int v = 0; v < kRowUnroll; ++v) {
+          if (!ok[v]) continue;
+          const int x = x0 + 32 * v;
+          const int i0 = tab_i0[tb + x];
+          float sv;
+          if (p.mode == SONAR_RESAMPLE_BILINEAR) {
+            const int i1 = tab_i1[tb + x];
+            const float w1 = tab_w1[tb + x], w0 = 1.0f - w1;
+            sv = wy0 * (w0 * __ldg(r0 + i0) + w1 * __ldg(r0 + i1)) + wy1 * (w0 * __ldg(r1 + i0) + w1 * __ldg(r1 + i1));
+          } else {
+            sv = __ldg(r0 + i0);
+          }
+          acc[v] = acc[v] + __fmul_rn(sv, wgt);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < kRowUnroll; ++v)
+        if (ok[v]) p.out[obase + x0 + 32 * v] = acc[v];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Perlin: grid cell == 1 pixel, so every output is the blend of four corner gradients dotted with
 // (+-0.5, +-0.5) (closed form verified against perlin_noise).
@@ -302,7 +397,19 @@ int sonar_pyramid_accum_f32(const SonarPyramidParams* params, void* stream) {
   if (p.n_levels < 0 || p.n_levels > SONAR_PYRAMID_MAX_LEVELS || p.out == nullptr) return (int)cudaErrorInvalidValue;
   for (int l = 0; l < p.n_levels; ++l)
     if (p.levels[l] == nullptr || p.level_h[l] <= 0 || p.level_w[l] <= 0) return (int)cudaErrorInvalidValue;
-  const bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
+  bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
+  for (int l = 0; l < p.n_levels; ++l)
+    if (p.level_h[l] == p.H && p.level_w[l] == p.W && !aligned16(p.levels[l])) vec = false;
+  const size_t tab_bytes = (size_t)p.n_levels * p.W * 12;
+  if (p.mode != SONAR_RESAMPLE_AREA && p.n_levels > 0 && tab_bytes <= 96 * 1024) {
+    // table-driven row kernel; one warp per row, grid sized to whole waves
+    const int64_t n_rows = p.planes * (int64_t)p.H;
+    const int grid = streaming_grid(n_rows, kBlock / 32, 2);
+    SONAR_CUDA_TRY(cudaFuncSetAttribute(pyramid_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+    pyramid_rows_kernel<<<grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p);
+    SONAR_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t total = p.planes * (int64_t)p.H * (vec ? p.W / 4 : p.W);
   const int grid = streaming_grid(total, kBlock, 4);
   if (vec)

@@ -280,17 +280,23 @@ sonar_step_coop_kernel(SonarStepParams p, PhiloxStream st, uint32_t calls, doubl
 }  // namespace sonar
 
 namespace sonar {
+static int g_coop_enabled = -1;  // -1: decide from the environment on first use
+
 static int coop_blocks_per_sm() {
-  static thread_local int cached = -1;
-  if (cached < 0) {
+  static thread_local int occupancy = -1;
+  if (occupancy < 0) {
     int dev = 0, coop = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cached = 0;
-    if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached, sonar_step_coop_kernel, kBlock, 0);
-    if (getenv("SONAR_B200_NO_COOP") != nullptr) cached = 0;
+    occupancy = 0;
+    if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, sonar_step_coop_kernel, kBlock, 0);
   }
-  return cached;
+  // Measured on B200 (profiles/): at 8x4x128x128 the cooperative launch takes 18 us against ~14 us for
+  // "materialise + moments" followed by the float4 step kernel -- the ALU-bound Philox phase and the
+  // memory phase cannot overlap across the grid barrier. Hence opt-in (SONAR_B200_COOP=1 or
+  // sonar_step_enable_cooperative(1)).
+  if (g_coop_enabled < 0) g_coop_enabled = getenv("SONAR_B200_COOP") != nullptr ? 1 : 0;
+  return g_coop_enabled ? occupancy : 0;
 }
 
 // cooperative grid for a draw of `grid_blocks` emulated ATen blocks covering n elements, or 0
@@ -305,6 +311,11 @@ static int64_t coop_grid_for(int64_t n, uint32_t grid_blocks) {
   return pairs <= kCoopPairs ? g : 0;
 }
 }  // namespace sonar
+
+extern "C" int sonar_step_enable_cooperative(int enable) {
+  sonar::g_coop_enabled = enable ? 1 : 0;
+  return 0;
+}
 
 extern "C" int sonar_step_single_launch_ok(int64_t n, uint32_t philox_grid_blocks) {
   return sonar::coop_grid_for(n, philox_grid_blocks) > 0 ? 1 : 0;

@@ -33,6 +33,9 @@ struct FftPlan {
   int n;
   int n_factors;
   int factors[SONAR_FFT_MAX_FACTORS];
+  int ns[SONAR_FFT_MAX_FACTORS];       // product of the radices before stage f
+  int tab_off[SONAR_FFT_MAX_FACTORS];  // offset of stage f in the butterfly table
+  int tab_size;
 };
 
 // tw[k] = exp(-2*pi*i*k/n); inverse transforms conjugate on the fly.
@@ -41,65 +44,120 @@ __device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int idx
   return inverse ? make_float2(w.x, -w.y) : w;
 }
 
+// multiply by -i (forward) / +i (inverse)
+__device__ __forceinline__ float2 rot90(float2 d, bool inverse) {
+  return inverse ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+}
+
+// Per-stage butterfly table, built once per CTA: for butterfly j of stage f
+//   .x = output base  (j / Ns) * Ns * R + (j % Ns)      .y = twiddle base (j % Ns) * N / (Ns * R)
+// so the transform loops contain no integer division.
+__device__ void build_fft_table(const FftPlan& plan, ushort2* __restrict__ tab) {
+  for (int f = 0; f < plan.n_factors; ++f) {
+    const int R = plan.factors[f], Ns = plan.ns[f], stride = plan.n / R, tw_step = plan.n / (Ns * R);
+    for (int j = threadIdx.x; j < stride; j += blockDim.x) {
+      const int k = j % Ns;
+      tab[plan.tab_off[f] + j] = make_ushort2((unsigned short)((j / Ns) * Ns * R + k), (unsigned short)(k * tw_step));
+    }
+  }
+}
+
 // Warp-cooperative Stockham autosort FFT of length plan.n. Input in `a`; returns the buffer that
 // holds the result (a or b). Unnormalised. All 32 lanes must call.
-__device__ float2* warp_fft(float2* a, float2* b, const FftPlan& plan, const float2* __restrict__ tw, bool inverse,
-                            int lane) {
+template <bool INVERSE>
+__device__ float2* warp_fft(float2* a, float2* b, const FftPlan& plan, const float2* __restrict__ tw,
+                            const ushort2* __restrict__ tab, int lane) {
   const int N = plan.n;
-  int Ns = 1;
   float2* src = a;
   float2* dst = b;
   for (int f = 0; f < plan.n_factors; ++f) {
     const int R = plan.factors[f];
-    const int stride = N / R;          // distance between the R inputs of one butterfly
-    const int tw_step = N / (Ns * R);  // w_N^(tw_step * k * s) == exp(-2 pi i k s / (Ns R))
-    if (R == 2) {
+    const int Ns = plan.ns[f];
+    const int stride = N / R;  // distance between the R inputs of one butterfly
+    const ushort2* t = tab + plan.tab_off[f];
+    if (R == 4) {
       for (int j = lane; j < stride; j += 32) {
-        const int k = j % Ns;
+        const ushort2 ix = t[j];
+        const int tb = ix.y;
         const float2 v0 = src[j];
-        const float2 v1 = cmul(src[j + stride], twiddle(tw, k * tw_step, inverse));
-        const int j0 = (j / Ns) * Ns * 2 + k;
-        dst[j0] = cadd(v0, v1);
-        dst[j0 + Ns] = csub(v0, v1);
-      }
-    } else if (R == 4) {
-      for (int j = lane; j < stride; j += 32) {
-        const int k = j % Ns;
-        const int base = k * tw_step;
-        const float2 v0 = src[j];
-        const float2 v1 = cmul(src[j + stride], twiddle(tw, base, inverse));
-        const float2 v2 = cmul(src[j + 2 * stride], twiddle(tw, 2 * base, inverse));
-        const float2 v3 = cmul(src[j + 3 * stride], twiddle(tw, 3 * base, inverse));
+        const float2 v1 = cmul(src[j + stride], twiddle(tw, tb, INVERSE));
+        const float2 v2 = cmul(src[j + 2 * stride], twiddle(tw, 2 * tb, INVERSE));
+        const float2 v3 = cmul(src[j + 3 * stride], twiddle(tw, 3 * tb, INVERSE));
         const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3);
-        const float2 d = csub(v1, v3);
-        // multiply by -i (forward) or +i (inverse)
-        const float2 a3 = inverse ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
-        const int j0 = (j / Ns) * Ns * 4 + k;
-        dst[j0] = cadd(a0, a2);
-        dst[j0 + Ns] = cadd(a1, a3);
-        dst[j0 + 2 * Ns] = csub(a0, a2);
-        dst[j0 + 3 * Ns] = csub(a1, a3);
+        const float2 a3 = rot90(csub(v1, v3), INVERSE);
+        float2* o = dst + ix.x;
+        o[0] = cadd(a0, a2);
+        o[Ns] = cadd(a1, a3);
+        o[2 * Ns] = csub(a0, a2);
+        o[3 * Ns] = csub(a1, a3);
+      }
+    } else if (R == 2) {
+      for (int j = lane; j < stride; j += 32) {
+        const ushort2 ix = t[j];
+        const float2 v0 = src[j];
+        const float2 v1 = cmul(src[j + stride], twiddle(tw, ix.y, INVERSE));
+        dst[ix.x] = cadd(v0, v1);
+        dst[ix.x + Ns] = csub(v0, v1);
+      }
+    } else if (R == 3) {
+      for (int j = lane; j < stride; j += 32) {
+        const ushort2 ix = t[j];
+        const int tb = ix.y;
+        const float2 v0 = src[j];
+        const float2 v1 = cmul(src[j + stride], twiddle(tw, tb, INVERSE));
+        const float2 v2 = cmul(src[j + 2 * stride], twiddle(tw, 2 * tb, INVERSE));
+        const float2 t1 = cadd(v1, v2);
+        const float2 t2 = make_float2(v0.x - 0.5f * t1.x, v0.y - 0.5f * t1.y);
+        const float2 d = csub(v1, v2);
+        const float2 t3 = rot90(make_float2(0.86602540378443865f * d.x, 0.86602540378443865f * d.y), INVERSE);
+        float2* o = dst + ix.x;
+        o[0] = cadd(v0, t1);
+        o[Ns] = cadd(t2, t3);
+        o[2 * Ns] = csub(t2, t3);
+      }
+    } else if (R == 5) {
+      constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+      constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+      for (int j = lane; j < stride; j += 32) {
+        const ushort2 ix = t[j];
+        const int tb = ix.y;
+        const float2 v0 = src[j];
+        const float2 v1 = cmul(src[j + stride], twiddle(tw, tb, INVERSE));
+        const float2 v2 = cmul(src[j + 2 * stride], twiddle(tw, 2 * tb, INVERSE));
+        const float2 v3 = cmul(src[j + 3 * stride], twiddle(tw, 3 * tb, INVERSE));
+        const float2 v4 = cmul(src[j + 4 * stride], twiddle(tw, 4 * tb, INVERSE));
+        const float2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), b1 = csub(v1, v4), b2 = csub(v2, v3);
+        const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
+        const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
+        const float2 n1 = rot90(make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y), INVERSE);
+        const float2 n2 = rot90(make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y), INVERSE);
+        float2* o = dst + ix.x;
+        o[0] = make_float2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
+        o[Ns] = cadd(m1, n1);
+        o[2 * Ns] = cadd(m2, n2);
+        o[3 * Ns] = csub(m2, n2);
+        o[4 * Ns] = csub(m1, n1);
       }
     } else {
       // generic (prime) radix: each output is a direct R-term sum; one table lookup per term
       const int rot = N / R;
+      const int tw_step = N / (Ns * R);
       for (int o = lane; o < N; o += 32) {
         const int j = o % stride;   // butterfly
-        const int t = o / stride;   // which output of it
+        const int tt = o / stride;  // which output of it
         const int k = j % Ns;
-        const int step = (k * tw_step + t * rot) % N;
+        const int step = (k * tw_step + tt * rot) % N;
         float2 acc = src[j];
         int idx = 0;
-        for (int s = 1; s < R; ++s) {
+        for (int s2 = 1; s2 < R; ++s2) {
           idx += step;
           if (idx >= N) idx -= N;
-          acc = cadd(acc, cmul(src[j + s * stride], twiddle(tw, idx, inverse)));
+          acc = cadd(acc, cmul(src[j + s2 * stride], twiddle(tw, idx, INVERSE)));
         }
-        dst[(j / Ns) * Ns * R + k + t * Ns] = acc;
+        dst[(j / Ns) * Ns * R + k + tt * Ns] = acc;
       }
     }
     __syncwarp();
-    Ns *= R;
     float2* tmp = src;
     src = dst;
     dst = tmp;
@@ -117,7 +175,7 @@ struct SpectralLaunch {
   int spectrum_in_smem;
 };
 
-__global__ void __launch_bounds__(kFftThreads, 1)
+__global__ void __launch_bounds__(kFftThreads, 2)
 spectral_plane_kernel(SpectralLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SonarSpectralParams& p = L.p;
@@ -129,8 +187,14 @@ spectral_plane_kernel(SpectralLaunch L) {
   float2* warp_buf = tw_w + W + (size_t)warp * 2 * L.nmax;
   float2* bufA = warp_buf;
   float2* bufB = warp_buf + L.nmax;
-  float2* S = L.spectrum_in_smem ? (tw_w + W + (size_t)kFftWarps * 2 * L.nmax)
-                                 : (reinterpret_cast<float2*>(p.scratch) + (size_t)blockIdx.x * H * WhP);
+  float2* after_bufs = tw_w + W + (size_t)kFftWarps * 2 * L.nmax;
+  ushort2* tab_h = reinterpret_cast<ushort2*>(after_bufs);
+  ushort2* tab_w = tab_h + L.plan_h.tab_size;
+  float2* S = L.spectrum_in_smem
+                  ? reinterpret_cast<float2*>(tab_w + L.plan_w.tab_size + ((L.plan_h.tab_size + L.plan_w.tab_size) & 1))
+                  : (reinterpret_cast<float2*>(p.scratch) + (size_t)blockIdx.x * H * WhP);
+  build_fft_table(L.plan_h, tab_h);
+  build_fft_table(L.plan_w, tab_w);
 
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     double s, c;
@@ -153,7 +217,7 @@ spectral_plane_kernel(SpectralLaunch L) {
         for (int x = lane; x < W; x += 32)
           bufA[x] = make_float2(src[(int64_t)y * W + x], pair ? src[(int64_t)(y + 1) * W + x] : 0.0f);
         __syncwarp();
-        const float2* Z = warp_fft(bufA, bufB, L.plan_w, tw_w, false, lane);
+        const float2* Z = warp_fft<false>(bufA, bufB, L.plan_w, tw_w, tab_w, lane);
         // X1[k] = (Z[k] + conj(Z[-k])) / 2 ; X2[k] = (Z[k] - conj(Z[-k])) / (2i)
         for (int k = lane; k < Wh; k += 32) {
           const float2 zk = Z[k];
@@ -182,7 +246,7 @@ spectral_plane_kernel(SpectralLaunch L) {
       float2* cur = bufA;
       float2* other = bufB;
       if (p.in_real != nullptr) {
-        cur = warp_fft(bufA, bufB, L.plan_h, tw_h, false, lane);
+        cur = warp_fft<false>(bufA, bufB, L.plan_h, tw_h, tab_h, lane);
         other = cur == bufA ? bufB : bufA;
       }
       if (p.mask != nullptr) {
@@ -193,7 +257,7 @@ spectral_plane_kernel(SpectralLaunch L) {
         }
         __syncwarp();
       }
-      const float2* res = warp_fft(cur, other, L.plan_h, tw_h, true, lane);
+      const float2* res = warp_fft<true>(cur, other, L.plan_h, tw_h, tab_h, lane);
       for (int y = lane; y < H; y += 32) S[(size_t)y * WhP + k] = res[y];
       __syncwarp();
     }
@@ -224,7 +288,7 @@ spectral_plane_kernel(SpectralLaunch L) {
         bufA[k] = make_float2(z1.x - z2.y, z1.y + z2.x);
       }
       __syncwarp();
-      const float2* z = warp_fft(bufA, bufB, L.plan_w, tw_w, true, lane);
+      const float2* z = warp_fft<true>(bufA, bufB, L.plan_w, tw_w, tab_w, lane);
       for (int x = lane; x < W; x += 32) {
         const float2 v = z[x];
         dst[(int64_t)y * W + x] = v.x * p.out_scale;
@@ -239,6 +303,8 @@ spectral_plane_kernel(SpectralLaunch L) {
 static bool make_plan(int n, FftPlan* plan) {
   plan->n = n;
   plan->n_factors = 0;
+  plan->tab_size = 0;
+  if (n > 65535) return false;
   int rem = n;
   auto push = [&](int f) {
     if (plan->n_factors >= SONAR_FFT_MAX_FACTORS) return false;
@@ -255,8 +321,21 @@ static bool make_plan(int n, FftPlan* plan) {
       rem /= f;
     }
   if (rem > 1 && !push(rem)) return false;
-  if (n == 1) plan->n_factors = 0;
+  int ns = 1;
+  for (int f = 0; f < plan->n_factors; ++f) {
+    plan->ns[f] = ns;
+    plan->tab_off[f] = plan->tab_size;
+    plan->tab_size += n / plan->factors[f];
+    ns *= plan->factors[f];
+  }
   return true;
+}
+
+static size_t fixed_smem_bytes(int H, int W, const FftPlan& ph, const FftPlan& pw) {
+  const int nmax = H > W ? H : W;
+  size_t tab = (size_t)(ph.tab_size + pw.tab_size);
+  tab += tab & 1;  // keep the spectrum 8-byte aligned
+  return ((size_t)H + W + (size_t)kFftWarps * 2 * nmax) * sizeof(float2) + tab * sizeof(ushort2);
 }
 
 }  // namespace sonar
@@ -266,12 +345,14 @@ extern "C" {
 int64_t sonar_spectral_scratch_bytes(int H, int W) {
   using namespace sonar;
   if (H <= 0 || W <= 0) return 0;
-  const int wh = W / 2 + 1, wh_pad = wh | 1, nmax = H > W ? H : W;
-  const size_t fixed = ((size_t)H + W + (size_t)kFftWarps * 2 * nmax) * sizeof(float2);
+  FftPlan ph, pw;
+  if (!make_plan(H, &ph) || !make_plan(W, &pw)) return 0;
+  const int wh = W / 2 + 1, wh_pad = wh | 1;
+  const size_t fixed = fixed_smem_bytes(H, W, ph, pw);
   const size_t spec = (size_t)H * wh_pad * sizeof(float2);
   const DeviceInfo& di = device_info();
   if (fixed + spec <= (size_t)di.max_smem_optin) return 0;
-  return (int64_t)spec * di.sm_count;
+  return (int64_t)spec * di.sm_count * 2;
 }
 
 int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) {
@@ -288,18 +369,15 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) 
   L.wh_pad = L.wh | 1;
   L.nmax = p.H > p.W ? p.H : p.W;
   const DeviceInfo& di = device_info();
-  const size_t fixed = ((size_t)p.H + p.W + (size_t)kFftWarps * 2 * L.nmax) * sizeof(float2);
+  const size_t fixed = fixed_smem_bytes(p.H, p.W, L.plan_h, L.plan_w);
   const size_t spec = (size_t)p.H * L.wh_pad * sizeof(float2);
   if (fixed > (size_t)di.max_smem_optin) return (int)cudaErrorInvalidValue;  // 1-D length too large
   L.spectrum_in_smem = (fixed + spec <= (size_t)di.max_smem_optin) ? 1 : 0;
   const size_t smem = fixed + (L.spectrum_in_smem ? spec : 0);
-  int grid = di.sm_count;
-  if (L.spectrum_in_smem) {
-    const int per_sm = (int)((size_t)di.max_smem_optin / (smem + 1024));
-    grid = di.sm_count * (per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm));
-  } else if (p.scratch == nullptr) {
-    return (int)cudaErrorInvalidValue;
-  }
+  // two CTAs per SM when shared memory allows (the kernel is built for <= 64 registers / thread)
+  const int per_sm = (int)((size_t)(di.max_smem_optin + 1024) / (smem + 1024)) >= 2 ? 2 : 1;
+  int grid = di.sm_count * per_sm;
+  if (!L.spectrum_in_smem && p.scratch == nullptr) return (int)cudaErrorInvalidValue;
   if ((int64_t)grid > p.planes) grid = (int)p.planes;
   SONAR_CUDA_TRY(cudaFuncSetAttribute(spectral_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   spectral_plane_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream_>>>(L);

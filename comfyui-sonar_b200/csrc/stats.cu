@@ -98,7 +98,13 @@ philox_normal_fill_moments_kernel(float* __restrict__ out, int64_t begin, int64_
       const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
       if (li0 >= end) break;
       if (li0 + 3 * T < begin) continue;
-      const float4 v = philox_normal4(st, (uint32_t)vt, k);
+      float4 v;
+      if (li0 + 2 * T < end) {
+        v = philox_normal4(st, (uint32_t)vt, k);
+      } else {  // lanes 2, 3 lie beyond the slice: one Box-Muller is enough
+        const float2 lo = philox_normal2_lo(st, (uint32_t)vt, k);
+        v = make_float4(lo.x, lo.y, 0.f, 0.f);
+      }
       const float vals[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int lane = 0; lane < 4; ++lane) {

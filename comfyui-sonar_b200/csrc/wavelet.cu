@@ -73,23 +73,43 @@ dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b,
     const Tin* pa = in_a + plane * (int64_t)in_stride_h * W;
     const Tin* pb = in_b != nullptr ? in_b + plane * (int64_t)in_stride_h * W : nullptr;
     T acc_ll = 0, acc_lh = 0, acc_hl = 0, acc_hh = 0;
-    for (int jy = 0; jy < L; ++jy) {
-      const int sy = extend_index(2 * ky + jy - pad_t, H, mode);
-      if (sy < 0) continue;
-      T row_lo = 0, row_hi = 0;
-      for (int jx = 0; jx < L; ++jx) {
-        const int sx = extend_index(2 * kx + jx - pad_l, W, mode);
-        if (sx < 0) continue;
-        const int64_t o = (int64_t)sy * W + sx;
-        T v = (T)pa[o];
-        if (pb != nullptr) v -= (T)pb[o];
-        row_lo += f.a_lo[jx] * v;
-        row_hi += f.a_hi[jx] * v;
+    const int x_first = 2 * kx - pad_l, y_first = 2 * ky - pad_t;
+    const bool interior = x_first >= 0 && x_first + L <= W && y_first >= 0 && y_first + L <= H;
+    if (interior) {  // the whole L x L window lies inside the plane: no boundary extension
+      for (int jy = 0; jy < L; ++jy) {
+        const Tin* ra = pa + (int64_t)(y_first + jy) * W + x_first;
+        const Tin* rb = pb != nullptr ? pb + (int64_t)(y_first + jy) * W + x_first : nullptr;
+        T row_lo = 0, row_hi = 0;
+        for (int jx = 0; jx < L; ++jx) {
+          T v = (T)ra[jx];
+          if (rb != nullptr) v -= (T)rb[jx];
+          row_lo += f.a_lo[jx] * v;
+          row_hi += f.a_hi[jx] * v;
+        }
+        acc_ll += f.a_lo[jy] * row_lo;
+        acc_lh += f.a_hi[jy] * row_lo;
+        acc_hl += f.a_lo[jy] * row_hi;
+        acc_hh += f.a_hi[jy] * row_hi;
       }
-      acc_ll += f.a_lo[jy] * row_lo;
-      acc_lh += f.a_hi[jy] * row_lo;  // high along H, low along W
-      acc_hl += f.a_lo[jy] * row_hi;  // low along H, high along W
-      acc_hh += f.a_hi[jy] * row_hi;
+    } else {
+      for (int jy = 0; jy < L; ++jy) {
+        const int sy = extend_index(y_first + jy, H, mode);
+        if (sy < 0) continue;
+        T row_lo = 0, row_hi = 0;
+        for (int jx = 0; jx < L; ++jx) {
+          const int sx = extend_index(x_first + jx, W, mode);
+          if (sx < 0) continue;
+          const int64_t o = (int64_t)sy * W + sx;
+          T v = (T)pa[o];
+          if (pb != nullptr) v -= (T)pb[o];
+          row_lo += f.a_lo[jx] * v;
+          row_hi += f.a_hi[jx] * v;
+        }
+        acc_ll += f.a_lo[jy] * row_lo;
+        acc_lh += f.a_hi[jy] * row_lo;  // high along H, low along W
+        acc_hl += f.a_lo[jy] * row_hi;  // low along H, high along W
+        acc_hh += f.a_hi[jy] * row_hi;
+      }
     }
     const int64_t hw = (int64_t)h * w;
     const int64_t o = (int64_t)ky * w + kx;
@@ -115,68 +135,75 @@ struct SynthSet {
   T s_ll, s_lh, s_hl, s_hh;
 };
 
+// Polyphase form: the 2x2 output quad (2qy+py, 2qx+px) reads the SAME (L/2) x (L/2) window of
+// coefficients k = (qy + a, qx + b); tap index t = p + L - 2 - 2a. Every k of a quad is in range
+// (q <= n - L/2), so the loops carry no boundary tests; rows are combined along W first.
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, int h, int w, int out_h, int out_w,
                       T* __restrict__ out_t, float* __restrict__ out_f32, int crop_h, int crop_w,
                       const float* __restrict__ addend, float addend_scale, const float* __restrict__ x,
                       float x_scale, float recon_sign, Filters<T> f) {
-  const int L = f.L;
+  const int L = f.L, half = L >> 1;
   const int oh = out_f32 != nullptr ? crop_h : out_h;
   const int ow = out_f32 != nullptr ? crop_w : out_w;
-  const int64_t total = planes * (int64_t)oh * ow;
+  const int qh = (oh + 1) >> 1, qw = (ow + 1) >> 1;
+  const int64_t total = planes * (int64_t)qh * qw;
   const int64_t hw = (int64_t)h * w;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int ix = (int)(idx % ow);
-    const int iy = (int)((idx / ow) % oh);
-    const int64_t plane = idx / ((int64_t)ow * oh);
-    // taps: t = i + L - 2 - 2k in [0, L)  ->  k in [ceil((i-1)/2) .. floor((i+L-2)/2)] clipped to [0, n)
-    const int ty0 = iy + L - 2, tx0 = ix + L - 2;
-    int ky_lo = (ty0 - (L - 1) + 1) >> 1;
-    if (ky_lo < 0) ky_lo = 0;
-    int ky_hi = ty0 >> 1;
-    if (ky_hi > h - 1) ky_hi = h - 1;
-    int kx_lo = (tx0 - (L - 1) + 1) >> 1;
-    if (kx_lo < 0) kx_lo = 0;
-    int kx_hi = tx0 >> 1;
-    if (kx_hi > w - 1) kx_hi = w - 1;
-    T acc = 0;
+    const int qx = (int)(idx % qw);
+    const int qy = (int)((idx / qw) % qh);
+    const int64_t plane = idx / ((int64_t)qw * qh);
+    T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
     for (int s = 0; s < n_sets; ++s) {
       const SynthSet<T>& c = s == 0 ? a : b;
       const T* pll = c.ll + plane * (int64_t)c.ll_stride_h * c.ll_stride_w;
       const T* phi = c.hi + plane * 3 * hw;
-      T part = 0;
-      for (int ky = ky_lo; ky <= ky_hi; ++ky) {
-        const int ty = ty0 - 2 * ky;
-        const T gl_y = f.s_lo[ty], gh_y = f.s_hi[ty];
-        T col_lo = 0, col_hi = 0;  // contributions through the low / high H-filter
-        for (int kx = kx_lo; kx <= kx_hi; ++kx) {
-          const int tx = tx0 - 2 * kx;
-          const T gl_x = f.s_lo[tx], gh_x = f.s_hi[tx];
+      for (int ia = 0; ia < half; ++ia) {
+        const int ky = qy + ia;
+        if (ky >= h) break;  // only reachable for the cropped-away overhang
+        T rl0 = 0, rl1 = 0, rh0 = 0, rh1 = 0;
+        for (int ib = 0; ib < half; ++ib) {
+          const int kx = qx + ib;
+          if (kx >= w) break;
+          const int tx = L - 2 - 2 * ib;
+          const T glx0 = f.s_lo[tx], glx1 = f.s_lo[tx + 1], ghx0 = f.s_hi[tx], ghx1 = f.s_hi[tx + 1];
           const int64_t o = (int64_t)ky * w + kx;
           const T v_ll = pll[(int64_t)ky * c.ll_stride_w + kx] * c.s_ll;
-          const T v_lh = phi[o] * c.s_lh;           // high along H, low along W
-          const T v_hl = phi[hw + o] * c.s_hl;      // low along H, high along W
+          const T v_lh = phi[o] * c.s_lh;       // high along H, low along W
+          const T v_hl = phi[hw + o] * c.s_hl;  // low along H, high along W
           const T v_hh = phi[2 * hw + o] * c.s_hh;
-          col_lo += gl_x * v_ll + gh_x * v_hl;
-          col_hi += gl_x * v_lh + gh_x * v_hh;
+          rl0 += glx0 * v_ll + ghx0 * v_hl;
+          rl1 += glx1 * v_ll + ghx1 * v_hl;
+          rh0 += glx0 * v_lh + ghx0 * v_hh;
+          rh1 += glx1 * v_lh + ghx1 * v_hh;
         }
-        part += gl_y * col_lo + gh_y * col_hi;
+        const int ty = L - 2 - 2 * ia;
+        const T gly0 = f.s_lo[ty], gly1 = f.s_lo[ty + 1], ghy0 = f.s_hi[ty], ghy1 = f.s_hi[ty + 1];
+        o00 += gly0 * rl0 + ghy0 * rh0;
+        o01 += gly0 * rl1 + ghy0 * rh1;
+        o10 += gly1 * rl0 + ghy1 * rh0;
+        o11 += gly1 * rl1 + ghy1 * rh1;
       }
-      acc += part;
     }
-    if (out_f32 != nullptr) {
-      const int64_t o = (plane * crop_h + iy) * (int64_t)crop_w + ix;
-      T r = acc;
-      if (addend != nullptr) r += (T)addend_scale * (T)addend[o];
-      r = (T)recon_sign * r;
-      // reference casts the reconstruction to x.dtype first, then forms x - result in that dtype
-      float rf = (float)r;
-      if (x != nullptr) rf = x_scale * x[o] + rf;
-      out_f32[o] = rf;
-    } else {
-      out_t[(plane * out_h + iy) * (int64_t)out_w + ix] = acc;
+    const T vals[4] = {o00, o01, o10, o11};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int iy = 2 * qy + (q >> 1), ix = 2 * qx + (q & 1);
+      if (iy >= oh || ix >= ow) continue;
+      if (out_f32 != nullptr) {
+        const int64_t o = (plane * crop_h + iy) * (int64_t)crop_w + ix;
+        T r = vals[q];
+        if (addend != nullptr) r += (T)addend_scale * (T)addend[o];
+        r = (T)recon_sign * r;
+        // reference casts the reconstruction to x.dtype first, then forms x - result in that dtype
+        float rf = (float)r;
+        if (x != nullptr) rf = x_scale * x[o] + rf;
+        out_f32[o] = rf;
+      } else {
+        out_t[(plane * out_h + iy) * (int64_t)out_w + ix] = vals[q];
+      }
     }
   }
 }
@@ -229,7 +256,8 @@ int launch_synthesis(const SonarDwtSynthesisParams& p, cudaStream_t stream) {
   const int out_h = 2 * p.h - p.filters.length + 2, out_w = 2 * p.w - p.filters.length + 2;
   const bool final_level = p.out_f32 != nullptr;
   if (final_level && (p.crop_h > out_h || p.crop_w > out_w)) return (int)cudaErrorInvalidValue;
-  const int64_t total = p.planes * (int64_t)(final_level ? p.crop_h : out_h) * (final_level ? p.crop_w : out_w);
+  const int oh = final_level ? p.crop_h : out_h, ow = final_level ? p.crop_w : out_w;
+  const int64_t total = p.planes * (int64_t)((oh + 1) / 2) * ((ow + 1) / 2);  // one thread per 2x2 output quad
   const int grid = streaming_grid(total, kBlock, 4);
   dwt2_synthesis_kernel<T><<<grid, kBlock, 0, stream>>>(sets[0], sets[1], p.n_sets, p.planes, p.h, p.w, out_h, out_w,
                                                         (T*)p.out, p.out_f32, p.crop_h, p.crop_w, p.addend,

@@ -238,6 +238,12 @@ def step_single_launch_ok(numel: int, grid_blocks: int) -> bool:
     return hit
 
 
+def enable_cooperative_step(enable: bool) -> None:
+    """Opt in/out of the single cooperative launch for small fused steps (default: off)."""
+    _native.load().sonar_step_enable_cooperative(int(enable))
+    _SINGLE_LAUNCH_CACHE.clear()
+
+
 def scale_noise_apply(
     x: torch.Tensor,
     sums: torch.Tensor,

@@ -143,6 +143,9 @@ int sonar_step_f32(const SonarStepParams* params_host, void* stream);
  * launch (moments -> grid barrier -> step); callers with larger tensors materialise the noise with
  * sonar_philox_normal_fill_moments_f32 and use SONAR_NOISE_TENSOR_NORMALIZED instead. */
 int sonar_step_single_launch_ok(int64_t n, uint32_t philox_grid_blocks);
+/* The single cooperative launch is opt-in (env SONAR_B200_COOP=1 or this call): measured slower than
+ * the two-launch path on B200 at the configured sizes (profiles/README.md). */
+int sonar_step_enable_cooperative(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * Pyramid family: fused multi-level resample-and-accumulate.

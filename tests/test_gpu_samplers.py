@@ -90,10 +90,16 @@ def test_fused_philox_noise_equals_tensor_noise(sb, cuda):
         )
         return out, torch.cuda.default_generators[0].get_offset()
 
-    fused, off_a = run(False)
     plain, off_b = run(True)
-    assert off_a == off_b
-    assert_close(fused, plain, what="fused vs tensor noise", rtol=1e-6, atol=1e-5)
+    for coop in (False, True):  # two-launch path (default) and the opt-in single cooperative launch
+        sb.ops.enable_cooperative_step(coop)
+        try:
+            assert sb.ops.step_single_launch_ok(x0.numel(), sb.ops.philox_policy(x0.numel())[0]) == coop
+            fused, off_a = run(False)
+        finally:
+            sb.ops.enable_cooperative_step(False)
+        assert off_a == off_b
+        assert_close(fused, plain, what=f"fused (coop={coop}) vs tensor noise", rtol=1e-6, atol=1e-5)
 
 
 def test_fused_noise_large_tensor_path(sb, cuda):
