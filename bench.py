@@ -15,9 +15,10 @@ One bench "step" = one 30-step sampling run over one batch. Metric: latent noise
               ms_per_step = sum of those 30 event intervals, max over ranks.
 * e2e       : the same run through the public sampler function with HOST buffers: pinned x0 -> H2D,
               30 steps, result D2H, wall clock between device synchronisations.
-* roofline  : dominant kernel (sonar_step_philox_kernel): algorithmic bytes per launch
-              (20 B/element: read x, denoised, history; write x', history'; noise regenerated in
-              registers) / CUDA-event duration of that launch, against MEASURED_PEAKS.json hbm_gbs.
+* roofline  : dominant kernel (sonar_step_vec_kernel): algorithmic bytes per launch (24 B/element:
+              read x, denoised, history, raw noise; write x', history') / CUDA-event duration of that
+              launch with cold L2, against MEASURED_PEAKS.json hbm_gbs; the same kernel on the C5
+              per-GPU shard shape is reported as roofline_large_tensor.
 * cpu_baseline : the CPU oracle port of the reference algorithm (oracle/sonar_oracle.py) on the host
               cores, same workload, bounded sample.
 * N > 1     : weak scaling by batch: every rank holds 8 latents of a global batch of 8N; the global
@@ -44,7 +45,6 @@ sys.path.insert(0, str(REPO))
 SHAPE = (8, 4, 128, 128)
 N_SAMPLER_STEPS = 30
 ELEMS_PER_RUN = N_SAMPLER_STEPS * SHAPE[0] * SHAPE[1] * SHAPE[2] * SHAPE[3]
-STEP_BYTES_PER_ELEM = 20  # x, denoised, hist in; x', hist' out (fp32); Philox noise costs no HBM bytes
 WORKLOAD = "C2 sonar_euler_ancestral, SDXL latents 8x4x128x128, 30 steps, fused Gaussian noise"
 
 
@@ -224,6 +224,69 @@ class StepTimer:
         return sum(a.elapsed_time(b) for a, b in self.pairs)
 
 
+def step_kernel_roofline(sb, dev, shape, peak: float, peak_src: str, reps: int) -> dict:
+    """Times the dominant kernel alone (sonar_step_vec_kernel: momentum mix + history updates + Euler
+    step + normalise-on-load noise injection) with CUDA events on the launching stream, cold L2
+    (256 MiB flush enqueued right before each launch). Algorithmic bytes: 24 B/element = read x,
+    denoised, history, raw noise; write x', history'."""
+    import statistics as st
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n = 1
+    for d in shape:
+        n *= d
+    # several independent operand sets per timed interval: every launch still sees cold operands (each
+    # set is touched once after the flush) and the CUDA-event overhead is amortised over the batch
+    n_sets = max(2, min(8, (96 << 20) // (24 * n)))
+    sets = []
+    for _ in range(n_sets):
+        x, den, hist = (torch.randn(shape, device=dev) for _ in range(3))
+        draw = sb.ops.reserve_draw(n, dev)
+        raw = torch.empty_like(x)
+        sums = torch.empty(2, device=dev, dtype=torch.float64)
+        sb.ops.philox_normal_fill_moments(draw, raw, sums)
+        stepper = sb.samplers.SonarBase(sb.samplers.SonarConfig())
+        kw = {"draw": draw, "factor": 1.0, "normalized": True, "begin": 0, "tensor": raw, "sums": sums, "count": n}
+        sets.append((stepper, x, den, hist, kw))
+
+    def launch_all():
+        for stepper, x, den, hist, kw in sets:
+            stepper.history_d = hist
+            stepper.fused_step(3, x, den, 5.0, kind=sb.ops.STEP_EULER, c0=-1.5, noise_scale=0.7, noise_philox=kw)
+
+    for _ in range(3):
+        flush.zero_()
+        launch_all()
+    torch.cuda.synchronize()
+    us = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch_all()
+        e1.record()
+        torch.cuda.synchronize()
+        us.append(e0.elapsed_time(e1) * 1e3 / n_sets)
+    launch_us = st.median(us)
+    algo = 24 * n
+    achieved = algo / (launch_us * 1e-6) / 1e9
+    return {
+        "bound": "hbm",
+        "kernel": "sonar_step_vec_kernel",
+        "shape": list(shape),
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": algo,
+        "launch_us": launch_us,
+        "launches_timed": len(us) * n_sets,
+        "timing": f"CUDA events around {n_sets} back-to-back launches on distinct operand sets after a 256 MiB L2 flush",
+    }
+
+
 def sampler_run(sb, model, x0, sigmas):
     return sb.samplers.SonarEulerAncestral.sampler(model, x0, sigmas, extra_args={"seed": 0}, disable=True)
 
@@ -294,36 +357,14 @@ def run_b200_arm(args) -> None:
     value = ELEMS_PER_RUN * world / (ms_per_step * 1e-3)
 
     # ---------------- roofline of the dominant kernel (per-launch CUDA events) ----------------
-    sb.ops.TRACE = []
-    timer = StepTimer(dev, timed=False)
-    for _ in range(3):
-        one_run(timer, x0)
-    torch.cuda.synchronize()
-    per_kernel: dict[str, list[float]] = {}
-    for name, a, b in sb.ops.TRACE:
-        per_kernel.setdefault(name, []).append(a.elapsed_time(b) * 1e3)  # us
-    sb.ops.TRACE = None
-    step_us = statistics.mean(per_kernel["sonar_step_f32"])
     peak, peak_src = measured_peak()
-    algo_bytes = STEP_BYTES_PER_ELEM * x0.numel()
-    achieved = algo_bytes / (step_us * 1e-6) / 1e9
+    roofline = step_kernel_roofline(sb, dev, SHAPE, peak, peak_src, reps=40)
+    roofline_large = step_kernel_roofline(sb, dev, (1, 16, 33, 90, 160), peak, peak_src, reps=20)
     traffic_path = REPO / "profiles" / "traffic.json"
-    traffic = None
     if traffic_path.exists():
-        traffic = json.loads(traffic_path.read_text()).get("sonar_step_coop_kernel" if world == 1 else "sonar_step_philox_kernel")
-    roofline = {
-        "bound": "hbm",
-        "kernel": "sonar_step_coop_kernel" if world == 1 else "sonar_step_philox_kernel",
-        "achieved": achieved,
-        "peak": peak,
-        "unit": "GB/s",
-        "frac": achieved / peak,
-        "traffic": traffic,
-        "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": algo_bytes,
-        "launch_us": step_us,
-        "kernel_us": {k: statistics.mean(v) for k, v in per_kernel.items()},
-    }
+        traffic = json.loads(traffic_path.read_text())
+        roofline["traffic"] = traffic.get("sonar_step_vec_kernel@8x4x128x128")
+        roofline_large["traffic"] = traffic.get("sonar_step_vec_kernel@1x16x33x90x160")
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e_times = []
@@ -388,6 +429,7 @@ def run_b200_arm(args) -> None:
                 "timing": "sum of 30 CUDA-event intervals per run (Philox moments pre-pass + fused step), max over ranks",
             },
             "roofline": roofline,
+            "roofline_large_tensor": roofline_large,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": launches,

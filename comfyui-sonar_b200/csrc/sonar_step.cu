@@ -182,6 +182,48 @@ sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint
 // The double[2] sums slot is zeroed for the next launch by the kernel itself (ping-pong slots).
 constexpr int kCoopPairs = 4;
 
+// materialise + moments in one pass (same kernel as stats.cu's, local to this TU)
+__global__ void __launch_bounds__(kBlock)
+philox_fill_moments_device(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo,
+                           uint32_t k_hi, double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  double s = 0.0, ss = 0.0;
+  const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    float fs = 0.0f, fss = 0.0f;
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      float4 v;
+      if (li0 + 2 * T < end) {
+        v = philox_normal4(st, (uint32_t)vt, k);
+      } else {
+        const float2 lo = philox_normal2_lo(st, (uint32_t)vt, k);
+        v = make_float4(lo.x, lo.y, 0.f, 0.f);
+      }
+      const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) {
+          out[li - begin] = vals[lane];
+          fs += vals[lane];
+          fss += vals[lane] * vals[lane];
+        }
+      }
+    }
+    s += (double)fs;
+    ss += (double)fss;
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], s);
+    atomicAdd(&sums[1], ss);
+  }
+}
+
 // moments of the un-materialised Philox normal draw (same kernel as stats.cu's, local to this TU)
 __global__ void __launch_bounds__(kBlock)
 philox_normal_moments_device(int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo, uint32_t k_hi,
@@ -358,9 +400,20 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
                                                    args, 0, stream));
         return 0;
       }
-      // large tensors: moments pre-pass + step as two launches (launch cost is negligible there)
+      // Default path: ONE pass that materialises the normals into the caller's scratch (p.noise) while
+      // reducing their moments, then the float4 step kernel normalises them on load. Two launches, one
+      // C-ABI call; 8 B/element of extra traffic buys a single Philox evaluation per element.
       SONAR_CUDA_TRY(cudaMemsetAsync(slot, 0, 2 * sizeof(double), stream));
       const int grid_m = streaming_grid(T, kBlock, 1);
+      if (p.noise != nullptr) {
+        philox_fill_moments_device<<<grid_m, kBlock, 0, stream>>>(const_cast<float*>(p.noise), 0, end, st,
+                                                                  (uint32_t)k_lo, (uint32_t)k_hi, slot);
+        SONAR_LAUNCH_CHECK();
+        p.noise_kind = SONAR_NOISE_TENSOR_NORMALIZED;
+        p.noise_sums = slot;
+        goto dense_step;
+      }
+      // no scratch given: moments pre-pass, then regenerate the normals inside the step kernel
       philox_normal_moments_device<<<grid_m, kBlock, 0, stream>>>(0, end, st, (uint32_t)k_lo, (uint32_t)k_hi, slot);
       SONAR_LAUNCH_CHECK();
       p.noise_sums = slot;
@@ -372,6 +425,7 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     return 0;
   }
 
+dense_step:
   const bool vec_ok = aligned16(p.x) && aligned16(p.denoised) && aligned16(p.x_out) &&
                       (p.hist_in == nullptr || aligned16(p.hist_in)) &&
                       (p.hist_out == nullptr || aligned16(p.hist_out)) && (p.noise == nullptr || aligned16(p.noise));

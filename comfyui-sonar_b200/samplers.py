@@ -278,11 +278,13 @@ class SonarBase:
                 p.noise_kind, p.noise = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr()
                 p.noise_sums, p.noise_count = keep.data_ptr(), noise_philox["count"]
                 keep = (keep, raw)
-            elif noise_philox["normalized"]:  # the call does its own moments pre-pass (one launch when small)
+            elif noise_philox["normalized"]:
+                # un-sharded: one C-ABI call materialises the normals + moments and runs the step
                 keep = self._sums_scratch(x.device)
                 p.sums_scratch, p.sums_parity = keep.data_ptr(), self._sums_parity
                 self._sums_parity ^= 1
                 p.noise_count = x.numel()
+                p.noise = self._noise_scratch(x).data_ptr()
         elif noise_tensor is not None:
             if noise_tensor.dtype != torch.float32 or not noise_tensor.is_contiguous():
                 noise_tensor = noise_tensor.to(torch.float32).contiguous()
@@ -292,6 +294,13 @@ class SonarBase:
         if keeps_history:
             self.history_d = hist_out
         return x_out
+
+    def _noise_scratch(self, x: Tensor) -> Tensor:
+        """n-float scratch for the materialised normals, reused by every step of this sampler."""
+        buf = getattr(self, "_noise_buf", None)
+        if buf is None or buf.shape != x.shape or buf.device != x.device:
+            buf = self._noise_buf = torch.empty_like(x)
+        return buf
 
     def _sums_scratch(self, device) -> Tensor:
         buf = getattr(self, "_sums_buf", None)
@@ -325,14 +334,13 @@ class SonarBase:
             total, begin = parallel.global_draw_geometry(x.shape) if sharded else (x.numel(), 0)
             draw = ops.reserve_draw(total, x.device)
             kw = {"draw": draw, "factor": factor, "normalized": normalized, "begin": begin}
-            if normalized and (sharded or not ops.step_single_launch_ok(x.numel(), draw.grid_blocks)):
-                # Too large to keep the normals in registers across a grid barrier, or the statistics
-                # span several ranks: materialise this rank's slice once while reducing its moments
-                # (2 doubles all-reduced when sharded); the step kernel normalises on load.
-                raw = torch.empty_like(x)
+            if normalized and sharded:
+                # the statistics span several ranks: materialise this rank's slice once while reducing
+                # its moments, all-reduce the 2 doubles; the step kernel normalises on load
+                raw = self._noise_scratch(x)
                 sums = torch.empty(2, device=x.device, dtype=torch.float64)
                 ops.philox_normal_fill_moments(draw, raw, sums, begin=begin)
-                kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums) if sharded else x.numel()}
+                kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums)}
             return {"noise_philox": kw, "noise_scale": scale}
         return {"noise_tensor": self.noise_sampler(sigma, sigma_next), "noise_scale": scale}
 

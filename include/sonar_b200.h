@@ -132,8 +132,9 @@ typedef struct SonarStepParams {
                                runs all-reduce them); NULL = let this call do the moments pre-pass */
   int64_t noise_count;      /* global count behind noise_sums */
   /* noise_sums == NULL: double[4] scratch (two ping-pong slots, zeroed ONCE by the caller) + which
-   * slot this launch uses. Small tensors then take a single cooperative launch (moments -> grid
-   * barrier -> step, normals kept in registers); large ones a moments launch + a step launch. */
+   * slot this launch uses. The call then performs "materialise the normals into `noise` (n-float
+   * scratch) + moments" and the step in two launches; with the cooperative path enabled and a small
+   * tensor, a single launch (moments -> grid barrier -> step, normals kept in registers). */
   double* sums_scratch;
   int32_t sums_parity;
 } SonarStepParams;

@@ -109,7 +109,6 @@ def test_fused_noise_large_tensor_path(sb, cuda):
     sigmas = torch.tensor([14.6, 6.0, 1.5, 0.0])
     torch.manual_seed(0)
     x0 = (torch.randn(1, 16, 33, 90, 160) * sigmas[0]).to(cuda)
-    assert not sb.ops.step_single_launch_ok(x0.numel(), sb.ops.philox_policy(x0.numel())[0])
 
     def run(explicit):
         torch.manual_seed(5)
