@@ -59,9 +59,13 @@ class SonarStepParams(ctypes.Structure):
         ("noise_count", c_int64),
         ("sums_scratch", c_void_p),
         ("sums_parity", c_int32),
+        ("peer_world", c_int32),
+        ("peer_mailbox", c_void_p),
+        ("peer_epoch", c_double),
     ]
 
 
+PEER_MAX_RANKS = 8
 PYRAMID_MAX_LEVELS = 16
 PERLIN_MAX_ITERS = 8
 FFT_MAX_FACTORS = 24
@@ -192,6 +196,15 @@ SIGNATURES: dict[str, list] = {
     "sonar_philox_normal_fill_moments_f32": [
         c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p,
     ],
+    "sonar_peer_alloc": [POINTER(c_void_p)],
+    "sonar_peer_free": [c_void_p],
+    "sonar_peer_get_handle": [c_void_p, ctypes.c_char_p],
+    "sonar_peer_open_handle": [ctypes.c_char_p, POINTER(c_void_p)],
+    "sonar_peer_close_handle": [c_void_p],
+    "sonar_scale_noise_peers_f32": [
+        c_void_p, c_void_p, c_int64, c_void_p, c_int, c_double, c_int64, c_float, c_float, c_void_p,
+    ],
+    "sonar_peer_publish_sums": [POINTER(c_void_p), c_int, c_int, c_void_p, c_double, c_void_p],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
     "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],

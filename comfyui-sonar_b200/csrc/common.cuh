@@ -203,6 +203,30 @@ __device__ __forceinline__ NormDecision decide_normalisation(const double* __res
   return d;
 }
 
+// Batch-sharded statistics over peer memory (peer.cu): wait for the `world` partial sums of `epoch`
+// in the local mailbox, add them in rank order, take the same decision on every rank.
+// All threads of the block must call; `shared2` is 2 doubles of shared memory.
+__device__ __forceinline__ NormDecision decide_normalisation_peers(const double* mailbox, int world, double epoch,
+                                                                   int64_t count, float threshold_std_devs,
+                                                                   double* shared2) {
+  if (threadIdx.x == 0) {
+    const int parity = ((long long)epoch) & 1;
+    const volatile double* slots = mailbox + (size_t)parity * 8 * 4;
+    double s = 0.0, ss = 0.0;
+    for (int r = 0; r < world; ++r) {
+      while (slots[r * 4 + 2] != epoch) {
+      }
+      __threadfence();
+      s += slots[r * 4 + 0];
+      ss += slots[r * 4 + 1];
+    }
+    shared2[0] = s;
+    shared2[1] = ss;
+  }
+  __syncthreads();
+  return decide_normalisation(shared2, count, threshold_std_devs);
+}
+
 __device__ __forceinline__ float apply_norm(float v, const NormDecision& d) {
   if (d.sub_mean) v -= d.mean;
   if (d.div_std) v /= d.std;

@@ -75,8 +75,13 @@ sonar_step_vec_kernel(SonarStepParams p) {
   const bool write_h = p.hist_out != nullptr;
   // raw Gaussian tensor + device-resident sums: apply scale_noise on load
   const bool norm_noise = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
-  const NormDecision nd = norm_noise ? decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs)
-                                     : NormDecision{0.f, 1.f, 0, 0};
+  __shared__ double peer_sums[2];
+  const NormDecision nd =
+      !norm_noise ? NormDecision{0.f, 1.f, 0, 0}
+      : p.peer_world > 1
+          ? decide_normalisation_peers(p.peer_mailbox, p.peer_world, p.peer_epoch, p.noise_count,
+                                       p.noise_threshold_std_devs, peer_sums)
+          : decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs);
   const float nfac = norm_noise ? p.noise_factor : 1.0f;
   const int64_t n4 = p.n >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,8 +118,13 @@ sonar_step_scalar_kernel(SonarStepParams p) {
   const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
   const bool write_h = p.hist_out != nullptr;
   const bool norm_noise = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
-  const NormDecision nd = norm_noise ? decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs)
-                                     : NormDecision{0.f, 1.f, 0, 0};
+  __shared__ double peer_sums[2];
+  const NormDecision nd =
+      !norm_noise ? NormDecision{0.f, 1.f, 0, 0}
+      : p.peer_world > 1
+          ? decide_normalisation_peers(p.peer_mailbox, p.peer_world, p.peer_epoch, p.noise_count,
+                                       p.noise_threshold_std_devs, peer_sums)
+          : decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs);
   const float nfac = norm_noise ? p.noise_factor : 1.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
     const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f,
@@ -372,7 +382,10 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
   if (p.hist_state != SONAR_HIST_NONE && p.hist_in == nullptr) return (int)cudaErrorInvalidValue;
   if ((p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED) && p.noise == nullptr)
     return (int)cudaErrorInvalidValue;
-  if (p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED && p.noise_sums == nullptr) return (int)cudaErrorInvalidValue;
+  if (p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED && p.noise_sums == nullptr && p.peer_world <= 1)
+    return (int)cudaErrorInvalidValue;
+  if (p.peer_world > 1 && (p.peer_mailbox == nullptr || p.peer_world > SONAR_PEER_MAX_RANKS))
+    return (int)cudaErrorInvalidValue;
   if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr && p.sums_scratch == nullptr)
     return (int)cudaErrorInvalidValue;
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -131,8 +131,12 @@ philox_normal_fill_moments_kernel(float* __restrict__ out, int64_t begin, int64_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 scale_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, int vec_ok,
-                   const double* __restrict__ sums, int64_t count, float factor, float threshold_std_devs) {
-  const NormDecision nd = decide_normalisation(sums, count, threshold_std_devs);
+                   const double* __restrict__ sums, int64_t count, float factor, float threshold_std_devs,
+                   const double* __restrict__ peer_mailbox, int peer_world, double peer_epoch) {
+  __shared__ double peer_sums[2];
+  const NormDecision nd = peer_world > 1 ? decide_normalisation_peers(peer_mailbox, peer_world, peer_epoch, count,
+                                                                       threshold_std_devs, peer_sums)
+                                         : decide_normalisation(sums, count, threshold_std_devs);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
@@ -231,7 +235,19 @@ int sonar_scale_noise_f32(const float* x, float* out, int64_t n, const double* s
   const int vec_ok = (sonar::aligned16(x) && sonar::aligned16(out)) ? 1 : 0;
   const int grid = sonar::streaming_grid((n + 3) / 4, sonar::kBlock, 2);
   sonar::scale_noise_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, vec_ok, sums, count, factor,
-                                                                             threshold_std_devs);
+                                                                             threshold_std_devs, nullptr, 0, 0.0);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_scale_noise_peers_f32(const float* x, float* out, int64_t n, const double* mailbox, int world, double epoch,
+                                int64_t count, float factor, float threshold_std_devs, void* stream) {
+  if (n <= 0) return 0;
+  if (mailbox == nullptr || world < 2 || world > SONAR_PEER_MAX_RANKS) return (int)cudaErrorInvalidValue;
+  const int vec_ok = (sonar::aligned16(x) && sonar::aligned16(out)) ? 1 : 0;
+  const int grid = sonar::streaming_grid((n + 3) / 4, sonar::kBlock, 2);
+  sonar::scale_noise_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, vec_ok, nullptr, count, factor,
+                                                                             threshold_std_devs, mailbox, world, epoch);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

@@ -77,6 +77,13 @@ def scale_noise(
     if not noise.is_contiguous():
         noise = noise.contiguous()
     sums = ops.moments(noise)
+    ctx = parallel.active()
+    if ctx is not None and ctx.world_size > 1 and ctx.peers is not None:
+        # partial sums travel as NVLink stores into every rank's mailbox; the apply kernel waits for them
+        epoch = ctx.peers.publish(sums)
+        return ops.scale_noise_apply_peers(
+            noise, ctx.peers, epoch, parallel.global_numel(numel), factor, threshold_std_devs=threshold_std_devs,
+        )
     count = parallel.global_count(numel, sums)
     return ops.scale_noise_apply(noise, sums, count, factor, threshold_std_devs=threshold_std_devs)
 

@@ -261,6 +261,18 @@ def scale_noise_apply(
     return out
 
 
+def scale_noise_apply_peers(x: torch.Tensor, peers, epoch: float, count: int, factor: float = 1.0, *, threshold_std_devs: float = 2.5):
+    """scale_noise whose global statistics arrive through the peer mailboxes (parallel.PeerExchange)."""
+    _f32(x, "x")
+    lib, stream = _prepare(x)
+    _launch(
+        "sonar_scale_noise_peers_f32", lib.sonar_scale_noise_peers_f32,
+        _ptr(x), _ptr(x), x.numel(), ctypes.c_void_p(peers.local), peers.world_size, float(epoch), int(count),
+        float(factor), float(threshold_std_devs), stream,
+    )  # fmt: skip
+    return x
+
+
 def add_moments(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     _f32(a, "a")
     _f32(b, "b")

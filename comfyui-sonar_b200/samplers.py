@@ -264,7 +264,7 @@ class SonarBase:
         p.sigma, p.c0, p.c1 = sigma, c0, c1
         p.hist_in_div = hist_div
         p.noise_scale = noise_scale
-        p.noise_kind, p.noise, p.noise_sums, p.sums_scratch = ops.NOISE_NONE, 0, 0, 0
+        p.noise_kind, p.noise, p.noise_sums, p.sums_scratch, p.peer_world = ops.NOISE_NONE, 0, 0, 0, 0
         keep = None
         if noise_philox is not None:
             draw = noise_philox["draw"]
@@ -277,6 +277,9 @@ class SonarBase:
                 raw = noise_philox["tensor"]
                 p.noise_kind, p.noise = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr()
                 p.noise_sums, p.noise_count = keep.data_ptr(), noise_philox["count"]
+                peers = noise_philox.get("peers")
+                if peers is not None:
+                    p.peer_world, p.peer_mailbox, p.peer_epoch = peers.world_size, peers.local, noise_philox["epoch"]
                 keep = (keep, raw)
             elif noise_philox["normalized"]:
                 # un-sharded: one C-ABI call materialises the normals + moments and runs the step
@@ -340,7 +343,11 @@ class SonarBase:
                 raw = self._noise_scratch(x)
                 sums = torch.empty(2, device=x.device, dtype=torch.float64)
                 ops.philox_normal_fill_moments(draw, raw, sums, begin=begin)
-                kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums)}
+                ctx = parallel.active()
+                if ctx.peers is not None:  # NVLink mailbox stores, consumed on the device by the step kernel
+                    kw |= {"tensor": raw, "sums": sums, "count": total, "peers": ctx.peers, "epoch": ctx.peers.publish(sums)}
+                else:  # NCCL all-reduce of the two doubles
+                    kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums)}
             return {"noise_philox": kw, "noise_scale": scale}
         return {"noise_tensor": self.noise_sampler(sigma, sigma_next), "noise_scale": scale}
 

@@ -137,6 +137,12 @@ typedef struct SonarStepParams {
    * tensor, a single launch (moments -> grid barrier -> step, normals kept in registers). */
   double* sums_scratch;
   int32_t sums_parity;
+  /* batch-sharded statistics over peer memory (see sonar_peer_*): when peer_world > 1 the kernel
+   * waits until all peer_world partial sums of `peer_epoch` have landed in the LOCAL mailbox
+   * `peer_mailbox` and normalises with their total (noise_sums is ignored). */
+  int32_t peer_world;
+  const double* peer_mailbox;
+  double peer_epoch;
 } SonarStepParams;
 
 int sonar_step_f32(const SonarStepParams* params_host, void* stream);
@@ -327,6 +333,28 @@ typedef struct SonarDwtSynthesisParams {
 int sonar_dwt_coeff_len(int n, int filter_len);
 int sonar_dwt2_analysis(const SonarDwtAnalysisParams* params_host, void* stream);
 int sonar_dwt2_synthesis(const SonarDwtSynthesisParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory exchange of the global scale_noise statistics (one node, NVLink 5 / NVSwitch).
+ * replaces: the whole-batch reduction inside scale_noise when the batch is sharded over GPUs
+ *                                                          py/utils.py:100-106
+ * Each rank allocates one mailbox, exports its CUDA IPC handle (64 bytes, exchanged by the host
+ * over torch.distributed), opens every peer's handle, then per exchange calls
+ * sonar_peer_publish_sums (stores its two partial sums into every rank's mailbox over NVLink) and
+ * launches the step with peer_world / peer_mailbox / peer_epoch set. Epochs must increase by 1 per
+ * exchange on every rank; two parity slots make the scheme race free without a barrier.
+ * ---------------------------------------------------------------------------------------------- */
+#define SONAR_PEER_MAX_RANKS 8
+int sonar_peer_alloc(void** mailbox_out_host);
+int sonar_peer_free(void* mailbox);
+int sonar_peer_get_handle(const void* mailbox, unsigned char* handle64_host);
+int sonar_peer_open_handle(const unsigned char* handle64_host, void** mapped_out_host);
+int sonar_peer_close_handle(void* mapped);
+/* scale_noise whose statistics are the total of the `world` partial sums of `epoch` in `mailbox` */
+int sonar_scale_noise_peers_f32(const float* x, float* out, int64_t n, const double* mailbox, int world, double epoch,
+                                int64_t count, float factor, float threshold_std_devs, void* stream);
+int sonar_peer_publish_sums(void* const* mailboxes_host, int rank, int world, const double* local_sums, double epoch,
+                            void* stream);
 
 #ifdef __cplusplus
 }
