@@ -62,6 +62,8 @@ class SonarStepParams(ctypes.Structure):
         ("peer_world", c_int32),
         ("peer_mailbox", c_void_p),
         ("peer_epoch", c_double),
+        ("peer_rank", c_int32),
+        ("peer_targets", c_void_p * 8),
     ]
 
 

@@ -227,10 +227,28 @@ __device__ __forceinline__ NormDecision decide_normalisation_peers(const double*
   return decide_normalisation(shared2, count, threshold_std_devs);
 }
 
+// a / b for a divisor that is the same for every element: reciprocal computed once by the caller,
+// one Newton step on the residual -> the correctly rounded quotient whenever a/b is a normal number
+// (3 instructions instead of the ~12 of the generic IEEE division sequence).
+__device__ __forceinline__ float div_by(float a, float b, float inv_b) {
+  const float q = a * inv_b;
+  const float r = fmaf(-q, b, a);
+  return fmaf(r, inv_b, q);
+}
+
 __device__ __forceinline__ float apply_norm(float v, const NormDecision& d) {
   if (d.sub_mean) v -= d.mean;
   if (d.div_std) v /= d.std;
   return v;
+}
+
+// Block-cooperative decision: one thread does the fp64 arithmetic, everybody reads the result.
+// All threads of the block must call. `slot` is a NormDecision in shared memory.
+__device__ __forceinline__ NormDecision decide_normalisation_block(const double* __restrict__ sums, int64_t count,
+                                                                   float threshold_std_devs, NormDecision* slot) {
+  if (threadIdx.x == 0) *slot = decide_normalisation(sums, count, threshold_std_devs);
+  __syncthreads();
+  return *slot;
 }
 
 // ---------------------------------------------------------------------------------------------

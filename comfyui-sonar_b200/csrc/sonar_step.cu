@@ -29,29 +29,45 @@ __device__ __forceinline__ float update_history(const SonarStepParams& p, bool h
   return have_h ? blend<float>(p.history_blend, v * p.md_scale, h * p.hd_scale, p.hd_ratio) : v;
 }
 
-__device__ __forceinline__ StepElem step_element(const SonarStepParams& p, float x, float den, float h_raw,
-                                                 float noise) {
-  const bool m_is_one = p.momentum == 1.0f;
-  const bool denoised_mode = p.mode == SONAR_MODE_DENOISED;
-  bool have_h = p.hist_state != SONAR_HIST_NONE;
-  const bool have_h_first_mix = p.hist_state == SONAR_HIST_PRESENT;
-  float h = have_h ? h_raw / p.hist_in_div : 0.0f;
+// Per-launch constants derived once per thread from the parameter block.
+struct StepConsts {
+  float inv_sigma;
+  float inv_hist_div;
+  bool m_is_one, denoised_mode, have_h0, have_h_first_mix, scale_hist;
+};
+
+__device__ __forceinline__ StepConsts make_consts(const SonarStepParams& p) {
+  StepConsts c;
+  c.inv_sigma = 1.0f / p.sigma;
+  c.inv_hist_div = 1.0f / p.hist_in_div;
+  c.m_is_one = p.momentum == 1.0f;
+  c.denoised_mode = p.mode == SONAR_MODE_DENOISED;
+  c.have_h0 = p.hist_state != SONAR_HIST_NONE;
+  c.have_h_first_mix = p.hist_state == SONAR_HIST_PRESENT;
+  c.scale_hist = p.hist_in_div != 1.0f;
+  return c;
+}
+
+__device__ __forceinline__ StepElem step_element(const SonarStepParams& p, const StepConsts& c, float x, float den,
+                                                 float h_raw, float noise) {
+  bool have_h = c.have_h0;
+  float h = have_h ? (c.scale_hist ? div_by(h_raw, p.hist_in_div, c.inv_hist_div) : h_raw) : 0.0f;
 
   // ---- get_momentum_denoised ----
   float md = den;
-  if (!m_is_one && have_h_first_mix && denoised_mode) md = blend<float>(p.momentum_blend, h * p.sigma, den, p.momentum);
+  if (!c.m_is_one && c.have_h_first_mix && c.denoised_mode) md = blend<float>(p.momentum_blend, h * p.sigma, den, p.momentum);
   if (p.history_active) {
-    h = update_history(p, have_h, h, den / p.sigma);
+    h = update_history(p, have_h, h, div_by(den, p.sigma, c.inv_sigma));
     have_h = true;
   }
   const float den_eff = p.momentum_active ? md : den;
 
   // ---- derivative / DPM-Solver++ difference term ----
-  const float d = p.kind == SONAR_STEP_EULER ? (x - den_eff) / p.sigma : p.c0 * den_eff;
+  const float d = p.kind == SONAR_STEP_EULER ? div_by(x - den_eff, p.sigma, c.inv_sigma) : p.c0 * den_eff;
 
   // ---- get_momentum_d ----
   float d_out = d;
-  if (!m_is_one && !denoised_mode) {
+  if (!c.m_is_one && !c.denoised_mode) {
     const float mom_d = have_h ? blend<float>(p.momentum_blend, h, d, p.momentum) : d;
     if (p.history_active) {
       h = update_history(p, have_h, h, p.mode == SONAR_MODE_NEW ? d : mom_d);
@@ -67,22 +83,51 @@ __device__ __forceinline__ StepElem step_element(const SonarStepParams& p, float
   return r;
 }
 
+// scale_noise on load: (v - mean) / std * factor with the division done by reciprocal + Newton step
+struct NoiseNorm {
+  float mean, std, inv_std, factor;
+  bool sub_mean, div_std;
+};
+
+__device__ __forceinline__ NoiseNorm make_noise_norm(const NormDecision& d, float factor) {
+  NoiseNorm n;
+  n.mean = d.mean;
+  n.std = d.std;
+  n.inv_std = 1.0f / d.std;
+  n.factor = factor;
+  n.sub_mean = d.sub_mean != 0;
+  n.div_std = d.div_std != 0;
+  return n;
+}
+
+__device__ __forceinline__ float norm_noise_value(float v, const NoiseNorm& n) {
+  if (n.sub_mean) v -= n.mean;
+  if (n.div_std) v = div_by(v, n.std, n.inv_std);
+  return v * n.factor;
+}
+
 // ---- contiguous float4 variant (no noise / tensor noise) ----
+__device__ __forceinline__ NormDecision tensor_noise_decision(const SonarStepParams& p, bool norm_noise,
+                                                              NormDecision* slot, double* peer_sums) {
+  if (!norm_noise) return NormDecision{0.f, 1.f, 0, 0};
+  if (p.peer_world > 1)
+    return decide_normalisation_peers(p.peer_mailbox, p.peer_world, p.peer_epoch, p.noise_count,
+                                      p.noise_threshold_std_devs, peer_sums);
+  return decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, slot);
+}
+
 __global__ void __launch_bounds__(kBlock)
 sonar_step_vec_kernel(SonarStepParams p) {
+  __shared__ NormDecision nd_slot;
+  __shared__ double peer_sums[2];
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
   const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
   const bool write_h = p.hist_out != nullptr;
   // raw Gaussian tensor + device-resident sums: apply scale_noise on load
   const bool norm_noise = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
-  __shared__ double peer_sums[2];
-  const NormDecision nd =
-      !norm_noise ? NormDecision{0.f, 1.f, 0, 0}
-      : p.peer_world > 1
-          ? decide_normalisation_peers(p.peer_mailbox, p.peer_world, p.peer_epoch, p.noise_count,
-                                       p.noise_threshold_std_devs, peer_sums)
-          : decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs);
-  const float nfac = norm_noise ? p.noise_factor : 1.0f;
+  const NoiseNorm nn = make_noise_norm(tensor_noise_decision(p, norm_noise, &nd_slot, peer_sums),
+                                       norm_noise ? p.noise_factor : 1.0f);
+  const StepConsts c = make_consts(p);
   const int64_t n4 = p.n >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -92,21 +137,21 @@ sonar_step_vec_kernel(SonarStepParams p) {
     const float4 h = has_h_in ? ld4(p.hist_in + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 nz = has_noise ? ld4_stream(p.noise + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (norm_noise) {
-      nz.x = apply_norm(nz.x, nd) * nfac;
-      nz.y = apply_norm(nz.y, nd) * nfac;
-      nz.z = apply_norm(nz.z, nd) * nfac;
-      nz.w = apply_norm(nz.w, nd) * nfac;
+      nz.x = norm_noise_value(nz.x, nn);
+      nz.y = norm_noise_value(nz.y, nn);
+      nz.z = norm_noise_value(nz.z, nn);
+      nz.w = norm_noise_value(nz.w, nn);
     }
-    const StepElem a = step_element(p, x.x, dn.x, h.x, nz.x);
-    const StepElem b = step_element(p, x.y, dn.y, h.y, nz.y);
-    const StepElem c = step_element(p, x.z, dn.z, h.z, nz.z);
-    const StepElem d = step_element(p, x.w, dn.w, h.w, nz.w);
-    st4(p.x_out + 4 * i, make_float4(a.x_out, b.x_out, c.x_out, d.x_out));
-    if (write_h) st4(p.hist_out + 4 * i, make_float4(a.h_out, b.h_out, c.h_out, d.h_out));
+    const StepElem a = step_element(p, c, x.x, dn.x, h.x, nz.x);
+    const StepElem b = step_element(p, c, x.y, dn.y, h.y, nz.y);
+    const StepElem e = step_element(p, c, x.z, dn.z, h.z, nz.z);
+    const StepElem d = step_element(p, c, x.w, dn.w, h.w, nz.w);
+    st4(p.x_out + 4 * i, make_float4(a.x_out, b.x_out, e.x_out, d.x_out));
+    if (write_h) st4(p.hist_out + 4 * i, make_float4(a.h_out, b.h_out, e.h_out, d.h_out));
   }
   for (int64_t i = (n4 << 2) + tid; i < p.n; i += stride) {
-    const float nzs = has_noise ? apply_norm(p.noise[i], nd) * nfac : 0.f;
-    const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, nzs);
+    const float nzs = has_noise ? (norm_noise ? norm_noise_value(p.noise[i], nn) : p.noise[i]) : 0.f;
+    const StepElem a = step_element(p, c, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, nzs);
     p.x_out[i] = a.x_out;
     if (write_h) p.hist_out[i] = a.h_out;
   }
@@ -114,21 +159,18 @@ sonar_step_vec_kernel(SonarStepParams p) {
 
 __global__ void __launch_bounds__(kBlock)
 sonar_step_scalar_kernel(SonarStepParams p) {
+  __shared__ NormDecision nd_slot;
+  __shared__ double peer_sums[2];
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
   const bool has_noise = p.noise_kind == SONAR_NOISE_TENSOR || p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
   const bool write_h = p.hist_out != nullptr;
   const bool norm_noise = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
-  __shared__ double peer_sums[2];
-  const NormDecision nd =
-      !norm_noise ? NormDecision{0.f, 1.f, 0, 0}
-      : p.peer_world > 1
-          ? decide_normalisation_peers(p.peer_mailbox, p.peer_world, p.peer_epoch, p.noise_count,
-                                       p.noise_threshold_std_devs, peer_sums)
-          : decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs);
-  const float nfac = norm_noise ? p.noise_factor : 1.0f;
+  const NoiseNorm nn = make_noise_norm(tensor_noise_decision(p, norm_noise, &nd_slot, peer_sums),
+                                       norm_noise ? p.noise_factor : 1.0f);
+  const StepConsts c = make_consts(p);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
-    const StepElem a = step_element(p, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f,
-                                    has_noise ? apply_norm(p.noise[i], nd) * nfac : 0.f);
+    const float nzs = has_noise ? (norm_noise ? norm_noise_value(p.noise[i], nn) : p.noise[i]) : 0.f;
+    const StepElem a = step_element(p, c, p.x[i], p.denoised[i], has_h_in ? p.hist_in[i] : 0.f, nzs);
     p.x_out[i] = a.x_out;
     if (write_h) p.hist_out[i] = a.h_out;
   }
@@ -138,9 +180,9 @@ sonar_step_scalar_kernel(SonarStepParams p) {
 // A (vt, k) pair owns the 4 elements li = vt + T*(4k + lane): T apart, so consecutive threads touch
 // consecutive addresses (coalesced scalar accesses). Element index li is GLOBAL (position in the
 // un-sharded noise tensor); the local tensors hold the slice [noise_begin, noise_begin + n).
-__device__ __forceinline__ void step_pair(const SonarStepParams& p, const NormDecision& nd, const float z[4],
-                                          int64_t li0, int64_t T, int64_t begin, int64_t end, bool has_h_in,
-                                          bool write_h) {
+__device__ __forceinline__ void step_pair(const SonarStepParams& p, const StepConsts& c, const NoiseNorm& nn,
+                                          const float z[4], int64_t li0, int64_t T, int64_t begin, int64_t end,
+                                          bool has_h_in, bool write_h) {
   float xs[4], ds[4], hs[4];
   bool ok[4];
 #pragma unroll
@@ -156,8 +198,8 @@ __device__ __forceinline__ void step_pair(const SonarStepParams& p, const NormDe
   for (int lane = 0; lane < 4; ++lane) {
     if (!ok[lane]) continue;
     const int64_t i = li0 + T * lane - begin;
-    const float nz = apply_norm(z[lane], nd) * p.noise_factor;
-    const StepElem a = step_element(p, xs[lane], ds[lane], hs[lane], nz);
+    const float nz = norm_noise_value(z[lane], nn);
+    const StepElem a = step_element(p, c, xs[lane], ds[lane], hs[lane], nz);
     p.x_out[i] = a.x_out;
     if (write_h) p.hist_out[i] = a.h_out;
   }
@@ -167,9 +209,12 @@ __global__ void __launch_bounds__(kBlock)
 sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint32_t k_hi) {
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
   const bool write_h = p.hist_out != nullptr;
+  __shared__ NormDecision nd_slot;
   const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
-                              ? decide_normalisation(p.noise_sums, p.noise_count, p.noise_threshold_std_devs)
+                              ? decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot)
                               : NormDecision{0.f, 1.f, 0, 0};
+  const NoiseNorm nn = make_noise_norm(nd, p.noise_factor);
+  const StepConsts c = make_consts(p);
   const int64_t T = st.threads;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t begin = p.noise_begin, end = p.noise_begin + p.n;
@@ -180,7 +225,7 @@ sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint
       if (li0 + 3 * T < begin) continue;
       const float4 z4 = philox_normal4(st, (uint32_t)vt, k);
       const float z[4] = {z4.x, z4.y, z4.z, z4.w};
-      step_pair(p, nd, z, li0, T, begin, end, has_h_in, write_h);
+      step_pair(p, c, nn, z, li0, T, begin, end, has_h_in, write_h);
     }
   }
 }
@@ -314,7 +359,10 @@ sonar_step_coop_kernel(SonarStepParams p, PhiloxStream st, uint32_t calls, doubl
     atomicAdd(&slot[1], ss);
   }
   cooperative_groups::this_grid().sync();
-  const NormDecision nd = decide_normalisation(slot, p.noise_count, p.noise_threshold_std_devs);
+  __shared__ NormDecision nd_slot;
+  const NoiseNorm nn = make_noise_norm(
+      decide_normalisation_block(slot, p.noise_count, p.noise_threshold_std_devs, &nd_slot), p.noise_factor);
+  const StepConsts c = make_consts(p);
   if (tid == 0) {
     next_slot[0] = 0.0;
     next_slot[1] = 0.0;
@@ -325,7 +373,7 @@ sonar_step_coop_kernel(SonarStepParams p, PhiloxStream st, uint32_t calls, doubl
     const uint32_t k = (uint32_t)j % calls;
     const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
     const bool live = vt < T && (uint32_t)j < calls * (uint32_t)((T + nthreads - 1) / nthreads) && li0 < end;
-    if (live) step_pair(p, nd, z[j], li0, T, 0, end, has_h_in, write_h);
+    if (live) step_pair(p, c, nn, z[j], li0, T, 0, end, has_h_in, write_h);
   }
 }
 
@@ -400,9 +448,25 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     if (self_stats) {
       // the caller left the moments pre-pass to us (un-sharded draw): sums_scratch is double[4],
       // two ping-pong slots, zero-initialised once by the caller
-      if (p.sums_scratch == nullptr || p.noise_begin != 0 || p.n != p.noise_numel_total) return (int)cudaErrorInvalidValue;
+      const bool sharded = p.peer_world > 1;
+      if (p.sums_scratch == nullptr || (!sharded && (p.noise_begin != 0 || p.n != p.noise_numel_total)))
+        return (int)cudaErrorInvalidValue;
       double* slot = p.sums_scratch + 2 * (p.sums_parity & 1);
       double* next_slot = p.sums_scratch + 2 * ((p.sums_parity & 1) ^ 1);
+      if (sharded) {
+        // batch-sharded: materialise + moments of THIS rank's slice, store the two partial sums into
+        // every rank's mailbox over NVLink, then the step kernel waits for all partials on the device
+        if (p.noise == nullptr) return (int)cudaErrorInvalidValue;
+        SONAR_CUDA_TRY(cudaMemsetAsync(slot, 0, 2 * sizeof(double), stream));
+        philox_fill_moments_device<<<streaming_grid(T, kBlock, 1), kBlock, 0, stream>>>(
+            const_cast<float*>(p.noise), p.noise_begin, end, st, (uint32_t)k_lo, (uint32_t)k_hi, slot);
+        SONAR_LAUNCH_CHECK();
+        const int rc = sonar_peer_publish_sums(p.peer_targets, p.peer_rank, p.peer_world, slot, p.peer_epoch, stream);
+        if (rc != 0) return rc;
+        p.noise_kind = SONAR_NOISE_TENSOR_NORMALIZED;
+        p.noise_sums = slot;
+        goto dense_step;
+      }
       p.noise_count = p.n;
       const int64_t calls = k_hi + 1;
       const int64_t coop_grid = coop_grid_for(p.n, p.philox_grid_blocks);

@@ -134,9 +134,10 @@ scale_noise_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t
                    const double* __restrict__ sums, int64_t count, float factor, float threshold_std_devs,
                    const double* __restrict__ peer_mailbox, int peer_world, double peer_epoch) {
   __shared__ double peer_sums[2];
+  __shared__ NormDecision nd_slot;
   const NormDecision nd = peer_world > 1 ? decide_normalisation_peers(peer_mailbox, peer_world, peer_epoch, count,
                                                                        threshold_std_devs, peer_sums)
-                                         : decide_normalisation(sums, count, threshold_std_devs);
+                                         : decide_normalisation_block(sums, count, threshold_std_devs, &nd_slot);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {

@@ -57,6 +57,11 @@ class PeerExchange:
             self._opened.append(ptr.value)
         dist.barrier(group=group)
 
+    def next_epoch(self) -> float:
+        """Reserves the next exchange epoch (for callers whose C-ABI call publishes by itself)."""
+        self.epoch += 1
+        return float(self.epoch)
+
     def publish(self, sums: torch.Tensor) -> float:
         """Stores this rank's (sum, sum^2) into every rank's mailbox; returns the epoch to wait for."""
         import ctypes

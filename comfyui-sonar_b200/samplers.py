@@ -277,9 +277,6 @@ class SonarBase:
                 raw = noise_philox["tensor"]
                 p.noise_kind, p.noise = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr()
                 p.noise_sums, p.noise_count = keep.data_ptr(), noise_philox["count"]
-                peers = noise_philox.get("peers")
-                if peers is not None:
-                    p.peer_world, p.peer_mailbox, p.peer_epoch = peers.world_size, peers.local, noise_philox["epoch"]
                 keep = (keep, raw)
             elif noise_philox["normalized"]:
                 # un-sharded: one C-ABI call materialises the normals + moments and runs the step
@@ -288,6 +285,15 @@ class SonarBase:
                 self._sums_parity ^= 1
                 p.noise_count = x.numel()
                 p.noise = self._noise_scratch(x).data_ptr()
+                peers = noise_philox.get("peers")
+                if peers is not None:
+                    p.noise_count = noise_philox["count"]
+                    p.peer_world, p.peer_rank = peers.world_size, peers.rank
+                    p.peer_mailbox, p.peer_epoch = peers.local, noise_philox["epoch"]
+                    if not getattr(self, "_peer_targets_set", False):
+                        for r in range(peers.world_size):
+                            p.peer_targets[r] = peers.mapped[r]
+                        self._peer_targets_set = True
         elif noise_tensor is not None:
             if noise_tensor.dtype != torch.float32 or not noise_tensor.is_contiguous():
                 noise_tensor = noise_tensor.to(torch.float32).contiguous()
@@ -338,15 +344,15 @@ class SonarBase:
             draw = ops.reserve_draw(total, x.device)
             kw = {"draw": draw, "factor": factor, "normalized": normalized, "begin": begin}
             if normalized and sharded:
-                # the statistics span several ranks: materialise this rank's slice once while reducing
-                # its moments, all-reduce the 2 doubles; the step kernel normalises on load
-                raw = self._noise_scratch(x)
-                sums = torch.empty(2, device=x.device, dtype=torch.float64)
-                ops.philox_normal_fill_moments(draw, raw, sums, begin=begin)
                 ctx = parallel.active()
-                if ctx.peers is not None:  # NVLink mailbox stores, consumed on the device by the step kernel
-                    kw |= {"tensor": raw, "sums": sums, "count": total, "peers": ctx.peers, "epoch": ctx.peers.publish(sums)}
-                else:  # NCCL all-reduce of the two doubles
+                if ctx.peers is not None:
+                    # one C-ABI call: materialise + moments of this rank's slice, NVLink stores of the two
+                    # partial sums into every rank's mailbox, step kernel waits for them on the device
+                    kw |= {"peers": ctx.peers, "epoch": ctx.peers.next_epoch(), "count": total}
+                else:  # no peer memory: NCCL all-reduce of the two doubles between two calls
+                    raw = self._noise_scratch(x)
+                    sums = torch.empty(2, device=x.device, dtype=torch.float64)
+                    ops.philox_normal_fill_moments(draw, raw, sums, begin=begin)
                     kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums)}
             return {"noise_philox": kw, "noise_scale": scale}
         return {"noise_tensor": self.noise_sampler(sigma, sigma_next), "noise_scale": scale}

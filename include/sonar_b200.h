@@ -143,6 +143,10 @@ typedef struct SonarStepParams {
   int32_t peer_world;
   const double* peer_mailbox;
   double peer_epoch;
+  /* with noise_sums == NULL and peer_world > 1 the call also publishes this rank's partial sums:
+   * it needs every rank's mailbox as mapped here (sonar_peer_open_handle) and this rank's index */
+  int32_t peer_rank;
+  void* peer_targets[8];
 } SonarStepParams;
 
 int sonar_step_f32(const SonarStepParams* params_host, void* stream);
