@@ -9,20 +9,22 @@ history 0.75, NEW mode, eta 1, s_noise 1); denoiser stub x*0.9 outside the timed
 One bench "step" = one 30-step sampling run over one batch. Metric: latent noise elements / second
 (elements = 30 x 524,288 per batch).
 
-* value     : device-resident throughput. Every sampler step's kernels (Philox moments pre-pass + fused
-              step) are bracketed by CUDA events on the launching stream; between sampler steps the
+* value     : device-resident throughput. Every sampler step's kernels (one fused step launch; the
+              first step also carries the batched Philox statistics of all 29 noise draws) are
+              bracketed by CUDA events on the launching stream; between sampler steps the
               stub denoiser runs and L2 is flushed (256 MiB write), as a real UNet call would do.
               ms_per_step = sum of those 30 event intervals, max over ranks.
 * e2e       : the same run through the public sampler function with HOST buffers: pinned x0 -> H2D,
               30 steps, result D2H, wall clock between device synchronisations.
-* roofline  : dominant kernel (sonar_step_vec_kernel): algorithmic bytes per launch (24 B/element:
-              read x, denoised, history, raw noise; write x', history') / CUDA-event duration of that
-              launch with cold L2, against MEASURED_PEAKS.json hbm_gbs; the same kernel on the C5
-              per-GPU shard shape is reported as roofline_large_tensor.
+* roofline  : dominant kernel (sonar_step_fast_philox_kernel): algorithmic bytes per launch
+              (20 B/element: read x, denoised, history; write x', history'; the noise is regenerated
+              from the Philox stream in registers) / CUDA-event duration of that launch with cold L2,
+              against MEASURED_PEAKS.json hbm_gbs; the same kernel on the C5 per-GPU shard shape is
+              reported as roofline_large_tensor.
 * cpu_baseline : the CPU oracle port of the reference algorithm (oracle/sonar_oracle.py) on the host
               cores, same workload, bounded sample.
 * N > 1     : weak scaling by batch: every rank holds 8 latents of a global batch of 8N; the global
-              scale_noise statistics are all-reduced (2 doubles, NCCL) per sampler step.
+              scale_noise statistics of all 29 draws are all-reduced ONCE per run (29x2 doubles, NCCL).
 """
 
 from __future__ import annotations
@@ -225,54 +227,65 @@ class StepTimer:
 
 
 def step_kernel_roofline(sb, dev, shape, peak: float, peak_src: str, reps: int) -> dict:
-    """Times the dominant kernel alone (sonar_step_vec_kernel: momentum mix + history updates + Euler
-    step + normalise-on-load noise injection) with CUDA events on the launching stream, cold L2
-    (256 MiB flush enqueued right before each launch). Algorithmic bytes: 24 B/element = read x,
-    denoised, history, raw noise; write x', history'."""
+    """Times the dominant kernel alone (sonar_step_fast_philox_kernel: momentum mix + both history
+    updates + Euler step + ancestral noise regenerated from the Philox stream and normalised from the
+    look-ahead statistics). Algorithmic bytes: 20 B/element = read x, denoised, history; write x',
+    history' (the noise never touches HBM).
+
+    The launches of several independent operand sets are captured into ONE CUDA graph, so the interval
+    between the two CUDA events is device time of back-to-back kernels, not host launch cadence (a
+    ctypes launch costs ~5 us on the host, as long as the kernel itself at this size). L2 is flushed
+    (256 MiB write) before every replay and each operand set is touched once per replay: cold reads."""
     import statistics as st
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n = 1
     for d in shape:
         n *= d
-    # several independent operand sets per timed interval: every launch still sees cold operands (each
-    # set is touched once after the flush) and the CUDA-event overhead is amortised over the batch
-    n_sets = max(2, min(8, (96 << 20) // (24 * n)))
+    n_sets = max(2, min(8, (96 << 20) // (20 * n)))
     sets = []
     for _ in range(n_sets):
         x, den, hist = (torch.randn(shape, device=dev) for _ in range(3))
         draw = sb.ops.reserve_draw(n, dev)
-        raw = torch.empty_like(x)
-        sums = torch.empty(2, device=dev, dtype=torch.float64)
-        sb.ops.philox_normal_fill_moments(draw, raw, sums)
+        sums = sb.ops.philox_normal_moments_batch(draw, [draw.offset], begin=0, count=n, device=dev)
         stepper = sb.samplers.SonarBase(sb.samplers.SonarConfig())
-        kw = {"draw": draw, "factor": 1.0, "normalized": True, "begin": 0, "tensor": raw, "sums": sums, "count": n}
+        kw = {"draw": draw, "factor": 1.0, "normalized": True, "begin": 0, "sums": sums, "sums_ptr": sums.data_ptr(), "count": n}
         sets.append((stepper, x, den, hist, kw))
+    outs = []
 
     def launch_all():
+        outs.clear()
         for stepper, x, den, hist, kw in sets:
             stepper.history_d = hist
-            stepper.fused_step(3, x, den, 5.0, kind=sb.ops.STEP_EULER, c0=-1.5, noise_scale=0.7, noise_philox=kw)
+            outs.append(stepper.fused_step(3, x, den, 5.0, kind=sb.ops.STEP_EULER, c0=-1.5, noise_scale=0.7, noise_philox=kw))
 
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            launch_all()
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        launch_all()
     for _ in range(3):
         flush.zero_()
-        launch_all()
+        graph.replay()
     torch.cuda.synchronize()
     us = []
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        launch_all()
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         us.append(e0.elapsed_time(e1) * 1e3 / n_sets)
     launch_us = st.median(us)
-    algo = 24 * n
+    algo = 20 * n
     achieved = algo / (launch_us * 1e-6) / 1e9
     return {
         "bound": "hbm",
-        "kernel": "sonar_step_vec_kernel",
+        "kernel": "sonar_step_fast_philox_kernel",
         "shape": list(shape),
         "achieved": achieved,
         "peak": peak,
@@ -283,7 +296,7 @@ def step_kernel_roofline(sb, dev, shape, peak: float, peak_src: str, reps: int) 
         "algorithmic_bytes_per_launch": algo,
         "launch_us": launch_us,
         "launches_timed": len(us) * n_sets,
-        "timing": f"CUDA events around {n_sets} back-to-back launches on distinct operand sets after a 256 MiB L2 flush",
+        "timing": f"CUDA events around one graph replay of {n_sets} back-to-back launches on distinct operand sets, after a 256 MiB L2 flush",
     }
 
 
@@ -363,8 +376,8 @@ def run_b200_arm(args) -> None:
     traffic_path = REPO / "profiles" / "traffic.json"
     if traffic_path.exists():
         traffic = json.loads(traffic_path.read_text())
-        roofline["traffic"] = traffic.get("sonar_step_vec_kernel@8x4x128x128")
-        roofline_large["traffic"] = traffic.get("sonar_step_vec_kernel@1x16x33x90x160")
+        roofline["traffic"] = traffic.get("sonar_step_fast_philox_kernel@8x4x128x128")
+        roofline_large["traffic"] = traffic.get("sonar_step_fast_philox_kernel@1x16x33x90x160")
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e_times = []
@@ -426,7 +439,7 @@ def run_b200_arm(args) -> None:
                 "per_gpu_shape": list(SHAPE),
                 "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
                 "l2": "256 MiB flush between sampler steps (where the UNet runs); stub denoiser untimed",
-                "timing": "sum of 30 CUDA-event intervals per run (Philox moments pre-pass + fused step), max over ranks",
+                "timing": "sum of 30 CUDA-event intervals per run (fused step launch; step 0 includes the batched Philox statistics of all draws), max over ranks",
             },
             "roofline": roofline,
             "roofline_large_tensor": roofline_large,

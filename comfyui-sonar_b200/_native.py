@@ -57,16 +57,13 @@ class SonarStepParams(ctypes.Structure):
         ("noise_numel_total", c_int64),
         ("noise_sums", c_void_p),
         ("noise_count", c_int64),
-        ("sums_scratch", c_void_p),
-        ("sums_parity", c_int32),
         ("peer_world", c_int32),
         ("peer_mailbox", c_void_p),
         ("peer_epoch", c_double),
-        ("peer_rank", c_int32),
-        ("peer_targets", c_void_p * 8),
     ]
 
 
+ABI_VERSION = 2  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PYRAMID_MAX_LEVELS = 16
 PERLIN_MAX_ITERS = 8
@@ -188,13 +185,14 @@ SIGNATURES: dict[str, list] = {
     ],
     "sonar_moments_f32": [c_void_p, c_int64, c_void_p, c_void_p],
     "sonar_philox_normal_moments": [c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p],
+    "sonar_philox_normal_moments_batch": [
+        POINTER(c_uint64), c_int, c_int64, c_int64, c_int64, c_uint64, c_uint32, c_void_p, c_void_p,
+    ],
     "sonar_scale_noise_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p],
     "sonar_add_moments_f32": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "sonar_scale_by_std_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p],
     "sonar_affine_f32": [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p],
     "sonar_step_f32": [POINTER(SonarStepParams), c_void_p],
-    "sonar_step_single_launch_ok": [c_int64, c_uint32],
-    "sonar_step_enable_cooperative": [c_int],
     "sonar_philox_normal_fill_moments_f32": [
         c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p,
     ],
@@ -272,6 +270,10 @@ def load(*, build_if_missing: bool = True) -> ctypes.CDLL:
             raise NativeLibraryError(f"{path} does not export {name}; rebuild the library") from exc
         fn.argtypes = argtypes
         fn.restype = RESTYPES.get(name, c_int)
+    if lib.sonar_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(
+            f"{path} has ABI version {lib.sonar_abi_version()}, this package needs {ABI_VERSION}: rebuild the library",
+        )
     _LIB = lib
     return lib
 

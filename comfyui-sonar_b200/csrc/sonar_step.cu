@@ -11,9 +11,6 @@
 // Philox stream torch.randn(device='cuda') would have produced, optionally with the conditional
 // global normalisation of scale_noise applied from device-resident sums (stats pre-pass in
 // stats.cu: zero HBM bytes for the noise).
-#include <cooperative_groups.h>
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "../../include/sonar_b200.h"
 
@@ -176,6 +173,153 @@ sonar_step_scalar_kernel(SonarStepParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Specialised ("fast") element: the configuration every stock Sonar sampler runs with -- momentum
+// and history both active, lerp blends, CLASSIC/NEW mode, momentum != 1, history not rescaled on
+// load -- with the sampler kind, the mode and the presence of a history as template parameters.
+// The generic step_element above evaluates ~10 launch-uniform conditions and two blend switches per
+// element (160 issued instructions per element in the round-1 ncu capture, 75 % issue-slot busy: the
+// kernel was instruction-bound, not memory-bound); this form is ~30.
+// ---------------------------------------------------------------------------------------------
+struct LerpW {
+  float w, omw;
+  bool small;  // |w| < 0.5: a + w*(b-a), else b - (b-a)*(1-w)   (ATen/native/Lerp.h:21-35)
+};
+
+__device__ __forceinline__ LerpW make_lerp(float w) { return LerpW{w, 1.0f - w, fabsf(w) < 0.5f}; }
+
+__device__ __forceinline__ float lerp_u(float a, float b, const LerpW& l) {
+  const float d = b - a;
+  return l.small ? a + l.w * d : b - d * l.omw;
+}
+
+struct FastConsts {
+  LerpW mom, hist;
+  float sigma, inv_sigma, c0, c1, hd_scale, md_scale, noise_scale;
+};
+
+__device__ __forceinline__ FastConsts make_fast_consts(const SonarStepParams& p) {
+  FastConsts c;
+  c.mom = make_lerp(p.momentum);
+  c.hist = make_lerp(p.hd_ratio);
+  c.sigma = p.sigma;
+  c.inv_sigma = 1.0f / p.sigma;
+  c.c0 = p.c0;
+  c.c1 = p.c1;
+  c.hd_scale = p.hd_scale;
+  c.md_scale = p.md_scale;
+  c.noise_scale = p.noise_scale;
+  return c;
+}
+
+template <int KIND, bool NEW_MODE, bool HAVE_H, bool NOISE>
+__device__ __forceinline__ StepElem step_element_fast(const FastConsts& c, float x, float den, float h, float noise) {
+  // get_momentum_denoised: history <- update(denoised / sigma)
+  const float den_s = div_by(den, c.sigma, c.inv_sigma);
+  const float h1 = HAVE_H ? lerp_u(den_s * c.md_scale, h * c.hd_scale, c.hist) : den_s;
+  // derivative (Euler) or DPM-Solver++ difference term
+  const float d = KIND == SONAR_STEP_EULER ? div_by(x - den, c.sigma, c.inv_sigma) : c.c0 * den;
+  // get_momentum_d: mix with the history, second history update
+  const float mom_d = lerp_u(h1, d, c.mom);
+  StepElem r;
+  r.h_out = lerp_u((NEW_MODE ? d : mom_d) * c.md_scale, h1 * c.hd_scale, c.hist);
+  r.x_out = KIND == SONAR_STEP_EULER ? mom_d * c.c0 + x : c.c1 * x - mom_d;
+  if (NOISE) r.x_out = r.x_out + noise * c.noise_scale;
+  return r;
+}
+
+// NOISE: 0 none, 1 tensor, 2 raw Gaussian tensor normalised on load
+template <int KIND, bool NEW_MODE, bool HAVE_H, int NOISE>
+__global__ void __launch_bounds__(kBlock)
+sonar_step_fast_vec_kernel(SonarStepParams p) {
+  __shared__ NormDecision nd_slot;
+  __shared__ double peer_sums[2];
+  const NoiseNorm nn = make_noise_norm(tensor_noise_decision(p, NOISE == 2, &nd_slot, peer_sums),
+                                       NOISE == 2 ? p.noise_factor : 1.0f);
+  const FastConsts c = make_fast_consts(p);
+  const int64_t n4 = p.n >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n4; i += stride) {
+    const float4 x = ld4_stream(p.x + 4 * i);
+    const float4 dn = ld4_stream(p.denoised + 4 * i);
+    const float4 h = HAVE_H ? ld4(p.hist_in + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nz = NOISE ? ld4_stream(p.noise + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NOISE == 2) {
+      nz.x = norm_noise_value(nz.x, nn);
+      nz.y = norm_noise_value(nz.y, nn);
+      nz.z = norm_noise_value(nz.z, nn);
+      nz.w = norm_noise_value(nz.w, nn);
+    }
+    const StepElem a = step_element_fast<KIND, NEW_MODE, HAVE_H, NOISE != 0>(c, x.x, dn.x, h.x, nz.x);
+    const StepElem b = step_element_fast<KIND, NEW_MODE, HAVE_H, NOISE != 0>(c, x.y, dn.y, h.y, nz.y);
+    const StepElem e = step_element_fast<KIND, NEW_MODE, HAVE_H, NOISE != 0>(c, x.z, dn.z, h.z, nz.z);
+    const StepElem d = step_element_fast<KIND, NEW_MODE, HAVE_H, NOISE != 0>(c, x.w, dn.w, h.w, nz.w);
+    st4(p.x_out + 4 * i, make_float4(a.x_out, b.x_out, e.x_out, d.x_out));
+    st4(p.hist_out + 4 * i, make_float4(a.h_out, b.h_out, e.h_out, d.h_out));
+  }
+  for (int64_t i = (n4 << 2) + tid; i < p.n; i += stride) {
+    const float nzs = NOISE ? (NOISE == 2 ? norm_noise_value(p.noise[i], nn) : p.noise[i]) : 0.f;
+    const StepElem a =
+        step_element_fast<KIND, NEW_MODE, HAVE_H, NOISE != 0>(c, p.x[i], p.denoised[i], HAVE_H ? p.hist_in[i] : 0.f, nzs);
+    p.x_out[i] = a.x_out;
+    p.hist_out[i] = a.h_out;
+  }
+}
+
+// Philox noise regenerated in registers: CUDA thread <-> virtual ATen thread vt, call k. The 4 lanes
+// of a (vt, k) pair are T elements apart, so consecutive threads touch consecutive addresses: every
+// access is a coalesced 128-byte warp transaction. All loads of a pair are issued before the Philox
+// rounds and the Box-Muller transform, which then run under the loads' latency.
+template <int KIND, bool NEW_MODE, bool HAVE_H>
+__global__ void __launch_bounds__(kBlock)
+sonar_step_fast_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint32_t k_hi) {
+  __shared__ NormDecision nd_slot;
+  const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
+                              ? decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot)
+                              : NormDecision{0.f, 1.f, 0, 0};
+  const NoiseNorm nn = make_noise_norm(nd, p.noise_factor);
+  const FastConsts c = make_fast_consts(p);
+  const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t begin = p.noise_begin, end = p.noise_begin + p.n;
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      float xs[4], ds[4], hs[4];
+      bool ok[4];
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        ok[lane] = li >= begin && li < end;
+        const int64_t i = ok[lane] ? li - begin : 0;
+        xs[lane] = ok[lane] ? __ldg(p.x + i) : 0.0f;
+        ds[lane] = ok[lane] ? __ldg(p.denoised + i) : 0.0f;
+        hs[lane] = (HAVE_H && ok[lane]) ? p.hist_in[i] : 0.0f;
+      }
+      float z[4];
+      if (ok[2] || ok[3]) {
+        const float4 z4 = philox_normal4(st, (uint32_t)vt, k);
+        z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+      } else {  // lanes 2, 3 lie outside the slice: one Box-Muller is enough
+        const float2 z2 = philox_normal2_lo(st, (uint32_t)vt, k);
+        z[0] = z2.x; z[1] = z2.y; z[2] = 0.0f; z[3] = 0.0f;
+      }
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        if (!ok[lane]) continue;
+        const int64_t i = li0 + T * lane - begin;
+        const StepElem a =
+            step_element_fast<KIND, NEW_MODE, HAVE_H, true>(c, xs[lane], ds[lane], hs[lane], norm_noise_value(z[lane], nn));
+        p.x_out[i] = a.x_out;
+        p.hist_out[i] = a.h_out;
+      }
+    }
+  }
+}
+
 // ---- Philox variants: CUDA thread <-> virtual ATen thread vt (Philox subsequence), call k ----
 // A (vt, k) pair owns the 4 elements li = vt + T*(4k + lane): T apart, so consecutive threads touch
 // consecutive addresses (coalesced scalar accesses). Element index li is GLOBAL (position in the
@@ -230,196 +374,57 @@ sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint
   }
 }
 
-// Single-launch variant for small tensors (launch-bound regime): phase 1 draws the Philox normals
-// into registers and reduces their moments, a grid-wide barrier publishes the global sums, phase 2
-// applies the conditional normalisation to the SAME registers and performs the step. The whole
-// grid must be co-resident (cooperative launch); each thread owns at most kCoopPairs (vt, k) pairs.
-// The double[2] sums slot is zeroed for the next launch by the kernel itself (ping-pong slots).
-constexpr int kCoopPairs = 4;
-
-// materialise + moments in one pass (same kernel as stats.cu's, local to this TU)
-__global__ void __launch_bounds__(kBlock)
-philox_fill_moments_device(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo,
-                           uint32_t k_hi, double* __restrict__ sums) {
-  __shared__ double scratch[64];
-  double s = 0.0, ss = 0.0;
-  const int64_t T = st.threads;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
-    float fs = 0.0f, fss = 0.0f;
-    for (uint32_t k = k_lo; k <= k_hi; ++k) {
-      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
-      if (li0 >= end) break;
-      if (li0 + 3 * T < begin) continue;
-      float4 v;
-      if (li0 + 2 * T < end) {
-        v = philox_normal4(st, (uint32_t)vt, k);
-      } else {
-        const float2 lo = philox_normal2_lo(st, (uint32_t)vt, k);
-        v = make_float4(lo.x, lo.y, 0.f, 0.f);
-      }
-      const float vals[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        const int64_t li = li0 + T * lane;
-        if (li >= begin && li < end) {
-          out[li - begin] = vals[lane];
-          fs += vals[lane];
-          fss += vals[lane] * vals[lane];
-        }
-      }
-    }
-    s += (double)fs;
-    ss += (double)fss;
-  }
-  block_sum2(s, ss, scratch);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sums[0], s);
-    atomicAdd(&sums[1], ss);
-  }
-}
-
-// moments of the un-materialised Philox normal draw (same kernel as stats.cu's, local to this TU)
-__global__ void __launch_bounds__(kBlock)
-philox_normal_moments_device(int64_t begin, int64_t end, PhiloxStream st, uint32_t k_lo, uint32_t k_hi,
-                             double* __restrict__ sums) {
-  __shared__ double scratch[64];
-  double s = 0.0, ss = 0.0;
-  const int64_t T = st.threads;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
-    float fs = 0.0f, fss = 0.0f;
-    for (uint32_t k = k_lo; k <= k_hi; ++k) {
-      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
-      if (li0 >= end) break;
-      if (li0 + 3 * T < begin) continue;
-      const float4 v = philox_normal4(st, (uint32_t)vt, k);
-      const float vals[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        const int64_t li = li0 + T * lane;
-        if (li >= begin && li < end) {
-          fs += vals[lane];
-          fss += vals[lane] * vals[lane];
-        }
-      }
-    }
-    s += (double)fs;
-    ss += (double)fss;
-  }
-  block_sum2(s, ss, scratch);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sums[0], s);
-    atomicAdd(&sums[1], ss);
-  }
-}
-
-__global__ void __launch_bounds__(kBlock, 4)
-sonar_step_coop_kernel(SonarStepParams p, PhiloxStream st, uint32_t calls, double* __restrict__ slot,
-                       double* __restrict__ next_slot) {
-  __shared__ double scratch[64];
-  const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
-  const bool write_h = p.hist_out != nullptr;
-  const int64_t T = st.threads;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t end = p.n;  // cooperative path: un-sharded draw, begin == 0
-  float z[kCoopPairs][4];
-  float fs = 0.0f, fss = 0.0f;
-#pragma unroll
-  for (int j = 0; j < kCoopPairs; ++j) {
-    const int64_t vt = tid + (int64_t)(j / calls) * nthreads;
-    const uint32_t k = (uint32_t)j % calls;
-    const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
-    const bool live = vt < T && (uint32_t)j < calls * (uint32_t)((T + nthreads - 1) / nthreads) && li0 < end;
-    if (live) {
-      if (li0 + 2 * T < end) {
-        const float4 z4 = philox_normal4(st, (uint32_t)vt, k);
-        z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
-      } else {  // lanes 2, 3 lie beyond the tensor: one Box-Muller is enough
-        const float2 z2 = philox_normal2_lo(st, (uint32_t)vt, k);
-        z[j][0] = z2.x; z[j][1] = z2.y; z[j][2] = 0.0f; z[j][3] = 0.0f;
-      }
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        const int64_t li = li0 + T * lane;
-        if (li < end) {
-          fs += z[j][lane];
-          fss += z[j][lane] * z[j][lane];
-        }
-      }
-    } else {
-      z[j][0] = z[j][1] = z[j][2] = z[j][3] = 0.0f;
-    }
-  }
-  double s = (double)fs, ss = (double)fss;
-  block_sum2(s, ss, scratch);
-  if (threadIdx.x == 0) {
-    atomicAdd(&slot[0], s);
-    atomicAdd(&slot[1], ss);
-  }
-  cooperative_groups::this_grid().sync();
-  __shared__ NormDecision nd_slot;
-  const NoiseNorm nn = make_noise_norm(
-      decide_normalisation_block(slot, p.noise_count, p.noise_threshold_std_devs, &nd_slot), p.noise_factor);
-  const StepConsts c = make_consts(p);
-  if (tid == 0) {
-    next_slot[0] = 0.0;
-    next_slot[1] = 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < kCoopPairs; ++j) {
-    const int64_t vt = tid + (int64_t)(j / calls) * nthreads;
-    const uint32_t k = (uint32_t)j % calls;
-    const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
-    const bool live = vt < T && (uint32_t)j < calls * (uint32_t)((T + nthreads - 1) / nthreads) && li0 < end;
-    if (live) step_pair(p, c, nn, z[j], li0, T, 0, end, has_h_in, write_h);
-  }
-}
-
 }  // namespace sonar
 
 namespace sonar {
-static int g_coop_enabled = -1;  // -1: decide from the environment on first use
-
-static int coop_blocks_per_sm() {
-  static thread_local int occupancy = -1;
-  if (occupancy < 0) {
-    int dev = 0, coop = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    occupancy = 0;
-    if (coop) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occupancy, sonar_step_coop_kernel, kBlock, 0);
-  }
-  // Measured on B200 (profiles/): at 8x4x128x128 the cooperative launch takes 18 us against ~14 us for
-  // "materialise + moments" followed by the float4 step kernel -- the ALU-bound Philox phase and the
-  // memory phase cannot overlap across the grid barrier. Hence opt-in (SONAR_B200_COOP=1 or
-  // sonar_step_enable_cooperative(1)).
-  if (g_coop_enabled < 0) g_coop_enabled = getenv("SONAR_B200_COOP") != nullptr ? 1 : 0;
-  return g_coop_enabled ? occupancy : 0;
+// the specialised kernels cover the configuration of the stock samplers (see step_element_fast)
+static bool fast_config(const SonarStepParams& p) {
+  return p.mode != SONAR_MODE_DENOISED && p.momentum != 1.0f && p.momentum_active && p.history_active &&
+         p.momentum_blend == SONAR_BLEND_LERP && p.history_blend == SONAR_BLEND_LERP && p.hist_out != nullptr &&
+         (p.hist_state == SONAR_HIST_NONE || p.hist_in_div == 1.0f);
 }
 
-// cooperative grid for a draw of `grid_blocks` emulated ATen blocks covering n elements, or 0
-static int64_t coop_grid_for(int64_t n, uint32_t grid_blocks) {
-  const int64_t T = (int64_t)grid_blocks * kBlock;
-  if (T <= 0 || n <= 0) return 0;
-  int64_t g = (int64_t)coop_blocks_per_sm() * device_info().sm_count;
-  if (g > (int64_t)grid_blocks) g = grid_blocks;
-  if (g <= 0) return 0;
-  const int64_t calls = ((n - 1) / T) / 4 + 1;
-  const int64_t pairs = ((T + g * kBlock - 1) / (g * kBlock)) * calls;
-  return pairs <= kCoopPairs ? g : 0;
+template <int KIND, bool NEW_MODE, bool HAVE_H>
+static void launch_fast_vec(const SonarStepParams& p, int grid, cudaStream_t stream) {
+  const bool tensor = p.noise_kind == SONAR_NOISE_TENSOR, norm = p.noise_kind == SONAR_NOISE_TENSOR_NORMALIZED;
+  if (norm)
+    sonar_step_fast_vec_kernel<KIND, NEW_MODE, HAVE_H, 2><<<grid, kBlock, 0, stream>>>(p);
+  else if (tensor)
+    sonar_step_fast_vec_kernel<KIND, NEW_MODE, HAVE_H, 1><<<grid, kBlock, 0, stream>>>(p);
+  else
+    sonar_step_fast_vec_kernel<KIND, NEW_MODE, HAVE_H, 0><<<grid, kBlock, 0, stream>>>(p);
 }
+
+template <int KIND, bool NEW_MODE, bool HAVE_H>
+static void launch_fast_philox(const SonarStepParams& p, const PhiloxStream& st, uint32_t k_lo, uint32_t k_hi, int grid,
+                               cudaStream_t stream) {
+  sonar_step_fast_philox_kernel<KIND, NEW_MODE, HAVE_H><<<grid, kBlock, 0, stream>>>(p, st, k_lo, k_hi);
+}
+
+// expands to the 8 (kind, mode, history) instantiations of LAUNCH<...>(args)
+#define SONAR_DISPATCH_FAST(LAUNCH, p, ...)                                                       \
+  do {                                                                                            \
+    const bool euler__ = (p).kind == SONAR_STEP_EULER, new__ = (p).mode == SONAR_MODE_NEW;        \
+    const bool have_h__ = (p).hist_state != SONAR_HIST_NONE;                                      \
+    if (euler__) {                                                                                \
+      if (new__) {                                                                                \
+        if (have_h__) LAUNCH<SONAR_STEP_EULER, true, true>(__VA_ARGS__);                          \
+        else LAUNCH<SONAR_STEP_EULER, true, false>(__VA_ARGS__);                                  \
+      } else {                                                                                    \
+        if (have_h__) LAUNCH<SONAR_STEP_EULER, false, true>(__VA_ARGS__);                         \
+        else LAUNCH<SONAR_STEP_EULER, false, false>(__VA_ARGS__);                                 \
+      }                                                                                           \
+    } else {                                                                                      \
+      if (new__) {                                                                                \
+        if (have_h__) LAUNCH<SONAR_STEP_DPMPP, true, true>(__VA_ARGS__);                          \
+        else LAUNCH<SONAR_STEP_DPMPP, true, false>(__VA_ARGS__);                                  \
+      } else {                                                                                    \
+        if (have_h__) LAUNCH<SONAR_STEP_DPMPP, false, true>(__VA_ARGS__);                         \
+        else LAUNCH<SONAR_STEP_DPMPP, false, false>(__VA_ARGS__);                                 \
+      }                                                                                           \
+    }                                                                                             \
+  } while (0)
 }  // namespace sonar
-
-extern "C" int sonar_step_enable_cooperative(int enable) {
-  sonar::g_coop_enabled = enable ? 1 : 0;
-  return 0;
-}
-
-extern "C" int sonar_step_single_launch_ok(int64_t n, uint32_t philox_grid_blocks) {
-  return sonar::coop_grid_for(n, philox_grid_blocks) > 0 ? 1 : 0;
-}
 
 extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
   using namespace sonar;
@@ -434,8 +439,7 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     return (int)cudaErrorInvalidValue;
   if (p.peer_world > 1 && (p.peer_mailbox == nullptr || p.peer_world > SONAR_PEER_MAX_RANKS))
     return (int)cudaErrorInvalidValue;
-  if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr && p.sums_scratch == nullptr)
-    return (int)cudaErrorInvalidValue;
+  if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr) return (int)cudaErrorInvalidValue;
   cudaStream_t stream = (cudaStream_t)stream_;
 
   if (p.noise_kind == SONAR_NOISE_PHILOX || p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED) {
@@ -444,71 +448,24 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     PhiloxStream st{p.philox_seed, p.philox_offset, p.philox_grid_blocks * (uint32_t)kBlock};
     const int64_t T = st.threads, end = p.noise_begin + p.n;
     const int64_t k_lo = (p.noise_begin / T) / 4, k_hi = ((end - 1) / T) / 4;
-    const bool self_stats = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr;
-    if (self_stats) {
-      // the caller left the moments pre-pass to us (un-sharded draw): sums_scratch is double[4],
-      // two ping-pong slots, zero-initialised once by the caller
-      const bool sharded = p.peer_world > 1;
-      if (p.sums_scratch == nullptr || (!sharded && (p.noise_begin != 0 || p.n != p.noise_numel_total)))
-        return (int)cudaErrorInvalidValue;
-      double* slot = p.sums_scratch + 2 * (p.sums_parity & 1);
-      double* next_slot = p.sums_scratch + 2 * ((p.sums_parity & 1) ^ 1);
-      if (sharded) {
-        // batch-sharded: materialise + moments of THIS rank's slice, store the two partial sums into
-        // every rank's mailbox over NVLink, then the step kernel waits for all partials on the device
-        if (p.noise == nullptr) return (int)cudaErrorInvalidValue;
-        SONAR_CUDA_TRY(cudaMemsetAsync(slot, 0, 2 * sizeof(double), stream));
-        philox_fill_moments_device<<<streaming_grid(T, kBlock, 1), kBlock, 0, stream>>>(
-            const_cast<float*>(p.noise), p.noise_begin, end, st, (uint32_t)k_lo, (uint32_t)k_hi, slot);
-        SONAR_LAUNCH_CHECK();
-        const int rc = sonar_peer_publish_sums(p.peer_targets, p.peer_rank, p.peer_world, slot, p.peer_epoch, stream);
-        if (rc != 0) return rc;
-        p.noise_kind = SONAR_NOISE_TENSOR_NORMALIZED;
-        p.noise_sums = slot;
-        goto dense_step;
-      }
-      p.noise_count = p.n;
-      const int64_t calls = k_hi + 1;
-      const int64_t coop_grid = coop_grid_for(p.n, p.philox_grid_blocks);
-      if (coop_grid > 0) {
-        uint32_t calls32 = (uint32_t)calls;
-        void* args[] = {&p, &st, &calls32, &slot, &next_slot};
-        SONAR_CUDA_TRY(cudaLaunchCooperativeKernel((void*)sonar_step_coop_kernel, dim3((unsigned)coop_grid), dim3(kBlock),
-                                                   args, 0, stream));
-        return 0;
-      }
-      // Default path: ONE pass that materialises the normals into the caller's scratch (p.noise) while
-      // reducing their moments, then the float4 step kernel normalises them on load. Two launches, one
-      // C-ABI call; 8 B/element of extra traffic buys a single Philox evaluation per element.
-      SONAR_CUDA_TRY(cudaMemsetAsync(slot, 0, 2 * sizeof(double), stream));
-      const int grid_m = streaming_grid(T, kBlock, 1);
-      if (p.noise != nullptr) {
-        philox_fill_moments_device<<<grid_m, kBlock, 0, stream>>>(const_cast<float*>(p.noise), 0, end, st,
-                                                                  (uint32_t)k_lo, (uint32_t)k_hi, slot);
-        SONAR_LAUNCH_CHECK();
-        p.noise_kind = SONAR_NOISE_TENSOR_NORMALIZED;
-        p.noise_sums = slot;
-        goto dense_step;
-      }
-      // no scratch given: moments pre-pass, then regenerate the normals inside the step kernel
-      philox_normal_moments_device<<<grid_m, kBlock, 0, stream>>>(0, end, st, (uint32_t)k_lo, (uint32_t)k_hi, slot);
-      SONAR_LAUNCH_CHECK();
-      p.noise_sums = slot;
-      p.sums_parity = 0;
-    }
     const int grid = streaming_grid(T, kBlock, 1);
-    sonar_step_philox_kernel<<<grid, kBlock, 0, stream>>>(p, st, (uint32_t)k_lo, (uint32_t)k_hi);
+    if (fast_config(p))
+      SONAR_DISPATCH_FAST(launch_fast_philox, p, p, st, (uint32_t)k_lo, (uint32_t)k_hi, grid, stream);
+    else
+      sonar_step_philox_kernel<<<grid, kBlock, 0, stream>>>(p, st, (uint32_t)k_lo, (uint32_t)k_hi);
     SONAR_LAUNCH_CHECK();
     return 0;
   }
 
-dense_step:
   const bool vec_ok = aligned16(p.x) && aligned16(p.denoised) && aligned16(p.x_out) &&
                       (p.hist_in == nullptr || aligned16(p.hist_in)) &&
                       (p.hist_out == nullptr || aligned16(p.hist_out)) && (p.noise == nullptr || aligned16(p.noise));
   if (vec_ok) {
     const int grid = streaming_grid((p.n + 3) / 4, kBlock, 2);
-    sonar_step_vec_kernel<<<grid, kBlock, 0, stream>>>(p);
+    if (fast_config(p))
+      SONAR_DISPATCH_FAST(launch_fast_vec, p, p, grid, stream);
+    else
+      sonar_step_vec_kernel<<<grid, kBlock, 0, stream>>>(p);
   } else {
     const int grid = streaming_grid(p.n, kBlock, 2);
     sonar_step_scalar_kernel<<<grid, kBlock, 0, stream>>>(p);

@@ -83,6 +83,56 @@ philox_normal_moments_kernel(int64_t begin, int64_t end, PhiloxStream st, uint32
   }
 }
 
+// Moments of SEVERAL future draws of the same shape in one launch (blockIdx.y = draw): a sampler
+// knows, at its first noise request, the generator offsets of every remaining ancestral-noise draw
+// of the run, so the statistics scale_noise needs are reduced once, ahead of time, and each sampler
+// step becomes a single launch that regenerates its normals in registers (samplers.py).
+constexpr int kMomentsBatch = 64;
+struct OffsetBatch {
+  uint64_t offset[kMomentsBatch];
+};
+
+__global__ void __launch_bounds__(kBlock)
+philox_normal_moments_batch_kernel(int64_t begin, int64_t end, PhiloxStream st, OffsetBatch offs, uint32_t k_lo,
+                                   uint32_t k_hi, double* __restrict__ sums) {
+  __shared__ double scratch[64];
+  st.offset = offs.offset[blockIdx.y];
+  double s = 0.0, ss = 0.0;
+  const int64_t T = st.threads;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    float fs = 0.0f, fss = 0.0f;
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      float4 v;
+      if (li0 + 2 * T < end) {
+        v = philox_normal4(st, (uint32_t)vt, k);
+      } else {  // lanes 2, 3 lie beyond the slice: one Box-Muller is enough
+        const float2 lo = philox_normal2_lo(st, (uint32_t)vt, k);
+        v = make_float4(lo.x, lo.y, 0.f, 0.f);
+      }
+      const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) {
+          fs += vals[lane];
+          fss += vals[lane] * vals[lane];
+        }
+      }
+    }
+    s += (double)fs;
+    ss += (double)fss;
+  }
+  block_sum2(s, ss, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[2 * blockIdx.y], s);
+    atomicAdd(&sums[2 * blockIdx.y + 1], ss);
+  }
+}
+
 // One pass: materialise the slice of a Philox normal draw AND reduce its moments (for tensors too
 // large to keep the normals in registers across a grid barrier: write once, read once).
 __global__ void __launch_bounds__(kBlock)
@@ -212,6 +262,29 @@ int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_tota
   sonar::philox_normal_moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(begin, end, s, (uint32_t)k_lo,
                                                                                        (uint32_t)k_hi, sums);
   SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_philox_normal_moments_batch(const uint64_t* offsets_host, int n_draws, int64_t begin, int64_t count,
+                                      int64_t numel_total, uint64_t seed, uint32_t grid_blocks, double* sums,
+                                      void* stream) {
+  using namespace sonar;
+  if (n_draws <= 0 || count <= 0) return 0;
+  if (offsets_host == nullptr || sums == nullptr || grid_blocks == 0 || begin < 0 || begin + count > numel_total)
+    return (int)cudaErrorInvalidValue;
+  PhiloxStream s{seed, 0, grid_blocks * (uint32_t)kBlock};
+  const int64_t T = s.threads, end = begin + count;
+  const int64_t k_lo = (begin / T) / 4, k_hi = ((end - 1) / T) / 4;
+  SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double) * (size_t)n_draws, (cudaStream_t)stream));
+  const int gx = streaming_grid(T, kBlock, 1);
+  for (int first = 0; first < n_draws; first += kMomentsBatch) {
+    const int m = n_draws - first < kMomentsBatch ? n_draws - first : kMomentsBatch;
+    OffsetBatch offs;
+    for (int i = 0; i < kMomentsBatch; ++i) offs.offset[i] = offsets_host[first + (i < m ? i : 0)];
+    philox_normal_moments_batch_kernel<<<dim3((unsigned)gx, (unsigned)m), kBlock, 0, (cudaStream_t)stream>>>(
+        begin, end, s, offs, (uint32_t)k_lo, (uint32_t)k_hi, sums + 2 * first);
+    SONAR_LAUNCH_CHECK();
+  }
   return 0;
 }
 

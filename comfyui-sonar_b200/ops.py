@@ -227,21 +227,21 @@ def philox_normal_fill_moments(draw: PhiloxDraw, out: torch.Tensor, sums: torch.
     return out
 
 
-_SINGLE_LAUNCH_CACHE: dict[tuple[int, int], bool] = {}
-
-
-def step_single_launch_ok(numel: int, grid_blocks: int) -> bool:
-    key = (int(numel), int(grid_blocks))
-    hit = _SINGLE_LAUNCH_CACHE.get(key)
-    if hit is None:
-        hit = _SINGLE_LAUNCH_CACHE[key] = bool(_native.load().sonar_step_single_launch_ok(*key))
-    return hit
-
-
-def enable_cooperative_step(enable: bool) -> None:
-    """Opt in/out of the single cooperative launch for small fused steps (default: off)."""
-    _native.load().sonar_step_enable_cooperative(int(enable))
-    _SINGLE_LAUNCH_CACHE.clear()
+def philox_normal_moments_batch(
+    draw: PhiloxDraw, offsets: Sequence[int], *, begin: int, count: int, device: torch.device,
+) -> torch.Tensor:
+    """(len(offsets), 2) float64 = (sum, sum^2) of elements [begin, begin+count) of the normal draws
+    that share `draw`'s seed / geometry and start at the given generator offsets. One launch (per 64
+    draws): the statistics of every remaining ancestral-noise draw of a sampler run."""
+    sums = torch.empty((len(offsets), 2), device=device, dtype=torch.float64)
+    lib, stream = _prepare(sums)
+    arr = (ctypes.c_uint64 * len(offsets))(*offsets)
+    _launch(
+        "sonar_philox_normal_moments_batch", lib.sonar_philox_normal_moments_batch,
+        arr, len(offsets), begin, count, draw.numel, draw.seed, draw.grid_blocks, _ptr(sums), stream,
+        launches=(len(offsets) + 63) // 64,
+    )  # fmt: skip
+    return sums
 
 
 def scale_noise_apply(

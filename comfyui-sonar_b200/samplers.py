@@ -6,6 +6,13 @@ function signatures and callback payloads (:483-526, :576-623, :773-820), same r
 (`add_samplers`, :823-847). The per-step tensor arithmetic -- ~15 full-tensor ATen passes and 4 host
 syncs per Euler-ancestral step upstream -- is ONE launch of `sonar_step_f32` per model evaluation.
 
+Default (Gaussian) ancestral noise never exists in HBM: the step kernel regenerates the values
+torch.randn(device='cuda') would have drawn from the Philox stream, in registers. The global
+mean / std that scale_noise needs (py/utils.py:100-106) depend only on (seed, generator offset), and
+the offsets of all remaining draws of a run are known at the first one, so their moments are
+reduced in ONE batched launch up front (`SonarBase._lookahead_sums`); each draw re-checks the
+generator offset and re-plans if somebody else consumed random numbers in between.
+
 Scalar schedule math (ancestral split, DPM-Solver++ log-sigma arithmetic) is evaluated once per step
 on a CPU float32 mirror of `sigmas` with the reference's own op sequence, so the coefficients handed
 to the kernel are the float32 values the reference computes and no step waits on the device.
@@ -24,7 +31,6 @@ from tqdm.auto import trange
 
 from . import hostutil, noise_graph as noise, ops, parallel
 from ._native import SonarStepParams
-from .kdiff import get_ancestral_step
 
 
 class HistoryType(Enum):
@@ -80,6 +86,9 @@ class SonarConfig(NamedTuple):
         return val if val is not None else default
 
 
+LOOKAHEAD_MAX_DRAWS = 256  # statistics of at most this many future noise draws per batched launch
+
+
 class SonarBase:
     """Momentum state + the fused step launcher (reference SonarBase, py/sonar.py:70-320)."""
 
@@ -96,7 +105,10 @@ class SonarBase:
         self.history_blend = hostutil.BLENDING_MODES[cfg.get_with_default("history_blend_mode", base)]
         self.guidance_blend = hostutil.BLENDING_MODES[cfg.get_with_default("guidance_blend_mode", base)]
         self._hist_pending_init: tuple[Tensor, float] | None = None
-        self._sums_parity = 0
+        # look-ahead statistics of the fused Gaussian noise draws (see _lookahead_sums)
+        self._lookahead: dict | None = None
+        self._lookahead_cap = LOOKAHEAD_MAX_DRAWS
+        self.noise_draws_left = 1  # samplers set this to the number of ancestral draws of the run
 
     _cfg_fixups = (
         ("momentum_mode", MomentumMode),
@@ -264,7 +276,7 @@ class SonarBase:
         p.sigma, p.c0, p.c1 = sigma, c0, c1
         p.hist_in_div = hist_div
         p.noise_scale = noise_scale
-        p.noise_kind, p.noise, p.noise_sums, p.sums_scratch, p.peer_world = ops.NOISE_NONE, 0, 0, 0, 0
+        p.noise_kind, p.noise, p.noise_sums, p.peer_world = ops.NOISE_NONE, 0, 0, 0
         keep = None
         if noise_philox is not None:
             draw = noise_philox["draw"]
@@ -272,28 +284,16 @@ class SonarBase:
             p.noise_factor = noise_philox["factor"]
             p.philox_seed, p.philox_offset, p.philox_grid_blocks = draw.seed, draw.offset, draw.grid_blocks
             p.noise_begin, p.noise_numel_total = noise_philox["begin"], draw.numel
-            keep = noise_philox.get("sums")
-            if keep is not None:  # materialised raw normals + device-resident (possibly all-reduced) sums
-                raw = noise_philox["tensor"]
-                p.noise_kind, p.noise = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr()
-                p.noise_sums, p.noise_count = keep.data_ptr(), noise_philox["count"]
-                keep = (keep, raw)
-            elif noise_philox["normalized"]:
-                # un-sharded: one C-ABI call materialises the normals + moments and runs the step
-                keep = self._sums_scratch(x.device)
-                p.sums_scratch, p.sums_parity = keep.data_ptr(), self._sums_parity
-                self._sums_parity ^= 1
-                p.noise_count = x.numel()
-                p.noise = self._noise_scratch(x).data_ptr()
-                peers = noise_philox.get("peers")
-                if peers is not None:
-                    p.noise_count = noise_philox["count"]
-                    p.peer_world, p.peer_rank = peers.world_size, peers.rank
-                    p.peer_mailbox, p.peer_epoch = peers.local, noise_philox["epoch"]
-                    if not getattr(self, "_peer_targets_set", False):
-                        for r in range(peers.world_size):
-                            p.peer_targets[r] = peers.mapped[r]
-                        self._peer_targets_set = True
+            if noise_philox["normalized"]:
+                raw = noise_philox.get("tensor")
+                if raw is not None:  # materialised raw normals, normalised on load from device sums
+                    keep = (noise_philox["sums"], raw)
+                    p.noise_kind, p.noise = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr()
+                    p.noise_sums = keep[0].data_ptr()
+                else:  # regenerated in registers; sums reduced ahead of time (look-ahead batch)
+                    keep = noise_philox["sums"]
+                    p.noise_sums = noise_philox["sums_ptr"]
+                p.noise_count = noise_philox["count"]
         elif noise_tensor is not None:
             if noise_tensor.dtype != torch.float32 or not noise_tensor.is_contiguous():
                 noise_tensor = noise_tensor.to(torch.float32).contiguous()
@@ -304,19 +304,31 @@ class SonarBase:
             self.history_d = hist_out
         return x_out
 
-    def _noise_scratch(self, x: Tensor) -> Tensor:
-        """n-float scratch for the materialised normals, reused by every step of this sampler."""
-        buf = getattr(self, "_noise_buf", None)
-        if buf is None or buf.shape != x.shape or buf.device != x.device:
-            buf = self._noise_buf = torch.empty_like(x)
-        return buf
+    def _lookahead_sums(self, draw: ops.PhiloxDraw, begin: int, count: int, device) -> tuple[Tensor, int]:
+        """Device (sum, sum^2) of the whole (global) normal draw `draw`, as (keep-alive tensor, pointer).
 
-    def _sums_scratch(self, device) -> Tensor:
-        buf = getattr(self, "_sums_buf", None)
-        if buf is None or buf.device != device:
-            buf = self._sums_buf = torch.zeros(4, device=device, dtype=torch.float64)
-            self._sums_parity = 0
-        return buf
+        First request of a run: ONE batched launch reduces the moments of this rank's slice of this
+        draw and of the next `noise_draws_left - 1` draws (their offsets follow from the generator's
+        fixed increment per draw), plus one all-reduce of the (K, 2) table when the batch is sharded.
+        Later requests look their offset up. A miss means another consumer advanced the generator
+        in between: re-plan from the current offset and stop looking more than one draw ahead."""
+        key = (draw.seed, draw.grid_blocks, draw.numel, begin, count, device)
+        la = self._lookahead
+        idx = None
+        if la is not None and la["key"] == key:
+            idx = la["index"].get(draw.offset)
+            if idx is None:
+                self._lookahead_cap = 1
+        if idx is None:
+            k = max(1, min(self.noise_draws_left, self._lookahead_cap))
+            offsets = [draw.offset + j * draw.counter_offset for j in range(k)]
+            sums = ops.philox_normal_moments_batch(draw, offsets, begin=begin, count=count, device=device)
+            parallel.global_count(count, sums)  # sharded: all-reduce the partial sums, once per table
+            la = self._lookahead = {
+                "key": key, "index": {o: j for j, o in enumerate(offsets)}, "sums": sums, "ptr": sums.data_ptr(),
+            }  # fmt: skip
+            idx = 0
+        return la["sums"], la["ptr"] + 16 * idx
 
     def prime_history(self, step: int, x: Tensor, denoised: Tensor, sigma: float) -> None:
         """Performs the (possibly random) history initialisation of this step NOW. The reference draws
@@ -343,17 +355,10 @@ class SonarBase:
             total, begin = parallel.global_draw_geometry(x.shape) if sharded else (x.numel(), 0)
             draw = ops.reserve_draw(total, x.device)
             kw = {"draw": draw, "factor": factor, "normalized": normalized, "begin": begin}
-            if normalized and sharded:
-                ctx = parallel.active()
-                if ctx.peers is not None:
-                    # one C-ABI call: materialise + moments of this rank's slice, NVLink stores of the two
-                    # partial sums into every rank's mailbox, step kernel waits for them on the device
-                    kw |= {"peers": ctx.peers, "epoch": ctx.peers.next_epoch(), "count": total}
-                else:  # no peer memory: NCCL all-reduce of the two doubles between two calls
-                    raw = self._noise_scratch(x)
-                    sums = torch.empty(2, device=x.device, dtype=torch.float64)
-                    ops.philox_normal_fill_moments(draw, raw, sums, begin=begin)
-                    kw |= {"tensor": raw, "sums": sums, "count": parallel.global_count(x.numel(), sums)}
+            if normalized:
+                sums, ptr = self._lookahead_sums(draw, begin, x.numel(), x.device)
+                kw |= {"sums": sums, "sums_ptr": ptr, "count": total}
+            self.noise_draws_left -= 1
             return {"noise_philox": kw, "noise_scale": scale}
         return {"noise_tensor": self.noise_sampler(sigma, sigma_next), "noise_scale": scale}
 
@@ -444,6 +449,14 @@ class SonarSampler(SonarWithGuidance):
         self.extra_args = extra_args
         # one device->host copy of the schedule for the whole run; per-step scalars come from here
         self.sigmas_host = sigmas.detach().to(dtype=torch.float32, device="cpu")
+        self.sigma_views = sigmas.unbind(0)  # 0-d views made once: no per-step indexing op
+        self.noise_draws_left = self.count_noise_draws()
+
+    NOISE_DRAWS_PER_STEP = 0
+
+    def count_noise_draws(self) -> int:
+        """Ancestral noise draws of the whole run (sizes the look-ahead statistics batch)."""
+        return self.NOISE_DRAWS_PER_STEP * int((self.sigmas_host[1:] > 0).sum())
 
     def call_model(self, x: Tensor, sigma: Tensor, *args, s_in=None, extra_args=None) -> Tensor:
         s_in = self.s_in if s_in is None else s_in
@@ -455,7 +468,7 @@ class SonarSampler(SonarWithGuidance):
         for i in trange(len(sigmas) - 1, disable=disable):
             x, sigma, sigma_hat, denoised = self.step(i, x)
             if callback is not None:
-                callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "denoised": denoised})
+                callback({"x": x, "i": i, "sigma": self.sigma_views[i], "sigma_hat": sigma_hat, "denoised": denoised})
         return x
 
     @classmethod
@@ -488,7 +501,7 @@ class SonarEuler(SonarSampler):
         return sched
 
     def step(self, step_index: int, sample: Tensor):
-        sigma = self.sigmas[step_index]
+        sigma = self.sigma_views[step_index]
         sigma_f, sigma_next_f, dt = self.schedule()[step_index]
         denoised = self.call_model(sample, sigma)
         result = self.momentum_step(step_index, sample, denoised, sigma_f, sigma_next_f, dt=dt)
@@ -514,6 +527,8 @@ class SonarEuler(SonarSampler):
 
 
 class SonarEulerAncestral(SonarSampler):
+    NOISE_DRAWS_PER_STEP = 1
+
     def __init__(self, eta: float = 1.0, s_noise: float = 1.0, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.eta = eta
@@ -534,7 +549,7 @@ class SonarEulerAncestral(SonarSampler):
         return sched
 
     def step(self, step_index: int, sample: Tensor):
-        sigma = self.sigmas[step_index]
+        sigma = self.sigma_views[step_index]
         sigma_f, sigma_next_f, sigma_down_f, dt, noise_scale = self.schedule()[step_index]
         denoised = self.call_model(sample, sigma)
         noise_kw = {}
@@ -576,6 +591,7 @@ class SonarDPMPPSDE(SonarSampler):
     evaluations and two fused launches per step, four history updates."""
 
     DEFAULT_NOISE_TYPE = noise.NoiseType.BROWNIAN
+    NOISE_DRAWS_PER_STEP = 2
 
     def __init__(self, eta: float = 1.0, s_noise: float = 1.0, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -627,41 +643,7 @@ class SonarDPMPPSDE(SonarSampler):
                 row = {k: v[i] for k, v in cols.items()}
                 row |= {"last": False, "s_t": s_t[i], "s_s": s_s[i], "s_t_next": s_t_next[i]}
                 sched.append(row)
-        self._sigma_mid_dev = s_s.to(self.sigmas.device, non_blocking=True)
-        return sched
-        sched = self._schedule = []
-        sh = self.sigmas_host
-        mids = []
-        for i in range(len(sh) - 1):
-            sigma, sigma_next = sh[i], sh[i + 1]
-            if sigma_next == 0:
-                sigma_down, _ = get_ancestral_step(sigma, sigma_next, eta=self.eta)
-                sigma_down = torch.as_tensor(sigma_down, dtype=torch.float32)
-                sched.append({"last": True, "sigma": float(sigma), "sigma_down": float(sigma_down), "dt": float(sigma_down - sigma)})
-                mids.append(torch.zeros(()))
-                continue
-            r = 1 / 2
-            t, t_next = self.t_fn(sigma), self.t_fn(sigma_next)
-            h = t_next - t
-            s = t + h * r
-            s_t, s_s = self.sigma_fn(t), self.sigma_fn(s)
-            sd, su = get_ancestral_step(s_t, s_s, self.eta)
-            s_ = self.t_fn(torch.as_tensor(sd))
-            s_t_next = self.sigma_fn(t_next)
-            sd2, su2 = get_ancestral_step(s_t, s_t_next, self.eta)
-            t_down = self.t_fn(torch.as_tensor(sd2))
-            sched.append(
-                {
-                    "last": False,
-                    "sigma": float(sigma),
-                    "s_t": s_t, "s_s": s_s, "s_t_next": s_t_next,
-                    "sigma_2": float(s_s),
-                    "c0_1": float((t - s_).expm1()), "c1_1": float(self.sigma_fn(s_) / s_t), "ns_1": float(self.s_noise * su),
-                    "c0_2": float((t - t_down).expm1()), "c1_2": float(self.sigma_fn(t_down) / s_t), "ns_2": float(self.s_noise * su2),
-                },  # fmt: skip
-            )
-            mids.append(s_s)
-        self._sigma_mid_dev = torch.stack(mids).to(self.sigmas.device, non_blocking=True)
+        self._sigma_mid_dev = s_s.to(self.sigmas.device, non_blocking=True).unbind(0)
         return sched
 
     def dpm_step(self, step_index: int, x: Tensor, denoised: Tensor, sc: dict) -> Tensor:
@@ -681,7 +663,7 @@ class SonarDPMPPSDE(SonarSampler):
         return self.fused_step(step_index, x, denoised_2, sc["sigma_2"], kind=ops.STEP_DPMPP, c0=sc["c0_2"], c1=sc["c1_2"], **noise_kw)
 
     def step(self, step_index: int, sample: Tensor):
-        sigma = self.sigmas[step_index]
+        sigma = self.sigma_views[step_index]
         sc = self.schedule()[step_index]
         denoised = self.call_model(sample, sigma)
         if sc["last"]:

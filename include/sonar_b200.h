@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 1
+#define SONAR_B200_ABI_VERSION 2
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
@@ -60,6 +60,14 @@ int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t n
 int sonar_moments_f32(const float* x, int64_t n, double* sums, void* stream);
 int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_total, uint64_t seed, uint64_t offset,
                                 uint32_t grid_blocks, double* sums, void* stream);
+/* Moments of n_draws draws of the same geometry (same seed / grid_blocks / slice), one launch:
+ * sums[2*i], sums[2*i+1] are OVERWRITTEN with the sum and the sum of squares of the slice of the draw
+ * whose generator offset is offsets_host[i]. A sampler calls this once, at its first noise request,
+ * for the ancestral-noise draws of ALL its remaining steps (their offsets are known in advance), so
+ * that each step is a single sonar_step_f32 launch with SONAR_NOISE_PHILOX_NORMALIZED. */
+int sonar_philox_normal_moments_batch(const uint64_t* offsets_host, int n_draws, int64_t begin, int64_t count,
+                                      int64_t numel_total, uint64_t seed, uint32_t grid_blocks, double* sums,
+                                      void* stream);
 /* materialise the slice AND write (not accumulate) its moments into sums, one pass */
 int sonar_philox_normal_fill_moments_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
                                          uint64_t offset, uint32_t grid_blocks, double* sums, void* stream);
@@ -88,7 +96,7 @@ enum {
   SONAR_NOISE_NONE = 0,
   SONAR_NOISE_TENSOR = 1,            /* noise read from `noise` */
   SONAR_NOISE_PHILOX = 2,            /* torch.randn(device='cuda') regenerated in registers */
-  SONAR_NOISE_PHILOX_NORMALIZED = 3, /* ... followed by scale_noise from `noise_sums` */
+  SONAR_NOISE_PHILOX_NORMALIZED = 3, /* ... followed by scale_noise decided from `noise_sums` */
   SONAR_NOISE_TENSOR_NORMALIZED = 4  /* raw Gaussian in `noise`, scale_noise applied on load from `noise_sums` */
 };
 
@@ -128,35 +136,20 @@ typedef struct SonarStepParams {
   uint32_t philox_grid_blocks;
   int64_t noise_begin;
   int64_t noise_numel_total;
-  const double* noise_sums; /* double[2], PHILOX_NORMALIZED: externally reduced sums (batch-sharded
-                               runs all-reduce them); NULL = let this call do the moments pre-pass */
-  int64_t noise_count;      /* global count behind noise_sums */
-  /* noise_sums == NULL: double[4] scratch (two ping-pong slots, zeroed ONCE by the caller) + which
-   * slot this launch uses. The call then performs "materialise the normals into `noise` (n-float
-   * scratch) + moments" and the step in two launches; with the cooperative path enabled and a small
-   * tensor, a single launch (moments -> grid barrier -> step, normals kept in registers). */
-  double* sums_scratch;
-  int32_t sums_parity;
-  /* batch-sharded statistics over peer memory (see sonar_peer_*): when peer_world > 1 the kernel
-   * waits until all peer_world partial sums of `peer_epoch` have landed in the LOCAL mailbox
-   * `peer_mailbox` and normalises with their total (noise_sums is ignored). */
+  /* double[2] = {sum, sum of squares} of the WHOLE noise tensor (all ranks), device resident:
+   * PHILOX_NORMALIZED: reduced ahead of time by sonar_philox_normal_moments_batch (and all-reduced
+   * when the batch is sharded); TENSOR_NORMALIZED: reduced by the producer of `noise`. */
+  const double* noise_sums;
+  int64_t noise_count; /* global element count behind noise_sums */
+  /* TENSOR_NORMALIZED with batch-sharded statistics over peer memory (see sonar_peer_*): when
+   * peer_world > 1 the kernel waits until all peer_world partial sums of `peer_epoch` have landed in
+   * the LOCAL mailbox `peer_mailbox` and normalises with their total (noise_sums is ignored). */
   int32_t peer_world;
   const double* peer_mailbox;
   double peer_epoch;
-  /* with noise_sums == NULL and peer_world > 1 the call also publishes this rank's partial sums:
-   * it needs every rank's mailbox as mapped here (sonar_peer_open_handle) and this rank's index */
-  int32_t peer_rank;
-  void* peer_targets[8];
 } SonarStepParams;
 
 int sonar_step_f32(const SonarStepParams* params_host, void* stream);
-/* 1 if a PHILOX_NORMALIZED step over n elements with noise_sums == NULL takes the single cooperative
- * launch (moments -> grid barrier -> step); callers with larger tensors materialise the noise with
- * sonar_philox_normal_fill_moments_f32 and use SONAR_NOISE_TENSOR_NORMALIZED instead. */
-int sonar_step_single_launch_ok(int64_t n, uint32_t philox_grid_blocks);
-/* The single cooperative launch is opt-in (env SONAR_B200_COOP=1 or this call): measured slower than
- * the two-launch path on B200 at the configured sizes (profiles/README.md). */
-int sonar_step_enable_cooperative(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * Pyramid family: fused multi-level resample-and-accumulate.

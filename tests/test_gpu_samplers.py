@@ -72,40 +72,47 @@ def test_momentum_one_is_plain_euler(sb, cuda):
 
 
 def test_fused_philox_noise_equals_tensor_noise(sb, cuda):
-    """The in-register Philox noise (stats pre-pass + fused step) equals drawing torch.randn on the
-    GPU, normalising it with scale_noise and adding it -- and advances torch's generator the same."""
+    """The in-register Philox noise (look-ahead statistics batch + one fused launch per step) equals
+    drawing torch.randn on the GPU, normalising it with scale_noise and adding it -- and advances
+    torch's generator the same."""
     torch.manual_seed(0)
     sigmas = torch.cat((torch.linspace(14.6, 0.03, 30), torch.zeros(1)))
     x0 = (torch.randn(8, 4, 128, 128) * sigmas[0]).to(cuda)
 
-    def run(force_tensor):
+    def run(force_tensor, model=stub_model):
         torch.manual_seed(77)
         ns = None
         if force_tensor:
             def ns(_s, _sn):
                 n = torch.randn(x0.shape, device=cuda)
                 return sb.hostutil.scale_noise(n, 1.0, normalized=True)
+        launches = sb.ops.LAUNCH_COUNT
         out = sb.samplers.SonarEulerAncestral.sampler(
-            stub_model, x0.clone(), sigmas.to(cuda), extra_args={"seed": 0}, disable=True, noise_sampler=ns,
+            model, x0.clone(), sigmas.to(cuda), extra_args={"seed": 0}, disable=True, noise_sampler=ns,
         )
-        return out, torch.cuda.default_generators[0].get_offset()
+        return out, torch.cuda.default_generators[0].get_offset(), sb.ops.LAUNCH_COUNT - launches
 
-    plain, off_b = run(True)
-    for coop in (False, True):  # two-launch path (default) and the opt-in single cooperative launch
-        sb.ops.enable_cooperative_step(coop)
-        try:
-            assert sb.ops.step_single_launch_ok(x0.numel(), sb.ops.philox_policy(x0.numel())[0]) == coop
-            fused, off_a = run(False)
-        finally:
-            sb.ops.enable_cooperative_step(False)
-        assert off_a == off_b
-        assert_close(fused, plain, what=f"fused (coop={coop}) vs tensor noise", rtol=1e-6, atol=1e-5)
+    plain, off_b, _ = run(True)
+    fused, off_a, launches = run(False)
+    assert off_a == off_b
+    assert launches == 30 + 1  # one fused launch per step + ONE statistics launch for all 29 draws
+    assert_close(fused, plain, what="fused vs tensor noise", rtol=1e-6, atol=1e-5)
+
+    # a denoiser that consumes random numbers itself invalidates the predicted generator offsets:
+    # the sampler must notice, re-plan, and still produce exactly the tensor-noise result
+    def noisy_model(x, sigma, **_kw):
+        return x * 0.9 + torch.randn(3, device=x.device).sum() * 0.0
+
+    plain, off_b, _ = run(True, noisy_model)
+    fused, off_a, launches = run(False, noisy_model)
+    assert off_a == off_b
+    assert launches > 30 + 1  # statistics were re-planned
+    assert_close(fused, plain, what="fused vs tensor noise, generator shared with the model", rtol=1e-6, atol=1e-5)
 
 
 def test_fused_noise_large_tensor_path(sb, cuda):
-    """Tensors too large for the single cooperative launch: noise materialised once with its
-    moments, normalised on load by the step kernel -- same values and generator advance as
-    torch.randn + scale_noise (config C5 per-GPU shard shape, DPM++ SDE)."""
+    """Config C5 per-GPU shard shape, DPM++ SDE (two noise draws per step, several Philox calls per
+    thread): same values and generator advance as torch.randn + scale_noise."""
     sigmas = torch.tensor([14.6, 6.0, 1.5, 0.0])
     torch.manual_seed(0)
     x0 = (torch.randn(1, 16, 33, 90, 160) * sigmas[0]).to(cuda)
