@@ -140,11 +140,29 @@ struct PhiloxStream {
   uint32_t threads;    // T = grid_blocks * 256 of the emulated ATen launch
 };
 
+// Philox4x32-10 (same rounds / constants as curand_Philox4x32_10, curand_philox4x32_x.h) written with
+// one 32x32->64 multiply per lane pair per round (IMAD.WIDE) instead of separate mulhi / mullo.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 __device__ __forceinline__ uint4 philox_raw(const PhiloxStream& s, uint32_t thread, uint64_t call) {
   const uint64_t c = (s.offset >> 2) + call;
-  uint4 ctr = make_uint4((uint32_t)c, (uint32_t)(c >> 32), thread, 0u);
-  uint2 key = make_uint2((uint32_t)s.seed, (uint32_t)(s.seed >> 32));
-  return curand_Philox4x32_10(ctr, key);
+  return philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), thread, 0u, (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
 }
 
 // curand_normal4 on the k-th block of thread `thread` (curand_normal.h: curand_box_muller4)

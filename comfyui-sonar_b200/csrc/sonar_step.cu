@@ -271,6 +271,41 @@ sonar_step_fast_vec_kernel(SonarStepParams p) {
 // of a (vt, k) pair are T elements apart, so consecutive threads touch consecutive addresses: every
 // access is a coalesced 128-byte warp transaction. All loads of a pair are issued before the Philox
 // rounds and the Box-Muller transform, which then run under the loads' latency.
+// FULL: all four lanes of the pair lie inside the slice (no per-lane predicates or index clamps).
+template <int KIND, bool NEW_MODE, bool HAVE_H, bool FULL>
+__device__ __forceinline__ void step_pair_fast(const SonarStepParams& p, const FastConsts& c, const NoiseNorm& nn,
+                                               const PhiloxStream& st, uint32_t vt, uint32_t k, int64_t li0, int64_t T,
+                                               int64_t begin, int64_t end) {
+  float xs[4], ds[4], hs[4];
+  bool ok[4];
+  int64_t idx[4];
+#pragma unroll
+  for (int lane = 0; lane < 4; ++lane) {
+    const int64_t li = li0 + T * lane;
+    ok[lane] = FULL || (li >= begin && li < end);
+    idx[lane] = ok[lane] ? li - begin : 0;
+    xs[lane] = __ldg(p.x + idx[lane]);
+    ds[lane] = __ldg(p.denoised + idx[lane]);
+    hs[lane] = HAVE_H ? p.hist_in[idx[lane]] : 0.0f;
+  }
+  float z[4];
+  if (FULL || ok[2] || ok[3]) {
+    const float4 z4 = philox_normal4(st, vt, k);
+    z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+  } else {  // lanes 2, 3 lie outside the slice: one Box-Muller is enough
+    const float2 z2 = philox_normal2_lo(st, vt, k);
+    z[0] = z2.x; z[1] = z2.y; z[2] = 0.0f; z[3] = 0.0f;
+  }
+#pragma unroll
+  for (int lane = 0; lane < 4; ++lane) {
+    if (!ok[lane]) continue;
+    const StepElem a =
+        step_element_fast<KIND, NEW_MODE, HAVE_H, true>(c, xs[lane], ds[lane], hs[lane], norm_noise_value(z[lane], nn));
+    p.x_out[idx[lane]] = a.x_out;
+    p.hist_out[idx[lane]] = a.h_out;
+  }
+}
+
 template <int KIND, bool NEW_MODE, bool HAVE_H>
 __global__ void __launch_bounds__(kBlock)
 sonar_step_fast_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint32_t k_hi) {
@@ -288,34 +323,10 @@ sonar_step_fast_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo,
       const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
       if (li0 >= end) break;
       if (li0 + 3 * T < begin) continue;
-      float xs[4], ds[4], hs[4];
-      bool ok[4];
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        const int64_t li = li0 + T * lane;
-        ok[lane] = li >= begin && li < end;
-        const int64_t i = ok[lane] ? li - begin : 0;
-        xs[lane] = ok[lane] ? __ldg(p.x + i) : 0.0f;
-        ds[lane] = ok[lane] ? __ldg(p.denoised + i) : 0.0f;
-        hs[lane] = (HAVE_H && ok[lane]) ? p.hist_in[i] : 0.0f;
-      }
-      float z[4];
-      if (ok[2] || ok[3]) {
-        const float4 z4 = philox_normal4(st, (uint32_t)vt, k);
-        z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
-      } else {  // lanes 2, 3 lie outside the slice: one Box-Muller is enough
-        const float2 z2 = philox_normal2_lo(st, (uint32_t)vt, k);
-        z[0] = z2.x; z[1] = z2.y; z[2] = 0.0f; z[3] = 0.0f;
-      }
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        if (!ok[lane]) continue;
-        const int64_t i = li0 + T * lane - begin;
-        const StepElem a =
-            step_element_fast<KIND, NEW_MODE, HAVE_H, true>(c, xs[lane], ds[lane], hs[lane], norm_noise_value(z[lane], nn));
-        p.x_out[i] = a.x_out;
-        p.hist_out[i] = a.h_out;
-      }
+      if (li0 >= begin && li0 + 3 * T < end)
+        step_pair_fast<KIND, NEW_MODE, HAVE_H, true>(p, c, nn, st, (uint32_t)vt, k, li0, T, begin, end);
+      else
+        step_pair_fast<KIND, NEW_MODE, HAVE_H, false>(p, c, nn, st, (uint32_t)vt, k, li0, T, begin, end);
     }
   }
 }

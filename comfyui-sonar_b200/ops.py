@@ -9,8 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from dataclasses import dataclass
-from typing import Sequence
+from typing import NamedTuple, Sequence
 
 import torch
 
@@ -92,8 +91,7 @@ def _f32(t: torch.Tensor, name: str) -> None:
 # --------------------------------------------------------------------------------------------
 # Philox draws
 # --------------------------------------------------------------------------------------------
-@dataclass(frozen=True)
-class PhiloxDraw:
+class PhiloxDraw(NamedTuple):
     """Identity of one torch-compatible CUDA draw: what torch.randn(numel) would have produced."""
 
     seed: int
@@ -118,24 +116,24 @@ def philox_policy(numel: int) -> tuple[int, int]:
 def reserve_draw(numel: int, device: torch.device, generator: torch.Generator | None = None) -> PhiloxDraw:
     """Consumes `numel` values from torch's CUDA generator exactly like an ATen distribution kernel
     would (same offset arithmetic), without launching anything."""
-    device = torch.device(device)
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("reserve_draw needs a CUDA device")
     idx = device.index if device.index is not None else torch.cuda.current_device()
     gen = generator if generator is not None else torch.cuda.default_generators[idx]
-    key = (idx, int(numel))
-    policy = _POLICY_CACHE.get(key)
+    policy = _POLICY_CACHE.get((idx, numel))
     if policy is None:
         with torch.cuda.device(idx):
             policy = philox_policy(numel)
         if len(_POLICY_CACHE) > 4096:
             _POLICY_CACHE.clear()
-        _POLICY_CACHE[key] = policy
+        _POLICY_CACHE[(idx, int(numel))] = policy
     grid, inc = policy
-    seed, offset = gen.initial_seed(), gen.get_offset()
+    offset = gen.get_offset()
     if numel > 0:
         gen.set_offset(offset + inc)
-    return PhiloxDraw(seed=seed, offset=offset, grid_blocks=grid, numel=int(numel), counter_offset=inc)
+    return PhiloxDraw(gen.initial_seed(), offset, grid, int(numel), inc)
 
 
 def philox_fill(
@@ -285,10 +283,39 @@ def add_moments(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, out: torch
 # --------------------------------------------------------------------------------------------
 # fused sonar step
 # --------------------------------------------------------------------------------------------
+_STEP_FN = None
+
+
+def launch_step(params_ref, device_index: int | None) -> None:
+    """sonar_step_f32 on torch's current stream of `device_index`. `params_ref` is ctypes.byref() of
+    a SonarStepParams whose pointers the caller has validated (float32, contiguous, that device).
+    The leanest path into the library: the sampler calls this once per model evaluation."""
+    global _STEP_FN, _LAST_DEVICE, LAUNCH_COUNT  # noqa: PLW0603
+    if _STEP_FN is None:
+        _STEP_FN = _native.load().sonar_step_f32
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    if device_index != _LAST_DEVICE:
+        _native.check(_native.load().sonar_set_device(device_index), "sonar_set_device")
+        _LAST_DEVICE = device_index
+    stream = ctypes.c_void_p(_raw_stream(device_index))
+    if TRACE is None:
+        code = _STEP_FN(params_ref, stream)
+    else:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        code = _STEP_FN(params_ref, stream)
+        end.record()
+        TRACE.append(("sonar_step_f32", start, end))
+    if code:
+        _native.check(code, "sonar_step_f32")
+    LAUNCH_COUNT += 1
+
+
 def sonar_step(params: SonarStepParams, *tensors: torch.Tensor | None) -> None:
     """Launches the fused step; `tensors` are the live tensors behind the pointers (validation)."""
-    lib, stream = _prepare(*tensors)
-    _launch("sonar_step_f32", lib.sonar_step_f32, ctypes.byref(params), stream)
+    _prepare(*tensors)
+    launch_step(ctypes.byref(params), next(t for t in tensors if t is not None).device.index)
 
 
 # --------------------------------------------------------------------------------------------
