@@ -85,6 +85,7 @@ class SonarPyramidParams(ctypes.Structure):
         ("n_levels", c_int32),
         ("mode", c_int32),
         ("base_scale", c_float),
+        ("sums", c_void_p),
     ]
 
 
@@ -100,6 +101,7 @@ class SonarPerlinParams(ctypes.Structure):
         ("iterations", c_int32),
         ("blend_mode", c_int32),
         ("div_fac", c_float),
+        ("sums", c_void_p),
     ]
 
 
@@ -114,6 +116,7 @@ class SonarSpectralParams(ctypes.Structure):
         ("H", c_int32),
         ("W", c_int32),
         ("out_scale", c_float),
+        ("sums", c_void_p),
     ]
 
 
@@ -189,7 +192,6 @@ SIGNATURES: dict[str, list] = {
         POINTER(c_uint64), c_int, c_int64, c_int64, c_int64, c_uint64, c_uint32, c_void_p, c_void_p,
     ],
     "sonar_scale_noise_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p],
-    "sonar_add_moments_f32": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "sonar_scale_by_std_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p],
     "sonar_affine_f32": [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p],
     "sonar_step_f32": [POINTER(SonarStepParams), c_void_p],
@@ -207,8 +209,8 @@ SIGNATURES: dict[str, list] = {
     "sonar_peer_publish_sums": [POINTER(c_void_p), c_int, c_int, c_void_p, c_double, c_void_p],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
-    "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p],
-    "sonar_axpby_f32": [c_void_p, c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p],
+    "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+    "sonar_axpby_f32": [c_void_p, c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_void_p],
     "sonar_composite_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
     "sonar_powerlaw_f32": [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p],
     "sonar_item_range_scratch_bytes": [c_int64],

@@ -126,6 +126,20 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
   }
 }
 
+// Producer kernels can reduce the moments of what they write (so scale_noise needs no separate read
+// pass): per-thread fp32 partials (s, ss) -> fp64 block sum -> two atomics per block into sums[0..1].
+// All threads of the block must call. sums == nullptr: nothing happens.
+__device__ __forceinline__ void commit_moments(double* __restrict__ sums, float s, float ss) {
+  if (sums == nullptr) return;  // launch-uniform
+  __shared__ double moments_scratch[64];
+  double ds = (double)s, dss = (double)ss;
+  block_sum2(ds, dss, moments_scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sums[0], ds);
+    atomicAdd(&sums[1], dss);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox, ATen-compatible random access
 //

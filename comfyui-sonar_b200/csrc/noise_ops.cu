@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kBlock)
 pyramid_accum_kernel(SonarPyramidParams p) {
   const int Wv = p.W / VEC;
   const int64_t total = p.planes * (int64_t)p.H * Wv;
+  float ms = 0.0f, mss = 0.0f;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int xv = (int)(idx % Wv);
@@ -113,12 +114,18 @@ pyramid_accum_kernel(SonarPyramidParams p) {
         acc[v] = acc[v] + __fmul_rn(s, wgt);
       }
     }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      ms += acc[v];
+      mss += acc[v] * acc[v];
+    }
     if (VEC == 4) {
       st4_stream(p.out + o, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
     } else {
       p.out[o] = acc[0];
     }
   }
+  commit_moments(p.sums, ms, mss);
 }
 
 // Table-driven variant (bilinear / nearest-exact): the x taps of every level depend only on x, so
@@ -152,6 +159,7 @@ pyramid_rows_kernel(SonarPyramidParams p) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t n_rows = p.planes * (int64_t)H;
+  float ms = 0.0f, mss = 0.0f;
   for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
        row += (int64_t)gridDim.x * warps_per_block) {
     const int y = (int)(row % H);
@@ -211,9 +219,14 @@ pyramid_rows_kernel(SonarPyramidParams p) {
       }
 #pragma unroll
       for (int v = 0; v < kRowUnroll; ++v)
-        if (ok[v]) p.out[obase + x0 + 32 * v] = acc[v];
+        if (ok[v]) {
+          p.out[obase + x0 + 32 * v] = acc[v];
+          ms += acc[v];
+          mss += acc[v] * acc[v];
+        }
     }
   }
+  commit_moments(p.sums, ms, mss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -243,6 +256,7 @@ __device__ __forceinline__ float perlin_value(const float* __restrict__ ang, int
 __global__ void __launch_bounds__(kBlock)
 perlin_accum_kernel(SonarPerlinParams p) {
   const int64_t chw = (int64_t)p.C * p.H * p.W;
+  float ms = 0.0f, mss = 0.0f;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chw;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(idx % p.W);
@@ -256,31 +270,90 @@ perlin_accum_kernel(SonarPerlinParams p) {
       float v = p.base != nullptr ? p.base[o] / p.div_fac : 0.0f;
       for (int it = 0; it < p.iterations; ++it) v += pv[it];
       p.out[o] = v;
+      ms += v;
+      mss += v * v;
     }
   }
+  commit_moments(p.sums, ms, mss);
 }
 
 // ---------------------------------------------------------------------------------------------
 // element-wise: blend, axpby, composite, power law
 // ---------------------------------------------------------------------------------------------
+// VEC = 4: float4 accesses (all pointers 16-byte aligned, n % 4 handled by a scalar tail)
+template <int VEC>
 __global__ void __launch_bounds__(kBlock)
 blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ t_tensor, float t_scalar,
-             float* __restrict__ out, int64_t n, int mode) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float t = t_tensor != nullptr ? t_tensor[i] : t_scalar;
-    out[i] = blend<float>(mode, a[i], b[i], t);
+             float* __restrict__ out, int64_t n, int mode, double* __restrict__ sums) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float ms = 0.0f, mss = 0.0f;
+  int64_t done = 0;
+  if (VEC == 4) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 va = ld4(a + 4 * i), vb = ld4(b + 4 * i);
+      const float4 vt = t_tensor != nullptr ? ld4(t_tensor + 4 * i) : make_float4(t_scalar, t_scalar, t_scalar, t_scalar);
+      float4 r;
+      r.x = blend<float>(mode, va.x, vb.x, vt.x);
+      r.y = blend<float>(mode, va.y, vb.y, vt.y);
+      r.z = blend<float>(mode, va.z, vb.z, vt.z);
+      r.w = blend<float>(mode, va.w, vb.w, vt.w);
+      st4(out + 4 * i, r);
+      ms += (r.x + r.y) + (r.z + r.w);
+      mss += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+    }
+    done = n4 << 2;
   }
+  for (int64_t i = done + tid; i < n; i += stride) {
+    const float t = t_tensor != nullptr ? t_tensor[i] : t_scalar;
+    const float r = blend<float>(mode, a[i], b[i], t);
+    out[i] = r;
+    ms += r;
+    mss += r * r;
+  }
+  commit_moments(sums, ms, mss);
 }
 
 // out = a * alpha + b * beta (b may be NULL)
+__device__ __forceinline__ float axpby_one(float a, float alpha, float b, float beta, bool has_b) {
+  float v = alpha == 1.0f ? a : a * alpha;
+  if (has_b) v = v + __fmul_rn(b, beta);
+  return v;
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(kBlock)
 axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta, float* __restrict__ out,
-             int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = alpha == 1.0f ? a[i] : a[i] * alpha;
-    if (b != nullptr) v = v + __fmul_rn(b[i], beta);
-    out[i] = v;
+             int64_t n, double* __restrict__ sums) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool has_b = b != nullptr;
+  float ms = 0.0f, mss = 0.0f;
+  int64_t done = 0;
+  if (VEC == 4) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 va = ld4(a + 4 * i);
+      const float4 vb = has_b ? ld4(b + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r;
+      r.x = axpby_one(va.x, alpha, vb.x, beta, has_b);
+      r.y = axpby_one(va.y, alpha, vb.y, beta, has_b);
+      r.z = axpby_one(va.z, alpha, vb.z, beta, has_b);
+      r.w = axpby_one(va.w, alpha, vb.w, beta, has_b);
+      st4(out + 4 * i, r);
+      ms += (r.x + r.y) + (r.z + r.w);
+      mss += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+    }
+    done = n4 << 2;
   }
+  for (int64_t i = done + tid; i < n; i += stride) {
+    const float r = axpby_one(a[i], alpha, has_b ? b[i] : 0.0f, beta, has_b);
+    out[i] = r;
+    ms += r;
+    mss += r * r;
+  }
+  commit_moments(sums, ms, mss);
 }
 
 // out = ((x + pre) * mul) + post with three separately rounded steps (sub_/mul_/add_ chains such as
@@ -400,6 +473,7 @@ int sonar_pyramid_accum_f32(const SonarPyramidParams* params, void* stream) {
   bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
   for (int l = 0; l < p.n_levels; ++l)
     if (p.level_h[l] == p.H && p.level_w[l] == p.W && !aligned16(p.levels[l])) vec = false;
+  if (p.sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(p.sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
   const size_t tab_bytes = (size_t)p.n_levels * p.W * 12;
   if (p.mode != SONAR_RESAMPLE_AREA && p.n_levels > 0 && tab_bytes <= 96 * 1024) {
     // table-driven row kernel; one warp per row, grid sized to whole waves
@@ -428,6 +502,7 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
   if (p.iterations < 0 || p.iterations > SONAR_PERLIN_MAX_ITERS || p.out == nullptr) return (int)cudaErrorInvalidValue;
   for (int i = 0; i < p.iterations; ++i)
     if (p.angles[i] == nullptr) return (int)cudaErrorInvalidValue;
+  if (p.sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(p.sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
   const int grid = streaming_grid((int64_t)p.C * p.H * p.W, kBlock, 4);
   perlin_accum_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(p);
   SONAR_LAUNCH_CHECK();
@@ -435,18 +510,31 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
 }
 
 int sonar_blend_f32(const float* a, const float* b, const float* t_tensor, float t_scalar, float* out, int64_t n,
-                    int mode, void* stream) {
+                    int mode, double* sums, void* stream) {
+  using namespace sonar;
   if (n <= 0) return 0;
-  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
-  sonar::blend_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode);
+  if (sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
+  const bool vec = aligned16(a) && aligned16(b) && aligned16(out) && (t_tensor == nullptr || aligned16(t_tensor));
+  const int grid = streaming_grid(vec ? (n + 3) / 4 : n, kBlock, 2);
+  if (vec)
+    blend_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode, sums);
+  else
+    blend_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode, sums);
   SONAR_LAUNCH_CHECK();
   return 0;
 }
 
-int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, void* stream) {
+int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, double* sums,
+                    void* stream) {
+  using namespace sonar;
   if (n <= 0) return 0;
-  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
-  sonar::axpby_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n);
+  if (sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
+  const bool vec = aligned16(a) && aligned16(out) && (b == nullptr || aligned16(b));
+  const int grid = streaming_grid(vec ? (n + 3) / 4 : n, kBlock, 2);
+  if (vec)
+    axpby_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums);
+  else
+    axpby_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

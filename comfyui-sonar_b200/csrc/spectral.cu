@@ -208,6 +208,7 @@ spectral_plane_kernel(SpectralLaunch L) {
   }
   __syncthreads();
 
+  float ms = 0.0f, mss = 0.0f;  // moments of everything this thread writes
   for (int64_t plane = blockIdx.x; plane < p.planes; plane += gridDim.x) {
     // ---------------- phase A: fill S ----------------
     if (p.in_real != nullptr) {
@@ -291,13 +292,22 @@ spectral_plane_kernel(SpectralLaunch L) {
       const float2* z = warp_fft<true>(bufA, bufB, L.plan_w, tw_w, tab_w, lane);
       for (int x = lane; x < W; x += 32) {
         const float2 v = z[x];
-        dst[(int64_t)y * W + x] = v.x * p.out_scale;
-        if (pair) dst[(int64_t)(y + 1) * W + x] = v.y * p.out_scale;
+        const float o0 = v.x * p.out_scale;
+        dst[(int64_t)y * W + x] = o0;
+        ms += o0;
+        mss += o0 * o0;
+        if (pair) {
+          const float o1 = v.y * p.out_scale;
+          dst[(int64_t)(y + 1) * W + x] = o1;
+          ms += o1;
+          mss += o1 * o1;
+        }
       }
       __syncwarp();
     }
     __syncthreads();
   }
+  commit_moments(p.sums, ms, mss);
 }
 
 static bool make_plan(int n, FftPlan* plan) {
@@ -379,6 +389,7 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) 
   int grid = di.sm_count * per_sm;
   if (!L.spectrum_in_smem && p.scratch == nullptr) return (int)cudaErrorInvalidValue;
   if ((int64_t)grid > p.planes) grid = (int)p.planes;
+  if (p.sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(p.sums, 0, 2 * sizeof(double), (cudaStream_t)stream_));
   SONAR_CUDA_TRY(cudaFuncSetAttribute(spectral_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   spectral_plane_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream_>>>(L);
   SONAR_LAUNCH_CHECK();

@@ -219,25 +219,6 @@ scale_by_std_kernel(const float* __restrict__ x, float* __restrict__ out, int64_
     out[i] = x[i] * mult;
 }
 
-// out = (a [+ b]) and moments of the result in the same pass (chain accumulation, noise.py:189-194)
-__global__ void __launch_bounds__(kBlock)
-add_moments_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n,
-                   double* __restrict__ sums) {
-  __shared__ double scratch[64];
-  double s = 0.0, ss = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = a[i] + b[i];
-    out[i] = v;
-    s += (double)v;
-    ss += (double)v * (double)v;
-  }
-  block_sum2(s, ss, scratch);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sums[0], s);
-    atomicAdd(&sums[1], ss);
-  }
-}
-
 }  // namespace sonar
 
 extern "C" {
@@ -331,14 +312,6 @@ int sonar_scale_by_std_f32(const float* x, float* out, int64_t n, const double* 
   if (n <= 0) return 0;
   const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
   sonar::scale_by_std_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, sums, count, scale);
-  SONAR_LAUNCH_CHECK();
-  return 0;
-}
-
-int sonar_add_moments_f32(const float* a, const float* b, float* out, int64_t n, double* sums, void* stream) {
-  if (n <= 0) return 0;
-  const int grid = sonar::streaming_grid(n, sonar::kBlock, 2);
-  sonar::add_moments_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(a, b, out, n, sums);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

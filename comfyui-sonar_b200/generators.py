@@ -191,7 +191,7 @@ class FramesToChannelsNoiseGenerator(NoiseGenerator):
     def fix_output_frames(self, noise: torch.Tensor) -> torch.Tensor:
         if not self.frames:
             return noise
-        return noise.reshape(self.batch, self.channels, self.frames, self.height, self.width)
+        return ops.reshape_keep_sums(noise, (self.batch, self.channels, self.frames, self.height, self.width))
 
     def rand_like(self, *args, shape=None, **kwargs) -> torch.Tensor:
         noise = super().rand_like(*args, shape=shape, **kwargs)

@@ -76,7 +76,9 @@ def scale_noise(
         return scale_noise(work, factor, normalized=True, threshold_std_devs=threshold_std_devs).to(noise.dtype)
     if not noise.is_contiguous():
         noise = noise.contiguous()
-    sums = ops.moments(noise)
+    sums = ops.attached_sums(noise)  # reduced by the kernel that produced `noise`, if it is still fresh
+    if sums is None:
+        sums = ops.moments(noise)
     ctx = parallel.active()
     if ctx is not None and ctx.world_size > 1 and ctx.peers is not None:
         # partial sums travel as NVLink stores into every rank's mailbox; the apply kernel waits for them

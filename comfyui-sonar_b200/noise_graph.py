@@ -533,7 +533,7 @@ class CustomNoiseParametersNoise(_ChildHolder):
             if fixed_aspect:
                 noise = noise.flatten(start_dim=-spatdims)[..., : height * width]
             if noise.shape != orig_shape:
-                noise = noise.reshape(orig_shape)
+                noise = ops.reshape_keep_sums(noise, orig_shape)
             if noise.dtype != orig_dtype or noise.device != orig_device:
                 noise = noise.to(device=orig_device, dtype=orig_dtype)
             return scale_noise(noise, factor, normalized=normalize)

@@ -199,6 +199,52 @@ def new_sums(device: torch.device) -> torch.Tensor:
     return torch.zeros(2, device=device, dtype=torch.float64)
 
 
+# Producer kernels (spectral, pyramid, perlin, blend, axpby) reduce {sum, sum^2} of what they write in
+# the same launch. The double[2] slots come from a per-device ring (no allocation, no memset launch from
+# Python: the C entry point clears its slot in-stream) and travel with the output tensor as the
+# attribute `_sonar_sums = (slot, tensor._version)`: scale_noise uses them instead of a moments pass
+# as long as nobody has modified the tensor since (torch bumps _version on in-place ops; our own
+# in-place kernels call drop_sums).
+_SUMS_RING: dict = {}
+_SUMS_RING_SLOTS = 256
+
+
+def sums_slot(device: torch.device) -> torch.Tensor:
+    ring = _SUMS_RING.get(device)
+    if ring is None:
+        base = torch.zeros((_SUMS_RING_SLOTS, 2), device=device, dtype=torch.float64)
+        ring = _SUMS_RING[device] = [list(base.unbind(0)), 0]
+    slots, i = ring
+    ring[1] = (i + 1) % _SUMS_RING_SLOTS
+    return slots[i]
+
+
+def attach_sums(t: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
+    t._sonar_sums = (slot, t._version)  # noqa: SLF001
+    return t
+
+
+def attached_sums(t: torch.Tensor) -> torch.Tensor | None:
+    tag = getattr(t, "_sonar_sums", None)
+    if tag is None or tag[1] != t._version:  # noqa: SLF001
+        return None
+    return tag[0]
+
+
+def reshape_keep_sums(t: torch.Tensor, shape) -> torch.Tensor:
+    """t.reshape(shape); a view of the same elements keeps the producer's statistics."""
+    out = t.reshape(shape)
+    slot = attached_sums(t)
+    if slot is not None and out is not t and out.data_ptr() == t.data_ptr():
+        attach_sums(out, slot)
+    return out
+
+
+def drop_sums(t: torch.Tensor) -> None:
+    if getattr(t, "_sonar_sums", None) is not None:
+        t._sonar_sums = None  # noqa: SLF001
+
+
 def moments(x: torch.Tensor, sums: torch.Tensor | None = None) -> torch.Tensor:
     """Accumulates (sum, sum of squares) of x into the device double[2] `sums`."""
     _f32(x, "x")
@@ -255,6 +301,7 @@ def scale_noise_apply(
     _f32(x, "x")
     out = x if out is None else out
     lib, stream = _prepare(x, out, sums)
+    drop_sums(out)
     _launch("sonar_scale_noise_f32", lib.sonar_scale_noise_f32, _ptr(x), _ptr(out), x.numel(), _ptr(sums), int(count), float(factor), float(threshold_std_devs), stream)
     return out
 
@@ -263,21 +310,13 @@ def scale_noise_apply_peers(x: torch.Tensor, peers, epoch: float, count: int, fa
     """scale_noise whose global statistics arrive through the peer mailboxes (parallel.PeerExchange)."""
     _f32(x, "x")
     lib, stream = _prepare(x)
+    drop_sums(x)
     _launch(
         "sonar_scale_noise_peers_f32", lib.sonar_scale_noise_peers_f32,
         _ptr(x), _ptr(x), x.numel(), ctypes.c_void_p(peers.local), peers.world_size, float(epoch), int(count),
         float(factor), float(threshold_std_devs), stream,
     )  # fmt: skip
     return x
-
-
-def add_moments(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-    _f32(a, "a")
-    _f32(b, "b")
-    out = a if out is None else out
-    lib, stream = _prepare(a, b, out, sums)
-    _launch("sonar_add_moments_f32", lib.sonar_add_moments_f32, _ptr(a), _ptr(b), _ptr(out), a.numel(), _ptr(sums), stream)
-    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -325,17 +364,19 @@ def scale(x: torch.Tensor, factor: float) -> torch.Tensor:
     """x *= factor (in place) through the axpby kernel."""
     _f32(x, "x")
     lib, stream = _prepare(x)
-    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), stream)
+    drop_sums(x)
+    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), None, stream)
     return x
 
 
 def axpby(a: torch.Tensor, alpha: float, b: torch.Tensor | None, beta: float = 1.0, out: torch.Tensor | None = None):
-    """out = a * alpha + b * beta."""
+    """out = a * alpha + b * beta; the moments of `out` ride along (attached_sums)."""
     _f32(a, "a")
     out = torch.empty_like(a) if out is None else out
     lib, stream = _prepare(a, b, out)
-    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), stream)
-    return out
+    slot = sums_slot(out.device)
+    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), _ptr(slot), stream)
+    return attach_sums(out, slot)
 
 
 def affine(x: torch.Tensor, pre_add: float, mul: float, post_add: float, out: torch.Tensor | None = None):
@@ -343,6 +384,7 @@ def affine(x: torch.Tensor, pre_add: float, mul: float, post_add: float, out: to
     _f32(x, "x")
     out = x if out is None else out
     lib, stream = _prepare(x, out)
+    drop_sums(out)
     _launch("sonar_affine_f32", lib.sonar_affine_f32, _ptr(x), _ptr(out), x.numel(), float(pre_add), float(mul), float(post_add), stream)
     return out
 
@@ -351,6 +393,7 @@ def scale_by_std(x: torch.Tensor, sums: torch.Tensor, count: int, scale: float) 
     """x *= scale / std(x) (in place), std from device sums."""
     _f32(x, "x")
     lib, stream = _prepare(x, sums)
+    drop_sums(x)
     _launch("sonar_scale_by_std_f32", lib.sonar_scale_by_std_f32, _ptr(x), _ptr(x), x.numel(), _ptr(sums), int(count), float(scale), stream)
     return x
 
@@ -373,8 +416,9 @@ def blend(a: torch.Tensor, b: torch.Tensor, t, *, mode: str = "lerp", out: torch
         t_scalar = float(t)
     out = torch.empty_like(a) if out is None else out
     lib, stream = _prepare(a, b, t_tensor, out)
-    _launch("sonar_blend_f32", lib.sonar_blend_f32, _ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], stream)
-    return out
+    slot = sums_slot(out.device)
+    _launch("sonar_blend_f32", lib.sonar_blend_f32, _ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], _ptr(slot), stream)
+    return attach_sums(out, slot)
 
 
 def composite(dst: torch.Tensor, src: torch.Tensor, mask: torch.Tensor, out: torch.Tensor | None = None):
@@ -387,6 +431,7 @@ def composite(dst: torch.Tensor, src: torch.Tensor, mask: torch.Tensor, out: tor
         raise ValueError("composite: mask must have shape (batch, 1, H, W)")
     out = torch.empty_like(dst) if out is None else out
     lib, stream = _prepare(dst, src, mask, out)
+    drop_sums(out)
     _launch("sonar_composite_f32", lib.sonar_composite_f32, _ptr(dst), _ptr(src), _ptr(mask), _ptr(out), b, channels, hw, stream)
     return out
 
@@ -395,6 +440,7 @@ def powerlaw(x: torch.Tensor, alpha: float, *, use_sign: bool, out: torch.Tensor
     _f32(x, "x")
     out = torch.empty_like(x) if out is None else out
     lib, stream = _prepare(x, out)
+    drop_sums(out)
     _launch("sonar_powerlaw_f32", lib.sonar_powerlaw_f32, _ptr(x), _ptr(out), x.numel(), float(alpha), int(use_sign), stream)
     return out
 
@@ -410,6 +456,7 @@ def div_item_max(x: torch.Tensor, *, use_abs: bool = True) -> torch.Tensor:
     items = x.shape[0]
     scratch = _range_scratch(items, x.device)
     lib, stream = _prepare(x, scratch)
+    drop_sums(x)
     _launch("sonar_item_div_max_f32", lib.sonar_item_div_max_f32, _ptr(x), _ptr(x), items, x.numel() // items, int(use_abs), _ptr(scratch), stream, launches=2)
     return x
 
@@ -463,8 +510,10 @@ def pyramid_accumulate(
     p.planes, p.H, p.W = planes, H, W
     p.n_levels, p.mode, p.base_scale = len(levels), RESAMPLE_IDS[mode], float(base_scale)
     lib, stream = _prepare(out, base, *levels)
+    slot = sums_slot(out.device)
+    p.sums = slot.data_ptr()
     _launch("sonar_pyramid_accum_f32", lib.sonar_pyramid_accum_f32, ctypes.byref(p), stream)
-    return out
+    return attach_sums(out, slot)
 
 
 def resample(x: torch.Tensor, height: int, width: int, *, mode: str = "bilinear") -> torch.Tensor:
@@ -495,8 +544,10 @@ def perlin_accumulate(
     p.B, p.C, p.H, p.W = B, C, H, W
     p.iterations, p.blend_mode, p.div_fac = len(angles), BLEND_IDS[blend_mode], float(div_fac)
     lib, stream = _prepare(out, base, *angles)
+    slot = sums_slot(out.device)
+    p.sums = slot.data_ptr()
     _launch("sonar_perlin_accum_f32", lib.sonar_perlin_accum_f32, ctypes.byref(p), stream)
-    return out
+    return attach_sums(out, slot)
 
 
 # --------------------------------------------------------------------------------------------
@@ -553,8 +604,10 @@ def spectral_filter(
     p.mask = 0 if mask is None else mask.data_ptr()
     p.scratch = 0 if scratch is None else scratch.data_ptr()
     p.planes, p.H, p.W, p.out_scale = planes, H, W, float(out_scale)
+    slot = sums_slot(out.device)
+    p.sums = slot.data_ptr()
     _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
-    return out
+    return attach_sums(out, slot)
 
 
 # --------------------------------------------------------------------------------------------

@@ -73,7 +73,6 @@ int sonar_philox_normal_fill_moments_f32(float* out, int64_t begin, int64_t coun
                                          uint64_t offset, uint32_t grid_blocks, double* sums, void* stream);
 int sonar_scale_noise_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float factor,
                           float threshold_std_devs, void* stream);
-int sonar_add_moments_f32(const float* a, const float* b, float* out, int64_t n, double* sums, void* stream);
 /* out = x * (scale / unbiased_std) -- GreenTestNoiseGenerator.generate, py/noise_generation.py:703 */
 int sonar_scale_by_std_f32(const float* x, float* out, int64_t n, const double* sums, int64_t count, float scale,
                            void* stream);
@@ -177,6 +176,7 @@ typedef struct SonarPyramidParams {
   int32_t n_levels;
   int32_t mode; /* SONAR_RESAMPLE_* */
   float base_scale;
+  double* sums; /* optional double[2]: OVERWRITTEN with {sum, sum of squares} of `out` (same launch) */
 } SonarPyramidParams;
 
 int sonar_pyramid_accum_f32(const SonarPyramidParams* params_host, void* stream);
@@ -199,6 +199,7 @@ typedef struct SonarPerlinParams {
   int32_t iterations;
   int32_t blend_mode; /* SONAR_BLEND_* */
   float div_fac;
+  double* sums; /* optional double[2]: OVERWRITTEN with {sum, sum of squares} of `out` */
 } SonarPerlinParams;
 
 int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
@@ -214,11 +215,14 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
  * blend: out = mode(a, b, t) with t = t_tensor[i] if t_tensor else t_scalar. `out` may alias a or b.
  * axpby: out = a*alpha + b*beta (b may be NULL).
  * composite: out = dst*(1-mask) + src*mask, mask (batch,1,H,W) broadcast over channels.
+ * `sums` (blend, axpby; optional double[2]) is OVERWRITTEN with {sum, sum of squares} of `out`, reduced in the
+ * same launch: the producer of a tensor hands scale_noise its statistics, saving the separate read pass.
  * item_*: reductions over everything but the leading dim; scratch from sonar_item_range_scratch_bytes.
  * ---------------------------------------------------------------------------------------------- */
 int sonar_blend_f32(const float* a, const float* b, const float* t_tensor, float t_scalar, float* out, int64_t n,
-                    int mode, void* stream);
-int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, void* stream);
+                    int mode, double* sums, void* stream);
+int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, double* sums,
+                    void* stream);
 /* out = ((x + pre_add) * mul) + post_add, each step rounded (UniformNoiseGenerator.generate,
  * py/noise_generation.py:508-514) */
 int sonar_affine_f32(const float* x, float* out, int64_t n, float pre_add, float mul, float post_add, void* stream);
@@ -256,6 +260,7 @@ typedef struct SonarSpectralParams {
   int32_t H;
   int32_t W;
   float out_scale;
+  double* sums; /* optional double[2]: OVERWRITTEN with {sum, sum of squares} of `out` */
 } SonarSpectralParams;
 
 int64_t sonar_spectral_scratch_bytes(int H, int W);

@@ -232,3 +232,45 @@ def test_full_size_configs_vs_oracle(sb, cuda):
     with sb.rng.injected(pdraws):
         got = sb.noise_graph.get_noise_sampler("perlin", x, None, None, normalized=True)(None, None)
     assert_close(got, want, what="perlin C3")
+
+
+def test_producer_kernels_hand_over_their_moments(sb, cuda):
+    """blend / axpby / pyramid / perlin / spectral reduce {sum, sum^2} of their output in the same
+    launch; scale_noise uses them only while the tensor is unmodified."""
+    torch.manual_seed(4)
+    a, b = torch.randn(3, 4, 33, 40, device=cuda), torch.randn(3, 4, 33, 40, device=cuda)
+
+    def check(t, what):
+        slot = sb.ops.attached_sums(t)
+        assert slot is not None, f"{what}: no statistics attached"
+        d = t.double()
+        want = torch.stack((d.sum(), (d * d).sum()))
+        torch.testing.assert_close(slot, want, rtol=1e-6, atol=1e-4, msg=lambda m: f"{what}: {m}")
+
+    check(sb.ops.blend(a, b, 0.3), "blend")
+    check(sb.ops.axpby(a, 0.5, b, 2.0), "axpby")
+    check(sb.ops.axpby(a[..., 1:].contiguous().flatten()[1:], 1.0, None), "axpby unaligned")
+    levels = [torch.randn(12, 33, 40, device=cuda), torch.randn(12, 9, 11, device=cuda)]
+    check(sb.ops.pyramid_accumulate(a.reshape(12, 33, 40), levels, [1.0, 0.7], out_hw=(33, 40)), "pyramid")
+    angles = [torch.rand(4, 34, 41, device=cuda) * 6.28 for _ in range(2)]
+    check(sb.ops.perlin_accumulate(torch.rand(3, 4, 33, 40, device=cuda), angles, shape=(3, 4, 33, 40)), "perlin")
+    spec = torch.randn(5, 18, 11, dtype=torch.complex64, device=cuda)
+    check(sb.ops.spectral_filter(spectrum=spec, mask=None, hw=(18, 20), out_scale=1.0 / math.sqrt(360)), "spectral")
+
+    # scale_noise with handed-over statistics == scale_noise from scratch
+    t = sb.ops.blend(a * 1.5 + 0.2, b, 0.3)
+    want = orc.scale_noise(t.cpu().clone(), 1.0, normalized=True)
+    assert_close(sb.hostutil.scale_noise(t, 1.0, normalized=True), want, what="scale_noise with attached sums")
+    # a torch in-place op invalidates them (tensor version changes); so do our own in-place kernels
+    t = sb.ops.blend(a, b, 0.3)
+    t.mul_(3.0).add_(1.0)
+    assert sb.ops.attached_sums(t) is None
+    want = orc.scale_noise(t.cpu().clone(), 1.0, normalized=True)
+    assert_close(sb.hostutil.scale_noise(t, 1.0, normalized=True), want, what="scale_noise after in-place edit")
+    t = sb.ops.blend(a, b, 0.3)
+    sb.ops.scale(t, 2.0)
+    assert sb.ops.attached_sums(t) is None
+    # a view of the same elements keeps them
+    t = sb.ops.blend(a, b, 0.3)
+    v = sb.ops.reshape_keep_sums(t, (3, 4, 33 * 40))
+    assert sb.ops.attached_sums(v) is not None
