@@ -86,6 +86,7 @@ class SonarPyramidParams(ctypes.Structure):
         ("mode", c_int32),
         ("base_scale", c_float),
         ("sums", c_void_p),
+        ("sums_clear", c_void_p),
     ]
 
 
@@ -102,6 +103,7 @@ class SonarPerlinParams(ctypes.Structure):
         ("blend_mode", c_int32),
         ("div_fac", c_float),
         ("sums", c_void_p),
+        ("sums_clear", c_void_p),
     ]
 
 
@@ -117,6 +119,7 @@ class SonarSpectralParams(ctypes.Structure):
         ("W", c_int32),
         ("out_scale", c_float),
         ("sums", c_void_p),
+        ("sums_clear", c_void_p),
     ]
 
 
@@ -174,6 +177,31 @@ class SonarDwtSynthesisParams(ctypes.Structure):
     ]
 
 
+WCFG_MAX_LEVELS = 8
+
+
+class SonarWcfgFusedParams(ctypes.Structure):
+    _fields_ = [
+        ("in_a", c_void_p),
+        ("in_b", c_void_p),
+        ("out", c_void_p),
+        ("addend", c_void_p),
+        ("addend_scale", c_float),
+        ("x", c_void_p),
+        ("x_scale", c_float),
+        ("recon_sign", c_float),
+        ("planes", c_int64),
+        ("H", c_int32),
+        ("W", c_int32),
+        ("levels", c_int32),
+        ("mode", c_int32),
+        ("use_f64", c_int32),
+        ("scale_ll", c_double),
+        ("scale_hi", (c_double * 3) * WCFG_MAX_LEVELS),
+        ("filters", SonarWaveletFilters),
+    ]
+
+
 # name -> argtypes; every function returns int. Kept in one table so tests can check that the
 # library exports exactly what include/sonar_b200.h declares.
 SIGNATURES: dict[str, list] = {
@@ -209,8 +237,8 @@ SIGNATURES: dict[str, list] = {
     "sonar_peer_publish_sums": [POINTER(c_void_p), c_int, c_int, c_void_p, c_double, c_void_p],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
-    "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p],
-    "sonar_axpby_f32": [c_void_p, c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_void_p],
+    "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],
+    "sonar_axpby_f32": [c_void_p, c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "sonar_composite_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
     "sonar_powerlaw_f32": [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p],
     "sonar_item_range_scratch_bytes": [c_int64],
@@ -223,10 +251,12 @@ SIGNATURES: dict[str, list] = {
     "sonar_dwt_coeff_len": [c_int, c_int],
     "sonar_dwt2_analysis": [POINTER(SonarDwtAnalysisParams), c_void_p],
     "sonar_dwt2_synthesis": [POINTER(SonarDwtSynthesisParams), c_void_p],
+    "sonar_wcfg_fused_smem_bytes": [c_int, c_int, c_int, c_int, c_int],
+    "sonar_wcfg_fused": [POINTER(SonarWcfgFusedParams), c_void_p],
 }
 
 # functions whose return value is not an error code
-RESTYPES = {"sonar_spectral_scratch_bytes": c_int64}
+RESTYPES = {"sonar_spectral_scratch_bytes": c_int64, "sonar_wcfg_fused_smem_bytes": c_int64}
 
 _LIB: ctypes.CDLL | None = None
 
@@ -293,6 +323,7 @@ __all__ = [
     "SonarWaveletFilters",
     "SonarDwtAnalysisParams",
     "SonarDwtSynthesisParams",
+    "SonarWcfgFusedParams",
     "NativeLibraryError",
     "SonarStepParams",
     "check",

@@ -127,9 +127,11 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
 }
 
 // Producer kernels can reduce the moments of what they write (so scale_noise needs no separate read
-// pass): per-thread fp32 partials (s, ss) -> fp64 block sum -> two atomics per block into sums[0..1].
+// pass): per-thread fp32 partials (s, ss) -> fp64 block sum -> two atomics per block into sums[0..1],
+// which must be zero on entry. `clear` (optional) is ANOTHER double[2] that the launch zeroes: callers
+// recycle a ring of slots without a memset node per launch (slot i's producer clears slot i+1).
 // All threads of the block must call. sums == nullptr: nothing happens.
-__device__ __forceinline__ void commit_moments(double* __restrict__ sums, float s, float ss) {
+__device__ __forceinline__ void commit_moments(double* __restrict__ sums, double* __restrict__ clear, float s, float ss) {
   if (sums == nullptr) return;  // launch-uniform
   __shared__ double moments_scratch[64];
   double ds = (double)s, dss = (double)ss;
@@ -137,6 +139,10 @@ __device__ __forceinline__ void commit_moments(double* __restrict__ sums, float 
   if (threadIdx.x == 0) {
     atomicAdd(&sums[0], ds);
     atomicAdd(&sums[1], dss);
+    if (clear != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+      clear[0] = 0.0;
+      clear[1] = 0.0;
+    }
   }
 }
 

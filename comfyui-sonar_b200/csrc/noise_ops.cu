@@ -125,7 +125,7 @@ pyramid_accum_kernel(SonarPyramidParams p) {
       p.out[o] = acc[0];
     }
   }
-  commit_moments(p.sums, ms, mss);
+  commit_moments(p.sums, p.sums_clear, ms, mss);
 }
 
 // Table-driven variant (bilinear / nearest-exact): the x taps of every level depend only on x, so
@@ -226,7 +226,7 @@ pyramid_rows_kernel(SonarPyramidParams p) {
         }
     }
   }
-  commit_moments(p.sums, ms, mss);
+  commit_moments(p.sums, p.sums_clear, ms, mss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +274,7 @@ perlin_accum_kernel(SonarPerlinParams p) {
       mss += v * v;
     }
   }
-  commit_moments(p.sums, ms, mss);
+  commit_moments(p.sums, p.sums_clear, ms, mss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,7 +284,7 @@ perlin_accum_kernel(SonarPerlinParams p) {
 template <int VEC>
 __global__ void __launch_bounds__(kBlock)
 blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ t_tensor, float t_scalar,
-             float* __restrict__ out, int64_t n, int mode, double* __restrict__ sums) {
+             float* __restrict__ out, int64_t n, int mode, double* __restrict__ sums, double* __restrict__ sums_clear) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float ms = 0.0f, mss = 0.0f;
@@ -312,7 +312,7 @@ blend_kernel(const float* __restrict__ a, const float* __restrict__ b, const flo
     ms += r;
     mss += r * r;
   }
-  commit_moments(sums, ms, mss);
+  commit_moments(sums, sums_clear, ms, mss);
 }
 
 // out = a * alpha + b * beta (b may be NULL)
@@ -325,7 +325,7 @@ __device__ __forceinline__ float axpby_one(float a, float alpha, float b, float 
 template <int VEC>
 __global__ void __launch_bounds__(kBlock)
 axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta, float* __restrict__ out,
-             int64_t n, double* __restrict__ sums) {
+             int64_t n, double* __restrict__ sums, double* __restrict__ sums_clear) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool has_b = b != nullptr;
@@ -353,7 +353,7 @@ axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__
     ms += r;
     mss += r * r;
   }
-  commit_moments(sums, ms, mss);
+  commit_moments(sums, sums_clear, ms, mss);
 }
 
 // out = ((x + pre) * mul) + post with three separately rounded steps (sub_/mul_/add_ chains such as
@@ -473,7 +473,6 @@ int sonar_pyramid_accum_f32(const SonarPyramidParams* params, void* stream) {
   bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
   for (int l = 0; l < p.n_levels; ++l)
     if (p.level_h[l] == p.H && p.level_w[l] == p.W && !aligned16(p.levels[l])) vec = false;
-  if (p.sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(p.sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
   const size_t tab_bytes = (size_t)p.n_levels * p.W * 12;
   if (p.mode != SONAR_RESAMPLE_AREA && p.n_levels > 0 && tab_bytes <= 96 * 1024) {
     // table-driven row kernel; one warp per row, grid sized to whole waves
@@ -502,7 +501,6 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
   if (p.iterations < 0 || p.iterations > SONAR_PERLIN_MAX_ITERS || p.out == nullptr) return (int)cudaErrorInvalidValue;
   for (int i = 0; i < p.iterations; ++i)
     if (p.angles[i] == nullptr) return (int)cudaErrorInvalidValue;
-  if (p.sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(p.sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
   const int grid = streaming_grid((int64_t)p.C * p.H * p.W, kBlock, 4);
   perlin_accum_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(p);
   SONAR_LAUNCH_CHECK();
@@ -510,31 +508,29 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
 }
 
 int sonar_blend_f32(const float* a, const float* b, const float* t_tensor, float t_scalar, float* out, int64_t n,
-                    int mode, double* sums, void* stream) {
+                    int mode, double* sums, double* sums_clear, void* stream) {
   using namespace sonar;
   if (n <= 0) return 0;
-  if (sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
   const bool vec = aligned16(a) && aligned16(b) && aligned16(out) && (t_tensor == nullptr || aligned16(t_tensor));
   const int grid = streaming_grid(vec ? (n + 3) / 4 : n, kBlock, 2);
   if (vec)
-    blend_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode, sums);
+    blend_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode, sums, sums_clear);
   else
-    blend_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode, sums);
+    blend_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, b, t_tensor, t_scalar, out, n, mode, sums, sums_clear);
   SONAR_LAUNCH_CHECK();
   return 0;
 }
 
 int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, double* sums,
-                    void* stream) {
+                    double* sums_clear, void* stream) {
   using namespace sonar;
   if (n <= 0) return 0;
-  if (sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double), (cudaStream_t)stream));
   const bool vec = aligned16(a) && aligned16(out) && (b == nullptr || aligned16(b));
   const int grid = streaming_grid(vec ? (n + 3) / 4 : n, kBlock, 2);
   if (vec)
-    axpby_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums);
+    axpby_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums, sums_clear);
   else
-    axpby_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums);
+    axpby_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums, sums_clear);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

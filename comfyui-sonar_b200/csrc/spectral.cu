@@ -307,7 +307,7 @@ spectral_plane_kernel(SpectralLaunch L) {
     }
     __syncthreads();
   }
-  commit_moments(p.sums, ms, mss);
+  commit_moments(p.sums, p.sums_clear, ms, mss);
 }
 
 static bool make_plan(int n, FftPlan* plan) {
@@ -389,7 +389,6 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) 
   int grid = di.sm_count * per_sm;
   if (!L.spectrum_in_smem && p.scratch == nullptr) return (int)cudaErrorInvalidValue;
   if ((int64_t)grid > p.planes) grid = (int)p.planes;
-  if (p.sums != nullptr) SONAR_CUDA_TRY(cudaMemsetAsync(p.sums, 0, 2 * sizeof(double), (cudaStream_t)stream_));
   SONAR_CUDA_TRY(cudaFuncSetAttribute(spectral_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   spectral_plane_kernel<<<grid, kFftThreads, smem, (cudaStream_t)stream_>>>(L);
   SONAR_LAUNCH_CHECK();

@@ -56,6 +56,55 @@ struct Filters {
 // value(y, x) = in_a[y, x] - in_b[y, x] (in_b optional) so that level 1 can transform cond - uncond
 // straight from the fp32 inputs.
 // ---------------------------------------------------------------------------------------------
+// One output position (ky, kx) of an analysis level: the four sub-band coefficients of the
+// L x L window at (2ky - pad_t, 2kx - pad_l) of value = pa - pb (pb optional). Rows of the input are
+// `row_stride` elements apart (global planes: W; shared-memory buffers: their own pitch).
+template <typename T, typename Tin>
+__device__ __forceinline__ void analysis_point(const Tin* __restrict__ pa, const Tin* __restrict__ pb, int row_stride,
+                                               int H, int W, int ky, int kx, int pad_t, int pad_l, int mode,
+                                               const Filters<T>& f, T& acc_ll, T& acc_lh, T& acc_hl, T& acc_hh) {
+  const int L = f.L;
+  acc_ll = 0, acc_lh = 0, acc_hl = 0, acc_hh = 0;
+  const int x_first = 2 * kx - pad_l, y_first = 2 * ky - pad_t;
+  const bool interior = x_first >= 0 && x_first + L <= W && y_first >= 0 && y_first + L <= H;
+  if (interior) {  // the whole L x L window lies inside the plane: no boundary extension
+    for (int jy = 0; jy < L; ++jy) {
+      const Tin* ra = pa + (int64_t)(y_first + jy) * row_stride + x_first;
+      const Tin* rb = pb != nullptr ? pb + (int64_t)(y_first + jy) * row_stride + x_first : nullptr;
+      T row_lo = 0, row_hi = 0;
+      for (int jx = 0; jx < L; ++jx) {
+        T v = (T)ra[jx];
+        if (rb != nullptr) v -= (T)rb[jx];
+        row_lo += f.a_lo[jx] * v;
+        row_hi += f.a_hi[jx] * v;
+      }
+      acc_ll += f.a_lo[jy] * row_lo;
+      acc_lh += f.a_hi[jy] * row_lo;
+      acc_hl += f.a_lo[jy] * row_hi;
+      acc_hh += f.a_hi[jy] * row_hi;
+    }
+  } else {
+    for (int jy = 0; jy < L; ++jy) {
+      const int sy = extend_index(y_first + jy, H, mode);
+      if (sy < 0) continue;
+      T row_lo = 0, row_hi = 0;
+      for (int jx = 0; jx < L; ++jx) {
+        const int sx = extend_index(x_first + jx, W, mode);
+        if (sx < 0) continue;
+        const int64_t o = (int64_t)sy * row_stride + sx;
+        T v = (T)pa[o];
+        if (pb != nullptr) v -= (T)pb[o];
+        row_lo += f.a_lo[jx] * v;
+        row_hi += f.a_hi[jx] * v;
+      }
+      acc_ll += f.a_lo[jy] * row_lo;
+      acc_lh += f.a_hi[jy] * row_lo;  // high along H, low along W
+      acc_hl += f.a_lo[jy] * row_hi;  // low along H, high along W
+      acc_hh += f.a_hi[jy] * row_hi;
+    }
+  }
+}
+
 template <typename T, typename Tin>
 __global__ void __launch_bounds__(kBlock)
 dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, T* __restrict__ ll,
@@ -72,45 +121,8 @@ dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b,
     const int64_t plane = idx / ((int64_t)w * h);
     const Tin* pa = in_a + plane * (int64_t)in_stride_h * W;
     const Tin* pb = in_b != nullptr ? in_b + plane * (int64_t)in_stride_h * W : nullptr;
-    T acc_ll = 0, acc_lh = 0, acc_hl = 0, acc_hh = 0;
-    const int x_first = 2 * kx - pad_l, y_first = 2 * ky - pad_t;
-    const bool interior = x_first >= 0 && x_first + L <= W && y_first >= 0 && y_first + L <= H;
-    if (interior) {  // the whole L x L window lies inside the plane: no boundary extension
-      for (int jy = 0; jy < L; ++jy) {
-        const Tin* ra = pa + (int64_t)(y_first + jy) * W + x_first;
-        const Tin* rb = pb != nullptr ? pb + (int64_t)(y_first + jy) * W + x_first : nullptr;
-        T row_lo = 0, row_hi = 0;
-        for (int jx = 0; jx < L; ++jx) {
-          T v = (T)ra[jx];
-          if (rb != nullptr) v -= (T)rb[jx];
-          row_lo += f.a_lo[jx] * v;
-          row_hi += f.a_hi[jx] * v;
-        }
-        acc_ll += f.a_lo[jy] * row_lo;
-        acc_lh += f.a_hi[jy] * row_lo;
-        acc_hl += f.a_lo[jy] * row_hi;
-        acc_hh += f.a_hi[jy] * row_hi;
-      }
-    } else {
-      for (int jy = 0; jy < L; ++jy) {
-        const int sy = extend_index(y_first + jy, H, mode);
-        if (sy < 0) continue;
-        T row_lo = 0, row_hi = 0;
-        for (int jx = 0; jx < L; ++jx) {
-          const int sx = extend_index(x_first + jx, W, mode);
-          if (sx < 0) continue;
-          const int64_t o = (int64_t)sy * W + sx;
-          T v = (T)pa[o];
-          if (pb != nullptr) v -= (T)pb[o];
-          row_lo += f.a_lo[jx] * v;
-          row_hi += f.a_hi[jx] * v;
-        }
-        acc_ll += f.a_lo[jy] * row_lo;
-        acc_lh += f.a_hi[jy] * row_lo;  // high along H, low along W
-        acc_hl += f.a_lo[jy] * row_hi;  // low along H, high along W
-        acc_hh += f.a_hi[jy] * row_hi;
-      }
-    }
+    T acc_ll, acc_lh, acc_hl, acc_hh;
+    analysis_point<T, Tin>(pa, pb, W, H, W, ky, kx, pad_t, pad_l, mode, f, acc_ll, acc_lh, acc_hl, acc_hh);
     const int64_t hw = (int64_t)h * w;
     const int64_t o = (int64_t)ky * w + kx;
     ll[plane * hw + o] = acc_ll;
@@ -135,6 +147,43 @@ struct SynthSet {
   T s_ll, s_lh, s_hl, s_hh;
 };
 
+// Accumulates the contribution of one coefficient set to the 2x2 output quad (2qy+py, 2qx+px).
+// pll: approximation band with row pitch ll_pitch; phi: three detail bands, `band_stride` apart, row
+// pitch hi_pitch; (h, w) = valid coefficient extent.
+template <typename T>
+__device__ __forceinline__ void synthesis_quad(const T* __restrict__ pll, int ll_pitch, const T* __restrict__ phi,
+                                               int64_t band_stride, int hi_pitch, int h, int w, int qy, int qx, T s_ll,
+                                               T s_lh, T s_hl, T s_hh, const Filters<T>& f, T& o00, T& o01, T& o10,
+                                               T& o11) {
+  const int L = f.L, half = L >> 1;
+  for (int ia = 0; ia < half; ++ia) {
+    const int ky = qy + ia;
+    if (ky >= h) break;  // only reachable for the cropped-away overhang
+    T rl0 = 0, rl1 = 0, rh0 = 0, rh1 = 0;
+    for (int ib = 0; ib < half; ++ib) {
+      const int kx = qx + ib;
+      if (kx >= w) break;
+      const int tx = L - 2 - 2 * ib;
+      const T glx0 = f.s_lo[tx], glx1 = f.s_lo[tx + 1], ghx0 = f.s_hi[tx], ghx1 = f.s_hi[tx + 1];
+      const int64_t o = (int64_t)ky * hi_pitch + kx;
+      const T v_ll = pll[(int64_t)ky * ll_pitch + kx] * s_ll;
+      const T v_lh = phi[o] * s_lh;                    // high along H, low along W
+      const T v_hl = phi[band_stride + o] * s_hl;      // low along H, high along W
+      const T v_hh = phi[2 * band_stride + o] * s_hh;
+      rl0 += glx0 * v_ll + ghx0 * v_hl;
+      rl1 += glx1 * v_ll + ghx1 * v_hl;
+      rh0 += glx0 * v_lh + ghx0 * v_hh;
+      rh1 += glx1 * v_lh + ghx1 * v_hh;
+    }
+    const int ty = L - 2 - 2 * ia;
+    const T gly0 = f.s_lo[ty], gly1 = f.s_lo[ty + 1], ghy0 = f.s_hi[ty], ghy1 = f.s_hi[ty + 1];
+    o00 += gly0 * rl0 + ghy0 * rh0;
+    o01 += gly0 * rl1 + ghy0 * rh1;
+    o10 += gly1 * rl0 + ghy1 * rh0;
+    o11 += gly1 * rl1 + ghy1 * rh1;
+  }
+}
+
 // Polyphase form: the 2x2 output quad (2qy+py, 2qx+px) reads the SAME (L/2) x (L/2) window of
 // coefficients k = (qy + a, qx + b); tap index t = p + L - 2 - 2a. Every k of a quad is in range
 // (q <= n - L/2), so the loops carry no boundary tests; rows are combined along W first.
@@ -144,7 +193,6 @@ dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, 
                       T* __restrict__ out_t, float* __restrict__ out_f32, int crop_h, int crop_w,
                       const float* __restrict__ addend, float addend_scale, const float* __restrict__ x,
                       float x_scale, float recon_sign, Filters<T> f) {
-  const int L = f.L, half = L >> 1;
   const int oh = out_f32 != nullptr ? crop_h : out_h;
   const int ow = out_f32 != nullptr ? crop_w : out_w;
   const int qh = (oh + 1) >> 1, qw = (ow + 1) >> 1;
@@ -158,34 +206,8 @@ dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, 
     T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
     for (int s = 0; s < n_sets; ++s) {
       const SynthSet<T>& c = s == 0 ? a : b;
-      const T* pll = c.ll + plane * (int64_t)c.ll_stride_h * c.ll_stride_w;
-      const T* phi = c.hi + plane * 3 * hw;
-      for (int ia = 0; ia < half; ++ia) {
-        const int ky = qy + ia;
-        if (ky >= h) break;  // only reachable for the cropped-away overhang
-        T rl0 = 0, rl1 = 0, rh0 = 0, rh1 = 0;
-        for (int ib = 0; ib < half; ++ib) {
-          const int kx = qx + ib;
-          if (kx >= w) break;
-          const int tx = L - 2 - 2 * ib;
-          const T glx0 = f.s_lo[tx], glx1 = f.s_lo[tx + 1], ghx0 = f.s_hi[tx], ghx1 = f.s_hi[tx + 1];
-          const int64_t o = (int64_t)ky * w + kx;
-          const T v_ll = pll[(int64_t)ky * c.ll_stride_w + kx] * c.s_ll;
-          const T v_lh = phi[o] * c.s_lh;       // high along H, low along W
-          const T v_hl = phi[hw + o] * c.s_hl;  // low along H, high along W
-          const T v_hh = phi[2 * hw + o] * c.s_hh;
-          rl0 += glx0 * v_ll + ghx0 * v_hl;
-          rl1 += glx1 * v_ll + ghx1 * v_hl;
-          rh0 += glx0 * v_lh + ghx0 * v_hh;
-          rh1 += glx1 * v_lh + ghx1 * v_hh;
-        }
-        const int ty = L - 2 - 2 * ia;
-        const T gly0 = f.s_lo[ty], gly1 = f.s_lo[ty + 1], ghy0 = f.s_hi[ty], ghy1 = f.s_hi[ty + 1];
-        o00 += gly0 * rl0 + ghy0 * rh0;
-        o01 += gly0 * rl1 + ghy0 * rh1;
-        o10 += gly1 * rl0 + ghy1 * rh0;
-        o11 += gly1 * rl1 + ghy1 * rh1;
-      }
+      synthesis_quad<T>(c.ll + plane * (int64_t)c.ll_stride_h * c.ll_stride_w, c.ll_stride_w, c.hi + plane * 3 * hw, hw, w,
+                        h, w, qy, qx, c.s_ll, c.s_lh, c.s_hl, c.s_hh, f, o00, o01, o10, o11);
     }
     const T vals[4] = {o00, o01, o10, o11};
 #pragma unroll
@@ -204,6 +226,134 @@ dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, 
       } else {
         out_t[(plane * out_h + iy) * (int64_t)out_w + ix] = vals[q];
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole wavelet-CFG call in ONE launch: one CTA per plane, all J analysis levels, the per-band
+// scaling and all J synthesis levels with every coefficient resident in shared memory (db2 / 3 levels
+// on a 128x128 plane: 184 KB of fp64 coefficients). HBM traffic is the algorithmic minimum: the fp32
+// inputs are read once (level-1 windows overlap in L1), the fp32 result is written once.
+//   value = in_a - in_b ;  out = x_scale*x + (float)(recon_sign*(IDWT(S (.) DWT(value)) + addend_scale*addend))
+// Buffers: LL[j] holds ll_j during analysis and is reused for the reconstruction rec_{j+1} on the way
+// back (which may be one row/column larger); HI[j] holds the three detail bands of level j.
+// ---------------------------------------------------------------------------------------------
+struct WcfgGeom {
+  int levels;
+  int h[SONAR_WCFG_MAX_LEVELS], w[SONAR_WCFG_MAX_LEVELS];            // coefficient extents, fine -> coarse
+  int ll_off[SONAR_WCFG_MAX_LEVELS], hi_off[SONAR_WCFG_MAX_LEVELS];  // element offsets into shared memory
+  int total;                                                         // elements
+};
+
+static bool wcfg_geometry(int H, int W, int L, int levels, WcfgGeom* g) {
+  if (levels < 1 || levels > SONAR_WCFG_MAX_LEVELS || H <= 0 || W <= 0) return false;
+  g->levels = levels;
+  int hh = H, ww = W;
+  for (int j = 0; j < levels; ++j) {
+    hh = (hh + L - 1) / 2;
+    ww = (ww + L - 1) / 2;
+    g->h[j] = hh;
+    g->w[j] = ww;
+  }
+  int64_t off = 0;
+  for (int j = 0; j < levels; ++j) {
+    int64_t ll = (int64_t)g->h[j] * g->w[j];
+    if (j + 1 < levels) {  // rec_{j+1} lands here on the way back
+      const int64_t rec = (int64_t)(2 * g->h[j + 1] - L + 2) * (2 * g->w[j + 1] - L + 2);
+      if (rec > ll) ll = rec;
+    }
+    g->ll_off[j] = (int)off;
+    off += ll + (ll & 1);
+    g->hi_off[j] = (int)off;
+    off += 3 * (int64_t)g->h[j] * g->w[j];
+    off += off & 1;
+    if (off > (1 << 28)) return false;
+  }
+  g->total = (int)off;
+  return true;
+}
+
+constexpr int kWcfgThreads = 1024;
+
+template <typename T>
+struct WcfgScales {
+  T v[SONAR_WCFG_MAX_LEVELS * 3];  // [level][orientation], fine -> coarse
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kWcfgThreads, 1)
+wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, float* __restrict__ out,
+                  const float* __restrict__ addend, float addend_scale, const float* __restrict__ x, float x_scale,
+                  float recon_sign, int64_t planes, int H, int W, int mode, WcfgGeom g, T scale_ll, WcfgScales<T> scales,
+                  Filters<T> f) {
+  const T* scale_hi = scales.v;
+  extern __shared__ __align__(16) unsigned char wcfg_smem[];
+  T* sm = reinterpret_cast<T*>(wcfg_smem);
+  const int L = f.L, J = g.levels;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {
+    const float* pa = in_a + plane * (int64_t)H * W;
+    const float* pb = in_b != nullptr ? in_b + plane * (int64_t)H * W : nullptr;
+    // ---------------- analysis, fine -> coarse ----------------
+    for (int j = 0; j < J; ++j) {
+      const int Hin = j == 0 ? H : g.h[j - 1], Win = j == 0 ? W : g.w[j - 1];
+      const int h = g.h[j], w = g.w[j];
+      const int pad_t = (2 * (h - 1) - Hin + L) / 2, pad_l = (2 * (w - 1) - Win + L) / 2;
+      T* ll = sm + g.ll_off[j];
+      T* hi = sm + g.hi_off[j];
+      const int hw = h * w;
+      for (int idx = tid; idx < hw; idx += nthr) {
+        const int ky = idx / w, kx = idx - ky * w;
+        T c_ll, c_lh, c_hl, c_hh;
+        if (j == 0)
+          analysis_point<T, float>(pa, pb, W, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh, c_hl, c_hh);
+        else
+          analysis_point<T, T>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh,
+                               c_hl, c_hh);
+        ll[idx] = c_ll;
+        hi[idx] = c_lh;
+        hi[hw + idx] = c_hl;
+        hi[2 * hw + idx] = c_hh;
+      }
+      __syncthreads();
+    }
+    // ---------------- synthesis, coarse -> fine ----------------
+    for (int j = J - 1; j >= 0; --j) {
+      const int h = g.h[j], w = g.w[j];
+      const bool coarsest = j == J - 1;
+      const T* ll = sm + g.ll_off[j];
+      const int ll_pitch = coarsest ? w : 2 * g.w[j + 1] - L + 2;
+      const T s_ll = coarsest ? scale_ll : (T)1;
+      const T s_lh = scale_hi[3 * j], s_hl = scale_hi[3 * j + 1], s_hh = scale_hi[3 * j + 2];
+      const T* hi = sm + g.hi_off[j];
+      const int out_h = 2 * h - L + 2, out_w = 2 * w - L + 2;
+      const int oh = j == 0 ? H : out_h, ow = j == 0 ? W : out_w;  // the final level is cropped to the input size
+      const int qh = (oh + 1) >> 1, qw = (ow + 1) >> 1;
+      T* rec = j == 0 ? nullptr : sm + g.ll_off[j - 1];
+      for (int idx = tid; idx < qh * qw; idx += nthr) {
+        const int qy = idx / qw, qx = idx - qy * qw;
+        T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+        synthesis_quad<T>(ll, ll_pitch, hi, (int64_t)h * w, w, h, w, qy, qx, s_ll, s_lh, s_hl, s_hh, f, o00, o01, o10, o11);
+        const T vals[4] = {o00, o01, o10, o11};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int iy = 2 * qy + (q >> 1), ix = 2 * qx + (q & 1);
+          if (iy >= oh || ix >= ow) continue;
+          if (j == 0) {
+            const int64_t o = (plane * H + iy) * (int64_t)W + ix;
+            T r = vals[q];
+            if (addend != nullptr) r += (T)addend_scale * (T)addend[o];
+            r = (T)recon_sign * r;
+            float rf = (float)r;  // cast to the latent dtype first, then x - result (py/wavelet_cfg.py:729-747)
+            if (x != nullptr) rf = x_scale * x[o] + rf;
+            out[o] = rf;
+          } else {
+            rec[iy * out_w + ix] = vals[q];
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -266,6 +416,23 @@ int launch_synthesis(const SonarDwtSynthesisParams& p, cudaStream_t stream) {
   return 0;
 }
 
+template <typename T>
+int launch_wcfg_fused(const SonarWcfgFusedParams& p, const WcfgGeom& g, cudaStream_t stream) {
+  const Filters<T> f = make_filters<T>(&p.filters);
+  const size_t smem = (size_t)g.total * sizeof(T);
+  WcfgScales<T> sc;
+  for (int j = 0; j < SONAR_WCFG_MAX_LEVELS; ++j)
+    for (int o = 0; o < 3; ++o) sc.v[3 * j + o] = j < p.levels ? (T)p.scale_hi[j][o] : (T)0;
+  SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const DeviceInfo& di = device_info();
+  const int grid = (int)(p.planes < di.sm_count ? p.planes : di.sm_count);
+  wcfg_fused_kernel<T><<<grid, kWcfgThreads, smem, stream>>>(
+      p.in_a, p.in_b, p.out, p.addend, p.addend_scale, p.x, p.x_scale, p.recon_sign, p.planes, p.H, p.W, p.mode, g,
+      (T)p.scale_ll, sc, f);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace sonar
 
 extern "C" {
@@ -282,6 +449,28 @@ int sonar_dwt2_analysis(const SonarDwtAnalysisParams* params, void* stream) {
   if (p.h != sonar_dwt_coeff_len(p.H, p.filters.length) || p.w != sonar_dwt_coeff_len(p.W, p.filters.length))
     return (int)cudaErrorInvalidValue;
   return p.use_f64 ? launch_analysis<double>(p, (cudaStream_t)stream) : launch_analysis<float>(p, (cudaStream_t)stream);
+}
+
+int64_t sonar_wcfg_fused_smem_bytes(int H, int W, int filter_len, int levels, int use_f64) {
+  sonar::WcfgGeom g;
+  if (filter_len < 2 || filter_len > SONAR_DWT_MAX_TAPS || (filter_len & 1)) return 0;
+  if (!sonar::wcfg_geometry(H, W, filter_len, levels, &g)) return 0;
+  const int64_t bytes = (int64_t)g.total * (use_f64 ? 8 : 4);
+  return bytes <= (int64_t)sonar::device_info().max_smem_optin ? bytes : 0;
+}
+
+int sonar_wcfg_fused(const SonarWcfgFusedParams* params, void* stream) {
+  using namespace sonar;
+  if (params == nullptr) return (int)cudaErrorInvalidValue;
+  const SonarWcfgFusedParams& p = *params;
+  if (p.planes <= 0) return 0;
+  if (p.in_a == nullptr || p.out == nullptr) return (int)cudaErrorInvalidValue;
+  if (sonar_wcfg_fused_smem_bytes(p.H, p.W, p.filters.length, p.levels, p.use_f64) <= 0) return (int)cudaErrorInvalidValue;
+  WcfgGeom g;
+  wcfg_geometry(p.H, p.W, p.filters.length, p.levels, &g);
+  // the final level must reconstruct at least the input extent (true for every orthogonal bank here)
+  if (2 * g.h[0] - p.filters.length + 2 < p.H || 2 * g.w[0] - p.filters.length + 2 < p.W) return (int)cudaErrorInvalidValue;
+  return p.use_f64 ? launch_wcfg_fused<double>(p, g, (cudaStream_t)stream) : launch_wcfg_fused<float>(p, g, (cudaStream_t)stream);
 }
 
 int sonar_dwt2_synthesis(const SonarDwtSynthesisParams* params, void* stream) {

@@ -200,23 +200,39 @@ def new_sums(device: torch.device) -> torch.Tensor:
 
 
 # Producer kernels (spectral, pyramid, perlin, blend, axpby) reduce {sum, sum^2} of what they write in
-# the same launch. The double[2] slots come from a per-device ring (no allocation, no memset launch from
-# Python: the C entry point clears its slot in-stream) and travel with the output tensor as the
-# attribute `_sonar_sums = (slot, tensor._version)`: scale_noise uses them instead of a moments pass
-# as long as nobody has modified the tensor since (torch bumps _version on in-place ops; our own
-# in-place kernels call drop_sums).
+# the same launch. The double[2] slots come from a per-device ring that needs neither an allocation nor
+# a memset per launch: every slot starts zeroed, and the producer that fills slot i also clears slot
+# i+1 (stream order makes that safe: the last reader of slot i+1 was enqueued a whole ring ago).
+# The slot travels with the output tensor as the attribute `_sonar_sums = (slot, tensor._version)`:
+# scale_noise uses it instead of a moments pass as long as nobody has modified the tensor since (torch
+# bumps _version on in-place ops; our own in-place kernels call drop_sums).
 _SUMS_RING: dict = {}
 _SUMS_RING_SLOTS = 256
 
 
-def sums_slot(device: torch.device) -> torch.Tensor:
+def sums_slot(device: torch.device) -> tuple[torch.Tensor, int, int]:
+    """(slot tensor, its pointer, pointer of the slot to clear) -- call sums_advance(device) after the
+    launch succeeded (a slot that was handed out but never written must stay zero)."""
     ring = _SUMS_RING.get(device)
     if ring is None:
         base = torch.zeros((_SUMS_RING_SLOTS, 2), device=device, dtype=torch.float64)
-        ring = _SUMS_RING[device] = [list(base.unbind(0)), 0]
-    slots, i = ring
-    ring[1] = (i + 1) % _SUMS_RING_SLOTS
-    return slots[i]
+        ring = _SUMS_RING[device] = [list(base.unbind(0)), 0, base.data_ptr()]
+    slots, i, base_ptr = ring
+    return slots[i], base_ptr + 16 * i, base_ptr + 16 * ((i + 1) % _SUMS_RING_SLOTS)
+
+
+def sums_advance(device: torch.device) -> None:
+    ring = _SUMS_RING[device]
+    ring[1] = (ring[1] + 1) % _SUMS_RING_SLOTS
+
+
+def _sums_written(out: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
+    """After a producer launch: advance the ring and tag `out` (an empty tensor launches nothing, so
+    its slot stays untouched and is handed out again)."""
+    if out.numel() == 0:
+        return out
+    sums_advance(out.device)
+    return attach_sums(out, slot)
 
 
 def attach_sums(t: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
@@ -365,7 +381,7 @@ def scale(x: torch.Tensor, factor: float) -> torch.Tensor:
     _f32(x, "x")
     lib, stream = _prepare(x)
     drop_sums(x)
-    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), None, stream)
+    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(x), float(factor), None, 0.0, _ptr(x), x.numel(), None, None, stream)
     return x
 
 
@@ -374,9 +390,9 @@ def axpby(a: torch.Tensor, alpha: float, b: torch.Tensor | None, beta: float = 1
     _f32(a, "a")
     out = torch.empty_like(a) if out is None else out
     lib, stream = _prepare(a, b, out)
-    slot = sums_slot(out.device)
-    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), _ptr(slot), stream)
-    return attach_sums(out, slot)
+    slot, slot_ptr, clear_ptr = sums_slot(out.device)
+    _launch("sonar_axpby_f32", lib.sonar_axpby_f32, _ptr(a), float(alpha), _ptr(b), float(beta), _ptr(out), a.numel(), slot_ptr, clear_ptr, stream)
+    return _sums_written(out, slot)
 
 
 def affine(x: torch.Tensor, pre_add: float, mul: float, post_add: float, out: torch.Tensor | None = None):
@@ -416,9 +432,9 @@ def blend(a: torch.Tensor, b: torch.Tensor, t, *, mode: str = "lerp", out: torch
         t_scalar = float(t)
     out = torch.empty_like(a) if out is None else out
     lib, stream = _prepare(a, b, t_tensor, out)
-    slot = sums_slot(out.device)
-    _launch("sonar_blend_f32", lib.sonar_blend_f32, _ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], _ptr(slot), stream)
-    return attach_sums(out, slot)
+    slot, slot_ptr, clear_ptr = sums_slot(out.device)
+    _launch("sonar_blend_f32", lib.sonar_blend_f32, _ptr(a), _ptr(b), _ptr(t_tensor), t_scalar, _ptr(out), a.numel(), BLEND_IDS[mode], slot_ptr, clear_ptr, stream)
+    return _sums_written(out, slot)
 
 
 def composite(dst: torch.Tensor, src: torch.Tensor, mask: torch.Tensor, out: torch.Tensor | None = None):
@@ -510,10 +526,9 @@ def pyramid_accumulate(
     p.planes, p.H, p.W = planes, H, W
     p.n_levels, p.mode, p.base_scale = len(levels), RESAMPLE_IDS[mode], float(base_scale)
     lib, stream = _prepare(out, base, *levels)
-    slot = sums_slot(out.device)
-    p.sums = slot.data_ptr()
+    slot, p.sums, p.sums_clear = sums_slot(out.device)
     _launch("sonar_pyramid_accum_f32", lib.sonar_pyramid_accum_f32, ctypes.byref(p), stream)
-    return attach_sums(out, slot)
+    return _sums_written(out, slot)
 
 
 def resample(x: torch.Tensor, height: int, width: int, *, mode: str = "bilinear") -> torch.Tensor:
@@ -544,10 +559,9 @@ def perlin_accumulate(
     p.B, p.C, p.H, p.W = B, C, H, W
     p.iterations, p.blend_mode, p.div_fac = len(angles), BLEND_IDS[blend_mode], float(div_fac)
     lib, stream = _prepare(out, base, *angles)
-    slot = sums_slot(out.device)
-    p.sums = slot.data_ptr()
+    slot, p.sums, p.sums_clear = sums_slot(out.device)
     _launch("sonar_perlin_accum_f32", lib.sonar_perlin_accum_f32, ctypes.byref(p), stream)
-    return attach_sums(out, slot)
+    return _sums_written(out, slot)
 
 
 # --------------------------------------------------------------------------------------------
@@ -604,10 +618,9 @@ def spectral_filter(
     p.mask = 0 if mask is None else mask.data_ptr()
     p.scratch = 0 if scratch is None else scratch.data_ptr()
     p.planes, p.H, p.W, p.out_scale = planes, H, W, float(out_scale)
-    slot = sums_slot(out.device)
-    p.sums = slot.data_ptr()
+    slot, p.sums, p.sums_clear = sums_slot(out.device)
     _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
-    return attach_sums(out, slot)
+    return _sums_written(out, slot)
 
 
 # --------------------------------------------------------------------------------------------
@@ -710,4 +723,49 @@ def dwt2_synthesis(
         live += [addend, x]
     lib, stream = _prepare(out, *live)
     _launch("sonar_dwt2_synthesis", lib.sonar_dwt2_synthesis, ctypes.byref(p), stream)
+    return out
+
+
+def wcfg_fused_fits(height: int, width: int, filter_len: int, levels: int, *, use_f64: bool) -> bool:
+    """True when the whole coefficient pyramid of one (height, width) plane fits one SM's shared memory."""
+    if levels > _native.WCFG_MAX_LEVELS:
+        return False
+    return _native.load().sonar_wcfg_fused_smem_bytes(height, width, filter_len, levels, int(use_f64)) > 0
+
+
+def wcfg_fused(
+    a: torch.Tensor,
+    b: torch.Tensor | None,
+    filters: _native.SonarWaveletFilters,
+    *,
+    levels: int,
+    mode: str,
+    use_f64: bool,
+    scale_ll: float,
+    scale_hi: Sequence[Sequence[float]],
+    addend: torch.Tensor | None = None,
+    addend_scale: float = 1.0,
+    x: torch.Tensor | None = None,
+    x_scale: float = 1.0,
+    recon_sign: float = 1.0,
+) -> torch.Tensor:
+    """x_scale*x + float(recon_sign*(IDWT(S (.) DWT(a - b)) + addend_scale*addend)), cropped to the
+    input size, in ONE launch. a, b, addend, x: (planes, H, W) float32. scale_hi: [level][3], fine ->
+    coarse; scale_ll scales the coarsest approximation band."""
+    _f32(a, "a")
+    planes, height, width = a.shape
+    out = torch.empty_like(a)
+    p = _native.SonarWcfgFusedParams()
+    p.in_a, p.in_b, p.out = a.data_ptr(), (0 if b is None else b.data_ptr()), out.data_ptr()
+    p.addend, p.addend_scale = (0 if addend is None else addend.data_ptr()), float(addend_scale)
+    p.x, p.x_scale, p.recon_sign = (0 if x is None else x.data_ptr()), float(x_scale), float(recon_sign)
+    p.planes, p.H, p.W, p.levels = planes, height, width, levels
+    p.mode, p.use_f64 = DWT_MODE_IDS[mode], int(use_f64)
+    p.scale_ll = float(scale_ll)
+    for j, row in enumerate(scale_hi):
+        for o in range(3):
+            p.scale_hi[j][o] = float(row[o])
+    p.filters = filters
+    lib, stream = _prepare(a, b, out, addend, x)
+    _launch("sonar_wcfg_fused", lib.sonar_wcfg_fused, ctypes.byref(p), stream)
     return out

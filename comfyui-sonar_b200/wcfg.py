@@ -13,6 +13,10 @@ and when A + B is the same constant c0 in every band (the default configuration:
 second term is c0 * uncond by perfect reconstruction, so ONE analysis/synthesis pair over
 (cond - uncond) suffices; the synthesis kernel applies A on load, and its final level fuses
 "+ c0*uncond", the crop to x.shape, the fp32 cast and "x - result".
+
+When the coefficient pyramid of a plane fits one SM's shared memory (db2 / 3 levels / 128x128 in
+fp64: 184 KB) that whole pair is ONE launch (`ops.wcfg_fused`, one CTA per plane); otherwise one
+launch per level with the coefficients in L2/HBM.
 """
 
 from __future__ import annotations
@@ -610,6 +614,20 @@ class WaveletCFG:
         # one transform pair is enough when A + B is band-independent (then (A+B) (.) DWT(u) == c0 * u);
         # the c0 * u term is added at the input resolution, so the output must be cropped to it
         single = all(abs(s - c0) <= 1e-12 * max(1.0, abs(c0)) for s in sums) and crop == (height, width)
+
+        if (
+            single
+            and wavelet.inv_filters is wavelet.filters
+            and ops.wcfg_fused_fits(height, width, taps, wavelet.level, use_f64=coeff_dtype == torch.float64)
+        ):
+            # everything on chip: one launch, fp32 inputs read once, fp32 result written once
+            ep = epilogue or {}
+            return ops.wcfg_fused(
+                cond, uncond, wavelet.filters, levels=wavelet.level, mode=wavelet.mode,
+                use_f64=coeff_dtype == torch.float64, scale_ll=a_ll, scale_hi=a_hi,
+                addend=uncond if c0 != 0.0 else None, addend_scale=c0,
+                x=ep.get("x"), x_scale=ep.get("x_scale", 1.0), recon_sign=ep.get("recon_sign", 1.0),
+            )  # fmt: skip
 
         def analyse(a, b):
             cur, his = (a, b), []

@@ -176,7 +176,8 @@ typedef struct SonarPyramidParams {
   int32_t n_levels;
   int32_t mode; /* SONAR_RESAMPLE_* */
   float base_scale;
-  double* sums; /* optional double[2]: OVERWRITTEN with {sum, sum of squares} of `out` (same launch) */
+  double* sums;       /* optional double[2], zero on entry: += {sum, sum of squares} of `out` (same launch) */
+  double* sums_clear; /* optional double[2] the launch zeroes (next slot of the caller's ring) */
 } SonarPyramidParams;
 
 int sonar_pyramid_accum_f32(const SonarPyramidParams* params_host, void* stream);
@@ -199,7 +200,8 @@ typedef struct SonarPerlinParams {
   int32_t iterations;
   int32_t blend_mode; /* SONAR_BLEND_* */
   float div_fac;
-  double* sums; /* optional double[2]: OVERWRITTEN with {sum, sum of squares} of `out` */
+  double* sums;       /* optional double[2], zero on entry: += {sum, sum of squares} of `out` */
+  double* sums_clear; /* optional double[2] the launch zeroes */
 } SonarPerlinParams;
 
 int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
@@ -215,14 +217,16 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
  * blend: out = mode(a, b, t) with t = t_tensor[i] if t_tensor else t_scalar. `out` may alias a or b.
  * axpby: out = a*alpha + b*beta (b may be NULL).
  * composite: out = dst*(1-mask) + src*mask, mask (batch,1,H,W) broadcast over channels.
- * `sums` (blend, axpby; optional double[2]) is OVERWRITTEN with {sum, sum of squares} of `out`, reduced in the
- * same launch: the producer of a tensor hands scale_noise its statistics, saving the separate read pass.
+ * `sums` (optional double[2], zero on entry) receives {sum, sum of squares} of `out`, reduced in the same
+ * launch: the producer of a tensor hands scale_noise its statistics, saving the separate read pass.
+ * `sums_clear` (optional) is another double[2] the launch zeroes, so a caller can recycle a ring of
+ * slots (slot i's producer clears slot i+1) without a memset per launch.
  * item_*: reductions over everything but the leading dim; scratch from sonar_item_range_scratch_bytes.
  * ---------------------------------------------------------------------------------------------- */
 int sonar_blend_f32(const float* a, const float* b, const float* t_tensor, float t_scalar, float* out, int64_t n,
-                    int mode, double* sums, void* stream);
+                    int mode, double* sums, double* sums_clear, void* stream);
 int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, int64_t n, double* sums,
-                    void* stream);
+                    double* sums_clear, void* stream);
 /* out = ((x + pre_add) * mul) + post_add, each step rounded (UniformNoiseGenerator.generate,
  * py/noise_generation.py:508-514) */
 int sonar_affine_f32(const float* x, float* out, int64_t n, float pre_add, float mul, float post_add, void* stream);
@@ -260,7 +264,8 @@ typedef struct SonarSpectralParams {
   int32_t H;
   int32_t W;
   float out_scale;
-  double* sums; /* optional double[2]: OVERWRITTEN with {sum, sum of squares} of `out` */
+  double* sums;       /* optional double[2], zero on entry: += {sum, sum of squares} of `out` */
+  double* sums_clear; /* optional double[2] the launch zeroes */
 } SonarSpectralParams;
 
 int64_t sonar_spectral_scratch_bytes(int H, int W);
@@ -335,6 +340,38 @@ typedef struct SonarDwtSynthesisParams {
 int sonar_dwt_coeff_len(int n, int filter_len);
 int sonar_dwt2_analysis(const SonarDwtAnalysisParams* params_host, void* stream);
 int sonar_dwt2_synthesis(const SonarDwtSynthesisParams* params_host, void* stream);
+
+/* The whole wavelet-CFG combine in ONE launch (one CTA per plane, every coefficient of every level in
+ * shared memory):  value = in_a - in_b (in_b optional), coefficients scaled per band (scale_ll for the
+ * coarsest approximation, scale_hi[level][orientation], levels fine -> coarse), reconstruction cropped
+ * to (H, W):   out = x_scale*x + (float)(recon_sign*(recon + addend_scale*addend)).
+ * replaces: WaveletCFG.wavelet_cfg + process_output (2 forward + 1 inverse transforms and ~8 coefficient
+ *           passes upstream)                               py/wavelet_cfg.py:729-791
+ * sonar_wcfg_fused_smem_bytes returns the shared memory the call needs, or 0 when the coefficient
+ * pyramid does not fit one SM (the caller then uses the per-level entry points above). */
+#define SONAR_WCFG_MAX_LEVELS 8
+typedef struct SonarWcfgFusedParams {
+  const float* in_a;
+  const float* in_b;
+  float* out;
+  const float* addend;
+  float addend_scale;
+  const float* x;
+  float x_scale;
+  float recon_sign;
+  int64_t planes;
+  int32_t H;
+  int32_t W;
+  int32_t levels;
+  int32_t mode; /* SONAR_DWT_MODE_* */
+  int32_t use_f64;
+  double scale_ll;
+  double scale_hi[SONAR_WCFG_MAX_LEVELS][3];
+  SonarWaveletFilters filters;
+} SonarWcfgFusedParams;
+
+int64_t sonar_wcfg_fused_smem_bytes(int H, int W, int filter_len, int levels, int use_f64);
+int sonar_wcfg_fused(const SonarWcfgFusedParams* params_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Peer-memory exchange of the global scale_noise statistics (one node, NVLink 5 / NVSwitch).

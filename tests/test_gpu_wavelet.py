@@ -147,3 +147,42 @@ def test_rule_out_of_range_falls_back(sb, cuda):
     fn = sb.wcfg.WaveletCFG(existing_cfg=None, rules=sb.wcfg.WCFGRules.build(start_sigma=3.0, end_sigma=1.0, **C4_RULE))
     got = fn(_args(cond, uncond, x, sigma=5.0, scale=7.0))
     assert_close(got, x - ((cond - uncond) * 7.0 + uncond), what="fallback cfg")
+
+
+@pytest.mark.parametrize(
+    "rule,shape",
+    [
+        (C4_RULE, (3, 4, 128, 128)),
+        ({"wave": "db4", "level": 3, "diff": {"yl_scale": 2.0, "yh_scales": [[1, 2, 3], 2.5, 0.5]}}, (2, 3, 33, 47)),
+        ({"wave": "haar", "level": 4, "high_precision_mode": False, "diff": {"yl_scale": 4.0, "yh_scales": 2.0}}, (1, 4, 64, 96)),
+        ({"wave": "db2", "level": 2, "padding_mode": "periodic", "diff": {"yl_scale": 3.0, "yh_scales": 1.5}}, (2, 2, 40, 24)),
+        ({"wave": "db3", "level": 1, "padding_mode": "reflect", "diff": {"yl_scale": 3.0, "yh_scales": 1.5}}, (150, 1, 18, 20)),
+    ],
+)
+def test_fused_wcfg_launch_equals_per_level_path(sb, cuda, rule, shape, monkeypatch):
+    """The one-launch, all-in-shared-memory path computes exactly what the per-level kernels do."""
+    torch.manual_seed(9)
+    cond, uncond, x = (torch.randn(shape, device=cuda) for _ in range(3))
+    fn = sb.wcfg.WaveletCFG(existing_cfg=None, rules=sb.wcfg.WCFGRules.build(**rule))
+    seen = []
+    real = sb.ops.wcfg_fused
+    monkeypatch.setattr(sb.ops, "wcfg_fused", lambda *a, **k: (seen.append(1), real(*a, **k))[1])
+    fused = fn(_args(cond, uncond, x))
+    assert seen, "fused path not taken"
+    monkeypatch.setattr(sb.ops, "wcfg_fused_fits", lambda *a, **k: False)
+    per_level = fn(_args(cond, uncond, x))
+    assert len(seen) == 1
+    tol = 1e-6 if rule.get("high_precision_mode", True) else 2e-5
+    assert_close(fused, per_level, what="fused vs per-level", rtol=tol, atol=tol)
+
+
+def test_fused_wcfg_declines_what_does_not_fit(sb, cuda):
+    """256x256 fp64 planes exceed one SM's shared memory: the per-level path runs (and is correct)."""
+    assert sb.ops.wcfg_fused_fits(128, 128, 4, 3, use_f64=True)
+    assert not sb.ops.wcfg_fused_fits(256, 256, 4, 3, use_f64=True)
+    torch.manual_seed(10)
+    cond, uncond, x = (torch.randn(1, 2, 256, 256) for _ in range(3))
+    want = orc.wavelet_cfg(cond, uncond, x, _filters(sb, "db2"), level=3, diff=(5, [[3, 4, 5]] * 3))
+    fn = sb.wcfg.WaveletCFG(existing_cfg=None, rules=sb.wcfg.WCFGRules.build(**C4_RULE))
+    got = fn(_args(cond.to(cuda), uncond.to(cuda), x.to(cuda)))
+    assert_close(got, want, what="256x256")
