@@ -71,6 +71,27 @@ FFT_MAX_FACTORS = 24
 DWT_MAX_TAPS = 40
 
 
+FILL_BATCH_MAX = 16
+
+
+class SonarFillDesc(ctypes.Structure):
+    _fields_ = [
+        ("out", c_void_p),
+        ("begin", c_int64),
+        ("count", c_int64),
+        ("numel_total", c_int64),
+        ("offset", c_uint64),
+        ("grid_blocks", c_uint32),
+        ("kind", c_int32),
+        ("p0", c_float),
+        ("p1", c_float),
+    ]
+
+
+class SonarFillBatch(ctypes.Structure):
+    _fields_ = [("n", c_int32), ("seed", c_uint64), ("draws", SonarFillDesc * FILL_BATCH_MAX)]
+
+
 class SonarPyramidParams(ctypes.Structure):
     _fields_ = [
         ("out", c_void_p),
@@ -214,6 +235,7 @@ SIGNATURES: dict[str, list] = {
     "sonar_philox_uniform_f32": [
         c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_float, c_float, c_void_p,
     ],
+    "sonar_philox_fill_batch": [POINTER(SonarFillBatch), c_void_p],
     "sonar_moments_f32": [c_void_p, c_int64, c_void_p, c_void_p],
     "sonar_philox_normal_moments": [c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p],
     "sonar_philox_normal_moments_batch": [

@@ -132,8 +132,9 @@ pyramid_accum_kernel(SonarPyramidParams p) {
 // each CTA computes them once into shared memory; a warp then walks whole rows, computing the y taps
 // once per row. Per pixel and level that leaves 3 table reads, 4 cached loads and 6 FMAs instead of
 // the float divisions and tap arithmetic of the generic path.
-constexpr int kRowUnroll = 4;  // pixels per lane per pass, 32 apart: conflict-free tables, coalesced rows
-
+// VEC = 4: each lane owns 4 consecutive pixels (W % 4 == 0, 16-byte aligned rows): base, full-size
+// level and output move as float4; VEC = 1: any width / alignment.
+template <int VEC>
 __global__ void __launch_bounds__(kBlock)
 pyramid_rows_kernel(SonarPyramidParams p) {
   extern __shared__ __align__(16) unsigned char pyr_smem[];
@@ -159,37 +160,51 @@ pyramid_rows_kernel(SonarPyramidParams p) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t n_rows = p.planes * (int64_t)H;
+  const bool bilinear = p.mode == SONAR_RESAMPLE_BILINEAR;
   float ms = 0.0f, mss = 0.0f;
   for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
        row += (int64_t)gridDim.x * warps_per_block) {
     const int y = (int)(row % H);
     const int64_t plane = row / H;
     const int64_t obase = row * W;
-    for (int x0 = lane; x0 < W; x0 += 32 * kRowUnroll) {
-      float acc[kRowUnroll];
-      bool ok[kRowUnroll];
+    for (int x0 = lane * VEC; x0 < W; x0 += 32 * VEC) {
+      float acc[VEC];
+      if (p.base != nullptr) {
+        if (VEC == 4) {
+          const float4 b4 = ld4_stream(p.base + obase + x0);
+          acc[0] = b4.x; acc[1 % VEC] = b4.y; acc[2 % VEC] = b4.z; acc[3 % VEC] = b4.w;
+        } else {
+          acc[0] = __ldg(p.base + obase + x0);
+        }
+        if (p.base_scale != 1.0f) {
 #pragma unroll
-      for (int v = 0; v < kRowUnroll; ++v) {
-        const int x = x0 + 32 * v;
-        ok[v] = x < W;
-        acc[v] = (ok[v] && p.base != nullptr) ? __ldg(p.base + obase + x) : 0.0f;
-        if (p.base_scale != 1.0f) acc[v] *= p.base_scale;
+          for (int v = 0; v < VEC; ++v) acc[v] *= p.base_scale;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.0f;
       }
       for (int l = 0; l < p.n_levels; ++l) {
         const int lh = p.level_h[l], lw = p.level_w[l];
         const float* src = p.levels[l] + plane * (int64_t)lh * lw;
         const float wgt = p.weights[l];
         if (lh == H && lw == W) {  // identity level: straight copy-accumulate
-          const float* r = src + (int64_t)y * W;
-#pragma unroll
-          for (int v = 0; v < kRowUnroll; ++v)
-            if (ok[v]) acc[v] = acc[v] + __fmul_rn(__ldg(r + x0 + 32 * v), wgt);
+          const float* r = src + (int64_t)y * W + x0;
+          if (VEC == 4) {
+            const float4 s4 = ld4_stream(r);
+            acc[0] = acc[0] + __fmul_rn(s4.x, wgt);
+            acc[1 % VEC] = acc[1 % VEC] + __fmul_rn(s4.y, wgt);
+            acc[2 % VEC] = acc[2 % VEC] + __fmul_rn(s4.z, wgt);
+            acc[3 % VEC] = acc[3 % VEC] + __fmul_rn(s4.w, wgt);
+          } else {
+            acc[0] = acc[0] + __fmul_rn(__ldg(r), wgt);
+          }
           continue;
         }
         const float* r0;
         const float* r1;
         float wy0, wy1;
-        if (p.mode == SONAR_RESAMPLE_BILINEAR) {
+        if (bilinear) {
           const LinTap ty = linear_tap(y, lh, (float)lh / (float)H);
           r0 = src + (int64_t)ty.i0 * lw;
           r1 = src + (int64_t)ty.i1 * lw;
@@ -200,16 +215,14 @@ pyramid_rows_kernel(SonarPyramidParams p) {
           wy0 = 1.0f;
           wy1 = 0.0f;
         }
-        const int tb = l * W;
+        const int tb = l * W + x0;
 #pragma unroll
-        for (int v = 0; v < kRowUnroll; ++v) {
-          if (!ok[v]) continue;
-          const int x = x0 + 32 * v;
-          const int i0 = tab_i0[tb + x];
+        for (int v = 0; v < VEC; ++v) {
+          const int i0 = tab_i0[tb + v];
           float sv;
-          if (p.mode == SONAR_RESAMPLE_BILINEAR) {
-            const int i1 = tab_i1[tb + x];
-            const float w1 = tab_w1[tb + x], w0 = 1.0f - w1;
+          if (bilinear) {
+            const int i1 = tab_i1[tb + v];
+            const float w1 = tab_w1[tb + v], w0 = 1.0f - w1;
             sv = wy0 * (w0 * __ldg(r0 + i0) + w1 * __ldg(r0 + i1)) + wy1 * (w0 * __ldg(r1 + i0) + w1 * __ldg(r1 + i1));
           } else {
             sv = __ldg(r0 + i0);
@@ -218,12 +231,14 @@ pyramid_rows_kernel(SonarPyramidParams p) {
         }
       }
 #pragma unroll
-      for (int v = 0; v < kRowUnroll; ++v)
-        if (ok[v]) {
-          p.out[obase + x0 + 32 * v] = acc[v];
-          ms += acc[v];
-          mss += acc[v] * acc[v];
-        }
+      for (int v = 0; v < VEC; ++v) {
+        ms += acc[v];
+        mss += acc[v] * acc[v];
+      }
+      if (VEC == 4)
+        st4_stream(p.out + obase + x0, make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]));
+      else
+        p.out[obase + x0] = acc[0];
     }
   }
   commit_moments(p.sums, p.sums_clear, ms, mss);
@@ -253,8 +268,89 @@ __device__ __forceinline__ float perlin_value(const float* __restrict__ ang, int
   return blend<float>(mode, row0, row1, 0.5f);
 }
 
+// corner gradient . offset for the four corners of pixel (y, x), from precomputed sin / cos
+__device__ __forceinline__ float perlin_from_corners(float s00, float c00, float s01, float c01, float s10, float c10,
+                                                     float s11, float c11, int mode) {
+  const float d00 = __fadd_rn(__fmul_rn(c00, 0.5f), __fmul_rn(s00, 0.5f));
+  const float d01 = __fadd_rn(__fmul_rn(c01, -0.5f), __fmul_rn(s01, 0.5f));
+  const float d10 = __fadd_rn(__fmul_rn(c10, 0.5f), __fmul_rn(s10, -0.5f));
+  const float d11 = __fadd_rn(__fmul_rn(c11, -0.5f), __fmul_rn(s11, -0.5f));
+  const float row0 = blend<float>(mode, d00, d01, 0.5f);
+  const float row1 = blend<float>(mode, d10, d11, 0.5f);
+  return blend<float>(mode, row0, row1, 0.5f);
+}
+
+// One thread per (c, y, VEC consecutive x): the 2 x (VEC+1) corner angles are turned into sin/cos once
+// (10 sincosf for 4 pixels instead of 16), the stencil value is kept in registers and added to every
+// batch item with float4 traffic. ITERS is a template parameter so pv[][] stays in registers.
+template <int VEC, int ITERS>
 __global__ void __launch_bounds__(kBlock)
 perlin_accum_kernel(SonarPerlinParams p) {
+  const int Wv = p.W / VEC;
+  const int64_t chw = (int64_t)p.C * p.H * p.W;
+  const int64_t total = (int64_t)p.C * p.H * Wv;
+  const float inv_div = 1.0f / p.div_fac;
+  float ms = 0.0f, mss = 0.0f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x0 = (int)(idx % Wv) * VEC;
+    const int y = (int)((idx / Wv) % p.H);
+    const int c = (int)(idx / ((int64_t)Wv * p.H));
+    float pv[ITERS][VEC];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int64_t gw = p.W + 1;
+      const float* a0 = p.angles[it] + (int64_t)c * (p.H + 1) * gw + (int64_t)y * gw + x0;
+      const float* a1 = a0 + gw;
+      float s0[VEC + 1], c0[VEC + 1], s1[VEC + 1], c1[VEC + 1];
+#pragma unroll
+      for (int v = 0; v <= VEC; ++v) {
+        sincosf(__ldg(a0 + v), &s0[v], &c0[v]);
+        sincosf(__ldg(a1 + v), &s1[v], &c1[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        pv[it][v] = perlin_from_corners(s0[v], c0[v], s0[v + 1], c0[v + 1], s1[v], c1[v], s1[v + 1], c1[v + 1], p.blend_mode);
+    }
+    const int64_t o0 = (int64_t)c * p.H * p.W + (int64_t)y * p.W + x0;
+#pragma unroll 4
+    for (int b = 0; b < p.B; ++b) {
+      const int64_t o = (int64_t)b * chw + o0;
+      float v[VEC];
+      if (p.base != nullptr) {
+        if (VEC == 4) {
+          const float4 b4 = ld4_stream(p.base + o);
+          v[0] = b4.x; v[1 % VEC] = b4.y; v[2 % VEC] = b4.z; v[3 % VEC] = b4.w;
+        } else {
+          v[0] = __ldg(p.base + o);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = div_by(v[k], p.div_fac, inv_div);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = 0.0f;
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] += pv[it][k];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        ms += v[k];
+        mss += v[k] * v[k];
+      }
+      if (VEC == 4)
+        st4_stream(p.out + o, make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
+      else
+        p.out[o] = v[0];
+    }
+  }
+  commit_moments(p.sums, p.sums_clear, ms, mss);
+}
+
+// any iteration count (up to SONAR_PERLIN_MAX_ITERS): one pixel per thread
+__global__ void __launch_bounds__(kBlock)
+perlin_accum_generic_kernel(SonarPerlinParams p) {
   const int64_t chw = (int64_t)p.C * p.H * p.W;
   float ms = 0.0f, mss = 0.0f;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < chw;
@@ -478,8 +574,13 @@ int sonar_pyramid_accum_f32(const SonarPyramidParams* params, void* stream) {
     // table-driven row kernel; one warp per row, grid sized to whole waves
     const int64_t n_rows = p.planes * (int64_t)p.H;
     const int grid = streaming_grid(n_rows, kBlock / 32, 2);
-    SONAR_CUDA_TRY(cudaFuncSetAttribute(pyramid_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
-    pyramid_rows_kernel<<<grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p);
+    if (vec) {
+      SONAR_CUDA_TRY(cudaFuncSetAttribute(pyramid_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      pyramid_rows_kernel<4><<<grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p);
+    } else {
+      SONAR_CUDA_TRY(cudaFuncSetAttribute(pyramid_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      pyramid_rows_kernel<1><<<grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p);
+    }
     SONAR_LAUNCH_CHECK();
     return 0;
   }
@@ -501,8 +602,27 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
   if (p.iterations < 0 || p.iterations > SONAR_PERLIN_MAX_ITERS || p.out == nullptr) return (int)cudaErrorInvalidValue;
   for (int i = 0; i < p.iterations; ++i)
     if (p.angles[i] == nullptr) return (int)cudaErrorInvalidValue;
-  const int grid = streaming_grid((int64_t)p.C * p.H * p.W, kBlock, 4);
-  perlin_accum_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(p);
+  const bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
+  const int64_t threads = (int64_t)p.C * p.H * (vec ? p.W / 4 : p.W);
+  const int grid = streaming_grid(threads, kBlock, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PERLIN_LAUNCH(ITERS)                                        \
+  do {                                                              \
+    if (vec)                                                        \
+      perlin_accum_kernel<4, ITERS><<<grid, kBlock, 0, st>>>(p);    \
+    else                                                            \
+      perlin_accum_kernel<1, ITERS><<<grid, kBlock, 0, st>>>(p);    \
+  } while (0)
+  switch (p.iterations) {
+    case 1: PERLIN_LAUNCH(1); break;
+    case 2: PERLIN_LAUNCH(2); break;
+    case 3: PERLIN_LAUNCH(3); break;
+    case 4: PERLIN_LAUNCH(4); break;
+    default:
+      perlin_accum_generic_kernel<<<streaming_grid((int64_t)p.C * p.H * p.W, kBlock, 4), kBlock, 0, st>>>(p);
+      break;
+  }
+#undef PERLIN_LAUNCH
   SONAR_LAUNCH_CHECK();
   return 0;
 }

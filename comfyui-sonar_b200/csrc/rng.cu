@@ -52,6 +52,60 @@ philox_fill_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxSt
   }
 }
 
+// Several draws in ONE launch (blockIdx.y = draw): a pyramid sample needs its base, its full-size
+// level and 2-3 tiny coarse levels, a Perlin sample its base and two angle grids -- five / three
+// launches of a few microseconds of work each, i.e. mostly launch latency. Draws keep their own ATen
+// geometry (T = 256 * grid_blocks), offset and transform, so every value is what a separate
+// torch.randn / Tensor.uniform_ call would have produced.
+struct FillBatchDev {
+  float* out[SONAR_FILL_BATCH_MAX];
+  int64_t begin[SONAR_FILL_BATCH_MAX], end[SONAR_FILL_BATCH_MAX];
+  uint64_t offset[SONAR_FILL_BATCH_MAX];
+  uint32_t threads[SONAR_FILL_BATCH_MAX], k_lo[SONAR_FILL_BATCH_MAX], k_hi[SONAR_FILL_BATCH_MAX];
+  int32_t kind[SONAR_FILL_BATCH_MAX];
+  float p0[SONAR_FILL_BATCH_MAX], p1[SONAR_FILL_BATCH_MAX];
+  uint64_t seed;
+};
+
+__global__ void __launch_bounds__(kBlock)
+philox_fill_batch_kernel(FillBatchDev b) {
+  const int d = blockIdx.y;
+  const PhiloxStream s{b.seed, b.offset[d], b.threads[d]};
+  const int64_t T = s.threads, begin = b.begin[d], end = b.end[d];
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  float* __restrict__ out = b.out[d];
+  const float p0 = b.p0[d], p1 = b.p1[d];
+  const bool normal = b.kind[d] == DIST_NORMAL;
+  const uint32_t k_lo = b.k_lo[d], k_hi = b.k_hi[d];
+  for (int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vt < T; vt += nthreads) {
+    for (uint32_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t li0 = vt + T * (int64_t)(4 * (uint64_t)k);
+      if (li0 >= end) break;
+      if (li0 + 3 * T < begin) continue;
+      float4 v;
+      if (normal) {
+        v = philox_normal4(s, (uint32_t)vt, k);
+        v.x = v.x * p1 + p0;
+        v.y = v.y * p1 + p0;
+        v.z = v.z * p1 + p0;
+        v.w = v.w * p1 + p0;
+      } else {
+        v = philox_uniform4(s, (uint32_t)vt, k);
+        v.x = uniform_transform(v.x, p0, p1);
+        v.y = uniform_transform(v.y, p0, p1);
+        v.z = uniform_transform(v.z, p0, p1);
+        v.w = uniform_transform(v.w, p0, p1);
+      }
+      const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int lane = 0; lane < 4; ++lane) {
+        const int64_t li = li0 + T * lane;
+        if (li >= begin && li < end) out[li - begin] = vals[lane];
+      }
+    }
+  }
+}
+
 template <int KIND>
 int launch_fill(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
                 uint64_t offset, uint32_t grid_blocks, float p0, float p1, cudaStream_t stream) {
@@ -100,6 +154,49 @@ int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t n
                              uint64_t offset, uint32_t grid_blocks, float from, float to, void* stream) {
   return sonar::launch_fill<sonar::DIST_UNIFORM>(out, begin, count, numel_total, seed, offset, grid_blocks, from,
                                                  to, (cudaStream_t)stream);
+}
+
+int sonar_philox_fill_batch(const SonarFillBatch* batch, void* stream) {
+  using namespace sonar;
+  if (batch == nullptr || batch->n < 0 || batch->n > SONAR_FILL_BATCH_MAX) return (int)cudaErrorInvalidValue;
+  FillBatchDev b;
+  b.seed = batch->seed;
+  int n = 0, gx = 1;
+  for (int i = 0; i < batch->n; ++i) {
+    const SonarFillDesc& d = batch->draws[i];
+    if (d.count <= 0) continue;
+    if (d.out == nullptr || d.grid_blocks == 0 || d.begin < 0 || d.begin + d.count > d.numel_total ||
+        (d.kind != DIST_NORMAL && d.kind != DIST_UNIFORM))
+      return (int)cudaErrorInvalidValue;
+    const int64_t T = (int64_t)d.grid_blocks * kBlock, end = d.begin + d.count;
+    b.out[n] = d.out;
+    b.begin[n] = d.begin;
+    b.end[n] = end;
+    b.offset[n] = d.offset;
+    b.threads[n] = (uint32_t)T;
+    b.k_lo[n] = (uint32_t)((d.begin / T) / 4);
+    b.k_hi[n] = (uint32_t)(((end - 1) / T) / 4);
+    b.kind[n] = d.kind;
+    b.p0[n] = d.p0;
+    b.p1[n] = d.p1;
+    const int g = streaming_grid(T, kBlock, 1);
+    if (g > gx) gx = g;
+    ++n;
+  }
+  if (n == 0) return 0;
+  for (int i = n; i < SONAR_FILL_BATCH_MAX; ++i) {  // unused slots: well-defined values
+    b.out[i] = nullptr;
+    b.begin[i] = b.end[i] = 0;
+    b.offset[i] = 0;
+    b.threads[i] = kBlock;
+    b.k_lo[i] = 1;
+    b.k_hi[i] = 0;
+    b.kind[i] = 0;
+    b.p0[i] = b.p1[i] = 0.0f;
+  }
+  philox_fill_batch_kernel<<<dim3((unsigned)gx, (unsigned)n), kBlock, 0, (cudaStream_t)stream>>>(b);
+  SONAR_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // extern "C"

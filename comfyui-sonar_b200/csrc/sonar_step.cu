@@ -272,15 +272,18 @@ sonar_step_fast_vec_kernel(SonarStepParams p) {
 // access is a coalesced 128-byte warp transaction. All loads of a pair are issued before the Philox
 // rounds and the Box-Muller transform, which then run under the loads' latency.
 // FULL: all four lanes of the pair lie inside the slice (no per-lane predicates or index clamps).
-template <int KIND, bool NEW_MODE, bool HAVE_H, bool FULL>
+// LANES = 2: the draw has at most two rows (numel <= 2T, e.g. an SDXL latent batch): lanes 2, 3 never
+// exist, one Box-Muller pair per Philox call, and the kernel fits 32 registers -> 8 CTAs per SM, i.e.
+// the whole emulated ATen grid (148 x 8 CTAs) is resident in a single wave.
+template <int KIND, bool NEW_MODE, bool HAVE_H, bool FULL, int LANES>
 __device__ __forceinline__ void step_pair_fast(const SonarStepParams& p, const FastConsts& c, const NoiseNorm& nn,
                                                const PhiloxStream& st, uint32_t vt, uint32_t k, int64_t li0, int64_t T,
                                                int64_t begin, int64_t end) {
-  float xs[4], ds[4], hs[4];
-  bool ok[4];
-  int64_t idx[4];
+  float xs[LANES], ds[LANES], hs[LANES];
+  bool ok[LANES];
+  int64_t idx[LANES];
 #pragma unroll
-  for (int lane = 0; lane < 4; ++lane) {
+  for (int lane = 0; lane < LANES; ++lane) {
     const int64_t li = li0 + T * lane;
     ok[lane] = FULL || (li >= begin && li < end);
     idx[lane] = ok[lane] ? li - begin : 0;
@@ -289,7 +292,7 @@ __device__ __forceinline__ void step_pair_fast(const SonarStepParams& p, const F
     hs[lane] = HAVE_H ? p.hist_in[idx[lane]] : 0.0f;
   }
   float z[4];
-  if (FULL || ok[2] || ok[3]) {
+  if (LANES == 4 && (FULL || ok[LANES - 2] || ok[LANES - 1])) {
     const float4 z4 = philox_normal4(st, vt, k);
     z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
   } else {  // lanes 2, 3 lie outside the slice: one Box-Muller is enough
@@ -297,7 +300,7 @@ __device__ __forceinline__ void step_pair_fast(const SonarStepParams& p, const F
     z[0] = z2.x; z[1] = z2.y; z[2] = 0.0f; z[3] = 0.0f;
   }
 #pragma unroll
-  for (int lane = 0; lane < 4; ++lane) {
+  for (int lane = 0; lane < LANES; ++lane) {
     if (!ok[lane]) continue;
     const StepElem a =
         step_element_fast<KIND, NEW_MODE, HAVE_H, true>(c, xs[lane], ds[lane], hs[lane], norm_noise_value(z[lane], nn));
@@ -306,8 +309,10 @@ __device__ __forceinline__ void step_pair_fast(const SonarStepParams& p, const F
   }
 }
 
+constexpr int kPhiloxStepBlock = 128;  // finer-grained CTAs: the 1.6-wave tail of 256-thread CTAs costs ~10 %
+
 template <int KIND, bool NEW_MODE, bool HAVE_H>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kPhiloxStepBlock)
 sonar_step_fast_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint32_t k_hi) {
   __shared__ NormDecision nd_slot;
   const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
@@ -324,11 +329,31 @@ sonar_step_fast_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo,
       if (li0 >= end) break;
       if (li0 + 3 * T < begin) continue;
       if (li0 >= begin && li0 + 3 * T < end)
-        step_pair_fast<KIND, NEW_MODE, HAVE_H, true>(p, c, nn, st, (uint32_t)vt, k, li0, T, begin, end);
+        step_pair_fast<KIND, NEW_MODE, HAVE_H, true, 4>(p, c, nn, st, (uint32_t)vt, k, li0, T, begin, end);
       else
-        step_pair_fast<KIND, NEW_MODE, HAVE_H, false>(p, c, nn, st, (uint32_t)vt, k, li0, T, begin, end);
+        step_pair_fast<KIND, NEW_MODE, HAVE_H, false, 4>(p, c, nn, st, (uint32_t)vt, k, li0, T, begin, end);
     }
   }
+}
+
+// Draws of at most two rows (numel_total <= 2T, un-sharded or sharded): k == 0, lanes 0 and 1 only.
+template <int KIND, bool NEW_MODE, bool HAVE_H>
+__global__ void __launch_bounds__(kBlock, 8)
+sonar_step_fast_philox2_kernel(SonarStepParams p, PhiloxStream st) {
+  __shared__ NormDecision nd_slot;
+  const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
+                              ? decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot)
+                              : NormDecision{0.f, 1.f, 0, 0};
+  const NoiseNorm nn = make_noise_norm(nd, p.noise_factor);
+  const FastConsts c = make_fast_consts(p);
+  const int64_t T = st.threads;
+  const int64_t begin = p.noise_begin, end = p.noise_begin + p.n;
+  const int64_t vt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // grid == the emulated ATen grid
+  if (vt >= T || vt >= end || vt + T < begin) return;
+  if (vt >= begin && vt + T < end)
+    step_pair_fast<KIND, NEW_MODE, HAVE_H, true, 2>(p, c, nn, st, (uint32_t)vt, 0u, vt, T, begin, end);
+  else
+    step_pair_fast<KIND, NEW_MODE, HAVE_H, false, 2>(p, c, nn, st, (uint32_t)vt, 0u, vt, T, begin, end);
 }
 
 // ---- Philox variants: CUDA thread <-> virtual ATen thread vt (Philox subsequence), call k ----
@@ -407,9 +432,15 @@ static void launch_fast_vec(const SonarStepParams& p, int grid, cudaStream_t str
 }
 
 template <int KIND, bool NEW_MODE, bool HAVE_H>
-static void launch_fast_philox(const SonarStepParams& p, const PhiloxStream& st, uint32_t k_lo, uint32_t k_hi, int grid,
+static void launch_fast_philox(const SonarStepParams& p, const PhiloxStream& st, uint32_t k_lo, uint32_t k_hi,
                                cudaStream_t stream) {
-  sonar_step_fast_philox_kernel<KIND, NEW_MODE, HAVE_H><<<grid, kBlock, 0, stream>>>(p, st, k_lo, k_hi);
+  const int64_t T = st.threads;
+  if (p.noise_numel_total <= 2 * T) {  // two rows at most: single-wave kernel, grid == emulated ATen grid
+    sonar_step_fast_philox2_kernel<KIND, NEW_MODE, HAVE_H><<<(unsigned)(T / kBlock), kBlock, 0, stream>>>(p, st);
+    return;
+  }
+  const int grid = streaming_grid(T, kPhiloxStepBlock, 1);
+  sonar_step_fast_philox_kernel<KIND, NEW_MODE, HAVE_H><<<grid, kPhiloxStepBlock, 0, stream>>>(p, st, k_lo, k_hi);
 }
 
 // expands to the 8 (kind, mode, history) instantiations of LAUNCH<...>(args)
@@ -461,7 +492,7 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     const int64_t k_lo = (p.noise_begin / T) / 4, k_hi = ((end - 1) / T) / 4;
     const int grid = streaming_grid(T, kBlock, 1);
     if (fast_config(p))
-      SONAR_DISPATCH_FAST(launch_fast_philox, p, p, st, (uint32_t)k_lo, (uint32_t)k_hi, grid, stream);
+      SONAR_DISPATCH_FAST(launch_fast_philox, p, p, st, (uint32_t)k_lo, (uint32_t)k_hi, stream);
     else
       sonar_step_philox_kernel<<<grid, kBlock, 0, stream>>>(p, st, (uint32_t)k_lo, (uint32_t)k_hi);
     SONAR_LAUNCH_CHECK();

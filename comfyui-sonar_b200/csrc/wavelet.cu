@@ -17,11 +17,9 @@
 
 namespace sonar {
 
-__device__ __forceinline__ int extend_index(int i, int n, int mode) {
-  // maps an index of the padded signal (already shifted by the left pad) into [0, n), or -1 (zero)
-  if (i >= 0 && i < n) return i;
+__device__ __forceinline__ int extend_index_wrapped(int i, int n, int mode) {
+  // general case: the index lies more than one signal length outside [0, n)
   switch (mode) {
-    case SONAR_DWT_MODE_ZERO: return -1;
     case SONAR_DWT_MODE_PERIODIC: {
       int m = i % n;
       return m < 0 ? m + n : m;
@@ -42,6 +40,21 @@ __device__ __forceinline__ int extend_index(int i, int n, int mode) {
   }
 }
 
+__device__ __forceinline__ int extend_index(int i, int n, int mode) {
+  // maps an index of the padded signal (already shifted by the left pad) into [0, n), or -1 (zero).
+  // One reflection / wrap covers every tap unless the filter is longer than the signal.
+  if ((unsigned)i < (unsigned)n) return i;
+  if (mode == SONAR_DWT_MODE_ZERO) return -1;
+  int m;
+  if (mode == SONAR_DWT_MODE_PERIODIC)
+    m = i < 0 ? i + n : i - n;
+  else if (mode == SONAR_DWT_MODE_REFLECT)
+    m = i < 0 ? -i : 2 * (n - 1) - i;
+  else
+    m = i < 0 ? -1 - i : 2 * n - 1 - i;
+  return (unsigned)m < (unsigned)n ? m : extend_index_wrapped(i, n, mode);
+}
+
 template <typename T>
 struct Filters {
   T a_lo[SONAR_DWT_MAX_TAPS];  // analysis, already reversed (correlation form)
@@ -59,19 +72,54 @@ struct Filters {
 // One output position (ky, kx) of an analysis level: the four sub-band coefficients of the
 // L x L window at (2ky - pad_t, 2kx - pad_l) of value = pa - pb (pb optional). Rows of the input are
 // `row_stride` elements apart (global planes: W; shared-memory buffers: their own pitch).
-template <typename T, typename Tin>
+// LT > 0: filter length known at compile time (loops fully unrolled, taps addressed with immediates);
+// LT == 0: any even length up to SONAR_DWT_MAX_TAPS at run time.
+template <typename T, typename Tin, int LT>
 __device__ __forceinline__ void analysis_point(const Tin* __restrict__ pa, const Tin* __restrict__ pb, int row_stride,
                                                int H, int W, int ky, int kx, int pad_t, int pad_l, int mode,
                                                const Filters<T>& f, T& acc_ll, T& acc_lh, T& acc_hl, T& acc_hh) {
-  const int L = f.L;
+  const int L = LT > 0 ? LT : f.L;
   acc_ll = 0, acc_lh = 0, acc_hl = 0, acc_hh = 0;
   const int x_first = 2 * kx - pad_l, y_first = 2 * ky - pad_t;
+  if (LT > 0) {
+    // compile-time length: ONE code path for interior and border outputs (a warp almost always holds
+    // both, so a separate slow border path would serialise in front of every interior output).
+    // Tap offsets are resolved once per output: 2L index computations instead of L*L.
+    int ox[LT > 0 ? LT : 1], oy[LT > 0 ? LT : 1];
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+      ox[j] = extend_index(x_first + j, W, mode);
+      const int sy = extend_index(y_first + j, H, mode);
+      oy[j] = sy < 0 ? -1 : sy * row_stride;
+    }
+#pragma unroll
+    for (int jy = 0; jy < LT; ++jy) {
+      T row_lo = 0, row_hi = 0;
+#pragma unroll
+      for (int jx = 0; jx < LT; ++jx) {
+        const bool in = (oy[jy] | ox[jx]) >= 0;  // zero padding: either index negative
+        const int o = in ? oy[jy] + ox[jx] : 0;
+        T v = (T)pa[o];
+        if (pb != nullptr) v -= (T)pb[o];
+        if (!in) v = 0;
+        row_lo += f.a_lo[jx] * v;
+        row_hi += f.a_hi[jx] * v;
+      }
+      acc_ll += f.a_lo[jy] * row_lo;
+      acc_lh += f.a_hi[jy] * row_lo;  // high along H, low along W
+      acc_hl += f.a_lo[jy] * row_hi;  // low along H, high along W
+      acc_hh += f.a_hi[jy] * row_hi;
+    }
+    return;
+  }
   const bool interior = x_first >= 0 && x_first + L <= W && y_first >= 0 && y_first + L <= H;
   if (interior) {  // the whole L x L window lies inside the plane: no boundary extension
-    for (int jy = 0; jy < L; ++jy) {
-      const Tin* ra = pa + (int64_t)(y_first + jy) * row_stride + x_first;
-      const Tin* rb = pb != nullptr ? pb + (int64_t)(y_first + jy) * row_stride + x_first : nullptr;
+    const Tin* ra = pa + (y_first * row_stride + x_first);
+    const Tin* rb = pb != nullptr ? pb + (y_first * row_stride + x_first) : nullptr;
+#pragma unroll
+    for (int jy = 0; jy < L; ++jy, ra += row_stride, rb += (pb != nullptr ? row_stride : 0)) {
       T row_lo = 0, row_hi = 0;
+#pragma unroll
       for (int jx = 0; jx < L; ++jx) {
         T v = (T)ra[jx];
         if (rb != nullptr) v -= (T)rb[jx];
@@ -91,7 +139,7 @@ __device__ __forceinline__ void analysis_point(const Tin* __restrict__ pa, const
       for (int jx = 0; jx < L; ++jx) {
         const int sx = extend_index(x_first + jx, W, mode);
         if (sx < 0) continue;
-        const int64_t o = (int64_t)sy * row_stride + sx;
+        const int o = sy * row_stride + sx;
         T v = (T)pa[o];
         if (pb != nullptr) v -= (T)pb[o];
         row_lo += f.a_lo[jx] * v;
@@ -105,12 +153,12 @@ __device__ __forceinline__ void analysis_point(const Tin* __restrict__ pa, const
   }
 }
 
-template <typename T, typename Tin>
+template <typename T, typename Tin, int LT>
 __global__ void __launch_bounds__(kBlock)
 dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, T* __restrict__ ll,
                      T* __restrict__ hi, int64_t planes, int H, int W, int in_stride_h, int h, int w, int mode,
                      Filters<T> f) {
-  const int L = f.L;
+  const int L = LT > 0 ? LT : f.L;
   const int pad_t = (2 * (h - 1) - H + L) / 2;
   const int pad_l = (2 * (w - 1) - W + L) / 2;
   const int64_t total = planes * (int64_t)h * w;
@@ -122,7 +170,7 @@ dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b,
     const Tin* pa = in_a + plane * (int64_t)in_stride_h * W;
     const Tin* pb = in_b != nullptr ? in_b + plane * (int64_t)in_stride_h * W : nullptr;
     T acc_ll, acc_lh, acc_hl, acc_hh;
-    analysis_point<T, Tin>(pa, pb, W, H, W, ky, kx, pad_t, pad_l, mode, f, acc_ll, acc_lh, acc_hl, acc_hh);
+    analysis_point<T, Tin, LT>(pa, pb, W, H, W, ky, kx, pad_t, pad_l, mode, f, acc_ll, acc_lh, acc_hl, acc_hh);
     const int64_t hw = (int64_t)h * w;
     const int64_t o = (int64_t)ky * w + kx;
     ll[plane * hw + o] = acc_ll;
@@ -150,23 +198,25 @@ struct SynthSet {
 // Accumulates the contribution of one coefficient set to the 2x2 output quad (2qy+py, 2qx+px).
 // pll: approximation band with row pitch ll_pitch; phi: three detail bands, `band_stride` apart, row
 // pitch hi_pitch; (h, w) = valid coefficient extent.
-template <typename T>
+template <typename T, int LT>
 __device__ __forceinline__ void synthesis_quad(const T* __restrict__ pll, int ll_pitch, const T* __restrict__ phi,
                                                int64_t band_stride, int hi_pitch, int h, int w, int qy, int qx, T s_ll,
                                                T s_lh, T s_hl, T s_hh, const Filters<T>& f, T& o00, T& o01, T& o10,
                                                T& o11) {
-  const int L = f.L, half = L >> 1;
+  const int L = LT > 0 ? LT : f.L, half = L >> 1;
+#pragma unroll
   for (int ia = 0; ia < half; ++ia) {
     const int ky = qy + ia;
     if (ky >= h) break;  // only reachable for the cropped-away overhang
     T rl0 = 0, rl1 = 0, rh0 = 0, rh1 = 0;
+#pragma unroll
     for (int ib = 0; ib < half; ++ib) {
       const int kx = qx + ib;
       if (kx >= w) break;
       const int tx = L - 2 - 2 * ib;
       const T glx0 = f.s_lo[tx], glx1 = f.s_lo[tx + 1], ghx0 = f.s_hi[tx], ghx1 = f.s_hi[tx + 1];
-      const int64_t o = (int64_t)ky * hi_pitch + kx;
-      const T v_ll = pll[(int64_t)ky * ll_pitch + kx] * s_ll;
+      const int o = ky * hi_pitch + kx;
+      const T v_ll = pll[ky * ll_pitch + kx] * s_ll;
       const T v_lh = phi[o] * s_lh;                    // high along H, low along W
       const T v_hl = phi[band_stride + o] * s_hl;      // low along H, high along W
       const T v_hh = phi[2 * band_stride + o] * s_hh;
@@ -187,7 +237,7 @@ __device__ __forceinline__ void synthesis_quad(const T* __restrict__ pll, int ll
 // Polyphase form: the 2x2 output quad (2qy+py, 2qx+px) reads the SAME (L/2) x (L/2) window of
 // coefficients k = (qy + a, qx + b); tap index t = p + L - 2 - 2a. Every k of a quad is in range
 // (q <= n - L/2), so the loops carry no boundary tests; rows are combined along W first.
-template <typename T>
+template <typename T, int LT>
 __global__ void __launch_bounds__(kBlock)
 dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, int h, int w, int out_h, int out_w,
                       T* __restrict__ out_t, float* __restrict__ out_f32, int crop_h, int crop_w,
@@ -206,7 +256,7 @@ dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, 
     T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
     for (int s = 0; s < n_sets; ++s) {
       const SynthSet<T>& c = s == 0 ? a : b;
-      synthesis_quad<T>(c.ll + plane * (int64_t)c.ll_stride_h * c.ll_stride_w, c.ll_stride_w, c.hi + plane * 3 * hw, hw, w,
+      synthesis_quad<T, LT>(c.ll + plane * (int64_t)c.ll_stride_h * c.ll_stride_w, c.ll_stride_w, c.hi + plane * 3 * hw, hw, w,
                         h, w, qy, qx, c.s_ll, c.s_lh, c.s_hl, c.s_hh, f, o00, o01, o10, o11);
     }
     const T vals[4] = {o00, o01, o10, o11};
@@ -281,7 +331,7 @@ struct WcfgScales {
   T v[SONAR_WCFG_MAX_LEVELS * 3];  // [level][orientation], fine -> coarse
 };
 
-template <typename T>
+template <typename T, int LT>
 __global__ void __launch_bounds__(kWcfgThreads, 1)
 wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, float* __restrict__ out,
                   const float* __restrict__ addend, float addend_scale, const float* __restrict__ x, float x_scale,
@@ -290,8 +340,9 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
   const T* scale_hi = scales.v;
   extern __shared__ __align__(16) unsigned char wcfg_smem[];
   T* sm = reinterpret_cast<T*>(wcfg_smem);
-  const int L = f.L, J = g.levels;
+  const int L = LT > 0 ? LT : f.L, J = g.levels;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const bool vec2_ok = (W & 1) == 0 && (((uintptr_t)out | (uintptr_t)addend | (uintptr_t)x) & 7u) == 0;
   for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {
     const float* pa = in_a + plane * (int64_t)H * W;
     const float* pb = in_b != nullptr ? in_b + plane * (int64_t)H * W : nullptr;
@@ -307,9 +358,9 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
         const int ky = idx / w, kx = idx - ky * w;
         T c_ll, c_lh, c_hl, c_hh;
         if (j == 0)
-          analysis_point<T, float>(pa, pb, W, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh, c_hl, c_hh);
+          analysis_point<T, float, LT>(pa, pb, W, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh, c_hl, c_hh);
         else
-          analysis_point<T, T>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh,
+          analysis_point<T, T, LT>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh,
                                c_hl, c_hh);
         ll[idx] = c_ll;
         hi[idx] = c_lh;
@@ -334,8 +385,31 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       for (int idx = tid; idx < qh * qw; idx += nthr) {
         const int qy = idx / qw, qx = idx - qy * qw;
         T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-        synthesis_quad<T>(ll, ll_pitch, hi, (int64_t)h * w, w, h, w, qy, qx, s_ll, s_lh, s_hl, s_hh, f, o00, o01, o10, o11);
+        synthesis_quad<T, LT>(ll, ll_pitch, hi, (int64_t)h * w, w, h, w, qy, qx, s_ll, s_lh, s_hl, s_hh, f, o00, o01, o10, o11);
         const T vals[4] = {o00, o01, o10, o11};
+        if (j == 0 && vec2_ok) {
+          // final level, even width: the quad's two rows are 8-byte aligned float2 accesses
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int iy = 2 * qy + r;
+            if (iy >= oh) continue;
+            const int64_t o = (plane * H + iy) * (int64_t)W + 2 * qx;
+            T r0 = vals[2 * r], r1 = vals[2 * r + 1];
+            if (addend != nullptr) {
+              const float2 ad = *reinterpret_cast<const float2*>(addend + o);
+              r0 += (T)addend_scale * (T)ad.x;
+              r1 += (T)addend_scale * (T)ad.y;
+            }
+            float2 res = make_float2((float)((T)recon_sign * r0), (float)((T)recon_sign * r1));
+            if (x != nullptr) {
+              const float2 xv = *reinterpret_cast<const float2*>(x + o);
+              res.x = x_scale * xv.x + res.x;
+              res.y = x_scale * xv.y + res.y;
+            }
+            *reinterpret_cast<float2*>(out + o) = res;
+          }
+          continue;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int iy = 2 * qy + (q >> 1), ix = 2 * qx + (q & 1);
@@ -373,18 +447,36 @@ Filters<T> make_filters(const SonarWaveletFilters* wf) {
   return f;
 }
 
+// compile-time filter lengths with their own instantiation (haar, db2, db3, db4); others run the generic loops
+#define SONAR_DISPATCH_TAPS(len, CALL) \
+  switch (len) {                       \
+    case 2: CALL(2); break;            \
+    case 4: CALL(4); break;            \
+    case 6: CALL(6); break;            \
+    case 8: CALL(8); break;            \
+    default: CALL(0); break;           \
+  }
+
 template <typename T>
 int launch_analysis(const SonarDwtAnalysisParams& p, cudaStream_t stream) {
   const Filters<T> f = make_filters<T>(&p.filters);
   const int64_t total = p.planes * (int64_t)p.h * p.w;
   const int grid = streaming_grid(total, kBlock, 4);
-  if (p.in_is_f32)
-    dwt2_analysis_kernel<T, float><<<grid, kBlock, 0, stream>>>((const float*)p.in_a, (const float*)p.in_b, (T*)p.ll,
-                                                                (T*)p.hi, p.planes, p.H, p.W, p.H, p.h, p.w, p.mode, f);
-  else
-    dwt2_analysis_kernel<T, T><<<grid, kBlock, 0, stream>>>((const T*)p.in_a, (const T*)p.in_b, (T*)p.ll, (T*)p.hi,
-                                                            p.planes, p.H, p.W, p.in_stride_h > 0 ? p.in_stride_h : p.H,
-                                                            p.h, p.w, p.mode, f);
+  if ((int64_t)(p.in_stride_h > p.H ? p.in_stride_h : p.H) * p.W >= (1ll << 31)) return (int)cudaErrorInvalidValue;
+#define ANALYSIS_F32(LT)                                                                                            \
+  dwt2_analysis_kernel<T, float, LT><<<grid, kBlock, 0, stream>>>((const float*)p.in_a, (const float*)p.in_b, (T*)p.ll, \
+                                                                  (T*)p.hi, p.planes, p.H, p.W, p.H, p.h, p.w, p.mode, f)
+#define ANALYSIS_T(LT)                                                                                          \
+  dwt2_analysis_kernel<T, T, LT><<<grid, kBlock, 0, stream>>>((const T*)p.in_a, (const T*)p.in_b, (T*)p.ll, (T*)p.hi, \
+                                                              p.planes, p.H, p.W, p.in_stride_h > 0 ? p.in_stride_h : p.H, \
+                                                              p.h, p.w, p.mode, f)
+  if (p.in_is_f32) {
+    SONAR_DISPATCH_TAPS(p.filters.length, ANALYSIS_F32)
+  } else {
+    SONAR_DISPATCH_TAPS(p.filters.length, ANALYSIS_T)
+  }
+#undef ANALYSIS_F32
+#undef ANALYSIS_T
   SONAR_LAUNCH_CHECK();
   return 0;
 }
@@ -406,12 +498,16 @@ int launch_synthesis(const SonarDwtSynthesisParams& p, cudaStream_t stream) {
   const int out_h = 2 * p.h - p.filters.length + 2, out_w = 2 * p.w - p.filters.length + 2;
   const bool final_level = p.out_f32 != nullptr;
   if (final_level && (p.crop_h > out_h || p.crop_w > out_w)) return (int)cudaErrorInvalidValue;
+  if ((int64_t)p.ll_rows[0] * p.ll_cols[0] >= (1ll << 31)) return (int)cudaErrorInvalidValue;
   const int oh = final_level ? p.crop_h : out_h, ow = final_level ? p.crop_w : out_w;
   const int64_t total = p.planes * (int64_t)((oh + 1) / 2) * ((ow + 1) / 2);  // one thread per 2x2 output quad
   const int grid = streaming_grid(total, kBlock, 4);
-  dwt2_synthesis_kernel<T><<<grid, kBlock, 0, stream>>>(sets[0], sets[1], p.n_sets, p.planes, p.h, p.w, out_h, out_w,
-                                                        (T*)p.out, p.out_f32, p.crop_h, p.crop_w, p.addend,
-                                                        p.addend_scale, p.x, p.x_scale, p.recon_sign, f);
+#define SYNTHESIS(LT)                                                                                               \
+  dwt2_synthesis_kernel<T, LT><<<grid, kBlock, 0, stream>>>(sets[0], sets[1], p.n_sets, p.planes, p.h, p.w, out_h, out_w, \
+                                                            (T*)p.out, p.out_f32, p.crop_h, p.crop_w, p.addend,         \
+                                                            p.addend_scale, p.x, p.x_scale, p.recon_sign, f)
+  SONAR_DISPATCH_TAPS(p.filters.length, SYNTHESIS)
+#undef SYNTHESIS
   SONAR_LAUNCH_CHECK();
   return 0;
 }
@@ -423,12 +519,17 @@ int launch_wcfg_fused(const SonarWcfgFusedParams& p, const WcfgGeom& g, cudaStre
   WcfgScales<T> sc;
   for (int j = 0; j < SONAR_WCFG_MAX_LEVELS; ++j)
     for (int o = 0; o < 3; ++o) sc.v[3 * j + o] = j < p.levels ? (T)p.scale_hi[j][o] : (T)0;
-  SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const DeviceInfo& di = device_info();
   const int grid = (int)(p.planes < di.sm_count ? p.planes : di.sm_count);
-  wcfg_fused_kernel<T><<<grid, kWcfgThreads, smem, stream>>>(
-      p.in_a, p.in_b, p.out, p.addend, p.addend_scale, p.x, p.x_scale, p.recon_sign, p.planes, p.H, p.W, p.mode, g,
-      (T)p.scale_ll, sc, f);
+#define WCFG_FUSED(LT)                                                                                              \
+  do {                                                                                                              \
+    SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_fused_kernel<T, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    wcfg_fused_kernel<T, LT><<<grid, kWcfgThreads, smem, stream>>>(p.in_a, p.in_b, p.out, p.addend, p.addend_scale, p.x, \
+                                                                   p.x_scale, p.recon_sign, p.planes, p.H, p.W, p.mode, g, \
+                                                                   (T)p.scale_ll, sc, f);                           \
+  } while (0)
+  SONAR_DISPATCH_TAPS(p.filters.length, WCFG_FUSED)
+#undef WCFG_FUSED
   SONAR_LAUNCH_CHECK();
   return 0;
 }

@@ -236,19 +236,20 @@ class PerlinOldNoiseGenerator(FramesToChannelsNoiseGenerator):
 
     def generate(self, *_args):
         hostutil.blend_mode_id(self.blend_mode)  # validates like BLENDING_MODES[...] would
-        base = self.rand_like(fun="uniform")
-        b, c, h, w = base.shape
-        angles = [
-            rng.uniform(
-                (c, h + 1, w + 1),
-                device=self.device,
-                generator=self.device_generator(),
-                low=0.0,
-                high=2.0 * math.pi,
-                batch_sharded=False,
-            )
-            for _ in range(self.iterations)
-        ]
+        with rng.batched():  # base + angle grids: one launch
+            base = self.rand_like(fun="uniform")
+            b, c, h, w = base.shape
+            angles = [
+                rng.uniform(
+                    (c, h + 1, w + 1),
+                    device=self.device,
+                    generator=self.device_generator(),
+                    low=0.0,
+                    high=2.0 * math.pi,
+                    batch_sharded=False,
+                )
+                for _ in range(self.iterations)
+            ]
         if base.dtype != torch.float32:
             base = base.float()
         noise = ops.perlin_accumulate(base, angles, shape=(b, c, h, w), div_fac=self.div_fac, blend_mode=self.blend_mode)
@@ -276,20 +277,21 @@ class PyramidNoiseGenerator(_PyramidBase):
         return super().ng_params() | {"discount": 0.7, "upscale_mode": "bilinear", "iterations": 10}
 
     def generate(self, *_args):
-        base = self.rand_like()
-        b, c, h, w = base.shape
-        orig_h, orig_w = h, w
-        host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
         levels, weights = [], []
-        for i in range(self.iterations):
-            # level size from one CPU-generator draw per level, exactly like the reference (:626-648):
-            # r = U(0,1)*2+2, cumulative int division, stop at a 1-pixel side (level 0 is full size)
-            r = rng.host_rand(1, host_gen).item() * 2 + 2
-            w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
-            levels.append(rng.normal((b, c, h, w), device=self.device, dtype=base.dtype, generator=self.device_generator()))
-            weights.append(self.discount**i)
-            if w == 1 or h == 1:
-                break
+        with rng.batched():  # base + every level: one launch
+            base = self.rand_like()
+            b, c, h, w = base.shape
+            orig_h, orig_w = h, w
+            host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
+            for i in range(self.iterations):
+                # level size from one CPU-generator draw per level, exactly like the reference (:626-648):
+                # r = U(0,1)*2+2, cumulative int division, stop at a 1-pixel side (level 0 is full size)
+                r = rng.host_rand(1, host_gen).item() * 2 + 2
+                w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
+                levels.append(rng.normal((b, c, h, w), device=self.device, dtype=base.dtype, generator=self.device_generator()))
+                weights.append(self.discount**i)
+                if w == 1 or h == 1:
+                    break
         return self.fix_output_frames(self._accumulate(base, levels, weights, orig_h, orig_w))
 
 
@@ -319,13 +321,14 @@ class HighresPyramidNoiseGenerator(_PyramidBase):
         host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
         rs = rng.host_rand(self.iterations, host_gen) * 2 + 2
         levels, weights = [], []
-        for i in range(self.iterations):
-            r = rs[i].item()
-            h, w = min(orig_h * 15, int(h * (r**i))), min(orig_w * 15, int(w * (r**i)))
-            levels.append(rng.normal((b, c, h, w), device=self.device, generator=self.device_generator()))
-            weights.append(self.discount**i)
-            if h >= orig_h * 15 or w >= orig_w * 15:
-                break
+        with rng.batched():
+            for i in range(self.iterations):
+                r = rs[i].item()
+                h, w = min(orig_h * 15, int(h * (r**i))), min(orig_w * 15, int(w * (r**i)))
+                levels.append(rng.normal((b, c, h, w), device=self.device, generator=self.device_generator()))
+                weights.append(self.discount**i)
+                if h >= orig_h * 15 or w >= orig_w * 15:
+                    break
         return self.fix_output_frames(self._accumulate(base.contiguous(), levels, weights, orig_h, orig_w))
 
 
@@ -345,12 +348,13 @@ class PyramidOldNoiseGenerator(_PyramidBase):
         b, c, h, w = self.get_adjusted_shape()
         levels, weights = [], []
         r = 1
-        for i in range(self.iterations):
-            r *= 2
-            levels.append(
-                rng.normal((b, c, h * r, w * r), device=self.device, generator=self.device_generator(), std=0.5**i),
-            )
-            weights.append(self.discount**i)
+        with rng.batched():
+            for i in range(self.iterations):
+                r *= 2
+                levels.append(
+                    rng.normal((b, c, h * r, w * r), device=self.device, generator=self.device_generator(), std=0.5**i),
+                )
+                weights.append(self.discount**i)
         # the reference accumulates into zeros: 0 + level*w is exact, so no base tensor is needed
         return self.fix_output_frames(self._accumulate(None, levels, weights, h, w).to(self.dtype))
 

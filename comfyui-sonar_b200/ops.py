@@ -156,6 +156,31 @@ def philox_fill(
     return out
 
 
+def philox_fill_batch(items: Sequence[tuple]) -> None:
+    """Materialises several draws with one launch per 16 draws of the same seed and device.
+    items: (draw, out, kind, p0, p1, begin) as for philox_fill."""
+    groups: dict = {}
+    for it in items:
+        if it[1].numel():
+            groups.setdefault((it[1].device, it[0].seed), []).append(it)
+    for (_dev, seed), group in groups.items():
+        for first in range(0, len(group), _native.FILL_BATCH_MAX):
+            chunk = group[first : first + _native.FILL_BATCH_MAX]
+            if len(chunk) == 1:
+                draw, out, kind, p0, p1, begin = chunk[0]
+                philox_fill(draw, out, kind=kind, p0=p0, p1=p1, begin=begin)
+                continue
+            b = _native.SonarFillBatch()
+            b.n, b.seed = len(chunk), seed
+            for d, (draw, out, kind, p0, p1, begin) in zip(b.draws, chunk):
+                d.out, d.begin = out.data_ptr(), begin
+                d.count = out.numel() * (2 if out.is_complex() else 1)
+                d.numel_total, d.offset, d.grid_blocks = draw.numel, draw.offset, draw.grid_blocks
+                d.kind, d.p0, d.p1 = (0 if kind == "normal" else 1), p0, p1
+            lib, stream = _prepare(*(it[1] for it in chunk))
+            _launch("sonar_philox_fill_batch", lib.sonar_philox_fill_batch, ctypes.byref(b), stream)
+
+
 def randn(
     shape: Sequence[int],
     *,

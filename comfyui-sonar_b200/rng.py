@@ -45,6 +45,37 @@ def _take_injected(shape: Sequence[int], device: torch.device, dtype: torch.dtyp
     return t.to(device=device, dtype=dtype).contiguous().clone()
 
 
+_PENDING: list | None = None
+
+
+@contextlib.contextmanager
+def batched() -> Iterator[None]:
+    """Draws requested inside the block are reserved on the generator immediately (order and offsets
+    exactly as without batching) but materialised together, by ONE launch, when the block exits.
+    The returned tensors must not be read by a kernel before that."""
+    global _PENDING  # noqa: PLW0603
+    if _PENDING is not None:  # nested: the outermost block flushes
+        yield
+        return
+    _PENDING = []
+    try:
+        yield
+    finally:
+        pending, _PENDING = _PENDING, None
+        if pending:
+            ops.philox_fill_batch(pending)
+
+
+@contextlib.contextmanager
+def _unbatched() -> Iterator[None]:
+    global _PENDING  # noqa: PLW0603
+    saved, _PENDING = _PENDING, None
+    try:
+        yield
+    finally:
+        _PENDING = saved
+
+
 def _fill(shape, device, dtype, generator, kind, p0, p1, batch_sharded) -> torch.Tensor:
     out = torch.empty(tuple(shape), device=device, dtype=dtype)
     if out.numel() == 0:
@@ -52,6 +83,9 @@ def _fill(shape, device, dtype, generator, kind, p0, p1, batch_sharded) -> torch
     floats_per_el = 2 if dtype == torch.complex64 else 1
     total, begin = parallel.global_draw_geometry(shape) if batch_sharded else (out.numel(), 0)
     draw = ops.reserve_draw(total * floats_per_el, out.device, generator)
+    if _PENDING is not None:
+        _PENDING.append((draw, out, kind, p0, p1, begin * floats_per_el))
+        return out
     return ops.philox_fill(draw, out, kind=kind, p0=p0, p1=p1, begin=begin * floats_per_el)
 
 
@@ -71,9 +105,10 @@ def normal(
     if inj is not None:
         return inj
     if dtype not in {torch.float32, torch.complex64}:
-        return normal(
-            shape, device=device, dtype=torch.float32, generator=generator, std=std, batch_sharded=batch_sharded,
-        ).to(dtype)
+        with _unbatched():  # the cast reads the draw right away
+            return normal(
+                shape, device=device, dtype=torch.float32, generator=generator, std=std, batch_sharded=batch_sharded,
+            ).to(dtype)
     eff = std / math.sqrt(2.0) if dtype == torch.complex64 else std
     return _fill(shape, device, dtype, generator, "normal", 0.0, float(eff), batch_sharded)
 
@@ -93,9 +128,10 @@ def uniform(
     if inj is not None:
         return inj
     if dtype != torch.float32:
-        return uniform(
-            shape, device=device, generator=generator, low=low, high=high, batch_sharded=batch_sharded,
-        ).to(dtype)
+        with _unbatched():
+            return uniform(
+                shape, device=device, generator=generator, low=low, high=high, batch_sharded=batch_sharded,
+            ).to(dtype)
     return _fill(shape, device, dtype, generator, "uniform", float(low), float(high), batch_sharded)
 
 

@@ -49,6 +49,28 @@ int sonar_philox_normal_f32(float* out, int64_t begin, int64_t count, int64_t nu
 int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
                              uint64_t offset, uint32_t grid_blocks, float from, float to, void* stream);
 
+/* Several draws in one launch (a pyramid sample = base + every level; a Perlin sample = base + angle
+ * grids). Each draw keeps its own geometry / offset / transform (kind 0: normal with mean p0, std p1;
+ * kind 1: uniform on [p0, p1)), so the values equal those of separate calls; all share `seed`. */
+#define SONAR_FILL_BATCH_MAX 16
+typedef struct SonarFillDesc {
+  float* out;
+  int64_t begin;
+  int64_t count;
+  int64_t numel_total;
+  uint64_t offset;
+  uint32_t grid_blocks;
+  int32_t kind;
+  float p0;
+  float p1;
+} SonarFillDesc;
+typedef struct SonarFillBatch {
+  int32_t n;
+  uint64_t seed;
+  SonarFillDesc draws[SONAR_FILL_BATCH_MAX];
+} SonarFillBatch;
+int sonar_philox_fill_batch(const SonarFillBatch* batch_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Global moments and scale_noise.
  * replaces: scale_noise                                    py/utils.py:85-106

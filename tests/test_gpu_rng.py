@@ -1,6 +1,8 @@
 """Bit-exact parity of the device Philox generators with torch's own CUDA generators."""
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -107,3 +109,36 @@ def test_empty_and_errors(sb, cuda):
         sb.ops.moments(torch.zeros(4))  # CPU tensor: no fallback
     with pytest.raises(TypeError):
         sb.ops.randn((4,), device=cuda, dtype=torch.float16)
+
+
+def test_batched_draws_equal_separate_torch_draws(sb, cuda):
+    """rng.batched(): several draws reserved in order, materialised by ONE launch, still bit-identical
+    to the sequence of torch calls (different sizes, kinds, transforms; more than 16 draws)."""
+    shapes = [(16, 16, 128, 128), (16, 16, 36, 36), (16, 16, 7, 7), (16, 16, 1, 1), (3, 5), (16, 129, 129)]
+    torch.manual_seed(2024)
+    want = []
+    for i in range(20):
+        shp = shapes[i % len(shapes)]
+        if i % 3 == 0:
+            want.append(torch.empty(shp, device=cuda).uniform_(0.0, 2.0 * math.pi))
+        elif i % 3 == 1:
+            want.append(torch.randn(shp, device=cuda))
+        else:
+            want.append(torch.randn(shp, device=cuda, dtype=torch.complex64))
+    off_want = torch.cuda.default_generators[0].get_offset()
+    torch.manual_seed(2024)
+    launches = sb.ops.LAUNCH_COUNT
+    got = []
+    with sb.rng.batched():
+        for i in range(20):
+            shp = shapes[i % len(shapes)]
+            if i % 3 == 0:
+                got.append(sb.rng.uniform(shp, device=cuda, low=0.0, high=2.0 * math.pi))
+            elif i % 3 == 1:
+                got.append(sb.rng.normal(shp, device=cuda))
+            else:
+                got.append(sb.rng.normal(shp, device=cuda, dtype=torch.complex64))
+    assert sb.ops.LAUNCH_COUNT - launches == 2  # 16 + 4 draws
+    assert torch.cuda.default_generators[0].get_offset() == off_want
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert torch.equal(g, w), f"draw {i}"
