@@ -30,6 +30,7 @@ One bench "step" = one 30-step sampling run over one batch. Metric: latent noise
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -346,6 +347,8 @@ def run_b200_arm(args) -> None:
     barrier()
     launches0 = sb.ops.LAUNCH_COUNT
     timers = []
+    gc.collect()
+    gc.disable()  # a collection pause between two launches would show up as device idle time
     with ClockSampler(local_rank) as clocks:
         t_wall = time.perf_counter()
         for _ in range(args.steps):
@@ -360,6 +363,7 @@ def run_b200_arm(args) -> None:
         while time.perf_counter() < t_end:
             one_run(warm_model, x0)
         torch.cuda.synchronize()
+    gc.enable()
     launches = sb.ops.LAUNCH_COUNT - launches0
     run_ms = [t.total_ms() for t in timers]
     ms_per_step = statistics.mean(run_ms)
@@ -382,6 +386,8 @@ def run_b200_arm(args) -> None:
     # ---------------- end to end through the public API with host buffers ----------------
     e2e_times = []
     e2e_model = StepTimer(dev, flush_bytes=0, timed=False)
+    gc.collect()
+    gc.disable()
     for i in range(3 + args.steps):
         barrier()
         t0 = time.perf_counter()
@@ -395,6 +401,7 @@ def run_b200_arm(args) -> None:
         if i >= 3:
             e2e_times.append(time.perf_counter() - t0)
         del out_host
+    gc.enable()
     e2e_s = statistics.mean(e2e_times)
     t_dev = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:

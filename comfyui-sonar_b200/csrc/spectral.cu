@@ -310,6 +310,310 @@ spectral_plane_kernel(SpectralLaunch L) {
   commit_moments(p.sums, p.sums_clear, ms, mss);
 }
 
+// =============================================================================================
+// Batched-lane variant for the hot case (half spectrum in, even W, radices 2/3/4/5): every FFT stage
+// is ONE pass of the whole CTA over the whole plane, with the lanes of a warp running the SAME
+// butterfly of 32 different transforms (columns: 32 adjacent k, contiguous in shared memory; rows: 32
+// rows, conflict-free thanks to the odd pitch). Twiddles and output offsets are warp-uniform, there
+// is no per-lane index arithmetic, no idle lanes for short transforms and no per-warp scratch.
+// Rows use the half-length c2r trick: for Hermitian X of even length W, with M = W/2,
+//   Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W},   k = 0..M-1
+//   z = sum_k Z[k] e^{+2 pi i k n / M}  ==>  x[2n] = Re z[n], x[2n+1] = Im z[n]
+// which also reproduces irfft2's treatment of the reference's NON-Hermitian input (the imaginary
+// parts of the k = 0 and k = M bins are dropped, nothing else of the upper half is read).
+// The round-1 warp-per-transform kernel needed ~237 issued instructions per output element at
+// 90x160 (ncu: 62 % issue-slot busy, instruction bound); this form needs ~50.
+// =============================================================================================
+constexpr int kBatchedThreads = 1024;
+constexpr int kBatchedMaxStages = 16;
+
+struct AxisPlan {
+  int n;
+  int n_stages;
+  int radix[kBatchedMaxStages];
+  int ns[kBatchedMaxStages];
+  int tab_off[kBatchedMaxStages];  // offset of the stage's butterfly table
+  int tab_size;
+};
+
+struct SpectralBatchedLaunch {
+  SonarSpectralParams p;
+  AxisPlan col;  // length H
+  AxisPlan row;  // length M = W / 2
+  int wh;        // M + 1
+  int pitch;     // odd, >= wh
+};
+
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {  // a * conj(w)
+  return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
+}
+
+// butterfly table of one axis: for butterfly j of stage f, .x = output base (j / Ns) * Ns * R + (j % Ns),
+// .y = twiddle base (j % Ns) * N / (Ns * R). Built once per CTA so the stage loops hold no division.
+__device__ void build_axis_table(const AxisPlan& plan, ushort2* __restrict__ tab) {
+  for (int f = 0; f < plan.n_stages; ++f) {
+    const int R = plan.radix[f], Ns = plan.ns[f], nb = plan.n / R, unit = plan.n / (Ns * R);
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+      const int k0 = j % Ns;
+      tab[plan.tab_off[f] + j] = make_ushort2((unsigned short)((j / Ns) * Ns * R + k0), (unsigned short)(k0 * unit));
+    }
+  }
+}
+
+// Where a stage reads its inputs from.
+enum StageSource : int {
+  SRC_SMEM = 0,      // the other ping-pong buffer
+  SRC_SPECTRUM = 1,  // first column stage: global half spectrum (.) gain mask
+  SRC_FOLD = 2       // first row stage: Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W}
+};
+
+struct StageIo {
+  const float2* src;   // SRC_SMEM / SRC_FOLD: shared-memory buffer; SRC_SPECTRUM: global plane
+  const float* mask;   // SRC_SPECTRUM
+  const float2* tw_w;  // SRC_FOLD
+  int M;               // SRC_FOLD
+  int src_pitch;       // SRC_SPECTRUM: row length of the global plane (Wh)
+};
+
+template <int SOURCE>
+__device__ __forceinline__ float2 stage_load(const StageIo& io, int t, int b, int stride_t, int stride_b) {
+  if (SOURCE == SRC_SPECTRUM) {  // t = row y, b = column k of the global plane
+    const int o = t * io.src_pitch + b;
+    float2 v = io.src[o];
+    if (io.mask != nullptr) {
+      const float g = __ldg(io.mask + o);
+      v.x *= g;
+      v.y *= g;
+    }
+    return v;
+  }
+  if (SOURCE == SRC_FOLD) {  // t = k, b = row y
+    const float2* r = io.src + b * stride_b;
+    float2 xk = r[t], xm = r[io.M - t];
+    if (t == 0) {  // c2r ignores the imaginary parts of the DC and Nyquist bins
+      xk.y = 0.0f;
+      xm.y = 0.0f;
+    }
+    const float2 a = make_float2(xk.x + xm.x, xk.y - xm.y);  // X[k] + conj X[M-k]
+    const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);  // X[k] - conj X[M-k]
+    const float2 bt = cmul(d, io.tw_w[t]);
+    return make_float2(a.x - bt.y, a.y + bt.x);  // A + i B
+  }
+  return io.src[t * stride_t + b * stride_b];
+}
+
+// One inverse Stockham stage over a batch of transforms. Element t of transform b lives at
+// t * stride_t + b * stride_b. The CTA's warps form a (chunk, butterfly) grid: a warp runs butterfly
+// j for the 32 transforms of its chunk, so twiddles and offsets are warp-uniform table reads.
+template <int SOURCE>
+__device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2* __restrict__ dst, int N, int R, int Ns,
+                                                      const float2* __restrict__ tw, const ushort2* __restrict__ tab,
+                                                      int nbatch, int stride_t, int stride_b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nb = N / R, nchunks = (nbatch + 31) >> 5;
+  const int cw = nchunks < nwarps ? nchunks : nwarps;  // warps along the chunk axis
+  const int jw = nwarps / cw;                          // warps along the butterfly axis
+  const int wj = warp / cw, wc = warp - wj * cw;
+  if (wj >= jw) return;  // nwarps % cw leftover warps idle for this stage
+  for (int c = wc; c < nchunks; c += cw) {
+    const int b = (c << 5) + lane;
+    if (b >= nbatch) continue;
+    for (int j = wj; j < nb; j += jw) {
+      const ushort2 e = tab[j];
+      const int tb = e.y;
+      float2* out = dst + (int)e.x * stride_t + b * stride_b;
+      const int out_step = Ns * stride_t;
+      if (R == 4) {
+        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
+        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
+        const float2 v2 = cmul_conj(stage_load<SOURCE>(io, j + 2 * nb, b, stride_t, stride_b), tw[2 * tb]);
+        const float2 v3 = cmul_conj(stage_load<SOURCE>(io, j + 3 * nb, b, stride_t, stride_b), tw[3 * tb]);
+        const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3);
+        const float2 d = csub(v1, v3);
+        const float2 a3 = make_float2(-d.y, d.x);  // * (+i)
+        out[0] = cadd(a0, a2);
+        out[out_step] = cadd(a1, a3);
+        out[2 * out_step] = csub(a0, a2);
+        out[3 * out_step] = csub(a1, a3);
+      } else if (R == 2) {
+        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
+        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
+        out[0] = cadd(v0, v1);
+        out[out_step] = csub(v0, v1);
+      } else if (R == 3) {
+        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
+        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
+        const float2 v2 = cmul_conj(stage_load<SOURCE>(io, j + 2 * nb, b, stride_t, stride_b), tw[2 * tb]);
+        const float2 t1 = cadd(v1, v2);
+        const float2 t2 = make_float2(v0.x - 0.5f * t1.x, v0.y - 0.5f * t1.y);
+        const float2 d = csub(v1, v2);
+        const float2 t3 = make_float2(-0.86602540378443865f * d.y, 0.86602540378443865f * d.x);
+        out[0] = cadd(v0, t1);
+        out[out_step] = cadd(t2, t3);
+        out[2 * out_step] = csub(t2, t3);
+      } else {  // R == 5
+        constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+        constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
+        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
+        const float2 v2 = cmul_conj(stage_load<SOURCE>(io, j + 2 * nb, b, stride_t, stride_b), tw[2 * tb]);
+        const float2 v3 = cmul_conj(stage_load<SOURCE>(io, j + 3 * nb, b, stride_t, stride_b), tw[3 * tb]);
+        const float2 v4 = cmul_conj(stage_load<SOURCE>(io, j + 4 * nb, b, stride_t, stride_b), tw[4 * tb]);
+        const float2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), b1 = csub(v1, v4), b2 = csub(v2, v3);
+        const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
+        const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
+        const float2 e1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+        const float2 e2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+        const float2 n1 = make_float2(-e1.y, e1.x), n2 = make_float2(-e2.y, e2.x);  // * (+i)
+        out[0] = make_float2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
+        out[out_step] = cadd(m1, n1);
+        out[2 * out_step] = cadd(m2, n2);
+        out[3 * out_step] = csub(m2, n2);
+        out[4 * out_step] = csub(m1, n1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBatchedThreads, 1)
+spectral_batched_kernel(SpectralBatchedLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SonarSpectralParams& p = L.p;
+  const int H = p.H, W = p.W, M = W >> 1, Wh = L.wh, P = L.pitch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float2* tw_h = reinterpret_cast<float2*>(smem_raw);  // e^{-2 pi i k / H}
+  float2* tw_m = tw_h + H;                             // e^{-2 pi i k / M}
+  float2* tw_w = tw_m + M;                             // e^{+2 pi i k / W}, k < M
+  float2* buf0 = tw_w + M;
+  float2* buf1 = buf0 + (size_t)H * P;
+  ushort2* tab_col = reinterpret_cast<ushort2*>(buf1 + (size_t)H * P);
+  ushort2* tab_row = tab_col + L.col.tab_size;
+  build_axis_table(L.col, tab_col);
+  build_axis_table(L.row, tab_row);
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    double sn, cs;
+    sincospi(-2.0 * (double)k / (double)H, &sn, &cs);
+    tw_h[k] = make_float2((float)cs, (float)sn);
+  }
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    double sn, cs;
+    sincospi(-2.0 * (double)k / (double)M, &sn, &cs);
+    tw_m[k] = make_float2((float)cs, (float)sn);
+    sincospi(2.0 * (double)k / (double)W, &sn, &cs);
+    tw_w[k] = make_float2((float)cs, (float)sn);
+  }
+  __syncthreads();
+  float ms = 0.0f, mss = 0.0f;
+  for (int64_t plane = blockIdx.x; plane < p.planes; plane += gridDim.x) {
+    // ---- columns: inverse complex FFT of length H, batch = Wh columns (lanes = adjacent k). The first
+    // stage reads the global half spectrum (coalesced along k) and applies the gain on the fly. ----
+    float2* cur = buf1;  // "previous" buffer; the first stage ignores it
+    float2* oth = buf0;
+    StageIo io;
+    io.mask = p.mask;
+    io.tw_w = tw_w;
+    io.M = M;
+    io.src_pitch = Wh;
+    for (int f = 0; f < L.col.n_stages; ++f) {
+      if (f == 0) {
+        io.src = reinterpret_cast<const float2*>(p.in_spec) + plane * (int64_t)H * Wh;
+        batched_stage_inverse<SRC_SPECTRUM>(io, oth, H, L.col.radix[0], L.col.ns[0], tw_h, tab_col, Wh, P, 1);
+      } else {
+        io.src = cur;
+        batched_stage_inverse<SRC_SMEM>(io, oth, H, L.col.radix[f], L.col.ns[f], tw_h, tab_col + L.col.tab_off[f], Wh, P, 1);
+      }
+      __syncthreads();
+      float2* t = cur;
+      cur = oth;
+      oth = t;
+    }
+    // ---- rows: inverse complex FFT of length M, batch = H rows (lanes = 32 rows, odd pitch). The first
+    // stage folds the Hermitian half row into M complex points while loading. ----
+    for (int f = 0; f < L.row.n_stages; ++f) {
+      io.src = cur;
+      if (f == 0)
+        batched_stage_inverse<SRC_FOLD>(io, oth, M, L.row.radix[0], L.row.ns[0], tw_m, tab_row, H, 1, P);
+      else
+        batched_stage_inverse<SRC_SMEM>(io, oth, M, L.row.radix[f], L.row.ns[f], tw_m, tab_row + L.row.tab_off[f], H, 1, P);
+      __syncthreads();
+      float2* t = cur;
+      cur = oth;
+      oth = t;
+    }
+    // ---- store: x[y][2n], x[y][2n+1] = z[y][n] * scale, coalesced float2, moments on the fly ----
+    float* dst = p.out + plane * (int64_t)H * W;
+    for (int y = warp; y < H; y += nwarps) {
+      for (int n = lane; n < M; n += 32) {
+        const float2 z = cur[y * P + n];
+        const float2 o = make_float2(z.x * p.out_scale, z.y * p.out_scale);
+        *reinterpret_cast<float2*>(dst + y * W + 2 * n) = o;
+        ms += o.x + o.y;
+        mss += o.x * o.x + o.y * o.y;
+      }
+    }
+    __syncthreads();  // the next plane's first stage overwrites a buffer this pass reads
+  }
+  commit_moments(p.sums, p.sums_clear, ms, mss);
+}
+
+static bool make_axis_plan(int n, AxisPlan* plan) {
+  plan->n = n;
+  plan->n_stages = 0;
+  plan->tab_size = 0;
+  if (n > 65535) return false;
+  int rem = n, ns = 1;
+  auto push = [&](int r) {
+    if (plan->n_stages >= kBatchedMaxStages) return false;
+    plan->radix[plan->n_stages] = r;
+    plan->ns[plan->n_stages] = ns;
+    plan->tab_off[plan->n_stages] = plan->tab_size;
+    plan->tab_size += n / r;
+    ++plan->n_stages;
+    ns *= r;
+    return true;
+  };
+  while (rem % 4 == 0) {
+    if (!push(4)) return false;
+    rem /= 4;
+  }
+  for (int r : {2, 3, 5})
+    while (rem % r == 0) {
+      if (!push(r)) return false;
+      rem /= r;
+    }
+  return rem == 1;  // any other prime factor: the generic kernel handles it
+}
+
+static size_t batched_smem_bytes(int H, int W, const AxisPlan& col, const AxisPlan& row) {
+  const int M = W / 2, wh = M + 1, pitch = wh | 1;
+  return ((size_t)H + 2 * (size_t)M + 2 * (size_t)H * pitch) * sizeof(float2) +
+         (size_t)(col.tab_size + row.tab_size) * sizeof(ushort2);
+}
+
+// 0 = launched; -1 = not applicable (caller falls back to the generic kernel); > 0 = CUDA error
+static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t stream) {
+  if (p.in_spec == nullptr || (p.W & 1) || p.W < 2 || p.H < 1) return -1;
+  if ((reinterpret_cast<uintptr_t>(p.out) & 7u) != 0) return -1;
+  SpectralBatchedLaunch L;
+  L.p = p;
+  if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row)) return -1;
+  // the spectrum load and the Hermitian fold ride on the first stage of each axis: both must exist
+  if (L.col.n_stages == 0 || L.row.n_stages == 0) return -1;
+  L.wh = p.W / 2 + 1;
+  L.pitch = L.wh | 1;
+  const DeviceInfo& di = device_info();
+  const size_t smem = batched_smem_bytes(p.H, p.W, L.col, L.row);
+  if (smem > (size_t)di.max_smem_optin || (int64_t)p.H * L.pitch >= (1 << 24)) return -1;
+  cudaError_t err = cudaFuncSetAttribute(spectral_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  const int per_sm = (int)((size_t)(di.max_smem_optin + 1024) / (smem + 1024)) >= 2 ? 2 : 1;
+  int64_t grid = (int64_t)di.sm_count * per_sm;
+  if (grid > p.planes) grid = p.planes;
+  spectral_batched_kernel<<<(unsigned)grid, kBatchedThreads, smem, stream>>>(L);
+  err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : (int)err;
+}
+
 static bool make_plan(int n, FftPlan* plan) {
   plan->n = n;
   plan->n_factors = 0;
@@ -374,6 +678,10 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) 
   if (p.planes <= 0) return 0;
   if (p.H <= 0 || p.W <= 0 || p.out == nullptr) return (int)cudaErrorInvalidValue;
   if ((p.in_real == nullptr) == (p.in_spec == nullptr)) return (int)cudaErrorInvalidValue;
+  {
+    const int rc = launch_spectral_batched(p, (cudaStream_t)stream_);
+    if (rc >= 0) return rc;
+  }
   if (!make_plan(p.H, &L.plan_h) || !make_plan(p.W, &L.plan_w)) return (int)cudaErrorInvalidValue;
   L.wh = p.W / 2 + 1;
   L.wh_pad = L.wh | 1;

@@ -113,6 +113,17 @@ def philox_policy(numel: int) -> tuple[int, int]:
     return grid.value, inc.value
 
 
+def philox_policy_cached(device_index: int, numel: int) -> tuple[int, int]:
+    policy = _POLICY_CACHE.get((device_index, numel))
+    if policy is None:
+        with torch.cuda.device(device_index):
+            policy = philox_policy(numel)
+        if len(_POLICY_CACHE) > 4096:
+            _POLICY_CACHE.clear()
+        _POLICY_CACHE[(device_index, int(numel))] = policy
+    return policy
+
+
 def reserve_draw(numel: int, device: torch.device, generator: torch.Generator | None = None) -> PhiloxDraw:
     """Consumes `numel` values from torch's CUDA generator exactly like an ATen distribution kernel
     would (same offset arithmetic), without launching anything."""
@@ -122,14 +133,7 @@ def reserve_draw(numel: int, device: torch.device, generator: torch.Generator | 
         raise RuntimeError("reserve_draw needs a CUDA device")
     idx = device.index if device.index is not None else torch.cuda.current_device()
     gen = generator if generator is not None else torch.cuda.default_generators[idx]
-    policy = _POLICY_CACHE.get((idx, numel))
-    if policy is None:
-        with torch.cuda.device(idx):
-            policy = philox_policy(numel)
-        if len(_POLICY_CACHE) > 4096:
-            _POLICY_CACHE.clear()
-        _POLICY_CACHE[(idx, int(numel))] = policy
-    grid, inc = policy
+    grid, inc = philox_policy_cached(idx, numel)
     offset = gen.get_offset()
     if numel > 0:
         gen.set_offset(offset + inc)

@@ -341,9 +341,94 @@ class SonarBase:
             parallel.global_count(count, sums)  # sharded: all-reduce the partial sums, once per table
             la = self._lookahead = {
                 "key": key, "index": {o: j for j, o in enumerate(offsets)}, "sums": sums, "ptr": sums.data_ptr(),
+                "inc": draw.counter_offset,
             }  # fmt: skip
             idx = 0
         return la["sums"], la["ptr"] + 16 * idx
+
+    # ------------------------------------------------------------------------------------
+    # stock lane: ZERO-init history + (optional) fused Gaussian noise, nothing else configured
+    # ------------------------------------------------------------------------------------
+    def stock_lane(self, x: Tensor) -> bool:
+        """True when every step of this run can take `stock_step`: float32 CUDA latent, ZERO history
+        init, no guidance, and the ancestral noise (if any) is the fusable plain Gaussian. Decided once."""
+        lane = getattr(self, "_stock_lane", None)
+        if lane is None:
+            guided = getattr(self, "guidance", None) is not None and self.guidance.factor != 0.0
+            lane = self._stock_lane = (
+                not guided
+                and self.cfg.init == HistoryType.ZERO
+                and x.dtype == torch.float32
+                and x.is_cuda
+                and (self.noise_draws_left == 0 or self._fused_noise_spec(x) is not None)
+            )
+            if lane:
+                self._step_params()
+                spec = self._fused_noise_spec(x) if self.noise_draws_left else None
+                self._stock_noise = spec  # (factor, normalized) or None
+                idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+                self._stock_gen, self._stock_dev = torch.cuda.default_generators[idx], idx
+        return lane
+
+    def stock_step(self, step: int, x: Tensor, denoised: Tensor, sigma: float, kind: int, c0: float, c1: float,
+                   noise_scale: float | None) -> Tensor | None:
+        """fused_step + ancestral_noise for the stock lane with every helper layer flattened out (this is
+        the per-step host cost the end-to-end number is made of). Returns None when the step must take
+        the general path (unexpected tensor layout, injected RNG, look-ahead miss)."""
+        if (
+            denoised.dtype != torch.float32
+            or denoised.device != x.device
+            or not denoised.is_contiguous()
+            or not x.is_contiguous()
+            or rng._INJECT is not None  # noqa: SLF001
+        ):
+            return None
+        p = self._params
+        if noise_scale is not None:
+            spec = self._stock_noise
+            if parallel.active() is not None or spec is None:
+                return None
+            gen = self._stock_gen
+            offset = gen.get_offset()
+            if spec[1]:  # normalised: statistics from the look-ahead table
+                la = self._lookahead
+                idx = None if la is None else la["index"].get(offset)
+                if idx is None or la["key"][0] != gen.initial_seed() or la["key"][2] != x.numel():
+                    return None  # first draw of the run, or somebody else advanced the generator: re-plan
+                p.noise_kind, p.noise_sums, p.noise_count = ops.NOISE_PHILOX_NORMALIZED, la["ptr"] + 16 * idx, x.numel()
+                grid, inc = la["key"][1], la["inc"]
+            else:
+                p.noise_kind = ops.NOISE_PHILOX
+                grid, inc = ops.philox_policy_cached(self._stock_dev, x.numel())
+            gen.set_offset(offset + inc)
+            self.noise_draws_left -= 1
+            p.noise_factor, p.noise_scale = spec[0], noise_scale
+            p.philox_seed, p.philox_offset, p.philox_grid_blocks = gen.initial_seed(), offset, grid
+            p.noise_begin, p.noise_numel_total, p.peer_world = 0, x.numel(), 0
+        else:
+            p.noise_kind = ops.NOISE_NONE
+        start, end, always, hist_on = self._gate
+        in_window = start <= step <= end
+        history_active = hist_on and (always or in_window)
+        x_out = torch.empty_like(x)
+        hist = self.history_d
+        if hist is not None:
+            p.hist_state = ops.HIST_PRESENT
+            p.hist_in = p.hist_out = hist.data_ptr()
+        else:
+            p.hist_state, p.hist_in = ops.HIST_NONE, 0
+            if history_active:
+                hist = torch.empty_like(x)
+                p.hist_out = hist.data_ptr()
+            else:
+                p.hist_out = 0
+        p.hist_in_div = 1.0
+        p.x, p.denoised, p.x_out, p.n = x.data_ptr(), denoised.data_ptr(), x_out.data_ptr(), x.numel()
+        p.kind, p.momentum_active, p.history_active = kind, in_window, history_active
+        p.sigma, p.c0, p.c1 = sigma, c0, c1
+        ops.launch_step(self._params_ref, self._stock_dev)
+        self.history_d = hist
+        return x_out
 
     def prime_history(self, step: int, x: Tensor, denoised: Tensor, sigma: float) -> None:
         """Performs the (possibly random) history initialisation of this step NOW. The reference draws
@@ -519,6 +604,10 @@ class SonarEuler(SonarSampler):
         sigma = self.sigma_views[step_index]
         sigma_f, sigma_next_f, dt = self.schedule()[step_index]
         denoised = self.model(sample, self.sigma_in[step_index], **self.extra_args)
+        if self.stock_lane(sample):
+            result = self.stock_step(step_index, sample, denoised, sigma_f, ops.STEP_EULER, dt, 0.0, None)
+            if result is not None:
+                return (result, sigma, sigma, denoised)
         result = self.momentum_step(step_index, sample, denoised, sigma_f, sigma_next_f, dt=dt)
         if sigma_next_f > 0:
             result = self.guidance_step(step_index, result, denoised)
@@ -567,8 +656,14 @@ class SonarEulerAncestral(SonarSampler):
         sigma = self.sigma_views[step_index]
         sigma_f, sigma_next_f, sigma_down_f, dt, noise_scale = self.schedule()[step_index]
         denoised = self.model(sample, self.sigma_in[step_index], **self.extra_args)
-        noise_kw = {}
         add_noise = sigma_next_f > 0
+        if self.stock_lane(sample):
+            result = self.stock_step(
+                step_index, sample, denoised, sigma_f, ops.STEP_EULER, dt, 0.0, noise_scale if add_noise else None,
+            )
+            if result is not None:
+                return (result, sigma, sigma, denoised)
+        noise_kw = {}
         guided = self.guidance is not None and self.guidance.factor != 0.0
         if add_noise and not guided:
             # x' = momentum_step(...) + noise * (s_noise * sigma_up): one launch
