@@ -143,17 +143,21 @@ pyramid_rows_kernel(SonarPyramidParams p) {
   int* tab_i0 = reinterpret_cast<int*>(pyr_smem);
   int* tab_i1 = tab_i0 + p.n_levels * W;
   float* tab_w1 = reinterpret_cast<float*>(tab_i1 + p.n_levels * W);
+  // VEC = 4: lane l reads the taps of pixels 4l + v, v = 0..3 -- stored as [v][W/4] so that the 32 lanes
+  // of a warp hit 32 consecutive words (a [x] layout would be a 4-way bank conflict)
+  const int Wq = W / VEC;
   for (int i = threadIdx.x; i < p.n_levels * W; i += blockDim.x) {
     const int l = i / W, x = i - l * W;
     const int lw = p.level_w[l];
+    const int slot = l * W + (VEC == 4 ? (x & 3) * Wq + (x >> 2) : x);
     if (p.mode == SONAR_RESAMPLE_BILINEAR) {
       const LinTap lt = linear_tap(x, lw, (float)lw / (float)W);
-      tab_i0[i] = lt.i0;
-      tab_i1[i] = lt.i1;
-      tab_w1[i] = lt.w1;
+      tab_i0[slot] = lt.i0;
+      tab_i1[slot] = lt.i1;
+      tab_w1[slot] = lt.w1;
     } else {
-      tab_i0[i] = tab_i1[i] = nearest_exact_idx(x, lw, (float)lw / (float)W);
-      tab_w1[i] = 0.0f;
+      tab_i0[slot] = tab_i1[slot] = nearest_exact_idx(x, lw, (float)lw / (float)W);
+      tab_w1[slot] = 0.0f;
     }
   }
   __syncthreads();
@@ -215,14 +219,15 @@ pyramid_rows_kernel(SonarPyramidParams p) {
           wy0 = 1.0f;
           wy1 = 0.0f;
         }
-        const int tb = l * W + x0;
+        const int tb = l * W + (VEC == 4 ? (x0 >> 2) : x0);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          const int i0 = tab_i0[tb + v];
+          const int ti = tb + (VEC == 4 ? v * Wq : 0);
+          const int i0 = tab_i0[ti];
           float sv;
           if (bilinear) {
-            const int i1 = tab_i1[tb + v];
-            const float w1 = tab_w1[tb + v], w0 = 1.0f - w1;
+            const int i1 = tab_i1[ti];
+            const float w1 = tab_w1[ti], w0 = 1.0f - w1;
             sv = wy0 * (w0 * __ldg(r0 + i0) + w1 * __ldg(r0 + i1)) + wy1 * (w0 * __ldg(r1 + i0) + w1 * __ldg(r1 + i1));
           } else {
             sv = __ldg(r0 + i0);

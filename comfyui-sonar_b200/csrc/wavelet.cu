@@ -153,6 +153,53 @@ __device__ __forceinline__ void analysis_point(const Tin* __restrict__ pa, const
   }
 }
 
+// Interior outputs only (the whole LT x LT window lies inside the plane): no index resolution, no
+// padding selects, row pointers advanced by a constant. VEC2: fp32 input rows read as float2 pairs
+// (x_first even, even row stride, 8-byte aligned planes).
+template <typename T, typename Tin, int LT, bool VEC2>
+__device__ __forceinline__ void analysis_interior(const Tin* __restrict__ pa, const Tin* __restrict__ pb, int row_stride,
+                                                  int y_first, int x_first, const Filters<T>& f, T& acc_ll, T& acc_lh,
+                                                  T& acc_hl, T& acc_hh) {
+  acc_ll = 0, acc_lh = 0, acc_hl = 0, acc_hh = 0;
+  const Tin* ra = pa + (y_first * row_stride + x_first);
+  const Tin* rb = pb != nullptr ? pb + (y_first * row_stride + x_first) : nullptr;
+#pragma unroll
+  for (int jy = 0; jy < LT; ++jy) {
+    T v[LT > 0 ? LT : 1];
+    if (VEC2) {
+#pragma unroll
+      for (int jx = 0; jx < LT; jx += 2) {
+        const float2 a2 = *reinterpret_cast<const float2*>(ra + jx);
+        v[jx] = (T)a2.x;
+        v[jx + 1] = (T)a2.y;
+        if (rb != nullptr) {
+          const float2 b2 = *reinterpret_cast<const float2*>(rb + jx);
+          v[jx] -= (T)b2.x;
+          v[jx + 1] -= (T)b2.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int jx = 0; jx < LT; ++jx) {
+        v[jx] = (T)ra[jx];
+        if (rb != nullptr) v[jx] -= (T)rb[jx];
+      }
+    }
+    T row_lo = 0, row_hi = 0;
+#pragma unroll
+    for (int jx = 0; jx < LT; ++jx) {
+      row_lo += f.a_lo[jx] * v[jx];
+      row_hi += f.a_hi[jx] * v[jx];
+    }
+    acc_ll += f.a_lo[jy] * row_lo;
+    acc_lh += f.a_hi[jy] * row_lo;
+    acc_hl += f.a_lo[jy] * row_hi;
+    acc_hh += f.a_hi[jy] * row_hi;
+    ra += row_stride;
+    if (rb != nullptr) rb += row_stride;
+  }
+}
+
 template <typename T, typename Tin, int LT>
 __global__ void __launch_bounds__(kBlock)
 dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, T* __restrict__ ll,
@@ -354,14 +401,45 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       T* ll = sm + g.ll_off[j];
       T* hi = sm + g.hi_off[j];
       const int hw = h * w;
+      // interior outputs first (fast path, all lanes alike), then the border ring: no warp ever runs
+      // both code paths back to back
+      int kx_lo = 0, kx_hi = -1, ky_lo = 0, ky_hi = -1;
+      if (LT > 0) {
+        kx_lo = (pad_l + 1) >> 1;
+        ky_lo = (pad_t + 1) >> 1;
+        kx_hi = Win - L + pad_l >= 0 ? min(w - 1, (Win - L + pad_l) >> 1) : -1;
+        ky_hi = Hin - L + pad_t >= 0 ? min(h - 1, (Hin - L + pad_t) >> 1) : -1;
+        const int iw = max(0, kx_hi - kx_lo + 1), ih = max(0, ky_hi - ky_lo + 1);
+        const bool vec2 = j == 0 && ((pad_l | W) & 1) == 0 && (((uintptr_t)in_a | (uintptr_t)in_b) & 7u) == 0 &&
+                          ((H * (int64_t)W) & 1) == 0;
+        for (int i = tid; i < iw * ih; i += nthr) {
+          const int iy = i / iw, ix = i - iy * iw;
+          const int ky = ky_lo + iy, kx = kx_lo + ix, idx = ky * w + kx;
+          T c_ll, c_lh, c_hl, c_hh;
+          if (j == 0) {
+            if (vec2)
+              analysis_interior<T, float, LT, true>(pa, pb, W, 2 * ky - pad_t, 2 * kx - pad_l, f, c_ll, c_lh, c_hl, c_hh);
+            else
+              analysis_interior<T, float, LT, false>(pa, pb, W, 2 * ky - pad_t, 2 * kx - pad_l, f, c_ll, c_lh, c_hl, c_hh);
+          } else {
+            analysis_interior<T, T, LT, false>(sm + g.ll_off[j - 1], nullptr, Win, 2 * ky - pad_t, 2 * kx - pad_l, f, c_ll,
+                                               c_lh, c_hl, c_hh);
+          }
+          ll[idx] = c_ll;
+          hi[idx] = c_lh;
+          hi[hw + idx] = c_hl;
+          hi[2 * hw + idx] = c_hh;
+        }
+      }
       for (int idx = tid; idx < hw; idx += nthr) {
         const int ky = idx / w, kx = idx - ky * w;
+        if (kx >= kx_lo && kx <= kx_hi && ky >= ky_lo && ky <= ky_hi) continue;  // done above
         T c_ll, c_lh, c_hl, c_hh;
         if (j == 0)
           analysis_point<T, float, LT>(pa, pb, W, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh, c_hl, c_hh);
         else
           analysis_point<T, T, LT>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh,
-                               c_hl, c_hh);
+                                   c_hl, c_hh);
         ll[idx] = c_ll;
         hi[idx] = c_lh;
         hi[hw + idx] = c_hl;
