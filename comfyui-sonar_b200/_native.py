@@ -65,6 +65,7 @@ class SonarStepParams(ctypes.Structure):
 
 ABI_VERSION = 2  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
+PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
 PERLIN_MAX_ITERS = 8
 FFT_MAX_FACTORS = 24
@@ -257,6 +258,7 @@ SIGNATURES: dict[str, list] = {
         c_void_p, c_void_p, c_int64, c_void_p, c_int, c_double, c_int64, c_float, c_float, c_void_p,
     ],
     "sonar_peer_publish_sums": [POINTER(c_void_p), c_int, c_int, c_void_p, c_double, c_void_p],
+    "sonar_peer_allreduce_table": [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_double, c_void_p],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
     "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],

@@ -9,7 +9,10 @@
 // spins on the N flags of its LOCAL mailbox and adds the N partials in rank order (deterministic).
 // No host round trip, no collective launch: ~2 us instead of ~45 us per exchange.
 //
-// Mailbox layout: double box[2 (epoch parity)][SONAR_PEER_MAX_RANKS][4] = {sum, sum^2, epoch, pad}.
+// Mailbox layout: double box[2 (epoch parity)][SONAR_PEER_MAX_RANKS][4] = {sum, sum^2, epoch, pad},
+// followed by a table region double tab[2][SONAR_PEER_MAX_RANKS][2 + SONAR_PEER_TABLE_MAX] =
+// {epoch, n, payload...} used by sonar_peer_allreduce_table (the (K, 2) look-ahead statistics of a
+// whole sampler run: one exchange per run instead of one per step).
 #include "common.cuh"
 #include "../../include/sonar_b200.h"
 
@@ -31,13 +34,53 @@ __global__ void peer_publish_kernel(PeerTargets targets, const double* __restric
   slot[2] = epoch;
 }
 
+constexpr size_t kPairDoubles = 2 * SONAR_PEER_MAX_RANKS * 4;
+constexpr size_t kTableSlot = 2 + SONAR_PEER_TABLE_MAX;
+constexpr size_t kMailboxDoubles = kPairDoubles + 2 * SONAR_PEER_MAX_RANKS * kTableSlot;
+
+// One CTA: (1) store this rank's table into every rank's mailbox over NVLink, fence, raise the epoch
+// flags; (2) wait until every rank's table of this epoch has landed in the LOCAL mailbox; (3) replace
+// the local table by the sum over ranks, added in rank order so that all ranks hold identical bits.
+__global__ void __launch_bounds__(512)
+peer_allreduce_table_kernel(PeerTargets targets, double* __restrict__ table, int n, int rank, int world, double epoch) {
+  const int parity = ((long long)epoch) & 1;
+  const size_t slot_of_me = kPairDoubles + ((size_t)parity * SONAR_PEER_MAX_RANKS + rank) * kTableSlot;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = table[i];
+    for (int dst = 0; dst < world; ++dst) ((volatile double*)targets.box[dst])[slot_of_me + 2 + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    volatile double* slot = targets.box[threadIdx.x] + slot_of_me;
+    slot[1] = (double)n;
+    __threadfence_system();
+    slot[0] = epoch;
+  }
+  // consume: thread r waits for rank r's flag in the local mailbox
+  volatile double* local = targets.box[rank];
+  if (threadIdx.x < world) {
+    const size_t s = kPairDoubles + ((size_t)parity * SONAR_PEER_MAX_RANKS + threadIdx.x) * kTableSlot;
+    while (local[s] != epoch) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r)
+      acc += local[kPairDoubles + ((size_t)parity * SONAR_PEER_MAX_RANKS + r) * kTableSlot + 2 + i];
+    table[i] = acc;
+  }
+}
+
 }  // namespace sonar
 
 extern "C" {
 
 int sonar_peer_alloc(void** mailbox_out) {
   if (mailbox_out == nullptr) return (int)cudaErrorInvalidValue;
-  const size_t bytes = 2 * SONAR_PEER_MAX_RANKS * 4 * sizeof(double);
+  const size_t bytes = sonar::kMailboxDoubles * sizeof(double);
   SONAR_CUDA_TRY(cudaMalloc(mailbox_out, bytes));
   SONAR_CUDA_TRY(cudaMemset(*mailbox_out, 0, bytes));
   return 0;
@@ -68,6 +111,19 @@ int sonar_peer_publish_sums(void* const* mailboxes_host, int rank, int world, co
   sonar::PeerTargets t;
   for (int r = 0; r < SONAR_PEER_MAX_RANKS; ++r) t.box[r] = r < world ? (double*)mailboxes_host[r] : nullptr;
   sonar::peer_publish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, local_sums, rank, world, epoch);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_peer_allreduce_table(void* const* mailboxes_host, int rank, int world, double* table, int n, double epoch,
+                               void* stream) {
+  if (world < 1 || world > SONAR_PEER_MAX_RANKS || rank < 0 || rank >= world || table == nullptr || n < 0 ||
+      n > SONAR_PEER_TABLE_MAX)
+    return (int)cudaErrorInvalidValue;
+  if (n == 0) return 0;
+  sonar::PeerTargets t;
+  for (int r = 0; r < SONAR_PEER_MAX_RANKS; ++r) t.box[r] = r < world ? (double*)mailboxes_host[r] : nullptr;
+  sonar::peer_allreduce_table_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(t, table, n, rank, world, epoch);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

@@ -77,6 +77,26 @@ class PeerExchange:
         ops.LAUNCH_COUNT += 1
         return float(self.epoch)
 
+    def allreduce_table(self, table: torch.Tensor) -> bool:
+        """In-place sum over ranks of a small float64 table through the mailboxes (one launch, no host
+        round trip). Returns False when the table is too large for a mailbox slot."""
+        import ctypes
+
+        from . import _native, ops
+
+        if table.dtype != torch.float64 or not table.is_contiguous() or table.numel() > _native.PEER_TABLE_MAX:
+            return False
+        self.epoch += 1
+        stream = ctypes.c_void_p(ops._raw_stream(table.device.index))  # noqa: SLF001
+        _native.check(
+            self.lib.sonar_peer_allreduce_table(
+                self.mapped, self.rank, self.world_size, ctypes.c_void_p(table.data_ptr()), table.numel(), float(self.epoch), stream,
+            ),
+            "sonar_peer_allreduce_table",
+        )
+        ops.LAUNCH_COUNT += 1
+        return True
+
     def close(self) -> None:
         for ptr in self._opened:
             self.lib.sonar_peer_close_handle(ptr)
@@ -178,6 +198,18 @@ def global_count(local_numel: int, sums: torch.Tensor) -> int:
     if ctx.local_batch == 0:
         return local_numel
     return (local_numel // ctx.local_batch) * ctx.total_batch
+
+
+def allreduce_table(table: torch.Tensor) -> None:
+    """Sums a small float64 table over the ranks of the active sharding context, in place: peer
+    mailboxes over NVLink when available, one NCCL all-reduce otherwise."""
+    ctx = _ACTIVE
+    if ctx is None or ctx.world_size == 1:
+        return
+    if ctx.peers is not None and ctx.peers.allreduce_table(table):
+        return
+    dist.all_reduce(table, op=dist.ReduceOp.SUM, group=ctx.group)
+    ctx.collectives += 1
 
 
 def global_numel(local_numel: int) -> int:

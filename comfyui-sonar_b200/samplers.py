@@ -338,7 +338,7 @@ class SonarBase:
             k = max(1, min(self.noise_draws_left, self._lookahead_cap))
             offsets = [draw.offset + j * draw.counter_offset for j in range(k)]
             sums = ops.philox_normal_moments_batch(draw, offsets, begin=begin, count=count, device=device)
-            parallel.global_count(count, sums)  # sharded: all-reduce the partial sums, once per table
+            parallel.allreduce_table(sums)  # sharded: sum the partial sums over ranks, once per table
             la = self._lookahead = {
                 "key": key, "index": {o: j for j, o in enumerate(offsets)}, "sums": sums, "ptr": sums.data_ptr(),
                 "inc": draw.counter_offset,

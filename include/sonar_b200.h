@@ -416,6 +416,12 @@ int sonar_scale_noise_peers_f32(const float* x, float* out, int64_t n, const dou
                                 int64_t count, float factor, float threshold_std_devs, void* stream);
 int sonar_peer_publish_sums(void* const* mailboxes_host, int rank, int world, const double* local_sums, double epoch,
                             void* stream);
+/* In-place sum over ranks of a small table of doubles (n <= SONAR_PEER_TABLE_MAX), e.g. the (K, 2)
+ * look-ahead statistics of all noise draws of a sampler run: one launch per rank, stores over NVLink,
+ * device-side wait, ranks added in rank order (identical bits everywhere). Same epoch rule as above. */
+#define SONAR_PEER_TABLE_MAX 512
+int sonar_peer_allreduce_table(void* const* mailboxes_host, int rank, int world, double* table, int n, double epoch,
+                               void* stream);
 
 #ifdef __cplusplus
 }
