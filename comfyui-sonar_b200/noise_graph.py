@@ -145,13 +145,19 @@ class CustomNoiseChain:
             raise ValueError("Failed to get noise sampler")
         factor = self.factor
 
-        def noise_sampler(sigma, sigma_next):
+        def accumulate(sigma, sigma_next):
             total = None
             for ns in samplers:
                 part = ns(sigma, sigma_next)
                 total = part if total is None else ops.axpby(total, 1.0, part, 1.0, out=total)
-            return scale_noise(total, factor, normalized=normalized)
+            return total
 
+        def noise_sampler(sigma, sigma_next):
+            return scale_noise(accumulate(sigma, sigma_next), factor, normalized=normalized)
+
+        # A consumer that applies scale_noise itself while reading the tensor (the fused Sonar step
+        # normalises on load) asks for the un-normalised sum and what is still owed to it.
+        noise_sampler.deferred = lambda sigma, sigma_next: (accumulate(sigma, sigma_next), factor, normalized)
         return noise_sampler
 
 

@@ -239,6 +239,7 @@ class SonarBase:
         noise_tensor: Tensor | None = None,
         noise_scale: float = 0.0,
         noise_philox: dict | None = None,
+        noise_deferred: tuple | None = None,
     ) -> Tensor:
         """One C-ABI call: momentum mix, both history updates, Euler / DPM++ update, noise injection.
 
@@ -305,6 +306,12 @@ class SonarBase:
                 p.noise_count = noise_philox["count"]
             else:
                 p.noise_kind = ops.NOISE_PHILOX
+        elif noise_deferred is not None:  # un-normalised tensor + its global {sum, sum^2}: scale_noise on load
+            raw, sums, count, factor = keep = noise_deferred
+            if raw.device != x.device:
+                raise RuntimeError(f"tensors on different devices: {x.device} vs {raw.device}")
+            p.noise_kind, p.noise, p.peer_world = ops.NOISE_TENSOR_NORMALIZED, raw.data_ptr(), 0
+            p.noise_sums, p.noise_count, p.noise_factor = sums.data_ptr(), count, factor
         elif noise_tensor is not None:
             if noise_tensor.dtype != torch.float32 or not noise_tensor.is_contiguous():
                 noise_tensor = noise_tensor.to(torch.float32).contiguous()
@@ -450,6 +457,20 @@ class SonarBase:
         """kwargs for fused_step that add noise_sampler(sigma, sigma_next) * scale."""
         spec = self._fused_noise_spec(x)
         if spec is None:
+            deferred = getattr(self.noise_sampler, "deferred", None)
+            if deferred is not None:
+                # chain noise: skip its final scale_noise pass (a read + a write of the whole tensor) and
+                # let the step kernel normalise while it loads, from the statistics the producer kernel
+                # reduced (or one moments pass); sharded runs sum the two doubles over ranks first
+                raw, factor, normalized = deferred(sigma, sigma_next)
+                if normalized and raw.dtype == torch.float32 and raw.shape == x.shape and raw.numel() and raw.is_contiguous():
+                    sums = ops.attached_sums(raw)
+                    if sums is None:
+                        sums = ops.moments(raw)
+                    parallel.allreduce_table(sums)
+                    count = parallel.global_numel(raw.numel())
+                    return {"noise_deferred": (raw, sums, count, factor), "noise_scale": scale}
+                return {"noise_tensor": hostutil.scale_noise(raw, factor, normalized=normalized), "noise_scale": scale}
             return {"noise_tensor": self.noise_sampler(sigma, sigma_next), "noise_scale": scale}
         factor, normalized = spec
         ctx = parallel.active()

@@ -192,3 +192,26 @@ def test_config_errors_match_reference(sb, golden):
             sb.samplers.SonarBase.get_config(None, eval(params))  # noqa: S307 - fixture literal
         assert type(info.value).__name__ == exc_name
         assert str(info.value) == msg
+
+
+def test_deferred_chain_normalisation_equals_explicit_scale_noise(sb, cuda):
+    """Chain noise handed to the step un-normalised (scale_noise applied on load from the producer's
+    statistics) == the same chain normalised by its own scale_noise pass first."""
+    ng = sb.noise_graph
+    chain = ng.CustomNoiseChain()
+    chain.add(ng.CustomNoiseItem(1.0, noise_type="pyramid"))
+    chain.add(ng.CustomNoiseItem(0.5, noise_type="perlin"))
+    sigmas = torch.cat((torch.linspace(12.0, 0.2, 7), torch.zeros(1))).to(cuda)
+    torch.manual_seed(11)
+    x0 = (torch.randn(3, 4, 40, 48) * 12.0).to(cuda)
+
+    def run(hide_deferred):
+        torch.manual_seed(42)
+        base = chain.make_noise_sampler(x0, sigmas[sigmas > 0].min().cpu(), sigmas.max().cpu(), seed=0)
+        assert hasattr(base, "deferred")
+        ns = (lambda s, sn: base(s, sn)) if hide_deferred else base
+        return sb.samplers.SonarEulerAncestral.sampler(
+            stub_model, x0.clone(), sigmas, extra_args={"seed": 0}, disable=True, noise_sampler=ns,
+        )
+
+    assert_close(run(False), run(True), what="deferred vs explicit", rtol=1e-6, atol=1e-5)
