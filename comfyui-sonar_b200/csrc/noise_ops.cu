@@ -319,7 +319,7 @@ perlin_accum_kernel(SonarPerlinParams p) {
     }
     const int64_t o0 = (int64_t)c * p.H * p.W + (int64_t)y * p.W + x0;
 #pragma unroll 4
-    for (int b = 0; b < p.B; ++b) {
+    for (int b = blockIdx.y; b < p.B; b += gridDim.y) {  // grid.y splits the batch when C*H*W alone is too few CTAs
       const int64_t o = (int64_t)b * chw + o0;
       float v[VEC];
       if (p.base != nullptr) {
@@ -611,12 +611,18 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
   const int64_t threads = (int64_t)p.C * p.H * (vec ? p.W / 4 : p.W);
   const int grid = streaming_grid(threads, kBlock, 4);
   cudaStream_t st = (cudaStream_t)stream;
+  // the stencil is shared by the batch; when (C, H, W) alone gives fewer CTAs than ~4 per SM the batch is
+  // split over grid.y (each slice recomputes the stencil, which is cheap next to its share of the traffic)
+  const int want = 4 * device_info().sm_count;
+  int gy = grid >= want ? 1 : (want + grid - 1) / grid;
+  if (gy > p.B) gy = p.B;
+  const dim3 grid2((unsigned)grid, (unsigned)gy);
 #define PERLIN_LAUNCH(ITERS)                                        \
   do {                                                              \
     if (vec)                                                        \
-      perlin_accum_kernel<4, ITERS><<<grid, kBlock, 0, st>>>(p);    \
+      perlin_accum_kernel<4, ITERS><<<grid2, kBlock, 0, st>>>(p);   \
     else                                                            \
-      perlin_accum_kernel<1, ITERS><<<grid, kBlock, 0, st>>>(p);    \
+      perlin_accum_kernel<1, ITERS><<<grid2, kBlock, 0, st>>>(p);   \
   } while (0)
   switch (p.iterations) {
     case 1: PERLIN_LAUNCH(1); break;

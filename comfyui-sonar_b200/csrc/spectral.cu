@@ -375,31 +375,61 @@ struct StageIo {
   int src_pitch;       // SRC_SPECTRUM: row length of the global plane (Wh)
 };
 
+// Input t' (0..R-1) of butterfly j for transform b: one base offset per (j, b), then a fixed step.
 template <int SOURCE>
-__device__ __forceinline__ float2 stage_load(const StageIo& io, int t, int b, int stride_t, int stride_b) {
-  if (SOURCE == SRC_SPECTRUM) {  // t = row y, b = column k of the global plane
-    const int o = t * io.src_pitch + b;
-    float2 v = io.src[o];
-    if (io.mask != nullptr) {
-      const float g = __ldg(io.mask + o);
-      v.x *= g;
-      v.y *= g;
+struct StageInputs {
+  const float2* p0;   // SRC_SMEM / SRC_SPECTRUM: &src[first element]; SRC_FOLD: row base
+  const float* m0;    // SRC_SPECTRUM: &mask[first element] (or nullptr)
+  const float2* tw_w; // SRC_FOLD
+  int step;           // distance between consecutive inputs (elements)
+  int t0, M;          // SRC_FOLD: first k, fold length
+
+  __device__ __forceinline__ float2 get(int i) const {
+    if (SOURCE == SRC_SPECTRUM) {
+      float2 v = p0[i * step];
+      if (m0 != nullptr) {
+        const float g = __ldg(m0 + i * step);
+        v.x *= g;
+        v.y *= g;
+      }
+      return v;
     }
-    return v;
-  }
-  if (SOURCE == SRC_FOLD) {  // t = k, b = row y
-    const float2* r = io.src + b * stride_b;
-    float2 xk = r[t], xm = r[io.M - t];
-    if (t == 0) {  // c2r ignores the imaginary parts of the DC and Nyquist bins
-      xk.y = 0.0f;
-      xm.y = 0.0f;
+    if (SOURCE == SRC_FOLD) {
+      const int t = t0 + i * step;
+      float2 xk = p0[t], xm = p0[M - t];
+      if (t == 0) {  // c2r ignores the imaginary parts of the DC and Nyquist bins
+        xk.y = 0.0f;
+        xm.y = 0.0f;
+      }
+      const float2 a = make_float2(xk.x + xm.x, xk.y - xm.y);  // X[k] + conj X[M-k]
+      const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);  // X[k] - conj X[M-k]
+      const float2 bt = cmul(d, tw_w[t]);
+      return make_float2(a.x - bt.y, a.y + bt.x);  // A + i B
     }
-    const float2 a = make_float2(xk.x + xm.x, xk.y - xm.y);  // X[k] + conj X[M-k]
-    const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);  // X[k] - conj X[M-k]
-    const float2 bt = cmul(d, io.tw_w[t]);
-    return make_float2(a.x - bt.y, a.y + bt.x);  // A + i B
+    return p0[i * step];
   }
-  return io.src[t * stride_t + b * stride_b];
+};
+
+template <int SOURCE>
+__device__ __forceinline__ StageInputs<SOURCE> stage_inputs(const StageIo& io, int j, int nb, int b, int stride_t,
+                                                            int stride_b) {
+  StageInputs<SOURCE> in;
+  in.tw_w = io.tw_w;
+  in.M = io.M;
+  in.m0 = nullptr;
+  in.t0 = j;
+  if (SOURCE == SRC_SPECTRUM) {  // element (row t, column b) of the global plane
+    in.p0 = io.src + (j * io.src_pitch + b);
+    in.m0 = io.mask != nullptr ? io.mask + (j * io.src_pitch + b) : nullptr;
+    in.step = nb * io.src_pitch;
+  } else if (SOURCE == SRC_FOLD) {  // transform index = k along the row of transform b
+    in.p0 = io.src + b * stride_b;
+    in.step = nb;
+  } else {
+    in.p0 = io.src + (j * stride_t + b * stride_b);
+    in.step = nb * stride_t;
+  }
+  return in;
 }
 
 // One inverse Stockham stage over a batch of transforms. Element t of transform b lives at
@@ -415,19 +445,21 @@ __device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2*
   const int jw = nwarps / cw;                          // warps along the butterfly axis
   const int wj = warp / cw, wc = warp - wj * cw;
   if (wj >= jw) return;  // nwarps % cw leftover warps idle for this stage
+  const int out_step = Ns * stride_t;
   for (int c = wc; c < nchunks; c += cw) {
     const int b = (c << 5) + lane;
     if (b >= nbatch) continue;
+    float2* out_b = dst + b * stride_b;
     for (int j = wj; j < nb; j += jw) {
       const ushort2 e = tab[j];
       const int tb = e.y;
-      float2* out = dst + (int)e.x * stride_t + b * stride_b;
-      const int out_step = Ns * stride_t;
+      float2* out = out_b + (int)e.x * stride_t;
+      const StageInputs<SOURCE> in = stage_inputs<SOURCE>(io, j, nb, b, stride_t, stride_b);
       if (R == 4) {
-        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
-        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
-        const float2 v2 = cmul_conj(stage_load<SOURCE>(io, j + 2 * nb, b, stride_t, stride_b), tw[2 * tb]);
-        const float2 v3 = cmul_conj(stage_load<SOURCE>(io, j + 3 * nb, b, stride_t, stride_b), tw[3 * tb]);
+        const float2 v0 = in.get(0);
+        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
+        const float2 v2 = cmul_conj(in.get(2), tw[2 * tb]);
+        const float2 v3 = cmul_conj(in.get(3), tw[3 * tb]);
         const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3);
         const float2 d = csub(v1, v3);
         const float2 a3 = make_float2(-d.y, d.x);  // * (+i)
@@ -436,14 +468,14 @@ __device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2*
         out[2 * out_step] = csub(a0, a2);
         out[3 * out_step] = csub(a1, a3);
       } else if (R == 2) {
-        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
-        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
+        const float2 v0 = in.get(0);
+        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
         out[0] = cadd(v0, v1);
         out[out_step] = csub(v0, v1);
       } else if (R == 3) {
-        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
-        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
-        const float2 v2 = cmul_conj(stage_load<SOURCE>(io, j + 2 * nb, b, stride_t, stride_b), tw[2 * tb]);
+        const float2 v0 = in.get(0);
+        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
+        const float2 v2 = cmul_conj(in.get(2), tw[2 * tb]);
         const float2 t1 = cadd(v1, v2);
         const float2 t2 = make_float2(v0.x - 0.5f * t1.x, v0.y - 0.5f * t1.y);
         const float2 d = csub(v1, v2);
@@ -454,11 +486,11 @@ __device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2*
       } else {  // R == 5
         constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
         constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
-        const float2 v0 = stage_load<SOURCE>(io, j, b, stride_t, stride_b);
-        const float2 v1 = cmul_conj(stage_load<SOURCE>(io, j + nb, b, stride_t, stride_b), tw[tb]);
-        const float2 v2 = cmul_conj(stage_load<SOURCE>(io, j + 2 * nb, b, stride_t, stride_b), tw[2 * tb]);
-        const float2 v3 = cmul_conj(stage_load<SOURCE>(io, j + 3 * nb, b, stride_t, stride_b), tw[3 * tb]);
-        const float2 v4 = cmul_conj(stage_load<SOURCE>(io, j + 4 * nb, b, stride_t, stride_b), tw[4 * tb]);
+        const float2 v0 = in.get(0);
+        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
+        const float2 v2 = cmul_conj(in.get(2), tw[2 * tb]);
+        const float2 v3 = cmul_conj(in.get(3), tw[3 * tb]);
+        const float2 v4 = cmul_conj(in.get(4), tw[4 * tb]);
         const float2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), b1 = csub(v1, v4), b2 = csub(v2, v3);
         const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
         const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);

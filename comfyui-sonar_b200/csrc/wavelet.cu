@@ -431,19 +431,41 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
           hi[2 * hw + idx] = c_hh;
         }
       }
-      for (int idx = tid; idx < hw; idx += nthr) {
-        const int ky = idx / w, kx = idx - ky * w;
-        if (kx >= kx_lo && kx <= kx_hi && ky >= ky_lo && ky <= ky_hi) continue;  // done above
-        T c_ll, c_lh, c_hl, c_hh;
-        if (j == 0)
-          analysis_point<T, float, LT>(pa, pb, W, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh, c_hl, c_hh);
-        else
-          analysis_point<T, T, LT>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh,
-                                   c_hl, c_hh);
-        ll[idx] = c_ll;
-        hi[idx] = c_lh;
-        hi[hw + idx] = c_hl;
-        hi[2 * hw + idx] = c_hh;
+      // border ring, enumerated densely (rows above the interior, rows below it, then the left / right
+      // columns of the interior rows): a warp of the ring holds 32 border outputs, not 1 or 2
+      {
+        const bool has_interior = kx_hi >= kx_lo && ky_hi >= ky_lo;
+        const int top = has_interior ? ky_lo * w : hw;            // outputs in the rows above (or everything)
+        const int bottom = has_interior ? (h - 1 - ky_hi) * w : 0;
+        const int right0 = kx_hi + 1;                              // first column right of the interior
+        const int side = has_interior ? kx_lo + (w - right0) : 0;  // border outputs per interior row
+        const int ring = top + bottom + (has_interior ? (ky_hi - ky_lo + 1) * side : 0);
+        for (int b = tid; b < ring; b += nthr) {
+          int ky, kx;
+          if (b < top) {
+            ky = b / w;
+            kx = b - ky * w;
+          } else if (b < top + bottom) {
+            const int r = (b - top) / w;
+            ky = ky_hi + 1 + r;
+            kx = (b - top) - r * w;
+          } else {
+            const int r = (b - top - bottom) / side, c = (b - top - bottom) - r * side;
+            ky = ky_lo + r;
+            kx = c < kx_lo ? c : right0 + (c - kx_lo);
+          }
+          const int idx = ky * w + kx;
+          T c_ll, c_lh, c_hl, c_hh;
+          if (j == 0)
+            analysis_point<T, float, LT>(pa, pb, W, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll, c_lh, c_hl, c_hh);
+          else
+            analysis_point<T, T, LT>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll,
+                                     c_lh, c_hl, c_hh);
+          ll[idx] = c_ll;
+          hi[idx] = c_lh;
+          hi[hw + idx] = c_hl;
+          hi[2 * hw + idx] = c_hh;
+        }
       }
       __syncthreads();
     }
