@@ -16,7 +16,7 @@ One bench "step" = one 30-step sampling run over one batch. Metric: latent noise
               ms_per_step = sum of those 30 event intervals, max over ranks.
 * e2e       : the same run through the public sampler function with HOST buffers: pinned x0 -> H2D,
               30 steps, result D2H, wall clock between device synchronisations.
-* roofline  : dominant kernel (sonar_step_fast_philox_kernel): algorithmic bytes per launch
+* roofline  : dominant kernel (sonar_step_fast_philox2_kernel): algorithmic bytes per launch
               (20 B/element: read x, denoised, history; write x', history'; the noise is regenerated
               from the Philox stream in registers) / CUDA-event duration of that launch with cold L2,
               against MEASURED_PEAKS.json hbm_gbs; the same kernel on the C5 per-GPU shard shape is
@@ -284,9 +284,11 @@ def step_kernel_roofline(sb, dev, shape, peak: float, peak_src: str, reps: int) 
     launch_us = st.median(us)
     algo = 20 * n
     achieved = algo / (launch_us * 1e-6) / 1e9
+    # draws of at most two ATen rows (numel <= 2 * 256 * grid) take the single-wave variant
+    two_rows = n <= 2 * 256 * sb.ops.philox_policy(n)[0]
     return {
         "bound": "hbm",
-        "kernel": "sonar_step_fast_philox_kernel",
+        "kernel": "sonar_step_fast_philox2_kernel" if two_rows else "sonar_step_fast_philox_kernel",
         "shape": list(shape),
         "achieved": achieved,
         "peak": peak,
@@ -380,8 +382,8 @@ def run_b200_arm(args) -> None:
     traffic_path = REPO / "profiles" / "traffic.json"
     if traffic_path.exists():
         traffic = json.loads(traffic_path.read_text())
-        roofline["traffic"] = traffic.get("sonar_step_fast_philox_kernel@8x4x128x128")
-        roofline_large["traffic"] = traffic.get("sonar_step_fast_philox_kernel@1x16x33x90x160")
+        roofline["traffic"] = traffic.get(roofline["kernel"] + "@8x4x128x128")
+        roofline_large["traffic"] = traffic.get(roofline_large["kernel"] + "@1x16x33x90x160")
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e_times = []

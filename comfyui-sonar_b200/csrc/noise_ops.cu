@@ -611,9 +611,10 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
   const int64_t threads = (int64_t)p.C * p.H * (vec ? p.W / 4 : p.W);
   const int grid = streaming_grid(threads, kBlock, 4);
   cudaStream_t st = (cudaStream_t)stream;
-  // the stencil is shared by the batch; when (C, H, W) alone gives fewer CTAs than ~4 per SM the batch is
-  // split over grid.y (each slice recomputes the stencil, which is cheap next to its share of the traffic)
-  const int want = 4 * device_info().sm_count;
+  // the stencil (20 sincosf per thread at VEC = 4) is shared by the batch and costs about as much as 16
+  // batch items of traffic, so the batch is split over grid.y only when (C, H, W) alone cannot give every
+  // SM a CTA (measured at 16x16x128x128: 15 us unsplit, 21 us split 3-way)
+  const int want = device_info().sm_count;
   int gy = grid >= want ? 1 : (want + grid - 1) / grid;
   if (gy > p.B) gy = p.B;
   const dim3 grid2((unsigned)grid, (unsigned)gy);
