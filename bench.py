@@ -70,12 +70,15 @@ class ClockSampler:
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     )
 
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, enabled: bool = True):
         self.device_index = device_index
+        self.enabled = enabled  # rank 0 samples its GPU; N pollers would only add host contention
         self.proc = None
         self.lines: list[str] = []
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device_index)],
@@ -351,18 +354,20 @@ def run_b200_arm(args) -> None:
     timers = []
     gc.collect()
     gc.disable()  # a collection pause between two launches would show up as device idle time
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, enabled=rank == 0) as clocks:
         t_wall = time.perf_counter()
         for _ in range(args.steps):
+            if world > 1:
+                barrier()  # ranks start each run together: the one exchange of a run measures NVLink, not host drift
             timer = StepTimer(dev)
             one_run(timer, x0)
             timer.close()
             timers.append(timer)
         barrier()
         wall = time.perf_counter() - t_wall
-        # keep the sampler busy long enough for a few clock samples
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
+        # keep the sampler busy long enough for a few clock samples; a FIXED run count, because every
+        # sharded run performs one exchange and all ranks must perform the same number of them
+        for _ in range(300):
             one_run(warm_model, x0)
         torch.cuda.synchronize()
     gc.enable()
