@@ -93,6 +93,23 @@ class SonarFillBatch(ctypes.Structure):
     _fields_ = [("n", c_int32), ("seed", c_uint64), ("draws", SonarFillDesc * FILL_BATCH_MAX)]
 
 
+class SonarGuidanceParams(ctypes.Structure):
+    _fields_ = [
+        ("x", c_void_p),
+        ("ref", c_void_p),
+        ("item_sums", c_void_p),
+        ("out", c_void_p),
+        ("items", c_int64),
+        ("per_item", c_int64),
+        ("ref_items", c_int32),
+        ("kind", c_int32),
+        ("blend_mode", c_int32),
+        ("factor", c_float),
+        ("sigma", c_float),
+        ("dt", c_float),
+    ]
+
+
 class SonarPyramidParams(ctypes.Structure):
     _fields_ = [
         ("out", c_void_p),
@@ -259,6 +276,8 @@ SIGNATURES: dict[str, list] = {
     ],
     "sonar_peer_publish_sums": [POINTER(c_void_p), c_int, c_int, c_void_p, c_double, c_void_p],
     "sonar_peer_allreduce_table": [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_double, c_void_p],
+    "sonar_item_moments_f32": [c_void_p, c_int64, c_int64, c_void_p, c_void_p],
+    "sonar_guidance_f32": [POINTER(SonarGuidanceParams), c_void_p],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
     "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],

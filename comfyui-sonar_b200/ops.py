@@ -798,3 +798,51 @@ def wcfg_fused(
     lib, stream = _prepare(a, b, out, addend, x)
     _launch("sonar_wcfg_fused", lib.sonar_wcfg_fused, ctypes.byref(p), stream)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# reference-latent guidance
+# --------------------------------------------------------------------------------------------
+GUIDANCE_LINEAR, GUIDANCE_EULER = 0, 1
+
+
+def item_moments(x: torch.Tensor) -> torch.Tensor:
+    """(items, 2) float64: sum and sum of squares of every leading-dim item of x."""
+    _f32(x, "x")
+    items = x.shape[0]
+    sums = torch.empty((items, 2), device=x.device, dtype=torch.float64)
+    lib, stream = _prepare(x, sums)
+    _launch("sonar_item_moments_f32", lib.sonar_item_moments_f32, _ptr(x), items, x.numel() // max(1, items), _ptr(sums), stream)
+    return sums
+
+
+def guidance(
+    x: torch.Tensor,
+    ref: torch.Tensor,
+    item_sums: torch.Tensor | None,
+    *,
+    kind: int,
+    blend_mode: str | int = "lerp",
+    factor: float = 0.0,
+    sigma: float = 1.0,
+    dt: float = 0.0,
+) -> torch.Tensor:
+    """guidance_linear / guidance_euler of the reference (py/sonar.py:380-411) in one pass: the target
+    is ref * std_i + mean_i with the per-item statistics taken from `item_sums` (item_moments of x for
+    LINEAR, of the denoised prediction for EULER)."""
+    _f32(x, "x")
+    _f32(ref, "ref")
+    items = x.shape[0]
+    per_item = x.numel() // max(1, items)
+    if ref.numel() not in {per_item, x.numel()}:
+        raise ValueError(f"guidance: reference latent {tuple(ref.shape)} does not broadcast over {tuple(x.shape)}")
+    out = torch.empty_like(x)
+    p = _native.SonarGuidanceParams()
+    p.x, p.ref, p.out = x.data_ptr(), ref.data_ptr(), out.data_ptr()
+    p.item_sums = 0 if item_sums is None else item_sums.data_ptr()
+    p.items, p.per_item, p.ref_items = items, per_item, (1 if ref.numel() == per_item and items != 1 else items)
+    p.kind, p.blend_mode = kind, (blend_mode if isinstance(blend_mode, int) else BLEND_IDS[blend_mode])
+    p.factor, p.sigma, p.dt = float(factor), float(sigma), float(dt)
+    lib, stream = _prepare(x, ref, item_sums, out)
+    _launch("sonar_guidance_f32", lib.sonar_guidance_f32, ctypes.byref(p), stream)
+    return out

@@ -437,6 +437,16 @@ class SonarBase:
         self.history_d = hist
         return x_out
 
+    def _momentum_denoised_preview(self, step: int, denoised: Tensor, sigma: float) -> Tensor:
+        """What get_momentum_denoised (:262-283) would return for `denoised` right now, without touching
+        the history: only DENOISED mode mixes the prediction with history * sigma."""
+        cfg = self.cfg
+        hist = self.history_d
+        if cfg.momentum_mode != MomentumMode.DENOISED or cfg.momentum == 1 or hist is None or not self.check_step(step):
+            return denoised
+        scaled = ops.axpby(hist, sigma, None)
+        return self.momentum_blend(scaled, denoised.to(torch.float32).contiguous(), cfg.momentum)
+
     def prime_history(self, step: int, x: Tensor, denoised: Tensor, sigma: float) -> None:
         """Performs the (possibly random) history initialisation of this step NOW. The reference draws
         the RAND history inside momentum_step, i.e. before the step's ancestral noise; callers that
@@ -502,8 +512,9 @@ class SonarBase:
 
 
 class SonarGuidanceMixin:
-    """Reference-latent guidance (:323-411). Ranked "next" in SURVEY.md section 8f: it runs as
-    device-side torch ops after the fused step, not yet fused into it."""
+    """Reference-latent guidance (:323-411): after the fused step, x is pulled towards a reference
+    latent that has been given the per-batch-item mean / std of x (LINEAR) or of the denoised prediction
+    (EULER). Two launches per guided step: per-item moments, then the shift + blend / Euler update."""
 
     def __init__(self, cfg: GuidanceConfig | None = None) -> None:
         self.guidance = cfg
@@ -511,45 +522,46 @@ class SonarGuidanceMixin:
 
     @staticmethod
     def prepare_ref_latent(latent: Tensor | None) -> Tensor | None:
+        """Per-plane standardisation of the reference latent (:335-341); setup, once per sampler."""
         if latent is None:
             return None
         avg = latent.mean(dim=(-2, -1), keepdim=True)
         std = latent.std(dim=(-2, -1), keepdim=True)
         return (latent - avg).div_(std).to(latent.dtype)
 
+    def _guidance_ref(self, x: Tensor) -> Tensor:
+        ref = self.ref_latent
+        if ref.device != x.device or ref.dtype != torch.float32 or not ref.is_contiguous():
+            ref = self.ref_latent = ref.to(device=x.device, dtype=torch.float32).contiguous()
+        return ref
+
     def guidance_step(self, step_index: int, x: Tensor, denoised: Tensor) -> Tensor:
         g = self.guidance
         if g is None or g.factor == 0.0 or not g.start_step <= step_index <= g.end_step:
             return x
-        if self.ref_latent.device != x.device:
-            self.ref_latent = self.ref_latent.to(device=x.device)
+        ref = self._guidance_ref(x)
+        x = x.contiguous()
         if g.guidance_type == GuidanceType.LINEAR:
-            return self.guidance_linear(x, self.ref_latent, g.factor, blend=self.guidance_blend)
+            return self.guidance_linear(x, ref, g.factor, blend=self.guidance_blend)
         if g.guidance_type == GuidanceType.EULER:
-            return self.guidance_euler(
-                self.sigmas[step_index], self.sigmas[step_index + 1], x, denoised, self.ref_latent, g.factor,
-            )
+            sh = self.sigma_host_views
+            return self.guidance_euler(sh[step_index], sh[step_index + 1], x, denoised, ref, g.factor)
         raise ValueError("Sonar: Guidance: Unknown guidance type")
 
     @classmethod
-    def guidance_shift(cls, t: Tensor, ref_latent: Tensor, *, dim=None) -> Tensor:
-        if dim is None:
-            dim = tuple(range(-(t.ndim - 1), 0))
-        return (ref_latent * t.std(dim=dim, keepdim=True)).add_(t.mean(dim=dim, keepdim=True))
-
-    @classmethod
     def guidance_euler(cls, sigma, sigma_next, x, denoised, ref_latent, factor: float = 0.2, *, do_shift: bool = True):
-        if torch.equal(torch.as_tensor(sigma), torch.as_tensor(sigma_next)):
+        sigma, sigma_next = torch.as_tensor(sigma, dtype=torch.float32).cpu(), torch.as_tensor(sigma_next, dtype=torch.float32).cpu()
+        if torch.equal(sigma, sigma_next):
             return cls.guidance_linear(x, ref_latent, factor=factor, do_shift=do_shift)
-        target = cls.guidance_shift(denoised, ref_latent) if do_shift else ref_latent
-        d = (x - target) / sigma
-        return (d * ((sigma_next - sigma) * factor)).add_(x)
+        sums = ops.item_moments(denoised.to(torch.float32).contiguous()) if do_shift else None
+        dt = float((sigma_next - sigma) * factor)  # float32, like the reference's 0-d tensor arithmetic
+        return ops.guidance(x, ref_latent, sums, kind=ops.GUIDANCE_EULER, sigma=float(sigma), dt=dt)
 
     @classmethod
     def guidance_linear(cls, x, ref_latent, factor: float = 0.2, *, blend=None, do_shift: bool = True):
-        target = cls.guidance_shift(x, ref_latent) if do_shift else ref_latent
-        blend = hostutil.BLENDING_MODES["lerp"] if blend is None else blend
-        return blend(x.contiguous(), target.contiguous(), factor)
+        sums = ops.item_moments(x) if do_shift else None
+        mode = hostutil.blend_mode_id("lerp" if blend is None else blend)
+        return ops.guidance(x, ref_latent, sums, kind=ops.GUIDANCE_LINEAR, blend_mode=mode, factor=factor)
 
 
 class SonarWithGuidance(SonarBase, SonarGuidanceMixin):
@@ -787,8 +799,11 @@ class SonarDPMPPSDE(SonarSampler):
         denoised_2 = self.model(x_2, self._sigma_mid_in[step_index], **self.extra_args)
         # ---- stage 2 (fac = 1/(2r) = 1: denoised_d = 0*md1 + 1*md2) ----
         if guided:
+            # the reference guides with denoised_d = get_momentum_denoised(denoised_2) (:720, :731): in
+            # DENOISED mode that is the history-mixed prediction, which the fused launch keeps in registers
+            denoised_d = self._momentum_denoised_preview(step_index, denoised_2, sc["sigma_2"])
             out = self.fused_step(step_index, x, denoised_2, sc["sigma_2"], kind=ops.STEP_DPMPP, c0=sc["c0_2"], c1=sc["c1_2"])
-            out = self.guidance_step(step_index, out, denoised_2)
+            out = self.guidance_step(step_index, out, denoised_d)
             drawn = self.noise_sampler(sc["s_t"], sc["s_t_next"])
             return ops.axpby(out.contiguous(), 1.0, drawn.contiguous(), sc["ns_2"])
         noise_kw = self.ancestral_noise(x, sc["s_t"], sc["s_t_next"], sc["ns_2"])

@@ -173,6 +173,34 @@ typedef struct SonarStepParams {
 int sonar_step_f32(const SonarStepParams* params_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Reference-latent guidance epilogue (runs right after the fused step of a guided sampler).
+ * replaces: SonarGuidanceMixin.guidance_shift / guidance_linear / guidance_euler
+ *                                                          py/sonar.py:372-411
+ * sonar_item_moments_f32: sums[2*i], sums[2*i+1] are OVERWRITTEN with the sum / sum of squares of item i
+ * of a dense (items, per_item) tensor (the per-batch-item mean / unbiased std of guidance_shift).
+ * sonar_guidance_f32:  target = ref * std_i + mean_i  (statistics from item_sums; NULL = no shift)
+ *   LINEAR: out = blend(x, target, factor)          EULER: out = x + (x - target) / sigma * dt
+ * ref is (items, per_item), or (1, per_item) broadcast over the batch (ref_items == 1). out may alias x.
+ * ---------------------------------------------------------------------------------------------- */
+enum { SONAR_GUIDANCE_LINEAR = 0, SONAR_GUIDANCE_EULER = 1 };
+typedef struct SonarGuidanceParams {
+  const float* x;
+  const float* ref;
+  const double* item_sums; /* double[items][2] */
+  float* out;
+  int64_t items;
+  int64_t per_item;
+  int32_t ref_items;
+  int32_t kind;       /* SONAR_GUIDANCE_* */
+  int32_t blend_mode; /* SONAR_BLEND_*, LINEAR only */
+  float factor;       /* LINEAR only */
+  float sigma;        /* EULER only */
+  float dt;           /* EULER only: (sigma_next - sigma) * factor */
+} SonarGuidanceParams;
+int sonar_item_moments_f32(const float* x, int64_t items, int64_t per_item, double* sums, void* stream);
+int sonar_guidance_f32(const SonarGuidanceParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Pyramid family: fused multi-level resample-and-accumulate.
  *   out[p,y,x] = base_scale*base[p,y,x] + sum_i weights[i] * resample(levels[i][p] -> HxW)[y,x]
  * replaces: PyramidNoiseGenerator.generate                 py/noise_generation.py:621-649

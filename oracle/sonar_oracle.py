@@ -360,6 +360,35 @@ def power_noise(draws, shape, filter_rfft, *, factor=1.0, normalized=True, spect
 # =============================================================================================
 # Sonar samplers (reference py/sonar.py) -- elementwise recurrences, float32 like the reference
 # =============================================================================================
+# =============================================================================================
+# Reference-latent guidance (py/sonar.py:323-411)
+# =============================================================================================
+def prepare_ref_latent(latent: torch.Tensor) -> torch.Tensor:
+    """:335-341 -- per-plane standardisation of the reference latent."""
+    avg = latent.mean(dim=(-2, -1), keepdim=True)
+    std = latent.std(dim=(-2, -1), keepdim=True)
+    return (latent - avg).div_(std).to(latent.dtype)
+
+
+def guidance_shift(t: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """:372-378 -- give the reference the per-batch-item mean / (unbiased) std of `t`."""
+    dim = tuple(range(-(t.ndim - 1), 0))
+    return (ref * t.std(dim=dim, keepdim=True)).add_(t.mean(dim=dim, keepdim=True))
+
+
+def guidance_linear(x, ref, factor, blend=None):
+    """:400-411"""
+    return (blend or torch_lerp)(x, guidance_shift(x, ref), factor)
+
+
+def guidance_euler(sigma, sigma_next, x, denoised, ref, factor):
+    """:380-398 -- an Euler step of size (sigma_next - sigma) * factor towards the shifted reference."""
+    if torch.equal(torch.as_tensor(sigma), torch.as_tensor(sigma_next)):
+        return guidance_linear(x, ref, factor)
+    d = (x - guidance_shift(denoised, ref)) / sigma
+    return (d * ((sigma_next - sigma) * factor)).add_(x)
+
+
 class SonarOracle:
     """Restates SonarBase :70-320, SonarEuler.step :460-480, SonarEulerAncestral.step :541-573 and
     SonarDPMPPSDE.momentum_step :649-735. Noise tensors are passed in (already normalised)."""
@@ -378,8 +407,13 @@ class SonarOracle:
         blend_mode="lerp",
         momentum_blend_mode=None,
         history_blend_mode=None,
+        guidance_blend_mode=None,
         init_noise=None,
+        guidance=None,
     ):
+        # guidance: dict(guidance_type="LINEAR"|"EULER", factor, start_step, end_step, ref=prepared latent)
+        self.guidance = guidance
+        self.gblend = BLENDING_MODES[guidance_blend_mode or blend_mode]
         self.m, self.mh, self.direction = momentum, momentum_hist, direction
         self.mode, self.init = mode, init
         self.start, self.end, self.always = momentum_start_step, momentum_end_step, always_update_history
@@ -436,6 +470,18 @@ class SonarOracle:
         self.update(d if self.mode == "new" else md, step)
         return md if self.check(step) else d
 
+    def guide(self, step, x, den, sigma, sigma_next):  # guidance_step :343-369
+        g = self.guidance
+        if g is None or g["factor"] == 0.0 or not g["start_step"] <= step <= g["end_step"]:
+            return x
+        if g["guidance_type"] == "LINEAR":
+            return guidance_linear(x, g["ref"], g["factor"], blend=self.gblend)
+        return guidance_euler(sigma, sigma_next, x, den, g["ref"], g["factor"])
+
+    def euler_step(self, step, x, den, sigma, sigma_next):  # SonarEuler.step :460-480
+        out = self.euler(step, x, den, sigma, sigma_next)
+        return self.guide(step, out, den, sigma, sigma_next) if sigma_next > 0 else out
+
     def euler(self, step, x, den, sigma, sigma_down):  # :309-320
         dt = sigma_down - sigma
         den = self.momentum_denoised(x, den, sigma, step)
@@ -445,6 +491,7 @@ class SonarOracle:
         sigma_down, sigma_up = get_ancestral_step(sigma, sigma_next, eta=eta)
         out = self.euler(step, x, den, sigma, sigma_down)
         if sigma_next > 0:
+            out = self.guide(step, out, den, sigma, sigma_next)
             out = out + noise * (s_noise * sigma_up)
         return out
 
@@ -480,6 +527,7 @@ class SonarOracle:
         diff_1 = (t - t_down).expm1() * denoised_d
         mdv = self.momentum_d(x, md2, s_s, step, d=diff_1)
         out = ((sigma_fn(t_down) / s_t) * x).sub_(mdv)
+        out = self.guide(step, out, denoised_d, sigma, sigma_next)  # :731 (guided by denoised_d, not the raw output)
         out += noise2.clone().mul_(s_noise * su)
         return out
 

@@ -307,6 +307,53 @@ def gen_samplers(ref) -> None:
     save("samplers", {"x0": x0, "sigmas": sigmas, "cases": out})
 
 
+def gen_guidance(ref) -> None:
+    """Reference-latent guidance (py/sonar.py:323-411) through all three samplers: LINEAR (lerp and
+    inject blends) and EULER, a step window, a batch-broadcast reference latent."""
+    sonar = ref.py.sonar
+    sigmas = torch.cat((torch.linspace(12.0, 0.05, 6), torch.zeros(1)))
+    torch.manual_seed(500)
+    x0 = torch.randn(3, 4, 8, 12) * sigmas[0]
+    ref_full = torch.randn(3, 4, 8, 12) * 2.0 + 0.3
+    ref_one = torch.randn(1, 4, 8, 12) - 0.5
+    variants = {
+        "linear": ({"guidance_type": "LINEAR", "factor": 0.05, "start_step": 0, "end_step": 9999}, ref_full, {}),
+        "linear_window_one": ({"guidance_type": "LINEAR", "factor": 0.1, "start_step": 1, "end_step": 3}, ref_one, {}),
+        "linear_inject": ({"guidance_type": "LINEAR", "factor": 0.02, "start_step": 0, "end_step": 9999}, ref_full,
+                          {"guidance_blend_mode": "inject"}),
+        "euler": ({"guidance_type": "EULER", "factor": 0.2, "start_step": 0, "end_step": 9999}, ref_full, {}),
+        "euler_denoised_mode": ({"guidance_type": "EULER", "factor": 0.3, "start_step": 1, "end_step": 9999}, ref_one,
+                                {"momentum_mode": "denoised"}),
+    }
+    samplers = {
+        "euler": (sonar.SonarEuler.sampler, {}),
+        "euler_ancestral": (sonar.SonarEulerAncestral.sampler, {"eta": 1.0, "s_noise": 1.0}),
+        "dpmpp_sde": (sonar.SonarDPMPPSDE.sampler, {"eta": 1.0, "s_noise": 1.0}),
+    }
+    out = {}
+    for sname, (fn, skw) in samplers.items():
+        for vname, (gkw, latent, extra) in variants.items():
+            guidance = sonar.GuidanceConfig(
+                guidance_type=sonar.GuidanceType[gkw["guidance_type"]], factor=gkw["factor"],
+                start_step=gkw["start_step"], end_step=gkw["end_step"], latent=latent.clone(),
+            )  # fmt: skip
+            params = dict(extra)
+            if sname.startswith("dpmpp"):
+                params.setdefault("noise_type", "gaussian")
+            steps = []
+            torch.manual_seed(501)
+            with record_draws() as draws:
+                result = fn(
+                    stub_model, x0.clone(), sigmas, extra_args={"seed": 0}, disable=True,
+                    sonar_params=params | {"guidance": guidance}, callback=lambda d: steps.append(d["x"].clone()), **skw,
+                )  # fmt: skip
+            out[f"{sname}/{vname}"] = {
+                "params": params, "guidance": gkw, "latent": latent.clone(), "sampler_kwargs": skw, "draws": draws,
+                "out": result.clone(), "steps": torch.stack(steps),
+            }  # fmt: skip
+    save("guidance", {"x0": x0, "sigmas": sigmas, "cases": out})
+
+
 def gen_host_logic(ref) -> None:
     """Host-only behaviour: config merging errors, yh scale expansion, rule parsing."""
     sonar, wf = ref.py.sonar, ref.py.wavelet_functions
@@ -364,10 +411,16 @@ def main() -> None:
         raise SystemExit("make_golden.py needs the reference at /root/reference")
     torch.set_num_threads(1)
     ref = load_reference()
+    only = sys.argv[1:]  # e.g. `make_golden.py guidance` regenerates one fixture
+    if only:
+        for name in only:
+            globals()[f"gen_{name}"](ref)
+        return
     gen_noise_types(ref)
     gen_power_noise(ref)
     gen_graph(ref)
     gen_samplers(ref)
+    gen_guidance(ref)
     gen_host_logic(ref)
     gen_node_schemas(ref)
 

@@ -134,6 +134,8 @@ def sampler_oracle_run(kind: str, case: dict, x0: torch.Tensor, sigmas: torch.Te
         always_update_history=params.get("always_update_history", True),
         momentum_blend_mode=params.get("momentum_blend_mode"),
         history_blend_mode=params.get("history_blend_mode"),
+        guidance_blend_mode=params.get("guidance_blend_mode"),
+        guidance=None if "guidance" not in case else case["guidance"] | {"ref": orc.prepare_ref_latent(case["latent"])},
     )
     mult = params.get("rand_init_noise_multiplier", 1.0)
 
@@ -149,7 +151,7 @@ def sampler_oracle_run(kind: str, case: dict, x0: torch.Tensor, sigmas: torch.Te
         if o.init == "rand" and o.hist is None and o.init_noise is None:
             o.init_noise = normalised(next(draws)) * mult
         if kind == "euler":
-            x = o.euler(i, x, den, sigma, sigma_next)
+            x = o.euler_step(i, x, den, sigma, sigma_next)
         elif kind.startswith("euler_ancestral"):
             noise = normalised(next(draws)) if sigma_next > 0 else None
             x = o.euler_ancestral(i, x, den, sigma, sigma_next, noise, eta=eta, s_noise=s_noise)

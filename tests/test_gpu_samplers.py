@@ -215,3 +215,50 @@ def test_deferred_chain_normalisation_equals_explicit_scale_noise(sb, cuda):
         )
 
     assert_close(run(False), run(True), what="deferred vs explicit", rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["euler", "euler_ancestral", "dpmpp_sde"])
+def test_guidance_golden(sb, cuda, golden, kind):
+    """Reference-latent guidance (py/sonar.py:323-411) on the CUDA kernels vs the recorded reference:
+    LINEAR (lerp / inject) and EULER, a step window, a batch-broadcast latent, DENOISED momentum mode."""
+    g = golden("guidance")
+    cases = [(k, c) for k, c in g["cases"].items() if k.split("/")[0] == kind]
+    assert len(cases) == 5
+    s = sb.samplers
+    for key, case in cases:
+        gk = case["guidance"]
+        guidance = s.GuidanceConfig(
+            guidance_type=s.GuidanceType[gk["guidance_type"]], factor=gk["factor"], start_step=gk["start_step"],
+            end_step=gk["end_step"], latent=case["latent"].clone(),
+        )  # fmt: skip
+        steps = []
+        with sb.rng.injected(case["draws"]) as left:
+            out = _sampler(sb, kind)(
+                stub_model, g["x0"].to(cuda), g["sigmas"].to(cuda), extra_args={"seed": 0}, disable=True,
+                sonar_params=dict(case["params"]) | {"guidance": guidance}, callback=lambda d: steps.append(d["x"].clone()),
+                **case["sampler_kwargs"],
+            )  # fmt: skip
+            assert not left, f"{key}: unused recorded draws"
+        assert_close(torch.stack(steps), case["steps"], what=key, **TOL)
+        assert_close(out, case["out"], what=key + " final", **TOL)
+
+
+def test_guidance_kernels_vs_oracle(sb, cuda):
+    """item_moments + guidance kernels vs the oracle on odd sizes (scalar tails, unaligned views)."""
+    torch.manual_seed(12)
+    for shape, ref_batch in (((3, 4, 9, 7), 3), ((2, 5, 16, 16), 1), ((1, 3, 33, 5), 1)):
+        x, den = torch.randn(shape) * 3 + 0.5, torch.randn(shape) * 2 - 1
+        ref = orc.prepare_ref_latent(torch.randn(ref_batch, *shape[1:]))
+        xd, dd, rd = x.to(cuda), den.to(cuda), ref.to(cuda)
+        sums = sb.ops.item_moments(xd)
+        d64 = x.double().flatten(1)
+        torch.testing.assert_close(sums.cpu(), torch.stack((d64.sum(1), (d64 * d64).sum(1)), dim=1), rtol=1e-9, atol=1e-7)
+        for mode in ("lerp", "inject", "subtract_b"):
+            want = orc.guidance_linear(x, ref, 0.15, blend=orc.BLENDING_MODES[mode])
+            got = sb.ops.guidance(xd, rd, sums, kind=sb.ops.GUIDANCE_LINEAR, blend_mode=mode, factor=0.15)
+            assert_close(got, want, what=f"linear {mode} {shape}")
+        sigma, sigma_next = torch.tensor(7.0), torch.tensor(4.5)
+        want = orc.guidance_euler(sigma, sigma_next, x, den, ref, 0.3)
+        got = sb.ops.guidance(xd, rd, sb.ops.item_moments(dd), kind=sb.ops.GUIDANCE_EULER, sigma=7.0,
+                              dt=float((sigma_next - sigma) * 0.3))
+        assert_close(got, want, what=f"euler {shape}")

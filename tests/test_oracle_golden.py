@@ -174,6 +174,21 @@ def test_samplers(golden, sname):
     assert ran >= 2
 
 
+@pytest.mark.parametrize("sname", ["euler", "euler_ancestral", "dpmpp_sde"])
+def test_guidance(golden, sname):
+    """Reference-latent guidance (py/sonar.py:323-411): LINEAR / EULER, windows, blends, broadcast latent."""
+    g = golden("guidance")
+    ran = 0
+    for key, case in g["cases"].items():
+        kind, variant = key.split("/")
+        if kind != sname:
+            continue
+        steps = sampler_oracle_run(kind, case, g["x0"], g["sigmas"], stub_model)
+        assert_close(steps, case["steps"], what=key, rtol=2e-5, atol=2e-5)
+        ran += 1
+    assert ran == 5
+
+
 def test_expand_scales(golden):
     for spec, want in golden("host_logic")["expand"]:
         if any(isinstance(v, str) for v in (spec if isinstance(spec, list) else [])):
