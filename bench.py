@@ -252,8 +252,10 @@ def step_kernel_roofline(sb, dev, shape, peak: float, peak_src: str, reps: int) 
         x, den, hist = (torch.randn(shape, device=dev) for _ in range(3))
         draw = sb.ops.reserve_draw(n, dev)
         sums = sb.ops.philox_normal_moments_batch(draw, [draw.offset], begin=0, count=n, device=dev)
+        dec = sb.ops.norm_decisions(sums, n)
         stepper = sb.samplers.SonarBase(sb.samplers.SonarConfig())
-        kw = {"draw": draw, "factor": 1.0, "normalized": True, "begin": 0, "sums": sums, "sums_ptr": sums.data_ptr(), "count": n}
+        kw = {"draw": draw, "factor": 1.0, "normalized": True, "begin": 0, "sums": (sums, dec), "sums_ptr": sums.data_ptr(),
+              "decision_ptr": dec.data_ptr(), "count": n}
         sets.append((stepper, x, den, hist, kw))
     outs = []
 

@@ -57,6 +57,7 @@ class SonarStepParams(ctypes.Structure):
         ("noise_numel_total", c_int64),
         ("noise_sums", c_void_p),
         ("noise_count", c_int64),
+        ("noise_decision", c_void_p),
         ("peer_world", c_int32),
         ("peer_mailbox", c_void_p),
         ("peer_epoch", c_double),
@@ -259,6 +260,7 @@ SIGNATURES: dict[str, list] = {
     "sonar_philox_normal_moments_batch": [
         POINTER(c_uint64), c_int, c_int64, c_int64, c_int64, c_uint64, c_uint32, c_void_p, c_void_p,
     ],
+    "sonar_norm_decisions": [c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p],
     "sonar_scale_noise_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p],
     "sonar_scale_by_std_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p],
     "sonar_affine_f32": [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p],

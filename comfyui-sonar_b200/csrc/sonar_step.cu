@@ -309,16 +309,26 @@ __device__ __forceinline__ void step_pair_fast(const SonarStepParams& p, const F
   }
 }
 
+// scale_noise decision for the regenerated normals: either precomputed once per draw
+// (sonar_norm_decisions: 16 bytes every thread loads, no barrier) or evaluated by thread 0 of each
+// CTA from the raw sums (a fp64 divide + sqrt behind a __syncthreads: ~23 % of the warp stall
+// cycles of the C2 launch in the round-1 ncu capture).
+__device__ __forceinline__ NormDecision philox_noise_decision(const SonarStepParams& p, NormDecision* slot) {
+  if (p.noise_kind != SONAR_NOISE_PHILOX_NORMALIZED) return NormDecision{0.f, 1.f, 0, 0};
+  if (p.noise_decision != nullptr) {  // launch-uniform
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p.noise_decision));
+    return NormDecision{d.x, d.y, d.z != 0.0f ? 1 : 0, d.w != 0.0f ? 1 : 0};
+  }
+  return decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, slot);
+}
+
 constexpr int kPhiloxStepBlock = 128;  // finer-grained CTAs: the 1.6-wave tail of 256-thread CTAs costs ~10 %
 
 template <int KIND, bool NEW_MODE, bool HAVE_H>
 __global__ void __launch_bounds__(kPhiloxStepBlock)
 sonar_step_fast_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint32_t k_hi) {
   __shared__ NormDecision nd_slot;
-  const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
-                              ? decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot)
-                              : NormDecision{0.f, 1.f, 0, 0};
-  const NoiseNorm nn = make_noise_norm(nd, p.noise_factor);
+  const NoiseNorm nn = make_noise_norm(philox_noise_decision(p, &nd_slot), p.noise_factor);
   const FastConsts c = make_fast_consts(p);
   const int64_t T = st.threads;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -341,10 +351,7 @@ template <int KIND, bool NEW_MODE, bool HAVE_H>
 __global__ void __launch_bounds__(kBlock, 8)
 sonar_step_fast_philox2_kernel(SonarStepParams p, PhiloxStream st) {
   __shared__ NormDecision nd_slot;
-  const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
-                              ? decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot)
-                              : NormDecision{0.f, 1.f, 0, 0};
-  const NoiseNorm nn = make_noise_norm(nd, p.noise_factor);
+  const NoiseNorm nn = make_noise_norm(philox_noise_decision(p, &nd_slot), p.noise_factor);
   const FastConsts c = make_fast_consts(p);
   const int64_t T = st.threads;
   const int64_t begin = p.noise_begin, end = p.noise_begin + p.n;
@@ -390,9 +397,12 @@ sonar_step_philox_kernel(SonarStepParams p, PhiloxStream st, uint32_t k_lo, uint
   const bool has_h_in = p.hist_state != SONAR_HIST_NONE;
   const bool write_h = p.hist_out != nullptr;
   __shared__ NormDecision nd_slot;
-  const NormDecision nd = p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED
-                              ? decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot)
-                              : NormDecision{0.f, 1.f, 0, 0};
+  const NormDecision nd = p.noise_kind != SONAR_NOISE_PHILOX_NORMALIZED
+                              ? NormDecision{0.f, 1.f, 0, 0}
+                              : (p.noise_decision != nullptr
+                                     ? NormDecision{p.noise_decision[0], p.noise_decision[1], p.noise_decision[2] != 0.0f ? 1 : 0,
+                                                    p.noise_decision[3] != 0.0f ? 1 : 0}
+                                     : decide_normalisation_block(p.noise_sums, p.noise_count, p.noise_threshold_std_devs, &nd_slot));
   const NoiseNorm nn = make_noise_norm(nd, p.noise_factor);
   const StepConsts c = make_consts(p);
   const int64_t T = st.threads;
@@ -481,7 +491,9 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
     return (int)cudaErrorInvalidValue;
   if (p.peer_world > 1 && (p.peer_mailbox == nullptr || p.peer_world > SONAR_PEER_MAX_RANKS))
     return (int)cudaErrorInvalidValue;
-  if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr) return (int)cudaErrorInvalidValue;
+  if (p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED && p.noise_sums == nullptr && p.noise_decision == nullptr)
+    return (int)cudaErrorInvalidValue;
+  if (p.noise_decision != nullptr && (reinterpret_cast<uintptr_t>(p.noise_decision) & 15u)) return (int)cudaErrorInvalidValue;
   cudaStream_t stream = (cudaStream_t)stream_;
 
   if (p.noise_kind == SONAR_NOISE_PHILOX || p.noise_kind == SONAR_NOISE_PHILOX_NORMALIZED) {

@@ -133,6 +133,17 @@ philox_normal_moments_batch_kernel(int64_t begin, int64_t end, PhiloxStream st, 
   }
 }
 
+// sums[i] -> the scale_noise decision of draw i as float[4] = {mean, std, subtract-mean flag, divide flag}:
+// evaluated ONCE per draw (fp64), so the kernels that consume it load 16 bytes instead of running a
+// fp64 divide + sqrt behind a barrier in every CTA.
+__global__ void norm_decisions_kernel(const double* __restrict__ sums, int n, int64_t count, float threshold_std_devs,
+                                      float* __restrict__ decisions) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const NormDecision d = decide_normalisation(sums + 2 * i, count, threshold_std_devs);
+  reinterpret_cast<float4*>(decisions)[i] = make_float4(d.mean, d.std, d.sub_mean ? 1.0f : 0.0f, d.div_std ? 1.0f : 0.0f);
+}
+
 // One pass: materialise the slice of a Philox normal draw AND reduce its moments (for tensors too
 // large to keep the normals in registers across a grid barrier: write once, read once).
 __global__ void __launch_bounds__(kBlock)
@@ -266,6 +277,16 @@ int sonar_philox_normal_moments_batch(const uint64_t* offsets_host, int n_draws,
         begin, end, s, offs, (uint32_t)k_lo, (uint32_t)k_hi, sums + 2 * first);
     SONAR_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int sonar_norm_decisions(const double* sums, int n, int64_t count, float threshold_std_devs, float* decisions,
+                         void* stream) {
+  if (n <= 0) return 0;
+  if (sums == nullptr || decisions == nullptr || count <= 0 || (reinterpret_cast<uintptr_t>(decisions) & 15u))
+    return (int)cudaErrorInvalidValue;
+  sonar::norm_decisions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, n, count, threshold_std_devs, decisions);
+  SONAR_LAUNCH_CHECK();
   return 0;
 }
 

@@ -333,6 +333,15 @@ def philox_normal_moments_batch(
     return sums
 
 
+def norm_decisions(sums: torch.Tensor, count: int, *, threshold_std_devs: float = 2.5) -> torch.Tensor:
+    """(K, 4) float32 = (mean, std, subtract flag, divide flag) of scale_noise for each row of `sums` (K, 2)."""
+    k = sums.shape[0]
+    out = torch.empty((k, 4), device=sums.device, dtype=torch.float32)
+    lib, stream = _prepare(sums, out)
+    _launch("sonar_norm_decisions", lib.sonar_norm_decisions, _ptr(sums), k, int(count), float(threshold_std_devs), _ptr(out), stream)
+    return out
+
+
 def scale_noise_apply(
     x: torch.Tensor,
     sums: torch.Tensor,

@@ -303,6 +303,7 @@ class SonarBase:
                 else:  # regenerated in registers; sums reduced ahead of time (look-ahead batch)
                     keep = noise_philox["sums"]
                     p.noise_kind, p.noise_sums = ops.NOISE_PHILOX_NORMALIZED, noise_philox["sums_ptr"]
+                    p.noise_decision = noise_philox.get("decision_ptr", 0)
                 p.noise_count = noise_philox["count"]
             else:
                 p.noise_kind = ops.NOISE_PHILOX
@@ -326,8 +327,9 @@ class SonarBase:
             self.history_d = hist_out
         return x_out
 
-    def _lookahead_sums(self, draw: ops.PhiloxDraw, begin: int, count: int, device) -> tuple[Tensor, int]:
-        """Device (sum, sum^2) of the whole (global) normal draw `draw`, as (keep-alive tensor, pointer).
+    def _lookahead_sums(self, draw: ops.PhiloxDraw, begin: int, count: int, device, total: int) -> tuple[Tensor, int, int]:
+        """Device statistics of the whole (global) normal draw `draw`: (keep-alive, pointer to its
+        (sum, sum^2), pointer to its precomputed scale_noise decision).
 
         First request of a run: ONE batched launch reduces the moments of this rank's slice of this
         draw and of the next `noise_draws_left - 1` draws (their offsets follow from the generator's
@@ -346,12 +348,15 @@ class SonarBase:
             offsets = [draw.offset + j * draw.counter_offset for j in range(k)]
             sums = ops.philox_normal_moments_batch(draw, offsets, begin=begin, count=count, device=device)
             parallel.allreduce_table(sums)  # sharded: sum the partial sums over ranks, once per table
+            # the conditional normalisation of every draw, decided once (fp64) instead of in every CTA of
+            # every step launch
+            decisions = ops.norm_decisions(sums, total)
             la = self._lookahead = {
-                "key": key, "index": {o: j for j, o in enumerate(offsets)}, "sums": sums, "ptr": sums.data_ptr(),
-                "inc": draw.counter_offset,
+                "key": key, "index": {o: j for j, o in enumerate(offsets)}, "sums": (sums, decisions),
+                "ptr": sums.data_ptr(), "dec_ptr": decisions.data_ptr(), "inc": draw.counter_offset,
             }  # fmt: skip
             idx = 0
-        return la["sums"], la["ptr"] + 16 * idx
+        return la["sums"], la["ptr"] + 16 * idx, la["dec_ptr"] + 16 * idx
 
     # ------------------------------------------------------------------------------------
     # stock lane: ZERO-init history + (optional) fused Gaussian noise, nothing else configured
@@ -403,6 +408,7 @@ class SonarBase:
                 if idx is None or la["key"][0] != gen.initial_seed() or la["key"][2] != x.numel():
                     return None  # first draw of the run, or somebody else advanced the generator: re-plan
                 p.noise_kind, p.noise_sums, p.noise_count = ops.NOISE_PHILOX_NORMALIZED, la["ptr"] + 16 * idx, x.numel()
+                p.noise_decision = la["dec_ptr"] + 16 * idx
                 grid, inc = la["key"][1], la["inc"]
             else:
                 p.noise_kind = ops.NOISE_PHILOX
@@ -491,7 +497,7 @@ class SonarBase:
         draw = ops.reserve_draw(total, x.device)
         kw = {"draw": draw, "factor": factor, "normalized": normalized, "begin": begin}
         if normalized:
-            kw["sums"], kw["sums_ptr"] = self._lookahead_sums(draw, begin, x.numel(), x.device)
+            kw["sums"], kw["sums_ptr"], kw["decision_ptr"] = self._lookahead_sums(draw, begin, x.numel(), x.device, total)
             kw["count"] = total
         self.noise_draws_left -= 1
         return {"noise_philox": kw, "noise_scale": scale}

@@ -90,6 +90,10 @@ int sonar_philox_normal_moments(int64_t begin, int64_t count, int64_t numel_tota
 int sonar_philox_normal_moments_batch(const uint64_t* offsets_host, int n_draws, int64_t begin, int64_t count,
                                       int64_t numel_total, uint64_t seed, uint32_t grid_blocks, double* sums,
                                       void* stream);
+/* decisions[4*i .. 4*i+3] = {mean, std, subtract-mean flag, divide flag} of scale_noise (py/utils.py:100-106)
+ * for the n statistics sums[2*i], sums[2*i+1] over `count` elements each. */
+int sonar_norm_decisions(const double* sums, int n, int64_t count, float threshold_std_devs, float* decisions,
+                         void* stream);
 /* materialise the slice AND write (not accumulate) its moments into sums, one pass */
 int sonar_philox_normal_fill_moments_f32(float* out, int64_t begin, int64_t count, int64_t numel_total, uint64_t seed,
                                          uint64_t offset, uint32_t grid_blocks, double* sums, void* stream);
@@ -162,6 +166,10 @@ typedef struct SonarStepParams {
    * when the batch is sharded); TENSOR_NORMALIZED: reduced by the producer of `noise`. */
   const double* noise_sums;
   int64_t noise_count; /* global element count behind noise_sums */
+  /* PHILOX_NORMALIZED, optional: float[4] = {mean, std, subtract-mean flag, divide flag} from
+   * sonar_norm_decisions (16-byte aligned). Takes precedence over noise_sums: the decision is then a
+   * 16-byte load instead of fp64 arithmetic behind a barrier in every CTA. */
+  const float* noise_decision;
   /* TENSOR_NORMALIZED with batch-sharded statistics over peer memory (see sonar_peer_*): when
    * peer_world > 1 the kernel waits until all peer_world partial sums of `peer_epoch` have landed in
    * the LOCAL mailbox `peer_mailbox` and normalises with their total (noise_sums is ignored). */
