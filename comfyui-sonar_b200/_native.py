@@ -264,6 +264,7 @@ SIGNATURES: dict[str, list] = {
     "sonar_scale_noise_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p],
     "sonar_scale_by_std_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p],
     "sonar_affine_f32": [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p],
+    "sonar_div_scalar_f32": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
     "sonar_step_f32": [POINTER(SonarStepParams), c_void_p],
     "sonar_philox_normal_fill_moments_f32": [
         c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p,

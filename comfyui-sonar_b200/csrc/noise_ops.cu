@@ -457,6 +457,14 @@ axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__
   commit_moments(sums, sums_clear, ms, mss);
 }
 
+// out = x / d with a correctly rounded quotient (tensor.div_(python scalar), e.g. the octave-noise
+// "result /= total_amplitude", py/noise_generation.py:2325)
+__global__ void __launch_bounds__(kBlock)
+div_scalar_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, float d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] / d;
+}
+
 // out = ((x + pre) * mul) + post with three separately rounded steps (sub_/mul_/add_ chains such as
 // UniformNoiseGenerator.generate, py/noise_generation.py:508-514, stay bit-exact)
 __global__ void __launch_bounds__(kBlock)
@@ -663,6 +671,14 @@ int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, flo
     axpby_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums, sums_clear);
   else
     axpby_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, out, n, sums, sums_clear);
+  SONAR_LAUNCH_CHECK();
+  return 0;
+}
+
+int sonar_div_scalar_f32(const float* x, float* out, int64_t n, float divisor, void* stream) {
+  if (n <= 0) return 0;
+  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
+  sonar::div_scalar_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(x, out, n, divisor);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import math
 from enum import Enum, auto
-from typing import Callable
+from typing import Callable, NamedTuple
 
 import torch
 
@@ -448,6 +448,115 @@ class OneFNoiseGenerator(_SpectralGainGenerator):
         return self.fix_output_frames(self.filtered().to(self.dtype))
 
 
+class WaveletNoiseOctave(NamedTuple):
+    octave: int
+    height: float
+    width: float
+    amplitude: float
+    total_amplitude: float
+
+
+class WaveletNoiseGenerator(FramesToChannelsNoiseGenerator):
+    """Octave ("wavelet") noise (:2204-2327): per octave, a draw minus its own low-pass (area pool down,
+    bilinear up), resized to the latent and accumulated with a geometric amplitude. Built from the
+    resampling, blend and axpby kernels; the draws of all octaves share one batched Philox launch."""
+
+    name = "wavelet"
+    MIN_DIMS = 4
+    MAX_DIMS = 5
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {
+            "octave_scale_mode": "adaptive_avg_pool2d",
+            "octave_rescale_mode": "bilinear",
+            "post_octave_rescale_mode": "bilinear",
+            "initial_amplitude": 1.0,
+            "persistence": 0.5,
+            "octaves": 4,
+            "octave_height_factor": 0.5,
+            "octave_width_factor": 0.5,
+            "height_factor": 2.0,
+            "width_factor": 2.0,
+            "min_height": 4,
+            "min_width": 4,
+            "update_blend": 1.0,
+            "update_blend_function": "lerp",
+            "noise_sampler": None,
+        }
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.set_octave_data()
+
+    def set_internal_noise_sampler(self, noise_sampler) -> None:
+        self.noise_sampler = noise_sampler
+
+    def set_octave_data(self) -> None:
+        """Octave sizes / amplitudes, host arithmetic identical to the reference (:2238-2278)."""
+        height, width = self.get_adjusted_shape()[-2:]
+        amplitude, total_amplitude = self.initial_amplitude, 0.0
+        curr_height, curr_width = height, width
+        octave_data = []
+        is_reverse = self.octaves < 0
+        octaves = range(self.octaves) if not is_reverse else reversed(range(abs(self.octaves)))
+        for octave in octaves:
+            curr_height /= self.height_factor**octave
+            curr_width /= self.width_factor**octave
+            if (
+                amplitude == 0
+                or curr_height < self.min_height
+                or curr_width < self.min_width
+                or curr_height * self.octave_height_factor < 1
+                or curr_width * self.octave_width_factor < 1
+            ):
+                if is_reverse and not octave_data:
+                    curr_height, curr_width = height, width
+                    continue
+                break
+            total_amplitude += abs(amplitude)
+            octave_data.append(WaveletNoiseOctave(octave, curr_height, curr_width, amplitude, total_amplitude))
+            amplitude *= self.persistence
+        if not octave_data or not total_amplitude:
+            raise ValueError("Unworkable parameters for wavelet noise")
+        self.octave_data = tuple(octave_data)
+
+    def _octave_detail(self, noise: torch.Tensor) -> torch.Tensor:
+        height, width = noise.shape[-2:]
+        scaled_height = int(max(1, height * self.octave_height_factor))
+        scaled_width = int(max(1, width * self.octave_width_factor))
+        low = hostutil.scale_samples(noise, scaled_width, scaled_height, mode=self.octave_scale_mode)
+        low = hostutil.scale_samples(low.contiguous(), width, height, mode=self.octave_rescale_mode).contiguous()
+        detail = ops.axpby(noise, 1.0, low, -1.0)  # noise - scaled_noise
+        blend = self.update_blend_function
+        if callable(blend) and blend is not torch.lerp:
+            return blend(noise, detail, self.update_blend)
+        return ops.blend(noise, detail, self.update_blend, mode="lerp" if callable(blend) else blend)
+
+    def generate(self, *args):
+        adjusted = self.get_adjusted_shape()
+        height, width = adjusted[-2:]
+        shapes = [(*adjusted[:-2], int(od.height), int(od.width)) for od in self.octave_data]
+        if self.noise_sampler:
+            draws = [self.noise_sampler(*args)[..., : shp[-2], : shp[-1]].reshape(shp).contiguous() for shp in shapes]
+        else:
+            with rng.batched():  # every octave's draw in one launch, reserved in the reference's order
+                draws = [self.rand_like(shape=shp) for shp in shapes]
+        result = None
+        for od, noise in zip(self.octave_data, draws):
+            if noise.dtype != torch.float32:
+                noise = noise.float()
+            octave = self._octave_detail(noise)
+            if tuple(octave.shape[-2:]) != (height, width):
+                octave = hostutil.scale_samples(octave.contiguous(), width, height, mode=self.post_octave_rescale_mode).contiguous()
+            # result += octave_output.mul_(amplitude): product rounded, then added
+            result = ops.axpby(octave, od.amplitude, None) if result is None else ops.axpby(result, 1.0, octave, od.amplitude, out=result)
+        total = self.octave_data[-1].total_amplitude
+        if total != 0:
+            result = ops.divide_scalar(result, total)
+        return self.fix_output_frames(result.to(self.dtype))
+
+
 class PowerLawNoiseGenerator(NoiseGenerator):
     name = "powerlaw"
 
@@ -534,7 +643,6 @@ PowerOldNoiseGenerator = _unsupported("power_old", "documented as wrong upstream
 PinkOldNoiseGenerator = _unsupported("pink_old", "documented as wrong upstream")
 VoronoiNoiseGenerator = _unsupported("voronoi", "not on the configured hot path")
 CollatzNoiseGenerator = _unsupported("collatz", "not on the configured hot path")
-WaveletNoiseGenerator = _unsupported("wavelet", "ranked 'next' in SURVEY.md section 8f")
 WaveletFilteredNoiseGenerator = _unsupported("wavelet_filtered", "ranked 'next' in SURVEY.md section 8f")
 ScatternetFilteredNoiseGenerator = _unsupported("scatternet_filtered", "needs pytorch_wavelets ScatLayer")
 

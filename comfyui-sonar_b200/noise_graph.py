@@ -642,7 +642,7 @@ NOISE_SAMPLERS: dict[NoiseType, Callable] = {
     NoiseType.DISTRO: _todo(NoiseType.DISTRO, "torch.distributions zoo"),
     NoiseType.STUDENTT: _todo(NoiseType.STUDENTT, "torch.distributions sampler"),
     NoiseType.LAPLACIAN: _todo(NoiseType.LAPLACIAN, "torch.distributions sampler"),
-    NoiseType.WAVELET: _todo(NoiseType.WAVELET, "ranked 'next', SURVEY.md section 8f"),
+    NoiseType.WAVELET: NoiseSampler.wrap(WaveletNoiseGenerator),
     NoiseType.PINK_OLD: _todo(NoiseType.PINK_OLD, "documented as wrong upstream"),
     NoiseType.POWER_OLD: _todo(NoiseType.POWER_OLD, "documented as wrong upstream"),
     NoiseType.PYRAMID_BISLERP: _todo(NoiseType.PYRAMID_BISLERP, "bislerp lives in ComfyUI"),

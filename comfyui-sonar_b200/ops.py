@@ -443,6 +443,15 @@ def affine(x: torch.Tensor, pre_add: float, mul: float, post_add: float, out: to
     return out
 
 
+def divide_scalar(x: torch.Tensor, divisor: float) -> torch.Tensor:
+    """x /= divisor (in place), IEEE division like Tensor.div_(scalar)."""
+    _f32(x, "x")
+    lib, stream = _prepare(x)
+    drop_sums(x)
+    _launch("sonar_div_scalar_f32", lib.sonar_div_scalar_f32, _ptr(x), _ptr(x), x.numel(), float(divisor), stream)
+    return x
+
+
 def scale_by_std(x: torch.Tensor, sums: torch.Tensor, count: int, scale: float) -> torch.Tensor:
     """x *= scale / std(x) (in place), std from device sums."""
     _f32(x, "x")

@@ -271,6 +271,7 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
  *           CompositeNoise noise_sampler                   py/noise.py:524-531
  *           MixedNoiseGenerator.generate accumulate        py/noise_generation.py:240-249
  *           PowerLawNoiseGenerator.generate                py/noise_generation.py:775-786
+ *           WaveletNoiseGenerator.generate (octave noise)  py/noise_generation.py:2204-2327
  *           normalize_to_scale                             py/utils.py:452-470
  * blend: out = mode(a, b, t) with t = t_tensor[i] if t_tensor else t_scalar. `out` may alias a or b.
  * axpby: out = a*alpha + b*beta (b may be NULL).
@@ -288,6 +289,8 @@ int sonar_axpby_f32(const float* a, float alpha, const float* b, float beta, flo
 /* out = ((x + pre_add) * mul) + post_add, each step rounded (UniformNoiseGenerator.generate,
  * py/noise_generation.py:508-514) */
 int sonar_affine_f32(const float* x, float* out, int64_t n, float pre_add, float mul, float post_add, void* stream);
+/* out = x / divisor, IEEE division (Tensor.div_(scalar); WaveletNoiseGenerator.generate, py/noise_generation.py:2325) */
+int sonar_div_scalar_f32(const float* x, float* out, int64_t n, float divisor, void* stream);
 int sonar_composite_f32(const float* dst, const float* src, const float* mask, float* out, int64_t batch,
                         int64_t channels, int64_t hw, void* stream);
 int sonar_powerlaw_f32(const float* x, float* out, int64_t n, float alpha, int use_sign, void* stream);

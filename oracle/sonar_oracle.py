@@ -281,6 +281,39 @@ def green_test_noise(draws, shape, scale_fac=1.0, x_pow=2, y_pow=2, power_base=1
     return torch.real(noise)
 
 
+def wavelet_octaves(height, width, *, octaves=4, initial_amplitude=1.0, persistence=0.5, height_factor=2.0,
+                    width_factor=2.0, min_height=4, min_width=4, octave_height_factor=0.5, octave_width_factor=0.5):
+    """WaveletNoiseGenerator.set_octave_data py/noise_generation.py:2238-2278 (forward octave order)."""
+    amp, total, ch, cw, out = initial_amplitude, 0.0, height, width, []
+    for octave in range(octaves):
+        ch /= height_factor**octave
+        cw /= width_factor**octave
+        if amp == 0 or ch < min_height or cw < min_width or ch * octave_height_factor < 1 or cw * octave_width_factor < 1:
+            break
+        total += abs(amp)
+        out.append((int(ch), int(cw), amp, total))
+        amp *= persistence
+    return out
+
+
+def wavelet_noise(draws, shape, **kw):
+    """WaveletNoiseGenerator.generate / _generate_octave py/noise_generation.py:2280-2327, defaults:
+    adaptive_avg_pool2d down by 0.5, bilinear up, detail = noise - low-pass, update_blend 1."""
+    b, c, h, w = shape
+    ohf, owf = kw.get("octave_height_factor", 0.5), kw.get("octave_width_factor", 0.5)
+    octs = wavelet_octaves(h, w, **kw)
+    result = torch.zeros(shape)
+    for oh, ow, amp, _total in octs:
+        noise = _next(draws, (b, c, oh, ow))
+        sh, sw = int(max(1, oh * ohf)), int(max(1, ow * owf))
+        low = F.interpolate(F.adaptive_avg_pool2d(noise, (sh, sw)), size=(oh, ow), mode="bilinear")
+        octave = torch.lerp(noise, noise - low, 1.0)
+        if octave.shape != result.shape:
+            octave = F.interpolate(octave, size=(h, w), mode="bilinear")
+        result += octave.mul_(amp)
+    return result / octs[-1][3]
+
+
 def powerlaw_noise(draws, alpha=2.0, div_max_dims=None, use_sign=False, use_div_max_abs=True):
     """PowerLawNoiseGenerator.generate :775-786."""
     noise = _next(draws)

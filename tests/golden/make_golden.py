@@ -104,13 +104,15 @@ def gen_noise_types(ref) -> None:
         "grey": (2, 4, 8, 8),
         "velvet": (2, 4, 8, 8),
         "violet": (2, 4, 8, 8),
+        "wavelet": (2, 3, 32, 32),
+        "wavelet_odd": (1, 2, 36, 52),
     }
     out = {}
     for i, (name, shape) in enumerate(cases.items()):
         torch.manual_seed(100 + i)
         x = torch.zeros(shape)
         with record_draws() as draws:
-            ns = noise.get_noise_sampler(name, x, None, None, seed=0, cpu=True, normalized=True)
+            ns = noise.get_noise_sampler(name.split("_odd")[0], x, None, None, seed=0, cpu=True, normalized=True)
             result = ns(None, None)
         out[name] = {"shape": shape, "draws": draws, "out": result.clone()}
     # 5-D latent through frames-to-channels generators

@@ -94,6 +94,8 @@ def oracle_noise_type(name: str, case: dict) -> torch.Tensor:
         a = orc.scale_noise(orc.green_test_noise(it, shape4)).mul_(0.55)
         b = orc.scale_noise(orc.green_test_noise(it, shape4)).mul_(0.7)
         out = a.add_(b).mul_(1.15)
+    elif name in {"wavelet", "wavelet_odd"}:
+        out = orc.wavelet_noise(it, shape4)
     elif name == "white":
         out = orc.powerlaw_noise(it, alpha=0.0, use_sign=True)
     elif name == "grey":
@@ -113,7 +115,7 @@ def oracle_noise_type(name: str, case: dict) -> torch.Tensor:
 NOISE_TYPE_NAMES = (
     "gaussian", "uniform", "perlin", "pyramid", "pyramid_discount5", "pyramid_area", "pyramid_mix", "pyramid_old",
     "highres_pyramid", "onef_pinkish", "onef_greenish", "onef_pinkish_mix", "onef_pinkishgreenish", "green_test",
-    "rainbow_mild", "white", "grey", "velvet", "violet", "pyramid_5d",
+    "rainbow_mild", "white", "grey", "velvet", "violet", "wavelet", "wavelet_odd", "pyramid_5d",
 )  # fmt: skip
 
 
