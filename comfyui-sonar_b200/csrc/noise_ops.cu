@@ -134,43 +134,73 @@ pyramid_accum_kernel(SonarPyramidParams p) {
 // the float divisions and tap arithmetic of the generic path.
 // VEC = 4: each lane owns 4 consecutive pixels (W % 4 == 0, 16-byte aligned rows): base, full-size
 // level and output move as float4; VEC = 1: any width / alignment.
+//
+// Bilinear levels are evaluated rows-first: for an output row the warp blends the two source rows of a
+// coarse level ONCE into a per-warp shared-memory row v[i] = wy0*r0[i] + wy1*r1[i] (lw values), and every
+// pixel then needs two shared-memory reads and one lerp per level instead of four gathers and three
+// lerps. ATen evaluates columns-first; the two orders agree to ~1 ulp (parity bar for interpolation:
+// 1e-5). Nearest-exact levels copy the single source row.
+struct PyrTap {  // one x (or y) tap: source indices and the weight of the second one
+  unsigned short i0, i1;
+  float w1;
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(kBlock)
-pyramid_rows_kernel(SonarPyramidParams p) {
+pyramid_rows_kernel(SonarPyramidParams p, int row_pitch) {
   extern __shared__ __align__(16) unsigned char pyr_smem[];
-  const int W = p.W, H = p.H;
-  // structure-of-arrays tables [n_levels][W]
-  int* tab_i0 = reinterpret_cast<int*>(pyr_smem);
-  int* tab_i1 = tab_i0 + p.n_levels * W;
-  float* tab_w1 = reinterpret_cast<float*>(tab_i1 + p.n_levels * W);
-  // VEC = 4: lane l reads the taps of pixels 4l + v, v = 0..3 -- stored as [v][W/4] so that the 32 lanes
-  // of a warp hit 32 consecutive words (a [x] layout would be a 4-way bank conflict)
+  const int W = p.W, H = p.H, NL = p.n_levels;
+  // x taps [n_levels][W] (VEC = 4: stored [v][W/4] so the 32 lanes of a warp read 32 consecutive
+  // entries), y taps [n_levels][H], then one blended-row scratch [n_levels][row_pitch] per warp
+  PyrTap* xtab = reinterpret_cast<PyrTap*>(pyr_smem);
+  PyrTap* ytab = xtab + NL * W;
+  float* vrows = reinterpret_cast<float*>(ytab + NL * H) + (size_t)(threadIdx.x >> 5) * NL * row_pitch;
+  const bool bilinear = p.mode == SONAR_RESAMPLE_BILINEAR;
   const int Wq = W / VEC;
-  for (int i = threadIdx.x; i < p.n_levels * W; i += blockDim.x) {
-    const int l = i / W, x = i - l * W;
-    const int lw = p.level_w[l];
-    const int slot = l * W + (VEC == 4 ? (x & 3) * Wq + (x >> 2) : x);
-    if (p.mode == SONAR_RESAMPLE_BILINEAR) {
-      const LinTap lt = linear_tap(x, lw, (float)lw / (float)W);
-      tab_i0[slot] = lt.i0;
-      tab_i1[slot] = lt.i1;
-      tab_w1[slot] = lt.w1;
+  for (int i = threadIdx.x; i < NL * (W + H); i += blockDim.x) {
+    const bool is_x = i < NL * W;
+    const int j = is_x ? i : i - NL * W, n = is_x ? W : H;
+    const int l = j / n, pos = j - l * n;
+    const int ln = is_x ? p.level_w[l] : p.level_h[l];
+    PyrTap t;
+    if (bilinear) {
+      const LinTap lt = linear_tap(pos, ln, (float)ln / (float)n);
+      t.i0 = (unsigned short)lt.i0;
+      t.i1 = (unsigned short)lt.i1;
+      t.w1 = lt.w1;
     } else {
-      tab_i0[slot] = tab_i1[slot] = nearest_exact_idx(x, lw, (float)lw / (float)W);
-      tab_w1[slot] = 0.0f;
+      t.i0 = t.i1 = (unsigned short)nearest_exact_idx(pos, ln, (float)ln / (float)n);
+      t.w1 = 0.0f;
     }
+    if (is_x)
+      xtab[l * W + (VEC == 4 ? (pos & 3) * Wq + (pos >> 2) : pos)] = t;
+    else
+      ytab[j] = t;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const int64_t n_rows = p.planes * (int64_t)H;
-  const bool bilinear = p.mode == SONAR_RESAMPLE_BILINEAR;
+  const unsigned n_rows = (unsigned)(p.planes * (int64_t)H);  // < 2^31 (checked by the launcher)
   float ms = 0.0f, mss = 0.0f;
-  for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
-       row += (int64_t)gridDim.x * warps_per_block) {
-    const int y = (int)(row % H);
-    const int64_t plane = row / H;
-    const int64_t obase = row * W;
+  for (unsigned row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows; row += gridDim.x * warps_per_block) {
+    const unsigned plane_u = row / (unsigned)H;
+    const int y = (int)(row - plane_u * (unsigned)H);
+    const int64_t plane = plane_u;
+    const int64_t obase = (int64_t)row * W;
+    // ---- blend the two source rows of every resampled level for this output row ----
+    for (int l = 0; l < NL; ++l) {
+      const int lh = p.level_h[l], lw = p.level_w[l];
+      if (lh == H && lw == W) continue;  // identity level: read straight from global below
+      const float* src = p.levels[l] + plane * (int64_t)lh * lw;
+      float* v = vrows + l * row_pitch;
+      const PyrTap ty = ytab[l * H + y];
+      const float* r0 = src + (int)ty.i0 * lw;
+      const float* r1 = src + (int)ty.i1 * lw;
+      const float wy0 = 1.0f - ty.w1;
+#pragma unroll 1
+      for (int i = lane; i < lw; i += 32) v[i] = bilinear ? wy0 * __ldg(r0 + i) + ty.w1 * __ldg(r1 + i) : __ldg(r0 + i);
+    }
+    __syncwarp();
     for (int x0 = lane * VEC; x0 < W; x0 += 32 * VEC) {
       float acc[VEC];
       if (p.base != nullptr) {
@@ -188,12 +218,13 @@ pyramid_rows_kernel(SonarPyramidParams p) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[v] = 0.0f;
       }
-      for (int l = 0; l < p.n_levels; ++l) {
+      const PyrTap* tx = xtab + (VEC == 4 ? (x0 >> 2) : x0);
+#pragma unroll 1
+      for (int l = 0; l < NL; ++l, tx += W) {
         const int lh = p.level_h[l], lw = p.level_w[l];
-        const float* src = p.levels[l] + plane * (int64_t)lh * lw;
         const float wgt = p.weights[l];
         if (lh == H && lw == W) {  // identity level: straight copy-accumulate
-          const float* r = src + (int64_t)y * W + x0;
+          const float* r = p.levels[l] + plane * (int64_t)lh * lw + (int64_t)y * W + x0;
           if (VEC == 4) {
             const float4 s4 = ld4_stream(r);
             acc[0] = acc[0] + __fmul_rn(s4.x, wgt);
@@ -205,34 +236,13 @@ pyramid_rows_kernel(SonarPyramidParams p) {
           }
           continue;
         }
-        const float* r0;
-        const float* r1;
-        float wy0, wy1;
-        if (bilinear) {
-          const LinTap ty = linear_tap(y, lh, (float)lh / (float)H);
-          r0 = src + (int64_t)ty.i0 * lw;
-          r1 = src + (int64_t)ty.i1 * lw;
-          wy0 = ty.w0;
-          wy1 = ty.w1;
-        } else {
-          r0 = r1 = src + (int64_t)nearest_exact_idx(y, lh, (float)lh / (float)H) * lw;
-          wy0 = 1.0f;
-          wy1 = 0.0f;
-        }
-        const int tb = l * W + (VEC == 4 ? (x0 >> 2) : x0);
+        const float* v = vrows + l * row_pitch;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const int ti = tb + (VEC == 4 ? v * Wq : 0);
-          const int i0 = tab_i0[ti];
-          float sv;
-          if (bilinear) {
-            const int i1 = tab_i1[ti];
-            const float w1 = tab_w1[ti], w0 = 1.0f - w1;
-            sv = wy0 * (w0 * __ldg(r0 + i0) + w1 * __ldg(r0 + i1)) + wy1 * (w0 * __ldg(r1 + i0) + w1 * __ldg(r1 + i1));
-          } else {
-            sv = __ldg(r0 + i0);
-          }
-          acc[v] = acc[v] + __fmul_rn(sv, wgt);
+        for (int k = 0; k < VEC; ++k) {
+          const PyrTap t = tx[VEC == 4 ? k * Wq : 0];
+          float sv = v[t.i0];
+          if (bilinear) sv = (1.0f - t.w1) * sv + t.w1 * v[t.i1];
+          acc[k] = acc[k] + __fmul_rn(sv, wgt);
         }
       }
 #pragma unroll
@@ -245,6 +255,7 @@ pyramid_rows_kernel(SonarPyramidParams p) {
       else
         p.out[obase + x0] = acc[0];
     }
+    __syncwarp();  // the next row overwrites the blended rows
   }
   commit_moments(p.sums, p.sums_clear, ms, mss);
 }
@@ -296,11 +307,13 @@ perlin_accum_kernel(SonarPerlinParams p) {
   const int64_t total = (int64_t)p.C * p.H * Wv;
   const float inv_div = 1.0f / p.div_fac;
   float ms = 0.0f, mss = 0.0f;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int x0 = (int)(idx % Wv) * VEC;
-    const int y = (int)((idx / Wv) % p.H);
-    const int c = (int)(idx / ((int64_t)Wv * p.H));
+  for (int64_t idx64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx64 < total;
+       idx64 += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned idx = (unsigned)idx64;  // C*H*W/VEC < 2^31 (checked by the launcher): 32-bit divisions
+    const unsigned row = idx / (unsigned)Wv;
+    const int x0 = (int)(idx - row * (unsigned)Wv) * VEC;
+    const int c = (int)(row / (unsigned)p.H);
+    const int y = (int)(row - (unsigned)c * (unsigned)p.H);
     float pv[ITERS][VEC];
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -473,15 +486,39 @@ affine_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, f
     out[i] = __fadd_rn(__fmul_rn(__fadd_rn(x[i], pre), mul), post);
 }
 
-// out = dst * (1 - mask) + src * mask, mask is (B, 1, H, W) broadcast over channels
+// out = dst * (1 - mask) + src * mask, mask is (B, 1, H, W) broadcast over channels.
+// grid.y = batch item; a thread owns VEC consecutive positions of the (H, W) plane, loads their mask
+// values once and walks the channels: no integer division, the mask is read once instead of C times.
+template <int VEC>
 __global__ void __launch_bounds__(kBlock)
 composite_kernel(const float* __restrict__ dst, const float* __restrict__ src, const float* __restrict__ mask,
-                 float* __restrict__ out, int64_t n, int64_t chw, int64_t hw) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / chw;
-    const float m = mask[b * hw + (i % hw)];
-    const float im = 1.0f - m;
-    out[i] = __fadd_rn(__fmul_rn(dst[i], im), __fmul_rn(src[i], m));
+                 float* __restrict__ out, int64_t channels, int64_t hw) {
+  const int64_t b = blockIdx.y;
+  const float* mb = mask + b * hw;
+  const int64_t item = b * channels * hw;
+  for (int64_t pos = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; pos < hw;
+       pos += (int64_t)gridDim.x * blockDim.x * VEC) {
+    float m[VEC], im[VEC];
+    if (VEC == 4) {
+      const float4 m4 = ld4(mb + pos);
+      m[0] = m4.x; m[1 % VEC] = m4.y; m[2 % VEC] = m4.z; m[3 % VEC] = m4.w;
+    } else {
+      m[0] = mb[pos];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) im[v] = 1.0f - m[v];
+    for (int64_t c = 0; c < channels; ++c) {
+      const int64_t o = item + c * hw + pos;
+      if (VEC == 4) {
+        const float4 d = ld4(dst + o), sv = ld4(src + o);
+        st4(out + o, make_float4(__fadd_rn(__fmul_rn(d.x, im[0]), __fmul_rn(sv.x, m[0])),
+                                 __fadd_rn(__fmul_rn(d.y, im[1 % VEC]), __fmul_rn(sv.y, m[1 % VEC])),
+                                 __fadd_rn(__fmul_rn(d.z, im[2 % VEC]), __fmul_rn(sv.z, m[2 % VEC])),
+                                 __fadd_rn(__fmul_rn(d.w, im[3 % VEC]), __fmul_rn(sv.w, m[3 % VEC]))));
+      } else {
+        out[o] = __fadd_rn(__fmul_rn(dst[o], im[0]), __fmul_rn(src[o], m[0]));
+      }
+    }
   }
 }
 
@@ -582,17 +619,29 @@ int sonar_pyramid_accum_f32(const SonarPyramidParams* params, void* stream) {
   bool vec = (p.W % 4 == 0) && aligned16(p.out) && (p.base == nullptr || aligned16(p.base));
   for (int l = 0; l < p.n_levels; ++l)
     if (p.level_h[l] == p.H && p.level_w[l] == p.W && !aligned16(p.levels[l])) vec = false;
-  const size_t tab_bytes = (size_t)p.n_levels * p.W * 12;
-  if (p.mode != SONAR_RESAMPLE_AREA && p.n_levels > 0 && tab_bytes <= 96 * 1024) {
-    // table-driven row kernel; one warp per row, grid sized to whole waves
+  // table-driven row kernel: tap tables + one blended source row per level and warp in shared memory
+  int max_lw = 1;
+  bool taps_fit_u16 = true;  // tap indices are stored as unsigned short
+  for (int l = 0; l < p.n_levels; ++l) {
+    if (!(p.level_h[l] == p.H && p.level_w[l] == p.W) && p.level_w[l] > max_lw) max_lw = p.level_w[l];
+    if (p.level_h[l] > 65535 || p.level_w[l] > 65535) taps_fit_u16 = false;
+  }
+  const int row_pitch = max_lw;
+  const size_t tab_bytes = (size_t)p.n_levels * (p.W + p.H) * 8 + (size_t)(kBlock / 32) * p.n_levels * row_pitch * sizeof(float);
+  if (p.mode != SONAR_RESAMPLE_AREA && p.n_levels > 0 && taps_fit_u16 && tab_bytes <= 96 * 1024 && p.planes * (int64_t)p.H < (1ll << 31) &&
+      (int64_t)p.H * p.W < (1ll << 30) && p.H < 65536 && p.W < 65536) {
+    // one warp per row; PERSISTENT CTAs (4 per SM): every CTA builds the tap tables once and then walks
+    // many rows (with one CTA per 8 rows the table build was ~40 % of the issued instructions)
     const int64_t n_rows = p.planes * (int64_t)p.H;
-    const int grid = streaming_grid(n_rows, kBlock / 32, 2);
+    int64_t grid = (n_rows + kBlock / 32 - 1) / (kBlock / 32);
+    const int64_t cap = (int64_t)device_info().sm_count * 4;
+    if (grid > cap) grid = cap;
     if (vec) {
       SONAR_CUDA_TRY(cudaFuncSetAttribute(pyramid_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
-      pyramid_rows_kernel<4><<<grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p);
+      pyramid_rows_kernel<4><<<(unsigned)grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p, row_pitch);
     } else {
       SONAR_CUDA_TRY(cudaFuncSetAttribute(pyramid_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
-      pyramid_rows_kernel<1><<<grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p);
+      pyramid_rows_kernel<1><<<(unsigned)grid, kBlock, tab_bytes, (cudaStream_t)stream>>>(p, row_pitch);
     }
     SONAR_LAUNCH_CHECK();
     return 0;
@@ -633,7 +682,7 @@ int sonar_perlin_accum_f32(const SonarPerlinParams* params, void* stream) {
     else                                                            \
       perlin_accum_kernel<1, ITERS><<<grid2, kBlock, 0, st>>>(p);   \
   } while (0)
-  switch (p.iterations) {
+  switch ((int64_t)p.C * p.H * p.W < (1ll << 31) ? p.iterations : 0) {
     case 1: PERLIN_LAUNCH(1); break;
     case 2: PERLIN_LAUNCH(2); break;
     case 3: PERLIN_LAUNCH(3); break;
@@ -693,10 +742,19 @@ int sonar_affine_f32(const float* x, float* out, int64_t n, float pre_add, float
 
 int sonar_composite_f32(const float* dst, const float* src, const float* mask, float* out, int64_t batch,
                         int64_t channels, int64_t hw, void* stream) {
-  const int64_t n = batch * channels * hw;
-  if (n <= 0) return 0;
-  const int grid = sonar::streaming_grid(n, sonar::kBlock, 4);
-  sonar::composite_kernel<<<grid, sonar::kBlock, 0, (cudaStream_t)stream>>>(dst, src, mask, out, n, channels * hw, hw);
+  using namespace sonar;
+  if (batch <= 0 || channels <= 0 || hw <= 0) return 0;
+  if (batch > 65535) return (int)cudaErrorInvalidValue;
+  const bool vec = hw % 4 == 0 && aligned16(dst) && aligned16(src) && aligned16(mask) && aligned16(out);
+  const int64_t threads = vec ? hw / 4 : hw;
+  int64_t gx = (threads + kBlock - 1) / kBlock;
+  const int64_t cap = (int64_t)device_info().sm_count * 16 / batch + 1;
+  if (gx > cap) gx = cap;
+  const dim3 grid((unsigned)gx, (unsigned)batch);
+  if (vec)
+    composite_kernel<4><<<grid, kBlock, 0, (cudaStream_t)stream>>>(dst, src, mask, out, channels, hw);
+  else
+    composite_kernel<1><<<grid, kBlock, 0, (cudaStream_t)stream>>>(dst, src, mask, out, channels, hw);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

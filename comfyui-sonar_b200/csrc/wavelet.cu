@@ -211,9 +211,18 @@ dwt2_analysis_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b,
   const int64_t total = planes * (int64_t)h * w;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int kx = (int)(idx % w);
-    const int ky = (int)((idx / w) % h);
-    const int64_t plane = idx / ((int64_t)w * h);
+    int kx, ky;
+    int64_t plane;
+    if (total < (1ll << 31)) {  // 32-bit division (the 64-bit one is emulated: ~100 instructions each)
+      const unsigned i32 = (unsigned)idx, row = i32 / (unsigned)w;
+      kx = (int)(i32 - row * (unsigned)w);
+      plane = row / (unsigned)h;
+      ky = (int)(row - (unsigned)plane * (unsigned)h);
+    } else {
+      kx = (int)(idx % w);
+      ky = (int)((idx / w) % h);
+      plane = idx / ((int64_t)w * h);
+    }
     const Tin* pa = in_a + plane * (int64_t)in_stride_h * W;
     const Tin* pb = in_b != nullptr ? in_b + plane * (int64_t)in_stride_h * W : nullptr;
     T acc_ll, acc_lh, acc_hl, acc_hh;
@@ -297,9 +306,18 @@ dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, 
   const int64_t hw = (int64_t)h * w;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int qx = (int)(idx % qw);
-    const int qy = (int)((idx / qw) % qh);
-    const int64_t plane = idx / ((int64_t)qw * qh);
+    int qx, qy;
+    int64_t plane;
+    if (total < (1ll << 31)) {
+      const unsigned i32 = (unsigned)idx, row = i32 / (unsigned)qw;
+      qx = (int)(i32 - row * (unsigned)qw);
+      plane = row / (unsigned)qh;
+      qy = (int)(row - (unsigned)plane * (unsigned)qh);
+    } else {
+      qx = (int)(idx % qw);
+      qy = (int)((idx / qw) % qh);
+      plane = idx / ((int64_t)qw * qh);
+    }
     T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
     for (int s = 0; s < n_sets; ++s) {
       const SynthSet<T>& c = s == 0 ? a : b;
