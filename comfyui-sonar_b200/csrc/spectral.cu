@@ -332,6 +332,7 @@ struct AxisPlan {
   int n_stages;
   int radix[kBatchedMaxStages];
   int ns[kBatchedMaxStages];
+  int nb[kBatchedMaxStages];       // butterflies per transform in the stage (n / radix)
   int tab_off[kBatchedMaxStages];  // offset of the stage's butterfly table
   int tab_size;
 };
@@ -432,78 +433,110 @@ __device__ __forceinline__ StageInputs<SOURCE> stage_inputs(const StageIo& io, i
   return in;
 }
 
-// One inverse Stockham stage over a batch of transforms. Element t of transform b lives at
-// t * stride_t + b * stride_b. The CTA's warps form a (chunk, butterfly) grid: a warp runs butterfly
-// j for the 32 transforms of its chunk, so twiddles and offsets are warp-uniform table reads.
-template <int SOURCE>
-__device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2* __restrict__ dst, int N, int R, int Ns,
-                                                      const float2* __restrict__ tw, const ushort2* __restrict__ tab,
-                                                      int nbatch, int stride_t, int stride_b) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int nb = N / R, nchunks = (nbatch + 31) >> 5;
-  const int cw = nchunks < nwarps ? nchunks : nwarps;  // warps along the chunk axis
-  const int jw = nwarps / cw;                          // warps along the butterfly axis
-  const int wj = warp / cw, wc = warp - wj * cw;
+// Radix-R inverse butterfly on registers: v[t] already multiplied by its twiddle.
+template <int R>
+__device__ __forceinline__ void butterfly_inverse(float2 (&v)[R]) {
+  if (R == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  } else if (R == 4) {
+    const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]), a2 = cadd(v[1], v[3]);
+    const float2 d = csub(v[1], v[3]);
+    const float2 a3 = make_float2(-d.y, d.x);  // * (+i)
+    v[0] = cadd(a0, a2);
+    v[1] = cadd(a1, a3);
+    v[2] = csub(a0, a2);
+    v[3] = csub(a1, a3);
+  } else if (R == 3) {
+    const float2 t1 = cadd(v[1], v[2]);
+    const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+    const float2 d = csub(v[1], v[2]);
+    const float2 t3 = make_float2(-0.86602540378443865f * d.y, 0.86602540378443865f * d.x);
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(t2, t3);
+    v[2] = csub(t2, t3);
+  } else {  // R == 5
+    constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
+    constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+    const float2 v0 = v[0];
+    const float2 a1 = cadd(v[1], v[4 % R]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4 % R]), b2 = csub(v[2], v[3]);
+    const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
+    const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
+    const float2 e1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+    const float2 e2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+    const float2 n1 = make_float2(-e1.y, e1.x), n2 = make_float2(-e2.y, e2.x);  // * (+i)
+    v[0] = make_float2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
+    v[1] = cadd(m1, n1);
+    v[2] = cadd(m2, n2);
+    v[3] = csub(m2, n2);
+    v[4 % R] = csub(m1, n1);
+  }
+}
+
+// One inverse Stockham stage over a batch of transforms, radix R a template parameter (no per-butterfly
+// radix dispatch). Element t of transform b lives at t * stride_t + b * stride_b. The CTA's warps form a
+// (butterfly, chunk) grid: a warp owns butterflies j, j + jw, ... and, for each, the 32 transforms of its
+// chunk(s); table entry and twiddles are fetched once per butterfly and reused across chunks.
+// How the CTA's warps tile (butterfly, chunk-of-32-transforms) for one axis: computed once per kernel
+// (it only depends on the batch size), not once per stage call -- the integer divisions of this setup
+// were ~20 % of the issued instructions when every stage recomputed them.
+struct WarpGrid {
+  int nchunks;  // 32-transform chunks of the batch
+  int cw;       // warps along the chunk axis
+  int jw;       // warps along the butterfly axis
+  int wj, wc;   // this warp's coordinates (wj >= jw: idle)
+};
+
+__device__ __forceinline__ WarpGrid make_warp_grid(int nbatch) {
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  WarpGrid g;
+  g.nchunks = (nbatch + 31) >> 5;
+  g.cw = g.nchunks < nwarps ? g.nchunks : nwarps;
+  g.jw = nwarps / g.cw;
+  g.wj = warp / g.cw;
+  g.wc = warp - g.wj * g.cw;
+  return g;
+}
+
+template <int SOURCE, int R>
+__device__ __forceinline__ void batched_stage_radix(const StageIo& io, float2* __restrict__ dst, int nb, int Ns,
+                                                    const float2* __restrict__ tw, const ushort2* __restrict__ tab,
+                                                    int nbatch, int stride_t, int stride_b, const WarpGrid& g) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = g.nchunks, cw = g.cw, jw = g.jw, wj = g.wj, wc = g.wc;
   if (wj >= jw) return;  // nwarps % cw leftover warps idle for this stage
   const int out_step = Ns * stride_t;
-  for (int c = wc; c < nchunks; c += cw) {
-    const int b = (c << 5) + lane;
-    if (b >= nbatch) continue;
-    float2* out_b = dst + b * stride_b;
-    for (int j = wj; j < nb; j += jw) {
-      const ushort2 e = tab[j];
-      const int tb = e.y;
-      float2* out = out_b + (int)e.x * stride_t;
+  for (int j = wj; j < nb; j += jw) {
+    const ushort2 e = tab[j];
+    float2 w[R];
+#pragma unroll
+    for (int t = 1; t < R; ++t) w[t] = tw[t * (int)e.y];
+    for (int c = wc; c < nchunks; c += cw) {
+      const int b = (c << 5) + lane;
+      if (b >= nbatch) continue;
       const StageInputs<SOURCE> in = stage_inputs<SOURCE>(io, j, nb, b, stride_t, stride_b);
-      if (R == 4) {
-        const float2 v0 = in.get(0);
-        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
-        const float2 v2 = cmul_conj(in.get(2), tw[2 * tb]);
-        const float2 v3 = cmul_conj(in.get(3), tw[3 * tb]);
-        const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3);
-        const float2 d = csub(v1, v3);
-        const float2 a3 = make_float2(-d.y, d.x);  // * (+i)
-        out[0] = cadd(a0, a2);
-        out[out_step] = cadd(a1, a3);
-        out[2 * out_step] = csub(a0, a2);
-        out[3 * out_step] = csub(a1, a3);
-      } else if (R == 2) {
-        const float2 v0 = in.get(0);
-        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
-        out[0] = cadd(v0, v1);
-        out[out_step] = csub(v0, v1);
-      } else if (R == 3) {
-        const float2 v0 = in.get(0);
-        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
-        const float2 v2 = cmul_conj(in.get(2), tw[2 * tb]);
-        const float2 t1 = cadd(v1, v2);
-        const float2 t2 = make_float2(v0.x - 0.5f * t1.x, v0.y - 0.5f * t1.y);
-        const float2 d = csub(v1, v2);
-        const float2 t3 = make_float2(-0.86602540378443865f * d.y, 0.86602540378443865f * d.x);
-        out[0] = cadd(v0, t1);
-        out[out_step] = cadd(t2, t3);
-        out[2 * out_step] = csub(t2, t3);
-      } else {  // R == 5
-        constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
-        constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
-        const float2 v0 = in.get(0);
-        const float2 v1 = cmul_conj(in.get(1), tw[tb]);
-        const float2 v2 = cmul_conj(in.get(2), tw[2 * tb]);
-        const float2 v3 = cmul_conj(in.get(3), tw[3 * tb]);
-        const float2 v4 = cmul_conj(in.get(4), tw[4 * tb]);
-        const float2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), b1 = csub(v1, v4), b2 = csub(v2, v3);
-        const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
-        const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
-        const float2 e1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
-        const float2 e2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
-        const float2 n1 = make_float2(-e1.y, e1.x), n2 = make_float2(-e2.y, e2.x);  // * (+i)
-        out[0] = make_float2(v0.x + a1.x + a2.x, v0.y + a1.y + a2.y);
-        out[out_step] = cadd(m1, n1);
-        out[2 * out_step] = cadd(m2, n2);
-        out[3 * out_step] = csub(m2, n2);
-        out[4 * out_step] = csub(m1, n1);
-      }
+      float2 v[R];
+      v[0] = in.get(0);
+#pragma unroll
+      for (int t = 1; t < R; ++t) v[t] = cmul_conj(in.get(t), w[t]);
+      butterfly_inverse<R>(v);
+      float2* out = dst + (int)e.x * stride_t + b * stride_b;
+#pragma unroll
+      for (int t = 0; t < R; ++t) out[t * out_step] = v[t];
     }
+  }
+}
+
+template <int SOURCE>
+__device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2* __restrict__ dst, int nb, int R, int Ns,
+                                                      const float2* __restrict__ tw, const ushort2* __restrict__ tab,
+                                                      int nbatch, int stride_t, int stride_b, const WarpGrid& g) {
+  switch (R) {  // block-uniform
+    case 4: batched_stage_radix<SOURCE, 4>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
+    case 2: batched_stage_radix<SOURCE, 2>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
+    case 3: batched_stage_radix<SOURCE, 3>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
+    default: batched_stage_radix<SOURCE, 5>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
   }
 }
 
@@ -535,6 +568,7 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
     tw_w[k] = make_float2((float)cs, (float)sn);
   }
   __syncthreads();
+  const WarpGrid grid_col = make_warp_grid(Wh), grid_row = make_warp_grid(H);
   float ms = 0.0f, mss = 0.0f;
   for (int64_t plane = blockIdx.x; plane < p.planes; plane += gridDim.x) {
     // ---- columns: inverse complex FFT of length H, batch = Wh columns (lanes = adjacent k). The first
@@ -549,10 +583,10 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
     for (int f = 0; f < L.col.n_stages; ++f) {
       if (f == 0) {
         io.src = reinterpret_cast<const float2*>(p.in_spec) + plane * (int64_t)H * Wh;
-        batched_stage_inverse<SRC_SPECTRUM>(io, oth, H, L.col.radix[0], L.col.ns[0], tw_h, tab_col, Wh, P, 1);
+        batched_stage_inverse<SRC_SPECTRUM>(io, oth, L.col.nb[0], L.col.radix[0], L.col.ns[0], tw_h, tab_col, Wh, P, 1, grid_col);
       } else {
         io.src = cur;
-        batched_stage_inverse<SRC_SMEM>(io, oth, H, L.col.radix[f], L.col.ns[f], tw_h, tab_col + L.col.tab_off[f], Wh, P, 1);
+        batched_stage_inverse<SRC_SMEM>(io, oth, L.col.nb[f], L.col.radix[f], L.col.ns[f], tw_h, tab_col + L.col.tab_off[f], Wh, P, 1, grid_col);
       }
       __syncthreads();
       float2* t = cur;
@@ -564,9 +598,9 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
     for (int f = 0; f < L.row.n_stages; ++f) {
       io.src = cur;
       if (f == 0)
-        batched_stage_inverse<SRC_FOLD>(io, oth, M, L.row.radix[0], L.row.ns[0], tw_m, tab_row, H, 1, P);
+        batched_stage_inverse<SRC_FOLD>(io, oth, L.row.nb[0], L.row.radix[0], L.row.ns[0], tw_m, tab_row, H, 1, P, grid_row);
       else
-        batched_stage_inverse<SRC_SMEM>(io, oth, M, L.row.radix[f], L.row.ns[f], tw_m, tab_row + L.row.tab_off[f], H, 1, P);
+        batched_stage_inverse<SRC_SMEM>(io, oth, L.row.nb[f], L.row.radix[f], L.row.ns[f], tw_m, tab_row + L.row.tab_off[f], H, 1, P, grid_row);
       __syncthreads();
       float2* t = cur;
       cur = oth;
@@ -598,6 +632,7 @@ static bool make_axis_plan(int n, AxisPlan* plan) {
     if (plan->n_stages >= kBatchedMaxStages) return false;
     plan->radix[plan->n_stages] = r;
     plan->ns[plan->n_stages] = ns;
+    plan->nb[plan->n_stages] = n / r;
     plan->tab_off[plan->n_stages] = plan->tab_size;
     plan->tab_size += n / r;
     ++plan->n_stages;
