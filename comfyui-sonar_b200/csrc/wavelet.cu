@@ -253,7 +253,8 @@ struct SynthSet {
 
 // Accumulates the contribution of one coefficient set to the 2x2 output quad (2qy+py, 2qx+px).
 // pll: approximation band with row pitch ll_pitch; phi: three detail bands, `band_stride` apart, row
-// pitch hi_pitch; (h, w) = valid coefficient extent.
+// pitch hi_pitch; (h, w) = valid coefficient extent. The per-band scales are folded into the x taps
+// (one product per tap and band instead of one per coefficient) and every accumulation is a single FMA.
 template <typename T, int LT>
 __device__ __forceinline__ void synthesis_quad(const T* __restrict__ pll, int ll_pitch, const T* __restrict__ phi,
                                                int64_t band_stride, int hi_pitch, int h, int w, int qy, int qx, T s_ll,
@@ -265,28 +266,36 @@ __device__ __forceinline__ void synthesis_quad(const T* __restrict__ pll, int ll
     const int ky = qy + ia;
     if (ky >= h) break;  // only reachable for the cropped-away overhang
     T rl0 = 0, rl1 = 0, rh0 = 0, rh1 = 0;
+    const T* rll = pll + ky * ll_pitch + qx;
+    const T* rhi = phi + ky * hi_pitch + qx;
 #pragma unroll
     for (int ib = 0; ib < half; ++ib) {
-      const int kx = qx + ib;
-      if (kx >= w) break;
+      if (qx + ib >= w) break;
       const int tx = L - 2 - 2 * ib;
-      const T glx0 = f.s_lo[tx], glx1 = f.s_lo[tx + 1], ghx0 = f.s_hi[tx], ghx1 = f.s_hi[tx + 1];
-      const int o = ky * hi_pitch + kx;
-      const T v_ll = pll[ky * ll_pitch + kx] * s_ll;
-      const T v_lh = phi[o] * s_lh;                    // high along H, low along W
-      const T v_hl = phi[band_stride + o] * s_hl;      // low along H, high along W
-      const T v_hh = phi[2 * band_stride + o] * s_hh;
-      rl0 += glx0 * v_ll + ghx0 * v_hl;
-      rl1 += glx1 * v_ll + ghx1 * v_hl;
-      rh0 += glx0 * v_lh + ghx0 * v_hh;
-      rh1 += glx1 * v_lh + ghx1 * v_hh;
+      const T lo0 = f.s_lo[tx], lo1 = f.s_lo[tx + 1], hi0 = f.s_hi[tx], hi1 = f.s_hi[tx + 1];
+      const T v_ll = rll[ib];
+      const T v_lh = rhi[ib];                    // high along H, low along W
+      const T v_hl = rhi[band_stride + ib];      // low along H, high along W
+      const T v_hh = rhi[2 * band_stride + ib];
+      rl0 = fma(lo0 * s_ll, v_ll, rl0);
+      rl0 = fma(hi0 * s_hl, v_hl, rl0);
+      rl1 = fma(lo1 * s_ll, v_ll, rl1);
+      rl1 = fma(hi1 * s_hl, v_hl, rl1);
+      rh0 = fma(lo0 * s_lh, v_lh, rh0);
+      rh0 = fma(hi0 * s_hh, v_hh, rh0);
+      rh1 = fma(lo1 * s_lh, v_lh, rh1);
+      rh1 = fma(hi1 * s_hh, v_hh, rh1);
     }
     const int ty = L - 2 - 2 * ia;
     const T gly0 = f.s_lo[ty], gly1 = f.s_lo[ty + 1], ghy0 = f.s_hi[ty], ghy1 = f.s_hi[ty + 1];
-    o00 += gly0 * rl0 + ghy0 * rh0;
-    o01 += gly0 * rl1 + ghy0 * rh1;
-    o10 += gly1 * rl0 + ghy1 * rh0;
-    o11 += gly1 * rl1 + ghy1 * rh1;
+    o00 = fma(gly0, rl0, o00);
+    o00 = fma(ghy0, rh0, o00);
+    o01 = fma(gly0, rl1, o01);
+    o01 = fma(ghy0, rh1, o01);
+    o10 = fma(gly1, rl0, o10);
+    o10 = fma(ghy1, rh0, o10);
+    o11 = fma(gly1, rl1, o11);
+    o11 = fma(ghy1, rh1, o11);
   }
 }
 
