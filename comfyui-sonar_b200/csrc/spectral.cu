@@ -14,6 +14,9 @@
 // stays in shared memory -- or in an L2-resident global scratch when a plane is too large (256^2:
 // 258 KB > 227 KB) -- and every 1-D FFT is a warp-level mixed-radix Stockham transform in a per-warp
 // ping-pong scratch. Rows are processed two at a time (real pair <-> one complex FFT).
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/sonar_b200.h"
 
@@ -311,18 +314,26 @@ spectral_plane_kernel(SpectralLaunch L) {
 }
 
 // =============================================================================================
-// Batched-lane variant for the hot case (half spectrum in, even W, radices 2/3/4/5): every FFT stage
-// is ONE pass of the whole CTA over the whole plane, with the lanes of a warp running the SAME
-// butterfly of 32 different transforms (columns: 32 adjacent k, contiguous in shared memory; rows: 32
-// rows, conflict-free thanks to the odd pitch). Twiddles and output offsets are warp-uniform, there
-// is no per-lane index arithmetic, no idle lanes for short transforms and no per-warp scratch.
+// Batched variant for the hot case (even W, lengths that factor into radices 2/3/4/5/8/9/10/16): every
+// FFT stage is ONE pass of the whole CTA over a group of planes, one register-resident radix-R butterfly
+// per thread. Work items (butterfly j, transform b) are flattened with b fastest, so adjacent lanes run
+// the same butterfly of adjacent transforms (columns: adjacent k, contiguous in shared memory; rows:
+// adjacent rows, conflict-free thanks to the odd pitch) whatever the batch size; small planes (UNet
+// activations, 32x32) are processed several per CTA so the 1024 threads stay busy.
+// Large radices keep the pass count low: 90 = 10 x 9 and 80 = 10 x 8 are two passes each (radices 6..16
+// are Cooley-Tukey compositions of the 2/3/4/5 butterflies inside registers, inner twiddles compile-time
+// constants), and the first pass of every axis has no twiddle multiplications at all.
 // Rows use the half-length c2r trick: for Hermitian X of even length W, with M = W/2,
 //   Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W},   k = 0..M-1
 //   z = sum_k Z[k] e^{+2 pi i k n / M}  ==>  x[2n] = Re z[n], x[2n+1] = Im z[n]
 // which also reproduces irfft2's treatment of the reference's NON-Hermitian input (the imaginary
 // parts of the k = 0 and k = M bins are dropped, nothing else of the upper half is read).
-// The round-1 warp-per-transform kernel needed ~237 issued instructions per output element at
-// 90x160 (ncu: 62 % issue-slot busy, instruction bound); this form needs ~50.
+// Real input (rfft2 front end: PowerFilterNoiseItem, OneF / GreenTest, FreeU-Extreme ffilter) runs the
+// same inverse stages on conjugated data (FFT(z) = conj(IFFT(conj z))): rows r2c by the half-length
+// trick in reverse (the "unfold" rides on the first forward column stage), then columns, gain, and the
+// inverse path above -- the plane still makes exactly one trip from and one trip to HBM.
+// History: warp-per-transform kernel 237 issued instructions per output element at 90x160, radix 2..5
+// batched-lane kernel 158 (ncu r01g: 62 % issue-slot busy, 43 % of it integer / address arithmetic).
 // =============================================================================================
 constexpr int kBatchedThreads = 1024;
 constexpr int kBatchedMaxStages = 16;
@@ -331,7 +342,7 @@ struct AxisPlan {
   int n;
   int n_stages;
   int radix[kBatchedMaxStages];
-  int ns[kBatchedMaxStages];
+  int ns[kBatchedMaxStages];       // product of the radices before the stage
   int nb[kBatchedMaxStages];       // butterflies per transform in the stage (n / radix)
   int tab_off[kBatchedMaxStages];  // offset of the stage's butterfly table
   int tab_size;
@@ -339,108 +350,78 @@ struct AxisPlan {
 
 struct SpectralBatchedLaunch {
   SonarSpectralParams p;
-  AxisPlan col;  // length H
-  AxisPlan row;  // length M = W / 2
-  int wh;        // M + 1
-  int pitch;     // odd, >= wh
+  AxisPlan col;     // length H
+  AxisPlan row;     // length M = W / 2
+  int wh;           // M + 1
+  int pitch;        // odd, >= wh: row pitch of a plane in shared memory (complex elements)
+  int plane_elems;  // H * pitch
+  int group;        // planes per CTA pass
+  float scale;      // out_scale (x 1/2 for real input: the r2c unfold leaves a factor 2)
+  unsigned magic_m, magic_wh, magic_cols, magic_rows;  // ceil(2^32 / d) for d = M, wh, group * wh, group * H
 };
 
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {  // a * conj(w)
   return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
 }
 
-// butterfly table of one axis: for butterfly j of stage f, .x = output base (j / Ns) * Ns * R + (j % Ns),
-// .y = twiddle base (j % Ns) * N / (Ns * R). Built once per CTA so the stage loops hold no division.
-__device__ void build_axis_table(const AxisPlan& plan, ushort2* __restrict__ tab) {
-  for (int f = 0; f < plan.n_stages; ++f) {
-    const int R = plan.radix[f], Ns = plan.ns[f], nb = plan.n / R, unit = plan.n / (Ns * R);
-    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-      const int k0 = j % Ns;
-      tab[plan.tab_off[f] + j] = make_ushort2((unsigned short)((j / Ns) * Ns * R + k0), (unsigned short)(k0 * unit));
-    }
+// ---- compile-time roots of unity for the composite radices ----
+constexpr double kPiD = 3.14159265358979323846264338327950288;
+constexpr double cx_cos(double x) {
+  double term = 1.0, sum = 1.0;
+  for (int n = 1; n < 24; ++n) {
+    term *= -x * x / (double)((2 * n - 1) * (2 * n));
+    sum += term;
   }
+  return sum;
 }
-
-// Where a stage reads its inputs from.
-enum StageSource : int {
-  SRC_SMEM = 0,      // the other ping-pong buffer
-  SRC_SPECTRUM = 1,  // first column stage: global half spectrum (.) gain mask
-  SRC_FOLD = 2       // first row stage: Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W}
-};
-
-struct StageIo {
-  const float2* src;   // SRC_SMEM / SRC_FOLD: shared-memory buffer; SRC_SPECTRUM: global plane
-  const float* mask;   // SRC_SPECTRUM
-  const float2* tw_w;  // SRC_FOLD
-  int M;               // SRC_FOLD
-  int src_pitch;       // SRC_SPECTRUM: row length of the global plane (Wh)
-};
-
-// Input t' (0..R-1) of butterfly j for transform b: one base offset per (j, b), then a fixed step.
-template <int SOURCE>
-struct StageInputs {
-  const float2* p0;   // SRC_SMEM / SRC_SPECTRUM: &src[first element]; SRC_FOLD: row base
-  const float* m0;    // SRC_SPECTRUM: &mask[first element] (or nullptr)
-  const float2* tw_w; // SRC_FOLD
-  int step;           // distance between consecutive inputs (elements)
-  int t0, M;          // SRC_FOLD: first k, fold length
-
-  __device__ __forceinline__ float2 get(int i) const {
-    if (SOURCE == SRC_SPECTRUM) {
-      float2 v = p0[i * step];
-      if (m0 != nullptr) {
-        const float g = __ldg(m0 + i * step);
-        v.x *= g;
-        v.y *= g;
-      }
-      return v;
-    }
-    if (SOURCE == SRC_FOLD) {
-      const int t = t0 + i * step;
-      float2 xk = p0[t], xm = p0[M - t];
-      if (t == 0) {  // c2r ignores the imaginary parts of the DC and Nyquist bins
-        xk.y = 0.0f;
-        xm.y = 0.0f;
-      }
-      const float2 a = make_float2(xk.x + xm.x, xk.y - xm.y);  // X[k] + conj X[M-k]
-      const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);  // X[k] - conj X[M-k]
-      const float2 bt = cmul(d, tw_w[t]);
-      return make_float2(a.x - bt.y, a.y + bt.x);  // A + i B
-    }
-    return p0[i * step];
+constexpr double cx_sin(double x) {
+  double term = x, sum = x;
+  for (int n = 1; n < 24; ++n) {
+    term *= -x * x / (double)((2 * n) * (2 * n + 1));
+    sum += term;
   }
+  return sum;
+}
+template <int R, int K>
+struct Root {  // e^{+2 pi i K / R}
+  static constexpr int k = ((K % R) + R) % R;
+  static constexpr double angle = 2.0 * kPiD * (double)(2 * k <= R ? k : k - R) / (double)R;
+  static constexpr float c = (float)cx_cos(angle);
+  static constexpr float s = (float)cx_sin(angle);
 };
-
-template <int SOURCE>
-__device__ __forceinline__ StageInputs<SOURCE> stage_inputs(const StageIo& io, int j, int nb, int b, int stride_t,
-                                                            int stride_b) {
-  StageInputs<SOURCE> in;
-  in.tw_w = io.tw_w;
-  in.M = io.M;
-  in.m0 = nullptr;
-  in.t0 = j;
-  if (SOURCE == SRC_SPECTRUM) {  // element (row t, column b) of the global plane
-    in.p0 = io.src + (j * io.src_pitch + b);
-    in.m0 = io.mask != nullptr ? io.mask + (j * io.src_pitch + b) : nullptr;
-    in.step = nb * io.src_pitch;
-  } else if (SOURCE == SRC_FOLD) {  // transform index = k along the row of transform b
-    in.p0 = io.src + b * stride_b;
-    in.step = nb;
+template <int R, int K>
+__device__ __forceinline__ float2 mul_root(float2 a) {  // a * e^{+2 pi i K / R}
+  constexpr int k = ((K % R) + R) % R;
+  if constexpr (k == 0) {
+    return a;
+  } else if constexpr (4 * k == R) {
+    return make_float2(-a.y, a.x);
+  } else if constexpr (2 * k == R) {
+    return make_float2(-a.x, -a.y);
+  } else if constexpr (4 * k == 3 * R) {
+    return make_float2(a.y, -a.x);
   } else {
-    in.p0 = io.src + (j * stride_t + b * stride_b);
-    in.step = nb * stride_t;
+    constexpr float c = Root<R, K>::c, s = Root<R, K>::s;
+    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
   }
-  return in;
 }
 
-// Radix-R inverse butterfly on registers: v[t] already multiplied by its twiddle.
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// Prime-ish radix inverse butterfly on registers, natural order in and out.
 template <int R>
 __device__ __forceinline__ void butterfly_inverse(float2 (&v)[R]) {
-  if (R == 2) {
+  if constexpr (R == 2) {
     const float2 a = v[0], b = v[1];
     v[0] = cadd(a, b);
     v[1] = csub(a, b);
-  } else if (R == 4) {
+  } else if constexpr (R == 4) {
     const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]), a2 = cadd(v[1], v[3]);
     const float2 d = csub(v[1], v[3]);
     const float2 a3 = make_float2(-d.y, d.x);  // * (+i)
@@ -448,7 +429,7 @@ __device__ __forceinline__ void butterfly_inverse(float2 (&v)[R]) {
     v[1] = cadd(a1, a3);
     v[2] = csub(a0, a2);
     v[3] = csub(a1, a3);
-  } else if (R == 3) {
+  } else if constexpr (R == 3) {
     const float2 t1 = cadd(v[1], v[2]);
     const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
     const float2 d = csub(v[1], v[2]);
@@ -456,11 +437,12 @@ __device__ __forceinline__ void butterfly_inverse(float2 (&v)[R]) {
     v[0] = cadd(v[0], t1);
     v[1] = cadd(t2, t3);
     v[2] = csub(t2, t3);
-  } else {  // R == 5
+  } else {
+    static_assert(R == 5, "butterfly radix");
     constexpr float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;
     constexpr float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
     const float2 v0 = v[0];
-    const float2 a1 = cadd(v[1], v[4 % R]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4 % R]), b2 = csub(v[2], v[3]);
+    const float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
     const float2 m1 = make_float2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
     const float2 m2 = make_float2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
     const float2 e1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
@@ -470,88 +452,246 @@ __device__ __forceinline__ void butterfly_inverse(float2 (&v)[R]) {
     v[1] = cadd(m1, n1);
     v[2] = cadd(m2, n2);
     v[3] = csub(m2, n2);
-    v[4 % R] = csub(m1, n1);
+    v[4] = csub(m1, n1);
   }
 }
 
-// One inverse Stockham stage over a batch of transforms, radix R a template parameter (no per-butterfly
-// radix dispatch). Element t of transform b lives at t * stride_t + b * stride_b. The CTA's warps form a
-// (butterfly, chunk) grid: a warp owns butterflies j, j + jw, ... and, for each, the 32 transforms of its
-// chunk(s); table entry and twiddles are fetched once per butterfly and reused across chunks.
-// How the CTA's warps tile (butterfly, chunk-of-32-transforms) for one axis: computed once per kernel
-// (it only depends on the batch size), not once per stage call -- the integer divisions of this setup
-// were ~20 % of the issued instructions when every stage recomputed them.
-struct WarpGrid {
-  int nchunks;  // 32-transform chunks of the batch
-  int cw;       // warps along the chunk axis
-  int jw;       // warps along the butterfly axis
-  int wj, wc;   // this warp's coordinates (wj >= jw: idle)
+// Composite radices R = R1 * R2 (Cooley-Tukey inside registers); R1 == 1: a plain butterfly.
+template <int R>
+struct RadixSplit {
+  static constexpr int r1 = R == 6 ? 2 : R == 8 ? 2 : R == 9 ? 3 : R == 10 ? 2 : R == 16 ? 4 : 1;
+  static constexpr int r2 = R / r1;
 };
-
-__device__ __forceinline__ WarpGrid make_warp_grid(int nbatch) {
-  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  WarpGrid g;
-  g.nchunks = (nbatch + 31) >> 5;
-  g.cw = g.nchunks < nwarps ? g.nchunks : nwarps;
-  g.jw = nwarps / g.cw;
-  g.wj = warp / g.cw;
-  g.wc = warp - g.wj * g.cw;
-  return g;
+// Output index held by register slot `slot` after dft_inverse<R> (the digit reversal is applied by the
+// store addresses, not by moving registers).
+template <int R>
+__device__ __forceinline__ constexpr int dft_out_index(int slot) {
+  return RadixSplit<R>::r1 == 1 ? slot : (slot / RadixSplit<R>::r2) + RadixSplit<R>::r1 * (slot % RadixSplit<R>::r2);
 }
-
-template <int SOURCE, int R>
-__device__ __forceinline__ void batched_stage_radix(const StageIo& io, float2* __restrict__ dst, int nb, int Ns,
-                                                    const float2* __restrict__ tw, const ushort2* __restrict__ tab,
-                                                    int nbatch, int stride_t, int stride_b, const WarpGrid& g) {
-  const int lane = threadIdx.x & 31;
-  const int nchunks = g.nchunks, cw = g.cw, jw = g.jw, wj = g.wj, wc = g.wc;
-  if (wj >= jw) return;  // nwarps % cw leftover warps idle for this stage
-  const int out_step = Ns * stride_t;
-  for (int j = wj; j < nb; j += jw) {
-    const ushort2 e = tab[j];
-    float2 w[R];
+// X[u1 + R1 u2] = sum_t2 W_R2^{t2 u2} W_R^{t2 u1} sum_t1 W_R1^{t1 u1} v[t1 R2 + t2], W_n = e^{+2 pi i / n};
+// slot u1 R2 + u2 receives X[u1 + R1 u2].
+template <int R>
+__device__ __forceinline__ void dft_inverse(float2 (&v)[R]) {
+  constexpr int R1 = RadixSplit<R>::r1, R2 = RadixSplit<R>::r2;
+  if constexpr (R1 == 1) {
+    butterfly_inverse<R>(v);
+  } else {
+    static_for<0, R2>([&](auto t2c) {
+      constexpr int t2 = decltype(t2c)::value;
+      float2 a[R1];
 #pragma unroll
-    for (int t = 1; t < R; ++t) w[t] = tw[t * (int)e.y];
-    for (int c = wc; c < nchunks; c += cw) {
-      const int b = (c << 5) + lane;
-      if (b >= nbatch) continue;
-      const StageInputs<SOURCE> in = stage_inputs<SOURCE>(io, j, nb, b, stride_t, stride_b);
-      float2 v[R];
-      v[0] = in.get(0);
+      for (int t1 = 0; t1 < R1; ++t1) a[t1] = v[t1 * R2 + t2];
+      butterfly_inverse<R1>(a);
+      static_for<0, R1>([&](auto u1c) {
+        constexpr int u1 = decltype(u1c)::value;
+        v[u1 * R2 + decltype(t2c)::value] = mul_root<R, u1 * decltype(t2c)::value>(a[u1]);
+      });
+    });
 #pragma unroll
-      for (int t = 1; t < R; ++t) v[t] = cmul_conj(in.get(t), w[t]);
-      butterfly_inverse<R>(v);
-      float2* out = dst + (int)e.x * stride_t + b * stride_b;
+    for (int u1 = 0; u1 < R1; ++u1) {
+      float2 b[R2];
 #pragma unroll
-      for (int t = 0; t < R; ++t) out[t * out_step] = v[t];
+      for (int t2 = 0; t2 < R2; ++t2) b[t2] = v[u1 * R2 + t2];
+      butterfly_inverse<R2>(b);
+#pragma unroll
+      for (int u2 = 0; u2 < R2; ++u2) v[u1 * R2 + u2] = b[u2];
     }
   }
 }
 
-template <int SOURCE>
-__device__ __forceinline__ void batched_stage_inverse(const StageIo& io, float2* __restrict__ dst, int nb, int R, int Ns,
-                                                      const float2* __restrict__ tw, const ushort2* __restrict__ tab,
-                                                      int nbatch, int stride_t, int stride_b, const WarpGrid& g) {
-  switch (R) {  // block-uniform
-    case 4: batched_stage_radix<SOURCE, 4>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
-    case 2: batched_stage_radix<SOURCE, 2>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
-    case 3: batched_stage_radix<SOURCE, 3>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
-    default: batched_stage_radix<SOURCE, 5>(io, dst, nb, Ns, tw, tab, nbatch, stride_t, stride_b, g); break;
+// Where the first stage of an axis reads its inputs from.
+enum StageSource : int {
+  SRC_SMEM = 0,       // the other ping-pong buffer
+  SRC_SMEM_CONJ = 1,  // the other buffer, conjugated (first forward row stage over the packed real rows)
+  SRC_SPECTRUM = 2,   // first inverse column stage, spectrum input: global half spectrum (.) gain mask
+  SRC_CONJ_MASK = 3,  // first inverse column stage, real input: conj(forward result) (.) gain mask
+  SRC_FOLD = 4,       // first inverse row stage: Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W}
+  SRC_UNFOLD = 5      // first forward column stage: conj X[k] from the half-length row transforms
+};
+
+struct StageArgs {
+  const float2* src;     // shared-memory source (SRC_SPECTRUM: the group's first global plane)
+  float2* dst;
+  const float2* tw;      // e^{-2 pi i k / n} of the axis
+  const ushort2* tab;    // butterfly table of the stage (unused by first stages)
+  const float* mask;     // (H, wh) gain or nullptr
+  const float2* tw_w;    // e^{+2 pi i k / W}, k < M
+  int nb, ns;
+  int nbatch;            // transforms in this pass (valid planes x columns or rows)
+  unsigned magic_batch;  // ceil(2^32 / nbatch)
+  unsigned magic_wh;     // ceil(2^32 / wh)
+  int group;             // planes per pass the kernel was launched with (1: no plane split of b)
+  int wh, pitch, plane_elems, M;
+  int spec_plane_elems;  // H * wh (global spectrum plane)
+};
+
+// One inverse Stockham stage over a batch of transforms, one radix-R butterfly per thread and iteration.
+// Element t of transform b lives at base(b) + t * stride: columns base = plane * plane_elems + k, stride =
+// pitch; rows base = b * pitch (b = plane * H + y), stride = 1.
+template <int SOURCE, int R, bool COLS, bool FIRST>
+__device__ __forceinline__ void run_stage(const StageArgs& a) {
+  const int total = a.nb * a.nbatch;
+  const int stride = COLS ? a.pitch : 1;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    const int j = (int)__umulhi((unsigned)w, a.magic_batch);
+    const int b = w - j * a.nbatch;
+    int g = 0, k = b, base;
+    if (COLS) {
+      if (a.group > 1) {
+        g = (int)__umulhi((unsigned)b, a.magic_wh);
+        k = b - g * a.wh;
+      }
+      base = g * a.plane_elems + k;
+    } else {
+      base = b * a.pitch;
+    }
+    float2 v[R];
+    if (SOURCE == SRC_SPECTRUM) {
+      const int e0 = j * a.wh + k, estep = a.nb * a.wh;
+      const float2* gp = a.src + ((int64_t)g * a.spec_plane_elems + e0);
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = __ldg(gp + t * estep);
+      if (a.mask != nullptr) {
+        const float* mp = a.mask + e0;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+          const float gain = __ldg(mp + t * estep);
+          v[t].x *= gain;
+          v[t].y *= gain;
+        }
+      }
+    } else if (SOURCE == SRC_FOLD) {
+      const float2* p0 = a.src + base;
+#pragma unroll
+      for (int t = 0; t < R; ++t) {
+        const int idx = j + t * a.nb;
+        float2 xk = p0[idx], xm = p0[a.M - idx];
+        if (t == 0 && j == 0) {  // c2r ignores the imaginary parts of the DC and Nyquist bins
+          xk.y = 0.0f;
+          xm.y = 0.0f;
+        }
+        const float2 s = make_float2(xk.x + xm.x, xk.y - xm.y);  // X[k] + conj X[M-k]
+        const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);  // X[k] - conj X[M-k]
+        const float2 wd = cmul(d, a.tw_w[idx]);
+        v[t] = make_float2(s.x - wd.y, s.y + wd.x);  // s + i w d
+      }
+    } else if (SOURCE == SRC_UNFOLD) {
+      // conj X[k] = 1/2 [(Y[k] + conj Y[M-k]) + i e^{+2 pi i k / W} (Y[k] - conj Y[M-k])], Y = conj FFT_M(packed
+      // row), indices mod M (the 1/2 is folded into the output scale)
+      const bool nyq = k == a.M;
+      const int kk = nyq ? 0 : k, mm = (k == 0 || nyq) ? 0 : a.M - k;
+      const float2 wk = nyq ? make_float2(-1.0f, 0.0f) : a.tw_w[k];
+      const float2* yp = a.src + g * a.plane_elems + j * a.pitch;
+      const int ystep = a.nb * a.pitch;
+#pragma unroll
+      for (int t = 0; t < R; ++t) {
+        const float2 yk = yp[t * ystep + kk], ym = yp[t * ystep + mm];
+        const float2 s = make_float2(yk.x + ym.x, yk.y - ym.y);
+        const float2 d = make_float2(yk.x - ym.x, yk.y + ym.y);
+        const float2 wd = cmul(d, wk);
+        v[t] = make_float2(s.x - wd.y, s.y + wd.x);
+      }
+    } else {
+      const float2* p = a.src + base + j * stride;
+      const int step = a.nb * stride;
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = p[t * step];
+      if (SOURCE == SRC_SMEM_CONJ) {
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t].y = -v[t].y;
+      }
+      if (SOURCE == SRC_CONJ_MASK) {
+        const float* mp = a.mask + (j * a.wh + k);  // COLS only
+        const int mstep = a.nb * a.wh;
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+          const float gain = a.mask != nullptr ? __ldg(mp + t * mstep) : 1.0f;
+          v[t] = make_float2(v[t].x * gain, -v[t].y * gain);
+        }
+      }
+    }
+    int out_base = j * R;  // first stage: Ns = 1
+    if (!FIRST) {
+      const ushort2 e = a.tab[j];
+      out_base = e.x;
+      const float2* twp = a.tw;
+      const int tstep = e.y;
+#pragma unroll
+      for (int t = 1; t < R; ++t) v[t] = cmul_conj(v[t], twp[t * tstep]);
+    }
+    dft_inverse<R>(v);
+    float2* out = a.dst + base + out_base * stride;
+    const int ostep = (FIRST ? 1 : a.ns) * stride;
+#pragma unroll
+    for (int t = 0; t < R; ++t) out[dft_out_index<R>(t) * ostep] = v[t];
   }
 }
 
+template <int SOURCE, bool COLS, bool FIRST>
+__device__ __forceinline__ void dispatch_stage(int R, const StageArgs& a) {
+  switch (R) {  // block-uniform
+    case 16: run_stage<SOURCE, 16, COLS, FIRST>(a); break;
+    case 10: run_stage<SOURCE, 10, COLS, FIRST>(a); break;
+    case 9: run_stage<SOURCE, 9, COLS, FIRST>(a); break;
+    case 8: run_stage<SOURCE, 8, COLS, FIRST>(a); break;
+    case 5: run_stage<SOURCE, 5, COLS, FIRST>(a); break;
+    case 4: run_stage<SOURCE, 4, COLS, FIRST>(a); break;
+    case 3: run_stage<SOURCE, 3, COLS, FIRST>(a); break;
+    default: run_stage<SOURCE, 2, COLS, FIRST>(a); break;
+  }
+}
+
+// All stages of one axis. `first_src` feeds stage 0 (SOURCE kind FIRST_SOURCE); later stages ping-pong.
+// On return `cur` holds the result.
+template <int FIRST_SOURCE, bool COLS>
+__device__ __forceinline__ void run_axis(const AxisPlan& plan, StageArgs& a, const float2* first_src, const ushort2* tab,
+                                         float2*& cur, float2*& oth) {
+  for (int f = 0; f < plan.n_stages; ++f) {
+    a.dst = oth;
+    a.nb = plan.nb[f];
+    a.ns = plan.ns[f];
+    a.tab = tab + plan.tab_off[f];
+    if (f == 0) {
+      a.src = first_src;
+      dispatch_stage<FIRST_SOURCE, COLS, true>(plan.radix[0], a);
+    } else {
+      a.src = cur;
+      dispatch_stage<SRC_SMEM, COLS, false>(plan.radix[f], a);
+    }
+    __syncthreads();
+    float2* t = cur;
+    cur = oth;
+    oth = t;
+  }
+}
+
+// butterfly table of one axis: for butterfly j of stage f, .x = output base (j / Ns) * Ns * R + (j % Ns),
+// .y = twiddle base (j % Ns) * N / (Ns * R). Built once per CTA so the stage loops hold no division.
+__device__ void build_axis_table(const AxisPlan& plan, ushort2* __restrict__ tab) {
+  for (int f = 1; f < plan.n_stages; ++f) {
+    const int R = plan.radix[f], Ns = plan.ns[f], nb = plan.n / R, unit = plan.n / (Ns * R);
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+      const int k0 = j % Ns;
+      tab[plan.tab_off[f] + j] = make_ushort2((unsigned short)((j / Ns) * Ns * R + k0), (unsigned short)(k0 * unit));
+    }
+  }
+}
+
+__host__ __device__ __forceinline__ unsigned magic_of(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); }
+
+template <bool REAL>
 __global__ void __launch_bounds__(kBatchedThreads, 1)
 spectral_batched_kernel(SpectralBatchedLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SonarSpectralParams& p = L.p;
-  const int H = p.H, W = p.W, M = W >> 1, Wh = L.wh, P = L.pitch;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int H = p.H, W = p.W, M = W >> 1, Wh = L.wh, P = L.pitch, G = L.group;
   float2* tw_h = reinterpret_cast<float2*>(smem_raw);  // e^{-2 pi i k / H}
   float2* tw_m = tw_h + H;                             // e^{-2 pi i k / M}
   float2* tw_w = tw_m + M;                             // e^{+2 pi i k / W}, k < M
   float2* buf0 = tw_w + M;
-  float2* buf1 = buf0 + (size_t)H * P;
-  ushort2* tab_col = reinterpret_cast<ushort2*>(buf1 + (size_t)H * P);
+  float2* buf1 = buf0 + (size_t)G * L.plane_elems;
+  const unsigned magic_m = L.magic_m;
+  ushort2* tab_col = reinterpret_cast<ushort2*>(buf1 + (size_t)G * L.plane_elems);
   ushort2* tab_row = tab_col + L.col.tab_size;
   build_axis_table(L.col, tab_col);
   build_axis_table(L.row, tab_row);
@@ -568,115 +708,170 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
     tw_w[k] = make_float2((float)cs, (float)sn);
   }
   __syncthreads();
-  const WarpGrid grid_col = make_warp_grid(Wh), grid_row = make_warp_grid(H);
+  StageArgs a;
+  a.mask = p.mask;
+  a.tw_w = tw_w;
+  a.group = G;
+  a.wh = Wh;
+  a.pitch = P;
+  a.plane_elems = L.plane_elems;
+  a.M = M;
+  a.spec_plane_elems = H * Wh;
+  a.magic_wh = L.magic_wh;
+  int magic_for = G;
+  unsigned magic_cols = L.magic_cols, magic_rows = L.magic_rows;
   float ms = 0.0f, mss = 0.0f;
-  for (int64_t plane = blockIdx.x; plane < p.planes; plane += gridDim.x) {
-    // ---- columns: inverse complex FFT of length H, batch = Wh columns (lanes = adjacent k). The first
-    // stage reads the global half spectrum (coalesced along k) and applies the gain on the fly. ----
-    float2* cur = buf1;  // "previous" buffer; the first stage ignores it
-    float2* oth = buf0;
-    StageIo io;
-    io.mask = p.mask;
-    io.tw_w = tw_w;
-    io.M = M;
-    io.src_pitch = Wh;
-    for (int f = 0; f < L.col.n_stages; ++f) {
-      if (f == 0) {
-        io.src = reinterpret_cast<const float2*>(p.in_spec) + plane * (int64_t)H * Wh;
-        batched_stage_inverse<SRC_SPECTRUM>(io, oth, L.col.nb[0], L.col.radix[0], L.col.ns[0], tw_h, tab_col, Wh, P, 1, grid_col);
-      } else {
-        io.src = cur;
-        batched_stage_inverse<SRC_SMEM>(io, oth, L.col.nb[f], L.col.radix[f], L.col.ns[f], tw_h, tab_col + L.col.tab_off[f], Wh, P, 1, grid_col);
+  for (int64_t plane0 = (int64_t)blockIdx.x * G; plane0 < p.planes; plane0 += (int64_t)gridDim.x * G) {
+    const int valid = (int)(p.planes - plane0 < G ? p.planes - plane0 : G);
+    if (valid != magic_for) {  // ragged last group only
+      magic_cols = magic_of(valid * Wh);
+      magic_rows = magic_of(valid * H);
+      magic_for = valid;
+    }
+    const int rows_total = valid * H;
+    float2* cur = buf0;
+    float2* oth = buf1;
+    if (REAL) {
+      // packed rows: (x[2n], x[2n+1]) as one complex value, coalesced float2 loads, odd pitch in smem
+      const float2* src = reinterpret_cast<const float2*>(p.in_real + plane0 * (int64_t)H * W);
+      for (int i = threadIdx.x; i < rows_total * M; i += blockDim.x) {
+        const int r = (int)__umulhi((unsigned)i, magic_m);
+        cur[r * P + (i - r * M)] = __ldg(src + i);
       }
       __syncthreads();
-      float2* t = cur;
-      cur = oth;
-      oth = t;
+      a.tw = tw_m;
+      a.nbatch = rows_total;
+      a.magic_batch = magic_rows;
+      run_axis<SRC_SMEM_CONJ, false>(L.row, a, cur, tab_row, cur, oth);
+      a.tw = tw_h;
+      a.nbatch = valid * Wh;
+      a.magic_batch = magic_cols;
+      run_axis<SRC_UNFOLD, true>(L.col, a, cur, tab_col, cur, oth);
+      run_axis<SRC_CONJ_MASK, true>(L.col, a, cur, tab_col, cur, oth);
+    } else {
+      // columns: inverse complex FFT of length H, batch = columns of the group's planes; the first stage
+      // reads the global half spectrum (coalesced along k) and applies the gain on the fly
+      a.tw = tw_h;
+      a.nbatch = valid * Wh;
+      a.magic_batch = magic_cols;
+      run_axis<SRC_SPECTRUM, true>(L.col, a, reinterpret_cast<const float2*>(p.in_spec) + plane0 * (int64_t)H * Wh, tab_col, cur,
+                                   oth);
     }
-    // ---- rows: inverse complex FFT of length M, batch = H rows (lanes = 32 rows, odd pitch). The first
-    // stage folds the Hermitian half row into M complex points while loading. ----
-    for (int f = 0; f < L.row.n_stages; ++f) {
-      io.src = cur;
-      if (f == 0)
-        batched_stage_inverse<SRC_FOLD>(io, oth, L.row.nb[0], L.row.radix[0], L.row.ns[0], tw_m, tab_row, H, 1, P, grid_row);
-      else
-        batched_stage_inverse<SRC_SMEM>(io, oth, L.row.nb[f], L.row.radix[f], L.row.ns[f], tw_m, tab_row + L.row.tab_off[f], H, 1, P, grid_row);
-      __syncthreads();
-      float2* t = cur;
-      cur = oth;
-      oth = t;
+    // rows: inverse complex FFT of length M, batch = rows of the group's planes; the first stage folds the
+    // Hermitian half row into M complex points while loading
+    a.tw = tw_m;
+    a.nbatch = rows_total;
+    a.magic_batch = magic_rows;
+    run_axis<SRC_FOLD, false>(L.row, a, cur, tab_row, cur, oth);
+    // store: x[y][2n], x[y][2n+1] = z[y][n] * scale, coalesced float2, moments on the fly
+    float2* dst = reinterpret_cast<float2*>(p.out + plane0 * (int64_t)H * W);
+    for (int i = threadIdx.x; i < rows_total * M; i += blockDim.x) {
+      const int r = (int)__umulhi((unsigned)i, magic_m);
+      const float2 z = cur[r * P + (i - r * M)];
+      const float2 o = make_float2(z.x * L.scale, z.y * L.scale);
+      dst[i] = o;
+      ms += o.x + o.y;
+      mss += o.x * o.x + o.y * o.y;
     }
-    // ---- store: x[y][2n], x[y][2n+1] = z[y][n] * scale, coalesced float2, moments on the fly ----
-    float* dst = p.out + plane * (int64_t)H * W;
-    for (int y = warp; y < H; y += nwarps) {
-      for (int n = lane; n < M; n += 32) {
-        const float2 z = cur[y * P + n];
-        const float2 o = make_float2(z.x * p.out_scale, z.y * p.out_scale);
-        *reinterpret_cast<float2*>(dst + y * W + 2 * n) = o;
-        ms += o.x + o.y;
-        mss += o.x * o.x + o.y * o.y;
-      }
-    }
-    __syncthreads();  // the next plane's first stage overwrites a buffer this pass reads
+    __syncthreads();  // the next group's first stage overwrites a buffer this pass reads
   }
   commit_moments(p.sums, p.sums_clear, ms, mss);
+}
+
+// Fewest stages over the radix set, ties broken by the smaller radix sum (8 x 8 before 16 x 4).
+static void search_plan(int rem, int depth, int sum, int* cur, int* best, int* best_depth, int* best_sum) {
+  static const int kRadices[] = {16, 10, 9, 8, 5, 4, 3, 2};
+  if (rem == 1) {
+    if (depth < *best_depth || (depth == *best_depth && sum < *best_sum)) {
+      *best_depth = depth;
+      *best_sum = sum;
+      for (int i = 0; i < depth; ++i) best[i] = cur[i];
+    }
+    return;
+  }
+  if (depth + 1 > *best_depth || depth >= kBatchedMaxStages) return;
+  for (int r : kRadices) {
+    if (rem % r != 0 || (depth > 0 && r > cur[depth - 1])) continue;  // non-increasing: each multiset once
+    cur[depth] = r;
+    search_plan(rem / r, depth + 1, sum + r, cur, best, best_depth, best_sum);
+  }
 }
 
 static bool make_axis_plan(int n, AxisPlan* plan) {
   plan->n = n;
   plan->n_stages = 0;
   plan->tab_size = 0;
-  if (n > 65535) return false;
-  int rem = n, ns = 1;
-  auto push = [&](int r) {
-    if (plan->n_stages >= kBatchedMaxStages) return false;
-    plan->radix[plan->n_stages] = r;
-    plan->ns[plan->n_stages] = ns;
-    plan->nb[plan->n_stages] = n / r;
-    plan->tab_off[plan->n_stages] = plan->tab_size;
+  if (n < 2 || n > 65535) return false;
+  int cur[kBatchedMaxStages], best[kBatchedMaxStages], best_depth = kBatchedMaxStages + 1, best_sum = 1 << 30;
+  search_plan(n, 0, 0, cur, best, &best_depth, &best_sum);
+  if (best_depth > kBatchedMaxStages) return false;  // another prime factor: the generic kernel handles it
+  int ns = 1;
+  for (int f = 0; f < best_depth; ++f) {
+    const int r = best[f];
+    plan->radix[f] = r;
+    plan->ns[f] = ns;
+    plan->nb[f] = n / r;
+    plan->tab_off[f] = plan->tab_size;
     plan->tab_size += n / r;
-    ++plan->n_stages;
     ns *= r;
-    return true;
-  };
-  while (rem % 4 == 0) {
-    if (!push(4)) return false;
-    rem /= 4;
   }
-  for (int r : {2, 3, 5})
-    while (rem % r == 0) {
-      if (!push(r)) return false;
-      rem /= r;
-    }
-  return rem == 1;  // any other prime factor: the generic kernel handles it
+  plan->n_stages = best_depth;
+  return true;
 }
 
-static size_t batched_smem_bytes(int H, int W, const AxisPlan& col, const AxisPlan& row) {
+static size_t batched_smem_bytes(int H, int W, int group, const AxisPlan& col, const AxisPlan& row) {
   const int M = W / 2, wh = M + 1, pitch = wh | 1;
-  return ((size_t)H + 2 * (size_t)M + 2 * (size_t)H * pitch) * sizeof(float2) +
+  return ((size_t)H + 2 * (size_t)M + 2 * (size_t)group * H * pitch) * sizeof(float2) +
          (size_t)(col.tab_size + row.tab_size) * sizeof(ushort2);
 }
 
 // 0 = launched; -1 = not applicable (caller falls back to the generic kernel); > 0 = CUDA error
 static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t stream) {
-  if (p.in_spec == nullptr || (p.W & 1) || p.W < 2 || p.H < 1) return -1;
+  if ((p.W & 1) || p.W < 4 || p.H < 2) return -1;
   if ((reinterpret_cast<uintptr_t>(p.out) & 7u) != 0) return -1;
+  if (p.in_real != nullptr && (reinterpret_cast<uintptr_t>(p.in_real) & 7u) != 0) return -1;
   SpectralBatchedLaunch L;
   L.p = p;
   if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row)) return -1;
-  // the spectrum load and the Hermitian fold ride on the first stage of each axis: both must exist
-  if (L.col.n_stages == 0 || L.row.n_stages == 0) return -1;
-  L.wh = p.W / 2 + 1;
+  const int M = p.W / 2;
+  L.wh = M + 1;
   L.pitch = L.wh | 1;
+  L.plane_elems = p.H * L.pitch;
+  L.scale = p.in_real != nullptr ? 0.5f * p.out_scale : p.out_scale;
   const DeviceInfo& di = device_info();
-  const size_t smem = batched_smem_bytes(p.H, p.W, L.col, L.row);
-  if (smem > (size_t)di.max_smem_optin || (int64_t)p.H * L.pitch >= (1 << 24)) return -1;
-  cudaError_t err = cudaFuncSetAttribute(spectral_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (batched_smem_bytes(p.H, p.W, 1, L.col, L.row) > (size_t)di.max_smem_optin) return -1;
+  // planes per pass: enough butterflies to occupy the CTA in the leanest stage, without starving SMs
+  const int64_t items_col = (int64_t)(p.H / L.col.radix[0]) * L.wh, items_row = (int64_t)(M / L.row.radix[0]) * p.H;
+  const int64_t items_min = items_col < items_row ? items_col : items_row;
+  int64_t group = (kBatchedThreads + items_min - 1) / items_min;
+  const int64_t per_sm = (p.planes + di.sm_count - 1) / di.sm_count;
+  if (group > per_sm) group = per_sm;
+  if (const char* e = getenv("SONAR_SPECTRAL_GROUP")) group = atoi(e);  // experiment
+  while (group > 1 && batched_smem_bytes(p.H, p.W, (int)group, L.col, L.row) > (size_t)di.max_smem_optin) --group;
+  if (group < 1) group = 1;
+  L.group = (int)group;
+  // index arithmetic: 16-bit butterfly tables, 32-bit magic division exact for w * nbatch < 2^32
+  const int64_t nbatch_max = group * (L.wh > p.H ? L.wh : p.H);
+  const int64_t items_max = nbatch_max * ((p.H > M ? p.H : M) / 2);
+  if (items_max * nbatch_max >= (1ll << 32) || group * L.plane_elems >= (1 << 24)) return -1;
+  if (group * p.H * M * (int64_t)M >= (1ll << 32)) return -1;
+  L.magic_m = magic_of(M);
+  L.magic_wh = magic_of(L.wh);
+  L.magic_cols = magic_of(L.group * L.wh);
+  L.magic_rows = magic_of(L.group * p.H);
+  const size_t smem = batched_smem_bytes(p.H, p.W, L.group, L.col, L.row);
+  auto kernel = p.in_real != nullptr ? spectral_batched_kernel<true> : spectral_batched_kernel<false>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  const int per_sm = (int)((size_t)(di.max_smem_optin + 1024) / (smem + 1024)) >= 2 ? 2 : 1;
-  int64_t grid = (int64_t)di.sm_count * per_sm;
-  if (grid > p.planes) grid = p.planes;
-  spectral_batched_kernel<<<(unsigned)grid, kBatchedThreads, smem, stream>>>(L);
+  int64_t grid = (p.planes + L.group - 1) / L.group;
+  int threads = kBatchedThreads, ctas_per_sm = 1;
+  if (const char* e = getenv("SONAR_SPECTRAL_THREADS")) {  // experiment
+    threads = atoi(e);
+    ctas_per_sm = kBatchedThreads / threads;
+    if ((smem + 1024) * ctas_per_sm > (size_t)di.max_smem_optin + 1024) ctas_per_sm = 1;
+  }
+  if (grid > di.sm_count * ctas_per_sm) grid = di.sm_count * ctas_per_sm;
+  kernel<<<(unsigned)grid, threads, smem, stream>>>(L);
   err = cudaGetLastError();
   return err == cudaSuccess ? 0 : (int)err;
 }

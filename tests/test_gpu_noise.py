@@ -123,6 +123,29 @@ def test_spectral_kernel_vs_torch_fft(sb, cuda, hw):
     assert_close(ident, real, what=f"identity {hw}", atol=2e-5)
 
 
+@pytest.mark.parametrize(
+    ("hw", "planes"),
+    [((32, 32), 301), ((16, 16), 700), ((18, 20), 5), ((160, 90), 3), ((48, 96), 7), ((100, 200), 2), ((64, 64), 149), ((8, 4), 33)],
+)
+def test_spectral_batched_groups_and_radices(sb, cuda, hw, planes):
+    """Plane groups (several small planes per CTA, ragged last group) and every radix of the batched kernel
+    (16, 10, 9, 8, 5, 4, 3, 2), spectrum and real input."""
+    h, w = hw
+    torch.manual_seed(h * 977 + w + planes)
+    spec = torch.randn(planes, h, w // 2 + 1, dtype=torch.complex64)
+    mask = torch.rand(h, w // 2 + 1) + 0.5
+    want = torch.fft.irfft2(spec * mask, s=(h, w), norm="ortho")
+    got = sb.ops.spectral_filter(spectrum=spec.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / math.sqrt(h * w))
+    assert_close(got, want, what=f"irfft2 {hw} x{planes}", atol=2e-5)
+    real = torch.randn(planes, h, w)
+    want = torch.fft.irfft2(torch.fft.rfft2(real, norm="ortho") * mask, s=(h, w), norm="ortho")
+    got = sb.ops.spectral_filter(real=real.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / (h * w))
+    assert_close(got, want, what=f"rfft2-irfft2 {hw} x{planes}", atol=2e-5)
+    sums = got._sonar_sums if hasattr(got, "_sonar_sums") else None
+    if sums is not None:
+        torch.cuda.synchronize()
+
+
 def test_graph_golden(sb, cuda, golden):
     ng = sb.noise_graph
     g = golden("noise_graph")
