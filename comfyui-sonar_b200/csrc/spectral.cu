@@ -14,6 +14,8 @@
 // stays in shared memory -- or in an L2-resident global scratch when a plane is too large (256^2:
 // 258 KB > 227 KB) -- and every 1-D FFT is a warp-level mixed-radix Stockham transform in a per-warp
 // ping-pong scratch. Rows are processed two at a time (real pair <-> one complex FFT).
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <type_traits>
 
@@ -314,35 +316,45 @@ spectral_plane_kernel(SpectralLaunch L) {
 }
 
 // =============================================================================================
-// Batched variant for the hot case (even W, lengths that factor into radices 2/3/4/5/8/9/10/16): every
-// FFT stage is ONE pass of the whole CTA over a group of planes, one register-resident radix-R butterfly
-// per thread. Work items (butterfly j, transform b) are flattened with b fastest, so adjacent lanes run
-// the same butterfly of adjacent transforms (columns: adjacent k, contiguous in shared memory; rows:
-// adjacent rows, conflict-free thanks to the odd pitch) whatever the batch size; small planes (UNet
-// activations, 32x32) are processed several per CTA so the 1024 threads stay busy.
-// Large radices keep the pass count low: 90 = 10 x 9 and 80 = 10 x 8 are two passes each (radices 6..16
-// are Cooley-Tukey compositions of the 2/3/4/5 butterflies inside registers, inner twiddles compile-time
-// constants), and the first pass of every axis has no twiddle multiplications at all.
+// Batched in-place variant for the hot case (even W, lengths that factor into radices 2/3/4/5/8/9/10/16).
+//  * Every FFT stage is ONE pass of the CTA over a group of planes, one register-resident radix-R butterfly
+//    per work item (butterfly j, transform b), b fastest: adjacent lanes run the same butterfly of adjacent
+//    transforms (columns: adjacent column slots, contiguous in shared memory; rows: adjacent rows,
+//    conflict-free thanks to the odd pitch) whatever the batch size. Small planes (UNet activations,
+//    32x32) are processed several per CTA.
+//  * Large radices keep the pass count low: 90 = 10 x 9 and 80 = 10 x 8 are two passes each (radices 8..16
+//    are Cooley-Tukey compositions of the 2/3/4/5 butterflies inside registers, inner twiddles compile-time
+//    constants); the block-length-R stage of every axis has no twiddle multiplications.
+//  * The transforms are IN PLACE (decimation in time: digit-reversed slots in, natural order out;
+//    decimation in frequency: natural in, digit-reversed out): each butterfly owns its R slots, a plane
+//    needs ONE shared-memory copy (58 KB at 90x160, 67 KB at 128x128), so 2-4 CTAs share an SM and one
+//    CTA's barrier / global-load phases overlap the others' arithmetic. The ping-pong (Stockham) form of
+//    this kernel fit one CTA per SM and sat at 49 % issue-slot utilisation with no eligible warp half of
+//    the time (ncu r01h); on 64x64 planes, where both forms fit, 4 CTAs of 256 threads ran 1.5x faster
+//    than 1 CTA of 1024.
+//  * Digit reversal costs nothing: the first inverse column stage gathers the global half spectrum
+//    straight into digit-reversed row slots (and permuted column slots), after which the column DIT, the
+//    Hermitian fold and the row DIT leave the plane in natural order for a coalesced store.
 // Rows use the half-length c2r trick: for Hermitian X of even length W, with M = W/2,
 //   Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W},   k = 0..M-1
 //   z = sum_k Z[k] e^{+2 pi i k n / M}  ==>  x[2n] = Re z[n], x[2n+1] = Im z[n]
 // which also reproduces irfft2's treatment of the reference's NON-Hermitian input (the imaginary
 // parts of the k = 0 and k = M bins are dropped, nothing else of the upper half is read).
 // Real input (rfft2 front end: PowerFilterNoiseItem, OneF / GreenTest, FreeU-Extreme ffilter) runs the
-// same inverse stages on conjugated data (FFT(z) = conj(IFFT(conj z))): rows r2c by the half-length
-// trick in reverse (the "unfold" rides on the first forward column stage), then columns, gain, and the
-// inverse path above -- the plane still makes exactly one trip from and one trip to HBM.
+// same inverse-sign stages on conjugated data (FFT(z) = conj(IFFT(conj z))): packed rows -> row DIF ->
+// r2c unfold -> column DIF -> gain (.) conj -> the inverse path above. The plane still makes exactly one
+// trip from and one trip to HBM.
 // History: warp-per-transform kernel 237 issued instructions per output element at 90x160, radix 2..5
-// batched-lane kernel 158 (ncu r01g: 62 % issue-slot busy, 43 % of it integer / address arithmetic).
+// batched-lane kernel 158 (ncu r01g), ping-pong large-radix kernel 92 (ncu r01h).
 // =============================================================================================
-constexpr int kBatchedThreads = 1024;
+constexpr int kBatchedThreads = 512;  // per CTA, at most; >= 2 CTAs per SM
 constexpr int kBatchedMaxStages = 16;
 
 struct AxisPlan {
   int n;
   int n_stages;
   int radix[kBatchedMaxStages];
-  int ns[kBatchedMaxStages];       // product of the radices before the stage
+  int m[kBatchedMaxStages];        // distance between a butterfly's slots: n / (radix[0] * ... * radix[f])
   int nb[kBatchedMaxStages];       // butterflies per transform in the stage (n / radix)
   int tab_off[kBatchedMaxStages];  // offset of the stage's butterfly table
   int tab_size;
@@ -357,7 +369,7 @@ struct SpectralBatchedLaunch {
   int plane_elems;  // H * pitch
   int group;        // planes per CTA pass
   float scale;      // out_scale (x 1/2 for real input: the r2c unfold leaves a factor 2)
-  unsigned magic_m, magic_wh, magic_cols, magic_rows;  // ceil(2^32 / d) for d = M, wh, group * wh, group * H
+  unsigned magic_wh, magic_cols, magic_rows, magic_row_nb;  // ceil(2^32 / d): d = wh, group * wh, group * H, M / last row radix
 };
 
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {  // a * conj(w)
@@ -499,188 +511,258 @@ __device__ __forceinline__ void dft_inverse(float2 (&v)[R]) {
   }
 }
 
-// Where the first stage of an axis reads its inputs from.
+// Where the first executed stage of an axis gets its inputs from.
 enum StageSource : int {
-  SRC_SMEM = 0,       // the other ping-pong buffer
-  SRC_SMEM_CONJ = 1,  // the other buffer, conjugated (first forward row stage over the packed real rows)
+  SRC_PLAIN = 0,      // the butterfly's own slots
+  SRC_CONJ_IN = 1,    // own slots, conjugated
   SRC_SPECTRUM = 2,   // first inverse column stage, spectrum input: global half spectrum (.) gain mask
   SRC_CONJ_MASK = 3,  // first inverse column stage, real input: conj(forward result) (.) gain mask
-  SRC_FOLD = 4,       // first inverse row stage: Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W}
-  SRC_UNFOLD = 5      // first forward column stage: conj X[k] from the half-length row transforms
+  SRC_REAL_ROWS = 4   // first forward row stage: packed pairs (x[2n], -x[2n+1]) gathered from the global real plane
 };
+enum StageSink : int {
+  SINK_SLOTS = 0,  // back into the butterfly's own slots
+  SINK_GLOBAL = 1  // last inverse row stage: x[y][2n], x[y][2n+1] = z[n] * scale straight to the global plane
+};
+enum StageMode : int { MODE_DIT = 0, MODE_DIF = 1 };
 
 struct StageArgs {
-  const float2* src;     // shared-memory source (SRC_SPECTRUM: the group's first global plane)
-  float2* dst;
-  const float2* tw;      // e^{-2 pi i k / n} of the axis
-  const ushort2* tab;    // butterfly table of the stage (unused by first stages)
-  const float* mask;     // (H, wh) gain or nullptr
-  const float2* tw_w;    // e^{+2 pi i k / W}, k < M
-  int nb, ns;
-  int nbatch;            // transforms in this pass (valid planes x columns or rows)
-  unsigned magic_batch;  // ceil(2^32 / nbatch)
-  unsigned magic_wh;     // ceil(2^32 / wh)
-  int group;             // planes per pass the kernel was launched with (1: no plane split of b)
+  float2* buf;                  // the CTA's planes, [plane][row][pitch]
+  const float2* spec;           // SRC_SPECTRUM: the group's first global plane
+  const float2* tw;             // e^{-2 pi i k / n} of the axis
+  const ushort2* tab;           // butterfly table of the stage: .x first slot, .y twiddle step
+  const float* mask;            // (H, wh) gain or nullptr
+  const unsigned short* pos_m;  // row axis: index n -> slot after a DIF transform (= slot a DIT transform reads it from)
+  const unsigned short* idx_h;  // column axis: slot -> index ky
+  const float2* real_rows;      // SRC_REAL_ROWS: the group's first global plane as (W/2) float2 per row
+  float2* out_rows;             // SINK_GLOBAL: the group's first output plane as (W/2) float2 per row
+  float scale;                  // SINK_GLOBAL
+  float ms, mss;                // SINK_GLOBAL: moments of what this thread stored
+  unsigned magic_nb;            // ceil(2^32 / nb) of the block-length-R row stage
+  int nb, m;                    // butterflies per transform, distance between a butterfly's slots
+  int nbatch;                   // transforms in this pass (valid planes x columns or rows)
+  unsigned magic_batch;         // ceil(2^32 / nbatch)
+  unsigned magic_wh;            // ceil(2^32 / wh)
+  int group;                    // planes per pass the kernel was launched with (1: no plane split of b)
   int wh, pitch, plane_elems, M;
-  int spec_plane_elems;  // H * wh (global spectrum plane)
+  int spec_plane_elems;         // H * wh (global spectrum plane)
 };
 
-// One inverse Stockham stage over a batch of transforms, one radix-R butterfly per thread and iteration.
-// Element t of transform b lives at base(b) + t * stride: columns base = plane * plane_elems + k, stride =
-// pitch; rows base = b * pitch (b = plane * H + y), stride = 1.
-template <int SOURCE, int R, bool COLS, bool FIRST>
-__device__ __forceinline__ void run_stage(const StageArgs& a) {
+// One in-place inverse-sign stage over a batch of transforms: every (butterfly j, transform b) item owns
+// its R slots, so a thread may run any number of items and the CTA needs one buffer only.
+//   DIT (digit-reversed in -> natural out, stages last..first): twiddle the inputs, butterfly, store;
+//   DIF (natural in -> digit-reversed out, stages first..last): butterfly, twiddle the outputs, store.
+// NOTW: the stage with block length R (all twiddles are 1). Slot s of transform b lives at base(b) + s *
+// stride: columns base = plane * plane_elems + column slot, stride = pitch; rows base = b * pitch, stride 1.
+template <int MODE, int SOURCE, int SINK, int R, bool COLS, bool NOTW>
+__device__ __forceinline__ void run_stage(StageArgs& a) {
+  // The block-length-R row stage that talks to global memory runs its items butterfly-fastest: butterfly
+  // `lo` of a row owns indices lo + t * nb, so adjacent lanes touch adjacent float2 of the global row.
+  constexpr bool GLOBAL_ROWS = SOURCE == SRC_REAL_ROWS || SINK == SINK_GLOBAL;
+  static_assert(!GLOBAL_ROWS || (!COLS && NOTW), "global row stages are the block-length-R row stage");
   const int total = a.nb * a.nbatch;
   const int stride = COLS ? a.pitch : 1;
+  const int estep = a.m * stride;
   for (int w = threadIdx.x; w < total; w += blockDim.x) {
-    const int j = (int)__umulhi((unsigned)w, a.magic_batch);
-    const int b = w - j * a.nbatch;
-    int g = 0, k = b, base;
-    if (COLS) {
-      if (a.group > 1) {
-        g = (int)__umulhi((unsigned)b, a.magic_wh);
-        k = b - g * a.wh;
-      }
-      base = g * a.plane_elems + k;
-    } else {
+    int j, b, g = 0, c = 0, base, first_slot, tstep = 0;
+    if (GLOBAL_ROWS) {
+      b = a.nb == 1 ? w : (int)__umulhi((unsigned)w, a.magic_nb);  // (ceil(2^32 / 1) does not fit 32 bits)
+      j = w - b * a.nb;                 // lowest index of the butterfly
+      first_slot = (int)a.pos_m[j];     // its slots are first_slot .. first_slot + R - 1
       base = b * a.pitch;
+    } else {
+      j = (int)__umulhi((unsigned)w, a.magic_batch);
+      b = w - j * a.nbatch;
+      c = b;
+      if (COLS) {
+        if (a.group > 1) {
+          g = (int)__umulhi((unsigned)b, a.magic_wh);
+          c = b - g * a.wh;
+        }
+        base = g * a.plane_elems + c;
+      } else {
+        base = b * a.pitch;
+      }
+      const ushort2 e = a.tab[j];
+      first_slot = e.x;
+      tstep = e.y;
     }
+    float2* p = a.buf + base + first_slot * stride;
     float2 v[R];
-    if (SOURCE == SRC_SPECTRUM) {
-      const int e0 = j * a.wh + k, estep = a.nb * a.wh;
-      const float2* gp = a.src + ((int64_t)g * a.spec_plane_elems + e0);
+    if (SOURCE == SRC_SPECTRUM) {  // block length R: the slots are rows first_slot .. first_slot + R - 1
+      const float2* gp = a.spec + ((int64_t)g * a.spec_plane_elems + c);
+      const float* mp = a.mask + c;
+      const bool has_mask = a.mask != nullptr;
 #pragma unroll
-      for (int t = 0; t < R; ++t) v[t] = __ldg(gp + t * estep);
-      if (a.mask != nullptr) {
-        const float* mp = a.mask + e0;
-#pragma unroll
-        for (int t = 0; t < R; ++t) {
-          const float gain = __ldg(mp + t * estep);
+      for (int t = 0; t < R; ++t) {
+        const int off = (int)a.idx_h[first_slot + t] * a.wh;
+        v[t] = __ldg(gp + off);
+        if (has_mask) {
+          const float gain = __ldg(mp + off);
           v[t].x *= gain;
           v[t].y *= gain;
         }
       }
-    } else if (SOURCE == SRC_FOLD) {
-      const float2* p0 = a.src + base;
+    } else if (SOURCE == SRC_REAL_ROWS) {
+      const float2* gp = a.real_rows + ((int64_t)b * a.M + j);
 #pragma unroll
       for (int t = 0; t < R; ++t) {
-        const int idx = j + t * a.nb;
-        float2 xk = p0[idx], xm = p0[a.M - idx];
-        if (t == 0 && j == 0) {  // c2r ignores the imaginary parts of the DC and Nyquist bins
-          xk.y = 0.0f;
-          xm.y = 0.0f;
-        }
-        const float2 s = make_float2(xk.x + xm.x, xk.y - xm.y);  // X[k] + conj X[M-k]
-        const float2 d = make_float2(xk.x - xm.x, xk.y + xm.y);  // X[k] - conj X[M-k]
-        const float2 wd = cmul(d, a.tw_w[idx]);
-        v[t] = make_float2(s.x - wd.y, s.y + wd.x);  // s + i w d
-      }
-    } else if (SOURCE == SRC_UNFOLD) {
-      // conj X[k] = 1/2 [(Y[k] + conj Y[M-k]) + i e^{+2 pi i k / W} (Y[k] - conj Y[M-k])], Y = conj FFT_M(packed
-      // row), indices mod M (the 1/2 is folded into the output scale)
-      const bool nyq = k == a.M;
-      const int kk = nyq ? 0 : k, mm = (k == 0 || nyq) ? 0 : a.M - k;
-      const float2 wk = nyq ? make_float2(-1.0f, 0.0f) : a.tw_w[k];
-      const float2* yp = a.src + g * a.plane_elems + j * a.pitch;
-      const int ystep = a.nb * a.pitch;
-#pragma unroll
-      for (int t = 0; t < R; ++t) {
-        const float2 yk = yp[t * ystep + kk], ym = yp[t * ystep + mm];
-        const float2 s = make_float2(yk.x + ym.x, yk.y - ym.y);
-        const float2 d = make_float2(yk.x - ym.x, yk.y + ym.y);
-        const float2 wd = cmul(d, wk);
-        v[t] = make_float2(s.x - wd.y, s.y + wd.x);
+        v[t] = __ldg(gp + t * a.nb);
+        v[t].y = -v[t].y;
       }
     } else {
-      const float2* p = a.src + base + j * stride;
-      const int step = a.nb * stride;
 #pragma unroll
-      for (int t = 0; t < R; ++t) v[t] = p[t * step];
-      if (SOURCE == SRC_SMEM_CONJ) {
+      for (int t = 0; t < R; ++t) v[t] = p[t * estep];
+      if (SOURCE == SRC_CONJ_IN) {
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t].y = -v[t].y;
       }
       if (SOURCE == SRC_CONJ_MASK) {
-        const float* mp = a.mask + (j * a.wh + k);  // COLS only
-        const int mstep = a.nb * a.wh;
+        if (a.mask != nullptr) {
+          const float* mp = a.mask + c;
 #pragma unroll
-        for (int t = 0; t < R; ++t) {
-          const float gain = a.mask != nullptr ? __ldg(mp + t * mstep) : 1.0f;
-          v[t] = make_float2(v[t].x * gain, -v[t].y * gain);
+          for (int t = 0; t < R; ++t) {
+            const float gain = __ldg(mp + (int)a.idx_h[first_slot + t] * a.wh);
+            v[t] = make_float2(v[t].x * gain, -v[t].y * gain);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < R; ++t) v[t].y = -v[t].y;
         }
       }
     }
-    int out_base = j * R;  // first stage: Ns = 1
-    if (!FIRST) {
-      const ushort2 e = a.tab[j];
-      out_base = e.x;
-      const float2* twp = a.tw;
-      const int tstep = e.y;
+    if (MODE == MODE_DIT && !NOTW) {
 #pragma unroll
-      for (int t = 1; t < R; ++t) v[t] = cmul_conj(v[t], twp[t * tstep]);
+      for (int t = 1; t < R; ++t) v[t] = cmul_conj(v[t], a.tw[t * tstep]);
     }
     dft_inverse<R>(v);
-    float2* out = a.dst + base + out_base * stride;
-    const int ostep = (FIRST ? 1 : a.ns) * stride;
+    if (MODE == MODE_DIF && !NOTW) {
 #pragma unroll
-    for (int t = 0; t < R; ++t) out[dft_out_index<R>(t) * ostep] = v[t];
-  }
-}
-
-template <int SOURCE, bool COLS, bool FIRST>
-__device__ __forceinline__ void dispatch_stage(int R, const StageArgs& a) {
-  switch (R) {  // block-uniform
-    case 16: run_stage<SOURCE, 16, COLS, FIRST>(a); break;
-    case 10: run_stage<SOURCE, 10, COLS, FIRST>(a); break;
-    case 9: run_stage<SOURCE, 9, COLS, FIRST>(a); break;
-    case 8: run_stage<SOURCE, 8, COLS, FIRST>(a); break;
-    case 5: run_stage<SOURCE, 5, COLS, FIRST>(a); break;
-    case 4: run_stage<SOURCE, 4, COLS, FIRST>(a); break;
-    case 3: run_stage<SOURCE, 3, COLS, FIRST>(a); break;
-    default: run_stage<SOURCE, 2, COLS, FIRST>(a); break;
-  }
-}
-
-// All stages of one axis. `first_src` feeds stage 0 (SOURCE kind FIRST_SOURCE); later stages ping-pong.
-// On return `cur` holds the result.
-template <int FIRST_SOURCE, bool COLS>
-__device__ __forceinline__ void run_axis(const AxisPlan& plan, StageArgs& a, const float2* first_src, const ushort2* tab,
-                                         float2*& cur, float2*& oth) {
-  for (int f = 0; f < plan.n_stages; ++f) {
-    a.dst = oth;
-    a.nb = plan.nb[f];
-    a.ns = plan.ns[f];
-    a.tab = tab + plan.tab_off[f];
-    if (f == 0) {
-      a.src = first_src;
-      dispatch_stage<FIRST_SOURCE, COLS, true>(plan.radix[0], a);
+      for (int s = 0; s < R; ++s)
+        if (dft_out_index<R>(s) != 0) v[s] = cmul_conj(v[s], a.tw[dft_out_index<R>(s) * tstep]);
+    }
+    if (SINK == SINK_GLOBAL) {
+      float2* gp = a.out_rows + ((int64_t)b * a.M + j);
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const float2 o = make_float2(v[s].x * a.scale, v[s].y * a.scale);
+        gp[dft_out_index<R>(s) * a.nb] = o;
+        a.ms += o.x + o.y;
+        a.mss += o.x * o.x + o.y * o.y;
+      }
     } else {
-      a.src = cur;
-      dispatch_stage<SRC_SMEM, COLS, false>(plan.radix[f], a);
+#pragma unroll
+      for (int s = 0; s < R; ++s) p[dft_out_index<R>(s) * estep] = v[s];
     }
-    __syncthreads();
-    float2* t = cur;
-    cur = oth;
-    oth = t;
   }
 }
 
-// butterfly table of one axis: for butterfly j of stage f, .x = output base (j / Ns) * Ns * R + (j % Ns),
-// .y = twiddle base (j % Ns) * N / (Ns * R). Built once per CTA so the stage loops hold no division.
-__device__ void build_axis_table(const AxisPlan& plan, ushort2* __restrict__ tab) {
-  for (int f = 1; f < plan.n_stages; ++f) {
-    const int R = plan.radix[f], Ns = plan.ns[f], nb = plan.n / R, unit = plan.n / (Ns * R);
-    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-      const int k0 = j % Ns;
-      tab[plan.tab_off[f] + j] = make_ushort2((unsigned short)((j / Ns) * Ns * R + k0), (unsigned short)(k0 * unit));
+template <int MODE, int SOURCE, int SINK, bool COLS, bool NOTW>
+__device__ __forceinline__ void dispatch_stage(int R, StageArgs& a) {
+  switch (R) {  // block-uniform
+    case 16: run_stage<MODE, SOURCE, SINK, 16, COLS, NOTW>(a); break;
+    case 10: run_stage<MODE, SOURCE, SINK, 10, COLS, NOTW>(a); break;
+    case 9: run_stage<MODE, SOURCE, SINK, 9, COLS, NOTW>(a); break;
+    case 8: run_stage<MODE, SOURCE, SINK, 8, COLS, NOTW>(a); break;
+    case 5: run_stage<MODE, SOURCE, SINK, 5, COLS, NOTW>(a); break;
+    case 4: run_stage<MODE, SOURCE, SINK, 4, COLS, NOTW>(a); break;
+    case 3: run_stage<MODE, SOURCE, SINK, 3, COLS, NOTW>(a); break;
+    default: run_stage<MODE, SOURCE, SINK, 2, COLS, NOTW>(a); break;
+  }
+}
+
+// Inverse-sign transform of one axis by decimation in time, stages last..first: the block-length-R stage
+// reads FIRST_SOURCE (which supplies index k at slot pos[k]), the result is in natural order.
+template <int FIRST_SOURCE, bool COLS>
+__device__ __forceinline__ void run_axis_dit(const AxisPlan& plan, StageArgs& a, const ushort2* tab) {
+  for (int f = plan.n_stages - 1; f >= 0; --f) {
+    a.nb = plan.nb[f];
+    a.m = plan.m[f];
+    a.tab = tab + plan.tab_off[f];
+    if (f == plan.n_stages - 1)
+      dispatch_stage<MODE_DIT, FIRST_SOURCE, SINK_SLOTS, COLS, true>(plan.radix[f], a);
+    else
+      dispatch_stage<MODE_DIT, SRC_PLAIN, SINK_SLOTS, COLS, false>(plan.radix[f], a);
+    __syncthreads();
+  }
+}
+
+// Inverse-sign transform of one axis by decimation in frequency, stages first..last: natural order in,
+// index k ends at slot pos[k] -- or, with LAST_SINK = SINK_GLOBAL, in natural order in the global plane.
+template <int LAST_SINK, bool COLS>
+__device__ __forceinline__ void run_axis_dif(const AxisPlan& plan, StageArgs& a, const ushort2* tab) {
+  const int last = plan.n_stages - 1;
+  for (int f = 0; f <= last; ++f) {
+    a.nb = plan.nb[f];
+    a.m = plan.m[f];
+    a.tab = tab + plan.tab_off[f];
+    if (f == last)
+      dispatch_stage<MODE_DIF, SRC_PLAIN, LAST_SINK, COLS, true>(plan.radix[f], a);
+    else
+      dispatch_stage<MODE_DIF, SRC_PLAIN, SINK_SLOTS, COLS, false>(plan.radix[f], a);
+    __syncthreads();
+  }
+}
+
+// Hermitian pair pass over every row, in place and in natural order (column k at slot k, Nyquist at M):
+// each item turns the pair (A[k], A[M-k]) into (B[k], B[M-k]),
+//   B[k] = (A[k] + conj A[M-k]) + i e^{+2 pi i k / W} (A[k] - conj A[M-k]),
+// which is both the c2r fold (A = X, B = Z feeding the half-length inverse row transform) and the r2c
+// unfold (A = Y = conj FFT_M(packed row), B = 2 conj X). Only k = 0 differs: the fold drops the imaginary
+// parts of the DC and Nyquist bins and frees slot M, the unfold fills slot M.
+template <bool UNFOLD>
+__device__ __forceinline__ void pair_pass(float2* buf, int rows_total, unsigned magic_rows, int M, int pitch,
+                                          const float2* __restrict__ tw_w) {
+  const int total = ((M >> 1) + 1) * rows_total;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    const int k = (int)__umulhi((unsigned)w, magic_rows);
+    float2* row = buf + (w - k * rows_total) * pitch;
+    if (k == 0) {
+      if (UNFOLD) {
+        const float2 y0 = row[0];
+        row[0] = make_float2(2.0f * (y0.x - y0.y), 0.0f);
+        row[M] = make_float2(2.0f * (y0.x + y0.y), 0.0f);
+      } else {
+        const float x0 = row[0].x, xm = row[M].x;
+        row[0] = make_float2(x0 + xm, x0 - xm);
+      }
+      continue;
     }
+    const float2 ak = row[k], am = row[M - k];
+    const float2 s = make_float2(ak.x + am.x, ak.y - am.y);
+    const float2 d = make_float2(ak.x - am.x, ak.y + am.y);
+    const float2 wd = cmul(d, tw_w[k]);
+    row[k] = make_float2(s.x - wd.y, s.y + wd.x);
+    if (2 * k != M) row[M - k] = make_float2(s.x + wd.y, wd.x - s.y);
+  }
+}
+
+// Per-CTA tables of one axis. tab: for butterfly j of stage f (block length L = n / (R_0 .. R_{f-1}),
+// sub-length m = L / R_f): .x = first slot (j / m) * L + (j % m), .y = twiddle step (j % m) * (n / L).
+// pos[k] = slot of index k after a DIF transform (= slot a DIT transform wants it in), idx = its inverse.
+__device__ void build_axis_tables(const AxisPlan& plan, ushort2* __restrict__ tab, unsigned short* __restrict__ pos,
+                                  unsigned short* __restrict__ idx) {
+  for (int f = 0; f < plan.n_stages; ++f) {
+    const int R = plan.radix[f], m = plan.m[f], L = m * R, nb = plan.n / R, unit = plan.n / L;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+      const int i = j % m;
+      tab[plan.tab_off[f] + j] = make_ushort2((unsigned short)((j / m) * L + i), (unsigned short)(i * unit));
+    }
+  }
+  for (int k = threadIdx.x; k < plan.n; k += blockDim.x) {
+    int rem = k, slot = 0;
+    for (int f = 0; f < plan.n_stages; ++f) {
+      slot += (rem % plan.radix[f]) * plan.m[f];
+      rem /= plan.radix[f];
+    }
+    if (pos != nullptr) pos[k] = (unsigned short)slot;
+    if (idx != nullptr) idx[slot] = (unsigned short)k;
   }
 }
 
 __host__ __device__ __forceinline__ unsigned magic_of(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); }
 
 template <bool REAL>
-__global__ void __launch_bounds__(kBatchedThreads, 1)
+__global__ void __launch_bounds__(kBatchedThreads, 2)
 spectral_batched_kernel(SpectralBatchedLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SonarSpectralParams& p = L.p;
@@ -688,13 +770,13 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
   float2* tw_h = reinterpret_cast<float2*>(smem_raw);  // e^{-2 pi i k / H}
   float2* tw_m = tw_h + H;                             // e^{-2 pi i k / M}
   float2* tw_w = tw_m + M;                             // e^{+2 pi i k / W}, k < M
-  float2* buf0 = tw_w + M;
-  float2* buf1 = buf0 + (size_t)G * L.plane_elems;
-  const unsigned magic_m = L.magic_m;
-  ushort2* tab_col = reinterpret_cast<ushort2*>(buf1 + (size_t)G * L.plane_elems);
+  float2* buf = tw_w + M;
+  ushort2* tab_col = reinterpret_cast<ushort2*>(buf + (size_t)G * L.plane_elems);
   ushort2* tab_row = tab_col + L.col.tab_size;
-  build_axis_table(L.col, tab_col);
-  build_axis_table(L.row, tab_row);
+  unsigned short* pos_m = reinterpret_cast<unsigned short*>(tab_row + L.row.tab_size);
+  unsigned short* idx_h = pos_m + M;
+  build_axis_tables(L.col, tab_col, nullptr, idx_h);
+  build_axis_tables(L.row, tab_row, pos_m, nullptr);
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
     double sn, cs;
     sincospi(-2.0 * (double)k / (double)H, &sn, &cs);
@@ -709,8 +791,10 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
   }
   __syncthreads();
   StageArgs a;
+  a.buf = buf;
   a.mask = p.mask;
-  a.tw_w = tw_w;
+  a.pos_m = pos_m;
+  a.idx_h = idx_h;
   a.group = G;
   a.wh = Wh;
   a.pitch = P;
@@ -718,9 +802,12 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
   a.M = M;
   a.spec_plane_elems = H * Wh;
   a.magic_wh = L.magic_wh;
+  a.magic_nb = L.magic_row_nb;
+  a.scale = L.scale;
+  a.ms = 0.0f;
+  a.mss = 0.0f;
   int magic_for = G;
   unsigned magic_cols = L.magic_cols, magic_rows = L.magic_rows;
-  float ms = 0.0f, mss = 0.0f;
   for (int64_t plane0 = (int64_t)blockIdx.x * G; plane0 < p.planes; plane0 += (int64_t)gridDim.x * G) {
     const int valid = (int)(p.planes - plane0 < G ? p.planes - plane0 : G);
     if (valid != magic_for) {  // ragged last group only
@@ -729,53 +816,42 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
       magic_for = valid;
     }
     const int rows_total = valid * H;
-    float2* cur = buf0;
-    float2* oth = buf1;
     if (REAL) {
-      // packed rows: (x[2n], x[2n+1]) as one complex value, coalesced float2 loads, odd pitch in smem
-      const float2* src = reinterpret_cast<const float2*>(p.in_real + plane0 * (int64_t)H * W);
-      for (int i = threadIdx.x; i < rows_total * M; i += blockDim.x) {
-        const int r = (int)__umulhi((unsigned)i, magic_m);
-        cur[r * P + (i - r * M)] = __ldg(src + i);
-      }
-      __syncthreads();
+      // forward rows (half length, conj trick; the block-length-R stage gathers the packed real rows from
+      // global memory), r2c unfold, forward columns: conj rfft2 with ky at slot pos_h[ky]
+      a.real_rows = reinterpret_cast<const float2*>(p.in_real + plane0 * (int64_t)H * W);
       a.tw = tw_m;
       a.nbatch = rows_total;
       a.magic_batch = magic_rows;
-      run_axis<SRC_SMEM_CONJ, false>(L.row, a, cur, tab_row, cur, oth);
+      run_axis_dit<SRC_REAL_ROWS, false>(L.row, a, tab_row);
+      pair_pass<true>(buf, rows_total, magic_rows, M, P, tw_w);
+      __syncthreads();
       a.tw = tw_h;
       a.nbatch = valid * Wh;
       a.magic_batch = magic_cols;
-      run_axis<SRC_UNFOLD, true>(L.col, a, cur, tab_col, cur, oth);
-      run_axis<SRC_CONJ_MASK, true>(L.col, a, cur, tab_col, cur, oth);
+      run_axis_dif<SINK_SLOTS, true>(L.col, a, tab_col);
+      // gain, then inverse columns back to natural row order
+      run_axis_dit<SRC_CONJ_MASK, true>(L.col, a, tab_col);
     } else {
-      // columns: inverse complex FFT of length H, batch = columns of the group's planes; the first stage
-      // reads the global half spectrum (coalesced along k) and applies the gain on the fly
+      // inverse columns: the block-length-R stage gathers the rows of the global half spectrum into
+      // digit-reversed row slots (coalesced along k) and applies the gain on the fly
+      a.spec = reinterpret_cast<const float2*>(p.in_spec) + plane0 * (int64_t)H * Wh;
       a.tw = tw_h;
       a.nbatch = valid * Wh;
       a.magic_batch = magic_cols;
-      run_axis<SRC_SPECTRUM, true>(L.col, a, reinterpret_cast<const float2*>(p.in_spec) + plane0 * (int64_t)H * Wh, tab_col, cur,
-                                   oth);
+      run_axis_dit<SRC_SPECTRUM, true>(L.col, a, tab_col);
     }
-    // rows: inverse complex FFT of length M, batch = rows of the group's planes; the first stage folds the
-    // Hermitian half row into M complex points while loading
+    // c2r fold, then inverse rows of length M; the last stage scales and stores x[y][2n], x[y][2n+1] =
+    // z[y][n] to the global plane (its trailing barrier also protects the buffer from the next group)
+    pair_pass<false>(buf, rows_total, magic_rows, M, P, tw_w);
+    __syncthreads();
+    a.out_rows = reinterpret_cast<float2*>(p.out + plane0 * (int64_t)H * W);
     a.tw = tw_m;
     a.nbatch = rows_total;
     a.magic_batch = magic_rows;
-    run_axis<SRC_FOLD, false>(L.row, a, cur, tab_row, cur, oth);
-    // store: x[y][2n], x[y][2n+1] = z[y][n] * scale, coalesced float2, moments on the fly
-    float2* dst = reinterpret_cast<float2*>(p.out + plane0 * (int64_t)H * W);
-    for (int i = threadIdx.x; i < rows_total * M; i += blockDim.x) {
-      const int r = (int)__umulhi((unsigned)i, magic_m);
-      const float2 z = cur[r * P + (i - r * M)];
-      const float2 o = make_float2(z.x * L.scale, z.y * L.scale);
-      dst[i] = o;
-      ms += o.x + o.y;
-      mss += o.x * o.x + o.y * o.y;
-    }
-    __syncthreads();  // the next group's first stage overwrites a buffer this pass reads
+    run_axis_dif<SINK_GLOBAL, false>(L.row, a, tab_row);
   }
-  commit_moments(p.sums, p.sums_clear, ms, mss);
+  commit_moments(p.sums, p.sums_clear, a.ms, a.mss);
 }
 
 // Fewest stages over the radix set, ties broken by the smaller radix sum (8 x 8 before 16 x 4).
@@ -805,15 +881,15 @@ static bool make_axis_plan(int n, AxisPlan* plan) {
   int cur[kBatchedMaxStages], best[kBatchedMaxStages], best_depth = kBatchedMaxStages + 1, best_sum = 1 << 30;
   search_plan(n, 0, 0, cur, best, &best_depth, &best_sum);
   if (best_depth > kBatchedMaxStages) return false;  // another prime factor: the generic kernel handles it
-  int ns = 1;
+  int block = n;
   for (int f = 0; f < best_depth; ++f) {
     const int r = best[f];
     plan->radix[f] = r;
-    plan->ns[f] = ns;
+    plan->m[f] = block / r;
     plan->nb[f] = n / r;
     plan->tab_off[f] = plan->tab_size;
     plan->tab_size += n / r;
-    ns *= r;
+    block /= r;
   }
   plan->n_stages = best_depth;
   return true;
@@ -821,8 +897,9 @@ static bool make_axis_plan(int n, AxisPlan* plan) {
 
 static size_t batched_smem_bytes(int H, int W, int group, const AxisPlan& col, const AxisPlan& row) {
   const int M = W / 2, wh = M + 1, pitch = wh | 1;
-  return ((size_t)H + 2 * (size_t)M + 2 * (size_t)group * H * pitch) * sizeof(float2) +
-         (size_t)(col.tab_size + row.tab_size) * sizeof(ushort2);
+  size_t bytes = ((size_t)H + 2 * (size_t)M + (size_t)group * H * pitch) * sizeof(float2) +
+                 (size_t)(col.tab_size + row.tab_size) * sizeof(ushort2) + (size_t)(M + H) * sizeof(unsigned short);
+  return (bytes + 15) & ~(size_t)15;
 }
 
 // 0 = launched; -1 = not applicable (caller falls back to the generic kernel); > 0 = CUDA error
@@ -839,23 +916,30 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   L.plane_elems = p.H * L.pitch;
   L.scale = p.in_real != nullptr ? 0.5f * p.out_scale : p.out_scale;
   const DeviceInfo& di = device_info();
-  if (batched_smem_bytes(p.H, p.W, 1, L.col, L.row) > (size_t)di.max_smem_optin) return -1;
-  // planes per pass: enough butterflies to occupy the CTA in the leanest stage, without starving SMs
-  const int64_t items_col = (int64_t)(p.H / L.col.radix[0]) * L.wh, items_row = (int64_t)(M / L.row.radix[0]) * p.H;
-  const int64_t items_min = items_col < items_row ? items_col : items_row;
-  int64_t group = (kBatchedThreads + items_min - 1) / items_min;
-  const int64_t per_sm = (p.planes + di.sm_count - 1) / di.sm_count;
-  if (group > per_sm) group = per_sm;
-  if (const char* e = getenv("SONAR_SPECTRAL_GROUP")) group = atoi(e);  // experiment
-  while (group > 1 && batched_smem_bytes(p.H, p.W, (int)group, L.col, L.row) > (size_t)di.max_smem_optin) --group;
+  const size_t budget = (size_t)di.max_smem_optin;
+  if (batched_smem_bytes(p.H, p.W, 1, L.col, L.row) > budget) return -1;
+  auto ctas_that_fit = [&](int group) {  // by shared memory (1 KB per CTA is reserved by the runtime), at most 4
+    const size_t need = batched_smem_bytes(p.H, p.W, group, L.col, L.row) + 1024;
+    const size_t n = (budget + 1024) / need;
+    return (int)(n > 4 ? 4 : n);
+  };
+  // planes per pass: tiny planes are grouped until the leanest stage has ~256 butterflies, without starving SMs
+  int64_t items_min = INT64_MAX;
+  for (int f = 0; f < L.col.n_stages; ++f) items_min = std::min<int64_t>(items_min, (int64_t)L.col.nb[f] * L.wh);
+  for (int f = 0; f < L.row.n_stages; ++f) items_min = std::min<int64_t>(items_min, (int64_t)L.row.nb[f] * p.H);
+  int64_t group = (256 + items_min - 1) / items_min;
+  if (const char* e = getenv("SONAR_SPECTRAL_GROUP")) group = atoi(e);  // tuning experiments only
+  while (group > 1 && (ctas_that_fit((int)group) < 1 ||
+                       (p.planes + group - 1) / group < (int64_t)di.sm_count * ctas_that_fit((int)group)))
+    --group;
   if (group < 1) group = 1;
   L.group = (int)group;
-  // index arithmetic: 16-bit butterfly tables, 32-bit magic division exact for w * nbatch < 2^32
+  // index arithmetic: 16-bit slot tables, 32-bit magic division exact for w * d < 2^32
   const int64_t nbatch_max = group * (L.wh > p.H ? L.wh : p.H);
   const int64_t items_max = nbatch_max * ((p.H > M ? p.H : M) / 2);
   if (items_max * nbatch_max >= (1ll << 32) || group * L.plane_elems >= (1 << 24)) return -1;
   if (group * p.H * M * (int64_t)M >= (1ll << 32)) return -1;
-  L.magic_m = magic_of(M);
+  L.magic_row_nb = magic_of(L.row.nb[L.row.n_stages - 1]);
   L.magic_wh = magic_of(L.wh);
   L.magic_cols = magic_of(L.group * L.wh);
   L.magic_rows = magic_of(L.group * p.H);
@@ -863,14 +947,13 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   auto kernel = p.in_real != nullptr ? spectral_batched_kernel<true> : spectral_batched_kernel<false>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
+  // the register file holds 1024 threads at the kernel's 64 registers: split them over the CTAs that fit
+  int ctas_per_sm = ctas_that_fit(L.group);
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int threads = ctas_per_sm >= 4 ? 256 : ctas_per_sm == 3 ? 320 : kBatchedThreads;
+  if (const char* e = getenv("SONAR_SPECTRAL_THREADS")) threads = atoi(e);  // tuning experiments only
   int64_t grid = (p.planes + L.group - 1) / L.group;
-  int threads = kBatchedThreads, ctas_per_sm = 1;
-  if (const char* e = getenv("SONAR_SPECTRAL_THREADS")) {  // experiment
-    threads = atoi(e);
-    ctas_per_sm = kBatchedThreads / threads;
-    if ((smem + 1024) * ctas_per_sm > (size_t)di.max_smem_optin + 1024) ctas_per_sm = 1;
-  }
-  if (grid > di.sm_count * ctas_per_sm) grid = di.sm_count * ctas_per_sm;
+  if (grid > (int64_t)di.sm_count * ctas_per_sm) grid = (int64_t)di.sm_count * ctas_per_sm;
   kernel<<<(unsigned)grid, threads, smem, stream>>>(L);
   err = cudaGetLastError();
   return err == cudaSuccess ? 0 : (int)err;
