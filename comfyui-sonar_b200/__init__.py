@@ -8,6 +8,7 @@ Without ComfyUI (tests, bench) the compute modules are importable on their own:
     generators     noise generators         (reference py/noise_generation.py)
     noise_graph    chains / items           (reference py/noise.py)
     spectral_noise power-law spectral noise (reference py/nodes/powernoise.py)
+    freeu          FreeU-Extreme filter     (reference py/nodes/freeu_extreme.py)
     samplers       Sonar samplers           (reference py/sonar.py)
     wavelets, wcfg wavelet CFG              (reference py/wavelet_functions.py, py/wavelet_cfg.py)
     parallel       batch sharding over GPUs
@@ -19,7 +20,7 @@ from __future__ import annotations
 
 import sys
 
-from . import _native, generators, hostutil, kdiff, noise_graph, ops, parallel, rng, samplers, spectral_noise, wavelets, wcfg
+from . import _native, freeu, generators, hostutil, kdiff, noise_graph, ops, parallel, rng, samplers, spectral_noise, wavelets, wcfg
 
 __version__ = "0.1.0"
 
@@ -34,7 +35,7 @@ else:
     HAVE_COMFY = True
     from . import nodes
 
-    NODE_CLASS_MAPPINGS = nodes.NODE_CLASS_MAPPINGS
+    NODE_CLASS_MAPPINGS = nodes.NODE_CLASS_MAPPINGS | freeu.NODE_CLASS_MAPPINGS
     NODE_DISPLAY_NAME_MAPPINGS = nodes.NODE_DISPLAY_NAME_MAPPINGS
     samplers.add_samplers()
     _bi = sys.modules.get("_blepping_integrations", {})

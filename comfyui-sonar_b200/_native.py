@@ -242,6 +242,25 @@ class SonarWcfgFusedParams(ctypes.Structure):
     ]
 
 
+class SonarFreeuParams(ctypes.Structure):
+    _fields_ = [
+        ("x", c_void_p),
+        ("filtered", c_void_p),
+        ("hidden", c_void_p),
+        ("hidden_range", c_void_p),
+        ("batch", c_int64),
+        ("channels", c_int64),
+        ("hw", c_int64),
+        ("slice_offset", c_int64),
+        ("slice_channels", c_int64),
+        ("scale", c_float),
+        ("scale_minus_one", c_float),
+        ("blend", c_float),
+        ("blend_mode", c_int32),
+        ("use_blend", c_int32),
+    ]
+
+
 # name -> argtypes; every function returns int. Kept in one table so tests can check that the
 # library exports exactly what include/sonar_b200.h declares.
 SIGNATURES: dict[str, list] = {
@@ -299,10 +318,17 @@ SIGNATURES: dict[str, list] = {
     "sonar_dwt2_synthesis": [POINTER(SonarDwtSynthesisParams), c_void_p],
     "sonar_wcfg_fused_smem_bytes": [c_int, c_int, c_int, c_int, c_int],
     "sonar_wcfg_fused": [POINTER(SonarWcfgFusedParams), c_void_p],
+    "sonar_freeu_range_bytes": [c_int64],
+    "sonar_freeu_hidden_mean_f32": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    "sonar_freeu_apply_f32": [POINTER(SonarFreeuParams), c_void_p],
 }
 
 # functions whose return value is not an error code
-RESTYPES = {"sonar_spectral_scratch_bytes": c_int64, "sonar_wcfg_fused_smem_bytes": c_int64}
+RESTYPES = {
+    "sonar_spectral_scratch_bytes": c_int64,
+    "sonar_wcfg_fused_smem_bytes": c_int64,
+    "sonar_freeu_range_bytes": c_int64,
+}
 
 _LIB: ctypes.CDLL | None = None
 

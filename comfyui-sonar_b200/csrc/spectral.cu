@@ -16,7 +16,6 @@
 // ping-pong scratch. Rows are processed two at a time (real pair <-> one complex FFT).
 #include <algorithm>
 #include <cstdint>
-#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -873,7 +872,10 @@ static void search_plan(int rem, int depth, int sum, int* cur, int* best, int* b
   }
 }
 
-static bool make_axis_plan(int n, AxisPlan* plan) {
+// `ascending` puts the largest radix last. The row axis wants that: its block-length-R stage runs
+// butterfly-fastest against global memory, where butterfly j owns slots j * R .. j * R + R - 1, and a large
+// (ideally not power-of-two) R spreads adjacent lanes over the shared-memory banks (90x160: 37.9 -> 35.8 us).
+static bool make_axis_plan(int n, AxisPlan* plan, bool ascending = false) {
   plan->n = n;
   plan->n_stages = 0;
   plan->tab_size = 0;
@@ -883,7 +885,7 @@ static bool make_axis_plan(int n, AxisPlan* plan) {
   if (best_depth > kBatchedMaxStages) return false;  // another prime factor: the generic kernel handles it
   int block = n;
   for (int f = 0; f < best_depth; ++f) {
-    const int r = best[f];
+    const int r = ascending ? best[best_depth - 1 - f] : best[f];
     plan->radix[f] = r;
     plan->m[f] = block / r;
     plan->nb[f] = n / r;
@@ -909,7 +911,7 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   if (p.in_real != nullptr && (reinterpret_cast<uintptr_t>(p.in_real) & 7u) != 0) return -1;
   SpectralBatchedLaunch L;
   L.p = p;
-  if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row)) return -1;
+  if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row, /*ascending=*/true)) return -1;
   const int M = p.W / 2;
   L.wh = M + 1;
   L.pitch = L.wh | 1;
@@ -928,7 +930,6 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   for (int f = 0; f < L.col.n_stages; ++f) items_min = std::min<int64_t>(items_min, (int64_t)L.col.nb[f] * L.wh);
   for (int f = 0; f < L.row.n_stages; ++f) items_min = std::min<int64_t>(items_min, (int64_t)L.row.nb[f] * p.H);
   int64_t group = (256 + items_min - 1) / items_min;
-  if (const char* e = getenv("SONAR_SPECTRAL_GROUP")) group = atoi(e);  // tuning experiments only
   while (group > 1 && (ctas_that_fit((int)group) < 1 ||
                        (p.planes + group - 1) / group < (int64_t)di.sm_count * ctas_that_fit((int)group)))
     --group;
@@ -951,8 +952,8 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   int ctas_per_sm = ctas_that_fit(L.group);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   int threads = ctas_per_sm >= 4 ? 256 : ctas_per_sm == 3 ? 320 : kBatchedThreads;
-  if (const char* e = getenv("SONAR_SPECTRAL_THREADS")) threads = atoi(e);  // tuning experiments only
   int64_t grid = (p.planes + L.group - 1) / L.group;
+  // persistent CTAs: the per-CTA tables (twiddles, slot maps) are built once and reused for every group
   if (grid > (int64_t)di.sm_count * ctas_per_sm) grid = (int64_t)di.sm_count * ctas_per_sm;
   kernel<<<(unsigned)grid, threads, smem, stream>>>(L);
   err = cudaGetLastError();

@@ -671,6 +671,59 @@ def spectral_filter(
 
 
 # --------------------------------------------------------------------------------------------
+# FreeU-Extreme epilogue (reference py/nodes/freeu_extreme.py:183-227)
+# --------------------------------------------------------------------------------------------
+def freeu_hidden_mean(h: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """Channel mean of a (B, C, H, W) activation plus the per-item (min, max) partials freeu_apply needs."""
+    _f32(h, "h")
+    if h.ndim != 4:
+        raise ValueError("freeu_hidden_mean expects a (B, C, H, W) activation")
+    batch, channels, height, width = h.shape
+    hidden = torch.empty((batch, 1, height, width), device=h.device, dtype=torch.float32)
+    lib, stream = _prepare(h, hidden)
+    rng = torch.empty(max(int(lib.sonar_freeu_range_bytes(batch)), 8), device=h.device, dtype=torch.uint8)
+    _launch("sonar_freeu_hidden_mean_f32", lib.sonar_freeu_hidden_mean_f32, _ptr(h), _ptr(hidden), _ptr(rng), batch, channels,
+            height * width, stream)
+    return hidden, rng
+
+
+def freeu_apply(
+    x: torch.Tensor,
+    filtered: torch.Tensor | None,
+    hidden: tuple[torch.Tensor, torch.Tensor] | None,
+    *,
+    slice_offset: int,
+    slice_channels: int,
+    scale: float,
+    blend: float = 1.0,
+    blend_mode: str | None = None,
+) -> torch.Tensor:
+    """x[:, off:off+n] = blend(x[:, off:off+n], src * scale_map, blend) in place; src = `filtered` (dense
+    (B, n, H, W)) or the slice itself; scale_map = scale, or 1 + (scale - 1) * normalised hidden mean."""
+    _f32(x, "x")
+    if x.ndim != 4:
+        raise ValueError("freeu_apply expects a (B, C, H, W) activation")
+    batch, channels, height, width = x.shape
+    if filtered is not None:
+        _f32(filtered, "filtered")
+        if tuple(filtered.shape) != (batch, slice_channels, height, width):
+            raise ValueError(f"filtered slice has shape {tuple(filtered.shape)}, expected {(batch, slice_channels, height, width)}")
+    p = _native.SonarFreeuParams()
+    p.x = x.data_ptr()
+    p.filtered = 0 if filtered is None else filtered.data_ptr()
+    p.hidden = 0 if hidden is None else hidden[0].data_ptr()
+    p.hidden_range = 0 if hidden is None else hidden[1].data_ptr()
+    p.batch, p.channels, p.hw = batch, channels, height * width
+    p.slice_offset, p.slice_channels = int(slice_offset), int(slice_channels)
+    p.scale, p.scale_minus_one, p.blend = float(scale), float(scale - 1.0), float(blend)
+    p.use_blend = int(blend != 1.0)
+    p.blend_mode = BLEND_IDS[blend_mode] if p.use_blend else 0
+    lib, stream = _prepare(x, filtered, *(hidden or ()))
+    _launch("sonar_freeu_apply_f32", lib.sonar_freeu_apply_f32, ctypes.byref(p), stream)
+    return x
+
+
+# --------------------------------------------------------------------------------------------
 # DWT levels
 # --------------------------------------------------------------------------------------------
 DWT_MODE_IDS = {"symmetric": 0, "zero": 1, "reflect": 2, "periodic": 3}

@@ -435,6 +435,41 @@ int64_t sonar_wcfg_fused_smem_bytes(int H, int W, int filter_len, int levels, in
 int sonar_wcfg_fused(const SonarWcfgFusedParams* params_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * FreeU-Extreme epilogue around the spectral filter ("next" row).
+ * replaces: FreeUExtremeConfig.get_scale (hidden mean: channel mean of the activation, rescaled to
+ *           [0, 1] per batch item, -> 1 + (scale - 1) * mean)   py/nodes/freeu_extreme.py:183-194
+ *           FreeUExtremeConfig.apply (filtered slice * scale written back over the channel slice,
+ *           optionally through BLENDING_MODES)                  py/nodes/freeu_extreme.py:203-227
+ * The filter itself (ffilter, :10-29) is sonar_spectral_filter_f32 with in_real set.
+ * sonar_freeu_hidden_mean_f32: hidden (batch, hw) = mean over channels of h (batch, channels, hw);
+ * range_partial (sonar_freeu_range_bytes(batch) bytes) receives per-item (min, max) partials.
+ * sonar_freeu_apply_f32: x[b][slice_offset + c][p] = blend(x, src * sc, blend) in place, src =
+ * filtered[b][c][p] (dense slice) or x itself when filtered is NULL, sc = scale, or with `hidden`
+ * 1 + scale_minus_one * (hidden[b][p] - min_b) / (max_b - min_b). use_blend = 0 stores src * sc.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SonarFreeuParams {
+  float* x;
+  const float* filtered;
+  const float* hidden;       /* NULL: plain scalar scale */
+  const void* hidden_range;  /* from sonar_freeu_hidden_mean_f32, required with hidden */
+  int64_t batch;
+  int64_t channels;
+  int64_t hw;
+  int64_t slice_offset;
+  int64_t slice_channels;
+  float scale;
+  float scale_minus_one;
+  float blend;
+  int32_t blend_mode; /* SONAR_BLEND_* */
+  int32_t use_blend;
+} SonarFreeuParams;
+
+int64_t sonar_freeu_range_bytes(int64_t batch);
+int sonar_freeu_hidden_mean_f32(const float* h, float* hidden, void* range_partial, int64_t batch, int64_t channels,
+                                int64_t hw, void* stream);
+int sonar_freeu_apply_f32(const SonarFreeuParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Peer-memory exchange of the global scale_noise statistics (one node, NVLink 5 / NVSwitch).
  * replaces: the whole-batch reduction inside scale_noise when the batch is sharded over GPUs
  *                                                          py/utils.py:100-106

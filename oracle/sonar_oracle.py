@@ -396,6 +396,41 @@ def power_noise(draws, shape, filter_rfft, *, factor=1.0, normalized=True, spect
 # =============================================================================================
 # Reference-latent guidance (py/sonar.py:323-411)
 # =============================================================================================
+def freeu_ffilter(x: torch.Tensor, filter_kwargs: dict, normalization_factor: float = 1.0) -> torch.Tensor:
+    """ffilter py/nodes/freeu_extreme.py:10-29: irfft2(rfft2(x, ortho) * normalised PowerFilter, ortho)."""
+    filt = power_filter(x.shape, normalization_factor=normalization_factor, **filter_kwargs)
+    spec = torch.fft.rfft2(x.to(torch.float32), norm="ortho")
+    return torch.fft.irfft2(spec.mul_(filt), s=x.shape[-2:], norm="ortho").to(x.dtype)
+
+
+def freeu_scale(h: torch.Tensor, scale: float, hidden_mean: bool):
+    """FreeUExtremeConfig.get_scale py/nodes/freeu_extreme.py:183-194."""
+    if not hidden_mean:
+        return scale
+    hmean = h.mean(1).unsqueeze(1)
+    flat = hmean.view(hmean.shape[0], -1)
+    hmax, hmin = flat.max(dim=-1, keepdim=True)[0], flat.min(dim=-1, keepdim=True)[0]
+    hmean = (hmean - hmin.unsqueeze(2).unsqueeze(3)) / (hmax - hmin).unsqueeze(2).unsqueeze(3)
+    return 1.0 + (scale - 1.0) * hmean
+
+
+def freeu_apply(x: torch.Tensor, *, scale=1.0, hidden_mean=True, slice=1.0, slice_offset=0.0, blend=1.0,  # noqa: A002
+                blend_mode=None, filter=None, filter_norm=1.0) -> torch.Tensor:  # noqa: A002
+    """FreeUExtremeConfig.apply py/nodes/freeu_extreme.py:203-227 (+ apply_filter :229-246); returns a new tensor."""
+    x = x.clone()
+    features = x.shape[1]
+    sc = freeu_scale(x, scale, hidden_mean)
+    size, offs = int(features * slice), int(features * slice_offset)
+    part = x[:, offs : offs + size]
+    filtered = part if filter is None else freeu_ffilter(part, filter, filter_norm)
+    xslice = filtered * sc
+    if blend != 1.0:
+        modes = {"lerp": torch_lerp, "inject": lambda a, b, t: b * t + a, "subtract_b": lambda a, b, t: a - b * t}
+        xslice = modes[blend_mode](part, xslice, blend)
+    x[:, offs : offs + size] = xslice
+    return x
+
+
 def prepare_ref_latent(latent: torch.Tensor) -> torch.Tensor:
     """:335-341 -- per-plane standardisation of the reference latent."""
     avg = latent.mean(dim=(-2, -1), keepdim=True)

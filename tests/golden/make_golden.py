@@ -374,12 +374,94 @@ def gen_host_logic(ref) -> None:
     save("host_logic", out)
 
 
+def gen_freeu(ref) -> None:
+    """FreeU-Extreme: ffilter and FreeUExtremeConfig.apply on UNet-like activations,
+    and the patched-model handlers of FreeUExtremeNode."""
+    fx, pn = ref.py.nodes.freeu_extreme, ref.py.nodes.powernoise
+    out = {"ffilter": {}, "apply": {}, "node": {}}
+    torch.manual_seed(600)
+    for name, shape, fkw, norm in (
+        ("lowpass_16x20", (2, 6, 16, 20), {"alpha": 1.0}, 1.0),
+        ("band_32x32", (1, 8, 32, 32), {"alpha": 0.0, "min_freq": 0.1, "max_freq": 0.35}, 0.0),
+        ("odd_15x18", (1, 3, 15, 18), {"alpha": 0.5, "scale": 0.9}, 0.5),
+    ):
+        x = torch.randn(shape)
+        # (the reference's ffilter only works with a cache: without one `filter_rfft` is unbound, :12-15)
+        got = fx.ffilter(x.clone(), pn.PowerFilter(**fkw), normalization_factor=norm, cfg_idx=0, filter_cache={})
+        out["ffilter"][name] = {"x": x, "filter": fkw, "norm": norm, "out": got.clone()}
+    base = {"target": "backbone", "stage_1": True, "stage_2": True, "stage_3": True}
+    cases = {
+        "v2_full": {"scale": 1.3, "hidden_mean": True, "filter": {"alpha": 1.0}},
+        "plain_scale": {"scale": 0.8, "hidden_mean": False, "filter": None},
+        "slice_lerp": {"scale": 1.2, "hidden_mean": True, "slice": 0.5, "slice_offset": 0.25, "blend": 0.6,
+                       "blend_mode": "lerp", "filter": {"alpha": 0.5, "min_freq": 0.05}, "filter_norm": 1.0},
+        "slice_inject": {"scale": 1.1, "hidden_mean": False, "slice": 0.34, "slice_offset": 0.5, "blend": 0.25,
+                         "blend_mode": "inject", "filter": {"alpha": 1.0}, "filter_norm": 0.5},
+        "subtract": {"scale": 1.4, "hidden_mean": True, "blend": 0.5, "blend_mode": "subtract_b", "filter": None},
+    }  # fmt: skip
+    for i, (name, kw) in enumerate(cases.items()):
+        torch.manual_seed(610 + i)
+        x = torch.randn(2, 12, 16, 24)
+        kw = dict(kw)
+        fkw = kw.pop("filter")
+        cfg = fx.FreeUExtremeConfig(**base, **kw, sonar_power_filter_opt=None if fkw is None else pn.PowerFilter(**fkw))
+        got = cfg.apply(0, x.clone(), {})
+        out["apply"][name] = {"x": x, "config": kw, "filter": fkw, "out": got.clone()}
+
+    # the node: a stand-in model that records the patches; stage lookup by channel count, percent window
+    class _MS:
+        @staticmethod
+        def timestep(sigma):
+            return sigma * 100.0
+
+    class _Model:
+        def __init__(self):
+            self.patches = {}
+            self.model = type("M", (), {"model_config": type("C", (), {"unet_config": {"model_channels": 4}})()})()
+
+        def clone(self):
+            return self
+
+        def get_model_object(self, _name):
+            return _MS()
+
+        def set_model_input_block_patch(self, fn):
+            self.patches["input"] = fn
+
+        def set_model_patch(self, fn, name):
+            self.patches[name] = fn
+
+        def set_model_output_block_patch(self, fn):
+            self.patches["output"] = fn
+
+    second = fx.FreeUExtremeConfig(
+        target="skip", stage_2=True, start=0.0, end=1.0, scale=0.7, hidden_mean=False, final=True,
+        sonar_power_filter_opt=pn.PowerFilter(alpha=1.0), filter_norm=1.0,
+    )
+    first = fx.FreeUExtremeConfig(
+        target="backbone", stage_1=True, stage_2=True, start=0.2, end=0.9, scale=1.25, hidden_mean=True, final=False,
+        sonar_power_filter_opt=pn.PowerFilter(alpha=0.5), filter_norm=1.0, frux_config_opt=second,
+    )
+    (model,) = fx.FreeUExtremeNode.go(_Model(), False, input_config=first, middle_config=first, output_config=first)
+    torch.manual_seed(630)
+    h16, h8, hsp8, h5 = torch.randn(1, 16, 8, 8), torch.randn(2, 8, 12, 10), torch.randn(2, 8, 12, 10), torch.randn(1, 5, 8, 8)
+    rec = {"inputs": {"h16": h16, "h8": h8, "hsp8": hsp8, "h5": h5}, "calls": []}
+    for sigma in (5.0, 0.5, 9.5):  # pct = 1 - sigma / 9.99: inside, inside, outside the [0.2, 0.9] window
+        topt = {"sigmas": torch.tensor([sigma, sigma])}
+        a = model.patches["input"](h16.clone(), topt)
+        b = model.patches["middle_block_patch"](h5.clone(), topt)
+        c, d = model.patches["output"](h8.clone(), hsp8.clone(), topt)
+        rec["calls"].append({"sigma": sigma, "input": a.clone(), "middle": b.clone(), "out_h": c.clone(), "out_hsp": d.clone()})
+    out["node"] = rec
+    save("freeu", out)
+
+
 IN_SCOPE_NODES = (
     "SamplerSonarEuler", "SamplerSonarEulerA", "SamplerSonarDPMPPSDE", "SonarGuidanceConfig", "SonarCustomNoise",
     "SonarCustomNoiseAdv", "SonarPowerNoise", "SonarPowerFilterNoise", "SonarPowerFilter", "SonarAdvancedPyramidNoise",
     "SonarAdvanced1fNoise", "SonarAdvancedPowerLawNoise", "SonarCompositeNoise", "SonarScheduledNoise",
     "SonarBlendedNoise", "SonarRepeatedNoise", "SonarCustomNoiseParameters", "SONAR_CUSTOM_NOISE to NOISE",
-    "SamplerConfigOverride", "SonarWaveletCFG", "NoisyLatentLike",
+    "SamplerConfigOverride", "SonarWaveletCFG", "NoisyLatentLike", "FreeUExtremeConfig", "FreeUExtreme",
 )  # fmt: skip
 
 
@@ -424,6 +506,7 @@ def main() -> None:
     gen_samplers(ref)
     gen_guidance(ref)
     gen_host_logic(ref)
+    gen_freeu(ref)
     gen_node_schemas(ref)
 
 
