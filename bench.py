@@ -86,6 +86,12 @@ class ClockSampler:
             )  # fmt: skip
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi spends ~0.1-1 s initialising NVML (and holds driver locks while it does): wait for its
+            # first sample so that start-up does not land inside the first timed runs; the 100 ms polling that
+            # follows is what samples the timed region
+            deadline = time.perf_counter() + 5.0
+            while not self.lines and time.perf_counter() < deadline and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
@@ -349,7 +355,17 @@ def run_b200_arm(args) -> None:
 
     # ---------------- device-resident throughput ----------------
     warm_model = StepTimer(dev, timed=False)
+    def align_ranks():
+        """Ranks start a run together, so that the one exchange of a run measures NVLink and not host drift: a
+        host barrier, then a device-side rendezvous (peer mailboxes) behind which every host keeps enqueueing --
+        the GPUs leave it within NVLink latency of each other."""
+        barrier()
+        if world > 1:
+            with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
+                sb.parallel.device_barrier()
+
     for _ in range(max(3, args.warmup)):
+        align_ranks()
         one_run(warm_model, x0)
     barrier()
     launches0 = sb.ops.LAUNCH_COUNT
@@ -360,7 +376,7 @@ def run_b200_arm(args) -> None:
         t_wall = time.perf_counter()
         for _ in range(args.steps):
             if world > 1:
-                barrier()  # ranks start each run together: the one exchange of a run measures NVLink, not host drift
+                align_ranks()
             timer = StepTimer(dev)
             one_run(timer, x0)
             timer.close()

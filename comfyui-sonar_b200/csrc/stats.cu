@@ -268,7 +268,9 @@ int sonar_philox_normal_moments_batch(const uint64_t* offsets_host, int n_draws,
   const int64_t T = s.threads, end = begin + count;
   const int64_t k_lo = (begin / T) / 4, k_hi = ((end - 1) / T) / 4;
   SONAR_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * sizeof(double) * (size_t)n_draws, (cudaStream_t)stream));
-  const int gx = streaming_grid(T, kBlock, 1);
+  // 8 Philox calls per thread: one block reduction + two fp64 atomics per 2048 calls instead of per 256 (a
+  // 29-draw look-ahead table over 524,288 normals each: 100 -> 70 us)
+  const int gx = streaming_grid(T, kBlock * 8, 1);
   for (int first = 0; first < n_draws; first += kMomentsBatch) {
     const int m = n_draws - first < kMomentsBatch ? n_draws - first : kMomentsBatch;
     OffsetBatch offs;

@@ -212,6 +212,24 @@ def allreduce_table(table: torch.Tensor) -> None:
     ctx.collectives += 1
 
 
+_BARRIER_TABLE: dict = {}
+
+
+def device_barrier() -> bool:
+    """Device-side rendezvous of the ranks of the active sharding context: every GPU's stream stalls until
+    all ranks have reached this point (one peer-mailbox exchange over NVLink, no host synchronisation, so
+    each host keeps enqueueing behind it). Aligns the GPUs to NVLink latency rather than to the skew of the
+    host threads leaving an NCCL barrier. Returns False (and does nothing) without peer memory."""
+    ctx = _ACTIVE
+    if ctx is None or ctx.world_size == 1 or ctx.peers is None:
+        return False
+    dev = torch.cuda.current_device()
+    table = _BARRIER_TABLE.get(dev)
+    if table is None:
+        table = _BARRIER_TABLE[dev] = torch.zeros(1, device=torch.device("cuda", dev), dtype=torch.float64)
+    return ctx.peers.allreduce_table(table)
+
+
 def global_numel(local_numel: int) -> int:
     """Element count of the un-sharded tensor behind a local tensor of `local_numel` elements."""
     ctx = _ACTIVE

@@ -405,27 +405,32 @@ class SonarBase:
             # costs ~0.2 us; the general path invalidates this by resetting _stock_static)
             start, end, always, hist_on = self._gate
             self._stock_window = (start, end, hist_on and always, hist_on)
-            p.n, p.kind, p.hist_in_div, p.peer_world, p.noise_begin, p.noise_numel_total, p.noise_count = n, kind, 1.0, 0, 0, n, n
+            # batch-sharded runs regenerate this rank's slice [begin, begin + n) of the GLOBAL draw of `total` values
+            ctx = parallel.active()
+            total, begin = parallel.global_draw_geometry(x.shape) if ctx is not None and ctx.world_size > 1 else (n, 0)
+            self._stock_total = total
+            p.n, p.kind, p.hist_in_div, p.peer_world, p.noise_begin, p.noise_numel_total, p.noise_count = n, kind, 1.0, 0, begin, total, n
             spec = self._stock_noise
             if spec is not None:
                 p.noise_factor = spec[0]
             self._stock_static = (n, kind)
         if noise_scale is not None:
             spec = self._stock_noise
-            if parallel.active() is not None or spec is None:
+            if spec is None:
                 return None
             gen = self._stock_gen
             offset = gen.get_offset()
+            total = self._stock_total
             if spec[1]:  # normalised: statistics from the look-ahead table
                 la = self._lookahead
                 idx = None if la is None else la["index"].get(offset)
-                if idx is None or la["key"][0] != gen.initial_seed() or la["key"][2] != n:
+                if idx is None or la["key"][0] != gen.initial_seed() or la["key"][2] != total or la["key"][4] != n:
                     return None  # first draw of the run, or somebody else advanced the generator: re-plan
                 p.noise_kind, p.noise_sums, p.noise_decision = ops.NOISE_PHILOX_NORMALIZED, la["ptr"] + 16 * idx, la["dec_ptr"] + 16 * idx
                 grid, inc = la["key"][1], la["inc"]
             else:
                 p.noise_kind = ops.NOISE_PHILOX
-                grid, inc = ops.philox_policy_cached(self._stock_dev, n)
+                grid, inc = ops.philox_policy_cached(self._stock_dev, total)
             gen.set_offset(offset + inc)
             self.noise_draws_left -= 1
             p.noise_scale, p.philox_seed, p.philox_offset, p.philox_grid_blocks = noise_scale, gen.initial_seed(), offset, grid

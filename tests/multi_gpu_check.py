@@ -47,6 +47,7 @@ def main() -> None:
     for name, (sampler, kw) in jobs.items():
         want = run(sampler, x_full, **kw)
         with sb.parallel.sharded(batch) as ctx:
+            assert sb.parallel.device_barrier() == (ctx.peers is not None)  # device-side rendezvous, no host sync
             mine = run(sampler, sb.parallel.shard(x_full), **kw)
             got = sb.parallel.gather(mine)
             transport = "peer mailboxes" if ctx.peers is not None else "nccl"
