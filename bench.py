@@ -373,6 +373,9 @@ def run_b200_arm(args) -> None:
     gc.collect()
     gc.disable()  # a collection pause between two launches would show up as device idle time
     with ClockSampler(local_rank, enabled=rank == 0) as clocks:
+        align_ranks()
+        one_run(warm_model, x0)  # one more untimed run now that the clock poller is up (rank 0 waited for it)
+        barrier()
         t_wall = time.perf_counter()
         for _ in range(args.steps):
             if world > 1:

@@ -316,6 +316,7 @@ SIGNATURES: dict[str, list] = {
     "sonar_dwt_coeff_len": [c_int, c_int],
     "sonar_dwt2_analysis": [POINTER(SonarDwtAnalysisParams), c_void_p],
     "sonar_dwt2_synthesis": [POINTER(SonarDwtSynthesisParams), c_void_p],
+    "sonar_dwt2_synthesis_per": [POINTER(SonarDwtSynthesisParams), c_void_p],
     "sonar_wcfg_fused_smem_bytes": [c_int, c_int, c_int, c_int, c_int],
     "sonar_wcfg_fused": [POINTER(SonarWcfgFusedParams), c_void_p],
     "sonar_freeu_range_bytes": [c_int64],

@@ -24,6 +24,12 @@ __device__ __forceinline__ int extend_index_wrapped(int i, int n, int mode) {
       int m = i % n;
       return m < 0 ? m + n : m;
     }
+    case SONAR_DWT_MODE_PERIODIZATION: {  // period n rounded up to even, the extra sample repeats the last one
+      const int period = n + (n & 1);
+      int m = i % period;
+      if (m < 0) m += period;
+      return m < n ? m : n - 1;
+    }
     case SONAR_DWT_MODE_REFLECT: {  // whole-sample symmetry about 0 and n-1
       if (n == 1) return 0;
       const int period = 2 * (n - 1);
@@ -45,6 +51,7 @@ __device__ __forceinline__ int extend_index(int i, int n, int mode) {
   // One reflection / wrap covers every tap unless the filter is longer than the signal.
   if ((unsigned)i < (unsigned)n) return i;
   if (mode == SONAR_DWT_MODE_ZERO) return -1;
+  if (mode == SONAR_DWT_MODE_PERIODIZATION) return extend_index_wrapped(i, n, mode);
   int m;
   if (mode == SONAR_DWT_MODE_PERIODIC)
     m = i < 0 ? i + n : i - n;
@@ -351,6 +358,47 @@ dwt2_synthesis_kernel(SynthSet<T> a, SynthSet<T> b, int n_sets, int64_t planes, 
         out_t[(plane * out_h + iy) * (int64_t)out_w + ix] = vals[q];
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Periodization (non-expansive) synthesis level: N = 2h outputs per axis,
+//   out[i] = sum over taps t == u (mod 2) of c[((u - t) / 2) mod h] * g[t],  u = (i + L/2 - 1) mod N
+// (pytorch_wavelets sfb1d, mode "periodization": transposed convolution, the L-2 tail wrapped onto the
+// head, rolled by 1 - L/2). One thread per output pixel; used by the wavelet-filtered noise type
+// (py/noise_generation.py:1908-2032), not by the wavelet-CFG hot path.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+dwt2_per_synthesis_kernel(SynthSet<T> c, int64_t planes, int h, int w, T* __restrict__ out, Filters<T> f) {
+  const int L = f.L, oh = 2 * h, ow = 2 * w;
+  const int64_t total = planes * (int64_t)oh * ow, hw = (int64_t)h * w;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(idx % ow), iy = (int)((idx / ow) % oh);
+    const int64_t plane = idx / ((int64_t)ow * oh);
+    const int uy = (iy + L / 2 - 1) % oh, ux = (ix + L / 2 - 1) % ow;
+    const T* pll = c.ll + plane * (int64_t)c.ll_stride_h * c.ll_stride_w;
+    const T* phi = c.hi + plane * 3 * hw;
+    T acc = 0;
+    for (int ty = uy & 1; ty < L; ty += 2) {
+      int ky = ((uy - ty) / 2) % h;
+      if (ky < 0) ky += h;
+      T row_lo = 0, row_hi = 0;  // combined along W for the low-along-H and the high-along-H bands
+      for (int tx = ux & 1; tx < L; tx += 2) {
+        int kx = ((ux - tx) / 2) % w;
+        if (kx < 0) kx += w;
+        const int64_t o = (int64_t)ky * w + kx;
+        const T v_ll = pll[(int64_t)ky * c.ll_stride_w + kx] * c.s_ll;
+        const T v_lh = phi[o] * c.s_lh;           // high along H, low along W
+        const T v_hl = phi[hw + o] * c.s_hl;      // low along H, high along W
+        const T v_hh = phi[2 * hw + o] * c.s_hh;
+        row_lo += f.s_lo[tx] * v_ll + f.s_hi[tx] * v_hl;
+        row_hi += f.s_lo[tx] * v_lh + f.s_hi[tx] * v_hh;
+      }
+      acc += f.s_lo[ty] * row_lo + f.s_hi[ty] * row_hi;
+    }
+    out[idx] = acc;
   }
 }
 
@@ -674,7 +722,9 @@ int sonar_dwt2_analysis(const SonarDwtAnalysisParams* params, void* stream) {
   if (p.planes <= 0) return 0;
   if (p.filters.length < 2 || p.filters.length > SONAR_DWT_MAX_TAPS || (p.filters.length & 1)) return (int)cudaErrorInvalidValue;
   if (p.in_a == nullptr || p.ll == nullptr || p.hi == nullptr || p.H <= 0 || p.W <= 0) return (int)cudaErrorInvalidValue;
-  if (p.h != sonar_dwt_coeff_len(p.H, p.filters.length) || p.w != sonar_dwt_coeff_len(p.W, p.filters.length))
+  const bool per = p.mode == SONAR_DWT_MODE_PERIODIZATION;  // non-expansive: ceil(n / 2) coefficients
+  if (p.h != (per ? (p.H + 1) / 2 : sonar_dwt_coeff_len(p.H, p.filters.length)) ||
+      p.w != (per ? (p.W + 1) / 2 : sonar_dwt_coeff_len(p.W, p.filters.length)))
     return (int)cudaErrorInvalidValue;
   return p.use_f64 ? launch_analysis<double>(p, (cudaStream_t)stream) : launch_analysis<float>(p, (cudaStream_t)stream);
 }
@@ -692,7 +742,7 @@ int sonar_wcfg_fused(const SonarWcfgFusedParams* params, void* stream) {
   if (params == nullptr) return (int)cudaErrorInvalidValue;
   const SonarWcfgFusedParams& p = *params;
   if (p.planes <= 0) return 0;
-  if (p.in_a == nullptr || p.out == nullptr) return (int)cudaErrorInvalidValue;
+  if (p.in_a == nullptr || p.out == nullptr || p.mode == SONAR_DWT_MODE_PERIODIZATION) return (int)cudaErrorInvalidValue;
   if (sonar_wcfg_fused_smem_bytes(p.H, p.W, p.filters.length, p.levels, p.use_f64) <= 0) return (int)cudaErrorInvalidValue;
   WcfgGeom g;
   wcfg_geometry(p.H, p.W, p.filters.length, p.levels, &g);
@@ -713,6 +763,32 @@ int sonar_dwt2_synthesis(const SonarDwtSynthesisParams* params, void* stream) {
     if (p.ll[s] == nullptr || p.hi[s] == nullptr || p.ll_rows[s] < p.h || p.ll_cols[s] < p.w) return (int)cudaErrorInvalidValue;
   return p.use_f64 ? launch_synthesis<double>(p, (cudaStream_t)stream)
                    : launch_synthesis<float>(p, (cudaStream_t)stream);
+}
+
+int sonar_dwt2_synthesis_per(const SonarDwtSynthesisParams* params, void* stream) {
+  using namespace sonar;
+  if (params == nullptr) return (int)cudaErrorInvalidValue;
+  const SonarDwtSynthesisParams& p = *params;
+  if (p.planes <= 0 || p.h <= 0 || p.w <= 0) return 0;
+  if (p.n_sets != 1 || p.out == nullptr || p.out_f32 != nullptr || p.ll[0] == nullptr || p.hi[0] == nullptr)
+    return (int)cudaErrorInvalidValue;
+  const int L = p.filters.length;
+  if (L < 2 || (L & 1) || L > SONAR_DWT_MAX_TAPS || p.ll_rows[0] < p.h || p.ll_cols[0] < p.w) return (int)cudaErrorInvalidValue;
+  const int64_t total = p.planes * (int64_t)(2 * p.h) * (2 * p.w);
+  const int grid = streaming_grid(total, kBlock, 4);
+  if (p.use_f64) {
+    SynthSet<double> c{(const double*)p.ll[0], (const double*)p.hi[0], p.ll_rows[0], p.ll_cols[0],
+                       p.scales[0][0], p.scales[0][1], p.scales[0][2], p.scales[0][3]};
+    dwt2_per_synthesis_kernel<double><<<grid, kBlock, 0, (cudaStream_t)stream>>>(c, p.planes, p.h, p.w, (double*)p.out,
+                                                                                make_filters<double>(&p.filters));
+  } else {
+    SynthSet<float> c{(const float*)p.ll[0], (const float*)p.hi[0], p.ll_rows[0], p.ll_cols[0],
+                      (float)p.scales[0][0], (float)p.scales[0][1], (float)p.scales[0][2], (float)p.scales[0][3]};
+    dwt2_per_synthesis_kernel<float><<<grid, kBlock, 0, (cudaStream_t)stream>>>(c, p.planes, p.h, p.w, (float*)p.out,
+                                                                               make_filters<float>(&p.filters));
+  }
+  SONAR_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // extern "C"

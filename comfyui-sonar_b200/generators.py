@@ -625,6 +625,101 @@ class MixedNoiseGenerator(NoiseGenerator):
         return total.to(self.dtype)
 
 
+class WaveletFilteredNoiseGenerator(FramesToChannelsNoiseGenerator):
+    """Noise filtered in the wavelet domain (:1908-2032): DWT of the source noise (optionally a second
+    source for the detail bands, blended band-wise), per-band scaling, IDWT, crop. Defaults: haar, 3 levels,
+    the non-expansive "periodization" mode. The final `wavelet_scaling` rides on the synthesis kernels' loads;
+    `two_step_inverse` is accepted (the transform is linear: inverting the two halves separately and adding
+    them is the one-pass inverse)."""
+
+    name = "waveletfilter"
+    MIN_DIMS = 4
+    MAX_DIMS = 5
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        from .wavelets import Wavelet  # (wavelets imports ops only; late import keeps module init order simple)
+
+        inv_kwargs = {k: self.options[k] for k in ("inv_mode", "inv_biort", "inv_qshift", "inv_wave") if k in self.options}
+        self.wavelet = Wavelet(
+            wave=self.wave, level=self.level, mode=self.mode, use_1d_dwt=self.use_1d_dwt, use_dtcwt=self.use_dtcwt,
+            biort=self.biort, qshift=self.qshift, device=self.gen_device, dtype=torch.float32, **inv_kwargs,
+        )  # fmt: skip
+
+    @classmethod
+    def ng_params(cls):
+        return super().ng_params() | {
+            "mode": "periodization",
+            "level": 3,
+            "wave": "haar",
+            "use_1d_dwt": False,
+            "use_dtcwt": False,
+            "qshift": "qshift_a",
+            "biort": "near_sym_a",
+            "yl_scale": 1.0,
+            "yh_scales": 1.0,
+            "two_step_inverse": False,
+            "preblend_yl_scale_low": None,
+            "preblend_yh_scales_low": None,
+            "preblend_yl_scale_high": None,
+            "preblend_yh_scales_high": None,
+            "yl_blend_function": torch.lerp,
+            "yh_blend_function": torch.lerp,
+            "yl_blend_high": 0.0,
+            "yh_blend_high": 1.0,
+            "noise_sampler": None,
+            "noise_sampler_high": None,
+        }
+
+    def _fix_shape(self, noise, adjusted_shape):
+        if noise.shape != adjusted_shape:
+            noise = noise.reshape(*adjusted_shape)
+        if self.frames:
+            noise = noise.reshape(self.batch, self.channels * self.frames, self.height, self.width)
+        return noise
+
+    @staticmethod
+    def _blend_kernel(fn) -> Callable:
+        """torch.lerp (the reference default) and BLENDING_MODES names map onto the blend kernel."""
+        if fn is torch.lerp:
+            return hostutil.BLENDING_MODES["lerp"]
+        if isinstance(fn, str):
+            return hostutil.BLENDING_MODES[fn]
+        return fn
+
+    def generate(self, *args):
+        from .wavelets import wavelet_scaling
+
+        adjusted_shape = self.get_adjusted_shape()
+        noise = self.rand_like() if self.noise_sampler is None else self.noise_sampler(*args)
+        noise_high = None if self.noise_sampler_high is None else self._fix_shape(self.noise_sampler_high(*args), adjusted_shape)
+        noise = self._fix_shape(noise, adjusted_shape)
+        if noise.dtype != torch.float32:
+            noise = noise.float()
+        yl, yh = self.wavelet.forward(noise.contiguous())
+        if noise_high is not None:
+            yl_high, yh_high = self.wavelet.forward(noise_high.float().contiguous())
+            if self.preblend_yl_scale_high is not None or self.preblend_yh_scales_high is not None:
+                yl_high, yh_high = wavelet_scaling(
+                    yl_high, yh_high, fallback(self.preblend_yl_scale_high, 1.0), fallback(self.preblend_yh_scales_high, 1.0),
+                )
+            if self.preblend_yl_scale_low is not None or self.preblend_yh_scales_low is not None:
+                yl, yh = wavelet_scaling(
+                    yl, yh, fallback(self.preblend_yl_scale_low, 1.0), fallback(self.preblend_yh_scales_low, 1.0),
+                )
+            yl_blend, yh_blend = self._blend_kernel(self.yl_blend_function), self._blend_kernel(self.yh_blend_function)
+            yl = yl_blend(yl.contiguous(), yl_high.contiguous(), self.yl_blend_high)
+            yh = tuple(yh_blend(a.contiguous(), b.contiguous(), self.yh_blend_high) for a, b in zip(yh, yh_high))
+            del noise_high, yl_high, yh_high
+        result = self.wavelet.inverse(
+            yl, yh, two_step_inverse=self.two_step_inverse, yl_scale=self.yl_scale, yh_scales=self.yh_scales,
+        )
+        result = self.fix_output_frames(result)
+        if result.shape != (target := self.fix_output_frames(noise).shape):
+            result = result[tuple(slice(0, dl) for dl in target)]
+        return result.contiguous().to(self.dtype)
+
+
 def _unsupported(name: str, why: str) -> Callable:
     class _Unsupported(NoiseGenerator):
         def __init__(self, *_a, **_k):
@@ -643,7 +738,6 @@ PowerOldNoiseGenerator = _unsupported("power_old", "documented as wrong upstream
 PinkOldNoiseGenerator = _unsupported("pink_old", "documented as wrong upstream")
 VoronoiNoiseGenerator = _unsupported("voronoi", "not on the configured hot path")
 CollatzNoiseGenerator = _unsupported("collatz", "not on the configured hot path")
-WaveletFilteredNoiseGenerator = _unsupported("wavelet_filtered", "ranked 'next' in SURVEY.md section 8f")
 ScatternetFilteredNoiseGenerator = _unsupported("scatternet_filtered", "needs pytorch_wavelets ScatLayer")
 
 

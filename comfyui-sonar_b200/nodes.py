@@ -364,6 +364,52 @@ _PARAM_DTYPES = (
 )  # fmt: skip
 
 
+WAVELET_FILTER_YAML = """# YAML or JSON. Every key is optional; the values below are the defaults.
+wave: haar              # haar or db1..db12
+level: 3                # decomposition levels
+mode: periodization     # padding: periodization, symmetric, zero, reflect, periodic
+use_dtcwt: false        # DTCWT is not built in sonar_b200 (2-D DWT only)
+biort: near_sym_a       # DTCWT only
+qshift: qshift_a        # DTCWT only
+two_step_inverse: false # invert the low and high parts separately and add them (same result: the transform is linear)
+# inv_wave / inv_mode / inv_biort / inv_qshift override the settings of the inverse transform
+yl_scale: 1.0           # scale of the approximation (low-frequency) band
+yh_scales: 1.0          # scale(s) of the detail bands: a number, a list per level, or a list of [h, v, d] lists
+"""
+
+
+class SonarWaveletFilteredNoiseNode(SonarCustomNoiseNodeBase):
+    DESCRIPTION = "Custom noise type that allows filtering another custom noise source with wavelets."
+    REQUIRED = {  # noqa: RUF012
+        "normalize_noise": f_bool(False, "Controls whether the noise source is normalized before wavelet filtering occurs."),
+        "normalize": f_choice(TRISTATE, "default", "Controls whether the generated noise is normalized to 1.0 strength."),
+    }
+    OPTIONAL = {  # noqa: RUF012
+        "custom_noise": f_noise("Optional: Custom noise input. If unconnected will default to Gaussian noise."),
+        "custom_noise_high": f_noise(
+            "Optional: noise for the high-frequency side of the wavelet. If unconnected the same generator as custom_noise is used.",
+        ),
+        "yaml_parameters": ("STRING", YAML_OPTS | {"placeholder": WAVELET_FILTER_YAML}),
+    }
+
+    @classmethod
+    def get_item_class(cls):
+        return noise.WaveletFilteredNoise
+
+    def go(self, *, factor, rescale, normalize, normalize_noise, custom_noise=None, custom_noise_high=None,
+           yaml_parameters=None, sonar_custom_noise_opt=None):  # fmt: skip
+        return super().go(
+            factor,
+            rescale=rescale,
+            sonar_custom_noise_opt=sonar_custom_noise_opt,
+            normalize=self.get_normalize(normalize),
+            normalize_noise=normalize_noise,
+            noise=custom_noise,
+            noise_high=custom_noise_high if custom_noise_high is not None else custom_noise,
+            yaml_parameters=yaml_parameters,
+        )
+
+
 class SonarCustomNoiseParametersNode(SonarCustomNoiseNodeBase):
     DESCRIPTION = "Allows overriding shape / dtype / RNG parameters for the attached custom noise (e.g. video latents)."
     WITH_RESCALE = WITH_CHAIN = False
@@ -1058,6 +1104,7 @@ NODE_CLASS_MAPPINGS = {
     "SonarCompositeNoise": SonarCompositeNoiseNode,
     "SonarBlendedNoise": SonarBlendedNoiseNode,
     "SonarCustomNoiseParameters": SonarCustomNoiseParametersNode,
+    "SonarWaveletFilteredNoise": SonarWaveletFilteredNoiseNode,
     "SonarPowerNoise": SonarPowerNoiseNode,
     "SonarPowerFilterNoise": SonarPowerFilterNoiseNode,
     "SonarPowerFilter": SonarPowerFilterNode,

@@ -427,6 +427,44 @@ class RepeatedNoise(_ChildHolder):
         return noise_sampler
 
 
+class WaveletFilteredNoise(_ChildHolder):
+    """SonarWaveletFilteredNoise: another chain's noise filtered in the wavelet domain (:1521-1590). Extra
+    generator options (wave, level, mode, yl_scale, yh_scales, ...) arrive as `ns_kwargs` from the YAML."""
+
+    child_keys = ("noise", "noise_high")
+
+    def make_noise_sampler(self, x, sigma_min=None, sigma_max=None, *args, normalized=True, **kwargs):
+        factor = self.factor
+        normalize = self.get_normalize("normalize", normalized)
+        internal_ns = internal_ns_high = None
+        if getattr(self, "noise", None) is not None:
+            internal_ns = self.noise.make_noise_sampler(
+                x, *args, sigma_min=sigma_min, sigma_max=sigma_max, normalized=self.normalize_noise, **kwargs,
+            )
+        if getattr(self, "noise_high", None) is not None:
+            internal_ns_high = self.noise_high.make_noise_sampler(
+                x, *args, sigma_min=sigma_min, sigma_max=sigma_max, normalized=self.normalize_noise, **kwargs,
+            )
+        ns_kwargs = dict(getattr(self, "ns_kwargs", {}))
+        yl_blend_function = ns_kwargs.pop("yl_blend_function", torch.lerp)
+        yh_blend_function = ns_kwargs.pop("yh_blend_function", torch.lerp)
+        if isinstance(yl_blend_function, str):
+            yl_blend_function = hostutil.BLENDING_MODES[yl_blend_function]
+        if isinstance(yh_blend_function, str):
+            yh_blend_function = hostutil.BLENDING_MODES[yh_blend_function]
+        kwargs |= ns_kwargs
+        ns = WaveletFilteredNoiseGenerator(  # noqa: F405
+            x, *args, sigma_min=sigma_min, sigma_max=sigma_max, normalized=False, noise_sampler=internal_ns,
+            noise_sampler_high=internal_ns_high, yl_blend_function=yl_blend_function, yh_blend_function=yh_blend_function,
+            **kwargs,
+        )  # fmt: skip
+
+        def noise_sampler(sigma, sigma_next):
+            return scale_noise(ns(sigma, sigma_next), factor, normalized=normalize)
+
+        return noise_sampler
+
+
 class BlendedNoise(_ChildHolder):
     """blend_function(noise_1, noise_2, t); t a constant or a per-element mask noise normalised to
     [0,1] (:1302-1407)."""
@@ -559,7 +597,7 @@ def _out_of_scope_item(name: str) -> type:
 
 for _name in (
     "GuidedNoise", "ModulatedNoise", "RandomNoise", "ChannelNoise", "RippleFilteredNoise", "NormalizeToScaleNoise",
-    "ResizedNoise", "WaveletFilteredNoise", "ScatternetFilteredNoise", "LatentOperationFilteredNoise",
+    "ResizedNoise", "ScatternetFilteredNoise", "LatentOperationFilteredNoise",
     "BlendFilterNoise", "QuantileFilteredNoise", "PerDimNoise", "ShuffledNoise", "PatternBreakNoise", "BlehOpsNoise",
     "AdvancedDistroNoise", "AdvancedCollatzNoise", "AdvancedWaveletNoise", "AdvancedVoronoiNoise",
 ):  # fmt: skip

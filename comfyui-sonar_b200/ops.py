@@ -726,7 +726,8 @@ def freeu_apply(
 # --------------------------------------------------------------------------------------------
 # DWT levels
 # --------------------------------------------------------------------------------------------
-DWT_MODE_IDS = {"symmetric": 0, "zero": 1, "reflect": 2, "periodic": 3}
+DWT_MODE_IDS = {"symmetric": 0, "zero": 1, "reflect": 2, "periodic": 3, "periodization": 4}
+DWT_MODE_ALIASES = {"per": "periodization"}
 
 
 def make_filters(dec_lo, dec_hi, rec_lo, rec_hi) -> _native.SonarWaveletFilters:
@@ -740,8 +741,9 @@ def make_filters(dec_lo, dec_hi, rec_lo, rec_hi) -> _native.SonarWaveletFilters:
     return f
 
 
-def dwt_coeff_len(n: int, filter_len: int) -> int:
-    return (n + filter_len - 1) // 2
+def dwt_coeff_len(n: int, filter_len: int, mode: str = "symmetric") -> int:
+    """Coefficients per axis: (n + L - 1) // 2 for the expansive modes, ceil(n / 2) for periodization."""
+    return (n + 1) // 2 if mode == "periodization" else (n + filter_len - 1) // 2
 
 
 def dwt2_analysis(
@@ -760,7 +762,7 @@ def dwt2_analysis(
     if W != cols:
         raise ValueError("dwt2_analysis needs the row length of the buffer to equal W")
     L = filters.length
-    h, w = dwt_coeff_len(H, L), dwt_coeff_len(W, L)
+    h, w = dwt_coeff_len(H, L, mode), dwt_coeff_len(W, L, mode)
     ll = torch.empty((planes, h, w), device=a.device, dtype=coeff_dtype)
     hi = torch.empty((planes, 3, h, w), device=a.device, dtype=coeff_dtype)
     p = _native.SonarDwtAnalysisParams()
@@ -823,6 +825,29 @@ def dwt2_synthesis(
         live += [addend, x]
     lib, stream = _prepare(out, *live)
     _launch("sonar_dwt2_synthesis", lib.sonar_dwt2_synthesis, ctypes.byref(p), stream)
+    return out
+
+
+def dwt2_synthesis_per(ll: torch.Tensor, hi: torch.Tensor, scales: Sequence[float], filters: _native.SonarWaveletFilters) -> torch.Tensor:
+    """One reconstruction level of the non-expansive "periodization" transform: ll (planes, >=h, >=w), hi
+    (planes, 3, h, w) -> (planes, 2h, 2w) in the coefficient dtype, bands multiplied by `scales` on load."""
+    planes, _, h, w = hi.shape
+    if ll.dtype != hi.dtype or ll.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"dwt2_synthesis_per: coefficient dtypes {ll.dtype} / {hi.dtype}")
+    if ll.shape[0] != planes or ll.shape[1] < h or ll.shape[2] < w:
+        raise ValueError(f"dwt2_synthesis_per: ll {tuple(ll.shape)} does not cover hi {tuple(hi.shape)}")
+    out = torch.empty((planes, 2 * h, 2 * w), device=hi.device, dtype=hi.dtype)
+    p = _native.SonarDwtSynthesisParams()
+    p.ll[0], p.hi[0] = ll.data_ptr(), hi.data_ptr()
+    p.ll_rows[0], p.ll_cols[0] = ll.shape[1], ll.shape[2]
+    for i in range(4):
+        p.scales[0][i] = float(scales[i])
+    p.n_sets, p.planes, p.h, p.w = 1, planes, h, w
+    p.out, p.out_f32 = out.data_ptr(), 0
+    p.use_f64 = int(hi.dtype == torch.float64)
+    p.filters = filters
+    lib, stream = _prepare(ll, hi, out)
+    _launch("sonar_dwt2_synthesis_per", lib.sonar_dwt2_synthesis_per, ctypes.byref(p), stream)
     return out
 
 

@@ -75,6 +75,8 @@ class Wavelet:
     ):
         if use_dtcwt or use_1d_dwt:
             raise NotImplementedError("sonar_b200: only the 2-D DWT is in scope (no DTCWT / 1-D DWT kernels)")
+        mode = ops.DWT_MODE_ALIASES.get(mode, mode)
+        inv_mode = None if inv_mode is None else ops.DWT_MODE_ALIASES.get(inv_mode, inv_mode)
         if mode not in ops.DWT_MODE_IDS:
             raise NotImplementedError(
                 f"sonar_b200: padding mode {mode!r} has no kernel (supported: {', '.join(ops.DWT_MODE_IDS)})",
@@ -101,14 +103,36 @@ class Wavelet:
             yh.append(hi.reshape(*lead, 3, *hi.shape[-2:]))
         return cur.reshape(*lead, *cur.shape[-2:]), tuple(yh)
 
-    def inverse(self, yl: torch.Tensor, yh: Sequence, *, inverse_function: Callable | None = None, two_step_inverse: bool = False):
+    def inverse(
+        self,
+        yl: torch.Tensor,
+        yh: Sequence,
+        *,
+        inverse_function: Callable | None = None,
+        two_step_inverse: bool = False,
+        yl_scale: float = 1.0,
+        yh_scales=None,
+    ):
+        """IDWT. `yl_scale` / `yh_scales` (extension) fold `wavelet_scaling` into the synthesis kernels' loads
+        instead of a pass per band."""
         if inverse_function is not None:
             return inverse_function((yl, yh))
+        yh = tuple(yh)
+        band_scales = ((1.0, 1.0, 1.0),) * len(yh) if yh_scales is None else expand_yh_scales(yh, yh_scales=yh_scales)
         lead = yl.shape[:-2]
         ll = yl.reshape(-1, *yl.shape[-2:]).to(self.dtype).contiguous()
-        for hi in reversed(tuple(yh)):
+        for level in range(len(yh) - 1, -1, -1):
+            hi = yh[level]
             hi_p = hi.reshape(-1, 3, *hi.shape[-2:]).to(self.dtype).contiguous()
-            ll = ops.dwt2_synthesis([(ll, hi_p, (1.0, 1.0, 1.0, 1.0))], self.inv_filters)
+            sc = band_scales[level] if level < len(band_scales) else (1.0, 1.0, 1.0)
+            if isinstance(sc, (int, float)):
+                sc = (float(sc),) * 3
+            sc = (*sc, 1.0, 1.0, 1.0)[:3]
+            scales = (float(yl_scale) if level == len(yh) - 1 else 1.0, *sc)
+            if self.inv_mode == "periodization":
+                ll = ops.dwt2_synthesis_per(ll, hi_p, scales, self.inv_filters)
+            else:
+                ll = ops.dwt2_synthesis([(ll, hi_p, scales)], self.inv_filters)
         _ = two_step_inverse  # linear: one pass equals the two-step sum
         return ll.reshape(*lead, *ll.shape[-2:])
 

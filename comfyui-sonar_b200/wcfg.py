@@ -367,6 +367,11 @@ class WCFGWaveletSettings(NamedTuple):
         return WCFGWaveletSettings(**filter_dict(kwargs, cls._fields))
 
     def make_wavelet(self, **kwargs) -> Wavelet:
+        if "per" in (self.padding_mode, self.inv_padding_mode) or "periodization" in (self.padding_mode, self.inv_padding_mode):
+            raise NotImplementedError(
+                "sonar_b200: wavelet CFG runs on the expansive DWT kernels (symmetric / zero / reflect / periodic); "
+                "the non-expansive periodization mode is only built for the wavelet-filtered noise type",
+            )
         return Wavelet(
             wave=self.wave,
             level=self.level,

@@ -348,7 +348,13 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params_host, void* stre
  * (crop_h, crop_w):  out_f32 = x_scale*x + (float)(recon_sign*(recon + addend_scale*addend)).
  * ---------------------------------------------------------------------------------------------- */
 #define SONAR_DWT_MAX_TAPS 40
-enum { SONAR_DWT_MODE_SYMMETRIC = 0, SONAR_DWT_MODE_ZERO = 1, SONAR_DWT_MODE_REFLECT = 2, SONAR_DWT_MODE_PERIODIC = 3 };
+enum {
+  SONAR_DWT_MODE_SYMMETRIC = 0,
+  SONAR_DWT_MODE_ZERO = 1,
+  SONAR_DWT_MODE_REFLECT = 2,
+  SONAR_DWT_MODE_PERIODIC = 3,
+  SONAR_DWT_MODE_PERIODIZATION = 4 /* non-expansive: h = ceil(H / 2); analysis only, synthesis = sonar_dwt2_synthesis_per */
+};
 
 typedef struct SonarWaveletFilters {
   int32_t length;
@@ -401,6 +407,10 @@ typedef struct SonarDwtSynthesisParams {
 int sonar_dwt_coeff_len(int n, int filter_len);
 int sonar_dwt2_analysis(const SonarDwtAnalysisParams* params_host, void* stream);
 int sonar_dwt2_synthesis(const SonarDwtSynthesisParams* params_host, void* stream);
+/* One reconstruction level of the non-expansive "periodization" transform (WaveletFilteredNoiseGenerator's default
+ * mode, py/noise_generation.py:1908-2032): one coefficient set (n_sets = 1), out (planes, 2h, 2w) in the
+ * coefficient type; ll may be one row / column larger than h, w (ll_rows / ll_cols). */
+int sonar_dwt2_synthesis_per(const SonarDwtSynthesisParams* params_host, void* stream);
 
 /* The whole wavelet-CFG combine in ONE launch (one CTA per plane, every coefficient of every level in
  * shared memory):  value = in_a - in_b (in_b optional), coefficients scaled per band (scale_ll for the

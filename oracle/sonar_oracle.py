@@ -651,15 +651,59 @@ def _afb1d(x: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, mode: str, dim: 
     return F.conv2d(x, filt, stride=stride, groups=c)
 
 
+def _afb1d_per(x: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor, dim: int) -> torch.Tensor:
+    """pytorch_wavelets lowlevel.afb1d, mode "periodization" ([upstream], restated from memory): odd lengths
+    repeat the last sample, roll by -L/2, zero-pad L-1, correlate with the reversed filters at stride 2, fold
+    the L/2 overhanging outputs back onto the head, keep N/2."""
+    c = x.shape[1]
+    d = dim % 4
+    taps = lo.numel()
+    if x.shape[d] % 2 == 1:
+        x = torch.cat((x, x.narrow(d, x.shape[d] - 1, 1)), dim=d)
+    n = x.shape[d]
+    x = torch.roll(x, -(taps // 2), dims=d)
+    shape = [1, 1, 1, 1]
+    shape[d] = taps
+    filt = torch.cat([lo.flip(0).reshape(shape), hi.flip(0).reshape(shape)] * c, dim=0)
+    stride = (2, 1) if d == 2 else (1, 2)
+    pad = (taps - 1, 0) if d == 2 else (0, taps - 1)
+    lohi = F.conv2d(x, filt, padding=pad, stride=stride, groups=c)
+    n2, l2 = n // 2, taps // 2
+    head = lohi.narrow(d, 0, l2) + lohi.narrow(d, n2, l2)
+    return torch.cat((head, lohi.narrow(d, l2, n2 - l2)), dim=d) if n2 > l2 else head.narrow(d, 0, n2)
+
+
+def _sfb1d_per(lo: torch.Tensor, hi: torch.Tensor, g0: torch.Tensor, g1: torch.Tensor, dim: int) -> torch.Tensor:
+    """pytorch_wavelets lowlevel.sfb1d, mode "periodization": transposed convolution, the L-2 tail wrapped onto
+    the head, N = 2 * len kept, rolled by 1 - L/2."""
+    c = lo.shape[1]
+    d = dim % 4
+    taps = g0.numel()
+    shape = [1, 1, 1, 1]
+    shape[d] = taps
+    stride = (2, 1) if d == 2 else (1, 2)
+    f0 = torch.cat([g0.reshape(shape)] * c, dim=0)
+    f1 = torch.cat([g1.reshape(shape)] * c, dim=0)
+    y = F.conv_transpose2d(lo, f0, stride=stride, groups=c) + F.conv_transpose2d(hi, f1, stride=stride, groups=c)
+    n = 2 * lo.shape[d]
+    if taps > 2:
+        head = y.narrow(d, 0, taps - 2) + y.narrow(d, n, taps - 2)
+        y = torch.cat((head, y.narrow(d, taps - 2, n - (taps - 2))), dim=d)
+    else:
+        y = y.narrow(d, 0, n)
+    return torch.roll(y, 1 - taps // 2, dims=d)
+
+
 def dwt2_forward(x: torch.Tensor, filters, level: int, mode: str = "symmetric"):
     """pytorch_wavelets.DWTForward(J, wave, mode): (yl, [yh_1 (finest) .. yh_J])."""
     dec_lo, dec_hi, _, _ = filters
     lo = torch.tensor(dec_lo, dtype=x.dtype)
     hi = torch.tensor(dec_hi, dtype=x.dtype)
     yh, ll = [], x
+    per = mode in ("per", "periodization")
     for _ in range(level):
-        lohi = _afb1d(ll, lo, hi, mode, dim=3)
-        y = _afb1d(lohi, lo, hi, mode, dim=2)
+        lohi = _afb1d_per(ll, lo, hi, dim=3) if per else _afb1d(ll, lo, hi, mode, dim=3)
+        y = _afb1d_per(lohi, lo, hi, dim=2) if per else _afb1d(lohi, lo, hi, mode, dim=2)
         s = y.shape
         y = y.reshape(s[0], -1, 4, s[-2], s[-1])
         ll = y[:, :, 0].contiguous()
@@ -683,8 +727,9 @@ def _sfb1d(lo: torch.Tensor, hi: torch.Tensor, g0: torch.Tensor, g1: torch.Tenso
     )
 
 
-def dwt2_inverse(yl: torch.Tensor, yh: Sequence[torch.Tensor], filters):
-    """pytorch_wavelets.DWTInverse(wave, mode) for zero/symmetric/reflect/periodic."""
+def dwt2_inverse(yl: torch.Tensor, yh: Sequence[torch.Tensor], filters, mode: str = "symmetric"):
+    """pytorch_wavelets.DWTInverse(wave, mode); the expansive modes share one synthesis, periodization has its own."""
+    sfb = _sfb1d_per if mode in ("per", "periodization") else _sfb1d
     _, _, rec_lo, rec_hi = filters
     g0 = torch.tensor(rec_lo, dtype=yl.dtype)
     g1 = torch.tensor(rec_hi, dtype=yl.dtype)
@@ -695,9 +740,9 @@ def dwt2_inverse(yl: torch.Tensor, yh: Sequence[torch.Tensor], filters):
         if ll.shape[-1] > h.shape[-1]:
             ll = ll[..., :-1]
         lh, hl, hh = torch.unbind(h, dim=2)
-        lo = _sfb1d(ll, lh, g0, g1, dim=2)
-        hi = _sfb1d(hl, hh, g0, g1, dim=2)
-        ll = _sfb1d(lo, hi, g0, g1, dim=3)
+        lo = sfb(ll, lh, g0, g1, dim=2)
+        hi = sfb(hl, hh, g0, g1, dim=2)
+        ll = sfb(lo, hi, g0, g1, dim=3)
     return ll
 
 

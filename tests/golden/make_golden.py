@@ -462,6 +462,7 @@ IN_SCOPE_NODES = (
     "SonarAdvanced1fNoise", "SonarAdvancedPowerLawNoise", "SonarCompositeNoise", "SonarScheduledNoise",
     "SonarBlendedNoise", "SonarRepeatedNoise", "SonarCustomNoiseParameters", "SONAR_CUSTOM_NOISE to NOISE",
     "SamplerConfigOverride", "SonarWaveletCFG", "NoisyLatentLike", "FreeUExtremeConfig", "FreeUExtreme",
+    "SonarWaveletFilteredNoise",
 )  # fmt: skip
 
 
