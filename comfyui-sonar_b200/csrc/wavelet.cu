@@ -12,10 +12,14 @@
 // pad -> correlate -> decimate; row and column passes are fused (no row-filtered intermediate).
 // Band order of the detail tensor (planes, 3, h, w): [0] high along H / low along W,
 // [1] low along H / high along W, [2] high / high  (pytorch_wavelets AFB2D channel order).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "../../include/sonar_b200.h"
 
 namespace sonar {
+
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ int extend_index_wrapped(int i, int n, int mode) {
   // general case: the index lies more than one signal length outside [0, n)
@@ -413,14 +417,28 @@ dwt2_per_synthesis_kernel(SynthSet<T> c, int64_t planes, int h, int w, T* __rest
 // ---------------------------------------------------------------------------------------------
 struct WcfgGeom {
   int levels;
+  int pair;        // 1: a plane is shared by a cluster of two CTAs (see wcfg_fused_kernel)
+  int hi0_rows;    // rows of the level-1 detail bands a CTA holds (pair: its half plus the synthesis halo)
   int h[SONAR_WCFG_MAX_LEVELS], w[SONAR_WCFG_MAX_LEVELS];            // coefficient extents, fine -> coarse
   int ll_off[SONAR_WCFG_MAX_LEVELS], hi_off[SONAR_WCFG_MAX_LEVELS];  // element offsets into shared memory
   int total;                                                         // elements
 };
 
-static bool wcfg_geometry(int H, int W, int L, int levels, WcfgGeom* g) {
+// Level-1 coefficient rows [lo, hi) that rank `rank` of a CTA pair computes and keeps: the rows its half
+// of the final synthesis quads reads (quad qy reads rows qy .. qy + L/2 - 1).
+__host__ __device__ inline void wcfg_pair_rows(int H, int h0, int L, int rank, int* q_lo, int* q_hi, int* r_lo, int* r_hi) {
+  const int qh = (H + 1) >> 1, q_mid = (qh + 1) >> 1;
+  *q_lo = rank ? q_mid : 0;
+  *q_hi = rank ? qh : q_mid;
+  *r_lo = *q_lo;
+  const int top = *q_hi + L / 2 - 1;
+  *r_hi = top < h0 ? top : h0;
+}
+
+static bool wcfg_geometry(int H, int W, int L, int levels, WcfgGeom* g, bool pair = false) {
   if (levels < 1 || levels > SONAR_WCFG_MAX_LEVELS || H <= 0 || W <= 0) return false;
   g->levels = levels;
+  g->pair = pair ? 1 : 0;
   int hh = H, ww = W;
   for (int j = 0; j < levels; ++j) {
     hh = (hh + L - 1) / 2;
@@ -438,7 +456,18 @@ static bool wcfg_geometry(int H, int W, int L, int levels, WcfgGeom* g) {
     g->ll_off[j] = (int)off;
     off += ll + (ll & 1);
     g->hi_off[j] = (int)off;
-    off += 3 * (int64_t)g->h[j] * g->w[j];
+    int hi_rows = g->h[j];
+    if (j == 0) {
+      if (pair) {
+        int q_lo, q_hi, r_lo, r_hi;
+        wcfg_pair_rows(H, g->h[0], L, 0, &q_lo, &q_hi, &r_lo, &r_hi);
+        hi_rows = r_hi - r_lo;
+        wcfg_pair_rows(H, g->h[0], L, 1, &q_lo, &q_hi, &r_lo, &r_hi);
+        if (r_hi - r_lo > hi_rows) hi_rows = r_hi - r_lo;
+      }
+      g->hi0_rows = hi_rows;
+    }
+    off += 3 * (int64_t)hi_rows * g->w[j];
     off += off & 1;
     if (off > (1 << 28)) return false;
   }
@@ -453,7 +482,14 @@ struct WcfgScales {
   T v[SONAR_WCFG_MAX_LEVELS * 3];  // [level][orientation], fine -> coarse
 };
 
-template <typename T, int LT>
+// PAIR: a cluster of two CTAs shares a plane, for calls with fewer planes than half the SMs (SDXL batch
+// 16 x 4 channels = 64 planes on 148 SMs). The two heavy phases split by rows with no exchange of detail
+// coefficients: each CTA runs the level-1 analysis only for the coefficient rows its half of the final
+// synthesis reads (half the plane plus an L/2 - 1 row halo) and keeps those detail rows to itself; the
+// level-1 approximation rows are stored into BOTH CTAs' shared memory (distributed shared memory), after
+// which each CTA runs the small coarser levels redundantly and synthesises its half of the output rows.
+// ~63 % of the single-CTA work per CTA, one cluster barrier per plane.
+template <typename T, int LT, bool PAIR>
 __global__ void __launch_bounds__(kWcfgThreads, 1)
 wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, float* __restrict__ out,
                   const float* __restrict__ addend, float addend_scale, const float* __restrict__ x, float x_scale,
@@ -465,7 +501,21 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
   const int L = LT > 0 ? LT : f.L, J = g.levels;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const bool vec2_ok = (W & 1) == 0 && (((uintptr_t)out | (uintptr_t)addend | (uintptr_t)x) & 7u) == 0;
-  for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {
+  // level-1 rows / final quads of this CTA (everything without PAIR)
+  int q_lo = 0, q_hi = (H + 1) >> 1, r_lo = 0, r_hi = g.h[0], own_lo = 0, own_hi = g.h[0];
+  T* peer_ll0 = nullptr;
+  if (PAIR) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    wcfg_pair_rows(H, g.h[0], L, rank, &q_lo, &q_hi, &r_lo, &r_hi);
+    int a, b, c, split;
+    wcfg_pair_rows(H, g.h[0], L, 0, &a, &b, &c, &split);  // rank 0 owns approximation rows [0, split), rank 1 the rest
+    own_lo = rank ? split : 0;
+    own_hi = rank ? g.h[0] : split;
+    peer_ll0 = cluster.map_shared_rank(sm, rank ^ 1) + g.ll_off[0];
+  }
+  const int64_t plane_first = PAIR ? blockIdx.x >> 1 : blockIdx.x, plane_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+  for (int64_t plane = plane_first; plane < planes; plane += plane_step) {
     const float* pa = in_a + plane * (int64_t)H * W;
     const float* pb = in_b != nullptr ? in_b + plane * (int64_t)H * W : nullptr;
     // ---------------- analysis, fine -> coarse ----------------
@@ -474,8 +524,10 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       const int h = g.h[j], w = g.w[j];
       const int pad_t = (2 * (h - 1) - Hin + L) / 2, pad_l = (2 * (w - 1) - Win + L) / 2;
       T* ll = sm + g.ll_off[j];
-      T* hi = sm + g.hi_off[j];
-      const int hw = h * w;
+      // level 1 keeps only this CTA's detail rows [ra, rb): pointer biased so that ky * w + kx still indexes it
+      const int ra = j == 0 ? r_lo : 0, rb = j == 0 ? r_hi : h;
+      T* hi = sm + g.hi_off[j] - ra * w;
+      const int hw = (j == 0 ? g.hi0_rows : h) * w;
       // interior outputs first (fast path, all lanes alike), then the border ring: no warp ever runs
       // both code paths back to back
       int kx_lo = 0, kx_hi = -1, ky_lo = 0, ky_hi = -1;
@@ -484,12 +536,13 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
         ky_lo = (pad_t + 1) >> 1;
         kx_hi = Win - L + pad_l >= 0 ? min(w - 1, (Win - L + pad_l) >> 1) : -1;
         ky_hi = Hin - L + pad_t >= 0 ? min(h - 1, (Hin - L + pad_t) >> 1) : -1;
-        const int iw = max(0, kx_hi - kx_lo + 1), ih = max(0, ky_hi - ky_lo + 1);
+        const int iy_lo = max(ky_lo, ra), iy_hi = min(ky_hi, rb - 1);
+        const int iw = max(0, kx_hi - kx_lo + 1), ih = max(0, iy_hi - iy_lo + 1);
         const bool vec2 = j == 0 && ((pad_l | W) & 1) == 0 && (((uintptr_t)in_a | (uintptr_t)in_b) & 7u) == 0 &&
                           ((H * (int64_t)W) & 1) == 0;
         for (int i = tid; i < iw * ih; i += nthr) {
           const int iy = i / iw, ix = i - iy * iw;
-          const int ky = ky_lo + iy, kx = kx_lo + ix, idx = ky * w + kx;
+          const int ky = iy_lo + iy, kx = kx_lo + ix, idx = ky * w + kx;
           T c_ll, c_lh, c_hl, c_hh;
           if (j == 0) {
             if (vec2)
@@ -500,7 +553,12 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
             analysis_interior<T, T, LT, false>(sm + g.ll_off[j - 1], nullptr, Win, 2 * ky - pad_t, 2 * kx - pad_l, f, c_ll,
                                                c_lh, c_hl, c_hh);
           }
-          ll[idx] = c_ll;
+          if (!PAIR || j > 0) {
+            ll[idx] = c_ll;
+          } else if (ky >= own_lo && ky < own_hi) {
+            ll[idx] = c_ll;
+            peer_ll0[idx] = c_ll;
+          }
           hi[idx] = c_lh;
           hi[hw + idx] = c_hl;
           hi[2 * hw + idx] = c_hh;
@@ -510,23 +568,29 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       // columns of the interior rows): a warp of the ring holds 32 border outputs, not 1 or 2
       {
         const bool has_interior = kx_hi >= kx_lo && ky_hi >= ky_lo;
-        const int top = has_interior ? ky_lo * w : hw;            // outputs in the rows above (or everything)
-        const int bottom = has_interior ? (h - 1 - ky_hi) * w : 0;
+        // rows [ra, rb) of this CTA: those above the interior (or all of them), those below it, and the
+        // left / right columns of its interior rows
+        const int top_hi = has_interior ? min(rb, ky_lo) : rb;
+        const int bot_lo = has_interior ? max(ra, ky_hi + 1) : rb;
+        const int mid_lo = max(ky_lo, ra), mid_rows = has_interior ? max(0, min(ky_hi, rb - 1) - mid_lo + 1) : 0;
+        const int top = max(0, top_hi - ra) * w;
+        const int bottom = max(0, rb - bot_lo) * w;
         const int right0 = kx_hi + 1;                              // first column right of the interior
         const int side = has_interior ? kx_lo + (w - right0) : 0;  // border outputs per interior row
-        const int ring = top + bottom + (has_interior ? (ky_hi - ky_lo + 1) * side : 0);
+        const int ring = top + bottom + mid_rows * side;
         for (int b = tid; b < ring; b += nthr) {
           int ky, kx;
           if (b < top) {
-            ky = b / w;
-            kx = b - ky * w;
+            const int r = b / w;
+            ky = ra + r;
+            kx = b - r * w;
           } else if (b < top + bottom) {
             const int r = (b - top) / w;
-            ky = ky_hi + 1 + r;
+            ky = bot_lo + r;
             kx = (b - top) - r * w;
           } else {
             const int r = (b - top - bottom) / side, c = (b - top - bottom) - r * side;
-            ky = ky_lo + r;
+            ky = mid_lo + r;
             kx = c < kx_lo ? c : right0 + (c - kx_lo);
           }
           const int idx = ky * w + kx;
@@ -536,13 +600,21 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
           else
             analysis_point<T, T, LT>(sm + g.ll_off[j - 1], nullptr, Win, Hin, Win, ky, kx, pad_t, pad_l, mode, f, c_ll,
                                      c_lh, c_hl, c_hh);
-          ll[idx] = c_ll;
+          if (!PAIR || j > 0) {
+            ll[idx] = c_ll;
+          } else if (ky >= own_lo && ky < own_hi) {
+            ll[idx] = c_ll;
+            peer_ll0[idx] = c_ll;
+          }
           hi[idx] = c_lh;
           hi[hw + idx] = c_hl;
           hi[2 * hw + idx] = c_hh;
         }
       }
-      __syncthreads();
+      if (PAIR && j == 0)
+        cg::this_cluster().sync();  // both halves of the level-1 approximation have landed in both CTAs
+      else
+        __syncthreads();
     }
     // ---------------- synthesis, coarse -> fine ----------------
     for (int j = J - 1; j >= 0; --j) {
@@ -552,15 +624,17 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       const int ll_pitch = coarsest ? w : 2 * g.w[j + 1] - L + 2;
       const T s_ll = coarsest ? scale_ll : (T)1;
       const T s_lh = scale_hi[3 * j], s_hl = scale_hi[3 * j + 1], s_hh = scale_hi[3 * j + 2];
-      const T* hi = sm + g.hi_off[j];
+      const T* hi = sm + g.hi_off[j] - (j == 0 ? r_lo : 0) * w;  // level 1: this CTA's rows only (biased pointer)
+      const int64_t hi_band = (int64_t)(j == 0 ? g.hi0_rows : h) * w;
       const int out_h = 2 * h - L + 2, out_w = 2 * w - L + 2;
       const int oh = j == 0 ? H : out_h, ow = j == 0 ? W : out_w;  // the final level is cropped to the input size
       const int qh = (oh + 1) >> 1, qw = (ow + 1) >> 1;
       T* rec = j == 0 ? nullptr : sm + g.ll_off[j - 1];
-      for (int idx = tid; idx < qh * qw; idx += nthr) {
-        const int qy = idx / qw, qx = idx - qy * qw;
+      const int qy_first = j == 0 ? q_lo : 0, qy_count = (j == 0 ? min(q_hi, qh) : qh) - qy_first;
+      for (int idx = tid; idx < qy_count * qw; idx += nthr) {
+        const int qr = idx / qw, qy = qy_first + qr, qx = idx - qr * qw;
         T o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-        synthesis_quad<T, LT>(ll, ll_pitch, hi, (int64_t)h * w, w, h, w, qy, qx, s_ll, s_lh, s_hl, s_hh, f, o00, o01, o10, o11);
+        synthesis_quad<T, LT>(ll, ll_pitch, hi, hi_band, w, h, w, qy, qx, s_ll, s_lh, s_hl, s_hh, f, o00, o01, o10, o11);
         const T vals[4] = {o00, o01, o10, o11};
         if (j == 0 && vec2_ok) {
           // final level, even width: the quad's two rows are 8-byte aligned float2 accesses
@@ -604,6 +678,8 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
       }
       __syncthreads();
     }
+    // the partner stores the next plane's level-1 approximation into this CTA's LL[0], which held rec_1 until now
+    if (PAIR) cg::this_cluster().sync();
   }
 }
 
@@ -695,16 +771,40 @@ int launch_wcfg_fused(const SonarWcfgFusedParams& p, const WcfgGeom& g, cudaStre
   for (int j = 0; j < SONAR_WCFG_MAX_LEVELS; ++j)
     for (int o = 0; o < 3; ++o) sc.v[3 * j + o] = j < p.levels ? (T)p.scale_hi[j][o] : (T)0;
   const DeviceInfo& di = device_info();
-  const int grid = (int)(p.planes < di.sm_count ? p.planes : di.sm_count);
-#define WCFG_FUSED(LT)                                                                                              \
-  do {                                                                                                              \
-    SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_fused_kernel<T, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    wcfg_fused_kernel<T, LT><<<grid, kWcfgThreads, smem, stream>>>(p.in_a, p.in_b, p.out, p.addend, p.addend_scale, p.x, \
-                                                                   p.x_scale, p.recon_sign, p.planes, p.H, p.W, p.mode, g, \
-                                                                   (T)p.scale_ll, sc, f);                           \
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kWcfgThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  if (g.pair) {  // one cluster of two CTAs per plane
+    const int64_t clusters = p.planes < di.sm_count / 2 ? p.planes : di.sm_count / 2;
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)(p.planes < di.sm_count ? p.planes : di.sm_count));
+  }
+  const T scale_ll = (T)p.scale_ll;
+#define WCFG_FUSED_KERNEL(LT, PAIR)                                                                                      \
+  do {                                                                                                                   \
+    SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_fused_kernel<T, LT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    SONAR_CUDA_TRY(cudaLaunchKernelEx(&cfg, wcfg_fused_kernel<T, LT, PAIR>, p.in_a, p.in_b, p.out, p.addend, p.addend_scale, \
+                                      p.x, p.x_scale, p.recon_sign, p.planes, p.H, p.W, p.mode, g, scale_ll, sc, f));      \
+  } while (0)
+#define WCFG_FUSED(LT)                 \
+  do {                                 \
+    if (g.pair)                        \
+      WCFG_FUSED_KERNEL(LT, true);     \
+    else                               \
+      WCFG_FUSED_KERNEL(LT, false);    \
   } while (0)
   SONAR_DISPATCH_TAPS(p.filters.length, WCFG_FUSED)
 #undef WCFG_FUSED
+#undef WCFG_FUSED_KERNEL
   SONAR_LAUNCH_CHECK();
   return 0;
 }
@@ -745,7 +845,9 @@ int sonar_wcfg_fused(const SonarWcfgFusedParams* params, void* stream) {
   if (p.in_a == nullptr || p.out == nullptr || p.mode == SONAR_DWT_MODE_PERIODIZATION) return (int)cudaErrorInvalidValue;
   if (sonar_wcfg_fused_smem_bytes(p.H, p.W, p.filters.length, p.levels, p.use_f64) <= 0) return (int)cudaErrorInvalidValue;
   WcfgGeom g;
-  wcfg_geometry(p.H, p.W, p.filters.length, p.levels, &g);
+  // fewer planes than half the SMs: two CTAs (a cluster) per plane
+  const bool pair = 2 * p.planes <= device_info().sm_count && p.H >= 4 * p.filters.length;
+  wcfg_geometry(p.H, p.W, p.filters.length, p.levels, &g, pair);
   // the final level must reconstruct at least the input extent (true for every orthogonal bank here)
   if (2 * g.h[0] - p.filters.length + 2 < p.H || 2 * g.w[0] - p.filters.length + 2 < p.W) return (int)cudaErrorInvalidValue;
   return p.use_f64 ? launch_wcfg_fused<double>(p, g, (cudaStream_t)stream) : launch_wcfg_fused<float>(p, g, (cudaStream_t)stream);

@@ -142,7 +142,9 @@ class SonarBase:
         return SonarConfig(**(cfg._asdict() | merged))
 
     def set_noise_sampler(self, x: Tensor, sigmas: Tensor, noise_sampler: Callable | None, seed: int | None = None):
-        sigmas_host = sigmas.detach().float().cpu()
+        sigmas_host = getattr(self, "sigmas_host", None)  # the run's one device->host copy of the schedule
+        if sigmas_host is None or sigmas_host.shape != sigmas.shape:
+            sigmas_host = sigmas.detach().float().cpu()
         sigma_min, sigma_max = sigmas_host[sigmas_host > 0].min(), sigmas_host.max()
         if noise_sampler is not None and self.cfg.noise_type not in {None, self.DEFAULT_NOISE_TYPE}:
             print("Sonar: Warning: Noise sampler supplied, overriding noise type from settings", file=stderr)
@@ -618,8 +620,8 @@ class SonarSampler(SonarWithGuidance):
         return self.model(x, sigma * s_in, *args, **extra_args)
 
     def run(self, x: Tensor, callback, disable) -> Tensor:
-        sigmas = self.sigmas
-        for i in trange(len(sigmas) - 1, disable=disable):
+        n_steps = len(self.sigmas) - 1
+        for i in range(n_steps) if disable else trange(n_steps, disable=disable):  # (a disabled tqdm still costs ~40 us to build)
             x, sigma, sigma_hat, denoised = self.step(i, x)
             if callback is not None:
                 callback({"x": x, "i": i, "sigma": self.sigma_views[i], "sigma_hat": sigma_hat, "denoised": denoised})

@@ -152,7 +152,9 @@ def test_rule_out_of_range_falls_back(sb, cuda):
 @pytest.mark.parametrize(
     "rule,shape",
     [
-        (C4_RULE, (3, 4, 128, 128)),
+        (C4_RULE, (3, 4, 128, 128)),    # 12 planes: two CTAs (a cluster) per plane
+        (C4_RULE, (20, 4, 128, 128)),   # 80 planes: more than half the SMs -> one CTA per plane
+        (C4_RULE, (5, 3, 127, 90)),     # cluster path, odd height: uneven halves
         ({"wave": "db4", "level": 3, "diff": {"yl_scale": 2.0, "yh_scales": [[1, 2, 3], 2.5, 0.5]}}, (2, 3, 33, 47)),
         ({"wave": "haar", "level": 4, "high_precision_mode": False, "diff": {"yl_scale": 4.0, "yh_scales": 2.0}}, (1, 4, 64, 96)),
         ({"wave": "db2", "level": 2, "padding_mode": "periodic", "diff": {"yl_scale": 3.0, "yh_scales": 1.5}}, (2, 2, 40, 24)),
