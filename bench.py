@@ -47,6 +47,7 @@ sys.path.insert(0, str(REPO))
 
 SHAPE = (8, 4, 128, 128)
 N_SAMPLER_STEPS = 30
+FLUSH_PASSES = 8  # 256 MiB zero-fills per stub-denoiser call: L2 eviction + ~0.4 ms of device time (see StepTimer)
 ELEMS_PER_RUN = N_SAMPLER_STEPS * SHAPE[0] * SHAPE[1] * SHAPE[2] * SHAPE[3]
 WORKLOAD = "C2 sonar_euler_ancestral, SDXL latents 8x4x128x128, 30 steps, fused Gaussian noise"
 
@@ -208,9 +209,12 @@ class StepTimer:
     """Denoiser stub that doubles as the boundary of the timed regions: everything the sampler
     enqueues between two model calls is the hot path of one sampler step."""
 
-    def __init__(self, device, flush_bytes: int = 256 << 20, timed: bool = True):
+    def __init__(self, device, flush_bytes: int = 256 << 20, timed: bool = True, flush_passes: int = FLUSH_PASSES,
+                 on_first_call=None):
         self.flush = torch.empty(flush_bytes, dtype=torch.uint8, device=device) if flush_bytes else None
+        self.flush_passes = flush_passes
         self.timed = timed
+        self.on_first_call = on_first_call  # multi-GPU: device-side rendezvous of the ranks at the first denoiser call
         self.pairs: list[tuple[torch.cuda.Event, torch.cuda.Event]] = []
         self._open: torch.cuda.Event | None = None
 
@@ -224,8 +228,18 @@ class StepTimer:
     def __call__(self, x, sigma, **_kw):
         if self.timed:
             self.close()
+        if self.on_first_call is not None:
+            # the GPUs meet HERE, with the host already enqueueing the denoiser and the first sampler step behind
+            # the rendezvous: from its release on every rank runs from a full queue, so the exchange inside the
+            # first step measures NVLink and the slowest GPU, not the slowest Python thread
+            self.on_first_call()
+            self.on_first_call = None
         if self.flush is not None:
-            self.flush.zero_()  # evicts L2, like the UNet forward that sits here in real use
+            # evicts L2 and keeps the GPU busy for ~0.4 ms, like (a small fraction of) the UNet forward that sits
+            # here in real use: the host enqueues the next step while the device is still in the denoiser, so
+            # the timed intervals are device time of the hot path, not Python launch latency
+            for _ in range(self.flush_passes):
+                self.flush.zero_()
         den = x * 0.9
         if self.timed:
             self._open = torch.cuda.Event(enable_timing=True)
@@ -355,18 +369,20 @@ def run_b200_arm(args) -> None:
 
     # ---------------- device-resident throughput ----------------
     warm_model = StepTimer(dev, timed=False)
+    def device_rendezvous():
+        with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
+            sb.parallel.device_barrier()
+
+    rendezvous = device_rendezvous if world > 1 else None
+
     def align_ranks():
-        """Ranks start a run together, so that the one exchange of a run measures NVLink and not host drift: a
-        host barrier, then a device-side rendezvous (peer mailboxes) behind which every host keeps enqueueing --
-        the GPUs leave it within NVLink latency of each other."""
+        """Ranks start a run together: a host barrier here, and a device-side rendezvous (peer mailboxes) at the
+        run's first denoiser call (StepTimer.on_first_call)."""
         barrier()
-        if world > 1:
-            with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
-                sb.parallel.device_barrier()
 
     for _ in range(max(3, args.warmup)):
         align_ranks()
-        one_run(warm_model, x0)
+        one_run(StepTimer(dev, timed=False, on_first_call=rendezvous), x0)
     barrier()
     launches0 = sb.ops.LAUNCH_COUNT
     timers = []
@@ -374,13 +390,13 @@ def run_b200_arm(args) -> None:
     gc.disable()  # a collection pause between two launches would show up as device idle time
     with ClockSampler(local_rank, enabled=rank == 0) as clocks:
         align_ranks()
-        one_run(warm_model, x0)  # one more untimed run now that the clock poller is up (rank 0 waited for it)
+        one_run(StepTimer(dev, timed=False, on_first_call=rendezvous), x0)  # one more untimed run with the clock poller up
         barrier()
         t_wall = time.perf_counter()
         for _ in range(args.steps):
             if world > 1:
                 align_ranks()
-            timer = StepTimer(dev)
+            timer = StepTimer(dev, on_first_call=rendezvous)
             one_run(timer, x0)
             timer.close()
             timers.append(timer)
@@ -395,10 +411,16 @@ def run_b200_arm(args) -> None:
     launches = sb.ops.LAUNCH_COUNT - launches0
     run_ms = [t.total_ms() for t in timers]
     ms_per_step = statistics.mean(run_ms)
-    t_dev = torch.tensor([ms_per_step], device=dev, dtype=torch.float64)
+    # per rank: (mean run, mean first-step interval -- the one that holds the look-ahead pass and the exchange)
+    first_ms = statistics.mean(t.pairs[0][0].elapsed_time(t.pairs[0][1]) for t in timers)
+    per_rank = torch.tensor([ms_per_step, first_ms], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_dev.item())
+        gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
+        per_rank_ms = [[round(float(v), 4) for v in g.tolist()] for g in gathered]
+    else:
+        per_rank_ms = [[round(ms_per_step, 4), round(first_ms, 4)]]
+    ms_per_step = max(r[0] for r in per_rank_ms) if world > 1 else ms_per_step
     value = ELEMS_PER_RUN * world / (ms_per_step * 1e-3)
 
     # ---------------- roofline of the dominant kernel (per-launch CUDA events) ----------------
@@ -476,7 +498,7 @@ def run_b200_arm(args) -> None:
                 "global_batch": global_batch,
                 "per_gpu_shape": list(SHAPE),
                 "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
-                "l2": "256 MiB flush between sampler steps (where the UNet runs); stub denoiser untimed",
+                "l2": f"{FLUSH_PASSES} x 256 MiB flush between sampler steps (where the UNet runs, ~0.4 ms of device time); stub denoiser untimed",
                 "timing": "sum of 30 CUDA-event intervals per run (fused step launch; step 0 includes the batched Philox statistics of all draws), max over ranks",
             },
             "roofline": roofline,
@@ -487,6 +509,7 @@ def run_b200_arm(args) -> None:
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,
             "runs_ms": run_ms,
+            "per_rank_ms": per_rank_ms,  # [mean run, mean first sampler step] of every rank
         }
         if extras is not None:
             line["other_configs"] = extras
