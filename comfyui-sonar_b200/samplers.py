@@ -648,8 +648,9 @@ def _host_schedule(sigmas: Tensor) -> Tensor:
     if cached is not None and cached[0]() is sigmas and cached[1] == sigmas._version:  # noqa: SLF001
         return cached[2]
     host = sigmas.detach().to(dtype=torch.float32, device="cpu")
-    if sigmas.is_cuda:
-        _SCHEDULE_CACHE[0] = (weakref.ref(sigmas), sigmas._version, host)  # noqa: SLF001
+    if host.data_ptr() == sigmas.data_ptr():  # float32 CPU schedule: `to` returned the same storage
+        host = host.clone()
+    _SCHEDULE_CACHE[0] = (weakref.ref(sigmas), sigmas._version, host)  # noqa: SLF001
     return host
 
 

@@ -173,6 +173,8 @@ def _gloo_worker(rank: int, world: int, port: int, q) -> None:
             total, begin = sb.parallel.global_draw_geometry(local.shape)
             gathered = sb.parallel.gather(local)
             to_zero = sb.parallel.gather(local, dst=0)
+            # no peer memory under gloo: the device rendezvous declines instead of hanging or touching CUDA
+            assert ctx.peers is None and sb.parallel.device_barrier() is False
             q.put((rank, ctx.batch_sizes, count, sums.tolist(), total, begin, torch.equal(gathered, full),
                    None if to_zero is None else torch.equal(to_zero, full), ctx.collectives))
     finally:
@@ -200,3 +202,22 @@ def test_sharding_world_size_2_gloo():
         assert sums == pytest.approx([float(full.sum()), float((full * full).sum())])
         assert gathered_ok and (dst_ok is True if rank == 0 else dst_ok is None)
         assert collectives == 3
+
+
+def test_host_schedule_copy_is_cached_per_tensor_object(sb):
+    """The sampler's one device->host copy of the sigma schedule is reused only for the very same, unmodified
+    tensor object (weak reference + version counter), never for another tensor with equal values."""
+    from sonar_b200 import samplers
+
+    a = torch.linspace(14.6, 0.0, 8)
+    h1 = samplers._host_schedule(a)
+    assert h1 is samplers._host_schedule(a) and h1.data_ptr() != a.data_ptr()
+    a.mul_(0.5)  # in-place edit bumps the version: fresh copy
+    h2 = samplers._host_schedule(a)
+    assert h2 is not h1 and torch.equal(h2, a)
+    b = a.clone()
+    h3 = samplers._host_schedule(b)
+    assert h3 is not h2 and torch.equal(h3, b)
+    del b
+    assert torch.equal(samplers._host_schedule(a), a)  # cache slot now points at a dead tensor: recopied
+    assert samplers._host_schedule(a.double()).dtype == torch.float32
