@@ -11,9 +11,12 @@ One bench "step" = one 30-step sampling run over one batch. Metric: latent noise
 
 * value     : device-resident throughput. Every sampler step's kernels (one fused step launch; the
               first step also carries the batched Philox statistics of all 29 noise draws) are
-              bracketed by CUDA events on the launching stream; between sampler steps the
-              stub denoiser runs and L2 is flushed (256 MiB write), as a real UNet call would do.
-              ms_per_step = sum of those 30 event intervals, max over ranks.
+              bracketed by CUDA events on the launching stream; between sampler steps the stub
+              denoiser runs: FLUSH_PASSES x 256 MiB of zero-fill, which evicts L2 and occupies the GPU
+              for ~0.4 ms (a small fraction of a real UNet call), so the host enqueues the next step
+              while the device is still "in the UNet" and the intervals hold device time, not Python
+              launch latency. ms_per_step = sum of those 30 event intervals, max over ranks
+              (`per_rank_ms` lists every rank: mean run, mean first step).
 * e2e       : the same run through the public sampler function with HOST buffers: pinned x0 -> H2D,
               30 steps, result D2H, wall clock between device synchronisations.
 * roofline  : dominant kernel (sonar_step_fast_philox2_kernel): algorithmic bytes per launch
@@ -24,7 +27,10 @@ One bench "step" = one 30-step sampling run over one batch. Metric: latent noise
 * cpu_baseline : the CPU oracle port of the reference algorithm (oracle/sonar_oracle.py) on the host
               cores, same workload, bounded sample.
 * N > 1     : weak scaling by batch: every rank holds 8 latents of a global batch of 8N; the global
-              scale_noise statistics of all 29 draws are all-reduced ONCE per run (29x2 doubles, NCCL).
+              scale_noise statistics of all 29 draws are summed over ranks ONCE per run (29x2 doubles through
+              the NVLink peer mailboxes, inside the first sampler step). Before each run the ranks meet at a
+              host barrier and, at the run's first denoiser call, at a device-side rendezvous
+              (parallel.device_barrier) behind which every host keeps enqueueing.
 """
 
 from __future__ import annotations
