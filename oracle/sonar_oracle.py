@@ -11,7 +11,9 @@ directly against /root/reference when that tree is present). Exception -- the 2-
 transform: the reference delegates it to pytorch_wavelets, which is absent from the reference tree
 and from this image (no pinned version), so `dwt2_forward` / `dwt2_inverse` restate that library's
 published algorithm and their parity is UNPINNED (anchored only on perfect reconstruction,
-orthonormality and the equal-scales identity).
+orthonormality and the equal-scales identity). The same holds for the "periodization" mode used by the
+wavelet-filtered noise type (`_afb1d_per` / `_sfb1d_per`: perfect reconstruction incl. odd sizes, Parseval,
+the haar block transform). FreeU-Extreme (`freeu_*`) IS pinned: tests/golden/freeu.pt.
 
 Random inputs are always *injected*: generator functions take `draws`, the base tensors in the
 order the reference would draw them.
