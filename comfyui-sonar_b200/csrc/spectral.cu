@@ -331,18 +331,22 @@ spectral_plane_kernel(SpectralLaunch L) {
 //    this kernel fit one CTA per SM and sat at 49 % issue-slot utilisation with no eligible warp half of
 //    the time (ncu r01h); on 64x64 planes, where both forms fit, 4 CTAs of 256 threads ran 1.5x faster
 //    than 1 CTA of 1024.
-//  * Digit reversal costs nothing: the first inverse column stage gathers the global half spectrum
-//    straight into digit-reversed row slots (and permuted column slots), after which the column DIT, the
-//    Hermitian fold and the row DIT leave the plane in natural order for a coalesced store.
+//  * Digit reversal costs nothing, and there is no separate load or store pass: the block-length-R stage at
+//    the global-memory end of an axis does the permutation with its addresses. Spectrum input: the first
+//    inverse column stage (DIT) gathers whole rows of the global half spectrum into digit-reversed row slots
+//    (coalesced along k, gain applied on the fly) and the column transform ends in natural order; the
+//    Hermitian fold runs in natural order; the row transform is DIF and its last stage, run
+//    butterfly-fastest so that adjacent lanes touch adjacent float2 of the row, scales and stores straight
+//    to the global plane in natural order while reducing the output moments.
 // Rows use the half-length c2r trick: for Hermitian X of even length W, with M = W/2,
 //   Z[k] = (X[k] + conj X[M-k]) + i (X[k] - conj X[M-k]) e^{+2 pi i k / W},   k = 0..M-1
 //   z = sum_k Z[k] e^{+2 pi i k n / M}  ==>  x[2n] = Re z[n], x[2n+1] = Im z[n]
 // which also reproduces irfft2's treatment of the reference's NON-Hermitian input (the imaginary
 // parts of the k = 0 and k = M bins are dropped, nothing else of the upper half is read).
 // Real input (rfft2 front end: PowerFilterNoiseItem, OneF / GreenTest, FreeU-Extreme ffilter) runs the
-// same inverse-sign stages on conjugated data (FFT(z) = conj(IFFT(conj z))): packed rows -> row DIF ->
-// r2c unfold -> column DIF -> gain (.) conj -> the inverse path above. The plane still makes exactly one
-// trip from and one trip to HBM.
+// same inverse-sign stages on conjugated data (FFT(z) = conj(IFFT(conj z))): row DIT whose first stage gathers
+// the packed real rows from global memory -> r2c unfold -> column DIF -> gain (.) conj on the loads of the
+// column DIT -> the fold and row DIF above. The plane still makes exactly one trip from and one trip to HBM.
 // History: warp-per-transform kernel 237 issued instructions per output element at 90x160, radix 2..5
 // batched-lane kernel 158 (ncu r01g), ping-pong large-radix kernel 92 (ncu r01h).
 // =============================================================================================
