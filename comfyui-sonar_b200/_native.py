@@ -163,6 +163,24 @@ class SonarSpectralParams(ctypes.Structure):
     ]
 
 
+SPECTRAL_PLAN_MAX_STAGES = 16
+
+
+class SonarSpectralPlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("batched", c_int32),
+        ("group", c_int32),
+        ("threads", c_int32),
+        ("ctas_per_sm", c_int32),
+        ("grid", c_int64),
+        ("smem_bytes", c_int64),
+        ("n_col_stages", c_int32),
+        ("n_row_stages", c_int32),
+        ("col_radix", c_int32 * SPECTRAL_PLAN_MAX_STAGES),
+        ("row_radix", c_int32 * SPECTRAL_PLAN_MAX_STAGES),
+    ]
+
+
 class SonarWaveletFilters(ctypes.Structure):
     _fields_ = [
         ("length", c_int32),
@@ -313,6 +331,7 @@ SIGNATURES: dict[str, list] = {
     ],
     "sonar_spectral_scratch_bytes": [c_int, c_int],
     "sonar_spectral_filter_f32": [POINTER(SonarSpectralParams), c_void_p],
+    "sonar_spectral_plan": [c_int, c_int, c_int64, c_int, POINTER(SonarSpectralPlanInfo)],
     "sonar_dwt_coeff_len": [c_int, c_int],
     "sonar_dwt2_analysis": [POINTER(SonarDwtAnalysisParams), c_void_p],
     "sonar_dwt2_synthesis": [POINTER(SonarDwtSynthesisParams), c_void_p],

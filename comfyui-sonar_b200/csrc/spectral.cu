@@ -908,14 +908,16 @@ static size_t batched_smem_bytes(int H, int W, int group, const AxisPlan& col, c
   return (bytes + 15) & ~(size_t)15;
 }
 
-// 0 = launched; -1 = not applicable (caller falls back to the generic kernel); > 0 = CUDA error
-static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t stream) {
-  if ((p.W & 1) || p.W < 4 || p.H < 2) return -1;
-  if ((reinterpret_cast<uintptr_t>(p.out) & 7u) != 0) return -1;
-  if (p.in_real != nullptr && (reinterpret_cast<uintptr_t>(p.in_real) & 7u) != 0) return -1;
-  SpectralBatchedLaunch L;
+// Host-side planning of the batched kernel (no CUDA calls besides the cached device attributes): fills the
+// launch block and the launch geometry; false = not applicable (the generic kernel handles the call).
+static bool plan_spectral_batched(const SonarSpectralParams& p, SpectralBatchedLaunch* out, int* threads_out,
+                                  int* ctas_per_sm_out, int64_t* grid_out, size_t* smem_out) {
+  if ((p.W & 1) || p.W < 4 || p.H < 2) return false;
+  if ((reinterpret_cast<uintptr_t>(p.out) & 7u) != 0) return false;
+  if (p.in_real != nullptr && (reinterpret_cast<uintptr_t>(p.in_real) & 7u) != 0) return false;
+  SpectralBatchedLaunch& L = *out;
   L.p = p;
-  if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row, /*ascending=*/true)) return -1;
+  if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row, /*ascending=*/true)) return false;
   const int M = p.W / 2;
   L.wh = M + 1;
   L.pitch = L.wh | 1;
@@ -923,7 +925,7 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   L.scale = p.in_real != nullptr ? 0.5f * p.out_scale : p.out_scale;
   const DeviceInfo& di = device_info();
   const size_t budget = (size_t)di.max_smem_optin;
-  if (batched_smem_bytes(p.H, p.W, 1, L.col, L.row) > budget) return -1;
+  if (batched_smem_bytes(p.H, p.W, 1, L.col, L.row) > budget) return false;
   auto ctas_that_fit = [&](int group) {  // by shared memory (1 KB per CTA is reserved by the runtime), at most 4
     const size_t need = batched_smem_bytes(p.H, p.W, group, L.col, L.row) + 1024;
     const size_t n = (budget + 1024) / need;
@@ -942,23 +944,35 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   // index arithmetic: 16-bit slot tables, 32-bit magic division exact for w * d < 2^32
   const int64_t nbatch_max = group * (L.wh > p.H ? L.wh : p.H);
   const int64_t items_max = nbatch_max * ((p.H > M ? p.H : M) / 2);
-  if (items_max * nbatch_max >= (1ll << 32) || group * L.plane_elems >= (1 << 24)) return -1;
-  if (group * p.H * M * (int64_t)M >= (1ll << 32)) return -1;
+  if (items_max * nbatch_max >= (1ll << 32) || group * L.plane_elems >= (1 << 24)) return false;
+  if (group * p.H * M * (int64_t)M >= (1ll << 32)) return false;
   L.magic_row_nb = magic_of(L.row.nb[L.row.n_stages - 1]);
   L.magic_wh = magic_of(L.wh);
   L.magic_cols = magic_of(L.group * L.wh);
   L.magic_rows = magic_of(L.group * p.H);
-  const size_t smem = batched_smem_bytes(p.H, p.W, L.group, L.col, L.row);
-  auto kernel = p.in_real != nullptr ? spectral_batched_kernel<true> : spectral_batched_kernel<false>;
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return (int)err;
+  *smem_out = batched_smem_bytes(p.H, p.W, L.group, L.col, L.row);
   // the register file holds 1024 threads at the kernel's 64 registers: split them over the CTAs that fit
   int ctas_per_sm = ctas_that_fit(L.group);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  int threads = ctas_per_sm >= 4 ? 256 : ctas_per_sm == 3 ? 320 : kBatchedThreads;
+  *ctas_per_sm_out = ctas_per_sm;
+  *threads_out = ctas_per_sm >= 4 ? 256 : ctas_per_sm == 3 ? 320 : kBatchedThreads;
   int64_t grid = (p.planes + L.group - 1) / L.group;
   // persistent CTAs: the per-CTA tables (twiddles, slot maps) are built once and reused for every group
   if (grid > (int64_t)di.sm_count * ctas_per_sm) grid = (int64_t)di.sm_count * ctas_per_sm;
+  *grid_out = grid;
+  return true;
+}
+
+// 0 = launched; -1 = not applicable (caller falls back to the generic kernel); > 0 = CUDA error
+static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t stream) {
+  SpectralBatchedLaunch L;
+  int threads = 0, ctas_per_sm = 0;
+  int64_t grid = 0;
+  size_t smem = 0;
+  if (!plan_spectral_batched(p, &L, &threads, &ctas_per_sm, &grid, &smem)) return -1;
+  auto kernel = p.in_real != nullptr ? spectral_batched_kernel<true> : spectral_batched_kernel<false>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
   kernel<<<(unsigned)grid, threads, smem, stream>>>(L);
   err = cudaGetLastError();
   return err == cudaSuccess ? 0 : (int)err;
@@ -1017,6 +1031,37 @@ int64_t sonar_spectral_scratch_bytes(int H, int W) {
   const DeviceInfo& di = device_info();
   if (fixed + spec <= (size_t)di.max_smem_optin) return 0;
   return (int64_t)spec * di.sm_count * 2;
+}
+
+int sonar_spectral_plan(int H, int W, int64_t planes, int real_input, SonarSpectralPlanInfo* info) {
+  using namespace sonar;
+  if (info == nullptr || H <= 0 || W <= 0 || planes < 0) return (int)cudaErrorInvalidValue;
+  *info = SonarSpectralPlanInfo{};
+  SonarSpectralParams p = {};
+  float* const aligned = reinterpret_cast<float*>(uintptr_t{64});  // alignment matters to the plan, the address does not
+  p.out = aligned;
+  p.in_real = real_input ? aligned : nullptr;
+  p.in_spec = real_input ? nullptr : aligned;
+  p.planes = planes;
+  p.H = H;
+  p.W = W;
+  p.out_scale = 1.0f;
+  SpectralBatchedLaunch L;
+  int threads = 0, ctas_per_sm = 0;
+  int64_t grid = 0;
+  size_t smem = 0;
+  if (!plan_spectral_batched(p, &L, &threads, &ctas_per_sm, &grid, &smem)) return 0;  // generic kernel
+  info->batched = 1;
+  info->group = L.group;
+  info->threads = threads;
+  info->ctas_per_sm = ctas_per_sm;
+  info->grid = grid;
+  info->smem_bytes = (int64_t)smem;
+  info->n_col_stages = L.col.n_stages;
+  info->n_row_stages = L.row.n_stages;
+  for (int f = 0; f < L.col.n_stages && f < SONAR_SPECTRAL_PLAN_MAX_STAGES; ++f) info->col_radix[f] = L.col.radix[f];
+  for (int f = 0; f < L.row.n_stages && f < SONAR_SPECTRAL_PLAN_MAX_STAGES; ++f) info->row_radix[f] = L.row.radix[f];
+  return 0;
 }
 
 int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) {

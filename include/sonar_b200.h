@@ -332,6 +332,26 @@ typedef struct SonarSpectralParams {
 int64_t sonar_spectral_scratch_bytes(int H, int W);
 int sonar_spectral_filter_f32(const SonarSpectralParams* params_host, void* stream);
 
+/* Host-only query (no GPU work): how sonar_spectral_filter_f32 would run `planes` planes of (H, W).
+ * batched = 1: the in-place shared-memory kernel with `group` planes per CTA pass, `threads` threads per CTA,
+ * `ctas_per_sm` resident CTAs, `grid` CTAs, `smem_bytes` of dynamic shared memory and the listed radices for the
+ * column axis (length H) and the row axis (length W / 2), in stage order. batched = 0: the generic
+ * warp-per-transform kernel (odd W, other prime factors, planes too large for shared memory). */
+#define SONAR_SPECTRAL_PLAN_MAX_STAGES 16
+typedef struct SonarSpectralPlanInfo {
+  int32_t batched;
+  int32_t group;
+  int32_t threads;
+  int32_t ctas_per_sm;
+  int64_t grid;
+  int64_t smem_bytes;
+  int32_t n_col_stages;
+  int32_t n_row_stages;
+  int32_t col_radix[SONAR_SPECTRAL_PLAN_MAX_STAGES];
+  int32_t row_radix[SONAR_SPECTRAL_PLAN_MAX_STAGES];
+} SonarSpectralPlanInfo;
+int sonar_spectral_plan(int H, int W, int64_t planes, int real_input, SonarSpectralPlanInfo* info_host);
+
 /* ------------------------------------------------------------------------------------------------
  * 2-D DWT levels + wavelet-CFG combine.
  * replaces: Wavelet.forward / Wavelet.inverse               py/wavelet_functions.py:81-105
