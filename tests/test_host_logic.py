@@ -43,6 +43,16 @@ def test_struct_layouts_match_the_header(sb, tmp_path):
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     for n, size in zip(names, sizes):
         assert ctypes.sizeof(getattr(sb._native, n)) == size, n
+    # ... and every field sits at the offset the C compiler gives it (same names in the header and the mirror)
+    fields = [(n, f[0]) for n in names for f in getattr(sb._native, n)._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof({n}, {f}));' for n, f in fields)
+    src.write_text(
+        f'#include <stdio.h>\n#include <stddef.h>\n#include "{REPO}/include/sonar_b200.h"\nint main(void){{{body}return 0;}}\n',
+    )
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    offsets = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    for (n, f), off in zip(fields, offsets):
+        assert getattr(getattr(sb._native, n), f).offset == off, f"{n}.{f}"
 
 
 def test_no_cpu_fallback(sb):
