@@ -18,6 +18,20 @@ def _header_symbols() -> set[str]:
     return set(re.findall(r"^\s*(?:int|int64_t)\s+(sonar_\w+)\s*\(", text, flags=re.M))
 
 
+def test_ctypes_signatures_have_the_header_arity(sb):
+    """Every prototype in include/sonar_b200.h takes as many parameters as its ctypes argtypes entry, and the
+    functions that do not return an error code are the ones registered with their own restype."""
+    text = re.sub(r"/\*.*?\*/", "", (REPO / "include" / "sonar_b200.h").read_text(), flags=re.S)
+    protos = re.findall(r"^\s*(int|int64_t)\s+(sonar_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M | re.S)
+    assert len(protos) == len(sb._native.SIGNATURES)
+    for ret, name, args in protos:
+        args = args.strip()
+        n_args = 0 if args in ("", "void") else args.count(",") + 1
+        assert n_args == len(sb._native.SIGNATURES[name]), f"{name}: header has {n_args} parameters"
+        if ret == "int64_t":
+            assert name in sb._native.RESTYPES, f"{name} returns int64_t: needs a ctypes restype"
+
+
 def test_library_exports_every_declared_symbol(sb):
     lib = sb._native.load()
     declared = _header_symbols()
