@@ -1,0 +1,67 @@
+"""Static checks on the built library (cuobjdump, no GPU): register / stack budgets of the hot kernels and the
+design claim that tensor cores are deliberately unused. Guards against silent regressions such as a kernel
+tipping over its launch-bounds register budget and spilling (the 2-item unroll of the wavelet-CFG kernel
+cost 37 -> 43 us that way)."""
+from __future__ import annotations
+
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import REPO
+
+LIB = REPO / "comfyui-sonar_b200" / "libsonar_b200.so"
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or shutil.which("c++filt") is None,
+                                reason="needs the CUDA toolkit's cuobjdump")
+
+
+@pytest.fixture(scope="module")
+def usage(sb):
+    sb._native.load()  # builds the library if it is missing
+    out = subprocess.run(["cuobjdump", "-res-usage", str(LIB)], capture_output=True, text=True, check=True).stdout
+    rows = re.findall(r"Function (\S+):\s*\n?\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out)
+    assert len(rows) > 100, "no kernels parsed from cuobjdump -res-usage"
+    names = subprocess.run(["c++filt", *[r[0] for r in rows]], capture_output=True, text=True, check=True).stdout.splitlines()
+    return [(name, int(reg), int(stack), int(shared), int(local)) for name, (_, reg, stack, shared, local) in zip(names, rows)]
+
+
+def _select(usage, pattern):
+    hit = [u for u in usage if re.search(pattern, u[0])]
+    assert hit, f"no kernel matches {pattern}"
+    return hit
+
+
+def test_library_is_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", str(LIB)], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_register_and_stack_budgets(usage):
+    # single-wave step kernel for SDXL-sized draws: 32 registers so that 8 CTAs of 256 threads fit an SM
+    for name, reg, stack, _shared, _local in _select(usage, r"sonar_step_fast_philox2_kernel"):
+        assert reg <= 32 and stack == 0, (name, reg, stack)
+    for name, reg, stack, _shared, _local in _select(usage, r"sonar_step"):  # every specialised and generic variant
+        assert reg <= 48 and stack <= 8, (name, reg, stack)
+    # 1024 threads per SM at 64 registers: the shared-memory-resident kernels may spill a few words, not more
+    for name, reg, stack, _shared, _local in _select(usage, r"spectral_batched_kernel"):
+        assert reg <= 64 and stack <= 128, (name, reg, stack)
+    for name, reg, stack, _shared, _local in _select(usage, r"wcfg_fused_kernel<double, 4"):
+        assert reg <= 64 and stack <= 32, (name, reg, stack)
+    for name, reg, stack, _shared, _local in _select(usage, r"wcfg_fused_kernel"):
+        assert reg <= 64 and stack <= 192, (name, reg, stack)
+    # streaming kernels never touch local memory
+    for name, _reg, stack, _shared, _local in _select(usage, r"(blend_kernel|scale_noise_kernel|moments_kernel|freeu_apply_kernel|philox_fill)"):
+        assert stack == 0, (name, stack)
+    assert all(u[4] == 0 for u in usage), "no kernel declares static local memory"
+
+
+def test_tensor_cores_are_deliberately_unused():
+    """Nothing on this path is a dense contraction: no MMA instruction of any generation."""
+    sass = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
+    assert not re.search(r"\b(HMMA|IMMA|DMMA|QMMA|UTCHMMA|UTCQMMA|UTCMMA|HGMMA)\b", sass)
+    # ... while the kernels do use what the path needs: Philox wide multiplies, MUFU for Box-Muller, fp64 FMAs
+    for needle in ("IMAD.WIDE", "MUFU.RSQ", "DFMA"):
+        assert needle in sass, needle
