@@ -64,7 +64,7 @@ class SonarStepParams(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 2  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
+ABI_VERSION = 3  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
@@ -74,6 +74,7 @@ DWT_MAX_TAPS = 40
 
 
 FILL_BATCH_MAX = 16
+MIXER_SMALL_MAX = 8  # SONAR_MIXER_SMALL_MAX
 
 
 class SonarFillDesc(ctypes.Structure):
@@ -331,6 +332,7 @@ SIGNATURES: dict[str, list] = {
     ],
     "sonar_spectral_scratch_bytes": [c_int, c_int],
     "sonar_spectral_filter_f32": [POINTER(SonarSpectralParams), c_void_p],
+    "sonar_channel_mix_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p],
     "sonar_spectral_plan": [c_int, c_int, c_int64, c_int, POINTER(SonarSpectralPlanInfo)],
     "sonar_dwt_coeff_len": [c_int, c_int],
     "sonar_dwt2_analysis": [POINTER(SonarDwtAnalysisParams), c_void_p],

@@ -23,7 +23,7 @@ struct StepElem {
 
 __device__ __forceinline__ float update_history(const SonarStepParams& p, bool have_h, float h, float v) {
   // update_hist: history = v if history is None else blend(v * md_scale, h * hd_scale, hd_ratio)
-  return have_h ? blend<float>(p.history_blend, v * p.md_scale, h * p.hd_scale, p.hd_ratio) : v;
+  return have_h ? blend<float>(p.history_blend, __fmul_rn(v, p.md_scale), __fmul_rn(h, p.hd_scale), p.hd_ratio) : v;
 }
 
 // Per-launch constants derived once per thread from the parameter block.
@@ -52,7 +52,8 @@ __device__ __forceinline__ StepElem step_element(const SonarStepParams& p, const
 
   // ---- get_momentum_denoised ----
   float md = den;
-  if (!c.m_is_one && c.have_h_first_mix && c.denoised_mode) md = blend<float>(p.momentum_blend, h * p.sigma, den, p.momentum);
+  if (!c.m_is_one && c.have_h_first_mix && c.denoised_mode)
+    md = blend<float>(p.momentum_blend, __fmul_rn(h, p.sigma), den, p.momentum);
   if (p.history_active) {
     h = update_history(p, have_h, h, div_by(den, p.sigma, c.inv_sigma));
     have_h = true;
@@ -60,7 +61,7 @@ __device__ __forceinline__ StepElem step_element(const SonarStepParams& p, const
   const float den_eff = p.momentum_active ? md : den;
 
   // ---- derivative / DPM-Solver++ difference term ----
-  const float d = p.kind == SONAR_STEP_EULER ? div_by(x - den_eff, p.sigma, c.inv_sigma) : p.c0 * den_eff;
+  const float d = p.kind == SONAR_STEP_EULER ? div_by(__fsub_rn(x, den_eff), p.sigma, c.inv_sigma) : __fmul_rn(p.c0, den_eff);
 
   // ---- get_momentum_d ----
   float d_out = d;
@@ -74,8 +75,9 @@ __device__ __forceinline__ StepElem step_element(const SonarStepParams& p, const
   }
 
   StepElem r;
-  r.x_out = p.kind == SONAR_STEP_EULER ? d_out * p.c0 + x : p.c1 * x - d_out;
-  if (p.noise_kind != SONAR_NOISE_NONE) r.x_out = r.x_out + noise * p.noise_scale;
+  // (d * dt).add_(x)  /  ((sigma_fn(s) / sigma_fn(t)) * x).sub_(d): every eager op rounds
+  r.x_out = p.kind == SONAR_STEP_EULER ? __fadd_rn(__fmul_rn(d_out, p.c0), x) : __fsub_rn(__fmul_rn(p.c1, x), d_out);
+  if (p.noise_kind != SONAR_NOISE_NONE) r.x_out = __fadd_rn(r.x_out, __fmul_rn(noise, p.noise_scale));
   r.h_out = h;
   return r;
 }
@@ -98,9 +100,9 @@ __device__ __forceinline__ NoiseNorm make_noise_norm(const NormDecision& d, floa
 }
 
 __device__ __forceinline__ float norm_noise_value(float v, const NoiseNorm& n) {
-  if (n.sub_mean) v -= n.mean;
+  if (n.sub_mean) v = __fsub_rn(v, n.mean);
   if (n.div_std) v = div_by(v, n.std, n.inv_std);
-  return v * n.factor;
+  return __fmul_rn(v, n.factor);
 }
 
 // ---- contiguous float4 variant (no noise / tensor noise) ----
@@ -188,9 +190,9 @@ struct LerpW {
 
 __device__ __forceinline__ LerpW make_lerp(float w) { return LerpW{w, 1.0f - w, fabsf(w) < 0.5f}; }
 
-__device__ __forceinline__ float lerp_u(float a, float b, const LerpW& l) {
-  const float d = b - a;
-  return l.small ? a + l.w * d : b - d * l.omw;
+__device__ __forceinline__ float lerp_u(float a, float b, const LerpW& l) {  // == torch_lerp (common.cuh)
+  const float d = __fsub_rn(b, a);
+  return l.small ? fmaf(l.w, d, a) : fmaf(-d, l.omw, b);
 }
 
 struct FastConsts {
@@ -216,15 +218,16 @@ template <int KIND, bool NEW_MODE, bool HAVE_H, bool NOISE>
 __device__ __forceinline__ StepElem step_element_fast(const FastConsts& c, float x, float den, float h, float noise) {
   // get_momentum_denoised: history <- update(denoised / sigma)
   const float den_s = div_by(den, c.sigma, c.inv_sigma);
-  const float h1 = HAVE_H ? lerp_u(den_s * c.md_scale, h * c.hd_scale, c.hist) : den_s;
+  const float h1 = HAVE_H ? lerp_u(__fmul_rn(den_s, c.md_scale), __fmul_rn(h, c.hd_scale), c.hist) : den_s;
   // derivative (Euler) or DPM-Solver++ difference term
-  const float d = KIND == SONAR_STEP_EULER ? div_by(x - den, c.sigma, c.inv_sigma) : c.c0 * den;
+  const float d = KIND == SONAR_STEP_EULER ? div_by(__fsub_rn(x, den), c.sigma, c.inv_sigma) : __fmul_rn(c.c0, den);
   // get_momentum_d: mix with the history, second history update
   const float mom_d = lerp_u(h1, d, c.mom);
   StepElem r;
-  r.h_out = lerp_u((NEW_MODE ? d : mom_d) * c.md_scale, h1 * c.hd_scale, c.hist);
-  r.x_out = KIND == SONAR_STEP_EULER ? mom_d * c.c0 + x : c.c1 * x - mom_d;
-  if (NOISE) r.x_out = r.x_out + noise * c.noise_scale;
+  r.h_out = lerp_u(__fmul_rn(NEW_MODE ? d : mom_d, c.md_scale), __fmul_rn(h1, c.hd_scale), c.hist);
+  // (d * dt).add_(x)  /  (c1 * x).sub_(d)  then  + noise * (s_noise * sigma_up): every eager op rounds
+  r.x_out = KIND == SONAR_STEP_EULER ? __fadd_rn(__fmul_rn(mom_d, c.c0), x) : __fsub_rn(__fmul_rn(c.c1, x), mom_d);
+  if (NOISE) r.x_out = __fadd_rn(r.x_out, __fmul_rn(noise, c.noise_scale));
   return r;
 }
 

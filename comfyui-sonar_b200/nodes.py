@@ -316,6 +316,42 @@ class SonarCompositeNoiseNode(SonarCustomNoiseNodeBase):
         )
 
 
+class SonarGuidedNoiseNode(SonarCustomNoiseNodeBase):
+    DESCRIPTION = "Custom noise type that mixes a references with another custom noise generator to guide the generation."
+    WITH_RESCALE = WITH_CHAIN = False
+    REQUIRED = {
+        "latent": ("LATENT", {"tooltip": "Latent to use for guidance."}),
+        "method": f_choice(("euler", "linear"), "euler"),
+        "guidance_factor": f_float(0.0125, min=-100.0, max=100.0),
+        "normalize_noise": f_choice(TRISTATE, "default"),
+        "normalize_result": f_choice(TRISTATE, "default"),
+        "normalize_ref": f_bool(True),
+    }
+    OPTIONAL = {"sonar_custom_noise": f_noise("Optional custom noise input to combine with the guidance.")}
+
+    @classmethod
+    def get_item_class(cls):
+        return noise.GuidedNoise
+
+    def go(self, *, factor, latent, normalize_noise, normalize_result, normalize_ref=True, method="euler",
+           guidance_factor=0.5, sonar_custom_noise=None):  # fmt: skip
+        from .samplers import SonarGuidanceMixin
+
+        # the reference standardises the latent where it lives (CPU); this package has no CPU path, so the one-off
+        # setup runs on the compute device (nodes/noise_filters.py:302-308)
+        samples = latent["samples"].to(device=model_management.get_torch_device(), dtype=torch.float32, copy=True)
+        ref_latent = hostutil.scale_noise(SonarGuidanceMixin.prepare_ref_latent(samples), normalized=normalize_ref)
+        return super().go(
+            factor,
+            ref_latent=ref_latent,
+            guidance_factor=guidance_factor,
+            noise=sonar_custom_noise.clone() if sonar_custom_noise is not None else None,
+            method=method,
+            normalize_noise=tristate(normalize_noise),
+            normalize_result=tristate(normalize_result),
+        )
+
+
 class SonarBlendedNoiseNode(SonarCustomNoiseNodeBase):
     DESCRIPTION = "Custom noise type that allows blending two other noise items."
     REQUIRED = {
@@ -1103,6 +1139,7 @@ NODE_CLASS_MAPPINGS = {
     "SonarScheduledNoise": SonarScheduledNoiseNode,
     "SonarCompositeNoise": SonarCompositeNoiseNode,
     "SonarBlendedNoise": SonarBlendedNoiseNode,
+    "SonarGuidedNoise": SonarGuidedNoiseNode,
     "SonarCustomNoiseParameters": SonarCustomNoiseParametersNode,
     "SonarWaveletFilteredNoise": SonarWaveletFilteredNoiseNode,
     "SonarPowerNoise": SonarPowerNoiseNode,

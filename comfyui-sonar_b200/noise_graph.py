@@ -585,6 +585,58 @@ class CustomNoiseParametersNoise(_ChildHolder):
         return noise_sampler
 
 
+class GuidedNoise(_ChildHolder):
+    """A child chain's noise (or zeros) pulled towards a reference latent with the samplers' guidance functions
+    (reference py/noise.py:536-623): guidance_linear / guidance_euler on the RAW reference
+    latent, shifted to the per-item mean / std of the noise ("linear") or of the latent the sampler was built for
+    ("euler") when a child chain is attached. Two launches per sample on `csrc/guidance.cu`."""
+
+    child_keys = ("noise", "ref_latent")
+
+    def __init__(self, factor, *, guidance_factor, ref_latent, method, normalize_noise, normalize_result, noise=None):
+        super().__init__(
+            factor,
+            normalize_noise=normalize_noise,
+            normalize_result=normalize_result,
+            ref_latent=ref_latent.clone(),
+            noise=noise.clone() if noise is not None else None,
+            method=method,
+            guidance_factor=guidance_factor,
+        )
+
+    def make_noise_sampler(self, x, *args, normalized=True, **kwargs):
+        from .samplers import SonarGuidanceMixin  # (samplers imports this module)
+
+        factor, guidance_factor = self.factor, self.guidance_factor
+        normalize_noise, normalize_result = (self.get_normalize(f"normalize_{k}", normalized) for k in ("noise", "result"))
+        ns = None if self.noise is None else self.noise.make_noise_sampler(x, *args, normalized=normalize_noise, **kwargs)
+        ref_latent = self.ref_latent.to(x, copy=True)
+        if ref_latent.shape[-2:] != x.shape[-2:]:  # setup, once per sampler
+            ref_latent = torch.nn.functional.interpolate(ref_latent, size=x.shape[-2:], mode="bicubic", align_corners=True)
+        ref_latent = ref_latent.to(torch.float32).contiguous()
+        latent = x.to(torch.float32).contiguous()
+        do_shift = ns is not None
+
+        def base(s, sn):
+            return torch.zeros_like(latent) if ns is None else ns(s, sn).to(torch.float32).contiguous()
+
+        if self.method == "linear":
+
+            def noise_sampler(s, sn):
+                guided = SonarGuidanceMixin.guidance_linear(base(s, sn), ref_latent, guidance_factor, do_shift=do_shift)
+                return scale_noise(guided, factor, normalized=normalize_result)
+
+        elif self.method == "euler":
+
+            def noise_sampler(s, sn):
+                guided = SonarGuidanceMixin.guidance_euler(s, sn, base(s, sn), latent, ref_latent, guidance_factor, do_shift=do_shift)
+                return scale_noise(guided, factor, normalized=normalize_result)
+
+        else:
+            raise ValueError("Bad method")
+        return noise_sampler
+
+
 def _out_of_scope_item(name: str) -> type:
     def make_noise_sampler(self, *args, **kwargs):
         raise NotImplementedError(
@@ -596,7 +648,7 @@ def _out_of_scope_item(name: str) -> type:
 
 
 for _name in (
-    "GuidedNoise", "ModulatedNoise", "RandomNoise", "ChannelNoise", "RippleFilteredNoise", "NormalizeToScaleNoise",
+    "ModulatedNoise", "RandomNoise", "ChannelNoise", "RippleFilteredNoise", "NormalizeToScaleNoise",
     "ResizedNoise", "ScatternetFilteredNoise", "LatentOperationFilteredNoise",
     "BlendFilterNoise", "QuantileFilteredNoise", "PerDimNoise", "ShuffledNoise", "PatternBreakNoise", "BlehOpsNoise",
     "AdvancedDistroNoise", "AdvancedCollatzNoise", "AdvancedWaveletNoise", "AdvancedVoronoiNoise",

@@ -670,6 +670,30 @@ def spectral_filter(
     return _sums_written(out, slot)
 
 
+def channel_mix(noise: torch.Tensor, mixer: torch.Tensor, mixer_host: torch.Tensor | None = None) -> torch.Tensor:
+    """out[b, c] = sum_k mixer[c, k] * noise[b, k] per pixel (ChannelMixer.apply); the moments of the result ride along."""
+    _f32(noise, "noise")
+    _f32(mixer, "mixer")
+    if noise.ndim != 4:
+        raise ValueError("channel_mix expects a (B, C, H, W) tensor")
+    batch, channels, height, width = noise.shape
+    if tuple(mixer.shape) != (channels, channels):
+        raise ValueError("Channel count mismatch")
+    out = torch.empty_like(noise)
+    lib, stream = _prepare(noise, mixer, out)
+    host_ptr = None
+    if mixer_host is not None and channels <= _native.MIXER_SMALL_MAX:
+        if mixer_host.dtype != torch.float32 or not mixer_host.is_contiguous() or mixer_host.is_cuda:
+            raise ValueError("mixer_host must be a contiguous float32 CPU tensor")
+        host_ptr = ctypes.c_void_p(mixer_host.data_ptr())
+    slot, slot_ptr, clear_ptr = sums_slot(out.device)
+    _launch(
+        "sonar_channel_mix_f32", lib.sonar_channel_mix_f32,
+        _ptr(noise), _ptr(out), _ptr(mixer), host_ptr, batch, channels, height * width, slot_ptr, clear_ptr, stream,
+    )  # fmt: skip
+    return _sums_written(out, slot)
+
+
 # --------------------------------------------------------------------------------------------
 # FreeU-Extreme epilogue (reference py/nodes/freeu_extreme.py:183-227)
 # --------------------------------------------------------------------------------------------

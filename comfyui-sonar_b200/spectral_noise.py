@@ -47,6 +47,8 @@ class ChannelMixer:
 
     def to(self, *args, **kwargs):
         if self.mixer is not None:
+            if self.mixer.device.type == "cpu":
+                self.mixer_host = self.mixer.to(torch.float32).contiguous()  # small matrices travel by value
             self.mixer = self.mixer.to(*args, **kwargs)
         return self
 
@@ -58,9 +60,11 @@ class ChannelMixer:
             raise ValueError("Channel count mismatch")
         if self.is_identity:
             return noise  # I @ noise is an exact copy
-        # a genuine (small) dense contraction: plain library GEMM
-        mixed = self.mixer @ noise.swapaxes(0, 1).reshape(c, -1)
-        return mixed.reshape(c, b, h, w).swapaxes(1, 0).contiguous()
+        # mixer @ noise.swapaxes(0, 1).reshape(c, -1), un-swapped: one kernel on the (B, C, H, W) layout
+        mixer = self.mixer
+        if mixer.dtype != torch.float32 or not mixer.is_contiguous():
+            mixer = self.mixer = mixer.to(torch.float32).contiguous()
+        return ops.channel_mix(noise.reshape(b, c, h, w).contiguous(), mixer, getattr(self, "mixer_host", None))
 
     __call__ = apply
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 2
+#define SONAR_B200_ABI_VERSION 3
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
@@ -331,6 +331,16 @@ typedef struct SonarSpectralParams {
 
 int64_t sonar_spectral_scratch_bytes(int H, int W);
 int sonar_spectral_filter_f32(const SonarSpectralParams* params_host, void* stream);
+
+/* Channel-correlation mixer of the power-noise family: out[b, c, p] = sum_k mixer[c, k] * in[b, k, p] for a dense
+ * (batch, channels, hw) tensor; `mixer` is the (channels x channels) row-major matrix ON THE DEVICE.
+ * replaces: ChannelMixer.apply                             py/nodes/powernoise.py:94-101
+ * channels <= SONAR_MIXER_SMALL_MAX and mixer_host != NULL (the same matrix in host memory): per-pixel mat-vec
+ * with the matrix passed by value; otherwise a tiled fp32 GEMM. `in` must not alias `out`.
+ * sums / sums_clear: as SonarSpectralParams (moments of the output accumulated into sums; may be NULL). */
+#define SONAR_MIXER_SMALL_MAX 8
+int sonar_channel_mix_f32(const float* in, float* out, const float* mixer, const float* mixer_host, int64_t batch,
+                          int32_t channels, int64_t hw, double* sums, double* sums_clear, void* stream);
 
 /* Host-only query (no GPU work): how sonar_spectral_filter_f32 would run `planes` planes of (H, W).
  * batched = 1: the in-place shared-memory kernel with `group` planes per CTA pass, `threads` threads per CTA,

@@ -384,11 +384,37 @@ def power_filter(
     return op
 
 
-def power_noise(draws, shape, filter_rfft, *, factor=1.0, normalized=True, spectral_input=True):
-    """PowerNoiseItem sampler :355-366 with common_mode == 0 (identity ChannelMixer)."""
+def channel_mixer(channels: int, common_mode: float, channel_correlation) -> torch.Tensor:
+    """ChannelMixer.build py/nodes/powernoise.py:63-88: unit-row-norm factor L*sqrt(D) of the LDL decomposition of
+    the channel correlation matrix (off-diagonals = given correlations x common_mode, missing ones = common_mode)."""
+    if isinstance(channel_correlation, str):
+        channel_correlation = torch.tensor([float(v) for v in channel_correlation.split(",") if v.strip()], dtype=torch.float)
+    pairs = channels * (channels - 1) // 2
+    given = channel_correlation[:pairs]
+    corr = torch.cat((given * common_mode, torch.full((pairs - given.numel(),), common_mode)))
+    m = torch.eye(channels).index_put_(tuple(torch.tril_indices(channels, channels, offset=-1)), corr)
+    m += m.tril(-1).mT
+    m = torch.linalg.ldl_factor(m).LD
+    diag = torch.diagonal_copy(m)
+    torch.diagonal(m)[:] = 1.0
+    m *= diag.clamp_min(0).sqrt().unsqueeze(0)
+    m /= m.norm(dim=1, keepdim=True)
+    return m
+
+
+def channel_mix(noise: torch.Tensor, mixer: torch.Tensor) -> torch.Tensor:
+    """ChannelMixer.apply :94-101: out[b, c] = sum_c' mixer[c, c'] noise[b, c'] per pixel."""
+    b, c, h, w = noise.shape
+    return (mixer @ noise.swapaxes(0, 1).reshape(c, -1)).reshape(c, b, h, w).swapaxes(1, 0)
+
+
+def power_noise(draws, shape, filter_rfft, *, factor=1.0, normalized=True, spectral_input=True, mixer=None):
+    """PowerNoiseItem sampler :355-366; `mixer` = channel_mixer(...) or None (identity, common_mode == 0)."""
     drawn = _next(draws)
     spec = drawn if spectral_input else torch.fft.rfft2(drawn, norm="ortho")
     noise = torch.fft.irfft2(spec.mul_(filter_rfft), s=shape[-2:], norm="ortho")
+    if mixer is not None:
+        noise = channel_mix(noise, mixer)
     return scale_noise(noise, factor, normalized=normalized)
 
 
@@ -446,17 +472,39 @@ def guidance_shift(t: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     return (ref * t.std(dim=dim, keepdim=True)).add_(t.mean(dim=dim, keepdim=True))
 
 
-def guidance_linear(x, ref, factor, blend=None):
+def guidance_linear(x, ref, factor, blend=None, do_shift=True):
     """:400-411"""
-    return (blend or torch_lerp)(x, guidance_shift(x, ref), factor)
+    return (blend or torch_lerp)(x, guidance_shift(x, ref) if do_shift else ref, factor)
 
 
-def guidance_euler(sigma, sigma_next, x, denoised, ref, factor):
+def guidance_euler(sigma, sigma_next, x, denoised, ref, factor, do_shift=True):
     """:380-398 -- an Euler step of size (sigma_next - sigma) * factor towards the shifted reference."""
     if torch.equal(torch.as_tensor(sigma), torch.as_tensor(sigma_next)):
-        return guidance_linear(x, ref, factor)
-    d = (x - guidance_shift(denoised, ref)) / sigma
+        return guidance_linear(x, ref, factor, do_shift=do_shift)
+    d = (x - (guidance_shift(denoised, ref) if do_shift else ref)) / sigma
     return (d * ((sigma_next - sigma) * factor)).add_(x)
+
+
+def guided_noise(draws, x, ref_latent, *, method, guidance_factor, factor=1.0, has_noise=True, sigma=None, sigma_next=None,
+                 normalize_noise=True, normalize_result=True):
+    """GuidedNoise.make_noise_sampler py/noise.py:565-623 around a Gaussian child chain: the child noise (or zeros)
+    is pulled towards the RAW reference latent (bicubic-resized to the latent when needed); method "euler" uses the
+    latent `x` the sampler was built for as the `denoised` argument (:608-616)."""
+    ref = ref_latent.to(x, copy=True)
+    if ref.shape[-2:] != x.shape[-2:]:
+        ref = F.interpolate(ref, size=x.shape[-2:], mode="bicubic", align_corners=True)
+    if has_noise:
+        # child chain (normalized=normalize_noise): one Gaussian item, summed, normalised once at the chain level
+        noise = scale_noise(_next(draws).clone(), 1.0, normalized=normalize_noise)
+    else:
+        noise = torch.zeros_like(x)
+    if method == "linear":
+        out = guidance_linear(noise, ref, guidance_factor, do_shift=has_noise)
+    elif method == "euler":
+        out = guidance_euler(sigma, sigma_next, noise, x, ref, guidance_factor, do_shift=has_noise)
+    else:
+        raise ValueError("Bad method")
+    return scale_noise(out, factor, normalized=normalize_result)
 
 
 class SonarOracle:

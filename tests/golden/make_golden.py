@@ -456,13 +456,137 @@ def gen_freeu(ref) -> None:
     save("freeu", out)
 
 
+def gen_round2(ref) -> None:
+    """Round-2 fixtures: (1) north-star config 5 as specified, scaled down -- frames_to_channels power noise as
+    the custom noise of sonar_dpmpp_sde on a 5-D video latent; (2) SonarPowerNoise with a non-identity
+    ChannelMixer (common_mode != 0, non-unit channel_correlation), incl. the filter-noise form and a
+    frames_to_channels latent with a large channel count; (3) GuidedNoise (py/noise.py:565-623)."""
+    noise, pn, sonar = ref.py.noise, ref.py.nodes.powernoise, ref.py.sonar
+    defaults = {
+        "time_brownian": False, "alpha": 0.0, "max_freq": 0.7071, "min_freq": 0.0, "stretch": 1.0, "rotate": 0.0,
+        "pnorm": 2.0, "mix": 1.0, "common_mode": 0.0, "channel_correlation": "1, 1, 1, 1, 1, 1",
+    }  # fmt: skip
+
+    def power_chain(**kw):
+        chain = noise.CustomNoiseChain()
+        chain.add(pn.PowerNoiseItem(1.0, **(defaults | kw)))
+        return chain
+
+    def video_chain(**kw):
+        item = noise.CustomNoiseParametersNoise(
+            1.0, noise=power_chain(**kw), normalize=None, override_device=None, override_dtype=None,
+            frames_to_channels=True, ensure_square_aspect_ratio=False, fix_invalid=False, rng_mode="default",
+            rng_offset_mode="disabled", rng_state_offset=0,
+        )  # fmt: skip
+        chain = noise.CustomNoiseChain()
+        chain.add(item)
+        return chain
+
+    out = {"c5": {}, "mixer": {}, "guided": {}}
+    # ---- (1) config 5: CustomNoiseParametersNoise(frames_to_channels) o PowerNoise(alpha=1) -> sonar_dpmpp_sde ----
+    sigmas = torch.cat((torch.linspace(14.6, 0.03, 5), torch.zeros(1)))
+    torch.manual_seed(700)
+    x0 = torch.randn(2, 3, 4, 18, 20) * sigmas[0]
+    for vname, params in (("default", {}), ("classic", {"momentum_mode": "classic"})):
+        steps = []
+        torch.manual_seed(701)
+        with record_draws() as draws:
+            result = sonar.SonarDPMPPSDE.sampler(
+                stub_model, x0.clone(), sigmas, extra_args={"seed": 0}, disable=True,
+                sonar_params=params | {"custom_noise": video_chain(alpha=1.0)},
+                callback=lambda d: steps.append(d["x"].clone()), eta=1.0, s_noise=1.0,
+            )  # fmt: skip
+        out["c5"][vname] = {"params": params, "draws": draws, "out": result.clone(), "steps": torch.stack(steps)}
+    out["c5"]["x0"], out["c5"]["sigmas"] = x0, sigmas
+
+    # ---- (2) non-identity ChannelMixer ----
+    variants = {
+        "c4_common": ((2, 4, 16, 20), {"alpha": 1.0, "common_mode": 0.3}),
+        "c4_corr": ((2, 4, 18, 16), {"alpha": 0.5, "common_mode": 0.5, "channel_correlation": "0.9, 0.5, -0.3, 0.2, 0.7, 1"}),
+        "c3_neg": ((1, 3, 16, 16), {"alpha": 0.0, "common_mode": -0.25, "channel_correlation": "1, 0.5"}),
+        "c16_short_corr": ((2, 16, 12, 16), {"alpha": 1.0, "common_mode": 0.2, "channel_correlation": "1, 0.3, 0.8"}),
+    }
+    for i, (name, (shape, kw)) in enumerate(variants.items()):
+        torch.manual_seed(710 + i)
+        x = torch.zeros(shape)
+        with record_draws() as draws:
+            result = power_chain(**kw).make_noise_sampler(x, None, None, seed=0, cpu=True, normalized=True)(None, None)
+        item = pn.PowerNoiseItem(1.0, **(defaults | kw))
+        mixer = pn.ChannelMixer(shape[1], item.common_mode, item.channel_correlation).mixer
+        out["mixer"][name] = {"shape": shape, "params": kw, "draws": draws, "mixer": mixer.clone(), "out": result.clone()}
+    # video latent: 12 x 11 = 132 folded channels, the (C x C) @ (C x B*H*W) product is a real GEMM
+    torch.manual_seed(720)
+    x5 = torch.zeros(2, 12, 11, 10, 12)
+    kw = {"alpha": 1.0, "common_mode": 0.1, "channel_correlation": "1, 0.5, 0.25"}
+    with record_draws() as draws:
+        result = video_chain(**kw).make_noise_sampler(x5, None, None, seed=0, cpu=True, normalized=True)(None, None)
+    out["mixer"]["video_c132"] = {"shape": tuple(x5.shape), "params": kw, "draws": draws, "out": result.clone()}
+    # the rfft2 front end (PowerFilterNoiseItem) with a mixer
+    torch.manual_seed(721)
+    x = torch.zeros(2, 4, 20, 24)
+    inner = noise.CustomNoiseChain()
+    inner.add(noise.CustomNoiseItem(1.0, noise_type="gaussian"))
+    item = pn.PowerFilterNoiseItem(
+        1.0, noise=inner, normalize_noise=None, normalize_result=None, power_filter=pn.PowerFilter(alpha=1.0),
+        mix=1.0, common_mode=0.4, channel_correlation="1,-0.5,0.5,1,1,0.2", time_brownian=True, filter_norm_factor=1.0,
+    )  # fmt: skip
+    chain = noise.CustomNoiseChain()
+    chain.add(item)
+    with record_draws() as draws:
+        result = chain.make_noise_sampler(x, None, None, seed=0, cpu=True, normalized=True)(None, None)
+    out["mixer"]["filter_noise_c4"] = {"shape": tuple(x.shape), "draws": draws, "out": result.clone()}
+
+    # ---- (3) GuidedNoise ----
+    def gaussian_chain():
+        c = noise.CustomNoiseChain()
+        c.add(noise.CustomNoiseItem(1.0, noise_type="gaussian"))
+        return c
+
+    shape = (3, 4, 12, 16)
+    torch.manual_seed(730)
+    x = torch.randn(shape) * 3.0 + 0.5
+    ref_same = torch.randn(shape) * 2.0 - 0.3
+    ref_one = torch.randn(1, 4, 12, 16) + 1.0
+    ref_small = torch.randn(3, 4, 6, 8)
+    gcases = {
+        "linear": {"method": "linear", "guidance_factor": 0.3, "ref": ref_same, "noise": True},
+        "linear_one_ref": {"method": "linear", "guidance_factor": 0.1, "ref": ref_one, "noise": True, "factor": 0.5},
+        "linear_no_noise": {"method": "linear", "guidance_factor": 0.25, "ref": ref_same, "noise": False},
+        "linear_resized_ref": {"method": "linear", "guidance_factor": 0.2, "ref": ref_small, "noise": True},
+        "euler": {"method": "euler", "guidance_factor": 0.2, "ref": ref_same, "noise": True},
+        "euler_no_noise": {"method": "euler", "guidance_factor": 0.4, "ref": ref_one, "noise": False},
+        "euler_equal_sigmas": {"method": "euler", "guidance_factor": 0.2, "ref": ref_same, "noise": True, "sigmas": (3.0, 3.0)},
+        "linear_unnormalized": {"method": "linear", "guidance_factor": 0.3, "ref": ref_same, "noise": True,
+                                "normalize_noise": False, "normalize_result": False},
+    }  # fmt: skip
+    for i, (name, kw) in enumerate(gcases.items()):
+        torch.manual_seed(740 + i)
+        item = noise.GuidedNoise(
+            kw.get("factor", 1.0), guidance_factor=kw["guidance_factor"], ref_latent=kw["ref"].clone(), method=kw["method"],
+            normalize_noise=kw.get("normalize_noise"), normalize_result=kw.get("normalize_result"),
+            noise=gaussian_chain() if kw["noise"] else None,
+        )  # fmt: skip
+        chain = noise.CustomNoiseChain()
+        chain.add(item)
+        s, sn = kw.get("sigmas", (5.0, 3.5))
+        with record_draws() as draws:
+            ns = chain.make_noise_sampler(x.clone(), torch.tensor(0.03), torch.tensor(14.6), seed=0, cpu=True, normalized=True)
+            result = ns(torch.tensor(s), torch.tensor(sn))
+        out["guided"][name] = {
+            "config": {k: v for k, v in kw.items() if k != "ref"}, "ref": kw["ref"].clone(), "sigmas": (s, sn),
+            "draws": draws, "out": result.clone(),
+        }  # fmt: skip
+    out["guided"]["x"] = x
+    save("round2", out)
+
+
 IN_SCOPE_NODES = (
     "SamplerSonarEuler", "SamplerSonarEulerA", "SamplerSonarDPMPPSDE", "SonarGuidanceConfig", "SonarCustomNoise",
     "SonarCustomNoiseAdv", "SonarPowerNoise", "SonarPowerFilterNoise", "SonarPowerFilter", "SonarAdvancedPyramidNoise",
     "SonarAdvanced1fNoise", "SonarAdvancedPowerLawNoise", "SonarCompositeNoise", "SonarScheduledNoise",
     "SonarBlendedNoise", "SonarRepeatedNoise", "SonarCustomNoiseParameters", "SONAR_CUSTOM_NOISE to NOISE",
     "SamplerConfigOverride", "SonarWaveletCFG", "NoisyLatentLike", "FreeUExtremeConfig", "FreeUExtreme",
-    "SonarWaveletFilteredNoise",
+    "SonarWaveletFilteredNoise", "SonarGuidedNoise",
 )  # fmt: skip
 
 
@@ -508,6 +632,7 @@ def main() -> None:
     gen_guidance(ref)
     gen_host_logic(ref)
     gen_freeu(ref)
+    gen_round2(ref)
     gen_node_schemas(ref)
 
 

@@ -146,4 +146,4 @@ def test_gpu_freeu_unet_sized_activation(sb, cuda):
     )
     got = cfg.apply(0, x.to(cuda), {})
     want = orc.freeu_apply(x, filter={"alpha": 1.0}, filter_norm=1.0, **kw)
-    assert_close(got, want, what="unet stage 1", atol=2e-5)
+    assert_close(got, want, what="unet stage 1")

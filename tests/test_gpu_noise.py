@@ -114,13 +114,13 @@ def test_spectral_kernel_vs_torch_fft(sb, cuda, hw):
     mask = torch.rand(h, w // 2 + 1) + 0.5
     want = torch.fft.irfft2(spec * mask, s=(h, w), norm="ortho")
     got = sb.ops.spectral_filter(spectrum=spec.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / math.sqrt(h * w))
-    assert_close(got, want, what=f"irfft2 {hw}", atol=2e-5)
+    assert_close(got, want, what=f"irfft2 {hw}")
     real = torch.randn(3, h, w)
     want = torch.fft.irfft2(torch.fft.rfft2(real, norm="ortho") * mask, s=(h, w), norm="ortho")
     got = sb.ops.spectral_filter(real=real.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / (h * w))
-    assert_close(got, want, what=f"rfft2-irfft2 {hw}", atol=2e-5)
+    assert_close(got, want, what=f"rfft2-irfft2 {hw}")
     ident = sb.ops.spectral_filter(real=real.to(cuda), mask=None, hw=hw, out_scale=1.0 / (h * w))
-    assert_close(ident, real, what=f"identity {hw}", atol=2e-5)
+    assert_close(ident, real, what=f"identity {hw}")
 
 
 @pytest.mark.parametrize(
@@ -136,11 +136,11 @@ def test_spectral_batched_groups_and_radices(sb, cuda, hw, planes):
     mask = torch.rand(h, w // 2 + 1) + 0.5
     want = torch.fft.irfft2(spec * mask, s=(h, w), norm="ortho")
     got = sb.ops.spectral_filter(spectrum=spec.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / math.sqrt(h * w))
-    assert_close(got, want, what=f"irfft2 {hw} x{planes}", atol=2e-5)
+    assert_close(got, want, what=f"irfft2 {hw} x{planes}")
     real = torch.randn(planes, h, w)
     want = torch.fft.irfft2(torch.fft.rfft2(real, norm="ortho") * mask, s=(h, w), norm="ortho")
     got = sb.ops.spectral_filter(real=real.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / (h * w))
-    assert_close(got, want, what=f"rfft2-irfft2 {hw} x{planes}", atol=2e-5)
+    assert_close(got, want, what=f"rfft2-irfft2 {hw} x{planes}")
     sums = got._sonar_sums if hasattr(got, "_sonar_sums") else None
     if sums is not None:
         torch.cuda.synchronize()

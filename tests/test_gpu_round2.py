@@ -1,0 +1,172 @@
+"""CUDA parity for the round-2 fixtures recorded from the unmodified reference: north-star config 5 as specified
+(frames_to_channels power noise as the custom noise of sonar_dpmpp_sde), the non-identity ChannelMixer kernel and
+GuidedNoise; plus config 5 at its full per-GPU shard size against the oracle."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from helpers import assert_close, stub_model
+from oracle import sonar_oracle as orc
+from test_round2_oracle import GUIDED, POWER_DEFAULTS, c5_oracle_run
+
+pytestmark = pytest.mark.gpu
+
+POWER_KW = {"time_brownian": False, "common_mode": 0.0, "channel_correlation": "1, 1, 1, 1, 1, 1"} | POWER_DEFAULTS
+
+
+def power_chain(sb, **kw):
+    chain = sb.noise_graph.CustomNoiseChain()
+    chain.add(sb.spectral_noise.PowerNoiseItem(1.0, **(POWER_KW | kw)))
+    return chain
+
+
+def video_chain(sb, **kw):
+    item = sb.noise_graph.CustomNoiseParametersNoise(
+        1.0, noise=power_chain(sb, **kw), normalize=None, override_device=None, override_dtype=None,
+        frames_to_channels=True, ensure_square_aspect_ratio=False, fix_invalid=False, rng_mode="default",
+        rng_offset_mode="disabled", rng_state_offset=0,
+    )  # fmt: skip
+    chain = sb.noise_graph.CustomNoiseChain()
+    chain.add(item)
+    return chain
+
+
+@pytest.mark.parametrize("variant", ["default", "classic"])
+def test_c5_job_golden(sb, cuda, golden, variant):
+    """Config 5 exactly as north_star states it, scaled down: the reference's own output for
+    sonar_dpmpp_sde(custom_noise = SonarCustomNoiseParameters(frames_to_channels) o SonarPowerNoise(alpha=1))."""
+    g = golden("round2")["c5"]
+    case = g[variant]
+    steps = []
+    with sb.rng.injected(case["draws"]) as left:
+        out = sb.samplers.SonarDPMPPSDE.sampler(
+            stub_model, g["x0"].to(cuda), g["sigmas"].to(cuda), extra_args={"seed": 0}, disable=True,
+            sonar_params=dict(case["params"]) | {"custom_noise": video_chain(sb, alpha=1.0)},
+            callback=lambda d: steps.append(d["x"].clone()), eta=1.0, s_noise=1.0,
+        )  # fmt: skip
+        assert not left, "unused recorded draws"
+    assert_close(torch.stack(steps), case["steps"], what=f"c5 {variant}")
+    assert_close(out, case["out"], what=f"c5 {variant} final")
+
+
+def test_c5_job_shard_size_vs_oracle(sb, cuda):
+    """Config 5 at the per-GPU shard size 1x16x33x90x160 with the DEVICE Philox stream (no injection): the product
+    draws its complex spectra from torch's CUDA generator state; the oracle is fed torch.randn(complex64,
+    device='cuda') from the same seed."""
+    sigmas = torch.tensor([14.6, 5.0, 1.2, 0.0])
+    torch.manual_seed(5)
+    x0 = torch.randn(1, 16, 33, 90, 160) * sigmas[0]
+
+    def model(x, sigma, **_kw):
+        return x * 0.9
+
+    torch.manual_seed(1234)
+    launches = sb.ops.LAUNCH_COUNT
+    got = sb.samplers.SonarDPMPPSDE.sampler(
+        model, x0.to(cuda), sigmas.to(cuda), extra_args={"seed": 0}, disable=True,
+        sonar_params={"custom_noise": video_chain(sb, alpha=1.0)},
+    )
+    offset_after = torch.cuda.default_generators[0].get_offset()
+    launches = sb.ops.LAUNCH_COUNT - launches
+    torch.manual_seed(1234)
+    draws = [torch.randn((1, 528, 90, 81), dtype=torch.complex64, device=cuda).cpu() for _ in range(4)]
+    assert torch.cuda.default_generators[0].get_offset() == offset_after  # generator advanced exactly like torch.randn
+    b, c, f, h, w = x0.shape
+    filt = orc.power_filter((b, c * f, h, w), alpha=1.0)
+    it = iter(draws)
+
+    def noise():
+        return orc.scale_noise(orc.power_noise(it, (b, c * f, h, w), filt, normalized=False).reshape(x0.shape), 1.0, normalized=True)
+
+    o, x = orc.SonarOracle(), x0.clone()
+    for i in range(3):
+        den = model(x, sigmas[i])
+        if sigmas[i + 1] == 0:
+            x = o.dpmpp_sde(i, x, den, sigmas[i], sigmas[i + 1], model, None, None)
+        else:
+            n1, n2 = noise(), noise()
+            x = o.dpmpp_sde(i, x, den, sigmas[i], sigmas[i + 1], model, n1, n2)
+    assert_close(got, x, what="c5 shard")
+    # 2 steps x 2 half steps x (one noise launch + one fused step launch) + the final Euler step
+    assert launches <= 2 * 2 * 2 + 1, launches
+
+
+@pytest.mark.parametrize("name", ["c4_common", "c4_corr", "c3_neg", "c16_short_corr"])
+def test_channel_mixer_golden(sb, cuda, golden, name):
+    case = golden("round2")["mixer"][name]
+    x = torch.zeros(case["shape"], device=cuda)
+    with sb.rng.injected(case["draws"]) as left:
+        out = power_chain(sb, **case["params"]).make_noise_sampler(x, None, None, seed=0, cpu=True, normalized=True)(None, None)
+        assert not left
+    assert_close(out, case["out"], what=name)
+
+
+def test_channel_mixer_video_golden(sb, cuda, golden):
+    case = golden("round2")["mixer"]["video_c132"]
+    x = torch.zeros(case["shape"], device=cuda)
+    with sb.rng.injected(case["draws"]) as left:
+        out = video_chain(sb, **case["params"]).make_noise_sampler(x, None, None, seed=0, cpu=True, normalized=True)(None, None)
+        assert not left
+    assert_close(out, case["out"], what="video_c132")
+
+
+def test_channel_mixer_filter_noise_golden(sb, cuda, golden):
+    case = golden("round2")["mixer"]["filter_noise_c4"]
+    ng, sn = sb.noise_graph, sb.spectral_noise
+    inner = ng.CustomNoiseChain()
+    inner.add(ng.CustomNoiseItem(1.0, noise_type="gaussian"))
+    item = sn.PowerFilterNoiseItem(
+        1.0, noise=inner, normalize_noise=None, normalize_result=None, power_filter=sn.PowerFilter(alpha=1.0),
+        mix=1.0, common_mode=0.4, channel_correlation="1,-0.5,0.5,1,1,0.2", time_brownian=True, filter_norm_factor=1.0,
+    )  # fmt: skip
+    chain = ng.CustomNoiseChain()
+    chain.add(item)
+    x = torch.zeros(case["shape"], device=cuda)
+    with sb.rng.injected(case["draws"]) as left:
+        out = chain.make_noise_sampler(x, None, None, seed=0, cpu=True, normalized=True)(None, None)
+        assert not left
+    assert_close(out, case["out"], what="filter_noise_c4")
+
+
+@pytest.mark.parametrize(
+    "shape", [(1, 528, 90, 160), (2, 132, 10, 12), (3, 5, 7, 9), (2, 8, 16, 16), (1, 70, 9, 13), (2, 16, 32, 32), (4, 4, 128, 128)],
+)
+def test_channel_mix_kernel_vs_matmul(sb, cuda, shape):
+    """out[b, c] = sum_k M[c, k] in[b, k] on both kernel forms (per-pixel mat-vec for C <= 8, tiled GEMM above),
+    ragged sizes included; the fused output moments must equal a separate reduction."""
+    torch.manual_seed(shape[1])
+    b, c, h, w = shape
+    noise = torch.randn(shape)
+    mixer = orc.channel_mixer(c, 0.15, "1, 0.5, -0.25, 0.75")
+    want = orc.channel_mix(noise.double(), mixer.double())
+    got = sb.ops.channel_mix(noise.to(cuda), mixer.to(cuda), mixer)
+    assert_close(got, want.float(), what=f"channel_mix {shape}")
+    sums = sb.ops.attached_sums(got)
+    assert sums is not None
+    ref = torch.stack((want.sum(), want.square().sum()))
+    torch.testing.assert_close(sums.cpu(), ref, rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", GUIDED)
+def test_guided_noise_golden(sb, cuda, golden, name):
+    g = golden("round2")["guided"]
+    case = g[name]
+    cfg = case["config"]
+    ng = sb.noise_graph
+    inner = None
+    if cfg["noise"]:
+        inner = ng.CustomNoiseChain()
+        inner.add(ng.CustomNoiseItem(1.0, noise_type="gaussian"))
+    item = ng.GuidedNoise(
+        cfg.get("factor", 1.0), guidance_factor=cfg["guidance_factor"], ref_latent=case["ref"].clone(), method=cfg["method"],
+        normalize_noise=cfg.get("normalize_noise"), normalize_result=cfg.get("normalize_result"), noise=inner,
+    )  # fmt: skip
+    chain = ng.CustomNoiseChain()
+    chain.add(item)
+    s, sn = case["sigmas"]
+    with sb.rng.injected(case["draws"]) as left:
+        ns = chain.make_noise_sampler(g["x"].to(cuda), torch.tensor(0.03), torch.tensor(14.6), seed=0, cpu=True, normalized=True)
+        out = ns(torch.tensor(s), torch.tensor(sn))
+        assert not left
+    assert_close(out, case["out"], what=name)

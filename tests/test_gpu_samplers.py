@@ -10,7 +10,7 @@ from oracle import sonar_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"rtol": 2e-5, "atol": 2e-5}  # 7 chained steps of fp32 arithmetic at |x| ~ 15
+TOL = {"rtol": 1e-5, "atol": 1e-5}  # the north-star fp32 tolerance
 
 
 def _sampler(sb, kind):
@@ -147,7 +147,7 @@ def test_c2_full_size_vs_oracle(sb, cuda):
         got = sb.samplers.SonarEulerAncestral.sampler(
             lambda x, s, **k: x * 0.9, x0.to(cuda), sigmas.to(cuda), extra_args={"seed": 0}, disable=True,
         )
-    assert_close(got, want[-1], what="C2", rtol=5e-5, atol=5e-5)
+    assert_close(got, want[-1], what="C2", rtol=1e-5, atol=1e-5)
 
 
 def test_c5_shard_dpmpp_vs_oracle(sb, cuda):
@@ -164,7 +164,7 @@ def test_c5_shard_dpmpp_vs_oracle(sb, cuda):
             lambda x, s, **k: x * 0.9, x0.to(cuda), sigmas.to(cuda), extra_args={"seed": 0}, disable=True,
             sonar_params={"noise_type": "gaussian"},
         )
-    assert_close(got, want[-1], what="C5 shard", rtol=2e-5, atol=2e-5)
+    assert_close(got, want[-1], what="C5 shard", rtol=1e-5, atol=1e-5)
 
 
 def test_step_kernel_unaligned_and_odd_sizes(sb, cuda):

@@ -168,8 +168,8 @@ def test_samplers(golden, sname):
         if kind != sname:
             continue
         steps = sampler_oracle_run(kind, case, g["x0"], g["sigmas"], stub_model)
-        assert_close(steps, case["steps"], what=key, rtol=2e-5, atol=2e-5)
-        assert_close(steps[-1], case["out"], what=key + " final", rtol=2e-5, atol=2e-5)
+        assert_close(steps, case["steps"], what=key, rtol=0, atol=0)
+        assert_close(steps[-1], case["out"], what=key + " final", rtol=0, atol=0)
         ran += 1
     assert ran >= 2
 
@@ -184,7 +184,7 @@ def test_guidance(golden, sname):
         if kind != sname:
             continue
         steps = sampler_oracle_run(kind, case, g["x0"], g["sigmas"], stub_model)
-        assert_close(steps, case["steps"], what=key, rtol=2e-5, atol=2e-5)
+        assert_close(steps, case["steps"], what=key, rtol=0, atol=0)
         ran += 1
     assert ran == 5
 
