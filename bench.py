@@ -3,34 +3,32 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], "C2"): sonar_euler_ancestral -- Sonar momentum step fused with
-Gaussian ancestral noise -- on SDXL latents 8x4x128x128, 30 sampler steps, defaults (momentum 0.95,
-history 0.75, NEW mode, eta 1, s_noise 1); denoiser stub x*0.9 outside the timed regions.
-One bench "step" = one 30-step sampling run over one batch. Metric: latent noise elements / second
-(elements = 30 x 524,288 per batch).
+Workload (BASELINE.json configs[4], "C5", the configuration north_star shards over 8 GPUs and the largest one that
+fits a single GPU): video latent 8x16x33x90x160 (Hunyuan-style 5-D), `sonar_dpmpp_sde` whose custom noise is
+SonarCustomNoiseParameters(frames_to_channels=True) o SonarPowerNoise(alpha=1) -- exactly the reference objects of
+py/noise.py:2103-2185 + py/nodes/powernoise.py:355-408 + py/sonar.py:649-770 -- for N_SAMPLER_STEPS sampler steps
+(each: 2 model evaluations, 2 power-noise samples, 2 fused momentum half steps; the last step is the sigma_next == 0
+Euler step). Denoiser stub x*0.9 outside the timed regions. One bench "step" = one such sampling run over the whole
+8-item batch. Metric: latent noise elements / second, elements = N_SAMPLER_STEPS x 60,825,600 per run
+(the unit of work is the latent, per sampler step).
 
-* value     : device-resident throughput. Every sampler step's kernels (one fused step launch; the
-              first step also carries the batched Philox statistics of all 29 noise draws) are
-              bracketed by CUDA events on the launching stream; between sampler steps the stub
-              denoiser runs: FLUSH_PASSES x 256 MiB of zero-fill, which evicts L2 and occupies the GPU
-              for ~0.4 ms (a small fraction of a real UNet call), so the host enqueues the next step
-              while the device is still "in the UNet" and the intervals hold device time, not Python
-              launch latency. ms_per_step = sum of those 30 event intervals, max over ranks
-              (`per_rank_ms` lists every rank: mean run, mean first step).
-* e2e       : the same run through the public sampler function with HOST buffers: pinned x0 -> H2D,
-              30 steps, result D2H, wall clock between device synchronisations.
-* roofline  : dominant kernel (sonar_step_fast_philox2_kernel): algorithmic bytes per launch
-              (20 B/element: read x, denoised, history; write x', history'; the noise is regenerated
-              from the Philox stream in registers) / CUDA-event duration of that launch with cold L2,
-              against MEASURED_PEAKS.json hbm_gbs; the same kernel on the C5 per-GPU shard shape is
-              reported as roofline_large_tensor.
-* cpu_baseline : the CPU oracle port of the reference algorithm (oracle/sonar_oracle.py) on the host
-              cores, same workload, bounded sample.
-* N > 1     : weak scaling by batch: every rank holds 8 latents of a global batch of 8N; the global
-              scale_noise statistics of all 29 draws are summed over ranks ONCE per run (29x2 doubles through
-              the NVLink peer mailboxes, inside the first sampler step). Before each run the ranks meet at a
-              host barrier and, at the run's first denoiser call, at a device-side rendezvous
-              (parallel.device_barrier) behind which every host keeps enqueueing.
+* value     : device-resident throughput. Everything the sampler enqueues between two model calls (power-noise
+              sample + fused half step) is bracketed by CUDA events on the launching stream; the stub denoiser
+              in between zero-fills FLUSH_PASSES x 256 MiB (L2 eviction, and enough device time that the host
+              enqueues the next half step while the device is still "in the DiT": the intervals hold device
+              time, not Python launch latency). ms_per_step = sum of those intervals, max over ranks.
+* e2e       : the same run through the public sampler function with HOST buffers: pinned x0 (this rank's shard)
+              -> H2D, the run, NCCL gather of the shards to rank 0 (N > 1), D2H of the whole result into pinned
+              host memory; wall clock between device synchronisations, max over ranks.
+* roofline  : the kernel with the largest share of the timed region, from a traced run (a CUDA-event pair around
+              every C-ABI launch on the launching stream): algorithmic bytes per launch / its mean
+              duration, against MEASURED_PEAKS.json hbm_gbs; `kernels` lists every kernel's share.
+* cpu_baseline : the CPU oracle port of the reference algorithm (oracle/sonar_oracle.py) on the host cores, on a
+              bounded sample of the same workload (one batch item, a few sampler steps).
+* N > 1     : STRONG scaling: the 8-item batch is split over the ranks (8 GPUs: one video latent each, as north_star
+              states); every rank regenerates its slice of the global Philox draws; the two doubles of each
+              scale_noise travel through the NVLink peer mailboxes (no data-path collective); `parity_max_abs_diff`
+              is the gathered result vs an un-sharded run of the whole batch on rank 0.
 """
 
 from __future__ import annotations
@@ -51,15 +49,23 @@ import torch
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
-SHAPE = (8, 4, 128, 128)
-N_SAMPLER_STEPS = 30
-FLUSH_PASSES = 8  # 256 MiB zero-fills per stub-denoiser call: L2 eviction + ~0.4 ms of device time (see StepTimer)
-ELEMS_PER_RUN = N_SAMPLER_STEPS * SHAPE[0] * SHAPE[1] * SHAPE[2] * SHAPE[3]
-WORKLOAD = "C2 sonar_euler_ancestral, SDXL latents 8x4x128x128, 30 steps, fused Gaussian noise"
+# SONAR_BENCH_ITEMS=k (diagnostics only): run the job on k batch items, e.g. 1 = the per-GPU work of the 8-GPU split
+SHAPE = (int(os.environ.get("SONAR_BENCH_ITEMS", "8")), 16, 33, 90, 160)
+ITEM_ELEMS = SHAPE[1] * SHAPE[2] * SHAPE[3] * SHAPE[4]
+N_SAMPLER_STEPS = 10
+FLUSH_PASSES = 4  # 256 MiB zero-fills per stub-denoiser call: L2 eviction + device time for the host to run ahead
+ELEMS_PER_RUN = N_SAMPLER_STEPS * SHAPE[0] * ITEM_ELEMS
+WORKLOAD = (
+    "C5 video latent 8x16x33x90x160: sonar_dpmpp_sde with frames_to_channels power noise (alpha=1) as custom noise, "
+    f"{N_SAMPLER_STEPS} sampler steps"
+)
+# SURVEY.md 8d, RNG-fused accounting: a power-noise sample writes 4 B/el (nothing is read); a fused half step reads
+# x, denoised, history, noise and writes x', history' = 24 B/el
+BYTES_NOISE, BYTES_STEP = 4.0, 24.0
 
 
-def make_sigmas() -> torch.Tensor:
-    return torch.cat((torch.linspace(14.6, 0.03, N_SAMPLER_STEPS), torch.zeros(1)))
+def make_sigmas(n: int = N_SAMPLER_STEPS) -> torch.Tensor:
+    return torch.cat((torch.linspace(14.6, 0.03, n), torch.zeros(1)))
 
 
 def measured_peak() -> tuple[float, str]:
@@ -93,9 +99,8 @@ class ClockSampler:
             )  # fmt: skip
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
-            # nvidia-smi spends ~0.1-1 s initialising NVML (and holds driver locks while it does): wait for its
-            # first sample so that start-up does not land inside the first timed runs; the 100 ms polling that
-            # follows is what samples the timed region
+            # nvidia-smi spends ~0.1-1 s initialising NVML: wait for its first sample so that start-up does not land
+            # inside the first timed runs; the 100 ms polling that follows is what samples the timed region
             deadline = time.perf_counter() + 5.0
             while not self.lines and time.perf_counter() < deadline and self.proc.poll() is None:
                 time.sleep(0.01)
@@ -142,38 +147,52 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(n_runs: int, sampler_steps: int = N_SAMPLER_STEPS) -> dict:
-    """Times oracle.SonarOracle.euler_ancestral + CPU Gaussian noise + scale_noise (what the
-    reference's SonarEulerAncestral.step does on CPU, py/sonar.py:541-573), all host threads."""
+def cpu_reference_run(n_runs: int, sampler_steps: int = 2, items: int = SHAPE[0]) -> dict:
+    """Times the oracle port of the C5 job on the CPU: oracle.power_noise (irfft2 of the shaped complex draw,
+    py/nodes/powernoise.py:355-366) + scale_noise + SonarOracle.dpmpp_sde (py/sonar.py:649-735), all host threads,
+    on `items` batch items and `sampler_steps` steps (all of them two-stage steps: the schedule does not reach 0)."""
     from oracle import sonar_oracle as orc
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sigmas = make_sigmas()
+    sigmas = make_sigmas()[: sampler_steps + 1]
+    shape = (items, *SHAPE[1:])
+    folded = (items, SHAPE[1] * SHAPE[2], SHAPE[3], SHAPE[4])
+    filt = orc.power_filter(folded, alpha=1.0)
     torch.manual_seed(0)
-    x0 = torch.randn(SHAPE) * sigmas[0]
+    x0 = torch.randn(shape) * sigmas[0]
+
+    def model(x, _sigma):
+        return x * 0.9
+
+    def noise():
+        spec = torch.randn((*folded[:-1], folded[-1] // 2 + 1), dtype=torch.complex64)
+        raw = orc.power_noise(iter([spec]), folded, filt, normalized=False)
+        return orc.scale_noise(raw.reshape(shape), 1.0, normalized=True)
+
     times = []
     for _ in range(n_runs):
         o = orc.SonarOracle()
         x = x0.clone()
-        den = x * 0.9
         t_run = 0.0
         for i in range(sampler_steps):
+            den = model(x, sigmas[i])  # untimed, like the GPU arm's stub
             t0 = time.perf_counter()
-            noise = orc.scale_noise(torch.randn(SHAPE), 1.0, normalized=True) if sigmas[i + 1] > 0 else None
-            x = o.euler_ancestral(i, x, den, sigmas[i], sigmas[i + 1], noise)
+            n1, n2 = noise(), noise()
+            x = o.dpmpp_sde(i, x, den, sigmas[i], sigmas[i + 1], model, n1, n2)
             t_run += time.perf_counter() - t0
-            den = x * 0.9  # denoiser stub, untimed
         times.append(t_run)
     best = min(times)
     elems = sampler_steps * x0.numel()
+    per_el = best / elems
     return {
-        "value": elems / best,
+        "value": 1.0 / per_el,
         "unit": "elements/s",
         "cores": cores,
         "kind": "port",
-        "sample": f"{n_runs} x {sampler_steps} sampler steps of C2 on CPU (oracle port, best run, stub denoiser untimed)",
-        "ms_per_step": best * 1e3 * (N_SAMPLER_STEPS / sampler_steps),
+        "sample": f"best of {n_runs} x {sampler_steps} sampler steps of C5 on {items} of 8 batch items (oracle port on CPU; the "
+        "second model call of each step is inside the timed region, x*0.9)",
+        "ms_per_step": per_el * ELEMS_PER_RUN * 1e3,
     }
 
 
@@ -182,9 +201,9 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     t0 = time.perf_counter()
-    for _ in range(args.warmup):
-        cpu_reference_run(1, sampler_steps=10)
-    res = cpu_reference_run(max(1, args.steps))
+    for _ in range(min(1, args.warmup)):
+        cpu_reference_run(1, sampler_steps=1, items=2)
+    res = cpu_reference_run(max(1, min(args.steps, 3)))
     line = {
         "impl": "reference",
         "metric": "latent noise elements/sec",
@@ -195,7 +214,7 @@ def run_reference_arm(args) -> None:
         "warmup": args.warmup,
         "ms_per_step": res["ms_per_step"],
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
@@ -212,8 +231,8 @@ def run_reference_arm(args) -> None:
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 class StepTimer:
-    """Denoiser stub that doubles as the boundary of the timed regions: everything the sampler
-    enqueues between two model calls is the hot path of one sampler step."""
+    """Denoiser stub that doubles as the boundary of the timed regions: everything the sampler enqueues between
+    two model calls is the hot path of one half step."""
 
     def __init__(self, device, flush_bytes: int = 256 << 20, timed: bool = True, flush_passes: int = FLUSH_PASSES,
                  on_first_call=None):
@@ -235,15 +254,11 @@ class StepTimer:
         if self.timed:
             self.close()
         if self.on_first_call is not None:
-            # the GPUs meet HERE, with the host already enqueueing the denoiser and the first sampler step behind
-            # the rendezvous: from its release on every rank runs from a full queue, so the exchange inside the
-            # first step measures NVLink and the slowest GPU, not the slowest Python thread
+            # the GPUs meet HERE, with the host already enqueueing the denoiser and the first half step behind the
+            # rendezvous: from its release on every rank runs from a full queue
             self.on_first_call()
             self.on_first_call = None
         if self.flush is not None:
-            # evicts L2 and keeps the GPU busy for ~0.4 ms, like (a small fraction of) the UNet forward that sits
-            # here in real use: the host enqueues the next step while the device is still in the denoiser, so
-            # the timed intervals are device time of the hot path, not Python launch latency
             for _ in range(self.flush_passes):
                 self.flush.zero_()
         den = x * 0.9
@@ -256,86 +271,80 @@ class StepTimer:
         return sum(a.elapsed_time(b) for a, b in self.pairs)
 
 
-def step_kernel_roofline(sb, dev, shape, peak: float, peak_src: str, reps: int) -> dict:
-    """Times the dominant kernel alone (sonar_step_fast_philox_kernel: momentum mix + both history
-    updates + Euler step + ancestral noise regenerated from the Philox stream and normalised from the
-    look-ahead statistics). Algorithmic bytes: 20 B/element = read x, denoised, history; write x',
-    history' (the noise never touches HBM).
+POWER_KW = dict(time_brownian=False, alpha=1.0, max_freq=0.7071, min_freq=0.0, stretch=1.0, rotate=0.0, pnorm=2.0,
+                mix=1.0, common_mode=0.0, channel_correlation="1, 1, 1, 1, 1, 1")  # fmt: skip
 
-    The launches of several independent operand sets are captured into ONE CUDA graph, so the interval
-    between the two CUDA events is device time of back-to-back kernels, not host launch cadence (a
-    ctypes launch costs ~5 us on the host, as long as the kernel itself at this size). L2 is flushed
-    (256 MiB write) before every replay and each operand set is touched once per replay: cold reads."""
-    import statistics as st
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    n = 1
-    for d in shape:
-        n *= d
-    n_sets = max(2, min(8, (96 << 20) // (20 * n)))
-    sets = []
-    for _ in range(n_sets):
-        x, den, hist = (torch.randn(shape, device=dev) for _ in range(3))
-        draw = sb.ops.reserve_draw(n, dev)
-        sums = sb.ops.philox_normal_moments_batch(draw, [draw.offset], begin=0, count=n, device=dev)
-        dec = sb.ops.norm_decisions(sums, n)
-        stepper = sb.samplers.SonarBase(sb.samplers.SonarConfig())
-        kw = {"draw": draw, "factor": 1.0, "normalized": True, "begin": 0, "sums": (sums, dec), "sums_ptr": sums.data_ptr(),
-              "decision_ptr": dec.data_ptr(), "count": n}
-        sets.append((stepper, x, den, hist, kw))
-    outs = []
+def power_chain(sb, **kw):
+    c = sb.noise_graph.CustomNoiseChain()
+    c.add(sb.spectral_noise.PowerNoiseItem(1.0, **(POWER_KW | kw)))
+    return c
 
-    def launch_all():
-        outs.clear()
-        for stepper, x, den, hist, kw in sets:
-            stepper.history_d = hist
-            outs.append(stepper.fused_step(3, x, den, 5.0, kind=sb.ops.STEP_EULER, c0=-1.5, noise_scale=0.7, noise_philox=kw))
 
-    side = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            launch_all()
-    side.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        launch_all()
-    for _ in range(3):
-        flush.zero_()
-        graph.replay()
-    torch.cuda.synchronize()
-    us = []
+def c5_chain(sb):
+    """SonarCustomNoiseParameters(frames_to_channels=True) o SonarPowerNoise(alpha=1)."""
+    item = sb.noise_graph.CustomNoiseParametersNoise(
+        1.0, noise=power_chain(sb), normalize=None, override_device=None, override_dtype=None, frames_to_channels=True,
+        ensure_square_aspect_ratio=False, fix_invalid=False, rng_mode="default", rng_offset_mode="disabled", rng_state_offset=0,
+    )  # fmt: skip
+    chain = sb.noise_graph.CustomNoiseChain()
+    chain.add(item)
+    return chain
+
+
+def sampler_run(sb, model, x0, sigmas, chain):
+    return sb.samplers.SonarDPMPPSDE.sampler(
+        model, x0, sigmas, extra_args={"seed": 0}, disable=True, sonar_params={"custom_noise": chain},
+    )
+
+
+# which launches of the C5 run are which kernel, and their algorithmic bytes per element of the tensor they produce
+C5_KERNELS = {
+    "sonar_spectral_filter_f32": ("spectral_batched_kernel (power-noise sample: Philox spectrum -> gain -> irfft2 -> moments)", BYTES_NOISE),
+    "sonar_step_f32": ("sonar_step_fast_vec_kernel (fused half step, noise normalised on load)", BYTES_STEP),
+}
+
+
+def traced_breakdown(sb, run, n_local_elems: int, peak: float, peak_src: str, reps: int) -> tuple[dict, list]:
+    """Per-kernel CUDA-event timing of the C5 run (ops.TRACE brackets every C-ABI launch on the launching stream).
+    Returns the roofline block of the kernel with the largest share and the table of all kernels."""
+    per: dict[str, list[float]] = {}
     for _ in range(reps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        graph.replay()
-        e1.record()
+        sb.ops.TRACE = []
+        run()
         torch.cuda.synchronize()
-        us.append(e0.elapsed_time(e1) * 1e3 / n_sets)
-    launch_us = st.median(us)
-    algo = 20 * n
-    achieved = algo / (launch_us * 1e-6) / 1e9
-    # draws of at most two ATen rows (numel <= 2 * 256 * grid) take the single-wave variant
-    two_rows = n <= 2 * 256 * sb.ops.philox_policy(n)[0]
-    return {
+        trace, sb.ops.TRACE = sb.ops.TRACE, None
+        for name, a, b in trace:
+            per.setdefault(name, []).append(a.elapsed_time(b) * 1e3)
+    total = sum(sum(v) for v in per.values())
+    table = []
+    for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        label, bytes_per_el = C5_KERNELS.get(name, (name, None))
+        row = {"entry_point": name, "kernel": label, "launches_per_run": len(v) // reps, "mean_us": statistics.mean(v),
+               "share_of_timed_region": sum(v) / total}  # fmt: skip
+        if bytes_per_el is not None:
+            algo = bytes_per_el * n_local_elems
+            row |= {"algorithmic_bytes_per_launch": algo, "achieved_gbs": algo / (statistics.mean(v) * 1e-6) / 1e9,
+                    "frac": algo / (statistics.mean(v) * 1e-6) / 1e9 / peak}  # fmt: skip
+        table.append(row)
+    top = next(r for r in table if "frac" in r)
+    roofline = {
         "bound": "hbm",
-        "kernel": "sonar_step_fast_philox2_kernel" if two_rows else "sonar_step_fast_philox_kernel",
-        "shape": list(shape),
-        "achieved": achieved,
+        "kernel": top["kernel"],
+        "achieved": top["achieved_gbs"],
         "peak": peak,
         "unit": "GB/s",
-        "frac": achieved / peak,
+        "frac": top["frac"],
         "traffic": None,
         "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": algo,
-        "launch_us": launch_us,
-        "launches_timed": len(us) * n_sets,
-        "timing": f"CUDA events around one graph replay of {n_sets} back-to-back launches on distinct operand sets, after a 256 MiB L2 flush",
+        "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
+        "launch_us": top["mean_us"],
+        "launches_timed": top["launches_per_run"] * reps,
+        "share_of_timed_region": top["share_of_timed_region"],
+        "timing": "CUDA-event pair around every launch of the timed C5 run on the launching stream (tensors of 243 MB per "
+        "GPU at N=1 exceed L2; the stub denoiser flushes L2 between half steps)",
     }
-
-
-def sampler_run(sb, model, x0, sigmas):
-    return sb.samplers.SonarEulerAncestral.sampler(model, x0, sigmas, extra_args={"seed": 0}, disable=True)
+    return roofline, table
 
 
 def run_b200_arm(args) -> None:
@@ -344,6 +353,8 @@ def run_b200_arm(args) -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; sonar_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    if world > SHAPE[0]:
+        raise SystemExit(f"bench.py: the C5 batch has {SHAPE[0]} items; at most {SHAPE[0]} ranks")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -361,33 +372,31 @@ def run_b200_arm(args) -> None:
 
     sigmas_host = make_sigmas()
     sigmas = sigmas_host.to(dev)
-    torch.manual_seed(1234 + rank)
-    x0 = torch.randn(SHAPE, device=dev) * sigmas_host[0]
-    x0_host = x0.cpu().pin_memory()
-    global_batch = SHAPE[0] * world
+    sizes = sb.parallel.split_sizes(SHAPE[0], world)
+    b0, nb = sum(sizes[:rank]), sizes[rank]
+    # identical synthetic latent on every rank (one CPU generator), then this rank's batch slice
+    gen = torch.Generator().manual_seed(1234)
+    x0_host = (torch.randn(SHAPE, generator=gen) * sigmas_host[0])[b0 : b0 + nb].contiguous().pin_memory()
+    x0 = x0_host.to(dev)
+    n_local = x0.numel()
+    chain = c5_chain(sb)
 
-    def one_run(model, src):
+    def one_run(model, src, sharded=True):
         torch.manual_seed(99)  # replicated generator: every rank reserves the same global draws
-        if world > 1:
-            with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
-                return sampler_run(sb, model, src, sigmas)
-        return sampler_run(sb, model, src, sigmas)
+        if world > 1 and sharded:
+            with sb.parallel.sharded(SHAPE[0], rank=rank, world_size=world):
+                return sampler_run(sb, model, src, sigmas, chain)
+        return sampler_run(sb, model, src, sigmas, chain)
 
-    # ---------------- device-resident throughput ----------------
-    warm_model = StepTimer(dev, timed=False)
     def device_rendezvous():
-        with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
+        with sb.parallel.sharded(SHAPE[0], rank=rank, world_size=world):
             sb.parallel.device_barrier()
 
     rendezvous = device_rendezvous if world > 1 else None
 
-    def align_ranks():
-        """Ranks start a run together: a host barrier here, and a device-side rendezvous (peer mailboxes) at the
-        run's first denoiser call (StepTimer.on_first_call)."""
-        barrier()
-
+    # ---------------- device-resident throughput ----------------
     for _ in range(max(3, args.warmup)):
-        align_ranks()
+        barrier()
         one_run(StepTimer(dev, timed=False, on_first_call=rendezvous), x0)
     barrier()
     launches0 = sb.ops.LAUNCH_COUNT
@@ -395,70 +404,89 @@ def run_b200_arm(args) -> None:
     gc.collect()
     gc.disable()  # a collection pause between two launches would show up as device idle time
     with ClockSampler(local_rank, enabled=rank == 0) as clocks:
-        align_ranks()
+        barrier()
         one_run(StepTimer(dev, timed=False, on_first_call=rendezvous), x0)  # one more untimed run with the clock poller up
         barrier()
+        launches0 = sb.ops.LAUNCH_COUNT
         t_wall = time.perf_counter()
         for _ in range(args.steps):
             if world > 1:
-                align_ranks()
+                barrier()
             timer = StepTimer(dev, on_first_call=rendezvous)
             one_run(timer, x0)
             timer.close()
             timers.append(timer)
         barrier()
         wall = time.perf_counter() - t_wall
-        # keep the sampler busy long enough for a few clock samples; a FIXED run count, because every
-        # sharded run performs one exchange and all ranks must perform the same number of them
-        for _ in range(300):
-            one_run(warm_model, x0)
+        launches = sb.ops.LAUNCH_COUNT - launches0
+        # keep the sampler busy long enough for a few clock samples (a FIXED run count: sharded runs exchange)
+        keep = StepTimer(dev, timed=False)
+        for _ in range(10):
+            one_run(keep, x0)
         torch.cuda.synchronize()
     gc.enable()
-    launches = sb.ops.LAUNCH_COUNT - launches0
     run_ms = [t.total_ms() for t in timers]
-    ms_per_step = statistics.mean(run_ms)
-    # per rank: (mean run, mean first-step interval -- the one that holds the look-ahead pass and the exchange)
-    first_ms = statistics.mean(t.pairs[0][0].elapsed_time(t.pairs[0][1]) for t in timers)
-    per_rank = torch.tensor([ms_per_step, first_ms], device=dev, dtype=torch.float64)
+    ms_local = statistics.mean(run_ms)
+    per_rank = torch.tensor([ms_local], device=dev, dtype=torch.float64)
     if world > 1:
         gathered = [torch.zeros_like(per_rank) for _ in range(world)]
         dist.all_gather(gathered, per_rank)
-        per_rank_ms = [[round(float(v), 4) for v in g.tolist()] for g in gathered]
+        per_rank_ms = [round(float(g.item()), 4) for g in gathered]
     else:
-        per_rank_ms = [[round(ms_per_step, 4), round(first_ms, 4)]]
-    ms_per_step = max(r[0] for r in per_rank_ms) if world > 1 else ms_per_step
-    value = ELEMS_PER_RUN * world / (ms_per_step * 1e-3)
+        per_rank_ms = [round(ms_local, 4)]
+    ms_per_step = max(per_rank_ms)
+    value = ELEMS_PER_RUN / (ms_per_step * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (per-launch CUDA events) ----------------
+    # ---------------- roofline of the dominant kernel (per-launch CUDA events in the same run) ----------------
     peak, peak_src = measured_peak()
-    roofline = step_kernel_roofline(sb, dev, SHAPE, peak, peak_src, reps=40)
-    roofline_large = step_kernel_roofline(sb, dev, (1, 16, 33, 90, 160), peak, peak_src, reps=20)
+    barrier()
+    tracer = StepTimer(dev, timed=False, on_first_call=rendezvous)
+    roofline, kernel_table = traced_breakdown(sb, lambda: one_run(tracer, x0), n_local, peak, peak_src, reps=2)
     traffic_path = REPO / "profiles" / "traffic.json"
     if traffic_path.exists():
-        traffic = json.loads(traffic_path.read_text())
-        roofline["traffic"] = traffic.get(roofline["kernel"] + "@8x4x128x128")
-        roofline_large["traffic"] = traffic.get(roofline_large["kernel"] + "@1x16x33x90x160")
+        roofline["traffic"] = json.loads(traffic_path.read_text()).get("c5:" + roofline["kernel"].split(" ")[0])
+
+    # ---------------- multi-GPU parity: gathered shards vs the un-sharded job on rank 0 ----------------
+    parity = None
+    if world > 1:
+        barrier()
+        out = one_run(StepTimer(dev, flush_bytes=0, timed=False), x0)
+        with sb.parallel.sharded(SHAPE[0], rank=rank, world_size=world):
+            full = sb.parallel.gather(out, dst=0)
+        if rank == 0:
+            x_full = (torch.randn(SHAPE, generator=torch.Generator().manual_seed(1234)) * sigmas_host[0]).to(dev)
+            want = one_run(StepTimer(dev, flush_bytes=0, timed=False), x_full, sharded=False)
+            parity = float((full - want).abs().max().item())
+            del x_full, want
+        del full, out
+        barrier()
 
     # ---------------- end to end through the public API with host buffers ----------------
     e2e_times = []
     e2e_model = StepTimer(dev, flush_bytes=0, timed=False)
     gc.collect()
     gc.disable()
-    # result lands in a pinned host buffer (what a serving loop does; a pageable destination adds a
-    # staging copy and first-touch page faults to every run)
-    out_host = torch.empty((global_batch if rank == 0 else SHAPE[0], *SHAPE[1:]), dtype=torch.float32).pin_memory()
-    for i in range(3 + args.steps):
+    out_host = torch.empty(SHAPE if rank == 0 else (nb, *SHAPE[1:]), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    for i in range(2 + args.steps):
         barrier()
         t0 = time.perf_counter()
         x_dev = x0_host.to(dev, non_blocking=True)
         out = one_run(e2e_model, x_dev)
         if world > 1:
-            with sb.parallel.sharded(global_batch, rank=rank, world_size=world):
-                out = sb.parallel.gather(out, dst=0)
-        if out is not None:
-            out_host[: out.shape[0]].copy_(out, non_blocking=True)
+            if rank == 0:
+                # this rank's own shard goes to the host while NCCL gathers the others over NVLink
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    out_host[b0 : b0 + nb].copy_(out, non_blocking=True)
+            with sb.parallel.sharded(SHAPE[0], rank=rank, world_size=world):
+                full = sb.parallel.gather(out, dst=0)
+            if rank == 0:
+                out_host[nb:].copy_(full[nb:], non_blocking=True)
+        else:
+            out_host.copy_(out, non_blocking=True)
         torch.cuda.synchronize()
-        if i >= 3:
+        if i >= 2:
             e2e_times.append(time.perf_counter() - t0)
     gc.enable()
     e2e_s = statistics.mean(e2e_times)
@@ -466,23 +494,27 @@ def run_b200_arm(args) -> None:
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     e2e_s = float(t_dev.item())
-    bytes_x = x0.numel() * 4
+    bytes_total = SHAPE[0] * ITEM_ELEMS * 4
     e2e = {
-        "value": ELEMS_PER_RUN * world / e2e_s,
+        "value": ELEMS_PER_RUN / e2e_s,
         "unit": "elements/s",
-        "h2d_bytes_per_step": bytes_x + sigmas.numel() * 0,
-        "d2h_bytes_per_step": bytes_x * (world if rank == 0 else 1),
+        "h2d_bytes_per_step": bytes_total,
+        "d2h_bytes_per_step": bytes_total,
         "ms_per_step": e2e_s * 1e3,
-        "note": "public sampler function, pinned host x0 -> H2D, 30 steps (stub denoiser inside), result D2H"
-        + (" after NCCL gather to rank 0" if world > 1 else ""),
+        "note": "public sampler function (SonarDPMPPSDE.sampler, custom_noise chain), pinned host x0 -> H2D (each rank its "
+        "shard), the sampler run with the stub denoiser inside, "
+        + ("NCCL gather to rank 0 overlapped with rank 0's own D2H, " if world > 1 else "")
+        + "whole result D2H into pinned memory; bytes are job totals",
     }
 
     extras = None
     cpu_baseline = None
     if rank == 0 and world == 1:
+        del x0, out
+        torch.cuda.empty_cache()
         if not args.no_extras:
             extras = run_extras(sb, dev, peak)
-        cpu = cpu_reference_run(3)
+        cpu = cpu_reference_run(2, items=4)
         cpu_baseline = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -495,28 +527,35 @@ def run_b200_arm(args) -> None:
             "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong",
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": {
                 "workload": WORKLOAD,
-                "global_batch": global_batch,
-                "per_gpu_shape": list(SHAPE),
-                "parallelism": f"batch-sharded x{world}" if world > 1 else "single GPU",
-                "l2": f"{FLUSH_PASSES} x 256 MiB flush between sampler steps (where the UNet runs, ~0.4 ms of device time); stub denoiser untimed",
-                "timing": "sum of 30 CUDA-event intervals per run (fused step launch; step 0 includes the batched Philox statistics of all draws), max over ranks",
+                "global_batch": SHAPE[0],
+                "global_shape": list(SHAPE),
+                "items_per_gpu": sizes,
+                "sampler_steps": N_SAMPLER_STEPS,
+                "parallelism": f"batch-sharded x{world} (strong split)" if world > 1 else "single GPU",
+                "l2": f"tensors of {bytes_total // world >> 20} MiB per GPU; {FLUSH_PASSES} x 256 MiB zero-fill between half steps "
+                "(stub denoiser, untimed) evicts L2",
+                "timing": "sum of the CUDA-event intervals between model calls (power-noise sample + fused half step), max over ranks",
+                "elements": "sampler steps x latent elements (each step = 2 noise samples + 2 fused half steps)",
             },
             "roofline": roofline,
-            "roofline_large_tensor": roofline_large,
+            "kernels": kernel_table,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,
             "runs_ms": run_ms,
-            "per_rank_ms": per_rank_ms,  # [mean run, mean first sampler step] of every rank
+            "per_rank_ms": per_rank_ms,
         }
+        if parity is not None:
+            line["parity_max_abs_diff"] = parity
+            line["parity_note"] = "max |gathered sharded result - un-sharded run of the whole batch on rank 0|, same seed"
         if extras is not None:
             line["other_configs"] = extras
         print(json.dumps(line), flush=True)
@@ -525,7 +564,7 @@ def run_b200_arm(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------------
-# the other BASELINE.json configs (single GPU): elements/s and roofline fraction of the top kernel
+# the other BASELINE.json configs (single GPU): elements/s and roofline fraction, SURVEY 8d byte accounting
 # ---------------------------------------------------------------------------------------------
 def _time_traced(sb, fn, reps: int, flush: torch.Tensor) -> tuple[float, dict]:
     """Mean total kernel time (us) and per-kernel means over `reps` traced invocations."""
@@ -565,6 +604,7 @@ def run_extras(sb, dev, peak: float) -> list[dict]:
                 "config": name,
                 "elements": elems,
                 "kernel_us": total_us,
+                "launches": len(per),
                 "elements_per_s": elems / (total_us * 1e-6),
                 "algorithmic_bytes_per_element": algo_bytes_per_elem,
                 "hbm_gbs": elems * algo_bytes_per_elem / (total_us * 1e-6) / 1e9,
@@ -575,21 +615,26 @@ def run_extras(sb, dev, peak: float) -> list[dict]:
             },
         )
 
-    # C1: SonarPowerNoise pink on 1x4x64x64 (RNG draw of the half spectrum + irfft2 + normalisation)
-    ng, sn = sb.noise_graph, sb.spectral_noise
-    power_kw = dict(time_brownian=False, alpha=1.0, max_freq=0.7071, min_freq=0.0, stretch=1.0, rotate=0.0, pnorm=2.0,
-                    mix=1.0, common_mode=0.0, channel_correlation="1, 1, 1, 1, 1, 1")  # fmt: skip
-
-    def power_chain():
-        c = ng.CustomNoiseChain()
-        c.add(sn.PowerNoiseItem(1.0, **power_kw))
-        return c
-
+    ng = sb.noise_graph
+    # C1: SonarPowerNoise pink on 1x4x64x64
     x = torch.zeros(1, 4, 64, 64, device=dev)
-    ns = power_chain().make_noise_sampler(x, None, None, seed=0)
+    ns = power_chain(sb).make_noise_sampler(x, None, None, seed=0)
     us, per = _time_traced(sb, lambda: ns(None, None), 10, flush)
-    record("C1 SonarPowerNoise pink 1x4x64x64", x.numel(), 8.125 + 8.125 + 12, us, per,
-           "bytes: spectrum write+read 2x8.125, irfft2 write 4, moments read 4, scale r/w... (see DESIGN.md)")
+    record("C1 SonarPowerNoise pink 1x4x64x64", x.numel(), 4.0, us, per,
+           "SURVEY 8d RNG-fused accounting: 4 B/el (the sample is written once; the chain's own normalisation pass is overhead)")
+
+    # C2: sonar_euler_ancestral, fused Gaussian noise, 8x4x128x128, 30 steps (round-1 headline workload)
+    sig2 = torch.cat((torch.linspace(14.6, 0.03, 30), torch.zeros(1))).to(dev)
+    x2 = torch.randn(8, 4, 128, 128, device=dev) * 14.6
+
+    def c2():
+        torch.manual_seed(99)
+        return sb.samplers.SonarEulerAncestral.sampler(lambda x, s, **k: x * 0.9, x2, sig2, extra_args={"seed": 0}, disable=True)
+
+    us, per = _time_traced(sb, c2, 5, flush)
+    record("C2 sonar_euler_ancestral 8x4x128x128, 30 steps, fused Gaussian noise", 30 * x2.numel(), 20.0, us, per,
+           "20 B/el/step: read x, denoised, history; write x', history'; noise regenerated from Philox in registers. Kernel "
+           "time only (launch-bound at this size: see DESIGN.md)")
 
     # C3: Scheduled(Blended(lerp .5, pyramid, perlin), fallback gaussian) on 16x16x128x128
     def chain_of(t):
@@ -603,16 +648,16 @@ def run_extras(sb, dev, peak: float) -> list[dict]:
     sched = ng.CustomNoiseChain()
     sched.add(ng.ScheduledNoise(1.0, noise=blended, start_sigma=10.0, end_sigma=1.0, normalize=None, fallback_noise=chain_of("gaussian")))
     x = torch.zeros(16, 16, 128, 128, device=dev)
-    ns = sched.make_noise_sampler(x, torch.tensor(0.03), torch.tensor(14.6), seed=0)
+    ns3 = sched.make_noise_sampler(x, torch.tensor(0.03), torch.tensor(14.6), seed=0)
     s, sn_ = torch.tensor(5.0), torch.tensor(4.5)
 
     def c3():
         torch.manual_seed(0)
-        return ns(s, sn_)
+        return ns3(s, sn_)
 
     us, per = _time_traced(sb, c3, 5, flush)
-    record("C3 Scheduled(Blended(pyramid, perlin)) 16x16x128x128", x.numel(), 16.8, us, per,
-           "16.8 B/el = injected-draw accounting of SURVEY 8d; the run also writes its own Philox draws")
+    record("C3 Scheduled(Blended(pyramid, perlin)) 16x16x128x128", x.numel(), 4.0, us, per,
+           "SURVEY 8d RNG-fused accounting: 4 B/el (one write of the result); 16.8 B/el with injected base draws")
 
     # C4: wavelet CFG db2 / 3 levels / separate H,V,D scales on 16x4x128x128
     class _MS:
@@ -633,29 +678,6 @@ def run_extras(sb, dev, peak: float) -> list[dict]:
     us, per = _time_traced(sb, lambda: fn(wargs), 10, flush)
     record("C4 wavelet CFG db2 L3 16x4x128x128 (fp64 coefficients)", xin.numel(), 16.0, us, per,
            "16 B/el: read cond, uncond, x; write result (fp64 is internal)")
-
-    # C5 per-GPU shard: video latent 1x16x33x90x160, power noise via frames_to_channels + DPM++ SDE half steps
-    x5 = torch.zeros(1, 16, 33, 90, 160, device=dev)
-    params = ng.CustomNoiseParametersNoise(
-        1.0, noise=power_chain(), normalize=None, override_device=None, override_dtype=None, frames_to_channels=True,
-        ensure_square_aspect_ratio=False, fix_invalid=False, rng_mode="default", rng_offset_mode="disabled", rng_state_offset=0)
-    c5 = ng.CustomNoiseChain()
-    c5.add(params)
-    ns5 = c5.make_noise_sampler(x5, None, None, seed=0)
-    us, per = _time_traced(sb, lambda: ns5(None, None), 5, flush)
-    record("C5 shard power noise 1x16x33x90x160", x5.numel(), 8.125 + 8.125 + 12, us, per, "as C1")
-
-    sig5 = torch.tensor([14.6, 7.0, 2.0, 0.7], device=dev)
-    xv = torch.randn(1, 16, 33, 90, 160, device=dev) * 14.6
-    cfg = {"noise_type": "gaussian"}
-
-    def c5_dpm():
-        torch.manual_seed(0)
-        return sb.samplers.SonarDPMPPSDE.sampler(lambda x, s, **k: x * 0.9, xv, sig5, extra_args={"seed": 0}, disable=True, sonar_params=cfg)
-
-    us, per = _time_traced(sb, c5_dpm, 3, flush)
-    record("C5 shard sonar_dpmpp_sde 3 steps 1x16x33x90x160 (fused Gaussian noise)", 3 * xv.numel(), 40.0, us, per,
-           "40 B/el/step: two fused half steps x 20 B/el; Philox moments pre-passes cost no HBM bytes")
     return out
 
 

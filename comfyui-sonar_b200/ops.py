@@ -624,10 +624,14 @@ def spectral_filter(
     mask: torch.Tensor | None,
     hw: tuple[int, int],
     out_scale: float,
+    out: torch.Tensor | None = None,
+    sums_into: tuple | None = None,
 ) -> torch.Tensor:
     """[rfft2 ->] mask -> irfft2 per (H, W) plane. Exactly one of real / spectrum is given.
 
     real: (..., H, W) float32; spectrum: (..., H, W//2+1) complex64; mask: (H, W//2+1) float32.
+    out: optional preallocated result (chunked callers). sums_into = (slot pointer, clear pointer or 0): accumulate
+    the moments into a slot the caller manages instead of taking one from the ring (the result is then not tagged).
     """
     H, W = hw
     wh = W // 2 + 1
@@ -647,7 +651,10 @@ def spectral_filter(
         _f32(mask, "mask")
         if mask.numel() != H * wh:
             raise ValueError(f"mask must have {H}x{wh} elements")
-    out = torch.empty((*lead, H, W), device=src.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((*lead, H, W), device=src.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (*lead, H, W):
+        raise ValueError(f"out must be float32 {(*lead, H, W)}")
     planes = out.numel() // (H * W)
     lib, stream = _prepare(src, mask, out)
     scratch = None
@@ -665,6 +672,11 @@ def spectral_filter(
     p.mask = 0 if mask is None else mask.data_ptr()
     p.scratch = 0 if scratch is None else scratch.data_ptr()
     p.planes, p.H, p.W, p.out_scale = planes, H, W, float(out_scale)
+    if sums_into is not None:
+        p.sums, p.sums_clear = sums_into
+        _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
+        drop_sums(out)
+        return out
     slot, p.sums, p.sums_clear = sums_slot(out.device)
     _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
     return _sums_written(out, slot)

@@ -25,7 +25,7 @@ def main() -> None:
     batch = 2 * world + 1  # ragged split on purpose
     torch.manual_seed(0)
     sigmas = torch.cat((torch.linspace(14.6, 0.5, 6), torch.zeros(1))).to(dev)
-    x_full = (torch.randn(batch, 4, 32, 48) * 14.6).to(dev)
+    x_image = (torch.randn(batch, 4, 32, 48) * 14.6).to(dev)
 
     def model(x, sigma, **_kw):
         return x * 0.9
@@ -44,7 +44,18 @@ def main() -> None:
         "dpmpp_sde/fused gaussian": (sb.samplers.SonarDPMPPSDE.sampler, {"sonar_params": {"noise_type": "gaussian"}}),
         "euler_ancestral/power+pyramid chain": (sb.samplers.SonarEulerAncestral.sampler, {"sonar_params": {"custom_noise": chain}}),
     }
+    # north-star config 5, scaled down: frames_to_channels power noise as the custom noise of sonar_dpmpp_sde (5-D latent)
+    video = ng.CustomNoiseChain()
+    inner = ng.CustomNoiseChain()
+    inner.add(sn.PowerNoiseItem(1.0, time_brownian=False, alpha=1.0, max_freq=0.7071, min_freq=0.0, stretch=1.0, rotate=0.0,
+                                pnorm=2.0, mix=1.0, common_mode=0.0, channel_correlation="1, 1, 1, 1, 1, 1"))
+    video.add(ng.CustomNoiseParametersNoise(
+        1.0, noise=inner, normalize=None, override_device=None, override_dtype=None, frames_to_channels=True,
+        ensure_square_aspect_ratio=False, fix_invalid=False, rng_mode="default", rng_offset_mode="disabled", rng_state_offset=0))
+    x_video = (torch.randn(batch, 4, 3, 18, 20) * 14.6).to(dev)
+    jobs["dpmpp_sde/C5 video power noise"] = (sb.samplers.SonarDPMPPSDE.sampler, {"sonar_params": {"custom_noise": video}})
     for name, (sampler, kw) in jobs.items():
+        x_full = x_video if "C5" in name else x_image
         want = run(sampler, x_full, **kw)
         with sb.parallel.sharded(batch) as ctx:
             assert sb.parallel.device_barrier() == (ctx.peers is not None)  # device-side rendezvous, no host sync

@@ -27,4 +27,4 @@ def test_sharded_equals_unsharded(transport):
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(REPO / "tests" / "multi_gpu_check.py")]  # fmt: skip
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, check=False)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
-    assert proc.stdout.count("OK ") == 3
+    assert proc.stdout.count("OK ") == 4

@@ -138,7 +138,7 @@ def test_channel_mix_kernel_vs_matmul(sb, cuda, shape):
     torch.manual_seed(shape[1])
     b, c, h, w = shape
     noise = torch.randn(shape)
-    mixer = orc.channel_mixer(c, 0.15, "1, 0.5, -0.25, 0.75")
+    mixer = orc.channel_mixer(c, 0.15, "1, 0.5, -0.25, 0.75").contiguous()  # (ldl_factor returns column-major storage)
     want = orc.channel_mix(noise.double(), mixer.double())
     got = sb.ops.channel_mix(noise.to(cuda), mixer.to(cuda), mixer)
     assert_close(got, want.float(), what=f"channel_mix {shape}")
