@@ -5,6 +5,7 @@ registers the three Sonar samplers when ComfyUI (`comfy`) is importable (referen
 Without ComfyUI (tests, bench) the compute modules are importable on their own:
 
     ops            tensor-level wrappers over the C ABI (include/sonar_b200.h)
+    torch_ops      the same entry points as torch.library custom ops (torch.ops.sonar_b200.*)
     generators     noise generators         (reference py/noise_generation.py)
     noise_graph    chains / items           (reference py/noise.py)
     spectral_noise power-law spectral noise (reference py/nodes/powernoise.py)
@@ -20,7 +21,7 @@ from __future__ import annotations
 
 import sys
 
-from . import _native, freeu, generators, hostutil, kdiff, noise_graph, ops, parallel, rng, samplers, spectral_noise, wavelets, wcfg
+from . import _native, freeu, generators, hostutil, kdiff, noise_graph, ops, parallel, rng, samplers, spectral_noise, torch_ops, wavelets, wcfg
 
 __version__ = "0.1.0"
 

@@ -369,6 +369,24 @@ def _build_if_possible() -> None:
     mod.build_library()
 
 
+def _warn_if_stale(path: Path) -> None:
+    """A library older than its sources runs old kernels silently: say so (a rebuild is `python build.py`)."""
+    try:
+        built = path.stat().st_mtime
+        deps = [*(PKG_DIR / "csrc").glob("*.cu"), *(PKG_DIR / "csrc").glob("*.cuh"), *(PKG_DIR.parent / "include").glob("*.h")]
+        newer = [d.name for d in deps if d.stat().st_mtime > built + 1.0]
+    except OSError:
+        return
+    if newer and path.parent == PKG_DIR:
+        import warnings
+
+        warnings.warn(
+            f"{path.name} is older than {', '.join(sorted(newer)[:4])}: rebuild with `python comfyui-sonar_b200/build.py`",
+            RuntimeWarning,
+            stacklevel=3,
+        )
+
+
 def load(*, build_if_missing: bool = True) -> ctypes.CDLL:
     """Loads the shared library (building it with nvcc first if it is absent). Raises loudly."""
     global _LIB  # noqa: PLW0603
@@ -385,6 +403,7 @@ def load(*, build_if_missing: bool = True) -> ctypes.CDLL:
             ) from exc
     if not path.exists():
         raise NativeLibraryError(f"{path} not found; sonar_b200 has no fallback path")
+    _warn_if_stale(path)
     try:
         lib = ctypes.CDLL(str(path))
     except OSError as exc:

@@ -255,6 +255,26 @@ __device__ __forceinline__ NormDecision decide_normalisation(const double* __res
   return d;
 }
 
+// Bounded spin on a peer flag: a rank that died, took another code path or issued its exchange on another
+// stream must not leave this GPU in a kernel that can never be killed. After kPeerWaitNs of waiting the kernel
+// traps -- the context fails loudly (cudaErrorLaunchFailure at the next API call) instead of hanging.
+constexpr unsigned long long kPeerWaitNs = 30ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void wait_for_epoch(const volatile double* flag, double epoch) {
+  if (*flag == epoch) return;
+  const unsigned long long t0 = global_timer_ns();
+  unsigned spins = 0;
+  while (*flag != epoch) {
+    if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > kPeerWaitNs) __trap();
+  }
+}
+
 // Batch-sharded statistics over peer memory (peer.cu): wait for the `world` partial sums of `epoch`
 // in the local mailbox, add them in rank order, take the same decision on every rank.
 // All threads of the block must call; `shared2` is 2 doubles of shared memory.
@@ -266,8 +286,7 @@ __device__ __forceinline__ NormDecision decide_normalisation_peers(const double*
     const volatile double* slots = mailbox + (size_t)parity * 8 * 4;
     double s = 0.0, ss = 0.0;
     for (int r = 0; r < world; ++r) {
-      while (slots[r * 4 + 2] != epoch) {
-      }
+      wait_for_epoch(&slots[r * 4 + 2], epoch);
       __threadfence();
       s += slots[r * 4 + 0];
       ss += slots[r * 4 + 1];

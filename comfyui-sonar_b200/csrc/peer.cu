@@ -61,8 +61,7 @@ peer_allreduce_table_kernel(PeerTargets targets, double* __restrict__ table, int
   volatile double* local = targets.box[rank];
   if (threadIdx.x < world) {
     const size_t s = kPairDoubles + ((size_t)parity * SONAR_PEER_MAX_RANKS + threadIdx.x) * kTableSlot;
-    while (local[s] != epoch) {
-    }
+    wait_for_epoch(&local[s], epoch);
     __threadfence_system();
   }
   __syncthreads();

@@ -239,20 +239,30 @@ _SUMS_RING: dict = {}
 _SUMS_RING_SLOTS = 256
 
 
+def _ring(device: torch.device) -> list:
+    """The ring of the (device, current stream) pair: the "producer of slot i clears slot i+1" argument is a
+    stream-order argument, so every stream gets its own ring. [slots, position, base pointer, launches so far]."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, _raw_stream(idx))
+    ring = _SUMS_RING.get(key)
+    if ring is None:
+        base = torch.zeros((_SUMS_RING_SLOTS, 2), device=device, dtype=torch.float64)
+        ring = _SUMS_RING[key] = [list(base.unbind(0)), 0, base.data_ptr(), 0]
+    return ring
+
+
 def sums_slot(device: torch.device) -> tuple[torch.Tensor, int, int]:
     """(slot tensor, its pointer, pointer of the slot to clear) -- call sums_advance(device) after the
     launch succeeded (a slot that was handed out but never written must stay zero)."""
-    ring = _SUMS_RING.get(device)
-    if ring is None:
-        base = torch.zeros((_SUMS_RING_SLOTS, 2), device=device, dtype=torch.float64)
-        ring = _SUMS_RING[device] = [list(base.unbind(0)), 0, base.data_ptr()]
-    slots, i, base_ptr = ring
+    slots, i, base_ptr, _ = _ring(device)
     return slots[i], base_ptr + 16 * i, base_ptr + 16 * ((i + 1) % _SUMS_RING_SLOTS)
 
 
-def sums_advance(device: torch.device) -> None:
-    ring = _SUMS_RING[device]
+def sums_advance(device: torch.device) -> list:
+    ring = _ring(device)
     ring[1] = (ring[1] + 1) % _SUMS_RING_SLOTS
+    ring[3] += 1
+    return ring
 
 
 def _sums_written(out: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
@@ -260,12 +270,14 @@ def _sums_written(out: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
     its slot stays untouched and is handed out again)."""
     if out.numel() == 0:
         return out
-    sums_advance(out.device)
-    return attach_sums(out, slot)
+    ring = sums_advance(out.device)
+    return attach_sums(out, slot, ring)
 
 
-def attach_sums(t: torch.Tensor, slot: torch.Tensor) -> torch.Tensor:
-    t._sonar_sums = (slot, t._version)  # noqa: SLF001
+def attach_sums(t: torch.Tensor, slot: torch.Tensor, ring: list | None = None) -> torch.Tensor:
+    # (slot, tensor version, ring, ring launch count when the slot was filled): the slot is recycled -- cleared by the
+    # producer of the previous slot, refilled by a later one -- once the ring has gone round, so the tag expires then
+    t._sonar_sums = (slot, t._version, ring, 0 if ring is None else ring[3])  # noqa: SLF001
     return t
 
 
@@ -273,6 +285,9 @@ def attached_sums(t: torch.Tensor) -> torch.Tensor | None:
     tag = getattr(t, "_sonar_sums", None)
     if tag is None or tag[1] != t._version:  # noqa: SLF001
         return None
+    ring = tag[2]
+    if ring is not None and ring[3] - tag[3] >= _SUMS_RING_SLOTS - 1:
+        return None  # stale: the ring wrapped since this tensor was produced
     return tag[0]
 
 
@@ -281,7 +296,8 @@ def reshape_keep_sums(t: torch.Tensor, shape) -> torch.Tensor:
     out = t.reshape(shape)
     slot = attached_sums(t)
     if slot is not None and out is not t and out.data_ptr() == t.data_ptr():
-        attach_sums(out, slot)
+        tag = t._sonar_sums  # noqa: SLF001
+        out._sonar_sums = (slot, out._version, tag[2], tag[3])  # noqa: SLF001
     return out
 
 

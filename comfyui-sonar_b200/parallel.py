@@ -114,7 +114,7 @@ def peer_exchange(rank: int, world_size: int, group=None) -> PeerExchange | None
     ranks cannot share memory (no NCCL / CUDA, or SONAR_B200_NO_PEER set)."""
     import os
 
-    key = id(group)
+    key = (id(group), dist.get_world_size(group) if dist.is_initialized() else world_size, rank)
     if key in _PEERS:
         return _PEERS[key]
     ok = (
@@ -170,6 +170,10 @@ def sharded(total_batch: int, *, rank: int | None = None, world_size: int | None
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world_size is None:
         world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+    if total_batch < world_size:
+        # a rank without items would skip the statistics exchange its peers wait for (and stop advancing its replicated
+        # generator): refuse the split instead of hanging
+        raise ValueError(f"cannot shard a batch of {total_batch} over {world_size} ranks: every rank needs at least one item")
     ctx = ShardContext(rank=rank, world_size=world_size, batch_sizes=split_sizes(total_batch, world_size), group=group)
     ctx.peers = peer_exchange(rank, world_size, group)
     prev, _ACTIVE = _ACTIVE, ctx

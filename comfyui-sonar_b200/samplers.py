@@ -629,6 +629,17 @@ class SonarSampler(SonarWithGuidance):
         return x
 
     @classmethod
+    def _sample(cls, ctor_args: tuple, model, x, sigmas, extra_args, callback, disable, noise_sampler, sonar_config, sonar_params):
+        """Body of the public sampler functions. Latents in another float format (fp16 / bf16 / fp64 models) are
+        sampled in float32 -- the kernels' arithmetic type -- and the result is cast back."""
+        latent_dtype = x.dtype
+        if x.is_cuda and latent_dtype in (torch.float16, torch.bfloat16, torch.float64):
+            x = x.to(torch.float32)
+        sonar = cls._build(ctor_args, model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
+        out = sonar.run(x, callback, disable)
+        return out if out.dtype == latent_dtype else out.to(latent_dtype)
+
+    @classmethod
     def _build(cls, ctor_args: tuple, model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params):
         sonar_config = cls.get_config(sonar_config, sonar_params)
         s_in = x.new_ones((x.shape[0],))
@@ -700,8 +711,7 @@ class SonarEuler(SonarSampler):
         sonar_config: SonarConfig | None = None,
         sonar_params: dict | None = None,
     ) -> Tensor:
-        sonar = cls._build((), model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
-        return sonar.run(x, callback, disable)
+        return cls._sample((), model, x, sigmas, extra_args, callback, disable, noise_sampler, sonar_config, sonar_params)
 
 
 class SonarEulerAncestral(SonarSampler):
@@ -766,8 +776,7 @@ class SonarEulerAncestral(SonarSampler):
         s_noise=1.0,
         noise_sampler: Callable | None = None,
     ):
-        sonar = cls._build((eta, s_noise), model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
-        return sonar.run(x, callback, disable)
+        return cls._sample((eta, s_noise), model, x, sigmas, extra_args, callback, disable, noise_sampler, sonar_config, sonar_params)
 
 
 class SonarDPMPPSDE(SonarSampler):
@@ -875,8 +884,7 @@ class SonarDPMPPSDE(SonarSampler):
         s_noise=1.0,
         noise_sampler=None,
     ) -> Tensor:
-        sonar = cls._build((eta, s_noise), model, x, sigmas, extra_args, noise_sampler, sonar_config, sonar_params)
-        return sonar.run(x, callback, disable)
+        return cls._sample((eta, s_noise), model, x, sigmas, extra_args, callback, disable, noise_sampler, sonar_config, sonar_params)
 
 
 EXTRA_SAMPLERS = {

@@ -297,3 +297,27 @@ def test_producer_kernels_hand_over_their_moments(sb, cuda):
     t = sb.ops.blend(a, b, 0.3)
     v = sb.ops.reshape_keep_sums(t, (3, 4, 33 * 40))
     assert sb.ops.attached_sums(v) is not None
+
+
+def test_attached_sums_expire_when_the_ring_wraps(sb, cuda):
+    """the producer-side statistics live in a 256-slot ring; a tensor held across a full turn of the ring
+    must not be normalised with another tensor's sums."""
+    a = torch.randn(4, 256, device=cuda)
+    held = sb.ops.axpby(a, 2.0, None)
+    slot = sb.ops.attached_sums(held)
+    assert slot is not None
+    want = torch.stack((held.double().sum(), held.double().square().sum()))
+    torch.testing.assert_close(slot, want, rtol=1e-9, atol=1e-9)
+    for _ in range(260):
+        sb.ops.axpby(a, 1.0, None)
+    assert sb.ops.attached_sums(held) is None
+    got = sb.hostutil.scale_noise(held.clone(), 1.0, normalized=True)  # falls back to its own moments pass
+    assert_close(got, orc.scale_noise(held.cpu().clone(), 1.0, normalized=True), what="stale tag ignored")
+    # a second stream gets a ring of its own
+    side = torch.cuda.Stream(device=cuda)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        other = sb.ops.axpby(a, 3.0, None)
+        s2 = sb.ops.attached_sums(other)
+    side.synchronize()
+    torch.testing.assert_close(s2, torch.stack((other.double().sum(), other.double().square().sum())), rtol=1e-9, atol=1e-9)

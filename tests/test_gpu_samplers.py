@@ -262,3 +262,13 @@ def test_guidance_kernels_vs_oracle(sb, cuda):
         got = sb.ops.guidance(xd, rd, sb.ops.item_moments(dd), kind=sb.ops.GUIDANCE_EULER, sigma=7.0,
                               dt=float((sigma_next - sigma) * 0.3))
         assert_close(got, want, what=f"euler {shape}")
+
+
+def test_half_precision_latents_are_sampled_in_fp32(sb, cuda, golden):
+    """fp16 / bf16 latents (what ComfyUI hands over for half-precision models) run through the fp32 kernels and come
+    back in their own dtype instead of raising."""
+    g = golden("samplers")
+    want = sb.samplers.SonarEuler.sampler(stub_model, g["x0"].to(cuda).half().float(), g["sigmas"].to(cuda), extra_args={}, disable=True)
+    got = sb.samplers.SonarEuler.sampler(stub_model, g["x0"].to(cuda).half(), g["sigmas"].to(cuda), extra_args={}, disable=True)
+    assert got.dtype == torch.float16
+    assert torch.equal(got, want.half())

@@ -248,3 +248,14 @@ def test_host_schedule_copy_is_cached_per_tensor_object(sb):
     del b
     assert torch.equal(samplers._host_schedule(a), a)  # cache slot now points at a dead tensor: recopied
     assert samplers._host_schedule(a.double()).dtype == torch.float32
+
+
+def test_sharding_rejects_a_batch_smaller_than_the_world(sb):
+    """a rank with an empty shard would skip the exchanges its peers wait for."""
+    import pytest
+
+    with pytest.raises(ValueError, match="at least one item"):
+        with sb.parallel.sharded(1, rank=0, world_size=2):
+            pass
+    with sb.parallel.sharded(5, rank=1, world_size=2) as ctx:
+        assert ctx.batch_sizes == [3, 2] and ctx.batch_begin == 3
