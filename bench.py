@@ -53,7 +53,7 @@ sys.path.insert(0, str(REPO))
 SHAPE = (int(os.environ.get("SONAR_BENCH_ITEMS", "8")), 16, 33, 90, 160)
 ITEM_ELEMS = SHAPE[1] * SHAPE[2] * SHAPE[3] * SHAPE[4]
 N_SAMPLER_STEPS = 10
-FLUSH_PASSES = 4  # 256 MiB zero-fills per stub-denoiser call: L2 eviction + device time for the host to run ahead
+FLUSH_PASSES = 16  # 256 MiB zero-fills per stub-denoiser call: L2 eviction + device time for the host to run ahead
 ELEMS_PER_RUN = N_SAMPLER_STEPS * SHAPE[0] * ITEM_ELEMS
 WORKLOAD = (
     "C5 video latent 8x16x33x90x160: sonar_dpmpp_sde with frames_to_channels power noise (alpha=1) as custom noise, "
@@ -300,14 +300,16 @@ def sampler_run(sb, model, x0, sigmas, chain):
 
 # which launches of the C5 run are which kernel, and their algorithmic bytes per element of the tensor they produce
 C5_KERNELS = {
-    "sonar_spectral_filter_f32": ("spectral_batched_kernel (power-noise sample: Philox spectrum -> gain -> irfft2 -> moments)", BYTES_NOISE),
+    "sonar_spectral_filter_f32": ("spectral_batched_kernel (power-noise sample: gain -> irfft2 -> moments; its complex Philox draw is sonar_philox_*)", BYTES_NOISE),
     "sonar_step_f32": ("sonar_step_fast_vec_kernel (fused half step, noise normalised on load)", BYTES_STEP),
 }
 
 
 def traced_breakdown(sb, run, n_local_elems: int, peak: float, peak_src: str, reps: int) -> tuple[dict, list]:
     """Per-kernel CUDA-event timing of the C5 run (ops.TRACE brackets every C-ABI launch on the launching stream).
-    Returns the roofline block of the kernel with the largest share and the table of all kernels."""
+    Returns the roofline block of the kernel with the largest share and the table of all kernels. Launches may batch
+    several units (look-ahead: several noise samples per FFT launch), so bytes are counted per run and divided by
+    the launches of the run."""
     per: dict[str, list[float]] = {}
     for _ in range(reps):
         sb.ops.TRACE = []
@@ -317,15 +319,17 @@ def traced_breakdown(sb, run, n_local_elems: int, peak: float, peak_src: str, re
         for name, a, b in trace:
             per.setdefault(name, []).append(a.elapsed_time(b) * 1e3)
     total = sum(sum(v) for v in per.values())
+    units = {"sonar_spectral_filter_f32": 2 * (N_SAMPLER_STEPS - 1), "sonar_step_f32": 2 * (N_SAMPLER_STEPS - 1) + 1}
     table = []
     for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         label, bytes_per_el = C5_KERNELS.get(name, (name, None))
-        row = {"entry_point": name, "kernel": label, "launches_per_run": len(v) // reps, "mean_us": statistics.mean(v),
-               "share_of_timed_region": sum(v) / total}  # fmt: skip
+        launches = len(v) // reps
+        row = {"entry_point": name, "kernel": label, "launches_per_run": launches, "mean_us": statistics.mean(v),
+               "us_per_run": sum(v) / reps, "share_of_timed_region": sum(v) / total}  # fmt: skip
         if bytes_per_el is not None:
-            algo = bytes_per_el * n_local_elems
-            row |= {"algorithmic_bytes_per_launch": algo, "achieved_gbs": algo / (statistics.mean(v) * 1e-6) / 1e9,
-                    "frac": algo / (statistics.mean(v) * 1e-6) / 1e9 / peak}  # fmt: skip
+            algo = bytes_per_el * n_local_elems * units[name] / launches  # per launch
+            row |= {"units_per_run": units[name], "algorithmic_bytes_per_launch": algo,
+                    "achieved_gbs": algo / (statistics.mean(v) * 1e-6) / 1e9, "frac": algo / (statistics.mean(v) * 1e-6) / 1e9 / peak}  # fmt: skip
         table.append(row)
     top = next(r for r in table if "frac" in r)
     roofline = {

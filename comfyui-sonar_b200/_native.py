@@ -64,7 +64,7 @@ class SonarStepParams(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 3  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
+ABI_VERSION = 4  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
@@ -161,6 +161,13 @@ class SonarSpectralParams(ctypes.Structure):
         ("out_scale", c_float),
         ("sums", c_void_p),
         ("sums_clear", c_void_p),
+        ("sums_segment_planes", c_int64),
+        ("philox_seed", c_uint64),
+        ("philox_offset", c_uint64),
+        ("philox_grid_blocks", c_uint32),
+        ("philox_std", c_float),
+        ("philox_begin", c_int64),
+        ("philox_numel_total", c_int64),
     ]
 
 

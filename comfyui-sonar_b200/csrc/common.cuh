@@ -213,6 +213,12 @@ __device__ __forceinline__ float2 philox_normal2_lo(const PhiloxStream& s, uint3
   return _curand_box_muller(r.x, r.y);
 }
 
+// One lane of curand_normal4: lanes 0, 1 are the Box-Muller pair of (r.x, r.y), lanes 2, 3 of (r.z, r.w)
+__device__ __forceinline__ float philox_normal_lane(const uint4& r, int lane) {
+  const float2 n = _curand_box_muller(lane < 2 ? r.x : r.z, lane < 2 ? r.y : r.w);
+  return (lane & 1) ? n.y : n.x;
+}
+
 // curand_uniform4 (values in (0, 1])
 __device__ __forceinline__ float4 philox_uniform4(const PhiloxStream& s, uint32_t thread, uint64_t call) {
   return _curand_uniform4(philox_raw(s, thread, call));

@@ -213,6 +213,8 @@ spectral_plane_kernel(SpectralLaunch L) {
   __syncthreads();
 
   float ms = 0.0f, mss = 0.0f;  // moments of everything this thread writes
+  __shared__ double seg_sums[2 * SONAR_SPECTRAL_MAX_SEGMENTS];  // per-segment statistics, see spectral_batched_kernel
+  if (threadIdx.x < 2 * SONAR_SPECTRAL_MAX_SEGMENTS) seg_sums[threadIdx.x] = 0.0;
   for (int64_t plane = blockIdx.x; plane < p.planes; plane += gridDim.x) {
     // ---------------- phase A: fill S ----------------
     if (p.in_real != nullptr) {
@@ -309,9 +311,21 @@ spectral_plane_kernel(SpectralLaunch L) {
       }
       __syncwarp();
     }
+    if (p.sums != nullptr) {
+      const float ws = warp_sum(ms), wss = warp_sum(mss);
+      if (lane == 0) {
+        const int seg = p.sums_segment_planes > 0 ? (int)(plane / p.sums_segment_planes) : 0;
+        atomicAdd(&seg_sums[2 * seg], (double)ws);
+        atomicAdd(&seg_sums[2 * seg + 1], (double)wss);
+      }
+      ms = mss = 0.0f;
+    }
     __syncthreads();
   }
-  commit_moments(p.sums, p.sums_clear, ms, mss);
+  if (p.sums != nullptr) {
+    if (threadIdx.x < 2 * SONAR_SPECTRAL_MAX_SEGMENTS && seg_sums[threadIdx.x] != 0.0) atomicAdd(&p.sums[threadIdx.x], seg_sums[threadIdx.x]);
+    if (p.sums_clear != nullptr && blockIdx.x == 0 && threadIdx.x < 2) p.sums_clear[threadIdx.x] = 0.0;
+  }
 }
 
 // =============================================================================================
@@ -373,6 +387,7 @@ struct SpectralBatchedLaunch {
   int group;        // planes per CTA pass
   float scale;      // out_scale (x 1/2 for real input: the r2c unfold leaves a factor 2)
   unsigned magic_wh, magic_cols, magic_rows, magic_row_nb;  // ceil(2^32 / d): d = wh, group * wh, group * H, M / last row radix
+  unsigned long long magic_T;  // floor(2^64 / T) + 1, T = threads of the emulated ATen launch (Philox input)
 };
 
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 w) {  // a * conj(w)
@@ -520,7 +535,8 @@ enum StageSource : int {
   SRC_CONJ_IN = 1,    // own slots, conjugated
   SRC_SPECTRUM = 2,   // first inverse column stage, spectrum input: global half spectrum (.) gain mask
   SRC_CONJ_MASK = 3,  // first inverse column stage, real input: conj(forward result) (.) gain mask
-  SRC_REAL_ROWS = 4   // first forward row stage: packed pairs (x[2n], -x[2n+1]) gathered from the global real plane
+  SRC_REAL_ROWS = 4,  // first forward row stage: packed pairs (x[2n], -x[2n+1]) gathered from the global real plane
+  SRC_PHILOX = 5      // first inverse column stage: torch.randn(complex64) regenerated from the Philox stream (.) gain mask
 };
 enum StageSink : int {
   SINK_SLOTS = 0,  // back into the butterfly's own slots
@@ -548,6 +564,10 @@ struct StageArgs {
   int group;                    // planes per pass the kernel was launched with (1: no plane split of b)
   int wh, pitch, plane_elems, M;
   int spec_plane_elems;         // H * wh (global spectrum plane)
+  // SRC_PHILOX: float index (in the global draw) of the group's first plane; the draw itself is read from the
+  // launch block in the constant bank (no registers in the kernels that do not use it)
+  int64_t philox_first;
+  const SpectralBatchedLaunch* launch;
 };
 
 // One in-place inverse-sign stage over a batch of transforms: every (butterfly j, transform b) item owns
@@ -599,6 +619,31 @@ __device__ __forceinline__ void run_stage(StageArgs& a) {
       for (int t = 0; t < R; ++t) {
         const int off = (int)a.idx_h[first_slot + t] * a.wh;
         v[t] = __ldg(gp + off);
+        if (has_mask) {
+          const float gain = __ldg(mp + off);
+          v[t].x *= gain;
+          v[t].y *= gain;
+        }
+      }
+    } else if (SOURCE == SRC_PHILOX) {
+      // element (g, row, c) of the local tensor is complex number e = (g * H + row) * wh + c, floats 2e and 2e + 1 of
+      // the draw; float li is lane (li / T) % 4 of call (li / T) / 4 of Philox subsequence li % T. T is even, so
+      // both floats of a complex number share the call index and the lane.
+      const float* mp = a.mask + c;
+      const bool has_mask = a.mask != nullptr;
+      const int64_t e0 = a.philox_first + 2 * ((int64_t)g * a.spec_plane_elems + c);
+      const SonarSpectralParams& pp = a.launch->p;
+      const PhiloxStream st{pp.philox_seed, pp.philox_offset, pp.philox_grid_blocks * (uint32_t)kBlock};
+      const float std = pp.philox_std;
+#pragma unroll
+      for (int t = 0; t < R; ++t) {
+        const int off = (int)a.idx_h[first_slot + t] * a.wh;
+        const uint64_t li = (uint64_t)(e0 + 2 * off);
+        const uint64_t q = __umul64hi(li, a.launch->magic_T);
+        const uint32_t vt = (uint32_t)(li - q * st.threads);
+        const int lane = (int)(q & 3u);
+        const uint4 r0 = philox_raw(st, vt, q >> 2), r1 = philox_raw(st, vt + 1u, q >> 2);
+        v[t] = make_float2(philox_normal_lane(r0, lane) * std, philox_normal_lane(r1, lane) * std);
         if (has_mask) {
           const float gain = __ldg(mp + off);
           v[t].x *= gain;
@@ -764,9 +809,12 @@ __device__ void build_axis_tables(const AxisPlan& plan, ushort2* __restrict__ ta
 
 __host__ __device__ __forceinline__ unsigned magic_of(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); }
 
-template <bool REAL>
+enum SpectralInput : int { INPUT_SPECTRUM = 0, INPUT_REAL = 1, INPUT_PHILOX = 2 };
+
+template <int INPUT>
 __global__ void __launch_bounds__(kBatchedThreads, 2)
-spectral_batched_kernel(SpectralBatchedLaunch L) {
+spectral_batched_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
+  constexpr bool REAL = INPUT == INPUT_REAL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SonarSpectralParams& p = L.p;
   const int H = p.H, W = p.W, M = W >> 1, Wh = L.wh, P = L.pitch, G = L.group;
@@ -809,6 +857,12 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
   a.scale = L.scale;
   a.ms = 0.0f;
   a.mss = 0.0f;
+  a.launch = &L;
+  // Statistics of what the CTA stores: after every group each warp adds its partials to a shared fp64 pair of the
+  // group's segment (a run of sums_segment_planes planes = one noise sample; the planner lets no group straddle two),
+  // and the CTA flushes the pairs it touched with one global atomic each at the end.
+  __shared__ double seg_sums[2 * SONAR_SPECTRAL_MAX_SEGMENTS];
+  if (threadIdx.x < 2 * SONAR_SPECTRAL_MAX_SEGMENTS) seg_sums[threadIdx.x] = 0.0;  // (ordered by the barriers of the first stage)
   int magic_for = G;
   unsigned magic_cols = L.magic_cols, magic_rows = L.magic_rows;
   for (int64_t plane0 = (int64_t)blockIdx.x * G; plane0 < p.planes; plane0 += (int64_t)gridDim.x * G) {
@@ -819,7 +873,7 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
       magic_for = valid;
     }
     const int rows_total = valid * H;
-    if (REAL) {
+    if constexpr (REAL) {
       // forward rows (half length, conj trick; the block-length-R stage gathers the packed real rows from
       // global memory), r2c unfold, forward columns: conj rfft2 with ky at slot pos_h[ky]
       a.real_rows = reinterpret_cast<const float2*>(p.in_real + plane0 * (int64_t)H * W);
@@ -835,6 +889,13 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
       run_axis_dif<SINK_SLOTS, true>(L.col, a, tab_col);
       // gain, then inverse columns back to natural row order
       run_axis_dit<SRC_CONJ_MASK, true>(L.col, a, tab_col);
+    } else if constexpr (INPUT == INPUT_PHILOX) {
+      // inverse columns whose block-length-R stage draws the half spectrum from the Philox stream in registers
+      a.philox_first = p.philox_begin + 2 * plane0 * (int64_t)H * Wh;
+      a.tw = tw_h;
+      a.nbatch = valid * Wh;
+      a.magic_batch = magic_cols;
+      run_axis_dit<SRC_PHILOX, true>(L.col, a, tab_col);
     } else {
       // inverse columns: the block-length-R stage gathers the rows of the global half spectrum into
       // digit-reversed row slots (coalesced along k) and applies the gain on the fly
@@ -853,8 +914,21 @@ spectral_batched_kernel(SpectralBatchedLaunch L) {
     a.nbatch = rows_total;
     a.magic_batch = magic_rows;
     run_axis_dif<SINK_GLOBAL, false>(L.row, a, tab_row);
+    if (p.sums != nullptr) {
+      const float ws = warp_sum(a.ms), wss = warp_sum(a.mss);
+      if ((threadIdx.x & 31) == 0) {
+        const int seg = p.sums_segment_planes > 0 ? (int)(plane0 / p.sums_segment_planes) : 0;
+        atomicAdd(&seg_sums[2 * seg], (double)ws);
+        atomicAdd(&seg_sums[2 * seg + 1], (double)wss);
+      }
+      a.ms = a.mss = 0.0f;
+    }
   }
-  commit_moments(p.sums, p.sums_clear, a.ms, a.mss);
+  if (p.sums != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 2 * SONAR_SPECTRAL_MAX_SEGMENTS && seg_sums[threadIdx.x] != 0.0) atomicAdd(&p.sums[threadIdx.x], seg_sums[threadIdx.x]);
+    if (p.sums_clear != nullptr && blockIdx.x == 0 && threadIdx.x < 2) p.sums_clear[threadIdx.x] = 0.0;
+  }
 }
 
 // Fewest stages over the radix set, ties broken by the smaller radix sum (8 x 8 before 16 x 4).
@@ -940,7 +1014,11 @@ static bool plan_spectral_batched(const SonarSpectralParams& p, SpectralBatchedL
                        (p.planes + group - 1) / group < (int64_t)di.sm_count * ctas_that_fit((int)group)))
     --group;
   if (group < 1) group = 1;
+  while (group > 1 && p.sums_segment_planes > 0 && p.sums_segment_planes % group != 0) --group;  // no group straddles a segment
   L.group = (int)group;
+  L.magic_T = 0;
+  if (p.philox_grid_blocks != 0)
+    L.magic_T = ~0ull / ((unsigned long long)p.philox_grid_blocks * kBlock) + 1ull;  // floor(2^64 / T) + 1 (T is no power of two > 2^63)
   // index arithmetic: 16-bit slot tables, 32-bit magic division exact for w * d < 2^32
   const int64_t nbatch_max = group * (L.wh > p.H ? L.wh : p.H);
   const int64_t items_max = nbatch_max * ((p.H > M ? p.H : M) / 2);
@@ -970,7 +1048,9 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   int64_t grid = 0;
   size_t smem = 0;
   if (!plan_spectral_batched(p, &L, &threads, &ctas_per_sm, &grid, &smem)) return -1;
-  auto kernel = p.in_real != nullptr ? spectral_batched_kernel<true> : spectral_batched_kernel<false>;
+  auto kernel = p.in_real != nullptr   ? spectral_batched_kernel<INPUT_REAL>
+                : p.in_spec != nullptr ? spectral_batched_kernel<INPUT_SPECTRUM>
+                                       : spectral_batched_kernel<INPUT_PHILOX>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
   kernel<<<(unsigned)grid, threads, smem, stream>>>(L);
@@ -1071,12 +1151,21 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) 
   L.p = *params;
   const SonarSpectralParams& p = L.p;
   if (p.planes <= 0) return 0;
-  if (p.H <= 0 || p.W <= 0 || p.out == nullptr) return (int)cudaErrorInvalidValue;
-  if ((p.in_real == nullptr) == (p.in_spec == nullptr)) return (int)cudaErrorInvalidValue;
+  if (p.H <= 0 || p.W <= 0 || p.out == nullptr || p.sums_segment_planes < 0) return (int)cudaErrorInvalidValue;
+  if (p.sums_segment_planes > 0 && (p.planes + p.sums_segment_planes - 1) / p.sums_segment_planes > SONAR_SPECTRAL_MAX_SEGMENTS)
+    return (int)cudaErrorInvalidValue;
+  if (p.in_real != nullptr && p.in_spec != nullptr) return (int)cudaErrorInvalidValue;
+  const bool philox = p.in_real == nullptr && p.in_spec == nullptr;
+  if (philox) {
+    const int64_t floats = 2 * p.planes * (int64_t)p.H * (p.W / 2 + 1);
+    if (p.philox_grid_blocks == 0 || p.philox_begin < 0 || (p.philox_begin & 1) || p.philox_begin + floats > p.philox_numel_total)
+      return (int)cudaErrorInvalidValue;
+  }
   {
     const int rc = launch_spectral_batched(p, (cudaStream_t)stream_);
     if (rc >= 0) return rc;
   }
+  if (philox) return (int)cudaErrorInvalidValue;  // only the batched kernel regenerates its input (even W, radices 2..16)
   if (!make_plan(p.H, &L.plan_h) || !make_plan(p.W, &L.plan_w)) return (int)cudaErrorInvalidValue;
   L.wh = p.W / 2 + 1;
   L.wh_pad = L.wh | 1;

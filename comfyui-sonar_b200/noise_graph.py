@@ -158,6 +158,12 @@ class CustomNoiseChain:
         # A consumer that applies scale_noise itself while reading the tensor (the fused Sonar step
         # normalises on load) asks for the un-normalised sum and what is still owed to it.
         noise_sampler.deferred = lambda sigma, sigma_next: (accumulate(sigma, sigma_next), factor, normalized)
+        # Look-ahead (see PowerNoiseItem.make_noise_sampler): a chain of ONE sigma-independent item hands its child's
+        # batches through; `pending` = what this level still owes each sample, applied by whoever consumes it.
+        child_lookahead = getattr(samplers[0], "lookahead", None) if len(samplers) == 1 else None
+        if child_lookahead is not None:
+            noise_sampler.lookahead = child_lookahead
+            noise_sampler.lookahead_pending = (factor, normalized)
         return noise_sampler
 
 
@@ -582,6 +588,24 @@ class CustomNoiseParametersNoise(_ChildHolder):
                 noise = noise.to(device=orig_device, dtype=orig_dtype)
             return scale_noise(noise, factor, normalized=normalize)
 
+        child_lookahead = getattr(ns, "lookahead", None)
+        child_pending = getattr(ns, "lookahead_pending", (1.0, False))
+        if (
+            child_lookahead is not None
+            and child_pending == (1.0, False)
+            and factor == 1
+            and not normalize
+            and not fix_invalid
+            and not fixed_aspect
+            and x.dtype == orig_dtype
+            and x.device == orig_device
+        ):
+            # a pure reshape around the child: its look-ahead batches pass through as views of the original shape
+            def lookahead(count: int):
+                batch = child_lookahead(count)
+                return None if batch is None else [(raw.reshape(orig_shape), sums, draw) for raw, sums, draw in batch]
+
+            noise_sampler.lookahead = lookahead
         return noise_sampler
 
 

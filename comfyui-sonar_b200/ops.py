@@ -140,6 +140,19 @@ def reserve_draw(numel: int, device: torch.device, generator: torch.Generator | 
     return PhiloxDraw(gen.initial_seed(), offset, grid, int(numel), inc)
 
 
+def peek_draws(numel: int, device: torch.device, count: int, generator: torch.Generator | None = None) -> list[PhiloxDraw]:
+    """The next `count` draws of `numel` values each, as consecutive torch calls would make them, WITHOUT advancing
+    the generator (speculative look-ahead: the caller advances it draw by draw as the values are consumed, and
+    discards the rest if somebody else used the generator in between)."""
+    if not isinstance(device, torch.device):
+        device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = generator if generator is not None else torch.cuda.default_generators[idx]
+    grid, inc = philox_policy_cached(idx, numel)
+    offset, seed = gen.get_offset(), gen.initial_seed()
+    return [PhiloxDraw(seed, offset + j * inc, grid, int(numel), inc) for j in range(count)]
+
+
 def philox_fill(
     draw: PhiloxDraw,
     out: torch.Tensor,
@@ -637,49 +650,56 @@ def spectral_filter(
     *,
     real: torch.Tensor | None = None,
     spectrum: torch.Tensor | None = None,
+    philox: tuple | None = None,
     mask: torch.Tensor | None,
     hw: tuple[int, int],
     out_scale: float,
     out: torch.Tensor | None = None,
     sums_into: tuple | None = None,
-) -> torch.Tensor:
-    """[rfft2 ->] mask -> irfft2 per (H, W) plane. Exactly one of real / spectrum is given.
+    segment_planes: int | None = None,
+):
+    """[rfft2 ->] mask -> irfft2 per (H, W) plane. Exactly one of real / spectrum / philox is given.
 
     real: (..., H, W) float32; spectrum: (..., H, W//2+1) complex64; mask: (H, W//2+1) float32.
-    out: optional preallocated result (chunked callers). sums_into = (slot pointer, clear pointer or 0): accumulate
-    the moments into a slot the caller manages instead of taking one from the ring (the result is then not tagged).
+    philox = (draw, begin, std, lead_shape, device): the half spectrum is torch.randn(complex64) regenerated inside
+    the kernel from `draw` (floats [begin, begin + 2 * planes * H * (W//2+1)) of it), never stored.
+    out: optional preallocated result. sums_into = (slot pointer, clear pointer or 0): accumulate the moments into a
+    slot the caller manages instead of taking one from the ring (the result is then not tagged).
+    segment_planes: the planes form runs of this many planes (one noise sample each); returns (out, table) with
+    table (n_segments, 2) float64 = {sum, sum of squares} of each run.
     """
     H, W = hw
     wh = W // 2 + 1
-    src = real if real is not None else spectrum
-    if (real is None) == (spectrum is None):
-        raise ValueError("give exactly one of real / spectrum")
+    if (real is not None) + (spectrum is not None) + (philox is not None) != 1:
+        raise ValueError("give exactly one of real / spectrum / philox")
     if real is not None:
         _f32(real, "real")
         if tuple(real.shape[-2:]) != (H, W):
             raise ValueError("real input plane size mismatch")
-        lead = real.shape[:-2]
-    else:
+        lead, device = real.shape[:-2], real.device
+    elif spectrum is not None:
         if spectrum.dtype != torch.complex64 or tuple(spectrum.shape[-2:]) != (H, wh):
             raise ValueError(f"spectrum must be complex64 (..., {H}, {wh})")
-        lead = spectrum.shape[:-2]
+        lead, device = spectrum.shape[:-2], spectrum.device
+    else:
+        lead, device = tuple(philox[3]), philox[4]
     if mask is not None:
         _f32(mask, "mask")
         if mask.numel() != H * wh:
             raise ValueError(f"mask must have {H}x{wh} elements")
     if out is None:
-        out = torch.empty((*lead, H, W), device=src.device, dtype=torch.float32)
+        out = torch.empty((*lead, H, W), device=device, dtype=torch.float32)
     elif out.dtype != torch.float32 or tuple(out.shape) != (*lead, H, W):
         raise ValueError(f"out must be float32 {(*lead, H, W)}")
     planes = out.numel() // (H * W)
-    lib, stream = _prepare(src, mask, out)
+    lib, stream = _prepare(real, spectrum, mask, out)
     scratch = None
     need = lib.sonar_spectral_scratch_bytes(H, W)
     if need > 0:
-        key = (src.device, H, W)
+        key = (device, H, W)
         scratch = _SPECTRAL_SCRATCH.get(key)
         if scratch is None:
-            scratch = torch.empty(need, device=src.device, dtype=torch.uint8)
+            scratch = torch.empty(need, device=device, dtype=torch.uint8)
             _SPECTRAL_SCRATCH[key] = scratch
     p = _native.SonarSpectralParams()
     p.out = out.data_ptr()
@@ -688,6 +708,18 @@ def spectral_filter(
     p.mask = 0 if mask is None else mask.data_ptr()
     p.scratch = 0 if scratch is None else scratch.data_ptr()
     p.planes, p.H, p.W, p.out_scale = planes, H, W, float(out_scale)
+    if philox is not None:
+        draw, begin, std = philox[:3]
+        p.philox_seed, p.philox_offset, p.philox_grid_blocks = draw.seed, draw.offset, draw.grid_blocks
+        p.philox_std, p.philox_begin, p.philox_numel_total = float(std), int(begin), draw.numel
+    if segment_planes is not None:
+        if planes % segment_planes:
+            raise ValueError("segment_planes must divide the plane count")
+        table = torch.zeros((planes // segment_planes, 2), device=device, dtype=torch.float64)
+        p.sums, p.sums_clear, p.sums_segment_planes = table.data_ptr(), 0, int(segment_planes)
+        _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
+        drop_sums(out)
+        return out, table
     if sums_into is not None:
         p.sums, p.sums_clear = sums_into
         _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
@@ -696,6 +728,22 @@ def spectral_filter(
     slot, p.sums, p.sums_clear = sums_slot(out.device)
     _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
     return _sums_written(out, slot)
+
+
+FILL_BATCH_MAX = _native.FILL_BATCH_MAX
+_PLAN_CACHE: dict = {}
+
+
+def spectral_plan_batched(height: int, width: int, planes: int) -> bool:
+    """True when sonar_spectral_filter_f32 runs (height, width) planes on the batched shared-memory kernel (even
+    width, lengths factoring into radices 2..16) -- the form that can regenerate its input from the Philox stream."""
+    key = (height, width, planes)
+    hit = _PLAN_CACHE.get(key)
+    if hit is None:
+        info = _native.SonarSpectralPlanInfo()
+        _native.check(_native.load().sonar_spectral_plan(height, width, planes, 0, ctypes.byref(info)), "sonar_spectral_plan")
+        hit = _PLAN_CACHE[key] = bool(info.batched)
+    return hit
 
 
 def channel_mix(noise: torch.Tensor, mixer: torch.Tensor, mixer_host: torch.Tensor | None = None) -> torch.Tensor:

@@ -491,6 +491,9 @@ class SonarBase:
         """kwargs for fused_step that add noise_sampler(sigma, sigma_next) * scale."""
         spec = self._fused_noise_spec(x)
         if spec is None:
+            ahead = self._lookahead_noise(x)
+            if ahead is not None:
+                return {"noise_deferred": ahead, "noise_scale": scale}
             deferred = getattr(self.noise_sampler, "deferred", None)
             if deferred is not None:
                 # chain noise: skip its final scale_noise pass (a read + a write of the whole tensor) and
@@ -519,6 +522,36 @@ class SonarBase:
             kw["count"] = total
         self.noise_draws_left -= 1
         return {"noise_philox": kw, "noise_scale": scale}
+
+    def _lookahead_noise(self, x: Tensor):
+        """Custom noise whose samples depend on the generator state only (power noise): the samples of the next few
+        draws are made together, one Philox launch + one FFT launch + one statistics exchange for the whole batch,
+        and handed out one per request. Every hand-out checks that torch's generator is where the batch assumed it
+        would be (nobody else drew in between) and advances it exactly as the draw itself would have; otherwise the
+        rest of the batch is dropped and made again from the current state. Returns the `noise_deferred` tuple."""
+        ns = self.noise_sampler
+        make = getattr(ns, "lookahead", None)
+        if make is None or self.noise_draws_left < 1:
+            return None
+        factor, normalized = ns.lookahead_pending
+        if not normalized:
+            return None
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        queue = getattr(self, "_noise_queue", None)
+        if queue and (queue[0][2].offset != gen.get_offset() or queue[0][2].seed != gen.initial_seed() or queue[0][0].shape != x.shape):
+            queue.clear()
+        if not queue:
+            batch = make(self.noise_draws_left)
+            if batch is None:
+                return None
+            table = batch[0][1]._base if batch[0][1]._base is not None else batch[0][1]  # noqa: SLF001
+            parallel.allreduce_table(table)  # sharded: ONE exchange for the statistics of the whole batch
+            queue = self._noise_queue = list(batch)
+        raw, sums, draw = queue.pop(0)
+        gen.set_offset(draw.offset + draw.counter_offset)
+        self.noise_draws_left -= 1
+        return (raw, sums, parallel.global_numel(raw.numel()), factor)
 
     def _fused_noise_spec(self, x: Tensor):
         """(factor, normalized) when the noise sampler is plain Gaussian noise of x's shape that the

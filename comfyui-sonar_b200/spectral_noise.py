@@ -11,10 +11,11 @@ in the shared-memory FFT kernel (`ops.spectral_filter`) and the moments/scale ke
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
-from . import ops, rng
+from . import ops, parallel, rng
 from .hostutil import scale_noise
 from .noise_graph import CustomNoiseItemBase
 
@@ -239,9 +240,15 @@ class PowerNoiseItem(CustomNoiseItemBase):
         ortho = 1.0 / math.sqrt(height * width)
         factor = self.factor
 
+        def finish(noise):
+            return scale_noise(mixer(noise, shape), factor, normalized=normalized)
+
         def sampler(sigma, sigma_next):
             drawn = noise_sampler(sigma, sigma_next)
             if spectral_input:
+                if isinstance(drawn, _PhiloxSpectrum):
+                    # small draw: the half spectrum is regenerated from the Philox stream inside the FFT kernel
+                    return finish(ops.spectral_filter(philox=drawn.args, mask=mask, hw=(height, width), out_scale=ortho))
                 # half spectrum drawn directly in frequency space: gain + irfft2(norm="ortho")
                 noise = ops.spectral_filter(spectrum=drawn, mask=mask, hw=(height, width), out_scale=ortho)
             else:
@@ -251,9 +258,9 @@ class PowerNoiseItem(CustomNoiseItemBase):
                 noise = ops.spectral_filter(
                     real=drawn.contiguous(), mask=mask, hw=(height, width), out_scale=ortho * ortho,
                 )
-            noise = mixer(noise, shape)
-            return scale_noise(noise, factor, normalized=normalized)
+            return finish(noise)
 
+        sampler.spectral = (mask, ortho, mixer, factor, normalized)  # for the look-ahead path of make_noise_sampler
         return sampler
 
     def make_noise_sampler(self, x, sigma_min=None, sigma_max=None, *, seed=None, cpu=True, normalized=True):
@@ -264,12 +271,77 @@ class PowerNoiseItem(CustomNoiseItemBase):
                 raise ValueError("time correlated brownian mode is valid only for stochastic samplers")
             raise NotImplementedError("sonar_b200: time_brownian needs torchsde's BrownianTree (out of scope)")
         bins = filter_rfft.shape[-1]
+        spec_shape = (*shape[:-1], bins)
+        height, width = shape[-2:]
+        planes = math.prod(shape[:-2])
+        in_kernel_ok = x.ndim == 4 and ops.spectral_plan_batched(height, width, planes)
+        std = 1.0 / math.sqrt(2.0)  # torch's complex normal: real and imaginary part each N(0, 1/2)
 
         def spectrum_sampler(_s, _sn):
             # complex64 randn on x.device from the global generator, ignoring cpu and seed (:396-401)
-            return rng.normal((*shape[:-1], bins), device=device, dtype=torch.complex64)
+            if in_kernel_ok and IN_KERNEL_PHILOX and rng._INJECT is None and rng._PENDING is None:  # noqa: SLF001
+                total, begin = parallel.global_draw_geometry(spec_shape)
+                grid, _ = ops.philox_policy_cached(device.index if device.index is not None else torch.cuda.current_device(), 2 * total)
+                if 2 * total <= 256 * grid:
+                    # a single ATen row: torch's own kernel spends one Philox call per value too, so regenerating the
+                    # draw inside the FFT kernel costs no extra instructions and saves the spectrum's write, read and
+                    # launch (but see IN_KERNEL_PHILOX: such draws have too few planes to fill the GPU)
+                    draw = ops.reserve_draw(2 * total, device)
+                    return _PhiloxSpectrum((draw, 2 * begin, std, spec_shape[:-2], device))
+            return rng.normal(spec_shape, device=device, dtype=torch.complex64)
 
-        return self.make_noise_sampler_internal(x, spectrum_sampler, filter_rfft, normalized=normalized, spectral_input=True)
+        sampler = self.make_noise_sampler_internal(x, spectrum_sampler, filter_rfft, normalized=normalized, spectral_input=True)
+        mask, ortho, mixer, factor, _ = sampler.spectral
+        if x.ndim == 4 and factor == 1 and not normalized and (mixer.mixer is None or mixer.is_identity):
+
+            def lookahead(count: int):
+                """The next `count` samples in ONE Philox launch + ONE FFT launch (per-sample statistics): a sample is a
+                function of the generator state only, so a consumer that knows it will ask again (a sampler with
+                `noise_draws_left`) can have them made together -- small launches run at a fraction of the throughput of
+                large ones (528 planes of 90x160: 36 us, 4224 planes: 22 us per 528). Returns [(raw sample, its {sum,
+                sum^2} row, draw)], or None when not applicable. The torch generator is NOT advanced: the consumer
+                advances it draw by draw (and drops the rest if somebody else drew in between)."""
+                if rng._INJECT is not None or rng._PENDING is not None:  # noqa: SLF001
+                    return None
+                numel = math.prod(shape)
+                cap = min(ops.FILL_BATCH_MAX, max(1, LOOKAHEAD_BYTES // (12 * numel)))
+                count = -(-count // -(-count // cap))  # equal batches: 18 draws under a cap of 11 are made 9 + 9
+                if count < 2:
+                    return None
+                total, begin = parallel.global_draw_geometry(spec_shape)
+                draws = ops.peek_draws(2 * total, device, count)
+                # (one allocation of one size per batch: the caching allocator hands the same block back every time)
+                spec_bytes = 8 * count * math.prod(spec_shape)
+                slab = torch.empty(spec_bytes + 4 * count * numel, device=device, dtype=torch.uint8)
+                spec = slab[:spec_bytes].view(torch.complex64).reshape(count, *spec_shape)
+                out = slab[spec_bytes:].view(torch.float32).reshape(count * planes, height, width)
+                ops.philox_fill_batch([(d, spec[j], "normal", 0.0, std, 2 * begin) for j, d in enumerate(draws)])
+                out, table = ops.spectral_filter(
+                    spectrum=spec.reshape(count * planes, height, bins), mask=mask, hw=(height, width), out_scale=ortho,
+                    segment_planes=planes, out=out,
+                )
+                out = out.reshape(count, *shape)
+                return [(out[j], table[j], draws[j]) for j in range(count)]
+
+            sampler.lookahead = lookahead
+        return sampler
+
+
+LOOKAHEAD_BYTES = 1 << 30  # spectrum + samples made ahead of time by one look-ahead batch
+# Regenerating a single-row complex draw inside the FFT kernel (ops.spectral_filter(philox=...)) is instruction-neutral
+# and saves a launch, but a single-row draw has at most ~70 planes of 64x64: the Philox work then runs on as many CTAs
+# instead of the ~66 x 256 threads of the fill kernel. Measured on B200, C1 (1x4x64x64): 39 us in-kernel vs 7 + 17.5 us
+# as two launches. Kept behind this switch (and tested), off by default.
+IN_KERNEL_PHILOX = os.environ.get("SONAR_B200_SPECTRAL_PHILOX") == "1"
+
+
+class _PhiloxSpectrum:
+    """A reserved complex normal draw that the FFT kernel regenerates in registers (ops.spectral_filter(philox=...))."""
+
+    __slots__ = ("args",)
+
+    def __init__(self, args):
+        self.args = args
 
 
 class PowerFilterNoiseItem(PowerNoiseItem):

@@ -53,7 +53,8 @@ def _contig(t: Tensor | None) -> Tensor | None:
 # ---------------------------------------------------------------------------------------------
 def _step(x: Tensor, denoised: Tensor, hist: Tensor | None, noise: Tensor | None, kind: int, mode: int, momentum: float,
           momentum_hist: float, direction: float, sigma: float, c0: float, c1: float, noise_scale: float,
-          momentum_active: bool, history_active: bool, momentum_blend: str, history_blend: str):  # fmt: skip
+          momentum_active: bool = True, history_active: bool = True, momentum_blend: str = "lerp",
+          history_blend: str = "lerp"):  # fmt: skip  (the dispatcher passes only what the caller gave: defaults repeat the schema's)
     """One fused Sonar half step (py/sonar.py:227-320, :460-480, :541-573, :649-735). hist = history_d or None
     (first step, ZERO init); noise = already-normalised ancestral noise or None. Returns (x', history')."""
     x, denoised, hist, noise = _contig(x), _contig(denoised), _contig(hist), _contig(noise)
@@ -112,7 +113,7 @@ _register("rand_like(Tensor x) -> Tensor", lambda x: ops.rand(x.shape, device=x.
 _register("moments(Tensor x) -> Tensor", lambda x: ops.moments(x.contiguous()))
 
 
-def _scale_noise(x: Tensor, factor: float, normalized: bool) -> Tensor:
+def _scale_noise(x: Tensor, factor: float = 1.0, normalized: bool = True) -> Tensor:
     from .hostutil import scale_noise
 
     return scale_noise(x.clone(memory_format=torch.contiguous_format), factor, normalized=normalized)
@@ -129,8 +130,8 @@ _register("spectral_filter(Tensor? real, Tensor? spectrum, Tensor? mask, int H, 
 _register("channel_mix(Tensor noise, Tensor mixer) -> Tensor", lambda noise, mixer: ops.channel_mix(noise.contiguous(), mixer.contiguous()))
 
 
-def _pyramid_accum(base: Tensor | None, levels: Sequence[Tensor], weights: Sequence[float], H: int, W: int, mode: str,  # noqa: N803
-                   base_scale: float) -> Tensor:  # fmt: skip
+def _pyramid_accum(base: Tensor | None, levels: Sequence[Tensor], weights: Sequence[float], H: int, W: int,  # noqa: N803
+                   mode: str = "bilinear", base_scale: float = 1.0) -> Tensor:  # fmt: skip
     return ops.pyramid_accumulate(_contig(base), [lv.contiguous() for lv in levels], list(weights), out_hw=(H, W), mode=mode,
                                   base_scale=base_scale)  # fmt: skip
 
@@ -151,7 +152,8 @@ _register(
 )
 
 
-def _guidance(x: Tensor, ref: Tensor, stats_of: Tensor | None, kind: int, blend_mode: str, factor: float, sigma: float, dt: float):
+def _guidance(x: Tensor, ref: Tensor, stats_of: Tensor | None, kind: int, blend_mode: str = "lerp", factor: float = 0.0,
+              sigma: float = 1.0, dt: float = 0.0):  # fmt: skip
     """guidance_linear / guidance_euler (py/sonar.py:380-411); stats_of = the tensor whose per-item mean / std the
     reference latent takes (None: no shift)."""
     sums = None if stats_of is None else ops.item_moments(stats_of.contiguous())

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 3
+#define SONAR_B200_ABI_VERSION 4
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
@@ -315,6 +315,7 @@ int sonar_item_minmax_rescale_f32(const float* x, float* out, int64_t items, int
  * H and W may be any positive sizes (mixed radix 4/2 + direct prime radices).
  * ---------------------------------------------------------------------------------------------- */
 #define SONAR_FFT_MAX_FACTORS 24
+#define SONAR_SPECTRAL_MAX_SEGMENTS 16
 typedef struct SonarSpectralParams {
   float* out;
   const float* in_real;
@@ -327,6 +328,20 @@ typedef struct SonarSpectralParams {
   float out_scale;
   double* sums;       /* optional double[2], zero on entry: += {sum, sum of squares} of `out` */
   double* sums_clear; /* optional double[2] the launch zeroes */
+  /* > 0: `sums` is double[2 * ceil(planes / sums_segment_planes)], one {sum, sum of squares} pair per run of
+   * sums_segment_planes consecutive planes (at most SONAR_SPECTRAL_MAX_SEGMENTS runs) -- several noise samples (each normalised on its own) in ONE launch. */
+  int64_t sums_segment_planes;
+  /* in_real == NULL and in_spec == NULL: the half spectrum is torch.randn(complex64) REGENERATED from the Philox
+   * stream inside the first column stage (never stored). Plane 0 starts at float `philox_begin` of a draw of
+   * `philox_numel_total` floats (2 per complex element; real and imaginary part ~ N(0, philox_std^2), 1/sqrt(2) for
+   * torch's complex normal). Costs one Philox call per float: meant for draws of a single ATen row
+   * (numel_total <= 256 * grid_blocks), where torch's own kernel uses one lane per call as well. */
+  uint64_t philox_seed;
+  uint64_t philox_offset;
+  uint32_t philox_grid_blocks;
+  float philox_std;
+  int64_t philox_begin;
+  int64_t philox_numel_total;
 } SonarSpectralParams;
 
 int64_t sonar_spectral_scratch_bytes(int H, int W);

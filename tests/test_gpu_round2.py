@@ -170,3 +170,61 @@ def test_guided_noise_golden(sb, cuda, golden, name):
         out = ns(torch.tensor(s), torch.tensor(sn))
         assert not left
     assert_close(out, case["out"], what=name)
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 64, 64), (2, 4, 32, 48), (8, 4, 128, 128)])
+@pytest.mark.parametrize("in_kernel", [False, True])
+def test_power_noise_device_philox_vs_oracle(sb, cuda, shape, in_kernel, monkeypatch):
+    """Config C1 with the DEVICE generator: small draws (a single ATen row) regenerate the complex spectrum from the
+    Philox stream inside the FFT kernel; larger ones materialise it. Either way the sample equals the oracle fed
+    torch.randn(complex64, device='cuda') from the same generator state, and the generator advances identically."""
+    b, c, h, w = shape
+    monkeypatch.setattr(sb.spectral_noise, "IN_KERNEL_PHILOX", in_kernel)
+    x = torch.zeros(shape, device=cuda)
+    ns = power_chain(sb, alpha=1.0).make_noise_sampler(x, None, None, seed=0, cpu=True, normalized=True)
+    torch.manual_seed(321)
+    launches = sb.ops.LAUNCH_COUNT
+    got = [ns(None, None) for _ in range(2)]
+    launches = sb.ops.LAUNCH_COUNT - launches
+    offset = torch.cuda.default_generators[0].get_offset()
+    torch.manual_seed(321)
+    draws = [torch.randn((b, c, h, w // 2 + 1), dtype=torch.complex64, device=cuda).cpu() for _ in range(2)]
+    assert torch.cuda.default_generators[0].get_offset() == offset
+    filt = orc.power_filter(shape, alpha=1.0)
+    for j in range(2):
+        want = orc.scale_noise(orc.power_noise(iter([draws[j]]), shape, filt, normalized=False), 1.0, normalized=True)
+        assert_close(got[j], want, what=f"power noise {shape} sample {j}")
+    single_row = 2 * b * c * h * (w // 2 + 1) <= 256 * sb.ops.philox_policy(2 * b * c * h * (w // 2 + 1))[0]
+    assert launches == (4 if single_row and in_kernel else 6), launches  # (Philox fill +) FFT + scale_noise per sample
+
+
+def test_noise_lookahead_equals_draw_by_draw(sb, cuda, monkeypatch):
+    """Look-ahead batches (several power-noise samples per Philox / FFT launch) change nothing but the launch count:
+    same samples, same generator advance -- also when the model itself consumes random numbers between the draws."""
+    sigmas = torch.cat((torch.linspace(14.6, 0.5, 5), torch.zeros(1))).to(cuda)
+    torch.manual_seed(9)
+    x0 = (torch.randn(2, 4, 3, 18, 20) * 14.6).to(cuda)
+
+    def plain(x, sigma, **_kw):
+        return x * 0.9
+
+    def noisy(x, sigma, **_kw):
+        return x * 0.9 + torch.randn(3, device=x.device).sum() * 0.0
+
+    def run(model):
+        torch.manual_seed(77)
+        launches = sb.ops.LAUNCH_COUNT
+        out = sb.samplers.SonarDPMPPSDE.sampler(
+            model, x0.clone(), sigmas, extra_args={"seed": 0}, disable=True, sonar_params={"custom_noise": video_chain(sb, alpha=1.0)},
+        )
+        return out, torch.cuda.default_generators[0].get_offset(), sb.ops.LAUNCH_COUNT - launches
+
+    for model in (plain, noisy):
+        ahead, off_a, launches_a = run(model)
+        monkeypatch.setattr(sb.spectral_noise, "LOOKAHEAD_BYTES", 0)
+        single, off_b, launches_b = run(model)
+        monkeypatch.undo()
+        assert off_a == off_b
+        assert_close(ahead, single, what=f"look-ahead vs draw by draw ({model.__name__})", rtol=1e-6, atol=1e-6)
+        if model is plain:
+            assert launches_a < launches_b  # 8 draws: 1 + 1 launches instead of 8 + 8

