@@ -64,7 +64,7 @@ class SonarStepParams(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 4  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
+ABI_VERSION = 5  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
@@ -126,6 +126,50 @@ class SonarPyramidParams(ctypes.Structure):
         ("n_levels", c_int32),
         ("mode", c_int32),
         ("base_scale", c_float),
+        ("sums", c_void_p),
+        ("sums_clear", c_void_p),
+    ]
+
+
+MIX_MAX_TABLES = 4  # SONAR_MIX_MAX_TABLES
+
+
+class SonarMixTerm(ctypes.Structure):
+    _fields_ = [
+        ("kind", c_int32),
+        ("n_levels", c_int32),
+        ("mode", c_int32),
+        ("full_level", c_int32),
+        ("iterations", c_int32),
+        ("base_scale", c_float),
+        ("div_fac", c_float),
+        ("uniform_from", c_float),
+        ("uniform_to", c_float),
+        ("base_offset", c_uint64),
+        ("level_offset", c_uint64 * PYRAMID_MAX_LEVELS),
+        ("levels", c_void_p * PYRAMID_MAX_LEVELS),
+        ("level_h", c_int32 * PYRAMID_MAX_LEVELS),
+        ("level_w", c_int32 * PYRAMID_MAX_LEVELS),
+        ("weights", c_float * PYRAMID_MAX_LEVELS),
+        ("tables", c_void_p * MIX_MAX_TABLES),
+    ]
+
+
+class SonarNoiseMixParams(ctypes.Structure):
+    _fields_ = [
+        ("out", c_void_p),
+        ("n", c_int64),
+        ("begin", c_int64),
+        ("numel_total", c_int64),
+        ("C", c_int32),
+        ("H", c_int32),
+        ("W", c_int32),
+        ("blend_mode", c_int32),
+        ("blend_t", c_float),
+        ("grid_blocks", c_uint32),
+        ("seed", c_uint64),
+        ("a", SonarMixTerm),
+        ("b", SonarMixTerm),
         ("sums", c_void_p),
         ("sums_clear", c_void_p),
     ]
@@ -328,6 +372,8 @@ SIGNATURES: dict[str, list] = {
     "sonar_guidance_f32": [POINTER(SonarGuidanceParams), c_void_p],
     "sonar_pyramid_accum_f32": [POINTER(SonarPyramidParams), c_void_p],
     "sonar_perlin_accum_f32": [POINTER(SonarPerlinParams), c_void_p],
+    "sonar_noise_mix_f32": [POINTER(SonarNoiseMixParams), c_void_p],
+    "sonar_perlin_tables_f32": [POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint32), c_int32, c_uint64, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "sonar_blend_f32": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p],
     "sonar_axpby_f32": [c_void_p, c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "sonar_composite_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p],

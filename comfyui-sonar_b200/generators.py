@@ -20,8 +20,18 @@ from typing import Callable, NamedTuple
 
 import torch
 
+import os
+
 from . import hostutil, ops, parallel, rng
 from .hostutil import fallback, scale_noise
+
+# Pyramid / Perlin samples (and their blends) are computed element-wise from the Philox stream (csrc/noise_mix.cu)
+# instead of materialising every base draw; SONAR_B200_FUSED_NOISE=0 selects the materialising kernels.
+FUSED_NOISE = os.environ.get("SONAR_B200_FUSED_NOISE", "1") != "0"
+# A generator on its own gains nothing from the fused kernel (B200, 16x16x128x128: pyramid 81 us fused vs 75 us, Perlin
+# 44 vs 40 us -- per-element bilinear taps cost more than the row-wise kernel saves in traffic); a blend of two
+# generators does (one launch instead of three full-size passes, a quarter of the HBM traffic). Singles: opt-in.
+FUSED_SINGLE_GENERATORS = os.environ.get("SONAR_B200_FUSED_SINGLE", "0") == "1"
 
 
 class NoiseType(Enum):
@@ -155,6 +165,24 @@ class NoiseGenerator:
             generator=self.device_generator(),
         )
 
+    # ---- RNG-fused generation (csrc/noise_mix.cu) ----
+    def fusable(self) -> bool:
+        """True when this generator's sample can be computed element-wise from the Philox stream by ops.noise_mix:
+        plain float32 draws from the default CUDA generator (no injected / batched draws in flight)."""
+        if not FUSED_NOISE or not hasattr(self, "plan_term") or rng._INJECT is not None or rng._PENDING is not None:  # noqa: SLF001
+            return False
+        if self.dtype != torch.float32 or self.device_generator() is not None or self.width is None or self.width < 2:
+            return False
+        _, c, h, w = shape = self.get_adjusted_shape()
+        total, _ = parallel.global_draw_geometry(shape)
+        # index ranges of the fused kernel: 32-bit elements, 24-bit planes and in-plane offsets, 16-bit W and C
+        if not (0 < total <= ops.MIX_MAX_ELEMENTS and h * w <= 1 << 24 and total // (h * w) < 1 << 24 and w < 65536 and c < 65536):
+            return False
+        return self.term_supported()
+
+    def term_supported(self) -> bool:
+        return True
+
     def output_hook(self, noise: torch.Tensor) -> torch.Tensor:
         return scale_noise(
             noise,
@@ -234,8 +262,24 @@ class PerlinOldNoiseGenerator(FramesToChannelsNoiseGenerator):
     def ng_params(cls):
         return super().ng_params() | {"div_fac": 2.0, "iterations": 2, "blend_mode": "lerp"}
 
+    def term_supported(self) -> bool:
+        return 0 < self.iterations <= ops.MIX_MAX_TABLES and self.blend_mode in ops.BLEND_IDS and self.get_adjusted_shape()[1] <= 65535
+
+    def plan_term(self):
+        """Reserves the draws of one sample in the reference's order (base uniform, then one angle grid per iteration)
+        and builds the stencil tables; the full-size base draw stays in the Philox stream."""
+        b, c, h, w = shape = self.get_adjusted_shape()
+        total, begin = parallel.global_draw_geometry(shape)
+        base = ops.reserve_draw(total, self.device)
+        grids = [ops.reserve_draw(c * (h + 1) * (w + 1), self.device) for _ in range(self.iterations)]
+        tables = ops.perlin_tables(grids, c, h, w, blend_mode=self.blend_mode, device=self.device)
+        return {"kind": ops.TERM_PERLIN, "base": base, "tables": tables, "div_fac": self.div_fac}, shape, begin
+
     def generate(self, *_args):
         hostutil.blend_mode_id(self.blend_mode)  # validates like BLENDING_MODES[...] would
+        if FUSED_SINGLE_GENERATORS and self.fusable():
+            term, shape, begin = self.plan_term()
+            return self.fix_output_frames(ops.noise_mix(shape, term, begin=begin, device=self.device))
         with rng.batched():  # base + angle grids: one launch
             base = self.rand_like(fun="uniform")
             b, c, h, w = base.shape
@@ -276,7 +320,36 @@ class PyramidNoiseGenerator(_PyramidBase):
     def ng_params(cls):
         return super().ng_params() | {"discount": 0.7, "upscale_mode": "bilinear", "iterations": 10}
 
+    def term_supported(self) -> bool:
+        return self.upscale_mode in ("bilinear", "nearest-exact") and self.iterations <= ops.PYRAMID_MAX_LEVELS
+
+    def plan_term(self):
+        """Reserves the draws of one sample in the reference's order (:621-649: base, then per level one CPU-generator
+        draw for its size and the level itself). The base and the full-size level 0 stay in the Philox stream; the
+        coarse levels (a few per cent of the elements) are materialised by one batched fill launch."""
+        b, c, h, w = shape = self.get_adjusted_shape()
+        orig_h, orig_w = h, w
+        total, begin = parallel.global_draw_geometry(shape)
+        base = ops.reserve_draw(total, self.device)
+        host_gen = self.generator if self.generator is not None and self.generator.device.type == "cpu" else None
+        levels, have_full = [], False
+        with rng.batched():
+            for i in range(self.iterations):
+                r = rng.host_rand(1, host_gen).item() * 2 + 2
+                w, h = max(1, int(w / (r**i))), max(1, int(h / (r**i)))
+                if (h, w) == (orig_h, orig_w) and not have_full:
+                    level, have_full = ops.reserve_draw(total, self.device), True
+                else:
+                    level = rng.normal((b, c, h, w), device=self.device, dtype=torch.float32)
+                levels.append((level, self.discount**i))
+                if w == 1 or h == 1:
+                    break
+        return {"kind": ops.TERM_PYRAMID, "base": base, "levels": levels, "mode": self.upscale_mode}, shape, begin
+
     def generate(self, *_args):
+        if FUSED_SINGLE_GENERATORS and self.fusable():
+            term, shape, begin = self.plan_term()
+            return self.fix_output_frames(ops.noise_mix(shape, term, begin=begin, device=self.device))
         levels, weights = [], []
         with rng.batched():  # base + every level: one launch
             base = self.rand_like()

@@ -160,6 +160,8 @@ class CustomNoiseChain:
         noise_sampler.deferred = lambda sigma, sigma_next: (accumulate(sigma, sigma_next), factor, normalized)
         # Look-ahead (see PowerNoiseItem.make_noise_sampler): a chain of ONE sigma-independent item hands its child's
         # batches through; `pending` = what this level still owes each sample, applied by whoever consumes it.
+        if len(samplers) == 1 and factor == 1 and not normalized and hasattr(samplers[0], "fused_term"):
+            noise_sampler.fusable, noise_sampler.fused_term = samplers[0].fusable, samplers[0].fused_term
         child_lookahead = getattr(samplers[0], "lookahead", None) if len(samplers) == 1 else None
         if child_lookahead is not None:
             noise_sampler.lookahead = child_lookahead
@@ -218,6 +220,23 @@ class NoiseSampler:
         if hasattr(noise, "to"):
             noise = noise.to(dtype=self.dtype, device=self.device)
         return noise
+
+    def fusable(self) -> bool:
+        """This sampler is a bare generator sample (nothing owed at this level) that ops.noise_mix can regenerate
+        from the Philox stream -- so a parent (BlendedNoise) may fuse it with its sibling instead of reading tensors."""
+        gen = self.noise_sampler
+        return (
+            self.factor == 1
+            and not self.normalized
+            and self.dtype == torch.float32
+            and hasattr(gen, "plan_term")
+            and not gen.normalized
+            and gen.normalize_dims is None
+            and gen.fusable()
+        )
+
+    def fused_term(self):
+        return self.noise_sampler.plan_term()
 
     def fused_gaussian(self):
         """If this sampler is plain Gaussian noise, returns (factor, normalized) so a consumer (the
@@ -517,7 +536,25 @@ class BlendedNoise(_ChildHolder):
 
         ns_1, ns_2, ns_mask = child(self.custom_noise_1), child(self.custom_noise_2), child(self.custom_noise_mask)
 
+        blend_name = getattr(blend_function, "sonar_blend_mode", None)
+        fuse = (
+            ns_mask is None
+            and blend_name in ops.BLEND_IDS
+            and isinstance(n2_blend, (int, float))
+            and hasattr(ns_1, "fused_term")
+            and hasattr(ns_2, "fused_term")
+        )
+
         def noise_sampler(s, sn):
+            if fuse and ns_1.fusable() and ns_2.fusable():
+                # both children are generator samples the mix kernel regenerates from the Philox stream: one launch
+                # writes blend(noise_1, noise_2, t) (draws reserved child 1 first, like the two calls below)
+                term_1, shape_1, begin = ns_1.fused_term()
+                term_2, shape_2, _ = ns_2.fused_term()
+                if shape_1 == shape_2:
+                    mixed = ops.noise_mix(shape_1, term_1, term_2, begin=begin, blend_mode=blend_name, blend_t=n2_blend, device=x.device)
+                    return scale_noise(ops.reshape_keep_sums(mixed, x.shape), factor, normalized=normalize)
+                raise RuntimeError("fused noise terms disagree on the latent shape")
             noise_1 = ns_1(s, sn)
             if ns_2 is None:
                 return scale_noise(noise_1, factor, normalized=normalize)

@@ -641,6 +641,90 @@ def perlin_accumulate(
 
 
 # --------------------------------------------------------------------------------------------
+# RNG-fused pyramid / Perlin / blend (csrc/noise_mix.cu)
+# --------------------------------------------------------------------------------------------
+TERM_PYRAMID, TERM_PERLIN = 1, 2
+MIX_MAX_TABLES, PYRAMID_MAX_LEVELS = _native.MIX_MAX_TABLES, _native.PYRAMID_MAX_LEVELS
+MIX_MAX_ELEMENTS = (1 << 32) - 1  # the fused kernel indexes the global tensor with 32 bits
+
+
+def perlin_tables(draws: Sequence[PhiloxDraw], channels: int, height: int, width: int, *, blend_mode: str, device) -> list[torch.Tensor]:
+    """(C, H, W) Perlin stencil of every iteration; the corner angles are the uniform [0, 2 pi) draws `draws`
+    (C (H+1) (W+1) values each), regenerated in registers. One launch."""
+    n = len(draws)
+    if n > _native.MIX_MAX_TABLES:
+        raise ValueError("too many perlin iterations for the fused kernel")
+    tables = torch.empty((n, channels, height, width), device=device, dtype=torch.float32)
+    lib, stream = _prepare(tables)
+    ptrs = (ctypes.c_void_p * n)(*(tables[i].data_ptr() for i in range(n)))
+    offsets = (ctypes.c_uint64 * n)(*(d.offset for d in draws))
+    grids = (ctypes.c_uint32 * n)(*(d.grid_blocks for d in draws))
+    _launch(
+        "sonar_perlin_tables_f32", lib.sonar_perlin_tables_f32,
+        ptrs, offsets, grids, n, draws[0].seed, channels, height, width, BLEND_IDS[blend_mode], stream,
+    )  # fmt: skip
+    return list(tables.unbind(0))
+
+
+def _fill_term(dst: "_native.SonarMixTerm", term: dict | None, keep: list) -> None:
+    if term is None:
+        dst.kind = 0
+        return
+    dst.kind = term["kind"]
+    dst.base_offset = term["base"].offset
+    dst.full_level = -1
+    if term["kind"] == TERM_PYRAMID:
+        levels = term["levels"]
+        if len(levels) > _native.PYRAMID_MAX_LEVELS:
+            raise ValueError("too many pyramid levels")
+        dst.n_levels, dst.mode, dst.base_scale = len(levels), RESAMPLE_IDS[term["mode"]], float(term.get("base_scale", 1.0))
+        for i, (lv, wgt) in enumerate(levels):
+            dst.weights[i] = float(wgt)
+            if isinstance(lv, PhiloxDraw):  # THE full-size level, regenerated from the stream
+                if dst.full_level >= 0:
+                    raise ValueError("at most one full-size pyramid level can be fused")
+                dst.full_level, dst.level_offset[i], dst.levels[i] = i, lv.offset, 0
+            else:
+                _f32(lv, "level")
+                keep.append(lv)
+                dst.levels[i], dst.level_h[i], dst.level_w[i] = lv.data_ptr(), lv.shape[-2], lv.shape[-1]
+    elif term["kind"] == TERM_PERLIN:
+        tables = term["tables"]
+        dst.iterations, dst.div_fac = len(tables), float(term["div_fac"])
+        dst.uniform_from, dst.uniform_to = 0.0, 1.0
+        for i, t in enumerate(tables):
+            keep.append(t)
+            dst.tables[i] = t.data_ptr()
+
+
+def noise_mix(shape: Sequence[int], term_a: dict, term_b: dict | None = None, *, begin: int = 0, blend_mode: str = "lerp",
+              blend_t: float = 0.5, device) -> torch.Tensor:  # fmt: skip
+    """blend(mode, A, B, t) -- or A alone -- for a (B, C, H, W) tensor whose terms are pyramid / Perlin noise (or plain
+    draws) regenerated from the Philox stream in registers. A term is a dict: kind, base (PhiloxDraw of the full-size
+    base draw), and for TERM_PYRAMID levels = [(PhiloxDraw | coarse tensor, weight)], mode; for TERM_PERLIN tables
+    (from perlin_tables), div_fac. `begin` = element offset of this rank's slice in the global draw."""
+    batch, channels, height, width = shape
+    out = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+    if out.numel() == 0:
+        return out
+    base = term_a["base"]
+    p = _native.SonarNoiseMixParams()
+    keep: list = []
+    _fill_term(p.a, term_a, keep)
+    _fill_term(p.b, term_b, keep)
+    if term_b is not None and (term_b["base"].numel != base.numel or term_b["base"].grid_blocks != base.grid_blocks):
+        raise ValueError("fused terms must draw tensors of the same size")
+    p.out, p.n, p.begin, p.numel_total = out.data_ptr(), out.numel(), int(begin), base.numel
+    p.C, p.H, p.W = channels, height, width
+    p.blend_mode, p.blend_t = BLEND_IDS[blend_mode], float(blend_t)
+    p.grid_blocks, p.seed = base.grid_blocks, base.seed
+    lib, stream = _prepare(out, *keep)
+    slot, p.sums, p.sums_clear = sums_slot(out.device)
+    _launch("sonar_noise_mix_f32", lib.sonar_noise_mix_f32, ctypes.byref(p), stream)
+    return _sums_written(out, slot)
+
+
+# --------------------------------------------------------------------------------------------
 # spectral shaping
 # --------------------------------------------------------------------------------------------
 _SPECTRAL_SCRATCH: dict[tuple, torch.Tensor] = {}

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 4
+#define SONAR_B200_ABI_VERSION 5
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
@@ -263,6 +263,64 @@ typedef struct SonarPerlinParams {
 } SonarPerlinParams;
 
 int sonar_perlin_accum_f32(const SonarPerlinParams* params_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RNG-fused noise synthesis: pyramid / Perlin noise (and their blend) computed element-wise from the Philox stream.
+ * replaces: PyramidNoiseGenerator.generate                 py/noise_generation.py:621-649
+ *           PerlinOldNoiseGenerator.generate               py/noise_generation.py:478-493
+ *           BlendedNoise noise_sampler (scalar weight)     py/noise.py:1391-1405
+ * out[i] = blend(mode, A(i), B(i), blend_t) (or A(i) when b.kind == NONE) for the elements [begin, begin + n) of a
+ * dense (B_total, C, H, W) tensor of numel_total elements; every full-size draw of the graph is a torch draw of
+ * numel_total values (geometry: grid_blocks from sonar_philox_policy) at its own generator offset and never touches
+ * memory. A term:
+ *   PYRAMID: base normal draw (base_offset) * base_scale + sum_l weights[l] * resample(level l); levels[l] != NULL is a
+ *            materialised coarse level (local planes, level_h[l], level_w[l]); levels[l] == NULL (l == full_level, at
+ *            most one) is the full-size level, a normal draw at level_offset[l]. mode: BILINEAR or NEAREST_EXACT.
+ *   PERLIN : uniform [uniform_from, uniform_to) base draw / div_fac + sum_it tables[it][c, y, x], tables from
+ *            sonar_perlin_tables_f32 (the stencil of iteration `it`, (C, H, W), shared by the batch).
+ * sonar_perlin_tables_f32: tables[it][c,y,x] = 2 x 2 gradient stencil of pixel (y, x) whose corner angles are the
+ * elements of a uniform [0, 2 pi) draw of C (H+1) (W+1) values at offsets[it] (regenerated in registers).
+ * ---------------------------------------------------------------------------------------------- */
+#define SONAR_MIX_MAX_TABLES 4
+enum { SONAR_TERM_NONE = 0, SONAR_TERM_PYRAMID = 1, SONAR_TERM_PERLIN = 2 };
+typedef struct SonarMixTerm {
+  int32_t kind;       /* SONAR_TERM_* */
+  int32_t n_levels;   /* PYRAMID */
+  int32_t mode;       /* PYRAMID: SONAR_RESAMPLE_BILINEAR / _NEAREST_EXACT */
+  int32_t full_level; /* PYRAMID: index of the full-size level, -1 = none */
+  int32_t iterations; /* PERLIN */
+  float base_scale;   /* PYRAMID */
+  float div_fac;      /* PERLIN */
+  float uniform_from; /* PERLIN: range of the base draw */
+  float uniform_to;
+  uint64_t base_offset;
+  uint64_t level_offset[SONAR_PYRAMID_MAX_LEVELS];
+  const float* levels[SONAR_PYRAMID_MAX_LEVELS];
+  int32_t level_h[SONAR_PYRAMID_MAX_LEVELS];
+  int32_t level_w[SONAR_PYRAMID_MAX_LEVELS];
+  float weights[SONAR_PYRAMID_MAX_LEVELS];
+  const float* tables[SONAR_MIX_MAX_TABLES];
+} SonarMixTerm;
+typedef struct SonarNoiseMixParams {
+  float* out;
+  int64_t n;           /* local elements (whole planes) */
+  int64_t begin;       /* element offset of the local slice in the global tensor (a multiple of H * W) */
+  int64_t numel_total; /* < 2^32; H * W <= 2^24, fewer than 2^24 planes, W and C < 2^16 */
+  int32_t C;
+  int32_t H;
+  int32_t W;
+  int32_t blend_mode; /* SONAR_BLEND_* */
+  float blend_t;
+  uint32_t grid_blocks;
+  uint64_t seed;
+  SonarMixTerm a;
+  SonarMixTerm b;
+  double* sums;       /* optional double[2], zero on entry: += {sum, sum of squares} of `out` */
+  double* sums_clear; /* optional double[2] the launch zeroes */
+} SonarNoiseMixParams;
+int sonar_noise_mix_f32(const SonarNoiseMixParams* params_host, void* stream);
+int sonar_perlin_tables_f32(float* const* tables_host, const uint64_t* offsets_host, const uint32_t* grid_blocks_host,
+                            int32_t n_tables, uint64_t seed, int32_t C, int32_t H, int32_t W, int32_t blend_mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Element-wise combinators.

@@ -46,7 +46,7 @@ def test_struct_layouts_match_the_header(sb, tmp_path):
     """sizeof of every by-value struct, as compiled by the C compiler, equals the ctypes mirror."""
     names = ["SonarStepParams", "SonarPyramidParams", "SonarPerlinParams", "SonarSpectralParams", "SonarSpectralPlanInfo",
              "SonarWaveletFilters", "SonarDwtAnalysisParams", "SonarDwtSynthesisParams", "SonarWcfgFusedParams",
-             "SonarFreeuParams", "SonarGuidanceParams", "SonarFillBatch"]  # fmt: skip
+             "SonarFreeuParams", "SonarGuidanceParams", "SonarFillBatch", "SonarMixTerm", "SonarNoiseMixParams"]  # fmt: skip
     names = [n for n in names if hasattr(sb._native, n)]
     assert len(names) >= 10
     src = tmp_path / "sz.c"
