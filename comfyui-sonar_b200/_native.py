@@ -64,7 +64,7 @@ class SonarStepParams(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 5  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
+ABI_VERSION = 6  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
@@ -230,6 +230,8 @@ class SonarSpectralPlanInfo(ctypes.Structure):
         ("n_row_stages", c_int32),
         ("col_radix", c_int32 * SPECTRAL_PLAN_MAX_STAGES),
         ("row_radix", c_int32 * SPECTRAL_PLAN_MAX_STAGES),
+        ("cluster", c_int32),
+        ("pad_", c_int32),
     ]
 
 

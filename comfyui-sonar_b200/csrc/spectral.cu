@@ -14,6 +14,8 @@
 // stays in shared memory -- or in an L2-resident global scratch when a plane is too large (256^2:
 // 258 KB > 227 KB) -- and every 1-D FFT is a warp-level mixed-radix Stockham transform in a per-warp
 // ping-pong scratch. Rows are processed two at a time (real pair <-> one complex FFT).
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdint>
 #include <type_traits>
@@ -563,6 +565,7 @@ struct StageArgs {
   unsigned magic_wh;            // ceil(2^32 / wh)
   int group;                    // planes per pass the kernel was launched with (1: no plane split of b)
   int wh, pitch, plane_elems, M;
+  int gstride;                  // row stride of the global spectrum / mask (wh; the cluster kernel's wh is its share of the columns)
   int spec_plane_elems;         // H * wh (global spectrum plane)
   // SRC_PHILOX: float index (in the global draw) of the group's first plane; the draw itself is read from the
   // launch block in the constant bank (no registers in the kernels that do not use it)
@@ -617,7 +620,7 @@ __device__ __forceinline__ void run_stage(StageArgs& a) {
       const bool has_mask = a.mask != nullptr;
 #pragma unroll
       for (int t = 0; t < R; ++t) {
-        const int off = (int)a.idx_h[first_slot + t] * a.wh;
+        const int off = (int)a.idx_h[first_slot + t] * a.gstride;
         v[t] = __ldg(gp + off);
         if (has_mask) {
           const float gain = __ldg(mp + off);
@@ -637,7 +640,7 @@ __device__ __forceinline__ void run_stage(StageArgs& a) {
       const float std = pp.philox_std;
 #pragma unroll
       for (int t = 0; t < R; ++t) {
-        const int off = (int)a.idx_h[first_slot + t] * a.wh;
+        const int off = (int)a.idx_h[first_slot + t] * a.gstride;
         const uint64_t li = (uint64_t)(e0 + 2 * off);
         const uint64_t q = __umul64hi(li, a.launch->magic_T);
         const uint32_t vt = (uint32_t)(li - q * st.threads);
@@ -669,7 +672,7 @@ __device__ __forceinline__ void run_stage(StageArgs& a) {
           const float* mp = a.mask + c;
 #pragma unroll
           for (int t = 0; t < R; ++t) {
-            const float gain = __ldg(mp + (int)a.idx_h[first_slot + t] * a.wh);
+            const float gain = __ldg(mp + (int)a.idx_h[first_slot + t] * a.gstride);
             v[t] = make_float2(v[t].x * gain, -v[t].y * gain);
           }
         } else {
@@ -848,6 +851,7 @@ spectral_batched_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
   a.idx_h = idx_h;
   a.group = G;
   a.wh = Wh;
+  a.gstride = Wh;
   a.pitch = P;
   a.plane_elems = L.plane_elems;
   a.M = M;
@@ -1058,6 +1062,241 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   return err == cudaSuccess ? 0 : (int)err;
 }
 
+// =============================================================================================
+// Cluster variant: planes whose half spectrum does not fit one SM (256x256: 264 KB) live in the DISTRIBUTED shared
+// memory of a cluster of two CTAs -- still one HBM read and one HBM write per plane, no L2 scratch.
+//  * column phase: CTA r holds columns [r * cols0, ...) of all H rows ([H][pitch_c], 133 KB at 256x256) and runs the
+//    inverse column transforms of its share exactly like the batched kernel (gather from the global spectrum with
+//    the gain applied, in place, natural row order out);
+//  * exchange: row y belongs to CTA y / (H/2) in the row phase. Every thread takes its elements into registers,
+//    the cluster synchronises (both buffers are now free to be overwritten), and each element is stored into its
+//    row-phase slot [y % (H/2)][col] of the owning CTA -- a local store or a store into the peer's shared memory;
+//  * row phase: fold, half-length inverse row transforms of the CTA's H/2 rows ([H/2][pitch_r]), last stage straight
+//    to the global plane with the moments, as in the batched kernel.
+// Real input (rfft2 front end) starts in the row layout -- forward rows of the CTA's half gathered from the global
+// real plane, unfold -- crosses to the column layout for the forward and inverse column transforms around the gain,
+// and crosses back: two exchanges.
+// =============================================================================================
+constexpr int kClusterThreads = 1024;
+constexpr int kClusterMaxRegsElems = 20;  // complex elements a thread carries through the exchange (thread-local staging)
+
+struct SpectralClusterLaunch {
+  SonarSpectralParams p;
+  AxisPlan col;   // length H
+  AxisPlan row;   // length M = W / 2
+  int wh;         // M + 1
+  int cols0;      // columns of CTA 0 in the column phase (CTA 1: wh - cols0)
+  int pitch_c;    // odd, >= cols0
+  int rows_half;  // H / 2
+  int pitch_r;    // odd, >= wh
+  int buf_elems;  // max(H * pitch_c, rows_half * pitch_r)
+  float scale;
+  unsigned magic_cols[2], magic_rows, magic_row_nb, magic_wh;
+};
+
+// Moves the cluster's plane between its two shared-memory layouts through thread-local staging: every thread takes
+// its elements out, the cluster synchronises (both buffers may now be overwritten), every element is stored into
+// its slot of the owning CTA (a local store or a store into the peer's shared memory), the cluster synchronises.
+//   TO_ROWS: [H][pitch_c] (my columns, all rows)  ->  [H/2][pitch_r] (my rows, all columns)
+//  !TO_ROWS: the way back.
+template <bool TO_ROWS>
+__device__ __forceinline__ void cluster_exchange(cooperative_groups::cluster_group& cluster, const SpectralClusterLaunch& L,
+                                                 float2* __restrict__ buf, float2* __restrict__ peer_buf, int rank, int H) {
+  const int col0 = rank * L.cols0, my_cols = rank == 0 ? L.cols0 : L.wh - L.cols0, row0 = rank * L.rows_half;
+  const int inner = TO_ROWS ? my_cols : L.wh;  // fastest index of the source walk
+  const unsigned magic = TO_ROWS ? L.magic_cols[rank] : L.magic_wh;
+  const int n = (TO_ROWS ? H : L.rows_half) * inner;
+  // (the staging array lives in the thread's local memory -- L1 -- on purpose: 17 complex values per thread would
+  // not fit the 64-register budget of a 1024-thread CTA next to the butterfly code)
+  float2 v[kClusterMaxRegsElems];
+#pragma unroll 1
+  for (int i = 0; i < kClusterMaxRegsElems; ++i) {
+    const int idx = threadIdx.x + i * kClusterThreads;
+    if (idx < n) {
+      const int r = (int)__umulhi((unsigned)idx, magic);
+      v[i] = buf[r * (TO_ROWS ? L.pitch_c : L.pitch_r) + (idx - r * inner)];
+    }
+  }
+  cluster.sync();  // every element of both buffers has been taken out: both may be overwritten
+#pragma unroll 1
+  for (int i = 0; i < kClusterMaxRegsElems; ++i) {
+    const int idx = threadIdx.x + i * kClusterThreads;
+    if (idx < n) {
+      const int r = (int)__umulhi((unsigned)idx, magic);
+      const int c = idx - r * inner;
+      if (TO_ROWS) {  // element (row r, column col0 + c) goes to the CTA that owns row r
+        const int owner = r >= L.rows_half ? 1 : 0;
+        (owner == rank ? buf : peer_buf)[(r - owner * L.rows_half) * L.pitch_r + col0 + c] = v[i];
+      } else {  // element (row row0 + r, column c) goes to the CTA that owns column c
+        const int owner = c >= L.cols0 ? 1 : 0;
+        (owner == rank ? buf : peer_buf)[(row0 + r) * L.pitch_c + (c - owner * L.cols0)] = v[i];
+      }
+    }
+  }
+  cluster.sync();  // my share is complete (the peer's stores included)
+}
+
+template <bool REAL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClusterThreads, 1)
+spectral_cluster_kernel(const __grid_constant__ SpectralClusterLaunch L) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const SonarSpectralParams& p = L.p;
+  const int H = p.H, W = p.W, M = W >> 1, Wh = L.wh;
+  float2* tw_h = reinterpret_cast<float2*>(smem_raw);
+  float2* tw_m = tw_h + H;
+  float2* tw_w = tw_m + M;
+  float2* buf = tw_w + M;
+  ushort2* tab_col = reinterpret_cast<ushort2*>(buf + L.buf_elems);
+  ushort2* tab_row = tab_col + L.col.tab_size;
+  unsigned short* pos_m = reinterpret_cast<unsigned short*>(tab_row + L.row.tab_size);
+  unsigned short* idx_h = pos_m + M;
+  float2* peer_buf = cluster.map_shared_rank(buf, rank ^ 1);
+  build_axis_tables(L.col, tab_col, nullptr, idx_h);
+  build_axis_tables(L.row, tab_row, pos_m, nullptr);
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    double sn, cs;
+    sincospi(-2.0 * (double)k / (double)H, &sn, &cs);
+    tw_h[k] = make_float2((float)cs, (float)sn);
+  }
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    double sn, cs;
+    sincospi(-2.0 * (double)k / (double)M, &sn, &cs);
+    tw_m[k] = make_float2((float)cs, (float)sn);
+    sincospi(2.0 * (double)k / (double)W, &sn, &cs);
+    tw_w[k] = make_float2((float)cs, (float)sn);
+  }
+  __shared__ double seg_sums[2 * SONAR_SPECTRAL_MAX_SEGMENTS];
+  if (threadIdx.x < 2 * SONAR_SPECTRAL_MAX_SEGMENTS) seg_sums[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int col0 = rank * L.cols0, my_cols = rank == 0 ? L.cols0 : Wh - L.cols0;
+  const int row0 = rank * L.rows_half;
+  StageArgs a;
+  a.buf = buf;
+  a.pos_m = pos_m;
+  a.idx_h = idx_h;
+  a.group = 1;
+  a.M = M;
+  a.spec_plane_elems = H * Wh;
+  a.gstride = Wh;
+  a.magic_wh = 0;
+  a.magic_nb = L.magic_row_nb;
+  a.scale = L.scale;
+  a.ms = 0.0f;
+  a.mss = 0.0f;
+  a.launch = nullptr;
+  a.mask = p.mask == nullptr ? nullptr : p.mask + col0;
+  auto column_phase_args = [&]() {
+    a.tw = tw_h;
+    a.wh = my_cols;
+    a.pitch = L.pitch_c;
+    a.plane_elems = H * L.pitch_c;
+    a.nbatch = my_cols;
+    a.magic_batch = L.magic_cols[rank];
+  };
+  auto row_phase_args = [&]() {
+    a.tw = tw_m;
+    a.pitch = L.pitch_r;
+    a.nbatch = L.rows_half;
+    a.magic_batch = L.magic_rows;
+  };
+  for (int64_t plane = blockIdx.x >> 1; plane < p.planes; plane += gridDim.x >> 1) {
+    if constexpr (REAL) {
+      // forward rows of my half of the plane (half length, conj trick; gathered from the global real rows), r2c
+      // unfold, to the column layout, forward columns, gain (.) conj, inverse columns
+      a.real_rows = reinterpret_cast<const float2*>(p.in_real + plane * (int64_t)H * W + (int64_t)row0 * W);
+      row_phase_args();
+      run_axis_dit<SRC_REAL_ROWS, false>(L.row, a, tab_row);
+      pair_pass<true>(buf, L.rows_half, L.magic_rows, M, L.pitch_r, tw_w);
+      __syncthreads();
+      cluster_exchange<false>(cluster, L, buf, peer_buf, rank, H);
+      column_phase_args();
+      run_axis_dif<SINK_SLOTS, true>(L.col, a, tab_col);
+      run_axis_dit<SRC_CONJ_MASK, true>(L.col, a, tab_col);
+    } else {
+      // inverse columns of my share of the columns, all rows (gather from the global spectrum with the gain applied)
+      a.spec = reinterpret_cast<const float2*>(p.in_spec) + plane * (int64_t)H * Wh + col0;
+      column_phase_args();
+      run_axis_dit<SRC_SPECTRUM, true>(L.col, a, tab_col);
+    }
+    cluster_exchange<true>(cluster, L, buf, peer_buf, rank, H);
+    // ---- row phase: my half of the rows, all columns ----
+    pair_pass<false>(buf, L.rows_half, L.magic_rows, M, L.pitch_r, tw_w);
+    __syncthreads();
+    a.out_rows = reinterpret_cast<float2*>(p.out + plane * (int64_t)H * W + (int64_t)row0 * W);
+    row_phase_args();
+    run_axis_dif<SINK_GLOBAL, false>(L.row, a, tab_row);
+    if (p.sums != nullptr) {
+      const float ws = warp_sum(a.ms), wss = warp_sum(a.mss);
+      if ((threadIdx.x & 31) == 0) {
+        const int seg = p.sums_segment_planes > 0 ? (int)(plane / p.sums_segment_planes) : 0;
+        atomicAdd(&seg_sums[2 * seg], (double)ws);
+        atomicAdd(&seg_sums[2 * seg + 1], (double)wss);
+      }
+      a.ms = a.mss = 0.0f;
+    }
+    // (the next plane's first phase writes only my own buffer; the peer stores into it again only after the next
+    // exchange's first barrier, which I reach after this row phase: no barrier needed here)
+  }
+  if (p.sums != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 2 * SONAR_SPECTRAL_MAX_SEGMENTS && seg_sums[threadIdx.x] != 0.0) atomicAdd(&p.sums[threadIdx.x], seg_sums[threadIdx.x]);
+    if (p.sums_clear != nullptr && blockIdx.x == 0 && threadIdx.x < 2) p.sums_clear[threadIdx.x] = 0.0;
+  }
+  cluster.sync();  // no CTA exits while its peer may still store into its shared memory
+}
+
+static size_t cluster_smem_bytes(int H, int W, int buf_elems, const AxisPlan& col, const AxisPlan& row) {
+  const int M = W / 2;
+  size_t bytes = ((size_t)H + 2 * (size_t)M + (size_t)buf_elems) * sizeof(float2) +
+                 (size_t)(col.tab_size + row.tab_size) * sizeof(ushort2) + (size_t)(M + H) * sizeof(unsigned short);
+  return (bytes + 15) & ~(size_t)15;
+}
+
+// 0 = launched; -1 = not applicable; > 0 = CUDA error.
+static bool plan_spectral_cluster(const SonarSpectralParams& p, SpectralClusterLaunch* out, size_t* smem_out) {
+  if ((p.W & 1) || (p.H & 1) || p.W < 4 || p.H < 4) return false;
+  if ((reinterpret_cast<uintptr_t>(p.out) & 7u) != 0) return false;
+  if (p.in_real != nullptr && (reinterpret_cast<uintptr_t>(p.in_real) & 7u) != 0) return false;
+  SpectralClusterLaunch& L = *out;
+  L.p = p;
+  if (!make_axis_plan(p.H, &L.col) || !make_axis_plan(p.W / 2, &L.row, /*ascending=*/true)) return false;
+  const int M = p.W / 2;
+  L.wh = M + 1;
+  L.cols0 = (L.wh + 1) / 2;
+  L.pitch_c = L.cols0 | 1;
+  L.rows_half = p.H / 2;
+  L.pitch_r = L.wh | 1;
+  L.buf_elems = std::max(p.H * L.pitch_c, L.rows_half * L.pitch_r);
+  L.scale = p.in_real != nullptr ? 0.5f * p.out_scale : p.out_scale;
+  if ((int64_t)p.H * L.cols0 > (int64_t)kClusterMaxRegsElems * kClusterThreads) return false;
+  if ((int64_t)L.rows_half * L.wh > (int64_t)kClusterMaxRegsElems * kClusterThreads) return false;
+  L.magic_wh = magic_of(L.wh);
+  if (L.buf_elems >= (1 << 24) || (int64_t)p.H * M * (int64_t)M >= (1ll << 32)) return false;
+  L.magic_cols[0] = magic_of(L.cols0);
+  L.magic_cols[1] = magic_of(L.wh - L.cols0);
+  L.magic_rows = magic_of(L.rows_half);
+  L.magic_row_nb = magic_of(L.row.nb[L.row.n_stages - 1]);
+  *smem_out = cluster_smem_bytes(p.H, p.W, L.buf_elems, L.col, L.row);
+  return *smem_out <= (size_t)device_info().max_smem_optin;
+}
+
+static int launch_spectral_cluster(const SonarSpectralParams& p, cudaStream_t stream) {
+  SpectralClusterLaunch L;
+  size_t smem = 0;
+  if (!plan_spectral_cluster(p, &L, &smem)) return -1;
+  auto kernel = p.in_real != nullptr ? spectral_cluster_kernel<true> : spectral_cluster_kernel<false>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  const DeviceInfo& di = device_info();
+  const int64_t clusters = p.planes < di.sm_count / 2 ? p.planes : di.sm_count / 2;
+  kernel<<<(unsigned)(2 * clusters), kClusterThreads, smem, stream>>>(L);
+  err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : (int)err;
+}
+
 static bool make_plan(int n, FftPlan* plan) {
   plan->n = n;
   plan->n_factors = 0;
@@ -1110,6 +1349,17 @@ int64_t sonar_spectral_scratch_bytes(int H, int W) {
   const size_t spec = (size_t)H * wh_pad * sizeof(float2);
   const DeviceInfo& di = device_info();
   if (fixed + spec <= (size_t)di.max_smem_optin) return 0;
+  {  // planes the 2-CTA cluster kernel keeps in distributed shared memory need no scratch either
+    SonarSpectralParams probe = {};
+    probe.out = reinterpret_cast<float*>(uintptr_t{64});
+    probe.in_spec = probe.out;
+    probe.planes = 1;
+    probe.H = H;
+    probe.W = W;
+    SpectralClusterLaunch C;
+    size_t smem = 0;
+    if (plan_spectral_cluster(probe, &C, &smem)) return 0;
+  }
   return (int64_t)spec * di.sm_count * 2;
 }
 
@@ -1130,7 +1380,22 @@ int sonar_spectral_plan(int H, int W, int64_t planes, int real_input, SonarSpect
   int threads = 0, ctas_per_sm = 0;
   int64_t grid = 0;
   size_t smem = 0;
-  if (!plan_spectral_batched(p, &L, &threads, &ctas_per_sm, &grid, &smem)) return 0;  // generic kernel
+  if (!plan_spectral_batched(p, &L, &threads, &ctas_per_sm, &grid, &smem)) {
+    SpectralClusterLaunch C;
+    if (!plan_spectral_cluster(p, &C, &smem)) return 0;  // generic kernel
+    const int64_t clusters = planes < device_info().sm_count / 2 ? planes : device_info().sm_count / 2;
+    info->cluster = 1;
+    info->group = 1;
+    info->threads = kClusterThreads;
+    info->ctas_per_sm = 1;
+    info->grid = 2 * clusters;
+    info->smem_bytes = (int64_t)smem;
+    info->n_col_stages = C.col.n_stages;
+    info->n_row_stages = C.row.n_stages;
+    for (int f = 0; f < C.col.n_stages && f < SONAR_SPECTRAL_PLAN_MAX_STAGES; ++f) info->col_radix[f] = C.col.radix[f];
+    for (int f = 0; f < C.row.n_stages && f < SONAR_SPECTRAL_PLAN_MAX_STAGES; ++f) info->row_radix[f] = C.row.radix[f];
+    return 0;
+  }
   info->batched = 1;
   info->group = L.group;
   info->threads = threads;
@@ -1163,6 +1428,10 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params, void* stream_) 
   }
   {
     const int rc = launch_spectral_batched(p, (cudaStream_t)stream_);
+    if (rc >= 0) return rc;
+  }
+  if (!philox) {  // too large for one SM's shared memory: a cluster of two
+    const int rc = launch_spectral_cluster(p, (cudaStream_t)stream_);
     if (rc >= 0) return rc;
   }
   if (philox) return (int)cudaErrorInvalidValue;  // only the batched kernel regenerates its input (even W, radices 2..16)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 5
+#define SONAR_B200_ABI_VERSION 6
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
@@ -432,6 +432,8 @@ typedef struct SonarSpectralPlanInfo {
   int32_t n_row_stages;
   int32_t col_radix[SONAR_SPECTRAL_PLAN_MAX_STAGES];
   int32_t row_radix[SONAR_SPECTRAL_PLAN_MAX_STAGES];
+  int32_t cluster;  /* 1: the plane lives in the distributed shared memory of a 2-CTA cluster (e.g. 256x256) */
+  int32_t pad_;
 } SonarSpectralPlanInfo;
 int sonar_spectral_plan(int H, int W, int64_t planes, int real_input, SonarSpectralPlanInfo* info_host);
 

@@ -321,3 +321,24 @@ def test_attached_sums_expire_when_the_ring_wraps(sb, cuda):
         s2 = sb.ops.attached_sums(other)
     side.synchronize()
     torch.testing.assert_close(s2, torch.stack((other.double().sum(), other.double().square().sum())), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize(("hw", "planes"), [((256, 256), 3), ((256, 256), 151), ((192, 320), 5), ((320, 192), 2), ((240, 288), 75)])
+def test_spectral_cluster_kernel(sb, cuda, hw, planes):
+    """Planes whose half spectrum exceeds one SM's shared memory (256x256: 264 KB) run on a cluster of two CTAs with
+    the plane in distributed shared memory: spectrum and real input, more planes than clusters, output moments."""
+    h, w = hw
+    torch.manual_seed(h + w + planes)
+    spec = torch.randn(planes, h, w // 2 + 1, dtype=torch.complex64)
+    mask = torch.rand(h, w // 2 + 1) + 0.5
+    want = torch.fft.irfft2(spec * mask, s=(h, w), norm="ortho")
+    got = sb.ops.spectral_filter(spectrum=spec.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / math.sqrt(h * w))
+    assert_close(got, want, what=f"cluster irfft2 {hw} x{planes}")
+    sums = sb.ops.attached_sums(got)
+    torch.testing.assert_close(sums.cpu(), torch.stack((want.double().sum(), want.double().square().sum())), rtol=1e-5, atol=1e-2)
+    real = torch.randn(planes, h, w)
+    want = torch.fft.irfft2(torch.fft.rfft2(real, norm="ortho") * mask, s=(h, w), norm="ortho")
+    got = sb.ops.spectral_filter(real=real.to(cuda), mask=mask.to(cuda), hw=hw, out_scale=1.0 / (h * w))
+    assert_close(got, want, what=f"cluster rfft2-irfft2 {hw} x{planes}")
+    ident = sb.ops.spectral_filter(real=real.to(cuda), mask=None, hw=hw, out_scale=1.0 / (h * w))
+    assert_close(ident, real, what=f"cluster identity {hw}")

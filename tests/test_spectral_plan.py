@@ -205,7 +205,10 @@ def test_every_plannable_axis_length_transforms_correctly(sb):
 def test_plan_declines_what_the_generic_kernel_handles(sb):
     assert _plan(sb, 31, 47).batched == 0       # odd width
     assert _plan(sb, 64, 2 * 7 * 8).batched == 0  # prime factor 7
-    assert _plan(sb, 256, 256).batched == 0     # 264 KB half spectrum does not fit shared memory
+    big = _plan(sb, 256, 256, planes=64)
+    assert big.batched == 0 and big.cluster == 1  # 264 KB half spectrum: distributed shared memory of a 2-CTA cluster
+    assert (big.threads, big.ctas_per_sm, big.grid) == (1024, 1, 128) and big.smem_bytes <= 227 * 1024
+    assert _plan(sb, 512, 512).batched == 0 and _plan(sb, 512, 512).cluster == 0  # beyond two SMs: generic kernel
     small = _plan(sb, 32, 32, planes=2560)
     assert small.batched == 1 and small.group > 1, "UNet-sized planes are grouped per CTA"
     assert _plan(sb, 32, 32, planes=4).group == 1, "few planes: one per CTA so more SMs work"
