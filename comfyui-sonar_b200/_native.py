@@ -64,7 +64,7 @@ class SonarStepParams(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 6  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
+ABI_VERSION = 8  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
@@ -73,7 +73,7 @@ FFT_MAX_FACTORS = 24
 DWT_MAX_TAPS = 40
 
 
-FILL_BATCH_MAX = 16
+FILL_BATCH_MAX = 32
 MIXER_SMALL_MAX = 8  # SONAR_MIXER_SMALL_MAX
 
 
@@ -387,7 +387,8 @@ SIGNATURES: dict[str, list] = {
     ],
     "sonar_spectral_scratch_bytes": [c_int, c_int],
     "sonar_spectral_filter_f32": [POINTER(SonarSpectralParams), c_void_p],
-    "sonar_channel_mix_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p],
+    "sonar_channel_mix_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p],
+    "sonar_channel_mix_packed_floats": [c_int32],
     "sonar_spectral_plan": [c_int, c_int, c_int64, c_int, POINTER(SonarSpectralPlanInfo)],
     "sonar_dwt_coeff_len": [c_int, c_int],
     "sonar_dwt2_analysis": [POINTER(SonarDwtAnalysisParams), c_void_p],
@@ -402,6 +403,7 @@ SIGNATURES: dict[str, list] = {
 
 # functions whose return value is not an error code
 RESTYPES = {
+    "sonar_channel_mix_packed_floats": c_int64,
     "sonar_spectral_scratch_bytes": c_int64,
     "sonar_wcfg_fused_smem_bytes": c_int64,
     "sonar_freeu_range_bytes": c_int64,

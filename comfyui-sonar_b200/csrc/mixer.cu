@@ -12,7 +12,8 @@
 //    mat-vec. One thread owns 4 consecutive pixels of one batch item, holds the C input float4 in
 //    registers and writes C output float4: exactly one read and one write of the tensor, float4 both ways.
 //  * video latents folded by frames_to_channels (C5: C = 16 x 33 = 528): a real GEMM, 64 x 128 output
-//    tiles, K in steps of 16 through shared memory, 4 x 8 outputs per thread. It stays on the fp32 FMA
+//    tiles, K in steps of 16 through a ring of shared-memory stages filled by bulk-async copies (cp.async.bulk +
+//    mbarrier, a dedicated producer warp), 4 x 8 outputs per thread. It stays on the fp32 FMA
 //    pipe on purpose: the north-star tolerance is 1e-5 and the tensor cores have no fp32 mode (TF32
 //    keeps 10 mantissa bits); the mixer is the identity (skipped) unless common_mode != 0.
 #include "common.cuh"
@@ -70,7 +71,7 @@ constexpr int kMixBM = 64, kMixBN = 128, kMixBK = 16;
 // grid: x = n tile (fastest: neighbouring CTAs share the A tile in L2), then m tile, then batch item
 __global__ void __launch_bounds__(kBlock)
 channel_mix_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ mixer, int C,
-                         int64_t hw, int tiles_n, int tiles_m, double* sums, double* sums_clear) {
+                         int64_t hw, int tiles_n, int tiles_m, int vec_ok, double* sums, double* sums_clear) {
   __shared__ float As[kMixBK][kMixBM + 4];  // [k][m]: M[m0 + m][k0 + k]
   __shared__ float Bs[kMixBK][kMixBN];      // [k][n]: in[b][k0 + k][n0 + n]
   const int tile = blockIdx.x;
@@ -86,7 +87,7 @@ channel_mix_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-  const bool n_vec = (hw & 3) == 0 && n0 + kMixBN <= hw;
+  const bool n_vec = vec_ok && (hw & 3) == 0 && n0 + kMixBN <= hw;  // float4 rows: 16-byte aligned tensors only
   for (int k0 = 0; k0 < C; k0 += kMixBK) {
     // A tile: 64 x 16 = 1024 elements, 4 per thread, read along k (contiguous in M's rows)
 #pragma unroll
@@ -157,6 +158,175 @@ channel_mix_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, 
   commit_moments(sums, sums_clear, s, ss);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-async pipelined variant of the tiled GEMM (the default for 16-byte-aligned operands): a producer warp streams
+// the A (64 x 16) and B (16 x 128) tiles of the next k-blocks into a ring of shared-memory stages with
+// cp.async.bulk (the TMA engine's 1-D bulk copy: one instruction per tile row, no registers, no address math in
+// the consumers), completion is counted in bytes on an mbarrier per stage (expect-tx), and eight consumer warps
+// do nothing but shared-memory loads and FMAs; a second mbarrier per stage hands the slot back to the producer.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMixStages = 3;
+constexpr int kMixAPitch = kMixBK + 4;  // floats per A row in shared memory: 80 bytes (16-byte multiple, spreads the banks)
+constexpr int kMixConsumers = 256;
+constexpr int kMixBulkThreads = kMixConsumers + 32;
+
+struct MixStageBuf {
+  float A[kMixBM][kMixAPitch];  // [m][k]: M[m0 + m][k0 + k]
+  float B[kMixBK][kMixBN];      // [k][n]: in[b][k0 + k][n0 + n]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled in bytes on `bar` (size and both addresses: multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// `packed` = the mixer pre-tiled by sonar_channel_mix_pack_bytes' layout: [tiles_m][k-blocks][64][kMixAPitch], zero
+// padded, so an A tile is ONE 5 KB bulk copy (64 separate 64-byte row copies made the kernel producer-bound: the
+// copy engine retires a descriptor every ~15 cycles) and ragged edges need no special case.
+__global__ void __launch_bounds__(kMixBulkThreads)
+channel_mix_bulk_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ packed, int C,
+                        int64_t hw, int tiles_n, int tiles_m, double* sums, double* sums_clear) {
+  __shared__ __align__(128) MixStageBuf stage[kMixStages];
+  __shared__ __align__(8) uint64_t full_bar[kMixStages], empty_bar[kMixStages];
+  const int tile = blockIdx.x;
+  const int tn = tile % tiles_n, tm = (tile / tiles_n) % tiles_m;
+  const int64_t b = tile / (tiles_n * tiles_m);
+  const int m0 = tm * kMixBM;
+  const int64_t n0 = (int64_t)tn * kMixBN;
+  const float* inb = in + b * C * hw;
+  float* outb = out + b * C * hw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMixStages; ++s) {
+      mbar_init(&full_bar[s], 1);                   // the producer's arrive.expect_tx; the copies complete the bytes
+      mbar_init(&empty_bar[s], kMixConsumers / 32);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int n_kblocks = (C + kMixBK - 1) / kMixBK;
+  constexpr uint32_t kBytesA = kMixBM * kMixAPitch * sizeof(float);
+  const float* a_tiles = packed + (int64_t)tm * n_kblocks * (kMixBM * kMixAPitch);
+  const uint32_t bytes_b_row = (uint32_t)((hw - n0 < kMixBN ? hw - n0 : kMixBN) * sizeof(float));
+  float s = 0.0f, ss = 0.0f;
+  if (warp == kMixConsumers / 32) {
+    // ---------------- producer warp ----------------
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+      const int st = kb % kMixStages;
+      const uint32_t phase = (uint32_t)(kb / kMixStages) & 1u;
+      mbar_wait(&empty_bar[st], phase ^ 1u);  // (a fresh barrier passes the first round)
+      const int k0 = kb * kMixBK;
+      const int kk = C - k0 < kMixBK ? C - k0 : kMixBK;  // rows of B that exist (the A tile is zero beyond them)
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[st], kBytesA + (uint32_t)kk * bytes_b_row);
+        bulk_g2s(&stage[st].A[0][0], a_tiles + (int64_t)kb * (kMixBM * kMixAPitch), kBytesA, &full_bar[st]);
+      }
+      __syncwarp();
+      if (lane < kk) bulk_g2s(&stage[st].B[lane][0], inb + (int64_t)(k0 + lane) * hw + n0, bytes_b_row, &full_bar[st]);
+    }
+  } else {
+    // ---------------- consumer warps: 16 x 16 threads, 4 rows x 8 columns each ----------------
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+      const int st = kb % kMixStages;
+      const uint32_t phase = (uint32_t)(kb / kMixStages) & 1u;
+      mbar_wait(&full_bar[st], phase);
+      const int k0 = kb * kMixBK;
+      const MixStageBuf& sb = stage[st];
+      if (C - k0 >= kMixBK) {
+#pragma unroll
+        for (int k4 = 0; k4 < kMixBK; k4 += 4) {
+          float4 a4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(&sb.A[ty * 4 + i][k4]);
+#pragma unroll
+          for (int kq = 0; kq < 4; ++kq) {
+            const float4 b0 = *reinterpret_cast<const float4*>(&sb.B[k4 + kq][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sb.B[k4 + kq][64 + tx * 4]);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float av = kq == 0 ? a4[i].x : kq == 1 ? a4[i].y : kq == 2 ? a4[i].z : a4[i].w;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av, bv[j], acc[i][j]);
+            }
+          }
+        }
+      } else {  // ragged last k-block: only the first C - k0 columns / rows of the tiles were copied
+        for (int k = 0; k < C - k0; ++k) {
+          const float4 b0 = *reinterpret_cast<const float4*>(&sb.B[k][tx * 4]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&sb.B[k][64 + tx * 4]);
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float av = sb.A[ty * 4 + i][k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av, bv[j], acc[i][j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);  // this warp is done with the slot
+    }
+    const bool n_vec = n0 + kMixBN <= hw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= C) continue;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int64_t n = n0 + half * 64 + tx * 4;
+        float* p = outb + (int64_t)m * hw + n;
+        const float* a = &acc[i][half * 4];
+        if (n_vec) {
+          st4(p, make_float4(a[0], a[1], a[2], a[3]));
+          s += (a[0] + a[1]) + (a[2] + a[3]);
+          ss += (a[0] * a[0] + a[1] * a[1]) + (a[2] * a[2] + a[3] * a[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < hw) {
+              p[j] = a[j];
+              s += a[j];
+              ss += a[j] * a[j];
+            }
+        }
+      }
+    }
+  }
+  commit_moments(sums, sums_clear, s, ss);
+}
+
 template <int C>
 static void launch_small(const float* in, float* out, const float* mixer_host, int64_t batch, int64_t hw, double* sums,
                          double* sums_clear, cudaStream_t stream) {
@@ -173,8 +343,16 @@ static void launch_small(const float* in, float* out, const float* mixer_host, i
 
 }  // namespace sonar
 
-extern "C" int sonar_channel_mix_f32(const float* in, float* out, const float* mixer, const float* mixer_host, int64_t batch,
-                                     int32_t channels, int64_t hw, double* sums, double* sums_clear, void* stream_) {
+extern "C" int64_t sonar_channel_mix_packed_floats(int32_t channels) {
+  using namespace sonar;
+  if (channels <= 0) return 0;
+  const int64_t tiles_m = (channels + kMixBM - 1) / kMixBM, kblocks = (channels + kMixBK - 1) / kMixBK;
+  return tiles_m * kblocks * kMixBM * kMixAPitch;
+}
+
+extern "C" int sonar_channel_mix_f32(const float* in, float* out, const float* mixer, const float* mixer_host,
+                                     const float* mixer_packed, int64_t batch, int32_t channels, int64_t hw, double* sums,
+                                     double* sums_clear, void* stream_) {
   using namespace sonar;
   if (batch <= 0 || hw <= 0 || channels <= 0) return 0;
   if (in == nullptr || out == nullptr || in == out || mixer == nullptr) return (int)cudaErrorInvalidValue;
@@ -197,8 +375,15 @@ extern "C" int sonar_channel_mix_f32(const float* in, float* out, const float* m
   const int64_t tiles_n = (hw + kMixBN - 1) / kMixBN;
   const int64_t grid = tiles_n * tiles_m * batch;
   if (grid > 0x7fffffffll || tiles_n > 0x7fffffffll) return (int)cudaErrorInvalidValue;
-  channel_mix_tiled_kernel<<<(unsigned)grid, kBlock, 0, stream>>>(in, out, mixer, channels, hw, (int)tiles_n, tiles_m, sums,
-                                                                 sums_clear);
+  // rows of A and B start on 16-byte boundaries: the bulk-async pipeline; anything else: the plain tiled kernel
+  // (below 32 channels most of a 64-row tile is padding and the plain kernel is as fast)
+  const bool bulk_ok = mixer_packed != nullptr && channels >= 32 && (hw & 3) == 0 && aligned16(in) && aligned16(mixer_packed) && aligned16(out);
+  if (bulk_ok)
+    channel_mix_bulk_kernel<<<(unsigned)grid, kMixBulkThreads, 0, stream>>>(in, out, mixer_packed, channels, hw, (int)tiles_n,
+                                                                           tiles_m, sums, sums_clear);
+  else
+    channel_mix_tiled_kernel<<<(unsigned)grid, kBlock, 0, stream>>>(in, out, mixer, channels, hw, (int)tiles_n, tiles_m,
+                                                                   aligned16(in) && aligned16(out) ? 1 : 0, sums, sums_clear);
   SONAR_LAUNCH_CHECK();
   return 0;
 }

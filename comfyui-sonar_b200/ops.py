@@ -830,8 +830,23 @@ def spectral_plan_batched(height: int, width: int, planes: int) -> bool:
     return hit
 
 
-def channel_mix(noise: torch.Tensor, mixer: torch.Tensor, mixer_host: torch.Tensor | None = None) -> torch.Tensor:
-    """out[b, c] = sum_k mixer[c, k] * noise[b, k] per pixel (ChannelMixer.apply); the moments of the result ride along."""
+def pack_mixer(mixer: torch.Tensor) -> torch.Tensor:
+    """The (C, C) mixer pre-tiled for the bulk-async GEMM: [ceil(C/64)][ceil(C/16)][64][20] floats, zero padded (one
+    contiguous 5 KB block per A tile). Setup work, once per sampler; returns a tensor on the mixer's device."""
+    c = mixer.shape[0]
+    tiles_m, kblocks = -(-c // 64), -(-c // 16)
+    src = torch.zeros((tiles_m * 64, kblocks * 16), dtype=torch.float32)
+    src[:c, :c] = mixer.detach().to("cpu", torch.float32)
+    packed = torch.zeros((tiles_m, kblocks, 64, 20), dtype=torch.float32)
+    packed[..., :16] = src.reshape(tiles_m, 64, kblocks, 16).permute(0, 2, 1, 3)
+    assert packed.numel() == _native.load().sonar_channel_mix_packed_floats(c)
+    return packed.to(mixer.device).contiguous()
+
+
+def channel_mix(noise: torch.Tensor, mixer: torch.Tensor, mixer_host: torch.Tensor | None = None,
+                mixer_packed: torch.Tensor | None = None) -> torch.Tensor:  # fmt: skip
+    """out[b, c] = sum_k mixer[c, k] * noise[b, k] per pixel (ChannelMixer.apply); the moments of the result ride along.
+    mixer_host: the matrix on the CPU (C <= 8: passed by value); mixer_packed: pack_mixer(mixer) (larger C: bulk-async GEMM)."""
     _f32(noise, "noise")
     _f32(mixer, "mixer")
     if noise.ndim != 4:
@@ -840,16 +855,18 @@ def channel_mix(noise: torch.Tensor, mixer: torch.Tensor, mixer_host: torch.Tens
     if tuple(mixer.shape) != (channels, channels):
         raise ValueError("Channel count mismatch")
     out = torch.empty_like(noise)
-    lib, stream = _prepare(noise, mixer, out)
+    lib, stream = _prepare(noise, mixer, out, mixer_packed)
     host_ptr = None
     if mixer_host is not None and channels <= _native.MIXER_SMALL_MAX:
         if mixer_host.dtype != torch.float32 or not mixer_host.is_contiguous() or mixer_host.is_cuda:
             raise ValueError("mixer_host must be a contiguous float32 CPU tensor")
         host_ptr = ctypes.c_void_p(mixer_host.data_ptr())
+    if mixer_packed is not None and mixer_packed.numel() != lib.sonar_channel_mix_packed_floats(channels):
+        raise ValueError("mixer_packed does not match the channel count (see pack_mixer)")
     slot, slot_ptr, clear_ptr = sums_slot(out.device)
     _launch(
         "sonar_channel_mix_f32", lib.sonar_channel_mix_f32,
-        _ptr(noise), _ptr(out), _ptr(mixer), host_ptr, batch, channels, height * width, slot_ptr, clear_ptr, stream,
+        _ptr(noise), _ptr(out), _ptr(mixer), host_ptr, _ptr(mixer_packed), batch, channels, height * width, slot_ptr, clear_ptr, stream,
     )  # fmt: skip
     return _sums_written(out, slot)
 

@@ -65,7 +65,10 @@ class ChannelMixer:
         mixer = self.mixer
         if mixer.dtype != torch.float32 or not mixer.is_contiguous():
             mixer = self.mixer = mixer.to(torch.float32).contiguous()
-        return ops.channel_mix(noise.reshape(b, c, h, w).contiguous(), mixer, getattr(self, "mixer_host", None))
+        packed = getattr(self, "mixer_packed", None)
+        if c > 8 and (packed is None or packed.device != mixer.device):
+            packed = self.mixer_packed = ops.pack_mixer(mixer)  # once per sampler: pre-tiled for the bulk-async GEMM
+        return ops.channel_mix(noise.reshape(b, c, h, w).contiguous(), mixer, getattr(self, "mixer_host", None), packed)
 
     __call__ = apply
 
@@ -327,7 +330,7 @@ class PowerNoiseItem(CustomNoiseItemBase):
         return sampler
 
 
-LOOKAHEAD_BYTES = 1 << 30  # spectrum + samples made ahead of time by one look-ahead batch
+LOOKAHEAD_BYTES = 2 << 30  # spectrum + samples made ahead of time by one look-ahead batch
 # Regenerating a single-row complex draw inside the FFT kernel (ops.spectral_filter(philox=...)) is instruction-neutral
 # and saves a launch, but a single-row draw has at most ~70 planes of 64x64: the Philox work then runs on as many CTAs
 # instead of the ~66 x 256 threads of the fill kernel. Measured on B200, C1 (1x4x64x64): 39 us in-kernel vs 7 + 17.5 us

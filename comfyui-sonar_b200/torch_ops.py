@@ -127,7 +127,12 @@ def _spectral_filter(real: Tensor | None, spectrum: Tensor | None, mask: Tensor 
 
 
 _register("spectral_filter(Tensor? real, Tensor? spectrum, Tensor? mask, int H, int W, float out_scale) -> Tensor", _spectral_filter)
-_register("channel_mix(Tensor noise, Tensor mixer) -> Tensor", lambda noise, mixer: ops.channel_mix(noise.contiguous(), mixer.contiguous()))
+_register(
+    "channel_mix(Tensor noise, Tensor mixer) -> Tensor",
+    lambda noise, mixer: ops.channel_mix(
+        noise.contiguous(), mixer.contiguous(), None, ops.pack_mixer(mixer) if mixer.shape[0] > 8 else None,
+    ),
+)
 
 
 def _pyramid_accum(base: Tensor | None, levels: Sequence[Tensor], weights: Sequence[float], H: int, W: int,  # noqa: N803

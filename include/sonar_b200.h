@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 6
+#define SONAR_B200_ABI_VERSION 8
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
@@ -52,7 +52,7 @@ int sonar_philox_uniform_f32(float* out, int64_t begin, int64_t count, int64_t n
 /* Several draws in one launch (a pyramid sample = base + every level; a Perlin sample = base + angle
  * grids). Each draw keeps its own geometry / offset / transform (kind 0: normal with mean p0, std p1;
  * kind 1: uniform on [p0, p1)), so the values equal those of separate calls; all share `seed`. */
-#define SONAR_FILL_BATCH_MAX 16
+#define SONAR_FILL_BATCH_MAX 32
 typedef struct SonarFillDesc {
   float* out;
   int64_t begin;
@@ -373,7 +373,7 @@ int sonar_item_minmax_rescale_f32(const float* x, float* out, int64_t items, int
  * H and W may be any positive sizes (mixed radix 4/2 + direct prime radices).
  * ---------------------------------------------------------------------------------------------- */
 #define SONAR_FFT_MAX_FACTORS 24
-#define SONAR_SPECTRAL_MAX_SEGMENTS 16
+#define SONAR_SPECTRAL_MAX_SEGMENTS 32
 typedef struct SonarSpectralParams {
   float* out;
   const float* in_real;
@@ -409,11 +409,15 @@ int sonar_spectral_filter_f32(const SonarSpectralParams* params_host, void* stre
  * (batch, channels, hw) tensor; `mixer` is the (channels x channels) row-major matrix ON THE DEVICE.
  * replaces: ChannelMixer.apply                             py/nodes/powernoise.py:94-101
  * channels <= SONAR_MIXER_SMALL_MAX and mixer_host != NULL (the same matrix in host memory): per-pixel mat-vec
- * with the matrix passed by value; otherwise a tiled fp32 GEMM. `in` must not alias `out`.
+ * with the matrix passed by value. Otherwise a tiled fp32 GEMM; with `mixer_packed` (device, 16-byte aligned; hw a
+ * multiple of 4) its tiles are streamed by bulk-async copies behind mbarriers. mixer_packed is the matrix pre-tiled
+ * as [ceil(C/64)][ceil(C/16)][64][20] floats, zero padded (entry [tm][kb][m][k] = mixer[64 tm + m][16 kb + k], k < 16),
+ * sonar_channel_mix_packed_floats(C) floats in all. `in` must not alias `out`.
  * sums / sums_clear: as SonarSpectralParams (moments of the output accumulated into sums; may be NULL). */
 #define SONAR_MIXER_SMALL_MAX 8
-int sonar_channel_mix_f32(const float* in, float* out, const float* mixer, const float* mixer_host, int64_t batch,
-                          int32_t channels, int64_t hw, double* sums, double* sums_clear, void* stream);
+int64_t sonar_channel_mix_packed_floats(int32_t channels);
+int sonar_channel_mix_f32(const float* in, float* out, const float* mixer, const float* mixer_host, const float* mixer_packed,
+                          int64_t batch, int32_t channels, int64_t hw, double* sums, double* sums_clear, void* stream);
 
 /* Host-only query (no GPU work): how sonar_spectral_filter_f32 would run `planes` planes of (H, W).
  * batched = 1: the in-place shared-memory kernel with `group` planes per CTA pass, `threads` threads per CTA,

@@ -140,7 +140,7 @@ def test_channel_mix_kernel_vs_matmul(sb, cuda, shape):
     noise = torch.randn(shape)
     mixer = orc.channel_mixer(c, 0.15, "1, 0.5, -0.25, 0.75").contiguous()  # (ldl_factor returns column-major storage)
     want = orc.channel_mix(noise.double(), mixer.double())
-    got = sb.ops.channel_mix(noise.to(cuda), mixer.to(cuda), mixer)
+    got = sb.ops.channel_mix(noise.to(cuda), mixer.to(cuda), mixer, sb.ops.pack_mixer(mixer.to(cuda)) if c > 8 else None)
     assert_close(got, want.float(), what=f"channel_mix {shape}")
     sums = sb.ops.attached_sums(got)
     assert sums is not None
