@@ -44,7 +44,8 @@ def test_register_and_stack_budgets(usage):
     for name, reg, stack, _shared, _local in _select(usage, r"sonar_step_fast_philox2_kernel"):
         assert reg <= 32 and stack == 0, (name, reg, stack)
     for name, reg, stack, _shared, _local in _select(usage, r"sonar_step"):  # every specialised and generic variant
-        assert reg <= 48 and stack <= 8, (name, reg, stack)
+        # (philox4 keeps the 16 normals of four Philox calls in registers: 64 = four CTAs of 256 per SM)
+        assert reg <= (64 if "philox4" in name else 48) and stack <= 8, (name, reg, stack)
     # 1024 threads per SM at 64 registers: the shared-memory-resident kernels may spill a few words, not more
     # (<2> regenerates its input from the Philox stream: the small-draw variant carries the generator state as well)
     for name, reg, stack, _shared, _local in _select(usage, r"spectral_batched_kernel"):
