@@ -407,7 +407,7 @@ def run_b200_arm(args) -> None:
     timers = []
     gc.collect()
     gc.disable()  # a collection pause between two launches would show up as device idle time
-    with ClockSampler(local_rank, enabled=rank == 0) as clocks:
+    with ClockSampler(local_rank, enabled=rank == 0 and os.environ.get("SONAR_BENCH_NO_CLOCKS") is None) as clocks:
         barrier()
         one_run(StepTimer(dev, timed=False, on_first_call=rendezvous), x0)  # one more untimed run with the clock poller up
         barrier()
@@ -417,8 +417,10 @@ def run_b200_arm(args) -> None:
             if world > 1:
                 barrier()
             timer = StepTimer(dev, on_first_call=rendezvous)
+            t_run = time.perf_counter()
             one_run(timer, x0)
             timer.close()
+            timer.host_ms = (time.perf_counter() - t_run) * 1e3  # host time to ENQUEUE the run (not a device time)
             timers.append(timer)
         barrier()
         wall = time.perf_counter() - t_wall
@@ -555,6 +557,8 @@ def run_b200_arm(args) -> None:
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall,
             "runs_ms": run_ms,
+            "runs_host_enqueue_ms": [round(t.host_ms, 2) for t in timers],
+            "runs_max_interval_ms": [round(max(a.elapsed_time(b) for a, b in t.pairs), 3) for t in timers],
             "per_rank_ms": per_rank_ms,
         }
         if parity is not None:

@@ -297,6 +297,8 @@ class PowerNoiseItem(CustomNoiseItemBase):
         mask, ortho, mixer, factor, _ = sampler.spectral
         if x.ndim == 4 and factor == 1 and not normalized and (mixer.mixer is None or mixer.is_identity):
 
+            state: dict = {}  # the sampler's look-ahead slab (see below)
+
             def lookahead(count: int):
                 """The next `count` samples in ONE Philox launch + ONE FFT launch (per-sample statistics): a sample is a
                 function of the generator state only, so a consumer that knows it will ask again (a sampler with
@@ -313,11 +315,18 @@ class PowerNoiseItem(CustomNoiseItemBase):
                     return None
                 total, begin = parallel.global_draw_geometry(spec_shape)
                 draws = ops.peek_draws(2 * total, device, count)
-                # (one allocation of one size per batch: the caching allocator hands the same block back every time)
+                # One slab per sampler for spectrum + samples, taken from (and returned to) a pool of our own: a batch is
+                # made only when the previous one has been consumed by kernels already enqueued on this stream, so the
+                # slab is simply overwritten. Going through torch's caching allocator for ~1 GB blocks nine times per
+                # run fragments it (smaller tensors get carved out of the freed slab) and ends in cudaMalloc / cudaFree
+                # stalls of 20-180 ms inside a sampler step.
                 spec_bytes = 8 * count * math.prod(spec_shape)
-                slab = torch.empty(spec_bytes + 4 * count * numel, device=device, dtype=torch.uint8)
-                spec = slab[:spec_bytes].view(torch.complex64).reshape(count, *spec_shape)
-                out = slab[spec_bytes:].view(torch.float32).reshape(count * planes, height, width)
+                need = spec_bytes + 4 * count * numel
+                slab = state.get("slab")
+                if slab is None or slab.tensor.numel() < need:
+                    slab = state["slab"] = _Slab.acquire(device, need)
+                spec = slab.tensor[:spec_bytes].view(torch.complex64).reshape(count, *spec_shape)
+                out = slab.tensor[spec_bytes:need].view(torch.float32).reshape(count * planes, height, width)
                 ops.philox_fill_batch([(d, spec[j], "normal", 0.0, std, 2 * begin) for j, d in enumerate(draws)])
                 out, table = ops.spectral_filter(
                     spectrum=spec.reshape(count * planes, height, bins), mask=mask, hw=(height, width), out_scale=ortho,
@@ -330,12 +339,36 @@ class PowerNoiseItem(CustomNoiseItemBase):
         return sampler
 
 
-LOOKAHEAD_BYTES = 2 << 30  # spectrum + samples made ahead of time by one look-ahead batch
+LOOKAHEAD_BYTES = int(os.environ.get("SONAR_B200_LOOKAHEAD_BYTES", 2 << 30))  # spectrum + samples made ahead of time by one look-ahead batch
 # Regenerating a single-row complex draw inside the FFT kernel (ops.spectral_filter(philox=...)) is instruction-neutral
 # and saves a launch, but a single-row draw has at most ~70 planes of 64x64: the Philox work then runs on as many CTAs
 # instead of the ~66 x 256 threads of the fill kernel. Measured on B200, C1 (1x4x64x64): 39 us in-kernel vs 7 + 17.5 us
 # as two launches. Kept behind this switch (and tested), off by default.
 IN_KERNEL_PHILOX = os.environ.get("SONAR_B200_SPECTRAL_PHILOX") == "1"
+
+
+class _Slab:
+    """A look-ahead buffer owned by one noise sampler; returns to the pool (keyed by device, stream and size) when the
+    sampler is garbage-collected, so the next sampler of the same shape on the same stream reuses it without an
+    allocator round trip."""
+
+    _pool: dict = {}
+
+    def __init__(self, key, tensor):
+        self.key, self.tensor = key, tensor
+
+    @classmethod
+    def acquire(cls, device, nbytes: int) -> "_Slab":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, ops._raw_stream(idx), int(nbytes))  # noqa: SLF001
+        free = cls._pool.get(key)
+        tensor = free.pop() if free else torch.empty(int(nbytes), device=device, dtype=torch.uint8)
+        return cls(key, tensor)
+
+    def __del__(self):
+        pool = self._pool.setdefault(self.key, [])
+        if len(pool) < 2:  # (at most two idle slabs per shape: the rest goes back to torch's allocator)
+            pool.append(self.tensor)
 
 
 class _PhiloxSpectrum:
