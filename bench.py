@@ -495,6 +495,23 @@ def run_b200_arm(args) -> None:
         if i >= 2:
             e2e_times.append(time.perf_counter() - t0)
     gc.enable()
+    # where the end-to-end time goes (one extra pass, events on the stream; not part of the timed numbers)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    barrier()
+    t0 = time.perf_counter()
+    ev[0].record()
+    x_dev = x0_host.to(dev, non_blocking=True)
+    ev[1].record()
+    out = one_run(e2e_model, x_dev)
+    ev[2].record()
+    t_enq = time.perf_counter() - t0
+    if world == 1:
+        out_host.copy_(out, non_blocking=True)
+    ev[3].record()
+    torch.cuda.synchronize()
+    e2e_breakdown = {"h2d_ms": ev[0].elapsed_time(ev[1]), "run_ms": ev[1].elapsed_time(ev[2]), "host_enqueue_ms": t_enq * 1e3}
+    if world == 1:
+        e2e_breakdown["d2h_ms"] = ev[2].elapsed_time(ev[3])
     e2e_s = statistics.mean(e2e_times)
     t_dev = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -507,6 +524,7 @@ def run_b200_arm(args) -> None:
         "h2d_bytes_per_step": bytes_total,
         "d2h_bytes_per_step": bytes_total,
         "ms_per_step": e2e_s * 1e3,
+        "breakdown_rank0": {k: round(v, 3) for k, v in e2e_breakdown.items()},
         "note": "public sampler function (SonarDPMPPSDE.sampler, custom_noise chain), pinned host x0 -> H2D (each rank its "
         "shard), the sampler run with the stub denoiser inside, "
         + ("NCCL gather to rank 0 overlapped with rank 0's own D2H, " if world > 1 else "")

@@ -113,11 +113,12 @@ def test_empty_and_errors(sb, cuda):
 
 def test_batched_draws_equal_separate_torch_draws(sb, cuda):
     """rng.batched(): several draws reserved in order, materialised by ONE launch, still bit-identical
-    to the sequence of torch calls (different sizes, kinds, transforms; more than 16 draws)."""
+    to the sequence of torch calls (different sizes, kinds, transforms; more draws than one launch holds)."""
+    n_draws = sb.ops.FILL_BATCH_MAX + 8
     shapes = [(16, 16, 128, 128), (16, 16, 36, 36), (16, 16, 7, 7), (16, 16, 1, 1), (3, 5), (16, 129, 129)]
     torch.manual_seed(2024)
     want = []
-    for i in range(20):
+    for i in range(n_draws):
         shp = shapes[i % len(shapes)]
         if i % 3 == 0:
             want.append(torch.empty(shp, device=cuda).uniform_(0.0, 2.0 * math.pi))
@@ -130,7 +131,7 @@ def test_batched_draws_equal_separate_torch_draws(sb, cuda):
     launches = sb.ops.LAUNCH_COUNT
     got = []
     with sb.rng.batched():
-        for i in range(20):
+        for i in range(n_draws):
             shp = shapes[i % len(shapes)]
             if i % 3 == 0:
                 got.append(sb.rng.uniform(shp, device=cuda, low=0.0, high=2.0 * math.pi))
@@ -138,7 +139,7 @@ def test_batched_draws_equal_separate_torch_draws(sb, cuda):
                 got.append(sb.rng.normal(shp, device=cuda))
             else:
                 got.append(sb.rng.normal(shp, device=cuda, dtype=torch.complex64))
-    assert sb.ops.LAUNCH_COUNT - launches == 2  # 16 + 4 draws
+    assert sb.ops.LAUNCH_COUNT - launches == 2  # FILL_BATCH_MAX + 8 draws
     assert torch.cuda.default_generators[0].get_offset() == off_want
     for i, (g, w) in enumerate(zip(got, want)):
         assert torch.equal(g, w), f"draw {i}"
