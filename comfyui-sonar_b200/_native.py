@@ -64,7 +64,7 @@ class SonarStepParams(ctypes.Structure):
     ]
 
 
-ABI_VERSION = 8  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
+ABI_VERSION = 9  # SONAR_B200_ABI_VERSION of include/sonar_b200.h this binding was written against
 PEER_MAX_RANKS = 8
 PEER_TABLE_MAX = 512
 PYRAMID_MAX_LEVELS = 16
@@ -338,6 +338,7 @@ class SonarFreeuParams(ctypes.Structure):
 SIGNATURES: dict[str, list] = {
     "sonar_abi_version": [],
     "sonar_set_device": [c_int],
+    "sonar_set_grid_limit": [c_int],
     "sonar_philox_policy": [c_int64, POINTER(c_uint32), POINTER(c_uint64)],
     "sonar_philox_normal_f32": [
         c_void_p, c_int64, c_int64, c_int64, c_uint64, c_uint64, c_uint32, c_float, c_float, c_void_p,

@@ -63,6 +63,22 @@ inline int streaming_grid(int64_t work_items, int items_per_block, int waves = 4
   return (int)(need < cap ? need : cap);
 }
 
+// Co-scheduling hint (sonar_set_grid_limit, api.cu): when > 0, the grid-stride kernels that honour it launch at
+// most this many CTAs per SM, leaving the other thread slots of every SM to a kernel on another stream -- the
+// ALU-bound noise producers (Philox fill, FFT) and the HBM-bound fused step then run on the same SMs at the same
+// time instead of one after the other.
+int& grid_limit_ctas_per_sm();
+
+inline int streaming_grid_shared(int64_t work_items, int items_per_block, int waves = 4) {
+  const int limit = grid_limit_ctas_per_sm();
+  if (limit <= 0) return streaming_grid(work_items, items_per_block, waves);
+  const DeviceInfo& di = device_info();
+  int64_t need = (work_items + items_per_block - 1) / items_per_block;
+  const int64_t cap = (int64_t)di.sm_count * limit;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
 // ---------------------------------------------------------------------------------------------
 // blend functions (reference: py/utils.py:17-21 BLENDING_MODES; ATen/native/Lerp.h:21-35)
 // ---------------------------------------------------------------------------------------------

@@ -117,7 +117,7 @@ int launch_fill(float* out, int64_t begin, int64_t count, int64_t numel_total, u
   // rows r = li / T touched by the slice -> Philox calls k = r / 4
   const int64_t k_lo = (begin / T) / 4;
   const int64_t k_hi = ((end - 1) / T) / 4;
-  const int grid = streaming_grid(T, kBlock, 1);
+  const int grid = streaming_grid_shared(T, kBlock, 1);
   philox_fill_kernel<KIND><<<grid, kBlock, 0, stream>>>(out, begin, end, s, (uint32_t)k_lo, (uint32_t)k_hi, p0, p1);
   SONAR_LAUNCH_CHECK();
   return 0;
@@ -179,7 +179,7 @@ int sonar_philox_fill_batch(const SonarFillBatch* batch, void* stream) {
     b.kind[n] = d.kind;
     b.p0[n] = d.p0;
     b.p1[n] = d.p1;
-    const int g = streaming_grid(T, kBlock, 1);
+    const int g = streaming_grid_shared(T, kBlock, 1);
     if (g > gx) gx = g;
     ++n;
   }

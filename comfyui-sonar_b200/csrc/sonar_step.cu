@@ -571,7 +571,7 @@ extern "C" int sonar_step_f32(const SonarStepParams* params, void* stream_) {
                       (p.hist_in == nullptr || aligned16(p.hist_in)) &&
                       (p.hist_out == nullptr || aligned16(p.hist_out)) && (p.noise == nullptr || aligned16(p.noise));
   if (vec_ok) {
-    const int grid = streaming_grid((p.n + 3) / 4, kBlock, 2);
+    const int grid = streaming_grid_shared((p.n + 3) / 4, kBlock, 2);
     if (fast_config(p))
       SONAR_DISPATCH_FAST(launch_fast_vec, p, p, grid, stream);
     else

@@ -1040,7 +1040,12 @@ static bool plan_spectral_batched(const SonarSpectralParams& p, SpectralBatchedL
   *threads_out = ctas_per_sm >= 4 ? 256 : ctas_per_sm == 3 ? 320 : kBatchedThreads;
   int64_t grid = (p.planes + L.group - 1) / L.group;
   // persistent CTAs: the per-CTA tables (twiddles, slot maps) are built once and reused for every group
-  if (grid > (int64_t)di.sm_count * ctas_per_sm) grid = (int64_t)di.sm_count * ctas_per_sm;
+  // co-scheduling hint (sonar_set_grid_limit): fewer resident CTAs per SM, same CTA shape -- the registers and thread
+  // slots left over go to a kernel on another stream
+  const int limit = grid_limit_ctas_per_sm();
+  const int resident = limit > 0 && limit < ctas_per_sm ? limit : ctas_per_sm;
+  if (limit > 0 && *threads_out > 256) *threads_out = 256;  // 3 x 256 threads x 64 registers leave a quarter of the register file
+  if (grid > (int64_t)di.sm_count * resident) grid = (int64_t)di.sm_count * resident;
   *grid_out = grid;
   return true;
 }

@@ -13,6 +13,7 @@
 // Band order of the detail tensor (planes, 3, h, w): [0] high along H / low along W,
 // [1] low along H / high along W, [2] high / high  (pytorch_wavelets AFB2D channel order).
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/sonar_b200.h"
@@ -683,6 +684,446 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strip kernel (the default for compile-time filter lengths): same plan as wcfg_fused_kernel -- one CTA or one
+// 2-CTA cluster per plane, every coefficient in shared memory, one launch -- re-organised around what the ncu
+// capture of that kernel showed (profiles/r02_c4_wcfg_fused_*): 2,640 instructions per warp of which 13 % were
+// DFMA; the rest was per-output index arithmetic, boundary selects, constant-bank loads of run-time indexed
+// geometry and the break tests of the synthesis taps. Here
+//   * every approximation plane that feeds another analysis level is stored WITH its boundary extension
+//     (a halo ring filled once per level from the interior), so inner loops never test a boundary;
+//   * a thread owns a column of R consecutive outputs ("strip"): an input row is loaded and row-filtered once
+//     and contributes to the LT/2 outputs whose windows contain it (32 + 16/R-ish DFMA per output instead of 48,
+//     2 + 2/R row loads instead of 4), synthesis likewise shares the row combination between stacked quads;
+//   * shared-memory windows are read as aligned pairs (LDS.128 for fp64): the window of output kx starts at the
+//     even padded column 2 kx;
+//   * the per-band CFG scales are applied once, where the coefficients are stored, not per synthesis tap;
+//   * R is picked per phase so that the strips just cover the CTA's threads (one round where possible).
+// ---------------------------------------------------------------------------------------------
+struct WcfgStripGeom {
+  int levels, pair, hi0_rows;
+  int h[SONAR_WCFG_MAX_LEVELS], w[SONAR_WCFG_MAX_LEVELS];            // coefficient extents, fine -> coarse
+  int ll_off[SONAR_WCFG_MAX_LEVELS], hi_off[SONAR_WCFG_MAX_LEVELS];  // element offsets into shared memory
+  int ll_pitch[SONAR_WCFG_MAX_LEVELS], ll_rows[SONAR_WCFG_MAX_LEVELS];  // LL[j] as the padded input of level j+1
+  int pad_t[SONAR_WCFG_MAX_LEVELS], pad_l[SONAR_WCFG_MAX_LEVELS];    // pads of level j's OWN input
+  int total;
+};
+
+static bool wcfg_strip_geometry(int H, int W, int L, int levels, WcfgStripGeom* g, bool pair) {
+  if (levels < 1 || levels > SONAR_WCFG_MAX_LEVELS || H <= 0 || W <= 0) return false;
+  g->levels = levels;
+  g->pair = pair ? 1 : 0;
+  int hh = H, ww = W;
+  for (int j = 0; j < levels; ++j) {
+    const int h = (hh + L - 1) / 2, w = (ww + L - 1) / 2;
+    g->h[j] = h;
+    g->w[j] = w;
+    g->pad_t[j] = (2 * (h - 1) - hh + L) / 2;
+    g->pad_l[j] = (2 * (w - 1) - ww + L) / 2;
+    hh = h;
+    ww = w;
+  }
+  int64_t off = 0;
+  for (int j = 0; j < levels; ++j) {
+    int rows = g->h[j], pitch = g->w[j] + (g->w[j] & 1);
+    if (j + 1 < levels) {  // padded input of level j+1; rec_{j+1} (2h' - L + 2 <= 2(h' - 1) + L) lands here on the way back
+      rows = 2 * (g->h[j + 1] - 1) + L;
+      pitch = 2 * (g->w[j + 1] - 1) + L;
+    }
+    g->ll_rows[j] = rows;
+    g->ll_pitch[j] = pitch;
+    g->ll_off[j] = (int)off;
+    off += (int64_t)rows * pitch;
+    off += off & 1;
+    g->hi_off[j] = (int)off;
+    int hi_rows = g->h[j];
+    if (j == 0) {
+      if (pair) {
+        int q_lo, q_hi, r_lo, r_hi;
+        wcfg_pair_rows(H, g->h[0], L, 0, &q_lo, &q_hi, &r_lo, &r_hi);
+        hi_rows = r_hi - r_lo;
+        wcfg_pair_rows(H, g->h[0], L, 1, &q_lo, &q_hi, &r_lo, &r_hi);
+        if (r_hi - r_lo > hi_rows) hi_rows = r_hi - r_lo;
+      }
+      g->hi0_rows = hi_rows;
+    }
+    off += 3 * (int64_t)hi_rows * g->w[j];
+    off += off & 1;
+    if (off > (1 << 28)) return false;
+  }
+  g->total = (int)off;
+  return true;
+}
+
+template <typename T> struct PairOf;
+template <> struct PairOf<double> { using type = double2; };
+template <> struct PairOf<float> { using type = float2; };
+
+// strip length that covers rows x cols outputs with the fewest (rounds x input rows per strip)
+// (the accumulators of a strip live in registers: 4 R values, at 64 registers per thread)
+template <typename T, int LT>
+struct StripMax {
+  static constexpr int value = sizeof(T) == 8 ? (LT <= 4 ? 2 : 1) : (LT <= 4 ? 4 : 2);
+};
+
+template <typename T, int LT>
+__device__ __forceinline__ int pick_strip(int rows, int cols, int nthr, bool analysis) {
+  constexpr int kMaxR = StripMax<T, LT>::value;
+  int best = 1, best_cost = 1 << 30;
+#pragma unroll
+  for (int r = 1; r <= kMaxR; ++r) {
+    const int items = ((rows + r - 1) / r) * cols;
+    const int rounds = (items + nthr - 1) / nthr;
+    const int cost = rounds * (analysis ? 2 * r + LT - 2 : r + LT / 2 - 1 + r);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = r;
+    }
+  }
+  return best;
+}
+
+// R stacked outputs (ky0 .. ky0+R-1, kx) of an analysis level whose input is a padded shared-memory plane: output
+// (ky, kx) reads padded rows 2ky .. 2ky+LT-1, padded columns 2kx .. 2kx+LT-1. acc[o] = {ll, lh, hl, hh}.
+template <typename T, int LT, int R>
+__device__ __forceinline__ void analysis_strip_smem(const T* __restrict__ src, int pitch, int last_row, int ky0, int kx,
+                                                    const Filters<T>& f, T (&acc)[R][4]) {
+  using P = typename PairOf<T>::type;
+#pragma unroll
+  for (int o = 0; o < R; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0;
+  const T* col = src + 2 * kx;
+#pragma unroll
+  for (int r = 0; r < 2 * R + LT - 2; ++r) {
+    const int pr = min(2 * ky0 + r, last_row);  // rows past the plane belong to outputs the caller drops
+    const T* p = col + pr * pitch;
+    T lo = 0, hi = 0;
+#pragma unroll
+    for (int jx = 0; jx < LT; jx += 2) {
+      const P v = *reinterpret_cast<const P*>(p + jx);
+      lo = fma(f.a_lo[jx], (T)v.x, lo);
+      hi = fma(f.a_hi[jx], (T)v.x, hi);
+      lo = fma(f.a_lo[jx + 1], (T)v.y, lo);
+      hi = fma(f.a_hi[jx + 1], (T)v.y, hi);
+    }
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+      const int jy = r - 2 * o;
+      if (jy >= 0 && jy < LT) {
+        acc[o][0] = fma(f.a_lo[jy], lo, acc[o][0]);
+        acc[o][1] = fma(f.a_hi[jy], lo, acc[o][1]);  // high along H, low along W
+        acc[o][2] = fma(f.a_lo[jy], hi, acc[o][2]);  // low along H, high along W
+        acc[o][3] = fma(f.a_hi[jy], hi, acc[o][3]);
+      }
+    }
+  }
+}
+
+// The same for level 1, whose input is value = a - b in global memory (fp32): the LT column offsets of the
+// window are resolved once per strip (ox[jx] < 0: zero padding), the row once per input row.
+template <typename T, int LT, int R>
+__device__ __forceinline__ void analysis_strip_global(const float* __restrict__ pa, const float* __restrict__ pb, int H,
+                                                      int W, int y_first, const int (&ox)[LT], int mode,
+                                                      const Filters<T>& f, T (&acc)[R][4]) {
+#pragma unroll
+  for (int o = 0; o < R; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0;
+#pragma unroll
+  for (int r = 0; r < 2 * R + LT - 2; ++r) {
+    const int sy = extend_index(min(y_first + r, 2 * H), H, mode);
+    const int base = max(sy, 0) * W;
+    T lo = 0, hi = 0;
+#pragma unroll
+    for (int jx = 0; jx < LT; ++jx) {
+      const int o = base + max(ox[jx], 0);
+      T v = (T)pa[o];
+      if (pb != nullptr) v -= (T)pb[o];
+      if ((sy | ox[jx]) < 0) v = 0;
+      lo = fma(f.a_lo[jx], v, lo);
+      hi = fma(f.a_hi[jx], v, hi);
+    }
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+      const int jy = r - 2 * o;
+      if (jy >= 0 && jy < LT) {
+        acc[o][0] = fma(f.a_lo[jy], lo, acc[o][0]);
+        acc[o][1] = fma(f.a_hi[jy], lo, acc[o][1]);
+        acc[o][2] = fma(f.a_lo[jy], hi, acc[o][2]);
+        acc[o][3] = fma(f.a_hi[jy], hi, acc[o][3]);
+      }
+    }
+  }
+}
+
+// R stacked 2x2 output quads (qy0 .. qy0+R-1, qx) of a synthesis level: quad q reads coefficient rows q .. q+LT/2-1,
+// columns qx .. qx+LT/2-1 (always in range, see dwt2_synthesis_kernel); the row combination along W is shared by the
+// quads that contain the row. Coefficients arrive already scaled. out[o] = {o00, o01, o10, o11}.
+template <typename T, int LT, int R>
+__device__ __forceinline__ void synthesis_strip(const T* __restrict__ pll, int ll_pitch, const T* __restrict__ phi,
+                                                int band_stride, int hi_pitch, int last_row, int qy0, int qx,
+                                                const Filters<T>& f, T (&out)[R][4]) {
+  constexpr int half = LT / 2;
+#pragma unroll
+  for (int o = 0; o < R; ++o) out[o][0] = out[o][1] = out[o][2] = out[o][3] = 0;
+#pragma unroll
+  for (int rr = 0; rr < R + half - 1; ++rr) {
+    const int ky = min(qy0 + rr, last_row);
+    const T* rll = pll + ky * ll_pitch + qx;
+    const T* rhi = phi + ky * hi_pitch + qx;
+    T rl0 = 0, rl1 = 0, rh0 = 0, rh1 = 0;
+#pragma unroll
+    for (int ib = 0; ib < half; ++ib) {
+      const int tx = LT - 2 - 2 * ib;
+      const T v_ll = rll[ib], v_lh = rhi[ib], v_hl = rhi[band_stride + ib], v_hh = rhi[2 * band_stride + ib];
+      rl0 = fma(f.s_lo[tx], v_ll, rl0);
+      rl0 = fma(f.s_hi[tx], v_hl, rl0);
+      rl1 = fma(f.s_lo[tx + 1], v_ll, rl1);
+      rl1 = fma(f.s_hi[tx + 1], v_hl, rl1);
+      rh0 = fma(f.s_lo[tx], v_lh, rh0);
+      rh0 = fma(f.s_hi[tx], v_hh, rh0);
+      rh1 = fma(f.s_lo[tx + 1], v_lh, rh1);
+      rh1 = fma(f.s_hi[tx + 1], v_hh, rh1);
+    }
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+      const int ia = rr - o;
+      if (ia >= 0 && ia < half) {
+        const int ty = LT - 2 - 2 * ia;
+        out[o][0] = fma(f.s_lo[ty], rl0, out[o][0]);
+        out[o][0] = fma(f.s_hi[ty], rh0, out[o][0]);
+        out[o][1] = fma(f.s_lo[ty], rl1, out[o][1]);
+        out[o][1] = fma(f.s_hi[ty], rh1, out[o][1]);
+        out[o][2] = fma(f.s_lo[ty + 1], rl0, out[o][2]);
+        out[o][2] = fma(f.s_hi[ty + 1], rh0, out[o][2]);
+        out[o][3] = fma(f.s_lo[ty + 1], rl1, out[o][3]);
+        out[o][3] = fma(f.s_hi[ty + 1], rh1, out[o][3]);
+      }
+    }
+  }
+}
+
+template <typename T>
+struct WcfgStripCtx {
+  T* sm;
+  T* peer_ll0;     // PAIR: the partner CTA's LL[0]
+  int own_lo, own_hi;  // PAIR: level-1 approximation rows this CTA publishes
+};
+
+// One analysis level over output rows [ra, rb): strips of R rows. j == 0 reads the fp32 inputs.
+template <typename T, int LT, int R, bool PAIR>
+__device__ __forceinline__ void wcfg_analysis_level(const WcfgStripGeom& g, int j, const float* pa, const float* pb, int H,
+                                                    int W, int mode, int ra, int rb, const WcfgStripCtx<T>& c, T s_ll,
+                                                    T s_lh, T s_hl, T s_hh, const Filters<T>& f) {
+  const int h = g.h[j], w = g.w[j], J = g.levels;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  // where ll_j goes: the padded input plane of level j+1 (interior at (pad_t, pad_l) of that level), or the plain
+  // coarsest plane
+  const bool last = j == J - 1;
+  const int dst_pitch = g.ll_pitch[j];
+  const int dst_org = last ? 0 : g.pad_t[j + 1] * dst_pitch + g.pad_l[j + 1];
+  T* ll = c.sm + g.ll_off[j] + dst_org;
+  T* hi = c.sm + g.hi_off[j] - ra * w;  // biased: row ky of the CTA's band lives at (ky - ra)
+  const int hw = (j == 0 ? g.hi0_rows : h) * w;
+  const int strips = (rb - ra + R - 1) / R;
+  const int items = strips * w;
+  for (int i = tid; i < items; i += nthr) {
+    const int s = i / w, kx = i - s * w;
+    const int ky0 = ra + s * R;
+    T acc[R][4];
+    if (j == 0) {
+      int ox[LT];
+#pragma unroll
+      for (int jx = 0; jx < LT; ++jx) ox[jx] = extend_index(2 * kx - g.pad_l[0] + jx, W, mode);
+      analysis_strip_global<T, LT, R>(pa, pb, H, W, 2 * ky0 - g.pad_t[0], ox, mode, f, acc);
+    } else {
+      analysis_strip_smem<T, LT, R>(c.sm + g.ll_off[j - 1], g.ll_pitch[j - 1], g.ll_rows[j - 1] - 1, ky0, kx, f, acc);
+    }
+#pragma unroll
+    for (int o = 0; o < R; ++o) {
+      const int ky = ky0 + o;
+      if (ky >= rb) break;
+      const T v_ll = last ? acc[o][0] * s_ll : acc[o][0];
+      const int at = ky * dst_pitch + kx;
+      if (!PAIR || j > 0) {
+        ll[at] = v_ll;
+      } else if (ky >= c.own_lo && ky < c.own_hi) {
+        ll[at] = v_ll;
+        c.peer_ll0[dst_org + at] = v_ll;
+      }
+      const int idx = ky * w + kx;
+      hi[idx] = acc[o][1] * s_lh;
+      hi[hw + idx] = acc[o][2] * s_hl;
+      hi[2 * hw + idx] = acc[o][3] * s_hh;
+    }
+  }
+}
+
+// Boundary extension of LL[j] (the input plane of level j+1): every cell outside the interior copies the interior
+// cell the extension mode maps it to (or zero).
+template <typename T>
+__device__ __forceinline__ void wcfg_fill_halo(const WcfgStripGeom& g, int j, int mode, T* sm) {
+  const int rows = g.ll_rows[j], pitch = g.ll_pitch[j], h = g.h[j], w = g.w[j];
+  const int pt = g.pad_t[j + 1], pl = g.pad_l[j + 1];
+  T* ll = sm + g.ll_off[j];
+  // ring enumerated densely: full rows above / below the interior, then the side columns of the interior rows
+  const int top = pt * pitch, bottom = max(0, rows - pt - h) * pitch;
+  const int side = pitch - w;
+  const int ring = top + bottom + h * side;
+  for (int b = threadIdx.x; b < ring; b += blockDim.x) {
+    int pr, pc;
+    if (b < top) {
+      pr = b / pitch;
+      pc = b - pr * pitch;
+    } else if (b < top + bottom) {
+      const int r = (b - top) / pitch;
+      pr = pt + h + r;
+      pc = (b - top) - r * pitch;
+    } else {
+      const int r = (b - top - bottom) / side, cc = (b - top - bottom) - r * side;
+      pr = pt + r;
+      pc = cc < pl ? cc : w + cc;
+    }
+    const int sy = extend_index(pr - pt, h, mode), sx = extend_index(pc - pl, w, mode);
+    ll[pr * pitch + pc] = (sy | sx) < 0 ? (T)0 : ll[(sy + pt) * pitch + (sx + pl)];
+  }
+}
+
+template <typename T, int LT, int R, bool FINAL>
+__device__ __forceinline__ void wcfg_synthesis_level(const WcfgStripGeom& g, int j, int qy_first, int qy_end, int qw,
+                                                     const T* sm_ll, int ll_pitch, T* rec, int rec_pitch, float* out,
+                                                     const float* addend, float addend_scale, const float* x, float x_scale,
+                                                     float recon_sign, int64_t plane, int H, int W, bool vec2_ok, int hi_bias,
+                                                     T* sm, const Filters<T>& f) {
+  using P = typename PairOf<T>::type;
+  const int h = g.h[j], w = g.w[j];
+  const T* hi = sm + g.hi_off[j] - hi_bias * w;
+  const int band = (j == 0 ? g.hi0_rows : h) * w;
+  const int strips = (qy_end - qy_first + R - 1) / R;
+  const int items = strips * qw;
+  const int oh = H, ow = W;  // FINAL only
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int s = i / qw, qx = i - s * qw;
+    const int qy0 = qy_first + s * R;
+    T o[R][4];
+    synthesis_strip<T, LT, R>(sm_ll, ll_pitch, hi, band, w, h - 1, qy0, qx, f, o);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int qy = qy0 + k;
+      if (qy >= qy_end) break;
+      if (!FINAL) {
+        T* r0 = rec + (2 * qy) * rec_pitch + 2 * qx;
+        P a, b;
+        a.x = o[k][0]; a.y = o[k][1]; b.x = o[k][2]; b.y = o[k][3];
+        *reinterpret_cast<P*>(r0) = a;
+        *reinterpret_cast<P*>(r0 + rec_pitch) = b;
+        continue;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int iy = 2 * qy + r;
+        if (iy >= oh) continue;
+        const int64_t at = (plane * H + iy) * (int64_t)W + 2 * qx;
+        T r0 = o[k][2 * r], r1 = o[k][2 * r + 1];
+        if (vec2_ok) {
+          if (addend != nullptr) {
+            const float2 ad = *reinterpret_cast<const float2*>(addend + at);
+            r0 += (T)addend_scale * (T)ad.x;
+            r1 += (T)addend_scale * (T)ad.y;
+          }
+          // the reference casts the reconstruction to the latent dtype first, then forms x - result (py/wavelet_cfg.py:729-747)
+          float2 res = make_float2((float)((T)recon_sign * r0), (float)((T)recon_sign * r1));
+          if (x != nullptr) {
+            const float2 xv = *reinterpret_cast<const float2*>(x + at);
+            res.x = x_scale * xv.x + res.x;
+            res.y = x_scale * xv.y + res.y;
+          }
+          *reinterpret_cast<float2*>(out + at) = res;
+        } else {
+          const T vals[2] = {r0, r1};
+#pragma unroll
+          for (int cx = 0; cx < 2; ++cx) {
+            if (2 * qx + cx >= ow) continue;
+            T v = vals[cx];
+            if (addend != nullptr) v += (T)addend_scale * (T)addend[at + cx];
+            float rf = (float)((T)recon_sign * v);
+            if (x != nullptr) rf = x_scale * x[at + cx] + rf;
+            out[at + cx] = rf;
+          }
+        }
+      }
+    }
+  }
+}
+
+#define SONAR_STRIP_DISPATCH(R_, CALL)          \
+  switch (R_) {                                 \
+    case 1: { constexpr int R = 1; CALL; } break; \
+    case 2: { constexpr int R = StripMax<T, LT>::value < 2 ? 1 : 2; CALL; } break; \
+    case 3: { constexpr int R = StripMax<T, LT>::value < 3 ? StripMax<T, LT>::value : 3; CALL; } break; \
+    default: { constexpr int R = StripMax<T, LT>::value; CALL; } break; \
+  }
+
+template <typename T, int LT, bool PAIR>
+__global__ void __launch_bounds__(kWcfgThreads, 1)
+wcfg_strip_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b, float* __restrict__ out,
+                  const float* __restrict__ addend, float addend_scale, const float* __restrict__ x, float x_scale,
+                  float recon_sign, int64_t planes, int H, int W, int mode, WcfgStripGeom g, T scale_ll, WcfgScales<T> scales,
+                  Filters<T> f) {
+  extern __shared__ __align__(16) unsigned char wcfg_smem[];
+  T* sm = reinterpret_cast<T*>(wcfg_smem);
+  const int J = g.levels, nthr = blockDim.x;
+  const bool vec2_ok = (W & 1) == 0 && (((uintptr_t)out | (uintptr_t)addend | (uintptr_t)x) & 7u) == 0;
+  int q_lo = 0, q_hi = (H + 1) >> 1, r_lo = 0, r_hi = g.h[0];
+  WcfgStripCtx<T> c{sm, nullptr, 0, g.h[0]};
+  if (PAIR) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    wcfg_pair_rows(H, g.h[0], LT, rank, &q_lo, &q_hi, &r_lo, &r_hi);
+    int a, b, cc, split;
+    wcfg_pair_rows(H, g.h[0], LT, 0, &a, &b, &cc, &split);  // rank 0 publishes approximation rows [0, split), rank 1 the rest
+    c.own_lo = rank ? split : 0;
+    c.own_hi = rank ? g.h[0] : split;
+    c.peer_ll0 = cluster.map_shared_rank(sm, rank ^ 1) + g.ll_off[0];
+  }
+  const int64_t plane_first = PAIR ? blockIdx.x >> 1 : blockIdx.x, plane_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+  for (int64_t plane = plane_first; plane < planes; plane += plane_step) {
+    const float* pa = in_a + plane * (int64_t)H * W;
+    const float* pb = in_b != nullptr ? in_b + plane * (int64_t)H * W : nullptr;
+    // ---------------- analysis, fine -> coarse ----------------
+    for (int j = 0; j < J; ++j) {
+      const int ra = j == 0 ? r_lo : 0, rb = j == 0 ? r_hi : g.h[j];
+      const T s_ll = j == J - 1 ? scale_ll : (T)1;
+      const T s_lh = scales.v[3 * j], s_hl = scales.v[3 * j + 1], s_hh = scales.v[3 * j + 2];
+      const int strip = pick_strip<T, LT>(rb - ra, g.w[j], nthr, true);
+      SONAR_STRIP_DISPATCH(strip, (wcfg_analysis_level<T, LT, R, PAIR>(g, j, pa, pb, H, W, mode, ra, rb, c, s_ll, s_lh, s_hl, s_hh, f)))
+      if (PAIR && j == 0)
+        cg::this_cluster().sync();  // both parts of the level-1 approximation have landed in both CTAs
+      else
+        __syncthreads();
+      if (j + 1 < J) {
+        wcfg_fill_halo<T>(g, j, mode, sm);
+        __syncthreads();
+      }
+    }
+    // ---------------- synthesis, coarse -> fine ----------------
+    for (int j = J - 1; j >= 0; --j) {
+      const int h = g.h[j], w = g.w[j];
+      const int out_h = 2 * h - LT + 2, out_w = 2 * w - LT + 2;
+      const int oh = j == 0 ? H : out_h, ow = j == 0 ? W : out_w;  // the final level is cropped to the input size
+      const int qh = (oh + 1) >> 1, qw = (ow + 1) >> 1;
+      const int qy_first = j == 0 ? q_lo : 0, qy_end = j == 0 ? min(q_hi, qh) : qh;
+      const T* ll = sm + g.ll_off[j];  // the coarsest approximation, or rec_{j+1} stored at the origin of LL[j]
+      const int strip = pick_strip<T, LT>(qy_end - qy_first, qw, nthr, false);
+      if (j == 0) {
+        SONAR_STRIP_DISPATCH(strip, (wcfg_synthesis_level<T, LT, R, true>(g, j, qy_first, qy_end, qw, ll, g.ll_pitch[0], nullptr, 0, out, addend, addend_scale, x, x_scale, recon_sign, plane, H, W, vec2_ok, r_lo, sm, f)))
+      } else {
+        SONAR_STRIP_DISPATCH(strip, (wcfg_synthesis_level<T, LT, R, false>(g, j, qy_first, qy_end, qw, ll, g.ll_pitch[j], sm + g.ll_off[j - 1], g.ll_pitch[j - 1], nullptr, nullptr, 0.f, nullptr, 0.f, 0.f, plane, H, W, false, 0, sm, f)))
+      }
+      __syncthreads();
+    }
+    // the partner stores the next plane's level-1 approximation into this CTA's LL[0], which held rec_1 until now
+    if (PAIR) cg::this_cluster().sync();
+  }
+}
+
 template <typename T>
 Filters<T> make_filters(const SonarWaveletFilters* wf) {
   Filters<T> f;
@@ -789,6 +1230,41 @@ int launch_wcfg_fused(const SonarWcfgFusedParams& p, const WcfgGeom& g, cudaStre
     cfg.gridDim = dim3((unsigned)(p.planes < di.sm_count ? p.planes : di.sm_count));
   }
   const T scale_ll = (T)p.scale_ll;
+  // compile-time filter lengths whose padded planes fit: the strip kernel (SONAR_B200_WCFG_STRIP=0: the first version)
+  WcfgStripGeom sg;
+  static const bool strip_enabled = [] {
+    const char* e = getenv("SONAR_B200_WCFG_STRIP");
+    return e == nullptr || e[0] != '0';
+  }();
+  const int L = p.filters.length;
+  if (strip_enabled && (L == 2 || L == 4 || L == 6 || L == 8) && wcfg_strip_geometry(p.H, p.W, L, p.levels, &sg, g.pair != 0) &&
+      (size_t)sg.total * sizeof(T) <= (size_t)di.max_smem_optin) {
+    cfg.dynamicSmemBytes = (size_t)sg.total * sizeof(T);
+#define WCFG_STRIP_KERNEL(LT, PAIR)                                                                                       \
+  do {                                                                                                                   \
+    SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_strip_kernel<T, LT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                        (int)cfg.dynamicSmemBytes));                                                      \
+    SONAR_CUDA_TRY(cudaLaunchKernelEx(&cfg, wcfg_strip_kernel<T, LT, PAIR>, p.in_a, p.in_b, p.out, p.addend, p.addend_scale, \
+                                      p.x, p.x_scale, p.recon_sign, p.planes, p.H, p.W, p.mode, sg, scale_ll, sc, f));     \
+  } while (0)
+#define WCFG_STRIP(LT)                 \
+  do {                                 \
+    if (g.pair)                        \
+      WCFG_STRIP_KERNEL(LT, true);     \
+    else                               \
+      WCFG_STRIP_KERNEL(LT, false);    \
+  } while (0)
+    switch (L) {
+      case 2: WCFG_STRIP(2); break;
+      case 4: WCFG_STRIP(4); break;
+      case 6: WCFG_STRIP(6); break;
+      default: WCFG_STRIP(8); break;
+    }
+#undef WCFG_STRIP
+#undef WCFG_STRIP_KERNEL
+    SONAR_LAUNCH_CHECK();
+    return 0;
+  }
 #define WCFG_FUSED_KERNEL(LT, PAIR)                                                                                      \
   do {                                                                                                                   \
     SONAR_CUDA_TRY(cudaFuncSetAttribute(wcfg_fused_kernel<T, LT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

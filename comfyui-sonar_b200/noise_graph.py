@@ -638,9 +638,11 @@ class CustomNoiseParametersNoise(_ChildHolder):
             and x.device == orig_device
         ):
             # a pure reshape around the child: its look-ahead batches pass through as views of the original shape
-            def lookahead(count: int):
-                batch = child_lookahead(count)
-                return None if batch is None else [(raw.reshape(orig_shape), sums, draw) for raw, sums, draw in batch]
+            def lookahead(count: int, **kw):
+                batch = child_lookahead(count, **kw)
+                if batch is None:
+                    return None
+                return type(batch)(((raw.reshape(orig_shape), sums, draw) for raw, sums, draw in batch), batch.table)
 
             noise_sampler.lookahead = lookahead
         return noise_sampler

@@ -45,6 +45,17 @@ def _launch(name: str, fn, *args, launches: int = 1) -> None:
 
 
 _LAST_DEVICE: int | None = None
+_GRID_LIMIT = 0
+
+
+def set_grid_limit(ctas_per_sm: int) -> None:
+    """Co-scheduling hint for the next launches of this thread (sonar_set_grid_limit): at most `ctas_per_sm` CTAs per SM
+    for the grid-stride streaming kernels and the batched FFT, 0 = default grids."""
+    global _GRID_LIMIT  # noqa: PLW0603
+    if ctas_per_sm != _GRID_LIMIT:
+        _native.load().sonar_set_grid_limit(int(ctas_per_sm))
+        _GRID_LIMIT = ctas_per_sm
+
 
 
 def _prepare(*tensors: torch.Tensor | None) -> tuple[ctypes.CDLL, ctypes.c_void_p]:
@@ -741,6 +752,7 @@ def spectral_filter(
     out: torch.Tensor | None = None,
     sums_into: tuple | None = None,
     segment_planes: int | None = None,
+    table: torch.Tensor | None = None,
 ):
     """[rfft2 ->] mask -> irfft2 per (H, W) plane. Exactly one of real / spectrum / philox is given.
 
@@ -750,7 +762,7 @@ def spectral_filter(
     out: optional preallocated result. sums_into = (slot pointer, clear pointer or 0): accumulate the moments into a
     slot the caller manages instead of taking one from the ring (the result is then not tagged).
     segment_planes: the planes form runs of this many planes (one noise sample each); returns (out, table) with
-    table (n_segments, 2) float64 = {sum, sum of squares} of each run.
+    table (n_segments, 2) float64 = {sum, sum of squares} of each run (`table`: a zeroed buffer of the caller's).
     """
     H, W = hw
     wh = W // 2 + 1
@@ -799,7 +811,10 @@ def spectral_filter(
     if segment_planes is not None:
         if planes % segment_planes:
             raise ValueError("segment_planes must divide the plane count")
-        table = torch.zeros((planes // segment_planes, 2), device=device, dtype=torch.float64)
+        if table is None:
+            table = torch.zeros((planes // segment_planes, 2), device=device, dtype=torch.float64)
+        elif table.dtype != torch.float64 or tuple(table.shape) != (planes // segment_planes, 2) or not table.is_contiguous():
+            raise ValueError("table must be a contiguous float64 (n_segments, 2) tensor")
         p.sums, p.sums_clear, p.sums_segment_planes = table.data_ptr(), 0, int(segment_planes)
         _launch("sonar_spectral_filter_f32", lib.sonar_spectral_filter_f32, ctypes.byref(p), stream)
         drop_sums(out)

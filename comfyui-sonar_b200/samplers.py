@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes
 import importlib
+import os
 import weakref
 from enum import Enum, auto
 from sys import stderr
@@ -33,6 +34,25 @@ from tqdm.auto import trange
 
 from . import hostutil, noise_graph as noise, ops, parallel, rng
 from ._native import SonarStepParams
+
+
+# Pipelined production of look-ahead noise (SonarBase._lookahead_noise). SONAR_B200_NOISE_PIPELINE=0 restores the
+# batched schedule; the *_CTAS knobs are the CTAs per SM each side may occupy while both run.
+NOISE_PIPELINE = os.environ.get("SONAR_B200_NOISE_PIPELINE", "1") != "0"
+NOISE_PIPELINE_CHUNK = int(os.environ.get("SONAR_B200_PIPELINE_CHUNK", "1"))
+PIPELINE_STEP_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_CTAS", "3"))
+PIPELINE_FILL_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FILL_CTAS", "5"))
+PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "2"))
+_PRODUCER_STREAMS: dict = {}
+
+
+def _producer_stream(device_index: int) -> "torch.cuda.Stream":
+    """The second stream of a device, on which look-ahead noise is produced (high priority: its CTAs take the slots
+    that free up first)."""
+    st = _PRODUCER_STREAMS.get(device_index)
+    if st is None:
+        st = _PRODUCER_STREAMS[device_index] = torch.cuda.Stream(device=device_index, priority=-1)
+    return st
 
 
 class HistoryType(Enum):
@@ -325,7 +345,19 @@ class SonarBase:
             p.noise_kind, p.noise, p.peer_world, keep = ops.NOISE_TENSOR, noise_tensor.data_ptr(), 0, noise_tensor
         else:
             p.noise_kind = ops.NOISE_NONE
-        ops.launch_step(self._params_ref, x.device.index)
+        join = getattr(self, "_noise_join", None)
+        if join is None:
+            ops.launch_step(self._params_ref, x.device.index)
+        else:
+            # a producer is running on the second stream: leave it thread slots on every SM, then make everything
+            # enqueued after this half step wait for it (the next model call starts with the next sample ready)
+            self._noise_join = None
+            ops.set_grid_limit(PIPELINE_STEP_CTAS)
+            try:
+                ops.launch_step(self._params_ref, x.device.index)
+            finally:
+                ops.set_grid_limit(0)
+            torch.cuda.current_stream().wait_event(join)
         del keep
         if hist_out is not None:
             self.history_d = hist_out
@@ -524,11 +556,19 @@ class SonarBase:
         return {"noise_philox": kw, "noise_scale": scale}
 
     def _lookahead_noise(self, x: Tensor):
-        """Custom noise whose samples depend on the generator state only (power noise): the samples of the next few
-        draws are made together, one Philox launch + one FFT launch + one statistics exchange for the whole batch,
-        and handed out one per request. Every hand-out checks that torch's generator is where the batch assumed it
-        would be (nobody else drew in between) and advances it exactly as the draw itself would have; otherwise the
-        rest of the batch is dropped and made again from the current state. Returns the `noise_deferred` tuple."""
+        """Custom noise whose samples depend on the generator state only (power noise): samples are made ahead of the
+        request and handed out one per request. Every hand-out checks that torch's generator is where the producer
+        assumed it would be (nobody else drew in between) and advances it exactly as the draw itself would have;
+        otherwise what was made ahead is dropped and made again from the current state. Returns the `noise_deferred`
+        tuple.
+
+        Two schedules. Batched (NOISE_PIPELINE off): the samples of the next few draws in one Philox launch + one FFT
+        launch + one statistics exchange. Pipelined (default): the producers are instruction-issue-bound (~70 % of
+        the issue slots, a third of the HBM bandwidth) and the fused step is HBM-bound (~20 % of the issue slots), so the
+        NEXT sample is produced on a second stream while the step kernel that consumes THIS one runs: both kernels
+        are launched with grids that leave each other thread slots on every SM (sonar_set_grid_limit) and the main
+        stream joins the producer stream right after the step launch, so everything still happens between the
+        two model calls that bracket the half step."""
         ns = self.noise_sampler
         make = getattr(ns, "lookahead", None)
         if make is None or self.noise_draws_left < 1:
@@ -539,19 +579,56 @@ class SonarBase:
         idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
         gen = torch.cuda.default_generators[idx]
         queue = getattr(self, "_noise_queue", None)
+        pending = getattr(self, "_noise_pending", None)
+        if not queue and pending is not None:
+            batch, ready = pending
+            self._noise_pending = None
+            torch.cuda.current_stream().wait_event(ready)  # (already joined after the previous step launch)
+            queue = self._noise_queue = batch
         if queue and (queue[0][2].offset != gen.get_offset() or queue[0][2].seed != gen.initial_seed() or queue[0][0].shape != x.shape):
             queue.clear()
         if not queue:
-            batch = make(self.noise_draws_left)
-            if batch is None:
-                return None
-            table = batch[0][1]._base if batch[0][1]._base is not None else batch[0][1]  # noqa: SLF001
-            parallel.allreduce_table(table)  # sharded: ONE exchange for the statistics of the whole batch
-            queue = self._noise_queue = list(batch)
+            if NOISE_PIPELINE:
+                made = self._produce_noise(make, x, overlapped=False)
+                if made is None:
+                    return None
+                batch, ready = made
+                torch.cuda.current_stream().wait_event(ready)
+            else:
+                batch = make(self.noise_draws_left)
+                if batch is None:
+                    return None
+                parallel.allreduce_table(batch.table)  # sharded: ONE exchange for the statistics of the whole batch
+            queue = self._noise_queue = batch
         raw, sums, draw = queue.pop(0)
         gen.set_offset(draw.offset + draw.counter_offset)
         self.noise_draws_left -= 1
+        if NOISE_PIPELINE and not queue and self.noise_draws_left >= 1:
+            # speculative: the next request normally finds the generator exactly here
+            self._noise_pending = self._produce_noise(make, x, overlapped=True)
         return (raw, sums, parallel.global_numel(raw.numel()), factor)
+
+    def _produce_noise(self, make, x: Tensor, *, overlapped: bool):
+        """Enqueues the production of the next NOISE_PIPELINE_CHUNK samples on the producer stream: (batch, event).
+        overlapped: the consumer launches its step kernel next, to run beside the producers (`_noise_join`)."""
+        idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        side = _producer_stream(idx)
+        main = torch.cuda.current_stream()
+        slot = getattr(self, "_noise_slot", 0)
+        # the buffer about to be overwritten was last read by a step kernel already enqueued on the consumer stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            batch = make(self.noise_draws_left, chunk=NOISE_PIPELINE_CHUNK, slot=slot,
+                         grid_limits=(PIPELINE_FILL_CTAS, PIPELINE_FFT_CTAS) if overlapped else None)
+            if batch is None:
+                return None
+            parallel.allreduce_table(batch.table)  # sharded: the statistics of the chunk, on the producer stream
+            ready = torch.cuda.Event()
+            ready.record(side)
+        self._noise_slot = slot ^ 1
+        if overlapped:
+            self._noise_join = ready
+        return batch, ready
 
     def _fused_noise_spec(self, x: Tensor):
         """(factor, normalized) when the noise sampler is plain Gaussian noise of x's shape that the

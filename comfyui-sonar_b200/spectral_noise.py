@@ -299,41 +299,63 @@ class PowerNoiseItem(CustomNoiseItemBase):
 
             state: dict = {}  # the sampler's look-ahead slab (see below)
 
-            def lookahead(count: int):
+            def lookahead(count: int, *, chunk: int | None = None, slot: int | None = None, grid_limits: tuple | None = None):
                 """The next `count` samples in ONE Philox launch + ONE FFT launch (per-sample statistics): a sample is a
                 function of the generator state only, so a consumer that knows it will ask again (a sampler with
                 `noise_draws_left`) can have them made together -- small launches run at a fraction of the throughput of
                 large ones (528 planes of 90x160: 36 us, 4224 planes: 22 us per 528). Returns [(raw sample, its {sum,
                 sum^2} row, draw)], or None when not applicable. The torch generator is NOT advanced: the consumer
-                advances it draw by draw (and drops the rest if somebody else drew in between)."""
+                advances it draw by draw (and drops the rest if somebody else drew in between).
+                chunk / slot (pipelined consumers, samplers._prefetch_noise): make exactly min(count, chunk) samples into
+                output buffer `slot` (0 / 1) of the slab, so that the consumer can read one buffer on its stream while
+                the next samples are written into the other one on a second stream. grid_limits = (fill, fft): CTAs per
+                SM the two producer launches may occupy (sonar_set_grid_limit; 0 = no limit)."""
                 if rng._INJECT is not None or rng._PENDING is not None:  # noqa: SLF001
                     return None
                 numel = math.prod(shape)
-                cap = min(ops.FILL_BATCH_MAX, max(1, LOOKAHEAD_BYTES // (12 * numel)))
-                count = -(-count // -(-count // cap))  # equal batches: 18 draws under a cap of 11 are made 9 + 9
-                if count < 2:
-                    return None
+                if chunk is None:
+                    cap = min(ops.FILL_BATCH_MAX, max(1, LOOKAHEAD_BYTES // (12 * numel)))
+                    count = -(-count // -(-count // cap))  # equal batches: 18 draws under a cap of 11 are made 9 + 9
+                    if count < 2:
+                        return None
+                    room = count
+                else:
+                    room = max(1, min(chunk, ops.FILL_BATCH_MAX))  # the slab is laid out for full chunks
+                    count = max(1, min(count, room))
                 total, begin = parallel.global_draw_geometry(spec_shape)
                 draws = ops.peek_draws(2 * total, device, count)
-                # One slab per sampler for spectrum + samples, taken from (and returned to) a pool of our own: a batch is
-                # made only when the previous one has been consumed by kernels already enqueued on this stream, so the
-                # slab is simply overwritten. Going through torch's caching allocator for ~1 GB blocks nine times per
+                # One slab per sampler for spectrum + samples + their statistics, taken from (and returned to) a pool of
+                # our own: a batch is made only when the previous one has been consumed by kernels already enqueued, so
+                # the slab is simply overwritten. Going through torch's caching allocator for ~1 GB blocks nine times per
                 # run fragments it (smaller tensors get carved out of the freed slab) and ends in cudaMalloc / cudaFree
                 # stalls of 20-180 ms inside a sampler step.
-                spec_bytes = 8 * count * math.prod(spec_shape)
-                need = spec_bytes + 4 * count * numel
+                spec_bytes = 8 * room * math.prod(spec_shape)
+                out_bytes = 4 * room * numel
+                tab_bytes = -(-16 * room // 256) * 256
+                n_slots = 1 if slot is None else 2
+                need = spec_bytes + n_slots * (out_bytes + tab_bytes)
                 slab = state.get("slab")
-                if slab is None or slab.tensor.numel() < need:
+                if slab is None or slab.tensor.numel() < need or state.get("layout") != (room, n_slots):
                     slab = state["slab"] = _Slab.acquire(device, need)
-                spec = slab.tensor[:spec_bytes].view(torch.complex64).reshape(count, *spec_shape)
-                out = slab.tensor[spec_bytes:need].view(torch.float32).reshape(count * planes, height, width)
-                ops.philox_fill_batch([(d, spec[j], "normal", 0.0, std, 2 * begin) for j, d in enumerate(draws)])
-                out, table = ops.spectral_filter(
-                    spectrum=spec.reshape(count * planes, height, bins), mask=mask, hw=(height, width), out_scale=ortho,
-                    segment_planes=planes, out=out,
-                )
+                    state["layout"] = (room, n_slots)
+                base = spec_bytes + (slot or 0) * (out_bytes + tab_bytes)
+                spec = slab.tensor[: 8 * count * math.prod(spec_shape)].view(torch.complex64).reshape(count, *spec_shape)
+                out = slab.tensor[base : base + 4 * count * numel].view(torch.float32).reshape(count * planes, height, width)
+                table = slab.tensor[base + out_bytes : base + out_bytes + 16 * count].view(torch.float64).reshape(count, 2)
+                table.zero_()
+                fill_limit, fft_limit = grid_limits or (0, 0)
+                try:
+                    ops.set_grid_limit(fill_limit)
+                    ops.philox_fill_batch([(d, spec[j], "normal", 0.0, std, 2 * begin) for j, d in enumerate(draws)])
+                    ops.set_grid_limit(fft_limit)
+                    out, table = ops.spectral_filter(
+                        spectrum=spec.reshape(count * planes, height, bins), mask=mask, hw=(height, width), out_scale=ortho,
+                        segment_planes=planes, out=out, table=table,
+                    )
+                finally:
+                    ops.set_grid_limit(0)
                 out = out.reshape(count, *shape)
-                return [(out[j], table[j], draws[j]) for j in range(count)]
+                return NoiseBatch(((out[j], table[j], draws[j]) for j in range(count)), table)
 
             sampler.lookahead = lookahead
         return sampler
@@ -345,6 +367,15 @@ LOOKAHEAD_BYTES = int(os.environ.get("SONAR_B200_LOOKAHEAD_BYTES", 2 << 30))  # 
 # instead of the ~66 x 256 threads of the fill kernel. Measured on B200, C1 (1x4x64x64): 39 us in-kernel vs 7 + 17.5 us
 # as two launches. Kept behind this switch (and tested), off by default.
 IN_KERNEL_PHILOX = os.environ.get("SONAR_B200_SPECTRAL_PHILOX") == "1"
+
+
+class NoiseBatch(list):
+    """[(raw sample, its {sum, sum^2} row, draw)] of one look-ahead batch + the (count, 2) statistics table the rows are
+    views of (what a sharded consumer all-reduces, once per batch)."""
+
+    def __init__(self, items, table):
+        super().__init__(items)
+        self.table = table
 
 
 class _Slab:

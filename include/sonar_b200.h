@@ -23,11 +23,16 @@
 extern "C" {
 #endif
 
-#define SONAR_B200_ABI_VERSION 8
+#define SONAR_B200_ABI_VERSION 9
 int sonar_abi_version(void);
 /* Binds the calling thread of THIS library's CUDA runtime to `device` (the library links cudart
  * statically; one process per GPU normally makes this a no-op). */
 int sonar_set_device(int device);
+/* Co-scheduling hint for the calling thread's next launches: when ctas_per_sm > 0 the grid-stride streaming kernels
+ * (Philox fills, the vectorised fused step) launch at most that many CTAs per SM, so that a kernel enqueued on
+ * ANOTHER stream finds free thread slots on every SM and the two run side by side (the ALU-bound noise producers under
+ * the HBM-bound step). 0 restores the default grids. No reference counterpart: eager PyTorch runs one kernel at a time. */
+int sonar_set_grid_limit(int ctas_per_sm);
 
 /* ------------------------------------------------------------------------------------------------
  * Philox generators, bit-exact with torch.randn / torch.rand / Tensor.uniform_ on CUDA.
