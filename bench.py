@@ -447,7 +447,33 @@ def run_b200_arm(args) -> None:
     peak, peak_src = measured_peak()
     barrier()
     tracer = StepTimer(dev, timed=False, on_first_call=rendezvous)
-    roofline, kernel_table = traced_breakdown(sb, lambda: one_run(tracer, x0), n_local, peak, peak_src, reps=2)
+    # per-kernel durations are taken with the noise pipeline OFF: with it on, the producers run beside the step kernel
+    # on a second stream and an event pair around one launch also times its neighbours (ncu serialises in the same way)
+    pipelined = bool(sb.samplers.NOISE_PIPELINE and n_local >= sb.samplers.PIPELINE_MIN_NUMEL)
+    sb.samplers.NOISE_PIPELINE, keep_flag = False, sb.samplers.NOISE_PIPELINE
+    try:
+        one_run(tracer, x0)
+        roofline, kernel_table = traced_breakdown(sb, lambda: one_run(tracer, x0), n_local, peak, peak_src, reps=2)
+    finally:
+        sb.samplers.NOISE_PIPELINE = keep_flag
+    roofline["timing"] += (
+        "; this traced run has the noise pipeline switched off (kernels one after the other, as under ncu) -- in the timed "
+        "runs the producers of the next sample overlap the step kernel, see roofline_job"
+    ) if pipelined else ""
+    # the job as a whole: SURVEY 8d bytes of every half step (24 B/el) and every noise sample (4 B/el) over the timed region
+    job_bytes = (BYTES_STEP * (2 * (N_SAMPLER_STEPS - 1) + 1) + BYTES_NOISE * 2 * (N_SAMPLER_STEPS - 1)) * n_local
+    roofline_job = {
+        "bound": "hbm",
+        "algorithmic_bytes_per_run": job_bytes,
+        "achieved": job_bytes / (ms_local * 1e-3) / 1e9,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": job_bytes / (ms_local * 1e-3) / 1e9 / peak,
+        "noise_pipeline": pipelined,
+        "note": "this rank's algorithmic bytes of the whole run (19 half steps x 24 B/el + 18 noise samples x 4 B/el) / its "
+        "device time; the noise producers are instruction-bound (Philox + Box-Muller, 90x160 FFT), which is what keeps this "
+        "below the step kernel's own fraction",
+    }
     traffic_path = REPO / "profiles" / "traffic.json"
     if traffic_path.exists():
         roofline["traffic"] = json.loads(traffic_path.read_text()).get("c5:" + roofline["kernel"].split(" ")[0])
@@ -565,9 +591,12 @@ def run_b200_arm(args) -> None:
                 "l2": f"tensors of {bytes_total // world >> 20} MiB per GPU; {FLUSH_PASSES} x 256 MiB zero-fill between half steps "
                 "(stub denoiser, untimed) evicts L2",
                 "timing": "sum of the CUDA-event intervals between model calls (power-noise sample + fused half step), max over ranks",
+                "noise_pipeline": "on: the next sample is produced on a second stream beside the step kernel, joined before the "
+                "next model call" if pipelined else "off (samples per GPU below PIPELINE_MIN_NUMEL: batched look-ahead)",
                 "elements": "sampler steps x latent elements (each step = 2 noise samples + 2 fused half steps)",
             },
             "roofline": roofline,
+            "roofline_job": roofline_job,
             "kernels": kernel_table,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,

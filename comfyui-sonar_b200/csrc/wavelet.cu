@@ -706,15 +706,18 @@ struct WcfgStripGeom {
   int ll_off[SONAR_WCFG_MAX_LEVELS], hi_off[SONAR_WCFG_MAX_LEVELS];  // element offsets into shared memory
   int ll_pitch[SONAR_WCFG_MAX_LEVELS], ll_rows[SONAR_WCFG_MAX_LEVELS];  // LL[j] as the padded input of level j+1
   int pad_t[SONAR_WCFG_MAX_LEVELS], pad_l[SONAR_WCFG_MAX_LEVELS];    // pads of level j's OWN input
+  int stage_off, stage_rows, stage_pitch;  // level-1 input (a - b, extended) staged in shared memory; rows == 0: read from global
   int total;
 };
 
-static bool wcfg_strip_geometry(int H, int W, int L, int levels, WcfgStripGeom* g, bool pair) {
+static bool wcfg_strip_geometry(int H, int W, int L, int levels, WcfgStripGeom* g, bool pair, size_t elem_bytes = 0,
+                                size_t smem_limit = 0) {
   if (levels < 1 || levels > SONAR_WCFG_MAX_LEVELS || H <= 0 || W <= 0) return false;
   g->levels = levels;
   g->pair = pair ? 1 : 0;
   int hh = H, ww = W;
   for (int j = 0; j < levels; ++j) {
+    if (hh < L || ww < L) return false;  // halos are filled with ONE reflection / wrap (extend_index_near)
     const int h = (hh + L - 1) / 2, w = (ww + L - 1) / 2;
     g->h[j] = h;
     g->w[j] = w;
@@ -751,6 +754,23 @@ static bool wcfg_strip_geometry(int H, int W, int L, int levels, WcfgStripGeom* 
     off += off & 1;
     if (off > (1 << 28)) return false;
   }
+  // the level-1 input of this CTA's output rows (all of them, or the wider half of a pair), when it still fits
+  g->stage_off = (int)off;
+  g->stage_rows = 0;
+  g->stage_pitch = 2 * (g->w[0] - 1) + L;
+  int out_rows = g->h[0];
+  if (pair) {
+    int q_lo, q_hi, r_lo, r_hi;
+    wcfg_pair_rows(H, g->h[0], L, 0, &q_lo, &q_hi, &r_lo, &r_hi);
+    out_rows = r_hi - r_lo;
+    wcfg_pair_rows(H, g->h[0], L, 1, &q_lo, &q_hi, &r_lo, &r_hi);
+    if (r_hi - r_lo > out_rows) out_rows = r_hi - r_lo;
+  }
+  const int64_t stage = (int64_t)(2 * out_rows + L - 2) * g->stage_pitch;
+  if (elem_bytes > 0 && (size_t)(off + stage) * elem_bytes <= smem_limit) {
+    g->stage_rows = 2 * out_rows + L - 2;
+    off += stage;
+  }
   g->total = (int)off;
   return true;
 }
@@ -763,7 +783,7 @@ template <> struct PairOf<float> { using type = float2; };
 // (the accumulators of a strip live in registers: 4 R values, at 64 registers per thread)
 template <typename T, int LT>
 struct StripMax {
-  static constexpr int value = sizeof(T) == 8 ? (LT <= 4 ? 2 : 1) : (LT <= 4 ? 4 : 2);
+  static constexpr int value = sizeof(T) == 8 ? (LT <= 4 ? 2 : 1) : 2;
 };
 
 template <typename T, int LT>
@@ -928,7 +948,11 @@ __device__ __forceinline__ void wcfg_analysis_level(const WcfgStripGeom& g, int 
     const int s = i / w, kx = i - s * w;
     const int ky0 = ra + s * R;
     T acc[R][4];
-    if (j == 0) {
+    if (j == 0 && g.stage_rows > 0) {
+      // staged rows start at padded row 2 ra
+      analysis_strip_smem<T, LT, R>(c.sm + g.stage_off - 2 * ra * g.stage_pitch, g.stage_pitch, 2 * ra + g.stage_rows - 1, ky0,
+                                    kx, f, acc);
+    } else if (j == 0) {
       int ox[LT];
 #pragma unroll
       for (int jx = 0; jx < LT; ++jx) ox[jx] = extend_index(2 * kx - g.pad_l[0] + jx, W, mode);
@@ -956,6 +980,63 @@ __device__ __forceinline__ void wcfg_analysis_level(const WcfgStripGeom& g, int 
   }
 }
 
+// One reflection / wrap only (callers guarantee the index is less than one signal length outside [0, n), which holds
+// for every halo when the filter is not longer than the signal): no integer division anywhere.
+__device__ __forceinline__ int extend_index_near(int i, int n, int mode) {
+  if ((unsigned)i < (unsigned)n) return i;
+  if (mode == SONAR_DWT_MODE_ZERO) return -1;
+  int m;
+  if (mode == SONAR_DWT_MODE_PERIODIC)
+    m = i < 0 ? i + n : i - n;
+  else if (mode == SONAR_DWT_MODE_REFLECT)
+    m = i < 0 ? -i : 2 * (n - 1) - i;
+  else
+    m = i < 0 ? -1 - i : 2 * n - 1 - i;
+  return min(max(m, 0), n - 1);
+}
+
+// Level-1 input of output rows [ra, ...): value = a - b converted once, stored with its boundary extension as padded
+// rows 2 ra .. 2 ra + stage_rows - 1. Interior: one item = 4 consecutive pixels of a row (16-byte loads of a and b,
+// two 16-byte shared stores); the pad_l / right halo columns are a second, tiny pass over scalar loads.
+template <typename T>
+__device__ __forceinline__ void wcfg_stage_input(const WcfgStripGeom& g, const float* __restrict__ pa,
+                                                 const float* __restrict__ pb, int H, int W, int mode, int ra, T* sm) {
+  using P = typename PairOf<T>::type;
+  const int pitch = g.stage_pitch, pl = g.pad_l[0], pt = g.pad_t[0], rows = g.stage_rows;
+  T* dst = sm + g.stage_off;
+  const bool vec4 = (W & 3) == 0 && (pl & 1) == 0 && (((uintptr_t)pa | (uintptr_t)pb) & 15u) == 0;
+  const int groups = vec4 ? W >> 2 : 0;
+  for (int i = threadIdx.x; i < rows * groups; i += blockDim.x) {
+    const int r = i / groups, c4 = (i - r * groups) << 2;
+    const int sy = extend_index_near(min(2 * ra + r - pt, 2 * H - 1), H, mode);
+    P v0, v1;
+    v0.x = v0.y = v1.x = v1.y = 0;
+    if (sy >= 0) {
+      const float4 a4 = ld4(pa + sy * W + c4);
+      v0.x = (T)a4.x; v0.y = (T)a4.y; v1.x = (T)a4.z; v1.y = (T)a4.w;
+      if (pb != nullptr) {
+        const float4 b4 = ld4(pb + sy * W + c4);
+        v0.x -= (T)b4.x; v0.y -= (T)b4.y; v1.x -= (T)b4.z; v1.y -= (T)b4.w;
+      }
+    }
+    T* d = dst + r * pitch + pl + c4;
+    *reinterpret_cast<P*>(d) = v0;
+    *reinterpret_cast<P*>(d + 2) = v1;
+  }
+  // what the vector pass did not cover: the halo columns, or every column when the plane is not 16-byte friendly
+  const int first = vec4 ? 0 : 0, side = vec4 ? pitch - W : pitch;
+  for (int i = threadIdx.x; i < rows * side; i += blockDim.x) {
+    const int r = i / side, cc = i - r * side;
+    const int pc = !vec4 ? cc : (cc < pl ? cc : W + cc);
+    const int sy = extend_index_near(min(2 * ra + r - pt, 2 * H - 1), H, mode);
+    const int sx = extend_index_near(pc - pl, W, mode);
+    T v = 0;
+    if ((sy | sx) >= 0) v = (T)pa[sy * W + sx] - (pb != nullptr ? (T)pb[sy * W + sx] : (T)0);
+    dst[r * pitch + pc] = v;
+  }
+  (void)first;
+}
+
 // Boundary extension of LL[j] (the input plane of level j+1): every cell outside the interior copies the interior
 // cell the extension mode maps it to (or zero).
 template <typename T>
@@ -981,7 +1062,7 @@ __device__ __forceinline__ void wcfg_fill_halo(const WcfgStripGeom& g, int j, in
       pr = pt + r;
       pc = cc < pl ? cc : w + cc;
     }
-    const int sy = extend_index(pr - pt, h, mode), sx = extend_index(pc - pl, w, mode);
+    const int sy = extend_index_near(pr - pt, h, mode), sx = extend_index_near(pc - pl, w, mode);
     ll[pr * pitch + pc] = (sy | sx) < 0 ? (T)0 : ll[(sy + pt) * pitch + (sx + pl)];
   }
 }
@@ -999,6 +1080,12 @@ __device__ __forceinline__ void wcfg_synthesis_level(const WcfgStripGeom& g, int
   const int strips = (qy_end - qy_first + R - 1) / R;
   const int items = strips * qw;
   const int oh = H, ow = W;  // FINAL only
+  if (FINAL) {  // plane bases once, 32-bit offsets inside the plane
+    const int64_t pbase = plane * (int64_t)H * W;
+    out += pbase;
+    if (addend != nullptr) addend += pbase;
+    if (x != nullptr) x += pbase;
+  }
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int s = i / qw, qx = i - s * qw;
     const int qy0 = qy_first + s * R;
@@ -1020,7 +1107,7 @@ __device__ __forceinline__ void wcfg_synthesis_level(const WcfgStripGeom& g, int
       for (int r = 0; r < 2; ++r) {
         const int iy = 2 * qy + r;
         if (iy >= oh) continue;
-        const int64_t at = (plane * H + iy) * (int64_t)W + 2 * qx;
+        const int at = iy * W + 2 * qx;  // (a plane has fewer than 2^31 elements)
         T r0 = o[k][2 * r], r1 = o[k][2 * r + 1];
         if (vec2_ok) {
           if (addend != nullptr) {
@@ -1053,12 +1140,13 @@ __device__ __forceinline__ void wcfg_synthesis_level(const WcfgStripGeom& g, int
   }
 }
 
-#define SONAR_STRIP_DISPATCH(R_, CALL)          \
-  switch (R_) {                                 \
-    case 1: { constexpr int R = 1; CALL; } break; \
-    case 2: { constexpr int R = StripMax<T, LT>::value < 2 ? 1 : 2; CALL; } break; \
-    case 3: { constexpr int R = StripMax<T, LT>::value < 3 ? StripMax<T, LT>::value : 3; CALL; } break; \
-    default: { constexpr int R = StripMax<T, LT>::value; CALL; } break; \
+#define SONAR_STRIP_DISPATCH(R_, CALL)                                  \
+  if ((R_) >= 2 && StripMax<T, LT>::value >= 2) {                       \
+    constexpr int R = StripMax<T, LT>::value >= 2 ? 2 : 1;              \
+    CALL;                                                               \
+  } else {                                                              \
+    constexpr int R = 1;                                                \
+    CALL;                                                               \
   }
 
 template <typename T, int LT, bool PAIR>
@@ -1087,6 +1175,10 @@ wcfg_strip_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
   for (int64_t plane = plane_first; plane < planes; plane += plane_step) {
     const float* pa = in_a + plane * (int64_t)H * W;
     const float* pb = in_b != nullptr ? in_b + plane * (int64_t)H * W : nullptr;
+    if (g.stage_rows > 0) {
+      wcfg_stage_input<T>(g, pa, pb, H, W, mode, r_lo, sm);
+      __syncthreads();
+    }
     // ---------------- analysis, fine -> coarse ----------------
     for (int j = 0; j < J; ++j) {
       const int ra = j == 0 ? r_lo : 0, rb = j == 0 ? r_hi : g.h[j];
@@ -1237,7 +1329,7 @@ int launch_wcfg_fused(const SonarWcfgFusedParams& p, const WcfgGeom& g, cudaStre
     return e == nullptr || e[0] != '0';
   }();
   const int L = p.filters.length;
-  if (strip_enabled && (L == 2 || L == 4 || L == 6 || L == 8) && wcfg_strip_geometry(p.H, p.W, L, p.levels, &sg, g.pair != 0) &&
+  if (strip_enabled && (L == 2 || L == 4 || L == 6 || L == 8) && wcfg_strip_geometry(p.H, p.W, L, p.levels, &sg, g.pair != 0, sizeof(T), (size_t)di.max_smem_optin) &&
       (size_t)sg.total * sizeof(T) <= (size_t)di.max_smem_optin) {
     cfg.dynamicSmemBytes = (size_t)sg.total * sizeof(T);
 #define WCFG_STRIP_KERNEL(LT, PAIR)                                                                                       \

@@ -40,9 +40,14 @@ from ._native import SonarStepParams
 # batched schedule; the *_CTAS knobs are the CTAs per SM each side may occupy while both run.
 NOISE_PIPELINE = os.environ.get("SONAR_B200_NOISE_PIPELINE", "1") != "0"
 NOISE_PIPELINE_CHUNK = int(os.environ.get("SONAR_B200_PIPELINE_CHUNK", "1"))
-PIPELINE_STEP_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_CTAS", "3"))
-PIPELINE_FILL_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FILL_CTAS", "5"))
-PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "2"))
+PIPELINE_STEP_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_CTAS", "4"))
+PIPELINE_FILL_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FILL_CTAS", "4"))
+PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "0"))
+# Below this many elements per sample the batched schedule wins: a one-sample producer launch is far from the throughput
+# of a batch of 9-18 (tail of the persistent FFT grid), and a 30 us step hides little of it. Measured on B200 with the
+# C5 job (tools/sweep_pipeline.sh): 1 / 2 video latents per GPU 1.30 / 2.53 ms batched vs 1.35 / 2.89 ms pipelined,
+# 3 / 4 / 6 / 8 latents 3.81 / 5.04 / 7.52 / 9.93 ms batched vs 3.48 / 4.48 / 6.68 / 8.64 ms pipelined.
+PIPELINE_MIN_NUMEL = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL", str(20_000_000)))
 _PRODUCER_STREAMS: dict = {}
 
 
@@ -587,8 +592,9 @@ class SonarBase:
             queue = self._noise_queue = batch
         if queue and (queue[0][2].offset != gen.get_offset() or queue[0][2].seed != gen.initial_seed() or queue[0][0].shape != x.shape):
             queue.clear()
+        pipelined = NOISE_PIPELINE and x.numel() >= PIPELINE_MIN_NUMEL
         if not queue:
-            if NOISE_PIPELINE:
+            if pipelined:
                 made = self._produce_noise(make, x, overlapped=False)
                 if made is None:
                     return None
@@ -603,7 +609,7 @@ class SonarBase:
         raw, sums, draw = queue.pop(0)
         gen.set_offset(draw.offset + draw.counter_offset)
         self.noise_draws_left -= 1
-        if NOISE_PIPELINE and not queue and self.noise_draws_left >= 1:
+        if pipelined and not queue and self.noise_draws_left >= 1:
             # speculative: the next request normally finds the generator exactly here
             self._noise_pending = self._produce_noise(make, x, overlapped=True)
         return (raw, sums, parallel.global_numel(raw.numel()), factor)

@@ -228,3 +228,37 @@ def test_noise_lookahead_equals_draw_by_draw(sb, cuda, monkeypatch):
         assert_close(ahead, single, what=f"look-ahead vs draw by draw ({model.__name__})", rtol=1e-6, atol=1e-6)
         if model is plain:
             assert launches_a < launches_b  # 8 draws: 1 + 1 launches instead of 8 + 8
+
+
+@pytest.mark.parametrize("chunk", [1, 3])
+def test_noise_pipeline_equals_batched(sb, cuda, monkeypatch, chunk):
+    """Pipelined production (next sample made on a second stream beside the fused step, co-scheduling grid limits,
+    ping-pong buffers) hands out the very same samples as the batched look-ahead: identical result bits and generator
+    advance -- also when the model draws random numbers in between (every speculative sample is then dropped)."""
+    sigmas = torch.cat((torch.linspace(14.6, 0.5, 6), torch.zeros(1))).to(cuda)
+    torch.manual_seed(10)
+    x0 = (torch.randn(2, 4, 3, 18, 20) * 14.6).to(cuda)
+
+    def plain(x, sigma, **_kw):
+        return x * 0.9
+
+    def noisy(x, sigma, **_kw):
+        return x * 0.9 + torch.randn(3, device=x.device).sum() * 0.0
+
+    def run(model, pipelined):
+        monkeypatch.setattr(sb.samplers, "NOISE_PIPELINE", pipelined)
+        monkeypatch.setattr(sb.samplers, "PIPELINE_MIN_NUMEL", 0)
+        monkeypatch.setattr(sb.samplers, "NOISE_PIPELINE_CHUNK", chunk)
+        torch.manual_seed(78)
+        out = sb.samplers.SonarDPMPPSDE.sampler(
+            model, x0.clone(), sigmas, extra_args={"seed": 0}, disable=True, sonar_params={"custom_noise": video_chain(sb, alpha=1.0)},
+        )
+        torch.cuda.synchronize()
+        return out, torch.cuda.default_generators[0].get_offset()
+
+    for model in (plain, noisy):
+        piped, off_a = run(model, True)
+        batched, off_b = run(model, False)
+        assert off_a == off_b
+        assert torch.equal(piped, batched), f"pipelined vs batched ({model.__name__})"
+    assert sb.ops._GRID_LIMIT == 0  # noqa: SLF001  (the co-scheduling hint never outlives a launch)
