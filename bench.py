@@ -365,6 +365,8 @@ def run_b200_arm(args) -> None:
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     import sonar_b200 as sb
 
@@ -632,7 +634,10 @@ def _time_traced(sb, fn, reps: int, flush: torch.Tensor) -> tuple[float, dict]:
     torch.cuda.synchronize()
     totals, per = [], {}
     for _ in range(reps):
-        flush.zero_()
+        # ~0.3 ms of queued zero-fills (they also evict L2): the host enqueues the traced launches while the device is
+        # still busy, so an event pair brackets the kernel alone and not the host's launch latency on an idle GPU
+        for _ in range(8):
+            flush.zero_()
         sb.ops.TRACE = []
         fn()
         torch.cuda.synchronize()
@@ -682,14 +687,18 @@ def run_extras(sb, dev, peak: float) -> list[dict]:
     sig2 = torch.cat((torch.linspace(14.6, 0.03, 30), torch.zeros(1))).to(dev)
     x2 = torch.randn(8, 4, 128, 128, device=dev) * 14.6
 
+    def c2_model(x, _s, **_k):
+        flush.zero_()  # the UNet's place: evicts L2 and lets the host run ahead of the device (see _time_traced)
+        return x * 0.9
+
     def c2():
         torch.manual_seed(99)
-        return sb.samplers.SonarEulerAncestral.sampler(lambda x, s, **k: x * 0.9, x2, sig2, extra_args={"seed": 0}, disable=True)
+        return sb.samplers.SonarEulerAncestral.sampler(c2_model, x2, sig2, extra_args={"seed": 0}, disable=True)
 
     us, per = _time_traced(sb, c2, 5, flush)
     record("C2 sonar_euler_ancestral 8x4x128x128, 30 steps, fused Gaussian noise", 30 * x2.numel(), 20.0, us, per,
            "20 B/el/step: read x, denoised, history; write x', history'; noise regenerated from Philox in registers. Kernel "
-           "time only (launch-bound at this size: see DESIGN.md)")
+           "time only, cold L2 (a 256 MiB zero-fill stands in for the UNet between steps); latency-bound at this size: see DESIGN.md")
 
     # C3: Scheduled(Blended(lerp .5, pyramid, perlin), fallback gaussian) on 16x16x128x128
     def chain_of(t):

@@ -16,6 +16,29 @@ enum DistKind : int { DIST_NORMAL = 0, DIST_UNIFORM = 1 };
 // The launch covers pairs p in [0, T*k_count): t = p % T, k = k_lo + p / T. With k_lo = 0 and
 // k_count = ceil(numel / 4T) this is exactly ATen's grid-stride loop. A slice [begin, end) of
 // the virtual tensor only keeps the lanes that fall inside it and writes them at (li - begin).
+// The four lanes of a call land T elements apart. Calls that lie wholly inside the slice (all but the first and the
+// last call row of a slice) take one pointer and three pointer bumps instead of four 64-bit range tests.
+__device__ __forceinline__ void store_lanes(float* __restrict__ out, const float4& v, int64_t li0, int64_t T, int64_t begin,
+                                            int64_t end) {
+  if (li0 >= begin && li0 + 3 * T < end) {
+    float* p = out + (li0 - begin);
+    p[0] = v.x;
+    p += T;
+    p[0] = v.y;
+    p += T;
+    p[0] = v.z;
+    p += T;
+    p[0] = v.w;
+    return;
+  }
+  const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int lane = 0; lane < 4; ++lane) {
+    const int64_t li = li0 + T * lane;
+    if (li >= begin && li < end) out[li - begin] = vals[lane];
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kBlock)
 philox_fill_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxStream s, uint32_t k_lo, uint32_t k_hi,
@@ -42,12 +65,7 @@ philox_fill_kernel(float* __restrict__ out, int64_t begin, int64_t end, PhiloxSt
         v.z = uniform_transform(v.z, p0, p1);
         v.w = uniform_transform(v.w, p0, p1);
       }
-      const float vals[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        const int64_t li = li0 + T * lane;
-        if (li >= begin && li < end) out[li - begin] = vals[lane];
-      }
+      store_lanes(out, v, li0, T, begin, end);
     }
   }
 }
@@ -96,12 +114,7 @@ philox_fill_batch_kernel(FillBatchDev b) {
         v.z = uniform_transform(v.z, p0, p1);
         v.w = uniform_transform(v.w, p0, p1);
       }
-      const float vals[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int lane = 0; lane < 4; ++lane) {
-        const int64_t li = li0 + T * lane;
-        if (li >= begin && li < end) out[li - begin] = vals[lane];
-      }
+      store_lanes(out, v, li0, T, begin, end);
     }
   }
 }
