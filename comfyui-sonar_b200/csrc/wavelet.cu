@@ -514,6 +514,7 @@ wcfg_fused_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
     own_lo = rank ? split : 0;
     own_hi = rank ? g.h[0] : split;
     peer_ll0 = cluster.map_shared_rank(sm, rank ^ 1) + g.ll_off[0];
+    cluster.sync();  // no store into the partner's shared memory before the partner CTA has started executing
   }
   const int64_t plane_first = PAIR ? blockIdx.x >> 1 : blockIdx.x, plane_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   for (int64_t plane = plane_first; plane < planes; plane += plane_step) {
@@ -1170,6 +1171,7 @@ wcfg_strip_kernel(const float* __restrict__ in_a, const float* __restrict__ in_b
     c.own_lo = rank ? split : 0;
     c.own_hi = rank ? g.h[0] : split;
     c.peer_ll0 = cluster.map_shared_rank(sm, rank ^ 1) + g.ll_off[0];
+    cluster.sync();  // no store into the partner's shared memory before the partner CTA has started executing
   }
   const int64_t plane_first = PAIR ? blockIdx.x >> 1 : blockIdx.x, plane_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   for (int64_t plane = plane_first; plane < planes; plane += plane_step) {
