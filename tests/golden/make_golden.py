@@ -590,6 +590,52 @@ IN_SCOPE_NODES = (
 )  # fmt: skip
 
 
+def gen_noisy_latent(ref) -> None:
+    """NoisyLatentLike (py/nodes/misc.py:55-150): the node end to end on the reference -- built-in
+    noise type and custom chain, repeat_batch, add_to_latent, the sigma / model multiplier (both max_denoise branches)."""
+    misc, noise, pn = ref.py.nodes.misc, ref.py.noise, ref.py.nodes.powernoise
+    defaults = {
+        "time_brownian": False, "alpha": 1.0, "max_freq": 0.7071, "min_freq": 0.0, "stretch": 1.0, "rotate": 0.0,
+        "pnorm": 2.0, "mix": 1.0, "common_mode": 0.0, "channel_correlation": "1, 1, 1, 1, 1, 1",
+    }  # fmt: skip
+    chain = noise.CustomNoiseChain()
+    chain.add(pn.PowerNoiseItem(1.0, **defaults))
+
+    class _MS:
+        sigma_max = torch.tensor(14.6)
+
+    class _LF:
+        scale_factor = 0.13025
+
+    class _Inner:
+        model_sampling, latent_format = _MS(), _LF()
+
+    class _Model:
+        model = _Inner()
+
+    torch.manual_seed(900)
+    latent = torch.randn(2, 4, 16, 24)
+    cases = {
+        "gaussian_repeat_add": {"noise_type": "gaussian", "seed": 11, "multiplier": 1.5, "add_to_latent": True, "repeat_batch": 2},
+        "power_custom": {"noise_type": "gaussian", "seed": 12, "multiplier": 0.75, "repeat_batch": 3, "custom": True},
+        "sigmas_max_denoise": {"noise_type": "gaussian", "seed": 13, "multiplier": 1.0, "add_to_latent": True,
+                               "sigmas": torch.tensor([14.6, 7.0, 1.0, 0.0])},
+        "sigmas_partial": {"noise_type": "gaussian", "seed": 14, "multiplier": 2.0, "normalize": False,
+                           "sigmas": torch.tensor([5.0, 2.0, 0.0])},
+    }  # fmt: skip
+    out = {"latent": latent, "scale_factor": _LF.scale_factor, "sigma_max": 14.6, "cases": {}}
+    for name, kw in cases.items():
+        kw = dict(kw)
+        custom, sigmas = kw.pop("custom", False), kw.pop("sigmas", None)
+        with record_draws() as draws:
+            (res,) = misc.NoisyLatentLikeNode.go(
+                latent={"samples": latent.clone()}, cpu_noise=True, custom_noise_opt=chain if custom else None,
+                mul_by_sigmas_opt=sigmas, model_opt=_Model() if sigmas is not None else None, **kw,
+            )
+        out["cases"][name] = {"kwargs": kw, "custom": custom, "sigmas": sigmas, "draws": draws, "out": res["samples"].clone()}
+    save("noisy_latent", out)
+
+
 def gen_node_schemas(ref) -> None:
     """INPUT_TYPES / RETURN_TYPES / FUNCTION / CATEGORY of the in-scope nodes (tooltips dropped)."""
     import json
@@ -633,6 +679,7 @@ def main() -> None:
     gen_host_logic(ref)
     gen_freeu(ref)
     gen_round2(ref)
+    gen_noisy_latent(ref)
     gen_node_schemas(ref)
 
 

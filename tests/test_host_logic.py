@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes
+import importlib
 import re
 import subprocess
 import sys
@@ -259,3 +260,22 @@ def test_sharding_rejects_a_batch_smaller_than_the_world(sb):
             pass
     with sb.parallel.sharded(5, rank=1, world_size=2) as ctx:
         assert ctx.batch_sizes == [3, 2] and ctx.batch_begin == 3
+
+
+def test_channel_mixer_is_memoised_and_identity_stays_on_the_host():
+    """ChannelMixer.build is a pure function of (channels, common_mode, correlation): built once, cloned per sampler;
+    the default (common_mode == 0) mixer is the identity and is never moved to the device."""
+    sn = importlib.import_module("sonar_b200.spectral_noise")
+    corr = torch.tensor([1.0, 0.5, 0.25])
+    a = sn.ChannelMixer(6, 0.3, corr)
+    b = sn.ChannelMixer(6, 0.3, corr.clone())
+    assert torch.equal(a.mixer, b.mixer) and a.mixer.data_ptr() != b.mixer.data_ptr()
+    assert not a.is_identity
+    fresh = a._build()  # noqa: SLF001
+    assert torch.equal(a.mixer, fresh)
+    # rows have unit norm (:88-89)
+    assert torch.allclose(a.mixer.norm(dim=1), torch.ones(6), atol=1e-6)
+    ident = sn.ChannelMixer(528, 0.0, torch.ones(6))
+    assert ident.is_identity and torch.equal(ident.mixer, torch.eye(528))
+    moved = ident.to("meta")  # would fail loudly if the identity were copied anywhere
+    assert moved.mixer.device.type == "cpu"

@@ -114,6 +114,41 @@ def test_config_c1_noise_object_golden(sb, golden):
 
 
 @pytest.mark.gpu
+def test_noisy_latent_like_golden(sb, golden):
+    """NoisyLatentLike end to end against the reference node (fixture recorded by make_golden.py gen_noisy_latent):
+    built-in and custom noise, repeat_batch, add_to_latent, the sigma / model multiplier in both max_denoise branches."""
+    fx = golden("noisy_latent")
+    n = sb.nodes
+
+    class _MS:
+        sigma_max = torch.tensor(fx["sigma_max"])
+
+    class _LF:
+        scale_factor = fx["scale_factor"]
+
+    class _Inner:
+        model_sampling, latent_format = _MS(), _LF()
+
+    class _Model:
+        model = _Inner()
+
+    kwargs = {k: (v[1]["default"] if len(v) > 1 and "default" in v[1] else None) for k, v in n.SonarPowerNoiseNode.INPUT_TYPES()["required"].items()}
+    (chain,) = n.SonarPowerNoiseNode().go(**(kwargs | {"alpha": 1.0}))
+    for name, case in fx["cases"].items():
+        with sb.rng.injected(case["draws"]) as left:
+            (res,) = n.NoisyLatentLikeNode.go(
+                latent={"samples": fx["latent"].clone()}, cpu_noise=True, custom_noise_opt=chain if case["custom"] else None,
+                mul_by_sigmas_opt=case["sigmas"], model_opt=_Model() if case["sigmas"] is not None else None, **case["kwargs"],
+            )
+            assert not left, f"{name}: recorded draws not consumed"
+        out = res["samples"]
+        assert out.device.type == "cpu" and out.dtype == torch.float32
+        # 1e-5 relative to the tensor's scale: the sigma cases multiply unit noise by ~110 before adding the latent
+        scale = max(1.0, float(case["out"].abs().max()))
+        assert_close(out / scale, case["out"] / scale, what=f"NoisyLatentLike {name}")
+
+
+@pytest.mark.gpu
 def test_noisy_latent_like_and_config_override(sb, cuda):
     n = sb.nodes
     latent = {"samples": torch.zeros(2, 4, 16, 16)}
