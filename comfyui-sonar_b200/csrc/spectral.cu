@@ -815,8 +815,7 @@ __host__ __device__ __forceinline__ unsigned magic_of(int d) { return (unsigned)
 enum SpectralInput : int { INPUT_SPECTRUM = 0, INPUT_REAL = 1, INPUT_PHILOX = 2 };
 
 template <int INPUT>
-__global__ void __launch_bounds__(kBatchedThreads, 2)
-spectral_batched_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
+__device__ __forceinline__ void spectral_batched_body(const SpectralBatchedLaunch& L) {
   constexpr bool REAL = INPUT == INPUT_REAL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SonarSpectralParams& p = L.p;
@@ -935,6 +934,21 @@ spectral_batched_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
   }
 }
 
+template <int INPUT>
+__global__ void __launch_bounds__(kBatchedThreads, 2)
+spectral_batched_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
+  spectral_batched_body<INPUT>(L);
+}
+
+// Co-scheduled form (sonar_set_grid_limit >= 3 around the launch): the same body at <= 48 registers, 3 CTAs x 320
+// threads = 46 K registers per SM, which leaves two 256-thread CTAs of the fused step (16 K registers) resident on
+// the same SM -- the issue-bound FFT then runs under the HBM-bound second half of the step launch.
+constexpr int kCoThreads = 320;
+__global__ void __launch_bounds__(kCoThreads, 4)
+spectral_batched_co_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
+  spectral_batched_body<INPUT_SPECTRUM>(L);
+}
+
 // Fewest stages over the radix set, ties broken by the smaller radix sum (8 x 8 before 16 x 4).
 static void search_plan(int rem, int depth, int sum, int* cur, int* best, int* best_depth, int* best_sum) {
   static const int kRadices[] = {16, 10, 9, 8, 5, 4, 3, 2};
@@ -1044,7 +1058,6 @@ static bool plan_spectral_batched(const SonarSpectralParams& p, SpectralBatchedL
   // slots left over go to a kernel on another stream
   const int limit = grid_limit_ctas_per_sm();
   const int resident = limit > 0 && limit < ctas_per_sm ? limit : ctas_per_sm;
-  if (limit > 0 && *threads_out > 256) *threads_out = 256;  // 3 x 256 threads x 64 registers leave a quarter of the register file
   if (grid > (int64_t)di.sm_count * resident) grid = (int64_t)di.sm_count * resident;
   *grid_out = grid;
   return true;
@@ -1060,6 +1073,11 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   auto kernel = p.in_real != nullptr   ? spectral_batched_kernel<INPUT_REAL>
                 : p.in_spec != nullptr ? spectral_batched_kernel<INPUT_SPECTRUM>
                                        : spectral_batched_kernel<INPUT_PHILOX>;
+  // co-scheduling hint >= 3 CTAs per SM: the low-register form (spectrum input), same CTA count per SM
+  if (grid_limit_ctas_per_sm() >= 3 && p.in_spec != nullptr && p.in_real == nullptr && ctas_per_sm >= 3) {
+    kernel = spectral_batched_co_kernel;
+    threads = kCoThreads;
+  }
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
   kernel<<<(unsigned)grid, threads, smem, stream>>>(L);

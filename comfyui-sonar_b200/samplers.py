@@ -42,12 +42,18 @@ NOISE_PIPELINE = os.environ.get("SONAR_B200_NOISE_PIPELINE", "1") != "0"
 NOISE_PIPELINE_CHUNK = int(os.environ.get("SONAR_B200_PIPELINE_CHUNK", "1"))
 PIPELINE_STEP_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_CTAS", "4"))
 PIPELINE_FILL_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FILL_CTAS", "4"))
-PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "0"))
+PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "3"))  # >= 3: the low-register FFT form
+# The step launch is made in two parts: the first PIPELINE_STEP_SPLIT of the elements beside the Philox fill (4 + 4
+# CTAs per SM), the rest beside the FFT in its 48-register form (3 x 320 threads) with the 2 step CTAs per SM the
+# register file still holds. tools/sweep_pipeline.sh on B200, interval between model calls at 8 video latents:
+# 466 us unsplit, 459 / 451 / 443 / 446 / 452 us at split 0.5 / 0.6 / 0.7 / 0.75 / 0.8 (535 at 0.4: the second part is slow).
+PIPELINE_STEP_SPLIT = float(os.environ.get("SONAR_B200_PIPELINE_STEP_SPLIT", "0.75"))
+PIPELINE_STEP_B_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_B_CTAS", "2"))
 # Below this many elements per sample the batched schedule wins: a one-sample producer launch is far from the throughput
 # of a batch of 9-18 (tail of the persistent FFT grid), and a 30 us step hides little of it. Measured on B200 with the
-# C5 job (tools/sweep_pipeline.sh): 1 / 2 video latents per GPU 1.30 / 2.53 ms batched vs 1.35 / 2.89 ms pipelined,
-# 3 / 4 / 6 / 8 latents 3.81 / 5.04 / 7.52 / 9.93 ms batched vs 3.48 / 4.48 / 6.68 / 8.64 ms pipelined.
-PIPELINE_MIN_NUMEL = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL", str(20_000_000)))
+# C5 job (tools/sweep_pipeline.sh, profiles/r02b_noise_pipeline_sweeps.txt): 1 video latent per GPU 1.27 ms batched vs
+# 1.52 ms pipelined, 2 / 3 / 4 / 8 latents 2.53 / 3.81 / 5.04 / 9.93 ms batched vs 2.41 / 3.36 / 4.32 / 8.30 ms pipelined.
+PIPELINE_MIN_NUMEL = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL", str(12_000_000)))
 _PRODUCER_STREAMS: dict = {}
 
 
@@ -357,9 +363,25 @@ class SonarBase:
             # a producer is running on the second stream: leave it thread slots on every SM, then make everything
             # enqueued after this half step wait for it (the next model call starts with the next sample ready)
             self._noise_join = None
-            ops.set_grid_limit(PIPELINE_STEP_CTAS)
+            n = p.n
+            n_a = (int(n * PIPELINE_STEP_SPLIT) // 4) * 4 if PIPELINE_STEP_SPLIT < 1.0 else n
             try:
-                ops.launch_step(self._params_ref, x.device.index)
+                ops.set_grid_limit(PIPELINE_STEP_CTAS)
+                if 0 < n_a < n:
+                    # two launches over the flat tensors: the first beside the Philox fill, the second (fewer CTAs
+                    # per SM) beside the co-scheduled FFT
+                    p.n = n_a
+                    ops.launch_step(self._params_ref, x.device.index)
+                    ops.set_grid_limit(PIPELINE_STEP_B_CTAS)
+                    shift = 4 * n_a
+                    p.n = n - n_a
+                    for name in ("x", "denoised", "x_out", "hist_in", "hist_out", "noise"):
+                        ptr = getattr(p, name)
+                        if ptr:
+                            setattr(p, name, ptr + shift)
+                    ops.launch_step(self._params_ref, x.device.index)
+                else:
+                    ops.launch_step(self._params_ref, x.device.index)
             finally:
                 ops.set_grid_limit(0)
             torch.cuda.current_stream().wait_event(join)

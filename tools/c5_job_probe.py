@@ -31,6 +31,6 @@ for _ in range(5):
     torch.cuda.synchronize()
     ts.append(t.total_ms())
 iv = [a.elapsed_time(b) * 1e3 for a, b in t.pairs]
-print(f"items={bench.SHAPE[0]} pipeline={sb.samplers.NOISE_PIPELINE} step_ctas={sb.samplers.PIPELINE_STEP_CTAS} fill_ctas={sb.samplers.PIPELINE_FILL_CTAS} fft_ctas={sb.samplers.PIPELINE_FFT_CTAS} "
+print(f"items={bench.SHAPE[0]} pipeline={sb.samplers.NOISE_PIPELINE} step_ctas={sb.samplers.PIPELINE_STEP_CTAS} fill_ctas={sb.samplers.PIPELINE_FILL_CTAS} fft_ctas={sb.samplers.PIPELINE_FFT_CTAS} split={sb.samplers.PIPELINE_STEP_SPLIT} stepB={sb.samplers.PIPELINE_STEP_B_CTAS} "
       f"chunk={sb.samplers.NOISE_PIPELINE_CHUNK}: {statistics.median(ts):.3f} ms per run  intervals(us): " + " ".join(f"{v:.0f}" for v in iv)
       + f"  checksum {float(out.double().sum()):.6f}")
