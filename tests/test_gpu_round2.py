@@ -50,10 +50,13 @@ def test_c5_job_golden(sb, cuda, golden, variant):
     assert_close(out, case["out"], what=f"c5 {variant} final")
 
 
-def test_c5_job_shard_size_vs_oracle(sb, cuda):
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_c5_job_shard_size_vs_oracle(sb, cuda, monkeypatch, pipelined):
     """Config 5 at the per-GPU shard size 1x16x33x90x160 with the DEVICE Philox stream (no injection): the product
     draws its complex spectra from torch's CUDA generator state; the oracle is fed torch.randn(complex64,
-    device='cuda') from the same seed."""
+    device='cuda') from the same seed. pipelined: the schedule of larger shards forced at this size -- producers on the
+    second stream, the 48-register FFT form, the step launch in two parts."""
+    monkeypatch.setattr(sb.samplers, "PIPELINE_MIN_NUMEL", 0 if pipelined else 1 << 62)
     sigmas = torch.tensor([14.6, 5.0, 1.2, 0.0])
     torch.manual_seed(5)
     x0 = torch.randn(1, 16, 33, 90, 160) * sigmas[0]
@@ -89,7 +92,8 @@ def test_c5_job_shard_size_vs_oracle(sb, cuda):
             x = o.dpmpp_sde(i, x, den, sigmas[i], sigmas[i + 1], model, n1, n2)
     assert_close(got, x, what="c5 shard")
     # 2 steps x 2 half steps x (one noise launch + one fused step launch) + the final Euler step
-    assert launches <= 2 * 2 * 2 + 1, launches
+    if not pipelined:
+        assert launches <= 2 * 2 * 2 + 1, launches
 
 
 @pytest.mark.parametrize("name", ["c4_common", "c4_corr", "c3_neg", "c16_short_corr"])
