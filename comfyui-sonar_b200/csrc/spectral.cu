@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <type_traits>
 
@@ -940,15 +941,6 @@ spectral_batched_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
   spectral_batched_body<INPUT>(L);
 }
 
-// Co-scheduled form (sonar_set_grid_limit >= 3 around the launch): the same body at <= 48 registers, 3 CTAs x 320
-// threads = 46 K registers per SM, which leaves two 256-thread CTAs of the fused step (16 K registers) resident on
-// the same SM -- the issue-bound FFT then runs under the HBM-bound second half of the step launch.
-constexpr int kCoThreads = 320;
-__global__ void __launch_bounds__(kCoThreads, 4)
-spectral_batched_co_kernel(const __grid_constant__ SpectralBatchedLaunch L) {
-  spectral_batched_body<INPUT_SPECTRUM>(L);
-}
-
 // Fewest stages over the radix set, ties broken by the smaller radix sum (8 x 8 before 16 x 4).
 static void search_plan(int rem, int depth, int sum, int* cur, int* best, int* best_depth, int* best_sum) {
   static const int kRadices[] = {16, 10, 9, 8, 5, 4, 3, 2};
@@ -1073,11 +1065,11 @@ static int launch_spectral_batched(const SonarSpectralParams& p, cudaStream_t st
   auto kernel = p.in_real != nullptr   ? spectral_batched_kernel<INPUT_REAL>
                 : p.in_spec != nullptr ? spectral_batched_kernel<INPUT_SPECTRUM>
                                        : spectral_batched_kernel<INPUT_PHILOX>;
-  // co-scheduling hint >= 3 CTAs per SM: the low-register form (spectrum input), same CTA count per SM
-  if (grid_limit_ctas_per_sm() >= 3 && p.in_spec != nullptr && p.in_real == nullptr && ctas_per_sm >= 3) {
-    kernel = spectral_batched_co_kernel;
-    threads = kCoThreads;
-  }
+  // Co-scheduling hint >= 3 CTAs per SM (sonar_set_grid_limit): 256-thread CTAs. 3 x 256 threads x 64 registers = 48 K
+  // registers per SM leave 16 K = two 256-thread CTAs of the fused step resident on the same SM, so the issue-bound FFT
+  // runs under the HBM-bound second part of the step launch. (Alone, 256 threads are as fast as 320: 179 vs 182 us for
+  // 4224 planes of 90x160; a 48-register instantiation at 320 threads was slower, 193 us.)
+  if (grid_limit_ctas_per_sm() >= 3 && ctas_per_sm >= 3 && threads > 256) threads = 256;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
   kernel<<<(unsigned)grid, threads, smem, stream>>>(L);

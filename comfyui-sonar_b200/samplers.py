@@ -42,17 +42,17 @@ NOISE_PIPELINE = os.environ.get("SONAR_B200_NOISE_PIPELINE", "1") != "0"
 NOISE_PIPELINE_CHUNK = int(os.environ.get("SONAR_B200_PIPELINE_CHUNK", "1"))
 PIPELINE_STEP_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_CTAS", "4"))
 PIPELINE_FILL_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FILL_CTAS", "4"))
-PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "3"))  # >= 3: the low-register FFT form
+PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "3"))  # >= 3: 256-thread FFT CTAs, 16 K registers stay free
 # The step launch is made in two parts: the first PIPELINE_STEP_SPLIT of the elements beside the Philox fill (4 + 4
-# CTAs per SM), the rest beside the FFT in its 48-register form (3 x 320 threads) with the 2 step CTAs per SM the
-# register file still holds. tools/sweep_pipeline.sh on B200, interval between model calls at 8 video latents:
-# 466 us unsplit, 459 / 451 / 443 / 446 / 452 us at split 0.5 / 0.6 / 0.7 / 0.75 / 0.8 (535 at 0.4: the second part is slow).
-PIPELINE_STEP_SPLIT = float(os.environ.get("SONAR_B200_PIPELINE_STEP_SPLIT", "0.75"))
+# CTAs per SM), the rest beside the FFT (3 x 256 threads x 64 registers) with the 2 step CTAs per SM the register file
+# still holds. tools/sweep_pipeline.sh on B200, interval between model calls at 8 video latents: 466 us unsplit;
+# 417 / 411 / 408 / 405 / 415 us at split 0.5 / 0.55 / 0.6 / 0.65 / 0.7 (a late second part stalls the next interval).
+PIPELINE_STEP_SPLIT = float(os.environ.get("SONAR_B200_PIPELINE_STEP_SPLIT", "0.6"))
 PIPELINE_STEP_B_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_B_CTAS", "2"))
 # Below this many elements per sample the batched schedule wins: a one-sample producer launch is far from the throughput
 # of a batch of 9-18 (tail of the persistent FFT grid), and a 30 us step hides little of it. Measured on B200 with the
 # C5 job (tools/sweep_pipeline.sh, profiles/r02b_noise_pipeline_sweeps.txt): 1 video latent per GPU 1.27 ms batched vs
-# 1.52 ms pipelined, 2 / 3 / 4 / 8 latents 2.53 / 3.81 / 5.04 / 9.93 ms batched vs 2.41 / 3.36 / 4.32 / 8.30 ms pipelined.
+# 1.57 ms pipelined, 2 / 4 / 8 latents 2.53 / 5.04 / 9.93 ms batched vs 2.38 / 4.02 / 7.71 ms pipelined.
 PIPELINE_MIN_NUMEL = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL", str(12_000_000)))
 _PRODUCER_STREAMS: dict = {}
 

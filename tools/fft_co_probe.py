@@ -8,8 +8,10 @@ dev = torch.device("cuda", 0)
 H, W, Wh = 90, 160, 81
 mask = torch.rand(H, Wh, device=dev) + 0.5
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-spec = torch.randn(4224, H, Wh, dtype=torch.complex64, device=dev)
-out = torch.empty(4224, H, W, device=dev)
+import os
+P = int(os.environ.get("PLANES", "4224"))
+spec = torch.randn(P, H, Wh, dtype=torch.complex64, device=dev)
+out = torch.empty(P, H, W, device=dev)
 ref = None
 for limit in (0, 3, 2):
     ts = []
@@ -25,4 +27,4 @@ for limit in (0, 3, 2):
         ts.append(a.elapsed_time(b) * 1e3)
     if ref is None:
         ref = out.clone()
-    print(f"limit {limit}: {sorted(ts)[len(ts) // 2]:7.1f} us   max |diff vs default| {float((out - ref).abs().max()):.2e}")
+    print(f"planes {P} limit {limit}: {sorted(ts)[len(ts) // 2]:7.1f} us   max |diff vs default| {float((out - ref).abs().max()):.2e}")
