@@ -451,7 +451,7 @@ def run_b200_arm(args) -> None:
     tracer = StepTimer(dev, timed=False, on_first_call=rendezvous)
     # per-kernel durations are taken with the noise pipeline OFF: with it on, the producers run beside the step kernel
     # on a second stream and an event pair around one launch also times its neighbours (ncu serialises in the same way)
-    pipelined = bool(sb.samplers.NOISE_PIPELINE and n_local >= sb.samplers.PIPELINE_MIN_NUMEL)
+    pipelined = bool(sb.samplers.NOISE_PIPELINE and n_local >= (sb.samplers.PIPELINE_MIN_NUMEL_SHARDED if world > 1 else sb.samplers.PIPELINE_MIN_NUMEL))
     sb.samplers.NOISE_PIPELINE, keep_flag = False, sb.samplers.NOISE_PIPELINE
     try:
         one_run(tracer, x0)

@@ -54,6 +54,11 @@ PIPELINE_STEP_B_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_B_CTAS", "2"
 # C5 job (tools/sweep_pipeline.sh, profiles/r02b_noise_pipeline_sweeps.txt): 1 video latent per GPU 1.27 ms batched vs
 # 1.57 ms pipelined, 2 / 4 / 8 latents 2.53 / 5.04 / 9.93 ms batched vs 2.38 / 4.02 / 7.71 ms pipelined.
 PIPELINE_MIN_NUMEL = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL", str(12_000_000)))
+# Batch-sharded runs exchange the statistics of every pipelined sample separately (18 exchanges per C5 run instead of
+# 1-2 per look-ahead batch), each of which also absorbs the skew between the ranks: on 4 GPUs x 2 latents the pipelined
+# job took 2.93 ms against 2.49 ms batched (2.38 vs 2.53 ms on one GPU with the same 2 latents); on 2 GPUs x 4 latents
+# 4.17 vs 4.67 ms. Sharded runs therefore pipeline only from twice the size.
+PIPELINE_MIN_NUMEL_SHARDED = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL_SHARDED", str(24_000_000)))
 _PRODUCER_STREAMS: dict = {}
 
 
@@ -614,7 +619,9 @@ class SonarBase:
             queue = self._noise_queue = batch
         if queue and (queue[0][2].offset != gen.get_offset() or queue[0][2].seed != gen.initial_seed() or queue[0][0].shape != x.shape):
             queue.clear()
-        pipelined = NOISE_PIPELINE and x.numel() >= PIPELINE_MIN_NUMEL
+        ctx = parallel.active()
+        sharded = ctx is not None and ctx.world_size > 1
+        pipelined = NOISE_PIPELINE and x.numel() >= (PIPELINE_MIN_NUMEL_SHARDED if sharded else PIPELINE_MIN_NUMEL)
         if not queue:
             if pipelined:
                 made = self._produce_noise(make, x, overlapped=False)
