@@ -1045,6 +1045,9 @@ static bool plan_spectral_batched(const SonarSpectralParams& p, SpectralBatchedL
   *ctas_per_sm_out = ctas_per_sm;
   *threads_out = ctas_per_sm >= 4 ? 256 : ctas_per_sm == 3 ? 320 : kBatchedThreads;
   int64_t grid = (p.planes + L.group - 1) / L.group;
+  // long launches (many passes per persistent CTA) run slightly faster on 256-thread CTAs: 9504 planes of 90x160
+  // 383 vs 390 us; at one or two passes per CTA 320 threads are equal or better (1056 planes: 59.4 vs 57.4 us)
+  if (ctas_per_sm == 3 && grid > 8 * (int64_t)di.sm_count * ctas_per_sm) *threads_out = 256;
   // persistent CTAs: the per-CTA tables (twiddles, slot maps) are built once and reused for every group
   // co-scheduling hint (sonar_set_grid_limit): fewer resident CTAs per SM, same CTA shape -- the registers and thread
   // slots left over go to a kernel on another stream
