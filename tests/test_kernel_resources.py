@@ -60,6 +60,21 @@ def test_register_and_stack_budgets(usage):
     assert all(u[4] == 0 for u in usage), "no kernel declares static local memory"
 
 
+def test_co_scheduling_register_budget(usage):
+    """The noise pipeline rests on register arithmetic: 4 fill CTAs + 4 step CTAs of 256 threads
+    fit one SM only at <= 32 registers each (2 x 32 K), and the 3 x 256-thread FFT CTAs at 64 registers (48 K) leave
+    exactly the 16 K two more step CTAs need."""
+    for name, reg, _stack, _shared, _local in _select(usage, r"philox_fill(_batch)?_kernel"):
+        assert reg <= 32, (name, reg)
+    # the C5 step: DPM++ half step, NEW momentum mode, history present, noise normalised on load
+    for name, reg, _stack, _shared, _local in _select(usage, r"sonar_step_fast_vec_kernel<1, true, true, 2>|sonar_step_fast_vec_kernel<\(int\)1, \(bool\)1, \(bool\)1, \(int\)2>"):
+        assert reg <= 32, (name, reg)
+    for name, reg, _stack, _shared, _local in _select(usage, r"spectral_batched_kernel<\(?(int\))?0>"):
+        assert 3 * 256 * reg + 2 * 256 * 32 <= 65536, (name, reg)
+    for name, reg, _stack, _shared, _local in _select(usage, r"wcfg_strip_kernel"):
+        assert reg <= 64, (name, reg)
+
+
 def test_tensor_cores_are_deliberately_unused():
     """Nothing on this path is a dense contraction: no MMA instruction of any generation."""
     sass = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
