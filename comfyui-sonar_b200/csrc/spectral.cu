@@ -388,6 +388,7 @@ struct SpectralBatchedLaunch {
   int pitch;        // odd, >= wh: row pitch of a plane in shared memory (complex elements)
   int plane_elems;  // H * pitch
   int group;        // planes per CTA pass
+  int fuse_fold;    // 1: the c2r fold runs inside the first row stage (run_stage_fold) instead of as a pass of its own
   float scale;      // out_scale (x 1/2 for real input: the r2c unfold leaves a factor 2)
   unsigned magic_wh, magic_cols, magic_rows, magic_row_nb;  // ceil(2^32 / d): d = wh, group * wh, group * H, M / last row radix
   unsigned long long magic_T;  // floor(2^64 / T) + 1, T = threads of the emulated ATen launch (Philox input)
@@ -722,6 +723,88 @@ __device__ __forceinline__ void dispatch_stage(int R, StageArgs& a) {
   }
 }
 
+// ---- c2r fold fused into the first row stage -------------------------------------------------------------------
+// The fold turns the pair (A[k], A[M-k]) into (B[k], B[M-k]) (see pair_pass). The first DIF row stage (block length M,
+// m = M / R) gives butterfly j the slots j + t m: their mirrors M - j - t m = (m - j) + (R - 1 - t) m are the slots of
+// butterfly m - j. One item therefore takes BOTH butterflies j and m - j (2R values), folds them in registers and
+// runs the two radix-R butterflies: the fold's own trip through shared memory (a load and a store per element, its
+// index arithmetic and its barrier) disappears. j = 0 (mirror: itself plus the Nyquist slot M) and j = m / 2 (its own
+// mirror) are single-butterfly items. Needs m even and R <= 8 (2R complex values in registers).
+__device__ __forceinline__ void fold_pair(float2& ak, float2& am, const float2 w) {
+  const float2 s = make_float2(ak.x + am.x, ak.y - am.y);
+  const float2 d = make_float2(ak.x - am.x, ak.y + am.y);
+  const float2 wd = cmul(d, w);
+  ak = make_float2(s.x - wd.y, s.y + wd.x);
+  am = make_float2(s.x + wd.y, wd.x - s.y);
+}
+
+// DIF butterfly of slots p[0], p[estep], ...: butterfly, twiddle the outputs, store (digit reversal by the addresses)
+template <int R>
+__device__ __forceinline__ void dif_finish(float2* p, float2 (&v)[R], int tstep, int estep, const float2* __restrict__ tw) {
+  dft_inverse<R>(v);
+#pragma unroll
+  for (int s = 0; s < R; ++s)
+    if (dft_out_index<R>(s) != 0) v[s] = cmul_conj(v[s], tw[dft_out_index<R>(s) * tstep]);
+#pragma unroll
+  for (int s = 0; s < R; ++s) p[dft_out_index<R>(s) * estep] = v[s];
+}
+
+template <int R>
+__device__ __forceinline__ void run_stage_fold(StageArgs& a, const float2* __restrict__ tw_w) {
+  const int m = a.m, M = a.M, half = m >> 1;
+  const int total = (half + 1) * a.nbatch;
+  for (int w = threadIdx.x; w < total; w += blockDim.x) {
+    const int jj = (int)__umulhi((unsigned)w, a.magic_batch);
+    const int b = w - jj * a.nbatch;
+    float2* row = a.buf + b * a.pitch;
+    if (jj == 0 || jj == half) {
+      float2 v[R];
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = row[jj + t * m];
+      if (jj == 0) {
+        const float x0 = v[0].x, xm = row[M].x;  // the fold drops the imaginary parts of the DC and Nyquist bins
+        v[0] = make_float2(x0 + xm, x0 - xm);
+#pragma unroll
+        for (int t = 1; 2 * t < R; ++t) fold_pair(v[t], v[R - t], tw_w[t * m]);
+        if ((R & 1) == 0) {  // k = M / 2 pairs with itself
+          float2 twin = v[R / 2];
+          fold_pair(v[R / 2], twin, tw_w[(R / 2) * m]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; 2 * t < R - 1; ++t) fold_pair(v[t], v[R - 1 - t], tw_w[jj + t * m]);
+        if (R & 1) {
+          float2 twin = v[(R - 1) / 2];
+          fold_pair(v[(R - 1) / 2], twin, tw_w[jj + ((R - 1) / 2) * m]);
+        }
+      }
+      dif_finish<R>(row + jj, v, jj, m, a.tw);
+    } else {
+      const int j2 = m - jj;
+      float2 va[R], vb[R];
+#pragma unroll
+      for (int t = 0; t < R; ++t) {
+        va[t] = row[jj + t * m];
+        vb[t] = row[j2 + t * m];
+      }
+#pragma unroll
+      for (int t = 0; t < R; ++t) fold_pair(va[t], vb[R - 1 - t], tw_w[jj + t * m]);
+      dif_finish<R>(row + jj, va, jj, m, a.tw);
+      dif_finish<R>(row + j2, vb, j2, m, a.tw);
+    }
+  }
+}
+
+__device__ __forceinline__ void dispatch_stage_fold(int R, StageArgs& a, const float2* __restrict__ tw_w) {
+  switch (R) {  // block-uniform
+    case 8: run_stage_fold<8>(a, tw_w); break;
+    case 5: run_stage_fold<5>(a, tw_w); break;
+    case 4: run_stage_fold<4>(a, tw_w); break;
+    case 3: run_stage_fold<3>(a, tw_w); break;
+    default: run_stage_fold<2>(a, tw_w); break;
+  }
+}
+
 // Inverse-sign transform of one axis by decimation in time, stages last..first: the block-length-R stage
 // reads FIRST_SOURCE (which supplies index k at slot pos[k]), the result is in natural order.
 template <int FIRST_SOURCE, bool COLS>
@@ -741,9 +824,9 @@ __device__ __forceinline__ void run_axis_dit(const AxisPlan& plan, StageArgs& a,
 // Inverse-sign transform of one axis by decimation in frequency, stages first..last: natural order in,
 // index k ends at slot pos[k] -- or, with LAST_SINK = SINK_GLOBAL, in natural order in the global plane.
 template <int LAST_SINK, bool COLS>
-__device__ __forceinline__ void run_axis_dif(const AxisPlan& plan, StageArgs& a, const ushort2* tab) {
+__device__ __forceinline__ void run_axis_dif(const AxisPlan& plan, StageArgs& a, const ushort2* tab, int first = 0) {
   const int last = plan.n_stages - 1;
-  for (int f = 0; f <= last; ++f) {
+  for (int f = first; f <= last; ++f) {
     a.nb = plan.nb[f];
     a.m = plan.m[f];
     a.tab = tab + plan.tab_off[f];
@@ -911,13 +994,21 @@ __device__ __forceinline__ void spectral_batched_body(const SpectralBatchedLaunc
     }
     // c2r fold, then inverse rows of length M; the last stage scales and stores x[y][2n], x[y][2n+1] =
     // z[y][n] to the global plane (its trailing barrier also protects the buffer from the next group)
-    pair_pass<false>(buf, rows_total, magic_rows, M, P, tw_w);
-    __syncthreads();
     a.out_rows = reinterpret_cast<float2*>(p.out + plane0 * (int64_t)H * W);
     a.tw = tw_m;
     a.nbatch = rows_total;
     a.magic_batch = magic_rows;
-    run_axis_dif<SINK_GLOBAL, false>(L.row, a, tab_row);
+    if (L.fuse_fold) {
+      a.nb = L.row.nb[0];
+      a.m = L.row.m[0];
+      dispatch_stage_fold(L.row.radix[0], a, tw_w);
+      __syncthreads();
+      run_axis_dif<SINK_GLOBAL, false>(L.row, a, tab_row, 1);
+    } else {
+      pair_pass<false>(buf, rows_total, magic_rows, M, P, tw_w);
+      __syncthreads();
+      run_axis_dif<SINK_GLOBAL, false>(L.row, a, tab_row);
+    }
     if (p.sums != nullptr) {
       const float ws = warp_sum(a.ms), wss = warp_sum(a.mss);
       if ((threadIdx.x & 31) == 0) {
@@ -1026,6 +1117,13 @@ static bool plan_spectral_batched(const SonarSpectralParams& p, SpectralBatchedL
   if (group < 1) group = 1;
   while (group > 1 && p.sums_segment_planes > 0 && p.sums_segment_planes % group != 0) --group;  // no group straddles a segment
   L.group = (int)group;
+  // the fold rides on the first row stage when that stage is not the last one, pairs up (m even) and is narrow
+  // enough for two butterflies in registers (SONAR_B200_FFT_FUSE_FOLD=0: the separate pass)
+  static const bool fuse_enabled = [] {
+    const char* e = getenv("SONAR_B200_FFT_FUSE_FOLD");
+    return e == nullptr || e[0] != '0';
+  }();
+  L.fuse_fold = fuse_enabled && L.row.n_stages >= 2 && L.row.radix[0] <= 8 && (L.row.m[0] & 1) == 0 ? 1 : 0;
   L.magic_T = 0;
   if (p.philox_grid_blocks != 0)
     L.magic_T = ~0ull / ((unsigned long long)p.philox_grid_blocks * kBlock) + 1ull;  // floor(2^64 / T) + 1 (T is no power of two > 2^63)

@@ -46,13 +46,15 @@ PIPELINE_FFT_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_FFT_CTAS", "3"))  # 
 # The step launch is made in two parts: the first PIPELINE_STEP_SPLIT of the elements beside the Philox fill (4 + 4
 # CTAs per SM), the rest beside the FFT (3 x 256 threads x 64 registers) with the 2 step CTAs per SM the register file
 # still holds. tools/sweep_pipeline.sh on B200, interval between model calls at 8 video latents: 466 us unsplit;
-# 417 / 411 / 408 / 405 / 415 us at split 0.5 / 0.55 / 0.6 / 0.65 / 0.7 (a late second part stalls the next interval).
-PIPELINE_STEP_SPLIT = float(os.environ.get("SONAR_B200_PIPELINE_STEP_SPLIT", "0.6"))
+# 406 / 405 / 413 / 420 us at split 0.65 / 0.7 / 0.75 / 0.8 (with the c2r fold fused into the FFT's first row stage; before
+# that 417 / 411 / 408 / 405 / 415 us at 0.5 / 0.55 / 0.6 / 0.65 / 0.7). At ~405 us the interval moves its 2.2 GB of actual
+# DRAM traffic at 5.4 TB/s (0.84 of the measured peak): a faster FFT alone no longer shortens it.
+PIPELINE_STEP_SPLIT = float(os.environ.get("SONAR_B200_PIPELINE_STEP_SPLIT", "0.7"))
 PIPELINE_STEP_B_CTAS = int(os.environ.get("SONAR_B200_PIPELINE_STEP_B_CTAS", "2"))
 # Below this many elements per sample the batched schedule wins: a one-sample producer launch is far from the throughput
 # of a batch of 9-18 (tail of the persistent FFT grid), and a 30 us step hides little of it. Measured on B200 with the
 # C5 job (tools/sweep_pipeline.sh, profiles/r02b_noise_pipeline_sweeps.txt): 1 video latent per GPU 1.27 ms batched vs
-# 1.57 ms pipelined, 2 / 4 / 8 latents 2.53 / 5.04 / 9.93 ms batched vs 2.38 / 4.02 / 7.71 ms pipelined.
+# 1.57 ms pipelined, 2 / 4 / 8 latents 2.53 / 5.04 / 9.93 ms batched vs 2.21 / 3.97 / 7.65 ms pipelined.
 PIPELINE_MIN_NUMEL = int(os.environ.get("SONAR_B200_PIPELINE_MIN_NUMEL", str(12_000_000)))
 # Batch-sharded runs exchange the statistics of every pipelined sample separately (18 exchanges per C5 run instead of
 # 1-2 per look-ahead batch), each of which also absorbs the skew between the ranks: on 4 GPUs x 2 latents the pipelined
