@@ -125,7 +125,9 @@ def test_spectral_kernel_vs_torch_fft(sb, cuda, hw):
 
 @pytest.mark.parametrize(
     ("hw", "planes"),
-    [((32, 32), 301), ((16, 16), 700), ((18, 20), 5), ((160, 90), 3), ((48, 96), 7), ((100, 200), 2), ((64, 64), 149), ((8, 4), 33)],
+    [((32, 32), 301), ((16, 16), 700), ((18, 20), 5), ((160, 90), 3), ((48, 96), 7), ((100, 200), 2), ((64, 64), 149), ((8, 4), 33),
+     # the c2r fold fused into the first row stage: first row radix 3 / 5 / 3 / 5 / 3 (three stages) / 4, m even
+     ((24, 24), 200), ((30, 80), 9), ((50, 48), 4), ((20, 100), 6), ((12, 192), 5), ((16, 64), 40)],
 )
 def test_spectral_batched_groups_and_radices(sb, cuda, hw, planes):
     """Plane groups (several small planes per CTA, ragged last group) and every radix of the batched kernel
