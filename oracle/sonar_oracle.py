@@ -10,8 +10,9 @@ against outputs of the reference itself, imported in the build container with re
 directly against /root/reference when that tree is present). Exception -- the 2-D wavelet
 transform: the reference delegates it to pytorch_wavelets, which is absent from the reference tree
 and from this image (no pinned version), so `dwt2_forward` / `dwt2_inverse` restate that library's
-published algorithm and their parity is UNPINNED (anchored only on perfect reconstruction,
-orthonormality and the equal-scales identity). The same holds for the "periodization" mode used by the
+published algorithm and their parity is UNPINNED (anchored on perfect reconstruction, orthonormality,
+the equal-scales identity and the library-free known answers of tests/test_oracle_wavelet_known_answers.py:
+closed-form and published filter values, PyWavelets' documentation examples, hand-derived band order and signs). The same holds for the "periodization" mode used by the
 wavelet-filtered noise type (`_afb1d_per` / `_sfb1d_per`: perfect reconstruction incl. odd sizes, Parseval,
 the haar block transform). FreeU-Extreme (`freeu_*`) IS pinned: tests/golden/freeu.pt.
 
