@@ -106,7 +106,19 @@ class PeerExchange:
             self.local = None
 
 
-_PEERS: dict = {}
+_PEERS: list = []  # [(process group object, world size, rank, PeerExchange | None)]
+
+
+def _group_object(group):
+    """The process-group OBJECT a `group` argument stands for (None = the default group). The cache below holds it
+    strongly and compares by identity: a group that was destroyed and re-created is a different object (an id() key could
+    be reused by the new one and hand out mailboxes mapped for ranks that no longer exist)."""
+    if group is not None or not dist.is_initialized():
+        return group
+    try:
+        return dist.distributed_c10d._get_default_group()  # noqa: SLF001
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def peer_exchange(rank: int, world_size: int, group=None) -> PeerExchange | None:
@@ -114,9 +126,11 @@ def peer_exchange(rank: int, world_size: int, group=None) -> PeerExchange | None
     ranks cannot share memory (no NCCL / CUDA, or SONAR_B200_NO_PEER set)."""
     import os
 
-    key = (id(group), dist.get_world_size(group) if dist.is_initialized() else world_size, rank)
-    if key in _PEERS:
-        return _PEERS[key]
+    pg = _group_object(group)
+    world = dist.get_world_size(group) if dist.is_initialized() else world_size
+    for entry in _PEERS:
+        if entry[0] is pg and entry[1] == world and entry[2] == rank:
+            return entry[3]
     ok = (
         world_size > 1
         and dist.is_initialized()
@@ -124,8 +138,14 @@ def peer_exchange(rank: int, world_size: int, group=None) -> PeerExchange | None
         and dist.get_backend(group) == "nccl"
         and os.environ.get("SONAR_B200_NO_PEER") is None
     )
-    _PEERS[key] = PeerExchange(rank, world_size, group) if ok else None
-    return _PEERS[key]
+    if len(_PEERS) > 8:  # groups that went away: release their mailboxes
+        for old in _PEERS[:-8]:
+            if old[3] is not None:
+                old[3].close()
+        del _PEERS[:-8]
+    exchange = PeerExchange(rank, world_size, group) if ok else None
+    _PEERS.append((pg, world, rank, exchange))
+    return exchange
 
 
 @dataclass

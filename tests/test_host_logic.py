@@ -279,3 +279,21 @@ def test_channel_mixer_is_memoised_and_identity_stays_on_the_host():
     assert ident.is_identity and torch.equal(ident.mixer, torch.eye(528))
     moved = ident.to("meta")  # would fail loudly if the identity were copied anywhere
     assert moved.mixer.device.type == "cpu"
+
+
+def test_peer_exchange_cache_is_keyed_on_the_group_object(monkeypatch):
+    """A process group that was destroyed and re-created must not be handed the mailboxes of the old one: the cache
+    compares the group OBJECT (held strongly), not its id()."""
+    par = importlib.import_module("sonar_b200.parallel")
+    monkeypatch.setattr(par, "_PEERS", [])
+
+    class FakeGroup:
+        pass
+
+    a, b = FakeGroup(), FakeGroup()
+    monkeypatch.setattr(par.dist, "is_initialized", lambda: False)  # no NCCL here: entries are None, the keying is what counts
+    assert par.peer_exchange(0, 2, a) is None and len(par._PEERS) == 1  # noqa: SLF001
+    assert par.peer_exchange(0, 2, a) is None and len(par._PEERS) == 1  # noqa: SLF001  (hit)
+    assert par.peer_exchange(0, 2, b) is None and len(par._PEERS) == 2  # noqa: SLF001  (another object: miss)
+    assert par._PEERS[0][0] is a and par._PEERS[1][0] is b  # noqa: SLF001
+    assert par.peer_exchange(1, 2, a) is None and len(par._PEERS) == 3  # noqa: SLF001  (another rank)
