@@ -214,3 +214,82 @@ def test_plan_declines_what_the_generic_kernel_handles(sb):
     assert _plan(sb, 32, 32, planes=4).group == 1, "few planes: one per CTA so more SMs work"
     big = _plan(sb, 90, 160, planes=528, real=True)
     assert big.ctas_per_sm == 3 and big.threads == 320 and big.grid == 444
+
+
+# ---------------------------------------------------------------------------------------------
+# the c2r fold fused into the first row stage (csrc/spectral.cu run_stage_fold)
+# ---------------------------------------------------------------------------------------------
+def _fold_pair(ak, am, wk):
+    s, d = ak + np.conj(am), ak - np.conj(am)
+    wd = wk * d
+    return s + 1j * wd, np.conj(s) + 1j * np.conj(wd)
+
+
+def _fused_fold_first_stage(buf, m_len, w, radices):
+    """buf: (h, m_len + 1) rows in natural order, Nyquist at slot m_len. Runs the fold and the first DIF row stage
+    the way the kernel's items do: butterfly j of that stage owns slots j + t m, whose mirrors are the slots of
+    butterfly m - j; one item folds both in 'registers' and runs the two butterflies. In place on buf[:, :m_len]."""
+    r = radices[0]
+    m = m_len // r
+    assert m % 2 == 0 and len(radices) >= 2
+    tw_w = np.exp(2j * np.pi * np.arange(m_len) / w)
+    t = np.arange(r)
+    dft = np.exp(2j * np.pi * np.outer(t, t) / r)
+
+    def finish(row, j, v):
+        v = dft @ v
+        v = v * np.exp(2j * np.pi * j * t / m_len)  # DIF: twiddle the outputs (block length = the whole row)
+        row[j + t * m] = v
+
+    for row in buf:
+        for jj in range(m // 2 + 1):
+            if jj in (0, m // 2):
+                v = row[jj + t * m].copy()
+                if jj == 0:
+                    x0, xm = row[0].real, row[m_len].real
+                    v[0] = (x0 + xm) + 1j * (x0 - xm)
+                    for tt in range(1, r):
+                        if 2 * tt < r:
+                            v[tt], v[r - tt] = _fold_pair(v[tt], v[r - tt], tw_w[tt * m])
+                    if r % 2 == 0:
+                        v[r // 2] = _fold_pair(v[r // 2], v[r // 2], tw_w[(r // 2) * m])[0]
+                else:
+                    for tt in range(r):
+                        if 2 * tt < r - 1:
+                            v[tt], v[r - 1 - tt] = _fold_pair(v[tt], v[r - 1 - tt], tw_w[jj + tt * m])
+                    if r % 2 == 1:
+                        mid = (r - 1) // 2
+                        v[mid] = _fold_pair(v[mid], v[mid], tw_w[jj + mid * m])[0]
+                finish(row, jj, v)
+            else:
+                j2 = m - jj
+                va, vb = row[jj + t * m].copy(), row[j2 + t * m].copy()
+                for tt in range(r):
+                    va[tt], vb[r - 1 - tt] = _fold_pair(va[tt], vb[r - 1 - tt], tw_w[jj + tt * m])
+                finish(row, jj, va)
+                finish(row, j2, vb)
+
+
+def test_fused_fold_equals_fold_pass_then_first_row_stage(sb):
+    """For every plannable width whose row plan lets the fold ride on the first row stage (two stages or more, first
+    radix <= 8, m even) the fused items compute exactly what pair_pass followed by that stage computes."""
+    rng = np.random.default_rng(11)
+    fused = 0
+    for n in range(4, 257):
+        info = _plan(sb, 4, 2 * n)
+        if not info.batched:
+            continue
+        _, radices = _radices(info)
+        if len(radices) < 2 or radices[0] > 8 or (n // radices[0]) % 2:
+            continue
+        fused += 1
+        h, w = 3, 2 * n
+        a = rng.standard_normal((h, n + 1)) + 1j * rng.standard_normal((h, n + 1))
+        want = a.copy()
+        _pair_pass(want, n, w, unfold=False)
+        rows = np.ascontiguousarray(want[:, :n].T)
+        _stage(rows, n, radices, 0, dit=False)
+        got = a.copy()
+        _fused_fold_first_stage(got, n, w, radices)
+        np.testing.assert_allclose(got[:, :n], rows.T, rtol=1e-12, atol=1e-12, err_msg=f"row length {n}, radices {radices}")
+    assert fused >= 15, fused  # e.g. 12, 24, 32, 40, 48, 64, 80 (the C5 width), 96, 128, ...
