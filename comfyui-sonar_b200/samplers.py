@@ -391,7 +391,7 @@ class SonarBase:
                     ops.launch_step(self._params_ref, x.device.index)
             finally:
                 ops.set_grid_limit(0)
-            torch.cuda.current_stream().wait_event(join)
+            torch.cuda.current_stream(x.device).wait_event(join)  # (the stream of x's device: the one the step was launched on)
         del keep
         if hist_out is not None:
             self.history_d = hist_out
@@ -617,7 +617,7 @@ class SonarBase:
         if not queue and pending is not None:
             batch, ready = pending
             self._noise_pending = None
-            torch.cuda.current_stream().wait_event(ready)  # (already joined after the previous step launch)
+            torch.cuda.current_stream(x.device).wait_event(ready)  # (already joined after the previous step launch)
             queue = self._noise_queue = batch
         if queue and (queue[0][2].offset != gen.get_offset() or queue[0][2].seed != gen.initial_seed() or queue[0][0].shape != x.shape):
             queue.clear()
@@ -630,7 +630,7 @@ class SonarBase:
                 if made is None:
                     return None
                 batch, ready = made
-                torch.cuda.current_stream().wait_event(ready)
+                torch.cuda.current_stream(x.device).wait_event(ready)
             else:
                 batch = make(self.noise_draws_left)
                 if batch is None:
@@ -650,7 +650,7 @@ class SonarBase:
         overlapped: the consumer launches its step kernel next, to run beside the producers (`_noise_join`)."""
         idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
         side = _producer_stream(idx)
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(idx)
         slot = getattr(self, "_noise_slot", 0)
         # the buffer about to be overwritten was last read by a step kernel already enqueued on the consumer stream
         side.wait_stream(main)
