@@ -323,7 +323,7 @@ class PowerNoiseItem(CustomNoiseItemBase):
                 output buffer `slot` (0 / 1) of the slab, so that the consumer can read one buffer on its stream while
                 the next samples are written into the other one on a second stream. grid_limits = (fill, fft): CTAs per
                 SM the two producer launches may occupy (sonar_set_grid_limit; 0 = no limit)."""
-                if rng._INJECT is not None or rng._PENDING is not None:  # noqa: SLF001
+                if rng._INJECT is not None or rng._PENDING is not None or LOOKAHEAD_BYTES <= 0:  # noqa: SLF001
                     return None
                 numel = math.prod(shape)
                 if chunk is None:
